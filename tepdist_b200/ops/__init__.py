@@ -1,0 +1,375 @@
+"""Device-op layer: hand-written sm_100a kernels behind a C ABI (``libtepdist_kernels.so``), loaded with
+ctypes.  On CUDA tensors every op here runs OUR kernel and raises if the library is missing (no silent
+eager fallback); CPU tensors take a plain-PyTorch reference path that the tests also use as the oracle.
+
+Launch accounting: ``launch_count()`` returns how many of our kernels were launched (bench.py reports it
+as ``gpu_launches``).
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+from typing import Optional
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB_PATH = os.path.join(_HERE, "libtepdist_kernels.so")
+_lib: Optional[ctypes.CDLL] = None
+_launches = 0
+_num_sms: Optional[int] = None
+
+
+class KernelLibraryMissing(RuntimeError):
+    pass
+
+
+def lib() -> ctypes.CDLL:
+    global _lib
+    if _lib is None:
+        if not os.path.exists(_LIB_PATH):
+            raise KernelLibraryMissing(
+                f"{_LIB_PATH} not built; run `python -m tepdist_b200.build_native` (nvcc, sm_100a)")
+        _lib = ctypes.CDLL(_LIB_PATH)
+        for name in dir(_Sig):
+            if name.startswith("tepd_"):
+                try:
+                    fn = getattr(_lib, name)
+                except AttributeError:  # symbol not in this build
+                    continue
+                fn.restype = ctypes.c_int
+                fn.argtypes = getattr(_Sig, name)
+    return _lib
+
+
+def available() -> bool:
+    return os.path.exists(_LIB_PATH)
+
+
+def launch_count() -> int:
+    return _launches
+
+
+def reset_launch_count() -> None:
+    global _launches
+    _launches = 0
+
+
+def _count(n: int = 1) -> None:
+    global _launches
+    _launches += n
+
+
+_vp, _i, _ll, _f = ctypes.c_void_p, ctypes.c_int, ctypes.c_longlong, ctypes.c_float
+
+
+class _Sig:
+    tepd_gemm_bf16 = [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _ll, _ll, _ll, _ll, _ll, _ll, _ll, _ll,
+                      _i, _i, _i, _i, _i, _i, _f, _i, _i, _i, _vp]
+    tepd_layernorm_fwd = [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _f, _vp]
+    tepd_layernorm_bwd = [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _vp]
+    tepd_gelu_fwd = [_vp, _vp, _ll, _vp]
+    tepd_gelu_bwd = [_vp, _vp, _vp, _ll, _vp]
+    tepd_colsum = [_vp, _vp, _i, _i, _vp]
+    tepd_embedding_fwd = [_vp, _vp, _vp, _vp, _i, _i, _i, _vp]
+    tepd_embedding_bwd = [_vp, _vp, _vp, _vp, _i, _i, _i, _vp]
+    tepd_xent_fwd_bwd = [_vp, _vp, _vp, _vp, _i, _i, _i, _f, _vp]
+    tepd_adamw = [_vp, _vp, _vp, _vp, _vp, _ll, _ll, _f, _f, _f, _f, _f, _f, _f, _f, _vp]
+    tepd_sgd = [_vp, _vp, _vp, _ll, _f, _f, _vp]
+    tepd_axpy_f32 = [_vp, _vp, _ll, _f, _vp]
+    tepd_cast_f32_bf16 = [_vp, _vp, _ll, _vp]
+    tepd_attn_fwd = [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _f, _i, _ll, _ll, _ll, _vp]
+    tepd_attn_bwd = [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _f, _i,
+                     _ll, _ll, _ll, _ll, _ll, _ll, _vp]
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _sms() -> int:
+    global _num_sms
+    if _num_sms is None:
+        _num_sms = torch.cuda.get_device_properties(torch.cuda.current_device()).multi_processor_count
+    return _num_sms
+
+
+def _check(rc: int, what: str) -> None:
+    if rc != 0:
+        raise RuntimeError(f"tepdist_b200 kernel '{what}' failed with code {rc}")
+
+
+def _p(t: Optional[torch.Tensor]) -> Optional[int]:
+    return None if t is None else t.data_ptr()
+
+
+# --------------------------------------------------------------------------------------------- GEMM
+def gemm(a: torch.Tensor, b: torch.Tensor, *, a_mn: bool = False, b_mn: bool = False,
+         bias: Optional[torch.Tensor] = None, residual: Optional[torch.Tensor] = None,
+         act: Optional[str] = None, out: Optional[torch.Tensor] = None,
+         out_dtype: torch.dtype = torch.bfloat16, accumulate: bool = False, alpha: float = 1.0,
+         split_k: int = 0, block_n: int = 0) -> torch.Tensor:
+    """D = act(alpha * A @ B + bias) + residual with A:(M,K), B:(K,N) as *logical* shapes.
+
+    Storage: ``a`` is [.., M, K] (a_mn=False) or [.., K, M] (a_mn=True); ``b`` is [.., N, K]
+    (b_mn=False, i.e. nn.Linear weight layout) or [.., K, N] (b_mn=True).  Optional leading batch dim.
+    ``accumulate`` adds into an fp32 ``out`` (gradient accumulation / split-K reduction target).
+    """
+    assert a.dim() == b.dim() and a.dim() in (2, 3)
+    batched = a.dim() == 3
+    if not batched:
+        a3, b3 = a.unsqueeze(0), b.unsqueeze(0)
+    else:
+        a3, b3 = a, b
+    batch = a3.shape[0]
+    M, K = (a3.shape[2], a3.shape[1]) if a_mn else (a3.shape[1], a3.shape[2])
+    N, Kb = (b3.shape[2], b3.shape[1]) if b_mn else (b3.shape[1], b3.shape[2])
+    assert K == Kb, f"contraction mismatch {K} vs {Kb}"
+    if out is None:
+        shape = (batch, M, N) if batched else (M, N)
+        out = torch.empty(shape, dtype=out_dtype, device=a.device)
+        assert not accumulate
+    out3 = out.unsqueeze(0) if out.dim() == 2 else out
+
+    if not a.is_cuda:  # reference path (CPU tests / oracle)
+        A = a3.float().transpose(1, 2) if a_mn else a3.float()
+        B = b3.float() if b_mn else b3.float().transpose(1, 2)
+        d = alpha * torch.matmul(A, B)
+        if bias is not None:
+            d = d + bias.float()
+        if act == "gelu":
+            d = torch.nn.functional.gelu(d, approximate="tanh")
+        if residual is not None:
+            d = d + residual.float().reshape(d.shape)
+        if accumulate:
+            out3.add_(d.to(out.dtype))
+        else:
+            out3.copy_(d.to(out.dtype))
+        return out
+
+    assert a.dtype == torch.bfloat16 and b.dtype == torch.bfloat16
+    assert a3.stride(2) == 1 and b3.stride(2) == 1 and out3.stride(2) == 1
+    if bias is not None:
+        assert bias.dtype in (torch.float32, torch.bfloat16) and bias.is_contiguous()
+    res3 = None
+    if residual is not None:
+        res3 = residual.reshape(out3.shape)
+        assert res3.dtype == torch.bfloat16 and res3.stride(2) == 1
+    if split_k == 0:
+        split_k = 1
+        if accumulate and out.dtype == torch.float32:
+            tiles = ((M + 127) // 128) * ((N + 255) // 256) * batch
+            kb = (K + 63) // 64
+            while tiles * split_k * 2 <= _sms() and split_k * 2 <= max(1, kb // 4):
+                split_k *= 2
+    rc = lib().tepd_gemm_bf16(
+        a3.data_ptr(), b3.data_ptr(), out3.data_ptr(), _p(bias), _p(res3),
+        M, N, K, batch, a3.stride(1), b3.stride(1), out3.stride(1),
+        a3.stride(0), b3.stride(0), out3.stride(0),
+        res3.stride(1) if res3 is not None else 0, res3.stride(0) if res3 is not None else 0,
+        int(a_mn), int(b_mn), int(out.dtype == torch.float32), int(accumulate),
+        1 if act == "gelu" else 0, int(bias is not None and bias.dtype == torch.bfloat16),
+        float(alpha), int(split_k), int(block_n), _sms(), _stream())
+    _check(rc, "gemm_bf16")
+    _count()
+    return out
+
+
+# --------------------------------------------------------------------------------------------- LayerNorm
+def layernorm_fwd(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, eps: float = 1e-5):
+    C = x.shape[-1]
+    rows = x.numel() // C
+    if not x.is_cuda:
+        xf = x.float()
+        mean = xf.mean(-1)
+        var = xf.var(-1, unbiased=False)
+        rstd = torch.rsqrt(var + eps)
+        y = ((xf - mean.unsqueeze(-1)) * rstd.unsqueeze(-1) * gamma.float() + beta.float()).to(x.dtype)
+        return y, mean.reshape(rows), rstd.reshape(rows)
+    assert x.dtype == torch.bfloat16 and x.is_contiguous() and gamma.dtype == torch.float32
+    y = torch.empty_like(x)
+    mean = torch.empty(rows, dtype=torch.float32, device=x.device)
+    rstd = torch.empty(rows, dtype=torch.float32, device=x.device)
+    _check(lib().tepd_layernorm_fwd(x.data_ptr(), gamma.data_ptr(), beta.data_ptr(), y.data_ptr(),
+                                    mean.data_ptr(), rstd.data_ptr(), rows, C, eps, _stream()), "layernorm_fwd")
+    _count()
+    return y, mean, rstd
+
+
+def layernorm_bwd(dy, x, gamma, mean, rstd, dgamma_acc: torch.Tensor, dbeta_acc: torch.Tensor):
+    """Returns dx; accumulates dgamma/dbeta into the given fp32 buffers."""
+    C = x.shape[-1]
+    rows = x.numel() // C
+    if not x.is_cuda:
+        xf, dyf = x.float().reshape(rows, C), dy.float().reshape(rows, C)
+        xh = (xf - mean.unsqueeze(-1)) * rstd.unsqueeze(-1)
+        g = dyf * gamma.float()
+        dx = rstd.unsqueeze(-1) * (g - g.mean(-1, keepdim=True) - xh * (g * xh).mean(-1, keepdim=True))
+        dgamma_acc.add_((dyf * xh).sum(0))
+        dbeta_acc.add_(dyf.sum(0))
+        return dx.to(x.dtype).reshape(x.shape)
+    dy = dy.contiguous()
+    dx = torch.empty_like(x)
+    _check(lib().tepd_layernorm_bwd(dy.data_ptr(), x.data_ptr(), gamma.data_ptr(), mean.data_ptr(), rstd.data_ptr(),
+                                    dx.data_ptr(), dgamma_acc.data_ptr(), dbeta_acc.data_ptr(), rows, C, _stream()),
+           "layernorm_bwd")
+    _count()
+    return dx
+
+
+# --------------------------------------------------------------------------------------------- GELU / colsum
+def gelu_fwd(x: torch.Tensor) -> torch.Tensor:
+    if not x.is_cuda:
+        return torch.nn.functional.gelu(x.float(), approximate="tanh").to(x.dtype)
+    assert x.is_contiguous() and x.dtype == torch.bfloat16
+    y = torch.empty_like(x)
+    _check(lib().tepd_gelu_fwd(x.data_ptr(), y.data_ptr(), x.numel(), _stream()), "gelu_fwd")
+    _count()
+    return y
+
+
+def gelu_bwd(dy: torch.Tensor, x: torch.Tensor) -> torch.Tensor:
+    if not x.is_cuda:
+        xf = x.float().detach().requires_grad_(True)
+        with torch.enable_grad():
+            y = torch.nn.functional.gelu(xf, approximate="tanh")
+        (g,) = torch.autograd.grad(y, xf, dy.float())
+        return g.to(x.dtype)
+    dy = dy.contiguous()
+    dx = torch.empty_like(x)
+    _check(lib().tepd_gelu_bwd(dy.data_ptr(), x.data_ptr(), dx.data_ptr(), x.numel(), _stream()), "gelu_bwd")
+    _count()
+    return dx
+
+
+def colsum_acc(x: torch.Tensor, out_acc: torch.Tensor) -> None:
+    """out_acc[c] += sum_r x[r, c] (bias gradients, fp32 accumulate)."""
+    C = x.shape[-1]
+    rows = x.numel() // C
+    if not x.is_cuda:
+        out_acc.add_(x.float().reshape(rows, C).sum(0))
+        return
+    x = x.contiguous()
+    _check(lib().tepd_colsum(x.data_ptr(), out_acc.data_ptr(), rows, C, _stream()), "colsum")
+    _count()
+
+
+# --------------------------------------------------------------------------------------------- embedding
+def embedding_fwd(tokens: torch.Tensor, wte: torch.Tensor, wpe: torch.Tensor) -> torch.Tensor:
+    B, S = tokens.shape
+    C = wte.shape[1]
+    if not tokens.is_cuda:
+        pos = torch.arange(S, device=tokens.device)
+        return (wte[tokens.long()].float() + wpe[pos].float()).to(wte.dtype)
+    out = torch.empty(B, S, C, dtype=wte.dtype, device=wte.device)
+    tok = tokens.to(torch.int32).contiguous()
+    _check(lib().tepd_embedding_fwd(tok.data_ptr(), wte.data_ptr(), wpe.data_ptr(), out.data_ptr(), B * S, S, C,
+                                    _stream()), "embedding_fwd")
+    _count()
+    return out
+
+
+def embedding_bwd(tokens: torch.Tensor, dout: torch.Tensor, dwte_acc: torch.Tensor, dwpe_acc: torch.Tensor) -> None:
+    B, S = tokens.shape
+    C = dout.shape[-1]
+    if not tokens.is_cuda:
+        d = dout.float().reshape(B * S, C)
+        dwte_acc.index_add_(0, tokens.reshape(-1).long(), d)
+        dwpe_acc[:S].add_(dout.float().reshape(B, S, C).sum(0))
+        return
+    tok = tokens.to(torch.int32).contiguous()
+    dout = dout.contiguous()
+    _check(lib().tepd_embedding_bwd(tok.data_ptr(), dout.data_ptr(), dwte_acc.data_ptr(), dwpe_acc.data_ptr(), B * S, S,
+                                    C, _stream()), "embedding_bwd")
+    _count()
+
+
+# --------------------------------------------------------------------------------------------- loss
+def xent_fwd_bwd(logits: torch.Tensor, labels: torch.Tensor, vocab: int, grad_scale: float):
+    """Fused softmax-cross-entropy.  ``logits`` [T, Vp] is overwritten with d(loss)/d(logits)*grad_scale
+    (columns >= vocab get zero).  Returns (sum(loss)*grad_scale as 1-elem fp32 tensor, per-row loss)."""
+    T, Vp = logits.shape
+    if not logits.is_cuda:
+        lf = logits.float()[:, :vocab]
+        lse = torch.logsumexp(lf, -1)
+        rows = lse - lf.gather(1, labels.long().unsqueeze(1)).squeeze(1)
+        p = torch.softmax(lf, -1)
+        p[torch.arange(T), labels.long()] -= 1.0
+        g = torch.zeros(T, Vp)
+        g[:, :vocab] = p * grad_scale
+        logits.copy_(g.to(logits.dtype))
+        return (rows.sum() * grad_scale).reshape(1), rows
+    assert logits.is_contiguous() and logits.dtype == torch.bfloat16
+    lab = labels.to(torch.int32).contiguous()
+    rows = torch.empty(T, dtype=torch.float32, device=logits.device)
+    total = torch.zeros(1, dtype=torch.float32, device=logits.device)
+    _check(lib().tepd_xent_fwd_bwd(logits.data_ptr(), lab.data_ptr(), rows.data_ptr(), total.data_ptr(), T, vocab, Vp,
+                                   grad_scale, _stream()), "xent_fwd_bwd")
+    _count()
+    return total, rows
+
+
+# --------------------------------------------------------------------------------------------- optimizer
+def adamw_step(p: torch.Tensor, g: torch.Tensor, m: torch.Tensor, v: torch.Tensor, p_bf16: Optional[torch.Tensor],
+               n_decay: int, lr: float, beta1: float, beta2: float, eps: float, wd: float, step: int,
+               grad_scale: float = 1.0) -> None:
+    """Fused AdamW over flat fp32 buffers (decay applies to the prefix [0, n_decay))."""
+    bc1 = 1.0 - beta1 ** step
+    bc2 = 1.0 - beta2 ** step
+    n = p.numel()
+    if not p.is_cuda:
+        gr = g * grad_scale
+        m.mul_(beta1).add_(gr, alpha=1 - beta1)
+        v.mul_(beta2).addcmul_(gr, gr, value=1 - beta2)
+        upd = (m / bc1) / ((v / bc2).sqrt() + eps)
+        decay = torch.zeros_like(p)
+        decay[:n_decay] = wd
+        p.sub_(lr * (upd + decay * p))
+        if p_bf16 is not None:
+            p_bf16.copy_(p.to(p_bf16.dtype))
+        return
+    assert p_bf16 is not None
+    _check(lib().tepd_adamw(p.data_ptr(), g.data_ptr(), m.data_ptr(), v.data_ptr(), p_bf16.data_ptr(), n, n_decay,
+                            lr, beta1, beta2, eps, wd, bc1, bc2, grad_scale, _stream()), "adamw")
+    _count()
+
+
+def sgd_step(p: torch.Tensor, g: torch.Tensor, p_bf16: Optional[torch.Tensor], lr: float, grad_scale: float = 1.0):
+    if not p.is_cuda:
+        p.sub_(lr * grad_scale * g)
+        if p_bf16 is not None:
+            p_bf16.copy_(p.to(p_bf16.dtype))
+        return
+    _check(lib().tepd_sgd(p.data_ptr(), g.data_ptr(), _p(p_bf16), p.numel(), lr, grad_scale, _stream()), "sgd")
+    _count()
+
+
+def axpy_f32(acc: torch.Tensor, g: torch.Tensor, a: float = 1.0) -> None:
+    if not acc.is_cuda:
+        acc.add_(g, alpha=a)
+        return
+    _check(lib().tepd_axpy_f32(acc.data_ptr(), g.data_ptr(), acc.numel(), a, _stream()), "axpy_f32")
+    _count()
+
+
+def cast_f32_bf16(src: torch.Tensor, dst: torch.Tensor) -> None:
+    if not src.is_cuda:
+        dst.copy_(src.to(dst.dtype))
+        return
+    _check(lib().tepd_cast_f32_bf16(src.data_ptr(), dst.data_ptr(), src.numel(), _stream()), "cast_f32_bf16")
+    _count()
+
+
+# --------------------------------------------------------------------------------------------- attention
+def attention_ref(q, k, v, scale: float, causal: bool = True):
+    """fp32 reference: q,k,v [B, H, S, D]."""
+    s = torch.matmul(q.float(), k.float().transpose(-1, -2)) * scale
+    if causal:
+        S = q.shape[-2]
+        mask = torch.ones(S, S, dtype=torch.bool, device=q.device).tril()
+        s = s.masked_fill(~mask, float("-inf"))
+    p = torch.softmax(s, -1)
+    return torch.matmul(p, v.float())
+
+
+from .attention import attention_fwd, attention_bwd  # noqa: E402,F401

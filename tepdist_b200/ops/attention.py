@@ -1,0 +1,81 @@
+"""Fused attention op wrappers (kernels in csrc/attention_sm100.cu).
+
+Tensors use the "bshd" convention: q/k/v are views [B, S, H, D] (arbitrary batch/seq/head strides, D
+contiguous) — typically slices of the fused qkv projection output [B, S, 3, H, D]; the output is a
+contiguous [B, S, H, D] tensor, i.e. already the [tokens, hidden] input of the output projection.
+"""
+from __future__ import annotations
+
+import math
+
+import torch
+
+
+def _ref_fwd(q, k, v, scale, causal):
+    # q,k,v: [B,S,H,D] -> fp32 math in [B,H,S,D]
+    qf, kf, vf = (t.float().permute(0, 2, 1, 3) for t in (q, k, v))
+    s = torch.matmul(qf, kf.transpose(-1, -2)) * scale
+    if causal:
+        S = q.shape[1]
+        mask = torch.ones(S, S, dtype=torch.bool, device=q.device).tril()
+        s = s.masked_fill(~mask, float("-inf"))
+    lse = torch.logsumexp(s, -1)  # [B,H,S]
+    p = torch.exp(s - lse.unsqueeze(-1))
+    o = torch.matmul(p, vf).permute(0, 2, 1, 3).contiguous()
+    return o.to(q.dtype), lse, p
+
+
+def attention_fwd(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, scale: float | None = None,
+                  causal: bool = True):
+    """Returns (o [B,S,H,D], lse [B,H,S])."""
+    B, S, H, D = q.shape
+    if scale is None:
+        scale = 1.0 / math.sqrt(D)
+    if not q.is_cuda:
+        o, lse, _ = _ref_fwd(q, k, v, scale, causal)
+        return o, lse
+    from . import lib, _check, _count, _stream
+    assert q.dtype == torch.bfloat16 and q.stride(3) == 1
+    assert q.stride() == k.stride() == v.stride(), "q/k/v must share strides (slices of one qkv buffer)"
+    o = torch.empty(B, S, H, D, dtype=q.dtype, device=q.device)
+    lse = torch.empty(B, H, S, dtype=torch.float32, device=q.device)
+    _check(lib().tepd_attn_fwd(q.data_ptr(), k.data_ptr(), v.data_ptr(), o.data_ptr(), lse.data_ptr(), B, H, S, D,
+                               float(scale), int(causal), q.stride(0), q.stride(1), q.stride(2), _stream()),
+           "attn_fwd")
+    _count()
+    return o, lse
+
+
+def attention_bwd(do: torch.Tensor, q, k, v, o, lse, scale: float | None = None, causal: bool = True,
+                  dqkv_out: torch.Tensor | None = None):
+    """Returns (dq, dk, dv) as [B,S,H,D] views (of ``dqkv_out`` [B,S,3,H,D] when given)."""
+    B, S, H, D = q.shape
+    if scale is None:
+        scale = 1.0 / math.sqrt(D)
+    if dqkv_out is None:
+        dqkv_out = torch.empty(B, S, 3, H, D, dtype=q.dtype, device=q.device)
+    dq, dk, dv = dqkv_out[:, :, 0], dqkv_out[:, :, 1], dqkv_out[:, :, 2]
+    if not q.is_cuda:
+        _, _, p = _ref_fwd(q, k, v, scale, causal)
+        dof = do.float().permute(0, 2, 1, 3)
+        qf, kf, vf = (t.float().permute(0, 2, 1, 3) for t in (q, k, v))
+        dvf = torch.matmul(p.transpose(-1, -2), dof)
+        dp = torch.matmul(dof, vf.transpose(-1, -2))
+        delta = (dof * o.float().permute(0, 2, 1, 3)).sum(-1, keepdim=True)
+        ds = p * (dp - delta) * scale
+        dqf = torch.matmul(ds, kf)
+        dkf = torch.matmul(ds.transpose(-1, -2), qf)
+        dq.copy_(dqf.permute(0, 2, 1, 3).to(q.dtype))
+        dk.copy_(dkf.permute(0, 2, 1, 3).to(q.dtype))
+        dv.copy_(dvf.permute(0, 2, 1, 3).to(q.dtype))
+        return dq, dk, dv
+    from . import lib, _check, _count, _stream
+    do = do.contiguous()
+    assert o.is_contiguous() and do.is_contiguous()
+    dq_acc = torch.zeros(B, S, H, D, dtype=torch.float32, device=q.device)
+    _check(lib().tepd_attn_bwd(do.data_ptr(), q.data_ptr(), k.data_ptr(), v.data_ptr(), o.data_ptr(), lse.data_ptr(),
+                               dq_acc.data_ptr(), dq.data_ptr(), dk.data_ptr(), dv.data_ptr(), B, H, S, D,
+                               float(scale), int(causal), q.stride(0), q.stride(1), q.stride(2),
+                               dq.stride(0), dq.stride(1), dq.stride(2), _stream()), "attn_bwd")
+    _count(3)
+    return dq, dk, dv

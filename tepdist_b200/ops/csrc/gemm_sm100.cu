@@ -1,0 +1,382 @@
+// Persistent warp-specialised bf16 GEMM for sm_100a: TMA -> smem (SWIZZLE_128B) -> tcgen05.mma ->
+// TMEM (double-buffered accumulators) -> tcgen05.ld epilogue (bias / GELU / residual / fp32 split-K
+// reduction fused).  This is the device-op layer that replaces the reference's cuBLAS GemmThunk
+// (reference: tensorflow/compiler/xla/service/gpu/gemm_thunk.cc).
+//
+//   D[b, M, N] = epilogue( alpha * A[b] (M x K)  *  B[b] (K x N) )
+//
+// Operand storage is described per operand by a "major" flag:
+//   A K-major : memory [b, M, K] (K contiguous)       A MN-major: memory [b, K, M] (M contiguous)
+//   B K-major : memory [b, N, K] (K contiguous)       B MN-major: memory [b, K, N] (N contiguous)
+// which covers forward (x @ W^T), dgrad (dy @ W) and wgrad (dy^T @ x) without any transposes.
+#include "sm100_ptx.cuh"
+#include <stdio.h>
+
+using namespace sm100;
+
+namespace {
+
+constexpr int BLOCK_M = 128;
+constexpr int BLOCK_K = 64;   // 64 bf16 = 128 B = one swizzle row
+constexpr int UMMA_K = 16;
+constexpr int NUM_THREADS = 192;  // warp0: TMA, warp1: MMA + TMEM alloc, warps 2..5: epilogue
+
+struct GemmParams {
+  int M, N, K, batch;
+  int m_blocks, n_blocks, k_blocks, split_k;
+  long long ldd, stride_d;       // output leading dim / batch stride (elements)
+  long long ld_res, stride_res;  // residual
+  void* D;
+  const void* bias;      // fp32 [N] or nullptr
+  const void* residual;  // bf16 [b, M, N] or nullptr
+  float alpha;
+  int out_fp32;    // 0: bf16 output, 1: fp32 output
+  int accumulate;  // 1: red.add into fp32 output (split-K / gradient accumulation)
+  int act;         // 0 none, 1 tanh-GELU
+  int bias_bf16;
+};
+
+__device__ __forceinline__ float gelu_tanh(float x) {
+  const float k0 = 0.7978845608028654f, k1 = 0.044715f;
+  float u = k0 * (x + k1 * x * x * x);
+  float t;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(u));
+  return 0.5f * x * (1.0f + t);
+}
+
+template <int BLOCK_N, bool A_MN, bool B_MN>
+struct Cfg {
+  static constexpr int A_BYTES = BLOCK_M * BLOCK_K * 2;
+  static constexpr int B_BYTES = BLOCK_N * BLOCK_K * 2;
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int STAGES = (BLOCK_N == 256) ? 4 : 6;
+  static constexpr int TMEM_COLS = 2 * BLOCK_N;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+};
+
+template <int BLOCK_N, bool A_MN, bool B_MN>
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
+                 const GemmParams p) {
+  using C = Cfg<BLOCK_N, A_MN, B_MN>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + C::STAGES * C::STAGE_BYTES);
+  uint64_t* empty_bar = full_bar + C::STAGES;
+  uint64_t* tmem_full = empty_bar + C::STAGES;
+  uint64_t* tmem_empty = tmem_full + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmap_a);
+    tma_prefetch_desc(&tmap_b);
+    for (int s = 0; s < C::STAGES; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&tmem_full[s], 1);
+      mbar_init(&tmem_empty[s], 4);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_slot, C::TMEM_COLS);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const int tiles_per_batch = p.m_blocks * p.n_blocks;
+  const int total_tiles = tiles_per_batch * p.batch * p.split_k;
+  const int kb_per_split = (p.k_blocks + p.split_k - 1) / p.split_k;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (elect_one()) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        int t = tile;
+        const int m_blk = t % p.m_blocks; t /= p.m_blocks;
+        const int n_blk = t % p.n_blocks; t /= p.n_blocks;
+        const int b = t % p.batch;
+        const int split = t / p.batch;
+        const int kb0 = split * kb_per_split;
+        const int kb1 = min(p.k_blocks, kb0 + kb_per_split);
+        for (int kb = kb0; kb < kb1; ++kb) {
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          uint8_t* sa = smem + stage * C::STAGE_BYTES;
+          uint8_t* sb = sa + C::A_BYTES;
+          mbar_expect_tx(&full_bar[stage], C::STAGE_BYTES);
+          if constexpr (!A_MN) {
+            tma_load_3d(sa, &tmap_a, &full_bar[stage], kb * BLOCK_K, m_blk * BLOCK_M, b);
+          } else {
+#pragma unroll
+            for (int j = 0; j < BLOCK_M / 64; ++j)
+              tma_load_3d(sa + j * (64 * BLOCK_K * 2), &tmap_a, &full_bar[stage],
+                          m_blk * BLOCK_M + j * 64, kb * BLOCK_K, b);
+          }
+          if constexpr (!B_MN) {
+            tma_load_3d(sb, &tmap_b, &full_bar[stage], kb * BLOCK_K, n_blk * BLOCK_N, b);
+          } else {
+#pragma unroll
+            for (int j = 0; j < BLOCK_N / 64; ++j)
+              tma_load_3d(sb + j * (64 * BLOCK_K * 2), &tmap_b, &full_bar[stage],
+                          n_blk * BLOCK_N + j * 64, kb * BLOCK_K, b);
+          }
+          if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    if (elect_one()) {
+      constexpr uint32_t idesc = make_idesc(UMMA_BF16, UMMA_BF16, BLOCK_M, BLOCK_N, A_MN ? 1 : 0, B_MN ? 1 : 0);
+      int stage = 0;
+      uint32_t phase = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        int t = tile / (tiles_per_batch * p.batch);
+        const int kb0 = t * kb_per_split;
+        const int kb1 = min(p.k_blocks, kb0 + kb_per_split);
+        mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * BLOCK_N;
+        for (int kb = kb0; kb < kb1; ++kb) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(smem + stage * C::STAGE_BYTES);
+          const uint32_t sb = sa + C::A_BYTES;
+#pragma unroll
+          for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
+            uint64_t da, db;
+            if constexpr (!A_MN) da = make_smem_desc_sw128(sa + k * UMMA_K * 2, 0, 1024);
+            else                 da = make_smem_desc_sw128(sa + k * UMMA_K * 128, 64 * BLOCK_K * 2, 1024);
+            if constexpr (!B_MN) db = make_smem_desc_sw128(sb + k * UMMA_K * 2, 0, 1024);
+            else                 db = make_smem_desc_sw128(sb + k * UMMA_K * 128, 64 * BLOCK_K * 2, 1024);
+            umma_f16_ss(d_tmem, da, db, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+          }
+          umma_commit(&empty_bar[stage]);  // frees the smem slot when these MMAs retire
+          if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
+        }
+        umma_commit(&tmem_full[acc]);  // accumulator ready for the epilogue
+        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+      }
+    }
+  } else {
+    // ===================== epilogue (4 warps, one TMEM lane quarter each) =====================
+    const int quarter = warp & 3;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      int t = tile;
+      const int m_blk = t % p.m_blocks; t /= p.m_blocks;
+      const int n_blk = t % p.n_blocks; t /= p.n_blocks;
+      const int b = t % p.batch;
+      const int split = t / p.batch;
+      const int kb0 = split * kb_per_split;
+      const bool has_k = kb0 < p.k_blocks;  // (always true for valid split configs)
+      mbar_wait(&tmem_full[acc], acc_phase);
+      tc_fence_after();
+      const int row = m_blk * BLOCK_M + quarter * 32 + lane;
+      const bool row_ok = row < p.M;
+      const uint32_t t_row = tmem_base + (uint32_t(quarter * 32) << 16) + acc * BLOCK_N;
+      const bool add_bias = p.bias != nullptr && split == 0;
+      const bool add_res = p.residual != nullptr && split == 0;
+#pragma unroll 1
+      for (int c = 0; c < BLOCK_N / 32; ++c) {
+        uint32_t r[32];
+        tmem_ld_32x32(t_row + c * 32, r);
+        tmem_ld_wait();
+        const int col0 = n_blk * BLOCK_N + c * 32;
+        if (row_ok && col0 < p.N && has_k) {
+          float v[32];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]) * p.alpha;
+          if (add_bias) {
+            if (p.bias_bf16) {
+              const __nv_bfloat16* bp = reinterpret_cast<const __nv_bfloat16*>(p.bias) + col0;
+#pragma unroll
+              for (int j = 0; j < 32; ++j) if (col0 + j < p.N) v[j] += __bfloat162float(bp[j]);
+            } else {
+              const float* bp = reinterpret_cast<const float*>(p.bias) + col0;
+#pragma unroll
+              for (int j = 0; j < 32; ++j) if (col0 + j < p.N) v[j] += __ldg(bp + j);
+            }
+          }
+          if (p.act == 1) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = gelu_tanh(v[j]);
+          }
+          if (add_res) {
+            const uint4* rp = reinterpret_cast<const uint4*>(
+                reinterpret_cast<const __nv_bfloat16*>(p.residual) + (long long)b * p.stride_res +
+                (long long)row * p.ld_res + col0);
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              if (col0 + q * 8 < p.N) {
+                uint4 u = __ldg(rp + q);
+                const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                  float2 f = __bfloat1622float2(h[e]);
+                  v[q * 8 + e * 2] += f.x;
+                  v[q * 8 + e * 2 + 1] += f.y;
+                }
+              }
+            }
+          }
+          const long long off = (long long)b * p.stride_d + (long long)row * p.ldd + col0;
+          if (!p.out_fp32) {
+            uint4* dp = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.D) + off);
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              if (col0 + q * 8 < p.N) {
+                uint4 u;
+                u.x = pack_bf16x2(v[q * 8 + 0], v[q * 8 + 1]);
+                u.y = pack_bf16x2(v[q * 8 + 2], v[q * 8 + 3]);
+                u.z = pack_bf16x2(v[q * 8 + 4], v[q * 8 + 5]);
+                u.w = pack_bf16x2(v[q * 8 + 6], v[q * 8 + 7]);
+                dp[q] = u;
+              }
+            }
+          } else if (!p.accumulate) {
+            float4* dp = reinterpret_cast<float4*>(reinterpret_cast<float*>(p.D) + off);
+#pragma unroll
+            for (int q = 0; q < 8; ++q)
+              if (col0 + q * 4 < p.N) dp[q] = make_float4(v[q * 4], v[q * 4 + 1], v[q * 4 + 2], v[q * 4 + 3]);
+          } else {
+            float* dp = reinterpret_cast<float*>(p.D) + off;
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+              if (col0 + q * 4 < p.N) {
+                asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dp + q * 4),
+                             "f"(v[q * 4]), "f"(v[q * 4 + 1]), "f"(v[q * 4 + 2]), "f"(v[q * 4 + 3])
+                             : "memory");
+              }
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, C::TMEM_COLS);
+  }
+}
+
+// ------------------------------------------------------------------ host side
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*,
+                                  CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion,
+                                  CUtensorMapFloatOOBfill);
+
+EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess || !p) {
+      fprintf(stderr, "[tepdist_b200] cuTensorMapEncodeTiled unavailable\n");
+      return nullptr;
+    }
+    fn = reinterpret_cast<EncodeTiledFn>(p);
+  }
+  return fn;
+}
+
+}  // namespace
+
+// 3-D bf16 tensor map: dims (inner, rows, batch); box (box_inner, box_rows, 1); SWIZZLE_128B.
+extern "C" int tepd_make_tmap_bf16_3d(CUtensorMap* out, const void* ptr, long long inner, long long rows,
+                                      long long batch, long long ld_elems, long long batch_stride_elems,
+                                      int box_inner, int box_rows) {
+  EncodeTiledFn fn = get_encode_fn();
+  if (!fn) return -1;
+  cuuint64_t dims[3] = {(cuuint64_t)inner, (cuuint64_t)rows, (cuuint64_t)batch};
+  cuuint64_t strides[2] = {(cuuint64_t)ld_elems * 2, (cuuint64_t)(batch > 1 ? batch_stride_elems : rows * ld_elems) * 2};
+  cuuint32_t box[3] = {(cuuint32_t)box_inner, (cuuint32_t)box_rows, 1};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(ptr), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? 0 : (int)r;
+}
+
+template <int BLOCK_N, bool A_MN, bool B_MN>
+static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, int num_sms,
+                       cudaStream_t stream) {
+  using C = Cfg<BLOCK_N, A_MN, B_MN>;
+  auto kern = gemm_bf16_kernel<BLOCK_N, A_MN, B_MN>;
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES);
+    if (e != cudaSuccess) return (int)e;
+    configured = true;
+  }
+  int total = p.m_blocks * p.n_blocks * p.batch * p.split_k;
+  int grid = total < num_sms ? total : num_sms;
+  kern<<<grid, NUM_THREADS, C::SMEM_BYTES, stream>>>(ta, tb, p);
+  return (int)cudaGetLastError();
+}
+
+// C ABI entry (called from Python via ctypes).  All leading dims / strides are in elements.
+extern "C" int tepd_gemm_bf16(const void* A, const void* B, void* D, const void* bias, const void* residual,
+                              int M, int N, int K, int batch, long long lda, long long ldb, long long ldd,
+                              long long stride_a, long long stride_b, long long stride_d, long long ld_res,
+                              long long stride_res, int a_mn, int b_mn, int out_fp32, int accumulate, int act,
+                              int bias_bf16, float alpha, int split_k, int block_n, int num_sms, void* stream) {
+  if (N % 8 != 0 || K % 8 != 0 || M <= 0) return -2;
+  if ((a_mn && (M % 8)) || (accumulate && !out_fp32)) return -3;
+  GemmParams p;
+  p.M = M; p.N = N; p.K = K; p.batch = batch;
+  if (block_n != 128 && block_n != 256) block_n = (N % 256 == 0 || N > 1024) ? 256 : 128;
+  p.m_blocks = (M + BLOCK_M - 1) / BLOCK_M;
+  p.n_blocks = (N + block_n - 1) / block_n;
+  p.k_blocks = (K + BLOCK_K - 1) / BLOCK_K;
+  if (split_k < 1) split_k = 1;
+  if (split_k > p.k_blocks) split_k = p.k_blocks;
+  if (split_k > 1) {
+    // make every split non-empty
+    int per = (p.k_blocks + split_k - 1) / split_k;
+    split_k = (p.k_blocks + per - 1) / per;
+    if (!(out_fp32 && accumulate)) return -4;
+  }
+  p.split_k = split_k;
+  p.ldd = ldd; p.stride_d = stride_d; p.ld_res = ld_res; p.stride_res = stride_res;
+  p.D = D; p.bias = bias; p.residual = residual; p.alpha = alpha;
+  p.out_fp32 = out_fp32; p.accumulate = accumulate; p.act = act; p.bias_bf16 = bias_bf16;
+
+  CUtensorMap ta, tb;
+  int rc;
+  if (!a_mn) rc = tepd_make_tmap_bf16_3d(&ta, A, K, M, batch, lda, stride_a, BLOCK_K, BLOCK_M);
+  else       rc = tepd_make_tmap_bf16_3d(&ta, A, M, K, batch, lda, stride_a, 64, BLOCK_K);
+  if (rc) return 100 + rc;
+  if (!b_mn) rc = tepd_make_tmap_bf16_3d(&tb, B, K, N, batch, ldb, stride_b, BLOCK_K, block_n);
+  else       rc = tepd_make_tmap_bf16_3d(&tb, B, N, K, batch, ldb, stride_b, 64, BLOCK_K);
+  if (rc) return 200 + rc;
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  if (num_sms <= 0) num_sms = 148;
+#define DISPATCH(BN)                                                                   \
+  if (!a_mn && !b_mn) return launch_gemm<BN, false, false>(ta, tb, p, num_sms, s);     \
+  if (!a_mn && b_mn) return launch_gemm<BN, false, true>(ta, tb, p, num_sms, s);       \
+  if (a_mn && !b_mn) return launch_gemm<BN, true, false>(ta, tb, p, num_sms, s);       \
+  return launch_gemm<BN, true, true>(ta, tb, p, num_sms, s);
+  if (block_n == 256) { DISPATCH(256) } else { DISPATCH(128) }
+#undef DISPATCH
+}

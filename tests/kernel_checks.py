@@ -1,0 +1,335 @@
+"""Numerics + timing checks for the sm_100a kernels against plain-PyTorch fp32 references.
+
+Used two ways: (1) `python tests/kernel_checks.py [names...]` on a GPU box runs every check in its own
+subprocess with a timeout (so one hung kernel cannot take the whole run down) and writes
+gpurun_out/kernel_checks.json; (2) tests/test_kernels_gpu.py imports the check functions under pytest.
+"""
+from __future__ import annotations
+
+import json
+import os
+import subprocess
+import sys
+import time
+
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+
+
+def _rel_err(a: torch.Tensor, b: torch.Tensor) -> float:
+    a, b = a.float(), b.float()
+    return ((a - b).norm() / (b.norm() + 1e-12)).item()
+
+
+def _time_ms(fn, iters=20, warmup=5):
+    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device="cuda")
+    for _ in range(warmup):
+        fn()
+    torch.cuda.synchronize()
+    ts = []
+    for _ in range(iters):
+        flush.zero_()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        fn()
+        e1.record()
+        torch.cuda.synchronize()
+        ts.append(e0.elapsed_time(e1))
+    ts.sort()
+    return ts[len(ts) // 2]
+
+
+# ------------------------------------------------------------------------------------------ GEMM
+def check_gemm_layouts():
+    from tepdist_b200 import ops
+    out = {}
+    torch.manual_seed(0)
+    for (M, N, K) in [(256, 256, 128), (384, 640, 320), (1024, 1024, 1024), (200, 136, 72)]:
+        for a_mn in (False, True):
+            for b_mn in (False, True):
+                if a_mn and M % 8:
+                    continue
+                A = torch.randn(M, K, device="cuda", dtype=torch.bfloat16)
+                B = torch.randn(K, N, device="cuda", dtype=torch.bfloat16)
+                a = A.t().contiguous() if a_mn else A
+                b = B if b_mn else B.t().contiguous()
+                ref = A.float() @ B.float()
+                for bn in (128, 256):
+                    d = ops.gemm(a, b, a_mn=a_mn, b_mn=b_mn, block_n=bn)
+                    torch.cuda.synchronize()
+                    err = _rel_err(d, ref)
+                    out[f"{M}x{N}x{K}_a{int(a_mn)}b{int(b_mn)}_bn{bn}"] = err
+                    assert err < 1e-2, (M, N, K, a_mn, b_mn, bn, err)
+    return out
+
+
+def check_gemm_epilogues():
+    from tepdist_b200 import ops
+    out = {}
+    torch.manual_seed(1)
+    M, N, K = 512, 768, 256
+    A = torch.randn(M, K, device="cuda", dtype=torch.bfloat16)
+    W = torch.randn(N, K, device="cuda", dtype=torch.bfloat16) * 0.05
+    bias = torch.randn(N, device="cuda", dtype=torch.float32)
+    res = torch.randn(M, N, device="cuda", dtype=torch.bfloat16)
+    ref = A.float() @ W.float().t() + bias
+    d = ops.gemm(A, W, bias=bias)
+    out["bias"] = _rel_err(d, ref)
+    d = ops.gemm(A, W, bias=bias.bfloat16())
+    out["bias_bf16"] = _rel_err(d, A.float() @ W.float().t() + bias.bfloat16().float())
+    d = ops.gemm(A, W, bias=bias, act="gelu")
+    out["gelu"] = _rel_err(d, torch.nn.functional.gelu(ref, approximate="tanh"))
+    d = ops.gemm(A, W, bias=bias, residual=res)
+    out["residual"] = _rel_err(d, ref + res.float())
+    d = ops.gemm(A, W, out_dtype=torch.float32, alpha=0.5)
+    out["fp32_alpha"] = _rel_err(d, 0.5 * (A.float() @ W.float().t()))
+    acc = torch.ones(M, N, device="cuda", dtype=torch.float32)
+    ops.gemm(A, W, out=acc, accumulate=True, split_k=1)
+    out["accumulate"] = _rel_err(acc, 1.0 + A.float() @ W.float().t())
+    acc = torch.zeros(M, N, device="cuda", dtype=torch.float32)
+    ops.gemm(A, W, out=acc, accumulate=True, split_k=4)
+    out["splitk4"] = _rel_err(acc, A.float() @ W.float().t())
+    # wgrad-style: dW[N,K] += dY[M,N]^T @ X[M,K]   (both operands MN-major, split-K over tokens)
+    T = 2048
+    dY = torch.randn(T, N, device="cuda", dtype=torch.bfloat16)
+    X = torch.randn(T, K, device="cuda", dtype=torch.bfloat16)
+    acc = torch.zeros(N, K, device="cuda", dtype=torch.float32)
+    ops.gemm(dY, X, a_mn=True, b_mn=True, out=acc, accumulate=True)
+    out["wgrad"] = _rel_err(acc, dY.float().t() @ X.float())
+    # batched
+    Ab = torch.randn(6, 256, 64, device="cuda", dtype=torch.bfloat16)
+    Bb = torch.randn(6, 384, 64, device="cuda", dtype=torch.bfloat16)
+    d = ops.gemm(Ab, Bb)
+    out["batched"] = _rel_err(d, torch.matmul(Ab.float(), Bb.float().transpose(1, 2)))
+    torch.cuda.synchronize()
+    for k, v in out.items():
+        assert v < 1e-2, (k, v)
+    return out
+
+
+def check_gemm_perf():
+    from tepdist_b200 import ops
+    out = {}
+    for (M, N, K) in [(8192, 8192, 8192), (4096, 4096, 1024), (4096, 1024, 4096), (4096, 3072, 1024), (4096, 50304, 1024)]:
+        A = torch.randn(M, K, device="cuda", dtype=torch.bfloat16)
+        W = torch.randn(N, K, device="cuda", dtype=torch.bfloat16)
+        for bn in (128, 256):
+            ms = _time_ms(lambda: ops.gemm(A, W, block_n=bn))
+            out[f"ours_{M}x{N}x{K}_bn{bn}_tflops"] = 2.0 * M * N * K / ms / 1e9
+        ms = _time_ms(lambda: torch.matmul(A, W.t()))
+        out[f"cublas_{M}x{N}x{K}_tflops"] = 2.0 * M * N * K / ms / 1e9
+    # wgrad shape with split-K
+    T, N, K = 4096, 1024, 4096
+    dY = torch.randn(T, N, device="cuda", dtype=torch.bfloat16)
+    X = torch.randn(T, K, device="cuda", dtype=torch.bfloat16)
+    acc = torch.zeros(N, K, device="cuda", dtype=torch.float32)
+    ms = _time_ms(lambda: ops.gemm(dY, X, a_mn=True, b_mn=True, out=acc, accumulate=True))
+    out["ours_wgrad_4096tok_1024x4096_tflops"] = 2.0 * T * N * K / ms / 1e9
+    ms = _time_ms(lambda: torch.matmul(dY.t(), X))
+    out["cublas_wgrad_tflops"] = 2.0 * T * N * K / ms / 1e9
+    return out
+
+
+# ------------------------------------------------------------------------------------------ elementwise
+def check_layernorm():
+    from tepdist_b200 import ops
+    out = {}
+    torch.manual_seed(2)
+    for C in (1024, 768, 1600):
+        rows = 1000
+        x = torch.randn(rows, C, device="cuda", dtype=torch.bfloat16) * 2 + 0.5
+        g = torch.randn(C, device="cuda") * 0.1 + 1
+        b = torch.randn(C, device="cuda") * 0.1
+        y, mean, rstd = ops.layernorm_fwd(x, g, b)
+        ref = torch.nn.functional.layer_norm(x.float(), (C,), g, b, 1e-5)
+        out[f"fwd_{C}"] = _rel_err(y, ref)
+        dy = torch.randn_like(x)
+        dg, db = torch.zeros(C, device="cuda"), torch.zeros(C, device="cuda")
+        dx = ops.layernorm_bwd(dy, x, g, mean, rstd, dg, db)
+        xr = x.float().requires_grad_(True)
+        gr, br = g.clone().requires_grad_(True), b.clone().requires_grad_(True)
+        torch.nn.functional.layer_norm(xr, (C,), gr, br, 1e-5).backward(dy.float())
+        out[f"dx_{C}"] = _rel_err(dx, xr.grad)
+        out[f"dgamma_{C}"] = _rel_err(dg, gr.grad)
+        out[f"dbeta_{C}"] = _rel_err(db, br.grad)
+    for k, v in out.items():
+        assert v < 1.5e-2, (k, v)
+    return out
+
+
+def check_gelu_colsum_embed():
+    from tepdist_b200 import ops
+    out = {}
+    torch.manual_seed(3)
+    x = torch.randn(512, 4096, device="cuda", dtype=torch.bfloat16)
+    out["gelu_fwd"] = _rel_err(ops.gelu_fwd(x), torch.nn.functional.gelu(x.float(), approximate="tanh"))
+    dy = torch.randn_like(x)
+    xr = x.float().requires_grad_(True)
+    torch.nn.functional.gelu(xr, approximate="tanh").backward(dy.float())
+    out["gelu_bwd"] = _rel_err(ops.gelu_bwd(dy, x), xr.grad)
+    acc = torch.zeros(4096, device="cuda")
+    ops.colsum_acc(x, acc)
+    out["colsum"] = _rel_err(acc, x.float().sum(0))
+    V, C, B, S = 1000, 256, 3, 64
+    wte = torch.randn(V, C, device="cuda", dtype=torch.bfloat16)
+    wpe = torch.randn(S, C, device="cuda", dtype=torch.bfloat16)
+    tok = torch.randint(0, V, (B, S), device="cuda")
+    e = ops.embedding_fwd(tok, wte, wpe)
+    out["embed_fwd"] = _rel_err(e, wte[tok].float() + wpe.float())
+    de = torch.randn(B, S, C, device="cuda", dtype=torch.bfloat16)
+    dwte, dwpe = torch.zeros(V, C, device="cuda"), torch.zeros(S, C, device="cuda")
+    ops.embedding_bwd(tok, de, dwte, dwpe)
+    ref = torch.zeros(V, C, device="cuda").index_add_(0, tok.reshape(-1), de.float().reshape(-1, C))
+    out["embed_bwd_wte"] = _rel_err(dwte, ref)
+    out["embed_bwd_wpe"] = _rel_err(dwpe, de.float().sum(0))
+    for k, v in out.items():
+        assert v < 1e-2, (k, v)
+    return out
+
+
+def check_xent_adam():
+    from tepdist_b200 import ops
+    out = {}
+    torch.manual_seed(4)
+    T, V, Vp = 256, 50257, 50304
+    logits = torch.randn(T, Vp, device="cuda", dtype=torch.bfloat16) * 3
+    labels = torch.randint(0, V, (T,), device="cuda")
+    lf = logits.float()[:, :V].clone().requires_grad_(True)
+    loss_ref = torch.nn.functional.cross_entropy(lf, labels, reduction="sum") / T
+    loss_ref.backward()
+    total, rows = ops.xent_fwd_bwd(logits, labels, V, 1.0 / T)
+    out["loss"] = abs(total.item() - loss_ref.item()) / abs(loss_ref.item())
+    out["dlogits"] = _rel_err(logits[:, :V], lf.grad)
+    out["dlogits_pad"] = logits[:, V:].float().abs().max().item()
+    n = 1 << 20
+    p = torch.randn(n, device="cuda")
+    g = torch.randn(n, device="cuda")
+    m, v = torch.zeros(n, device="cuda"), torch.zeros(n, device="cuda")
+    pb = torch.empty(n, device="cuda", dtype=torch.bfloat16)
+    pr = p.clone().requires_grad_(True)
+    opt = torch.optim.AdamW([pr], lr=1e-3, betas=(0.9, 0.95), eps=1e-8, weight_decay=0.1)
+    for step in (1, 2, 3):
+        pr.grad = g.clone()
+        opt.step()
+        ops.adamw_step(p, g, m, v, pb, n, 1e-3, 0.9, 0.95, 1e-8, 0.1, step)
+    out["adamw"] = _rel_err(p, pr.detach())
+    out["adamw_bf16"] = _rel_err(pb, pr.detach())
+    assert out["loss"] < 1e-3 and out["dlogits"] < 2e-2 and out["dlogits_pad"] == 0.0, out
+    assert out["adamw"] < 1e-5 and out["adamw_bf16"] < 5e-3, out
+    return out
+
+
+# ------------------------------------------------------------------------------------------ attention
+def _qkv(B, S, H, D, seed=5):
+    torch.manual_seed(seed)
+    qkv = torch.randn(B, S, 3, H, D, device="cuda", dtype=torch.bfloat16)
+    return qkv, qkv[:, :, 0], qkv[:, :, 1], qkv[:, :, 2]
+
+
+def check_attn_fwd():
+    from tepdist_b200 import ops
+    from tepdist_b200.ops.attention import _ref_fwd
+    out = {}
+    for (B, S, H, causal) in [(1, 128, 1, True), (2, 256, 3, True), (2, 512, 4, False), (1, 1024, 16, True)]:
+        qkv, q, k, v = _qkv(B, S, H, 64)
+        o, lse = ops.attention_fwd(q, k, v, causal=causal)
+        torch.cuda.synchronize()
+        o_ref, lse_ref, _ = _ref_fwd(q, k, v, 1.0 / 8.0, causal)
+        tag = f"B{B}S{S}H{H}c{int(causal)}"
+        out["o_" + tag] = _rel_err(o, o_ref)
+        out["lse_" + tag] = _rel_err(lse, lse_ref)
+        assert out["o_" + tag] < 2e-2 and out["lse_" + tag] < 1e-3, out
+    return out
+
+
+def check_attn_bwd():
+    from tepdist_b200 import ops
+    from tepdist_b200.ops.attention import _ref_fwd
+    out = {}
+    for (B, S, H, causal) in [(1, 128, 1, True), (2, 256, 3, True), (1, 512, 2, False), (1, 1024, 16, True)]:
+        qkv, q, k, v = _qkv(B, S, H, 64)
+        o, lse = ops.attention_fwd(q, k, v, causal=causal)
+        do = torch.randn_like(o)
+        dq, dk, dv = ops.attention_bwd(do, q, k, v, o, lse, causal=causal)
+        torch.cuda.synchronize()
+        qr, kr, vr = (t.float().detach().clone().requires_grad_(True) for t in (q, k, v))
+        s = torch.einsum("bqhd,bkhd->bhqk", qr, kr) / 8.0
+        if causal:
+            mask = torch.ones(S, S, dtype=torch.bool, device="cuda").tril()
+            s = s.masked_fill(~mask, float("-inf"))
+        oo = torch.einsum("bhqk,bkhd->bqhd", torch.softmax(s, -1), vr)
+        oo.backward(do.float())
+        tag = f"B{B}S{S}H{H}c{int(causal)}"
+        out["dq_" + tag] = _rel_err(dq, qr.grad)
+        out["dk_" + tag] = _rel_err(dk, kr.grad)
+        out["dv_" + tag] = _rel_err(dv, vr.grad)
+        for n in ("dq_", "dk_", "dv_"):
+            assert out[n + tag] < 3e-2, out
+    return out
+
+
+def check_attn_perf():
+    from tepdist_b200 import ops
+    out = {}
+    B, S, H, D = 4, 1024, 16, 64
+    qkv, q, k, v = _qkv(B, S, H, D)
+    ms = _time_ms(lambda: ops.attention_fwd(q, k, v))
+    fl = 4.0 * B * H * S * S * D / 2
+    out["fwd_ms"] = ms
+    out["fwd_tflops"] = fl / ms / 1e9
+    qc, kc, vc = (t.permute(0, 2, 1, 3).contiguous() for t in (q, k, v))
+    ms2 = _time_ms(lambda: torch.nn.functional.scaled_dot_product_attention(qc, kc, vc, is_causal=True))
+    out["sdpa_fwd_ms"] = ms2
+    try:
+        o, lse = ops.attention_fwd(q, k, v)
+        do = torch.randn_like(o)
+        msb = _time_ms(lambda: ops.attention_bwd(do, q, k, v, o, lse))
+        out["bwd_ms"] = msb
+        out["bwd_tflops"] = 2.5 * fl / msb / 1e9
+    except Exception as e:  # bwd kernel may not be built yet
+        out["bwd_error"] = repr(e)
+    return out
+
+
+CHECKS = {
+    "gemm_layouts": check_gemm_layouts,
+    "gemm_epilogues": check_gemm_epilogues,
+    "layernorm": check_layernorm,
+    "gelu_colsum_embed": check_gelu_colsum_embed,
+    "xent_adam": check_xent_adam,
+    "attn_fwd": check_attn_fwd,
+    "attn_bwd": check_attn_bwd,
+    "gemm_perf": check_gemm_perf,
+    "attn_perf": check_attn_perf,
+}
+
+
+def _run_one(name: str) -> None:
+    res = CHECKS[name]()
+    torch.cuda.synchronize()
+    print("RESULT " + json.dumps(res))
+
+
+if __name__ == "__main__":
+    if len(sys.argv) >= 3 and sys.argv[1] == "--one":
+        _run_one(sys.argv[2])
+        sys.exit(0)
+    names = [a for a in sys.argv[1:] if a in CHECKS] or list(CHECKS)
+    os.makedirs("gpurun_out", exist_ok=True)
+    summary = {}
+    for n in names:
+        t0 = time.time()
+        try:
+            pr = subprocess.run([sys.executable, __file__, "--one", n], capture_output=True, text=True, timeout=300)
+            res = None
+            for line in pr.stdout.splitlines():
+                if line.startswith("RESULT "):
+                    res = json.loads(line[7:])
+            summary[n] = {"rc": pr.returncode, "result": res, "secs": round(time.time() - t0, 1),
+                          "stderr": pr.stderr[-1500:] if pr.returncode else ""}
+        except subprocess.TimeoutExpired:
+            summary[n] = {"rc": "timeout", "secs": round(time.time() - t0, 1)}
+        print(n, json.dumps(summary[n])[:3000], flush=True)
+        with open("gpurun_out/kernel_checks.json", "w") as f:
+            json.dump(summary, f, indent=1)
