@@ -1,0 +1,82 @@
+"""Public user-facing API.
+
+    import tepdist_b200 as td
+    graph   = td.models.gpt2.build_gpt2_graph(cfg)          # or td.frontend.trace(module, ...)
+    trainer = td.Trainer(graph, strategy="auto")             # plans + builds the runtime on this rank
+    loss    = trainer.step({"tokens": tok_cpu, "labels": lab_cpu})
+
+`Trainer` is what a reference user's `session.run(train_op)` becomes: the first call plans and compiles,
+later calls execute the cached plan (reference: XlaRunOp -> BuildExecutionPlan / ExecutePlan).
+Launch with torchrun (one process per GPU); single-process works for 1 GPU / CPU.
+"""
+from __future__ import annotations
+
+import os
+from typing import Any, Dict, List, Optional
+
+import torch
+import torch.distributed as dist
+
+from .ir import Graph
+from .runtime.executor import Executor
+
+
+def init_distributed(backend: Optional[str] = None) -> Dict[str, int]:
+    """Rendezvous from torchrun env (RANK/LOCAL_RANK/WORLD_SIZE/MASTER_*); idempotent."""
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1 and not dist.is_initialized():
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        os.environ.setdefault("MASTER_PORT", "29500")
+        if backend is None:
+            backend = "nccl" if torch.cuda.is_available() else "gloo"
+        if backend == "nccl":
+            torch.cuda.set_device(local)
+            dist.init_process_group(backend, device_id=torch.device("cuda", local))
+        else:
+            dist.init_process_group(backend)
+    elif torch.cuda.is_available():
+        torch.cuda.set_device(local)
+    return {"rank": rank, "world": world, "local_rank": local}
+
+
+class Trainer:
+    def __init__(self, graph: Graph, strategy: str = "auto", device: Optional[torch.device] = None,
+                 use_cuda_graph: bool = True, seed: int = 0, comm_mode: str = "fused"):
+        self.ctx = init_distributed()
+        self.world, self.rank = self.ctx["world"], self.ctx["rank"]
+        if device is None:
+            device = torch.device("cuda", self.ctx["local_rank"]) if torch.cuda.is_available() else torch.device("cpu")
+        self.device = device
+        self.strategy = strategy
+        grad_sync = None
+        self.plan_info: Dict[str, Any] = {"strategy": strategy, "world": self.world}
+        if self.world > 1:
+            from .parallel import plan_and_build
+            self.exec = plan_and_build(graph, self, strategy, comm_mode, use_cuda_graph, seed)
+        else:
+            self.exec = Executor(graph, device, seed=seed, grad_sync=grad_sync, use_cuda_graph=use_cuda_graph)
+        self._pinned: Dict[str, torch.Tensor] = {}
+        self._loss_host = torch.zeros(1, dtype=torch.float32).pin_memory() if device.type == "cuda" else None
+
+    def step(self, feeds: Dict[str, torch.Tensor]) -> float:
+        """One training step on this rank's shard of the batch; returns the (local) loss as a python float.
+        Host tensors are copied to the device (async from pinned memory); the loss is read back."""
+        dev_feeds = {}
+        for k, t in feeds.items():
+            dev_feeds[k] = t if t.device == self.device else t.to(self.device, non_blocking=True)
+        out = self.exec.step(dev_feeds)
+        loss = out[0]
+        if self._loss_host is not None:
+            self._loss_host.copy_(loss.reshape(1), non_blocking=True)
+            torch.cuda.current_stream().synchronize()
+            return float(self._loss_host[0])
+        return float(loss)
+
+    def step_async(self, dev_feeds: Dict[str, torch.Tensor]) -> torch.Tensor:
+        """Device-resident variant (no host sync): returns the loss tensor."""
+        return self.exec.step(dev_feeds)[0]
+
+    def state_dict(self):
+        return self.exec.store.state_dict()

@@ -74,7 +74,7 @@ class _Sig:
     tepd_embedding_fwd = [_vp, _vp, _vp, _vp, _i, _i, _i, _vp]
     tepd_embedding_bwd = [_vp, _vp, _vp, _vp, _i, _i, _i, _vp]
     tepd_xent_fwd_bwd = [_vp, _vp, _vp, _vp, _i, _i, _i, _f, _vp]
-    tepd_adamw = [_vp, _vp, _vp, _vp, _vp, _ll, _ll, _f, _f, _f, _f, _f, _f, _f, _f, _vp]
+    tepd_adamw = [_vp, _vp, _vp, _vp, _vp, _ll, _ll, _f, _f, _f, _f, _f, _f, _f, _f, _vp, _vp]
     tepd_sgd = [_vp, _vp, _vp, _ll, _f, _f, _vp]
     tepd_axpy_f32 = [_vp, _vp, _ll, _f, _vp]
     tepd_cast_f32_bf16 = [_vp, _vp, _ll, _vp]
@@ -312,12 +312,15 @@ def xent_fwd_bwd(logits: torch.Tensor, labels: torch.Tensor, vocab: int, grad_sc
 # --------------------------------------------------------------------------------------------- optimizer
 def adamw_step(p: torch.Tensor, g: torch.Tensor, m: torch.Tensor, v: torch.Tensor, p_bf16: Optional[torch.Tensor],
                n_decay: int, lr: float, beta1: float, beta2: float, eps: float, wd: float, step: int,
-               grad_scale: float = 1.0) -> None:
-    """Fused AdamW over flat fp32 buffers (decay applies to the prefix [0, n_decay))."""
+               grad_scale: float = 1.0, hyper: Optional[torch.Tensor] = None) -> None:
+    """Fused AdamW over flat fp32 buffers (decay applies to the prefix [0, n_decay)).
+    ``hyper`` (device fp32 [4] = lr, bc1, bc2, grad_scale) overrides the scalars: CUDA-graph friendly."""
     bc1 = 1.0 - beta1 ** step
     bc2 = 1.0 - beta2 ** step
     n = p.numel()
     if not p.is_cuda:
+        if hyper is not None:
+            lr, bc1, bc2, grad_scale = (float(x) for x in hyper.tolist())
         gr = g * grad_scale
         m.mul_(beta1).add_(gr, alpha=1 - beta1)
         v.mul_(beta2).addcmul_(gr, gr, value=1 - beta2)
@@ -330,7 +333,7 @@ def adamw_step(p: torch.Tensor, g: torch.Tensor, m: torch.Tensor, v: torch.Tenso
         return
     assert p_bf16 is not None
     _check(lib().tepd_adamw(p.data_ptr(), g.data_ptr(), m.data_ptr(), v.data_ptr(), p_bf16.data_ptr(), n, n_decay,
-                            lr, beta1, beta2, eps, wd, bc1, bc2, grad_scale, _stream()), "adamw")
+                            lr, beta1, beta2, eps, wd, bc1, bc2, grad_scale, _p(hyper), _stream()), "adamw")
     _count()
 
 

@@ -357,7 +357,10 @@ __global__ void __launch_bounds__(512) xent_fwd_bwd_kernel(bf16* __restrict__ lo
 // prefix [0, n_decay) and a non-decayed suffix.
 __global__ void adamw_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
                              float* __restrict__ v, bf16* __restrict__ p_bf16, size_t n, size_t n_decay, float lr,
-                             float beta1, float beta2, float eps, float wd, float bc1, float bc2, float gscale) {
+                             float beta1, float beta2, float eps, float wd, float bc1, float bc2, float gscale,
+                             const float* __restrict__ hyper) {
+  // hyper (device, optional): {lr, bc1, bc2, gscale} so a captured CUDA graph sees per-step values
+  if (hyper) { lr = hyper[0]; bc1 = hyper[1]; bc2 = hyper[2]; gscale = hyper[3]; }
   const size_t nvec = n >> 2;
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < nvec; i += (size_t)gridDim.x * blockDim.x) {
     float4 pp = reinterpret_cast<float4*>(p)[i];
@@ -484,9 +487,10 @@ extern "C" int tepd_xent_fwd_bwd(void* logits, const void* labels, void* loss_ro
   return (int)cudaGetLastError();
 }
 extern "C" int tepd_adamw(void* p, const void* g, void* m, void* v, void* p_bf16, long long n, long long n_decay, float lr,
-                          float beta1, float beta2, float eps, float wd, float bc1, float bc2, float gscale, void* stream) {
+                          float beta1, float beta2, float eps, float wd, float bc1, float bc2, float gscale,
+                          const void* hyper, void* stream) {
   if (n % 4 || n_decay % 4) return -2;
-  adamw_kernel<<<grid_for(n / 4, 256), 256, 0, CS(stream)>>>((float*)p, (const float*)g, (float*)m, (float*)v, (bf16*)p_bf16, n, n_decay, lr, beta1, beta2, eps, wd, bc1, bc2, gscale);
+  adamw_kernel<<<grid_for(n / 4, 256), 256, 0, CS(stream)>>>((float*)p, (const float*)g, (float*)m, (float*)v, (bf16*)p_bf16, n, n_decay, lr, beta1, beta2, eps, wd, bc1, bc2, gscale, (const float*)hyper);
   return (int)cudaGetLastError();
 }
 extern "C" int tepd_sgd(void* p, const void* g, void* p_bf16, long long n, float lr, float gscale, void* stream) {
