@@ -1,0 +1,67 @@
+// Cost-based SPMD strategy planner for ONE mesh level.
+//
+// Reference parity: CostSpmdStrategy::StrategyPlanning
+// (xla/service/parallel/cost_spmd_strategy.cc:4782-4916): seed from user annotations -> memory plan
+// (SplitPlanByMemCost) -> critical-node decomposition of the forward graph into sub-graphs with the backward
+// ops attached by op_group (FindSubGraphs/ExpandSubGraphs) -> per sub-graph strategy selection (DP inside
+// cones + ILP across cones == PBQP reductions + branch&bound here) for every (head, tail) strategy pair ->
+// DP across sub-graphs keyed on the separator strategy -> post-process -> record DistSpec on every value.
+// InstAffinityMap's In/Out affinity (variable <-> updated output) and Var/Aux affinity (variable <-> slots)
+// are expressed as edges of the same optimisation problem.
+#pragma once
+#include <map>
+#include <string>
+#include <vector>
+
+#include "cost.h"
+#include "ir.h"
+#include "rules.h"
+
+namespace tepdist {
+
+struct SpmdOptions {
+  int num = 2;                       // devices at this mesh level
+  double var_mem_limit = 150e9;      // VAR_MEM_LIMIT (bytes per device for variables + slots + grads)
+  double cost_factor = 1.0;          // COST_FACTOR (all-to-all weight)
+  int opt_level = 2;                 // OPT_LEVEL: >=3 one whole-graph problem, <3 sub-graph DP
+  bool ignore_annotation = true;     // IGNORE_ANNOTATION
+  bool aux_affinity = false;         // AUX_AFFINITY (variable <-> optimizer slots share a layout)
+  int forward_sub_graph_num = 0;     // FORWARD_SUB_GRAPH_NUM: 0 = cut at every separator
+  double ilp_time_limit_s = 20.0;    // ILP_TIME_LIMIT
+  double replicate_penalty = 1e-3;   // per byte of activation computed redundantly (keeps free splits split)
+  double memory_weight = 1e-4;       // per byte of variable state stored per device
+  HwProfile hw;
+};
+
+struct SpmdStats {
+  double comm_bytes = 0;       // objective: per-device bytes moved by the inserted collectives
+  double solve_seconds = 0;
+  int num_subgraphs = 0;
+  int distinct_subgraphs = 0;  // after structural memoisation
+  int core_nodes_max = 0;      // largest irreducible ("ILP") core
+  bool optimal = true;
+  double var_bytes_per_device = 0;
+  int forced_weight_splits = 0;
+  std::map<std::string, int> collectives;  // kind -> count implied by the chosen plan
+};
+
+struct SpmdPlan {
+  // chosen candidate per node (ins = layout each operand must arrive in, outs = produced layouts)
+  std::vector<Candidate> choice;
+  SpmdStats stats;
+};
+
+// Forward separators: forward values through which ALL forward dataflow passes (the reference's critical nodes,
+// GraphSketch::FindCriticalInsts — FreedomDegree()==0 on the heavy path).
+std::vector<int> FindCriticalNodes(const Graph& g);
+
+// Plans one level and appends the chosen DimStrategy to every value's DistSpec (levels.push_back).
+SpmdPlan PlanSpmdLevel(Graph* g, const SpmdOptions& opt);
+
+// Rule / annotation driven planner (reference FastSpmdStrategy, RULE_MODE=true): propagate the user's
+// split / replicate annotations with InferGraph, everything undecided stays replicated.
+SpmdPlan PlanSpmdByRules(Graph* g, const SpmdOptions& opt);
+
+std::string DumpStrategies(const Graph& g, const SpmdPlan& plan);  // "strategies.txt" artefact
+
+}  // namespace tepdist

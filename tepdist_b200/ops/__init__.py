@@ -331,8 +331,7 @@ def adamw_step(p: torch.Tensor, g: torch.Tensor, m: torch.Tensor, v: torch.Tenso
         if p_bf16 is not None:
             p_bf16.copy_(p.to(p_bf16.dtype))
         return
-    assert p_bf16 is not None
-    _check(lib().tepd_adamw(p.data_ptr(), g.data_ptr(), m.data_ptr(), v.data_ptr(), p_bf16.data_ptr(), n, n_decay,
+    _check(lib().tepd_adamw(p.data_ptr(), g.data_ptr(), m.data_ptr(), v.data_ptr(), _p(p_bf16), n, n_decay,
                             lr, beta1, beta2, eps, wd, bc1, bc2, grad_scale, _p(hyper), _stream()), "adamw")
     _count()
 

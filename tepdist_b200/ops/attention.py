@@ -1,7 +1,7 @@
 """Fused attention op wrappers (kernels in csrc/attention_sm100.cu).
 
 Tensors use the "bshd" convention: q/k/v are views [B, S, H, D] (arbitrary batch/seq/head strides, D
-contiguous) — typically slices of the fused qkv projection output [B, S, 3, H, D]; the output is a
+contiguous) — typically slices of the fused qkv projection output [B, S, H, 3, D] (heads-major); the output is a
 contiguous [B, S, H, D] tensor, i.e. already the [tokens, hidden] input of the output projection.
 """
 from __future__ import annotations
@@ -48,13 +48,13 @@ def attention_fwd(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, scale: floa
 
 def attention_bwd(do: torch.Tensor, q, k, v, o, lse, scale: float | None = None, causal: bool = True,
                   dqkv_out: torch.Tensor | None = None):
-    """Returns (dq, dk, dv) as [B,S,H,D] views (of ``dqkv_out`` [B,S,3,H,D] when given)."""
+    """Returns (dq, dk, dv) as [B,S,H,D] views (of ``dqkv_out`` [B,S,H,3,D] when given)."""
     B, S, H, D = q.shape
     if scale is None:
         scale = 1.0 / math.sqrt(D)
     if dqkv_out is None:
-        dqkv_out = torch.empty(B, S, 3, H, D, dtype=q.dtype, device=q.device)
-    dq, dk, dv = dqkv_out[:, :, 0], dqkv_out[:, :, 1], dqkv_out[:, :, 2]
+        dqkv_out = torch.empty(B, S, H, 3, D, dtype=q.dtype, device=q.device)
+    dq, dk, dv = dqkv_out[:, :, :, 0], dqkv_out[:, :, :, 1], dqkv_out[:, :, :, 2]
     if not q.is_cuda:
         _, _, p = _ref_fwd(q, k, v, scale, causal)
         dof = do.float().permute(0, 2, 1, 3)

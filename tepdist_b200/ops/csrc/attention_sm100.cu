@@ -2,7 +2,7 @@
 //   S = Q K^T            tcgen05.mma  (A = Q  K-major, B = K  K-major)   -> TMEM (double buffered)
 //   P = online softmax   8 softmax warps read S with tcgen05.ld (two threads per query row, 64 cols each)
 //   O += P V             tcgen05.mma  (A = P  K-major from smem, B = V MN-major) -> TMEM -> registers
-// Q/K/V are read straight out of the fused qkv projection buffer [B, S, 3, H, D] with 4-D TMA maps
+// Q/K/V are read straight out of the fused qkv projection buffer [B, S, H, 3, D] (heads-major) with 4-D TMA maps
 // (no head-split transposes), O is written as [B, S, H, D] so it feeds the output projection GEMM.
 // The reference gets attention from XLA-fused batched dots + softmax fusions;
 // this kernel is the B200-native replacement.

@@ -355,6 +355,13 @@ __global__ void __launch_bounds__(512) xent_fwd_bwd_kernel(bf16* __restrict__ lo
 // master fp32 params, fp32 grads (already summed/averaged), fp32 m/v; writes the bf16 compute copy.
 // wd_mask: per-"segment" weight decay is encoded by the caller splitting the flat buffer into a decayed
 // prefix [0, n_decay) and a non-decayed suffix.
+__device__ __forceinline__ void adamw_one(float& p, float g, float& m, float& v, float lr, float beta1, float beta2,
+                                          float eps, float decay, float bc1, float bc2) {
+  m = beta1 * m + (1.f - beta1) * g;
+  v = beta2 * v + (1.f - beta2) * g * g;
+  const float mh = m / bc1, vh = v / bc2;
+  p -= lr * (mh / (sqrtf(vh) + eps) + decay * p);
+}
 __global__ void adamw_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
                              float* __restrict__ v, bf16* __restrict__ p_bf16, size_t n, size_t n_decay, float lr,
                              float beta1, float beta2, float eps, float wd, float bc1, float bc2, float gscale,
@@ -369,23 +376,26 @@ __global__ void adamw_kernel(float* __restrict__ p, const float* __restrict__ g,
     float4 vv = reinterpret_cast<float4*>(v)[i];
     float pa[4] = {pp.x, pp.y, pp.z, pp.w}, ga[4] = {gg.x, gg.y, gg.z, gg.w};
     float ma[4] = {mm.x, mm.y, mm.z, mm.w}, va[4] = {vv.x, vv.y, vv.z, vv.w};
-    const float decay = (i * 4 < n_decay) ? wd : 0.f;
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const float gr = ga[j] * gscale;
-      ma[j] = beta1 * ma[j] + (1.f - beta1) * gr;
-      va[j] = beta2 * va[j] + (1.f - beta2) * gr * gr;
-      const float mh = ma[j] / bc1, vh = va[j] / bc2;
-      pa[j] -= lr * (mh / (sqrtf(vh) + eps) + decay * pa[j]);
-    }
+    for (int j = 0; j < 4; ++j)
+      adamw_one(pa[j], ga[j] * gscale, ma[j], va[j], lr, beta1, beta2, eps, (i * 4 + j < n_decay) ? wd : 0.f, bc1, bc2);
     reinterpret_cast<float4*>(p)[i] = make_float4(pa[0], pa[1], pa[2], pa[3]);
     reinterpret_cast<float4*>(m)[i] = make_float4(ma[0], ma[1], ma[2], ma[3]);
     reinterpret_cast<float4*>(v)[i] = make_float4(va[0], va[1], va[2], va[3]);
-    __nv_bfloat162 lo = __floats2bfloat162_rn(pa[0], pa[1]), hi = __floats2bfloat162_rn(pa[2], pa[3]);
-    uint2 u;
-    u.x = *reinterpret_cast<uint32_t*>(&lo);
-    u.y = *reinterpret_cast<uint32_t*>(&hi);
-    reinterpret_cast<uint2*>(p_bf16)[i] = u;
+    if (p_bf16) {
+      __nv_bfloat162 lo = __floats2bfloat162_rn(pa[0], pa[1]), hi = __floats2bfloat162_rn(pa[2], pa[3]);
+      uint2 u;
+      u.x = *reinterpret_cast<uint32_t*>(&lo);
+      u.y = *reinterpret_cast<uint32_t*>(&hi);
+      reinterpret_cast<uint2*>(p_bf16)[i] = u;
+    }
+  }
+  // scalar tail (n not a multiple of 4)
+  for (size_t i = (nvec << 2) + blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    float pa = p[i], ma = m[i], va = v[i];
+    adamw_one(pa, g[i] * gscale, ma, va, lr, beta1, beta2, eps, (i < n_decay) ? wd : 0.f, bc1, bc2);
+    p[i] = pa; m[i] = ma; v[i] = va;
+    if (p_bf16) p_bf16[i] = __float2bfloat16(pa);
   }
 }
 
@@ -489,8 +499,10 @@ extern "C" int tepd_xent_fwd_bwd(void* logits, const void* labels, void* loss_ro
 extern "C" int tepd_adamw(void* p, const void* g, void* m, void* v, void* p_bf16, long long n, long long n_decay, float lr,
                           float beta1, float beta2, float eps, float wd, float bc1, float bc2, float gscale,
                           const void* hyper, void* stream) {
-  if (n % 4 || n_decay % 4) return -2;
-  adamw_kernel<<<grid_for(n / 4, 256), 256, 0, CS(stream)>>>((float*)p, (const float*)g, (float*)m, (float*)v, (bf16*)p_bf16, n, n_decay, lr, beta1, beta2, eps, wd, bc1, bc2, gscale, (const float*)hyper);
+  if ((reinterpret_cast<uintptr_t>(p) | reinterpret_cast<uintptr_t>(g) | reinterpret_cast<uintptr_t>(m) |
+       reinterpret_cast<uintptr_t>(v)) & 15) return -2;
+  if (p_bf16 && (reinterpret_cast<uintptr_t>(p_bf16) & 7)) return -3;
+  adamw_kernel<<<grid_for(n / 4 + 1, 256), 256, 0, CS(stream)>>>((float*)p, (const float*)g, (float*)m, (float*)v, (bf16*)p_bf16, n, n_decay, lr, beta1, beta2, eps, wd, bc1, bc2, gscale, (const float*)hyper);
   return (int)cudaGetLastError();
 }
 extern "C" int tepd_sgd(void* p, const void* g, void* p_bf16, long long n, float lr, float gscale, void* stream) {

@@ -1,12 +1,93 @@
-"""Parallel execution: building per-rank executors from a plan (DP / TP / PP / EP)."""
+"""Parallel execution: plan on rank 0 (the reference's master), dispatch the plan, build per-rank executors."""
 from __future__ import annotations
 
+import json
+from typing import Any, Dict, Optional
+
 import torch
+import torch.distributed as dist
+
+from ..ir import Graph
 
 
-def plan_and_build(graph, trainer, strategy, comm_mode, use_cuda_graph, seed):
-    """Multi-rank build.  strategy: 'auto' | 'dp' | 'tp' | 'pp...' (see planner).  Round-1 minimum: DP."""
+def plan_spmd(graph: Graph, num: int, strategy: str = "auto", options: Optional[Dict[str, Any]] = None):
+    """Run the C++ planner + SPMD transform for one mesh level of `num` devices.
+    Returns (sharded ir.Graph, info dict)."""
+    from .. import _C
+    from ..planner import from_native, merge_client_attrs, to_native
+    options = dict(options or {})
+    g = graph
+    if strategy in ("dp", "tp"):
+        g = Graph.from_dict(graph.to_dict())
+        for n in g.nodes:
+            if n.op == "input":
+                n.attrs["sharding"] = {"0": {"dim": 0 if strategy == "dp" else -1, "num": num}}
+    cg = to_native(g)
+    o = _C.SpmdOptions()
+    o.num = num
+    if strategy in ("dp", "tp"):
+        o.ignore_annotation = False
+    if strategy == "tp":
+        o.var_mem_limit = 1.0  # force every weight to be stored sharded -> tensor parallel
+    for k, v in options.items():
+        if hasattr(o, k):
+            setattr(o, k, v)
+    # "dp" / "rule": annotation-driven rule mode (reference FastSpmdStrategy, RULE_MODE=true): the batch split on the
+    # sample inputs is propagated through the graph, variables stay replicated, gradients come out partial.
+    plan = _C.plan_spmd_by_rules(cg, o) if strategy in ("rule", "dp") else _C.plan_spmd_level(cg, o)
+    cg.split_nums = [num]
+    cg.share_dev = [False]
+    tg, st = _C.spmd_transform(cg, plan, 0, num)
+    buckets = _C.combine_gradient_collectives(tg, int(options.get("bucket_bytes", 64 << 20)))
+    out = from_native(tg)
+    merge_client_attrs(out, graph)
+    tags: Dict[str, int] = {}
+    heavy = ("linear", "linear_dgrad", "matmul", "einsum", "conv2d", "conv2d_dgrad")
+    for i in range(cg.num_nodes()):
+        if cg.node_op(i) not in heavy:
+            continue
+        c = plan.choice[i]
+        w_split = any(cg.node_op(src) == "parameter" and not c.ins[k].is_glue() for k, (src, _) in enumerate(cg.node_inputs(i)))
+        act_split = any(not s.is_glue() for s in list(c.ins) + list(c.outs))
+        kind = "tp" if w_split else ("dp" if act_split else "replicated")
+        if cg.node_op(i) == "einsum" and c.tag == "batch" and w_split:
+            kind = "ep"   # a batch (expert) dim of the weight is split: expert parallel
+        tags[kind] = tags.get(kind, 0) + 1
+    info = {"comm_info": st.comm_info(), "comm_bytes": plan.stats.comm_bytes, "solve_seconds": plan.stats.solve_seconds,
+            "subgraphs": plan.stats.num_subgraphs, "distinct_subgraphs": plan.stats.distinct_subgraphs,
+            "collectives": dict(plan.stats.collectives), "dot_strategies": tags, "grad_buckets": buckets,
+            "strategies_txt": _C.dump_strategies(cg, plan)}
+    return out, info
+
+
+def classify_parallelism(info: Dict[str, Any], num: int) -> str:
+    t = info.get("dot_strategies", {})
+    if not t:
+        return f"replicated{num}"
+    kind = max(t, key=t.get)
+    c = info.get("collectives", {})
+    if kind == "dp" and c.get("reduce_scatter", 0) > c.get("all_reduce", 0):
+        return f"dp{num}+zero1"
+    return f"{kind}{num}"
+
+
+def plan_and_build(graph: Graph, trainer, strategy: str, comm_mode: str, use_cuda_graph: bool, seed: int):
     from ..runtime.executor import Executor
-    from .dp import make_nccl_grad_sync
-    sync = make_nccl_grad_sync()
-    return Executor(graph, trainer.device, seed=seed, grad_sync=sync, use_cuda_graph=use_cuda_graph)
+    from .collectives import CollectiveRunner
+    from .mesh import DeviceMesh
+    world, rank = trainer.world, trainer.rank
+    payload = [None]
+    if rank == 0:
+        sharded, info = plan_spmd(graph, world, strategy)
+        payload[0] = json.dumps({"graph": sharded.to_dict(), "info": {k: v for k, v in info.items() if k != "strategies_txt"}})
+    dist.broadcast_object_list(payload, src=0)   # master -> workers plan dispatch (reference DispatchPlan RPC)
+    d = json.loads(payload[0])
+    sharded = Graph.from_dict(d["graph"])
+    trainer.plan_info.update(d["info"])
+    trainer.plan_info["parallelism"] = classify_parallelism(d["info"], world)
+    mesh = DeviceMesh([world], [False], rank=rank, world=world)
+    mesh.build_process_groups()
+    trainer.mesh = mesh
+    runner = CollectiveRunner(mesh)
+    return Executor(sharded, trainer.device, seed=seed, use_cuda_graph=use_cuda_graph, collective=runner,
+                    coords=mesh.coords())

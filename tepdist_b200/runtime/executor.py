@@ -34,11 +34,21 @@ def torch_dtype(name: str, device: torch.device) -> torch.dtype:
     return _TORCH_DTYPE[name]
 
 
+def shard_of(t: torch.Tensor, attrs: Dict[str, Any], coords: Dict[int, int]) -> torch.Tensor:
+    """Slice a full tensor down to this rank's shard following the shard_dims/nums/levels a transform recorded."""
+    dims, nums, lvls = attrs.get("shard_dims", []), attrs.get("shard_nums", []), attrs.get("shard_levels", [])
+    for d, n, l in zip(dims, nums, lvls):
+        sz = t.shape[d] // n
+        t = t.narrow(d, coords.get(int(l), 0) * sz, sz)
+    return t
+
+
 class VariableStore:
     """Flat device-resident storage for all variables of a graph (+ grads and optimizer slots)."""
 
-    def __init__(self, graph: Graph, device: torch.device, seed: int = 0, shard_spec: Optional[Dict[int, Any]] = None):
+    def __init__(self, graph: Graph, device: torch.device, seed: int = 0, coords: Optional[Dict[int, int]] = None):
         self.device = device
+        self.coords = coords or {}
         params = graph.params()
         # decayed variables first so the fused AdamW kernel can use a prefix length
         params = sorted(params, key=lambda n: (not n.attrs.get("decay", True), n.id))
@@ -65,8 +75,14 @@ class VariableStore:
         self.compute = (torch.zeros(self.total, dtype=torch.bfloat16, device=device)
                         if device.type == "cuda" else None)
         self.names = {n.id: n.name for n in params}
+        # optimizer slots (`state` nodes): views into the flat m / v buffers when they have their variable's shape
+        # (fused update path), separate tensors otherwise (e.g. ZeRO-sharded slots of a replicated variable)
+        self.state: Dict[int, torch.Tensor] = {}
+        self._state_nodes = [n for n in graph.nodes if n.op == "state"]
         for n in params:
-            t = init_tensor(n.attrs.get("init", {"kind": "constant", "value": 0.0}), self.shape[n.id], seed, n.name)
+            full = tuple(n.attrs.get("full_shape", self.shape[n.id]))
+            t = init_tensor(n.attrs.get("init", {"kind": "constant", "value": 0.0}), full, seed, n.name)
+            t = shard_of(t, n.attrs, self.coords)   # this rank's shard of the (identically seeded) full tensor
             self.master_view(n.id).copy_(t.to(device))
         self.sync_compute()
 
@@ -74,6 +90,16 @@ class VariableStore:
         if self.m is None:
             self.m = torch.zeros_like(self.master)
             self.v = torch.zeros_like(self.master)
+        for n in self._state_nodes:
+            if n.id in self.state:
+                continue
+            pid = n.attrs.get("slot_of")
+            shape = tuple(n.outputs[0].shape)
+            if pid in self.shape and self.shape[pid] == shape:
+                buf = self.m if n.name.endswith("/m") else self.v
+                self.state[n.id] = self._view(buf, pid)
+            else:
+                self.state[n.id] = torch.zeros(shape, dtype=torch.float32, device=self.device)
 
     def _view(self, buf: torch.Tensor, pid: int) -> torch.Tensor:
         o = self.offset[pid]
@@ -122,10 +148,12 @@ class Executor:
 
     def __init__(self, graph: Graph, device: Optional[torch.device] = None, seed: int = 0,
                  grad_sync: Optional[Callable[[torch.Tensor], None]] = None, use_cuda_graph: bool = False,
-                 collective: Optional[Any] = None, store: Optional[VariableStore] = None):
+                 collective: Optional[Any] = None, store: Optional[VariableStore] = None,
+                 coords: Optional[Dict[int, int]] = None):
         self.g = graph
         self.device = device or torch.device("cuda" if torch.cuda.is_available() else "cpu")
-        self.store = store or VariableStore(graph, self.device, seed)
+        self.coords = coords or {}
+        self.store = store or VariableStore(graph, self.device, seed, self.coords)
         self.grad_sync = grad_sync
         self.collective = collective
         self.step_count = 0
@@ -157,10 +185,26 @@ class Executor:
         self.apply_nodes: List[Node] = [n for n in g.nodes if n.op.startswith("apply_")]
         for n in self.apply_nodes:
             pid = n.inputs[0].node
-            self.grad_binding[n.inputs[1].key()] = pid
+            if g.nodes[pid].op == "parameter":
+                self.grad_binding[n.inputs[1].key()] = pid
         self.first_apply = self.apply_nodes[0].id if self.apply_nodes else None
         if any(n.op == "apply_adamw" for n in self.apply_nodes):
             self.store.ensure_slots()
+        # nodes that (transitively) consume an optimizer output run after the update phase
+        self.post_apply: set = set()
+        for n in g.nodes:
+            if n.op.startswith("apply_") or any(v.node in self.post_apply for v in n.inputs):
+                self.post_apply.add(n.id)
+        # the flat fused update needs every apply node to act on whole variables laid out like the flat buffers
+        def _whole(n):
+            if g.nodes[n.inputs[0].node].op != "parameter":
+                return False
+            return all(g.nodes[v.node].op == "state" and tuple(g.type_of(v).shape) == tuple(g.type_of(n.inputs[0]).shape)
+                       for v in n.inputs[2:])
+        self.fused_apply_ok = all(_whole(n) for n in self.apply_nodes)
+        if not self.fused_apply_ok:
+            self.grad_binding = {}  # general path: gradients flow through the environment, not the flat buffer
+        self.update_target: Dict[Tuple[int, int], int] = {v.key(): var for var, v in g.updates.items()}
         self.ln_stats: Dict[Tuple[Tuple[int, int], Tuple[int, int]], Tuple[torch.Tensor, torch.Tensor]] = {}
         self.input_names = [n.name for n in g.inputs()]
 
@@ -209,28 +253,97 @@ class Executor:
         env: Dict[Tuple[int, int], torch.Tensor] = {}
         self.store.grad.zero_()  # GAInit
         launches0 = ops.launch_count()
-        for n in g.nodes:
-            if n.op == "state":
-                continue
-            if n.id == self.first_apply:
-                if self.grad_sync is not None:
-                    self.grad_sync(self.store.grad)
-                self._fused_apply()
-            if n.op.startswith("apply_"):
-                continue
+
+        def run_node(n: Node) -> None:
             ins = [env[v.key()] for v in n.inputs]
             outs = self._exec(n, ins, feeds)
             for i, t in enumerate(outs):
                 env[(n.id, i)] = t
                 pid = self.grad_binding.get((n.id, i))
-                if pid is not None:  # value is a variable's final gradient: make sure it lands in the flat buffer
+                if pid is not None and self.fused_apply_ok:  # a variable's final gradient lands in the flat buffer
                     gv = self.store.grad_view(pid)
                     if t.data_ptr() != gv.data_ptr():
                         gv.add_(t.reshape(gv.shape).to(gv.dtype))
+                var = self.update_target.get((n.id, i))
+                if var is not None and g.nodes[var].op == "parameter":  # e.g. all-gathered updated shards
+                    dst = self.store.compute_view(var)
+                    if t.data_ptr() != dst.data_ptr():
+                        dst.copy_(t.reshape(dst.shape))
+                        if dst.data_ptr() != self.store.master_view(var).data_ptr() and False:
+                            pass
             for k in self.free_after.get(n.id, ()):
-                env.pop(k, None)
+                if k not in self.grad_binding:
+                    env.pop(k, None)
+
+        for n in g.nodes:
+            if n.op == "state" or n.id in self.post_apply:
+                continue
+            run_node(n)
+        if self.apply_nodes:
+            if self.grad_sync is not None:
+                self.grad_sync(self.store.grad)
+            if self.fused_apply_ok:
+                self._fused_apply()
+                for n in self.apply_nodes:
+                    env[(n.id, 0)] = self.store.compute_view(n.inputs[0].node)
+            else:
+                for n in self.apply_nodes:
+                    self._apply_one(n, env)
+        for n in g.nodes:
+            if n.id in self.post_apply and not n.op.startswith("apply_"):
+                run_node(n)
         self._last_launches = ops.launch_count() - launches0
         return [env[v.key()] for v in g.outputs]
+
+    def _apply_one(self, n: Node, env: Dict[Tuple[int, int], torch.Tensor]) -> None:
+        """General (un-fused) optimizer update of one variable or one shard of it (ZeRO-style plans: the update acts
+        on dynamic_slice(parameter) with sharded slots; the updated shard is all-gathered by a later node)."""
+        g, st, o = self.g, self.store, self.opt
+        grad = env[n.inputs[1].key()].float().contiguous()
+
+        def storage(v: Value, which: str) -> torch.Tensor:
+            """Persistent storage behind `v` (a variable/slot, or this rank's dynamic_slice of one)."""
+            src = g.nodes[v.node]
+            def base(nd):
+                if nd.op == "parameter":
+                    return st.master_view(nd.id) if which == "master" else st.compute_view(nd.id)
+                assert nd.op == "state", nd.op
+                return st.state[nd.id]
+            if src.op in ("parameter", "state"):
+                return base(src)
+            assert src.op == "dynamic_slice", src.op
+            b = base(g.nodes[src.inputs[0].node])
+            d, num = int(src.attrs["dim"]), int(src.attrs["num"])
+            sz = b.shape[d] // num
+            return b.narrow(d, self.coords.get(int(src.attrs["level"]), 0) * sz, sz)
+
+        master = storage(n.inputs[0], "master")
+        comp = storage(n.inputs[0], "compute")
+        pm = master if master.is_contiguous() else master.contiguous()
+        pc = comp if (comp.is_contiguous() and comp.dtype == torch.bfloat16) else (
+            torch.empty(pm.shape, dtype=torch.bfloat16, device=pm.device) if pm.is_cuda else None)
+        decay = bool(n.attrs.get("decay", True))
+        if n.op == "apply_adamw":
+            m_st, v_st = storage(n.inputs[2], "state"), storage(n.inputs[3], "state")
+            m = m_st if m_st.is_contiguous() else m_st.contiguous()
+            v = v_st if v_st.is_contiguous() else v_st.contiguous()
+            numel = pm.numel()
+            ops.adamw_step(pm.view(-1), grad.view(-1), m.view(-1), v.view(-1), None if pc is None else pc.view(-1),
+                           numel if decay else 0, o.get("lr", 1e-3), o.get("beta1", 0.9), o.get("beta2", 0.999),
+                           o.get("eps", 1e-8), o.get("weight_decay", 0.0), self.step_count,
+                           hyper=self.hyper if pm.is_cuda else None)
+            if m.data_ptr() != m_st.data_ptr():
+                m_st.copy_(m); v_st.copy_(v)
+            env[(n.id, 1)], env[(n.id, 2)] = m, v
+        else:
+            ops.sgd_step(pm.view(-1), grad.view(-1), None if pc is None else pc.view(-1), o.get("lr", 1e-2))
+        if pm.data_ptr() != master.data_ptr():
+            master.copy_(pm)
+        if pc is not None and pc.data_ptr() != comp.data_ptr():
+            comp.copy_(pc.to(comp.dtype))
+        elif pc is None and comp.data_ptr() != master.data_ptr():
+            comp.copy_(master.to(comp.dtype))
+        env[(n.id, 0)] = comp if comp.is_contiguous() else comp.contiguous()
 
     def _fused_apply(self) -> None:
         st, o = self.store, self.opt
@@ -254,10 +367,14 @@ class Executor:
         dev = self.device
         if op == "parameter":
             return [self.store.compute_view(n.id)]
+        if op == "state":
+            return [self.store.state[n.id]]
         if op == "input":
             t = feeds[n.name]
             if t.device != dev:
                 t = t.to(dev, non_blocking=True)
+            if tuple(t.shape) != tuple(n.outputs[0].shape):  # fed the global batch: take this rank's shard
+                t = shard_of(t, a, self.coords).contiguous()
             return [t]
         if op == "constant":
             return [torch.full(n.outputs[0].shape, a["value"], dtype=torch_dtype(n.outputs[0].dtype, dev), device=dev)]
@@ -317,24 +434,24 @@ class Executor:
             B, S, C3 = qkv.shape
             H = a["heads"]
             D = C3 // 3 // H
-            q5 = qkv.view(B, S, 3, H, D)
-            o, lse = ops.attention_fwd(q5[:, :, 0], q5[:, :, 1], q5[:, :, 2], causal=a.get("causal", True))
+            q5 = qkv.view(B, S, H, 3, D)  # heads-major: a last-dim split is a split over heads
+            o, lse = ops.attention_fwd(q5[:, :, :, 0], q5[:, :, :, 1], q5[:, :, :, 2], causal=a.get("causal", True))
             return [o.view(B, S, H * D), lse]
         if op == "attention_bwd":
             do, qkv, o, lse = ins
             B, S, C3 = qkv.shape
             H = a["heads"]
             D = C3 // 3 // H
-            q5 = qkv.view(B, S, 3, H, D)
-            dqkv = torch.empty(B, S, 3, H, D, dtype=qkv.dtype, device=dev)
-            ops.attention_bwd(do.reshape(B, S, H, D), q5[:, :, 0], q5[:, :, 1], q5[:, :, 2], o.view(B, S, H, D), lse,
-                              causal=a.get("causal", True), dqkv_out=dqkv)
+            q5 = qkv.view(B, S, H, 3, D)
+            dqkv = torch.empty(B, S, H, 3, D, dtype=qkv.dtype, device=dev)
+            ops.attention_bwd(do.reshape(B, S, H, D), q5[:, :, :, 0], q5[:, :, :, 1], q5[:, :, :, 2], o.reshape(B, S, H, D),
+                              lse, causal=a.get("causal", True), dqkv_out=dqkv)
             return [dqkv.view(B, S, C3)]
         if op == "softmax_xent":
             logits, labels = ins
             Vp = logits.shape[-1]
             l2 = logits.reshape(-1, Vp)
-            T = l2.shape[0]
+            T = int(a.get("global_tokens", l2.shape[0]))  # batch-sharded: partial sum of the GLOBAL mean
             total, _rows = ops.xent_fwd_bwd(l2, labels.reshape(-1), a.get("vocab", Vp), 1.0 / T)
             return [total.reshape(()), l2.view(logits.shape)]
         return self._exec_generic(n, ins)
@@ -365,7 +482,9 @@ class Executor:
         if op in ("reduce_sum", "reduce_mean", "reduce_max"):
             axes = tuple(a["axes"])
             if op == "reduce_sum": r = x.float().sum(axes, keepdim=a.get("keepdims", False))
-            elif op == "reduce_mean": r = x.float().mean(axes, keepdim=a.get("keepdims", False))
+            elif op == "reduce_mean":
+                if "mean_divisor" in a: r = x.float().sum(axes, keepdim=a.get("keepdims", False)) / float(a["mean_divisor"])
+                else: r = x.float().mean(axes, keepdim=a.get("keepdims", False))
             else: r = x.float().amax(axes, keepdim=a.get("keepdims", False))
             return [r.to(torch_dtype(n.outputs[0].dtype, self.device))]
         if op == "reshape": return [x.reshape(n.outputs[0].shape)]
@@ -443,5 +562,7 @@ class Executor:
             return [(x / (H * W)).view(N, C, 1, 1).expand(N, C, H, W).contiguous()]
         if op in ("all_reduce", "all_gather", "reduce_scatter", "all_to_all", "dynamic_slice", "send", "recv"):
             assert self.collective is not None, f"collective op {op} without a communicator"
-            return self.collective.run(n, ins)
+            pid = self.grad_binding.get((n.id, 0))
+            out = self.store.grad_view(pid) if (pid is not None and op in ("all_reduce", "reduce_scatter")) else None
+            return self.collective.run(n, ins, out)
         raise NotImplementedError(op)

@@ -1,0 +1,45 @@
+"""Worker for multi-process CPU (gloo) tests: python tests/dist_worker.py <case> <out.json> under torchrun env."""
+import json
+import os
+import sys
+
+import torch
+import torch.distributed as dist
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+
+
+def case_gpt2(strategy):
+    from tepdist_b200.api import Trainer
+    from tepdist_b200.models.gpt2 import CONFIGS, build_gpt2_graph
+    cfg = CONFIGS["tiny"]
+    g = build_gpt2_graph(cfg, batch=4)
+    tr = Trainer(g, strategy=strategy, device=torch.device("cpu"), use_cuda_graph=False)
+    torch.manual_seed(0)
+    tok = torch.randint(0, cfg.n_vocab, (4, cfg.n_ctx), dtype=torch.int32)
+    lab = torch.roll(tok, -1, 1)
+    losses = [tr.step({"tokens": tok, "labels": lab}) for _ in range(4)]   # global batch fed; ranks take shards
+    return {"losses": losses, "parallelism": tr.plan_info.get("parallelism"), "collectives": tr.plan_info.get("collectives")}
+
+
+def case_mlp(strategy):
+    """examples/smoke_testing-style 2-layer MLP; planner emits a DP shard on CPU/gloo world_size=2 (BASELINE config 1)."""
+    from tepdist_b200.api import Trainer
+    from tepdist_b200.models.smoke import build_mlp_graph
+    g = build_mlp_graph(batch=8)
+    tr = Trainer(g, strategy=strategy, device=torch.device("cpu"), use_cuda_graph=False)
+    torch.manual_seed(0)
+    x, t = torch.randn(8, 16), torch.rand(8, 4)
+    losses = [tr.step({"x": x, "t": t}) for _ in range(5)]
+    return {"losses": losses, "parallelism": tr.plan_info.get("parallelism"), "collectives": tr.plan_info.get("collectives")}
+
+
+if __name__ == "__main__":
+    case, out = sys.argv[1], sys.argv[2]
+    name, _, strat = case.partition(":")
+    res = {"gpt2": case_gpt2, "mlp": case_mlp}[name](strat or "auto")
+    if int(os.environ.get("RANK", "0")) == 0:
+        json.dump(res, open(out, "w"))
+    if dist.is_initialized():
+        dist.barrier()
+        dist.destroy_process_group()

@@ -223,8 +223,8 @@ def check_xent_adam():
 # ------------------------------------------------------------------------------------------ attention
 def _qkv(B, S, H, D, seed=5):
     torch.manual_seed(seed)
-    qkv = torch.randn(B, S, 3, H, D, device="cuda", dtype=torch.bfloat16)
-    return qkv, qkv[:, :, 0], qkv[:, :, 1], qkv[:, :, 2]
+    qkv = torch.randn(B, S, H, 3, D, device="cuda", dtype=torch.bfloat16)  # heads-major fused qkv layout
+    return qkv, qkv[:, :, :, 0], qkv[:, :, :, 1], qkv[:, :, :, 2]
 
 
 def check_attn_fwd():
