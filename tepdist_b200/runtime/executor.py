@@ -86,6 +86,18 @@ class VariableStore:
             self.master_view(n.id).copy_(t.to(device))
         self.sync_compute()
 
+    def grow(self, total: int) -> None:
+        """Pad the flat buffers (bucket/chunk alignment for the sharded optimizer)."""
+        def pad(t):
+            if t is None:
+                return None
+            out = torch.zeros(total, dtype=t.dtype, device=t.device)
+            out[:t.numel()].copy_(t)
+            return out
+        self.master, self.grad, self.m, self.v, self.compute = (pad(x) for x in (self.master, self.grad, self.m, self.v, self.compute))
+        self.total = total
+        self.state.clear()
+
     def ensure_slots(self) -> None:
         if self.m is None:
             self.m = torch.zeros_like(self.master)
@@ -205,8 +217,114 @@ class Executor:
         if not self.fused_apply_ok:
             self.grad_binding = {}  # general path: gradients flow through the environment, not the flat buffer
         self.update_target: Dict[Tuple[int, int], int] = {v.key(): var for var, v in g.updates.items()}
+        self.flat_zero: Optional[Dict[str, Any]] = None
+        if not self.fused_apply_ok and self.collective is not None:
+            self._detect_flat_zero()
         self.ln_stats: Dict[Tuple[Tuple[int, int], Tuple[int, int]], Tuple[torch.Tensor, torch.Tensor]] = {}
         self.input_names = [n.name for n in g.inputs()]
+
+    def _detect_flat_zero(self) -> None:
+        """Recognise the planner's data-parallel optimizer pattern
+              grad -> {reduce_scatter | all_reduce}(level L) -> apply(param or dynamic_slice(param), slots...) [-> all_gather -> update]
+        on every variable and execute it over the FLAT buffers instead of per tensor: bucketed reduce-scatter of the
+        gradient buffer (launched as soon as a bucket's last gradient exists, overlapping the rest of backward), one
+        fused AdamW over the owned chunks, one all-gather of the bf16 parameters per bucket.  This is the combiner
+         taken to its conclusion; the per-tensor collectives of the plan become virtual."""
+        g = self.g
+        skip: set = set()
+        binding: Dict[Tuple[int, int], int] = {}
+        level = num = None
+
+        def param_of(v: Value) -> Optional[int]:
+            nd = g.nodes[v.node]
+            if nd.op == "parameter":
+                return nd.id
+            if nd.op == "dynamic_slice" and g.nodes[nd.inputs[0].node].op == "parameter":
+                skip.add(nd.id)
+                return nd.inputs[0].node
+            return None
+
+        for a in self.apply_nodes:
+            pid = param_of(a.inputs[0])
+            c = g.nodes[a.inputs[1].node]
+            if pid is None or c.op not in ("reduce_scatter", "all_reduce"):
+                return
+            l, k = int(c.attrs["level"]), int(c.attrs["num"])
+            if level is None:
+                level, num = l, k
+            elif (level, num) != (l, k):
+                return
+            binding[c.inputs[0].key()] = pid
+            skip.add(c.id)
+            for v in a.inputs[2:]:
+                nd = g.nodes[v.node]
+                if nd.op == "dynamic_slice":
+                    skip.add(nd.id)
+        if level is None or num <= 1:
+            return
+        # bucket ranges over the flat buffer, aligned so every rank's chunk stays 16-byte aligned
+        st = self.store
+        bucket_elems = int(self.opt.get("bucket_elems", 48 * 1024 * 1024))
+        gran = num * _ALIGN
+        bounds = [0]
+        offs = sorted((st.offset[p], p) for p in st.order)
+        for off, p in offs[1:]:
+            if off - bounds[-1] >= bucket_elems and off % gran == 0:
+                bounds.append(off)
+        total = (st.total + gran - 1) // gran * gran
+        if total != st.total:
+            st.grow(total)
+        bounds.append(total)
+        buckets = [(bounds[i], bounds[i + 1]) for i in range(len(bounds) - 1)]
+        # a bucket is ready once the last producer of any gradient inside it has run
+        ready_at: Dict[int, List[int]] = {}
+        prod_of_param = {pid: key[0] for key, pid in binding.items()}
+        for bi, (s0, e0) in enumerate(buckets):
+            last = max((prod_of_param[p] for off, p in offs if s0 <= off < e0 and p in prod_of_param), default=-1)
+            ready_at.setdefault(last, []).append(bi)
+        self.grad_binding = binding
+        self.flat_zero = {"level": level, "num": num, "skip": skip, "buckets": buckets, "ready_at": ready_at,
+                          "rank": self.coords.get(level, 0)}
+        self.fused_apply_ok = True  # gradients land in the flat buffer again
+
+    def _flat_zero_reduce(self, bi: int, pending: List[Any]) -> None:
+        import torch.distributed as dist
+        fz, st = self.flat_zero, self.store
+        s0, e0 = fz["buckets"][bi]
+        n, r = fz["num"], fz["rank"]
+        chunk = (e0 - s0) // n
+        pg = self.collective.mesh.group(fz["level"])
+        buf = st.grad[s0:e0]
+        own = st.grad[s0 + r * chunk:s0 + (r + 1) * chunk]
+        if buf.is_cuda:
+            pending.append(dist.reduce_scatter_tensor(own, buf, group=pg, async_op=True))
+        else:  # gloo has no reduce-scatter
+            pending.append(dist.all_reduce(buf, group=pg, async_op=True))
+
+    def _flat_zero_apply(self, pending: List[Any]) -> None:
+        import torch.distributed as dist
+        fz, st, o = self.flat_zero, self.store, self.opt
+        for w in pending:
+            w.wait()
+        n, r = fz["num"], fz["rank"]
+        pg = self.collective.mesh.group(fz["level"])
+        works = []
+        for (s0, e0) in fz["buckets"]:
+            chunk = (e0 - s0) // n
+            a, b = s0 + r * chunk, s0 + (r + 1) * chunk
+            nd = min(max(st.n_decay - a, 0), b - a)
+            kind = o.get("kind")
+            comp = None if st.compute is None else st.compute[a:b]
+            if kind == "adamw":
+                ops.adamw_step(st.master[a:b], st.grad[a:b], st.m[a:b], st.v[a:b], comp, nd, o.get("lr", 1e-3),
+                               o.get("beta1", 0.9), o.get("beta2", 0.999), o.get("eps", 1e-8), o.get("weight_decay", 0.0),
+                               self.step_count, hyper=self.hyper if st.master.is_cuda else None)
+            elif kind == "sgd":
+                ops.sgd_step(st.master[a:b], st.grad[a:b], comp, o.get("lr", 1e-2))
+            tgt = st.compute if st.compute is not None else st.master
+            works.append(dist.all_gather_into_tensor(tgt[s0:e0], tgt[a:b], group=pg, async_op=True))
+        for w in works:
+            w.wait()
 
     # ------------------------------------------------------------------ running
     def step(self, feeds: Dict[str, torch.Tensor]) -> List[torch.Tensor]:
@@ -230,7 +348,9 @@ class Executor:
             with torch.cuda.graph(self._graph):
                 self._static_out = self._run(self._static_in)
             self._launches_per_step = self._last_launches
-            return [t.clone() for t in self._static_out]  # the capture step itself does not execute
+            self._graph.replay()  # capture records but does not execute: run the recorded step now
+            ops._count(self._launches_per_step)
+            return self._static_out
         for k, t in feeds.items():
             self._static_in[k].copy_(t, non_blocking=True)
         self._graph.replay()
@@ -275,10 +395,24 @@ class Executor:
                 if k not in self.grad_binding:
                     env.pop(k, None)
 
+        fz = self.flat_zero
+        pending: List[Any] = []
+        if fz is not None and -1 in fz["ready_at"]:
+            for bi in fz["ready_at"][-1]:
+                self._flat_zero_reduce(bi, pending)
         for n in g.nodes:
             if n.op == "state" or n.id in self.post_apply:
                 continue
+            if fz is not None and n.id in fz["skip"]:
+                continue
             run_node(n)
+            if fz is not None and n.id in fz["ready_at"]:
+                for bi in fz["ready_at"][n.id]:
+                    self._flat_zero_reduce(bi, pending)   # overlaps with the remaining backward kernels
+        if fz is not None:
+            self._flat_zero_apply(pending)
+            self._last_launches = ops.launch_count() - launches0
+            return [env[v.key()] for v in g.outputs]
         if self.apply_nodes:
             if self.grad_sync is not None:
                 self.grad_sync(self.store.grad)
