@@ -15,6 +15,7 @@ struct State {
   std::vector<PBQP::Vec> cost;
   std::vector<std::map<int, PBQP::Mat>> adj;
   std::vector<char> alive;
+  double constant = 0;  // cost already committed by R0 eliminations and fixed nodes
 };
 
 struct Elim {  // how to recover the choice of an eliminated node
@@ -66,6 +67,7 @@ void Reduce(State& s, std::vector<Elim>& stack) {
           if (s.cost[u][i] < s.cost[u][best]) best = i;
         e.fixed = best;
         stack.push_back(e);
+        s.constant = sat(s.constant, s.cost[u][best]);
         s.alive[u] = 0;
         progress = true;
       } else if (deg == 1) {
@@ -135,6 +137,7 @@ double LowerBound(const State& s) {
 }
 
 void FixNode(State& s, int u, int opt) {
+  s.constant = sat(s.constant, s.cost[u][opt]);
   for (auto& kv : s.adj[u]) {
     const int v = kv.first;
     for (int j = 0; j < (int)s.cost[v].size(); ++j) s.cost[v][j] = sat(s.cost[v][j], kv.second[opt][j]);
@@ -175,46 +178,74 @@ PBQP::Result PBQP::Solve(double time_limit_s) {
   const int n = num_nodes();
   res.choice.assign(n, 0);
   if (n == 0) return res;
-  State root{cost_, adj_, std::vector<char>(n, 1)};
-  std::vector<Elim> base_stack;
-  Reduce(root, base_stack);
-  res.reduced_nodes = (int)base_stack.size();
-  for (int u = 0; u < n; ++u) res.core_nodes += root.alive[u] ? 1 : 0;
-
+  State root{cost_, adj_, std::vector<char>(n, 1), 0.0};
+  {
+    State probe = root;
+    std::vector<Elim> st;
+    Reduce(probe, st);
+    res.reduced_nodes = (int)st.size();
+    for (int u = 0; u < n; ++u) res.core_nodes += probe.alive[u] ? 1 : 0;
+  }
   auto t0 = std::chrono::steady_clock::now();
   auto timed_out = [&] {
     return std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count() > time_limit_s;
   };
-
-  // ---- branch & bound over the irreducible core -------------------------------------------
-  double best_cost = kInf * 4;
-  std::vector<Elim> best_stack;
   bool complete = true;
 
-  std::function<void(State&, std::vector<Elim>&, double)> bb = [&](State& s, std::vector<Elim>& stack, double fixed_cost) {
+  // Exact search: reduce (DP), split into connected components (independent sub-problems: this is what keeps a deep
+  // stack of identical layers linear instead of exponential), branch on the highest-degree node of a component.
+  // Returns the optimal cost of `s` if it is < ub (and fills `stack`), else >= ub.
+  std::function<double(State&, std::vector<Elim>&, double)> solve = [&](State& s, std::vector<Elim>& stack, double ub) -> double {
     ++res.bb_nodes;
     Reduce(s, stack);
-    int pick = -1;
-    size_t pick_deg = 0;
+    if (s.constant >= ub) return kInf * 8;
+    std::vector<int> alive;
     for (int u = 0; u < n; ++u)
-      if (s.alive[u] && s.adj[u].size() > pick_deg) { pick = u; pick_deg = s.adj[u].size(); }
-    if (pick < 0) {
-      // everything eliminated: total = sum of the independent (kind 0) minima accumulated in the stack
-      double total = fixed_cost;
-      // recompute by unwinding
-      std::vector<int> ch(n, -1);
-      for (int i = (int)stack.size() - 1; i >= 0; --i) {
-        const Elim& e = stack[i];
-        if (e.kind == 0 || e.kind == 3) ch[e.node] = e.fixed;
-        else if (e.kind == 1) ch[e.node] = e.best1[ch[e.a]];
-        else ch[e.node] = e.best2[ch[e.a]][ch[e.b]];
+      if (s.alive[u]) alive.push_back(u);
+    if (alive.empty()) return s.constant;
+    if (s.constant + LowerBound(s) >= ub) return kInf * 8;
+    // connected components
+    std::vector<int> comp(n, -1);
+    int nc = 0;
+    for (int u : alive) {
+      if (comp[u] >= 0) continue;
+      std::vector<int> q{u};
+      comp[u] = nc;
+      while (!q.empty()) {
+        int x = q.back();
+        q.pop_back();
+        for (auto& kv : s.adj[x])
+          if (comp[kv.first] < 0) { comp[kv.first] = nc; q.push_back(kv.first); }
       }
-      total = Evaluate(ch);
-      if (total < best_cost) { best_cost = total; best_stack = stack; }
-      return;
+      ++nc;
     }
-    if (LowerBound(s) >= best_cost) return;
-    // order options by local estimate
+    if (nc > 1) {
+      double total = s.constant;
+      std::vector<double> lbs(nc, 0.0);
+      std::vector<State> subs(nc);
+      for (int c = 0; c < nc; ++c) {
+        subs[c] = s;
+        subs[c].constant = 0;
+        for (int u : alive)
+          if (comp[u] != c) subs[c].alive[u] = 0;
+        lbs[c] = LowerBound(subs[c]);
+      }
+      double rest = 0;
+      for (int c = 0; c < nc; ++c) rest += lbs[c];
+      for (int c = 0; c < nc; ++c) {
+        rest -= lbs[c];
+        std::vector<Elim> st;
+        double r = solve(subs[c], st, ub - total - rest);
+        if (r >= kInf) return kInf * 8;
+        total += r;
+        stack.insert(stack.end(), st.begin(), st.end());
+        if (total + rest >= ub) return kInf * 8;
+      }
+      return total;
+    }
+    int pick = alive[0];
+    for (int u : alive)
+      if (s.adj[u].size() > s.adj[pick].size()) pick = u;
     std::vector<std::pair<double, int>> order;
     for (int i = 0; i < (int)s.cost[pick].size(); ++i) {
       double est = s.cost[pick][i];
@@ -226,31 +257,38 @@ PBQP::Result PBQP::Solve(double time_limit_s) {
       order.push_back({est, i});
     }
     std::sort(order.begin(), order.end());
-    bool first = true;
+    double best = ub;
+    std::vector<Elim> best_stack;
+    bool found = false, first = true;
     for (auto& oi : order) {
       if (oi.first >= kInf) continue;
-      if (!first && timed_out()) { complete = false; break; }  // RN fallback: keep only the greedy branch
+      if (!first && timed_out()) { complete = false; break; }  // past the time limit only the greedy branch is taken
       first = false;
       State c = s;
-      std::vector<Elim> st = stack;
+      std::vector<Elim> st;
       Elim e{pick, 3};
       e.fixed = oi.second;
       st.push_back(e);
       FixNode(c, pick, oi.second);
-      bb(c, st, fixed_cost);
+      double r = solve(c, st, best);
+      if (r < best) { best = r; best_stack = std::move(st); found = true; }
     }
+    if (!found) return kInf * 8;
+    stack.insert(stack.end(), best_stack.begin(), best_stack.end());
+    return best;
   };
-  std::vector<Elim> stack0 = base_stack;
-  bb(root, stack0, 0);
-  res.optimal = complete;
 
-  // ---- unwind -------------------------------------------------------------------------------
+  std::vector<Elim> stack;
+  double total = solve(root, stack, kInf * 4);
+  res.optimal = complete;
   std::vector<int> ch(n, 0);
-  for (int i = (int)best_stack.size() - 1; i >= 0; --i) {
-    const Elim& e = best_stack[i];
-    if (e.kind == 0 || e.kind == 3) ch[e.node] = e.fixed;
-    else if (e.kind == 1) ch[e.node] = e.best1[ch[e.a]];
-    else ch[e.node] = e.best2[ch[e.a]][ch[e.b]];
+  if (total < kInf * 4) {
+    for (int i = (int)stack.size() - 1; i >= 0; --i) {
+      const Elim& e = stack[i];
+      if (e.kind == 0 || e.kind == 3) ch[e.node] = e.fixed;
+      else if (e.kind == 1) ch[e.node] = e.best1[ch[e.a]];
+      else ch[e.node] = e.best2[ch[e.a]][ch[e.b]];
+    }
   }
   res.choice = ch;
   res.cost = Evaluate(ch);

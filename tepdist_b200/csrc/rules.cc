@@ -120,12 +120,12 @@ void MatmulRule(Ctx& c, const RuleOptions& opt) {
   const int ra = a.rank(), rb = b.rank(), ro = o.rank();
   const int am = ta ? ra - 1 : ra - 2, ak = ta ? ra - 2 : ra - 1;
   const int bk = tb ? rb - 1 : rb - 2, bn = tb ? rb - 2 : rb - 1;
-  if (!opt.save_variable_mem)
-    for (int d = 0; d < ro - 2; ++d) {  // batch dims (leading, right-aligned between operands)
+  for (int d = 0; d < ro - 2; ++d) {  // batch dims (leading, right-aligned between operands)
       int da = d - (ro - ra), db = d - (ro - rb);
       DS sa = (da >= 0 && da < ra - 2) ? c.S(da) : c.G();
       DS sb = (db >= 0 && db < rb - 2) ? c.S(db) : c.G();
       if (sa.is_glue() && sb.is_glue()) continue;
+      if (opt.save_variable_mem && (sa.is_glue() || sb.is_glue())) continue;
       c.add({sa, sb}, {c.S(d)}, "batch");
     }
   c.add({c.S(ak), c.S(bk)}, {c.P()}, "contract");
@@ -146,7 +146,9 @@ void EinsumRule(Ctx& c, const RuleOptions& opt) {
     int pa = (int)ia.find(l), pb = (int)ib.find(l), po = (int)out.find(l);
     bool in_a = pa != (int)std::string::npos, in_b = pb != (int)std::string::npos, in_o = po != (int)std::string::npos;
     if (in_a && in_b && in_o) {
-      if (!opt.save_variable_mem) c.add({c.S(pa), c.S(pb)}, {c.S(po)}, "batch");
+      // a batch label shards BOTH operands (e.g. the expert dim of an MoE weight): it never leaves a weight
+      // replicated, so the memory-save list does not suppress it (this is how expert parallelism survives)
+      c.add({c.S(pa), c.S(pb)}, {c.S(po)}, "batch");
     } else if (in_a && in_b) {
       c.add({c.S(pa), c.S(pb)}, {c.P()}, "contract");
     } else if (in_a && in_o) {
@@ -396,6 +398,12 @@ std::vector<Candidate> EnumerateCandidates(const Graph& g, const Node& n, int nu
   else if (op == "batchnorm_bwd") BatchNormBwdRule(c);
   else if (op == "maxpool2d" || op == "maxpool2d_bwd" || op == "global_avgpool" || op == "global_avgpool_bwd") Pool4dRule(c);
   else if (op == "apply_adamw" || op == "apply_sgd") ApplyRule(c);
+  else if (op == "moe_dispatch_mask" || op == "moe_dispatch_mask_bwd") {  // gating is independent per token group
+    bool ok = true;
+    for (int i = 0; i < c.nin(); ++i) ok &= c.divisible(c.in(i), 0);
+    if (ok) c.add(std::vector<DS>(c.nin(), c.S(0)), {c.S(0)}, "group");
+    c.add_glue();
+  }
   else c.add_glue();  // unknown op: replicated only (safe)
   return std::move(c.out);
 }

@@ -322,13 +322,14 @@ SpmdPlan PlanSpmdLevel(Graph* gp, const SpmdOptions& opt) {
   auto sep_options = [&](int nid) {
     std::vector<DimStrategy> o;
     for (auto& c : p.cands[nid])
-      if (std::find(o.begin(), o.end(), c.outs[0]) == o.end() && !c.outs[0].partial) o.push_back(c.outs[0]);
+      if (std::find(o.begin(), o.end(), c.outs[0]) == o.end()) o.push_back(c.outs[0]);
     return o;
   };
   std::vector<std::vector<DimStrategy>> sopt(seps.size());
   for (size_t k = 0; k < seps.size(); ++k) sopt[k] = sep_options(seps[k]);
 
   // foreign endpoint layout: mirror of the separator between the two segments when shapes agree
+  auto mirror = [](const DimStrategy* s) { return (s && s->partial) ? DimStrategy::Glue() : (s ? *s : DimStrategy::Glue()); };
   auto foreign_map = [&](int k, const DimStrategy* sh, const DimStrategy* st) {
     std::map<int, DimStrategy> f;
     for (int nid : members[k])
@@ -338,11 +339,11 @@ SpmdPlan PlanSpmdLevel(Graph* gp, const SpmdOptions& opt) {
         if (seg[other] == k) continue;
         DimStrategy s = DimStrategy::Glue();
         ValueRef val{e.prod, e.out_idx};
-        if (seg[other] == k - 1 && sh && k - 1 < (int)seps.size()) {
+        if (seg[other] < k && sh && k - 1 < (int)seps.size()) {  // (gradients of a separator may skip one sub-graph)
           if (other == seps[k - 1] && e.prod == other && e.out_idx == 0) s = *sh;
-          else if (g.type(val).dims == g.nodes[seps[k - 1]].outputs[0].dims) s = *sh;
-        } else if (seg[other] == k + 1 && st && k < (int)seps.size()) {
-          if (g.type(val).dims == g.nodes[seps[k]].outputs[0].dims) s = *st;
+          else if (g.type(val).dims == g.nodes[seps[k - 1]].outputs[0].dims) s = mirror(sh);
+        } else if (seg[other] > k && st && k < (int)seps.size()) {
+          if (g.type(val).dims == g.nodes[seps[k]].outputs[0].dims) s = mirror(st);
         }
         f[other] = s;
       }
@@ -359,8 +360,8 @@ SpmdPlan PlanSpmdLevel(Graph* gp, const SpmdOptions& opt) {
         if (e.prod != nid || seg[e.cons] == k || e.operand < 0) continue;
         DimStrategy s = DimStrategy::Glue();
         ValueRef val{e.prod, e.out_idx};
-        if (seg[e.cons] == k - 1 && sh && g.type(val).dims == g.nodes[seps[k - 1]].outputs[0].dims) s = *sh;
-        else if (seg[e.cons] == k + 1 && st && g.type(val).dims == g.nodes[seps[k]].outputs[0].dims) s = *st;
+        if (seg[e.cons] < k && sh && g.type(val).dims == g.nodes[seps[k - 1]].outputs[0].dims) s = mirror(sh);
+        else if (seg[e.cons] > k && st && g.type(val).dims == g.nodes[seps[k]].outputs[0].dims) s = mirror(st);
         if (e.out_idx == 0) pin[nid] = s;
       }
     }

@@ -189,6 +189,14 @@ class GraphBuilder:
     def one_hot(self, idx: Value, depth: int, dtype: Optional[str] = None, name="one_hot") -> Value:
         return self._n("one_hot", [idx], [TensorType(self.t(idx).shape + (depth,), dtype or self.cd)], {"depth": depth}, name).out()
 
+    def moe_dispatch_mask(self, gates: Value, capacity: int, top_k: int = 2, dtype: Optional[str] = None,
+                          name="dispatch_mask") -> Value:
+        """GShard-style top-k gating with per-expert capacity: gates [G,S,E] (probabilities) -> combine weights
+        [G,S,E,C] (zero where a token is dropped).  (reference: examples/gpt_moe/layers/moe_layers.py top2 gating)"""
+        G_, S_, E = self.t(gates).shape
+        return self._n("moe_dispatch_mask", [gates], [TensorType((G_, S_, E, capacity), dtype or self.cd)],
+                       {"capacity": capacity, "top_k": top_k}, name).out()
+
     # conv stack (Wide-ResNet): NCHW, weights OIHW; executed through cuDNN exactly as the reference does (K9)
     def conv2d(self, x: Value, w: Value, stride: int = 1, padding: int = 0, name="conv") -> Value:
         N, C, H, W = self.t(x).shape
@@ -419,6 +427,9 @@ def backward(b: GraphBuilder, loss: Value) -> Dict[int, Value]:
             push(n.inputs[0], B("maxpool2d_bwd", [dy, n.inputs[0], Value(n.id, 0)], [T(n.inputs[0])], dict(n.attrs), grp).out())
         elif n.op == "global_avgpool":
             push(n.inputs[0], B("global_avgpool_bwd", [dy], [T(n.inputs[0])], {}, grp).out())
+        elif n.op == "moe_dispatch_mask":
+            gts = n.inputs[0]
+            push(gts, B("moe_dispatch_mask_bwd", [dy, gts], [T(gts)], dict(n.attrs), grp).out())
         elif n.op in ("one_hot", "reduce_max"):
             pass
         else:

