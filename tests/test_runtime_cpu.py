@@ -1,0 +1,167 @@
+"""CPU tests for the C++ runtime core: slice utils + sharded Philox init (mirrors the reference's only unit tests,
+pjrt/slice_utils_test.cc and pjrt/initializers_test.cc — SURVEY §4), device mesh, task DAG, scheduler, ServiceEnv."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+from tepdist_b200 import _C
+
+S, G = _C.DimStrategy.split, _C.DimStrategy.glue
+
+
+# ------------------------------------------------------------------------------------------------ slice utils
+def _full(shape):
+    return np.arange(int(np.prod(shape)), dtype=np.float32).reshape(shape)
+
+
+def test_slice_major_minor_and_two_dims():
+    x = _full((4, 6))
+    np.testing.assert_array_equal(_C.slice_copy(x, [4, 6], [S(0, 2)], [1]), x[2:4])           # major dim
+    np.testing.assert_array_equal(_C.slice_copy(x, [4, 6], [S(1, 3)], [2]), x[:, 4:6])        # minor dim
+    np.testing.assert_array_equal(_C.slice_copy(x, [4, 6], [S(0, 2), S(1, 2)], [1, 0]), x[2:4, 0:3])   # two levels / two dims
+    np.testing.assert_array_equal(_C.slice_copy(x, [4, 6], [G()], [0]), x)                    # no dist spec
+
+
+def test_slice_same_dim_twice_and_strided():
+    x = _full((8, 3))
+    # same dim cut by two levels (micro-batch x SPMD): second level acts inside the first level's shard
+    got = _C.slice_copy(x, [8, 3], [S(0, 2), S(0, 2)], [1, 0])
+    np.testing.assert_array_equal(got, x[4:6])
+    # layout-aware split: within every block of 4 rows shard k owns the k-th half
+    got = _C.slice_copy(x, [8, 3], [S(0, 2, 4)], [1])
+    np.testing.assert_array_equal(got, np.concatenate([x[2:4], x[6:8]]))
+    runs = _C.slice_runs([8, 3], [S(0, 2, 4)], [1])
+    assert runs == [(6, 6), (18, 6)]
+
+
+# ------------------------------------------------------------------------------------------------ sharded init
+@pytest.mark.parametrize("kind", ["uniform", "normal", "truncated_normal"])
+@pytest.mark.parametrize("shape,levels,ids", [
+    ([16, 8], [S(0, 4)], [2]),                 # shard on top dim
+    ([6, 10], [S(1, 2)], [1]),                 # shard on inner dim
+    ([7, 13], [G()], [0]),                     # replication, prime sizes
+    ([3, 5, 8], [S(2, 4)], [3]),               # multi-dimension
+    ([12, 6], [S(0, 2), S(1, 3)], [1, 2]),     # two levels
+    ([2, 3], [S(1, 3)], [0]),                  # size < group in the other dim
+])
+def test_sharded_philox_equals_slice_of_full(kind, shape, levels, ids):
+    n = int(np.prod(shape))
+    full = np.asarray(_C.philox_fill(kind, 1234, 0, n, 0.5, 2.0, -1.0, 3.0)).reshape(shape)
+    shard = np.asarray(_C.philox_fill_shard(kind, 1234, shape, levels, ids, 0.5, 2.0, -1.0, 3.0))
+    ref = np.asarray(_C.slice_copy(full, shape, levels, ids))
+    np.testing.assert_array_equal(shard, ref)   # bit exact
+
+
+def test_philox_statistics_and_offsets():
+    a = np.asarray(_C.philox_fill("normal", 7, 0, 200000, 0.0, 1.0, 0, 1))
+    assert abs(a.mean()) < 0.01 and abs(a.std() - 1.0) < 0.01
+    b = np.asarray(_C.philox_fill("normal", 7, 1000, 50, 0.0, 1.0, 0, 1))
+    np.testing.assert_array_equal(b, a[1000:1050])          # any window of the stream is reproducible (multi-thread fill)
+    t = np.asarray(_C.philox_fill("truncated_normal", 9, 0, 100000, 0.0, 1.0, 0, 1))
+    assert np.abs(t).max() <= 2.0
+    u = np.asarray(_C.philox_fill("uniform", 9, 0, 100000, 0, 1, 2.0, 5.0))
+    assert u.min() >= 2.0 and u.max() <= 5.0 and abs(u.mean() - 3.5) < 0.02
+
+
+# ------------------------------------------------------------------------------------------------ device mesh
+def test_comm_dev_manager_groups():
+    m = _C.CommDevManager()
+    # level 0 = micro-batch (shared), level 1 = SPMD(2), level 2 = stage(4); stage rotated outermost
+    m.build([8, 2, 4], [True, False, False], [2, 1, 0], 2, 4)
+    assert m.total_devices() == 8
+    assert m.global_device([5, 1, 3]) == 3 * 2 + 1          # micro id contributes nothing
+    assert m.coords(7) == [0, 1, 3]
+    assert m.group_of(5, 1).devices == [4, 5] and m.rank_in_group(5, 1) == 1
+    assert m.group_of(5, 2).devices == [1, 3, 5, 7] and m.rank_in_group(5, 2) == 2
+    assert len(m.all_groups(1)) == 4 and len(m.all_groups(2)) == 2
+    assert m.worker_of(5) == 1 and m.local_device(5) == 1
+    assert m.group_spans_workers(m.group_of(5, 2)) and not m.group_spans_workers(m.group_of(5, 1))
+
+
+# ------------------------------------------------------------------------------------------------ task DAG + scheduler
+def _spec(S_, M, spmd=1):
+    sp = _C.PipelineSpec()
+    sp.num_stages, sp.num_micro, sp.spmd = S_, M, spmd
+    sp.fwd_seconds = [1e-3] * S_
+    sp.bwd_seconds = [2e-3] * S_
+    sp.ag_seconds = [5e-4] * S_
+    sp.act_bytes = [1e9] * S_
+    sp.boundary_bytes = [8e6] * (S_ - 1)
+    return sp
+
+
+def test_task_dag_structure_and_dominance():
+    sp = _spec(4, 8, 2)
+    dag = _C.build_pipeline_task_dag(sp)
+    kinds = [n.type for n in dag.nodes]
+    assert kinds.count(_C.TaskType.Compute) == 2 * 4 * 8
+    assert kinds.count(_C.TaskType.Send) == kinds.count(_C.TaskType.Recv) == 2 * 3 * 8
+    assert kinds.count(_C.TaskType.GA) == 4 * 8 and kinds.count(_C.TaskType.AG) == 4 and kinds.count(_C.TaskType.GAInit) == 4
+    assert len(dag.topo_order()) == len(dag.nodes)
+    idom = dag.dominance_tree()
+    assert idom[dag.source] == dag.source and all(i >= 0 for i in idom)
+    for n in dag.nodes:
+        if n.type == _C.TaskType.Send:
+            assert abs(n.device - n.peer_device) == sp.spmd       # neighbour stages only
+    assert "digraph" in dag.to_dot()
+
+
+def test_scheduler_is_1f1b_and_bounds_memory():
+    S_, M = 4, 8
+    sp = _spec(S_, M)
+    dag = _C.build_pipeline_task_dag(sp)
+    sch = _C.schedule_tasks(dag, sp, _C.ScheduleOptions())
+    # per-device order respects dependencies
+    pos = {}
+    for dev, tasks in sch.device_tasks.items():
+        for i, t in enumerate(tasks):
+            pos[t] = (dev, i)
+    for n in dag.nodes:
+        for c in n.children:
+            if pos[n.id][0] == pos[c][0]:
+                assert pos[n.id][1] < pos[c][1]
+            assert sch.finish[n.id] <= sch.start[c] + 1e-12
+    # 1F1B: stage s never holds more than S - s forward activations
+    for dev in range(S_):
+        assert sch.peak_bytes[dev] <= (S_ - dev) * 1e9 + 1
+    # pipeline efficiency close to the 1F1B ideal: (M * (f+b)) / ((M + S - 1) * (f+b))
+    ideal = (M + S_ - 1) * 3e-3 + 5e-4
+    assert sch.makespan < ideal * 1.15
+    assert 0 < sch.bubble_ratio < 0.45 and not sch.oom
+    # last stage alternates F and B from the start (steady 1F1B)
+    last = [dag.nodes[t].name for t in sch.device_tasks[S_ - 1] if dag.nodes[t].type == _C.TaskType.Compute]
+    assert last[:4] == ["F.s3.m0", "B.s3.m0", "F.s3.m1", "B.s3.m1"]
+    # GPipe-style (no cap) uses more memory on stage 0
+    o = _C.ScheduleOptions(); o.micro_num_limit = M
+    dag2 = _C.build_pipeline_task_dag(sp)
+    sch2 = _C.schedule_tasks(dag2, sp, o)
+    assert sch2.peak_bytes[0] >= sch.peak_bytes[0]
+    # GC plan: every task's output is released exactly once on its device list
+    rel = [r for n in dag.nodes for r in n.mem_to_release]
+    assert len(rel) == len(set(rel))
+    assert any(n.buffer_id >= 0 for n in dag.nodes if n.type == _C.TaskType.Recv)
+
+
+def test_scheduler_reports_oom():
+    sp = _spec(2, 4)
+    sp.mem_limit = 1.5e9
+    dag = _C.build_pipeline_task_dag(sp)
+    assert _C.schedule_tasks(dag, sp, _C.ScheduleOptions()).oom
+
+
+# ------------------------------------------------------------------------------------------------ config
+def test_service_env_load_order(tmp_path, monkeypatch):
+    env = _C.ServiceEnv.instance()
+    assert env.get_int("OPT_LEVEL") == 2 and env.get_bool("BUFFER_SAVE") and "VAR_MEM_LIMIT" in env.keys()
+    cfg = tmp_path / "config.json"
+    cfg.write_text(json.dumps({"NUM_STAGES": 4, "COST_FACTOR": 2.5, "RULE_MODE": True, "BOGUS": 1}))
+    monkeypatch.setenv("NUM_STAGES", "2")      # env overrides the file, with a warning
+    warnings = env.load(str(cfg))
+    assert env.get_int("NUM_STAGES") == 2 and env.get_double("COST_FACTOR") == 2.5 and env.get_bool("RULE_MODE")
+    assert any("BOGUS" in w for w in warnings) and any("NUM_STAGES" in w for w in warnings)
+    assert "NUM_STAGES=2" in env.dump()
+    env.set("NUM_STAGES", "0"); env.set("RULE_MODE", "false"); env.set("COST_FACTOR", "1.0")
+    with pytest.raises(IndexError):
+        env.get("NOPE")
