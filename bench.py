@@ -69,6 +69,9 @@ def main():
                           "pip install --no-index of /root/reference fails: not installable offline"}))
         return 0
 
+    if os.environ.get("TEPDIST_HANG_DUMP"):
+        import faulthandler
+        faulthandler.dump_traceback_later(int(os.environ["TEPDIST_HANG_DUMP"]), exit=True)
     import torch
     import torch.distributed as dist
     sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))

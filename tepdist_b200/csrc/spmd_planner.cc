@@ -103,6 +103,7 @@ void BuildProblem(Problem& p, SpmdStats* stats) {
       if (IsVariable(n.op)) {
         double b = n.op == "parameter" ? VarStateBytes(g, n, adam) : (double)n.outputs[0].bytes();
         cost += opt.memory_weight * (all_glue ? b : b / opt.num);
+        if (n.op == "parameter" && !all_glue) cost += 32.0 + opt.shard_storage_penalty * b;  // (> the dynamic-slice epsilon)
       } else if (!IsSource(n.op) && all_glue) {
         double b = 0;
         for (auto& t : n.outputs) b += (double)t.bytes();

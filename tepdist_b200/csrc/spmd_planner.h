@@ -29,7 +29,8 @@ struct SpmdOptions {
   int forward_sub_graph_num = 0;     // FORWARD_SUB_GRAPH_NUM: 0 = cut at every separator
   double ilp_time_limit_s = 20.0;    // ILP_TIME_LIMIT
   double replicate_penalty = 1e-3;   // per byte of activation computed redundantly (keeps free splits split)
-  double memory_weight = 1e-4;       // per byte of variable state stored per device
+  double memory_weight = 0.0;        // per byte of variable state stored per device (0: memory only via VAR_MEM_LIMIT)
+  double shard_storage_penalty = 1e-6;  // tie-break: keep variables stored whole unless sharding saves traffic
   HwProfile hw;
 };
 

@@ -46,12 +46,16 @@ def shard_of(t: torch.Tensor, attrs: Dict[str, Any], coords: Dict[int, int]) -> 
 class VariableStore:
     """Flat device-resident storage for all variables of a graph (+ grads and optimizer slots)."""
 
-    def __init__(self, graph: Graph, device: torch.device, seed: int = 0, coords: Optional[Dict[int, int]] = None):
+    def __init__(self, graph: Graph, device: torch.device, seed: int = 0, coords: Optional[Dict[int, int]] = None,
+                 tail: Optional[set] = None):
         self.device = device
         self.coords = coords or {}
+        tail = tail or set()
         params = graph.params()
-        # decayed variables first so the fused AdamW kernel can use a prefix length
-        params = sorted(params, key=lambda n: (not n.attrs.get("decay", True), n.id))
+        # decayed variables first so the fused AdamW kernel can use a prefix length; variables whose optimizer
+        # pattern is irregular (`tail`) go last so the flat sharded-optimizer range stays contiguous
+        params = sorted(params, key=lambda n: (n.id in tail, not n.attrs.get("decay", True), n.id))
+        self.regular_end = 0
         self.order = [n.id for n in params]
         self.offset: Dict[int, int] = {}
         self.shape: Dict[int, Tuple[int, ...]] = {}
@@ -64,8 +68,10 @@ class VariableStore:
             self.cdtype[n.id] = n.outputs[0].dtype
             sz = n.outputs[0].numel()
             off += (sz + _ALIGN - 1) // _ALIGN * _ALIGN
-            if n.attrs.get("decay", True):
+            if n.attrs.get("decay", True) and n.id not in tail:
                 self.n_decay = off
+            if n.id not in tail:
+                self.regular_end = off
         self.total = max(off, _ALIGN)
         f32 = dict(dtype=torch.float32, device=device)
         self.master = torch.zeros(self.total, **f32)
@@ -165,7 +171,9 @@ class Executor:
         self.g = graph
         self.device = device or torch.device("cuda" if torch.cuda.is_available() else "cpu")
         self.coords = coords or {}
-        self.store = store or VariableStore(graph, self.device, seed, self.coords)
+        self._fz_static = self._analyze_flat_zero(graph) if collective is not None else None
+        tail = self._fz_static["irregular_params"] if self._fz_static else set()
+        self.store = store or VariableStore(graph, self.device, seed, self.coords, tail=tail)
         self.grad_sync = grad_sync
         self.collective = collective
         self.step_count = 0
@@ -223,69 +231,122 @@ class Executor:
         self.ln_stats: Dict[Tuple[Tuple[int, int], Tuple[int, int]], Tuple[torch.Tensor, torch.Tensor]] = {}
         self.input_names = [n.name for n in g.inputs()]
 
-    def _detect_flat_zero(self) -> None:
+    @staticmethod
+    def _analyze_flat_zero(g: Graph) -> Optional[Dict[str, Any]]:
         """Recognise the planner's data-parallel optimizer pattern
               grad -> {reduce_scatter | all_reduce}(level L) -> apply(param or dynamic_slice(param), slots...) [-> all_gather -> update]
-        on every variable and execute it over the FLAT buffers instead of per tensor: bucketed reduce-scatter of the
-        gradient buffer (launched as soon as a bucket's last gradient exists, overlapping the rest of backward), one
-        fused AdamW over the owned chunks, one all-gather of the bf16 parameters per bucket.  This is the combiner
-         taken to its conclusion; the per-tensor collectives of the plan become virtual."""
-        g = self.g
+        Variables that follow it ("regular") are executed over the FLAT buffers: bucketed reduce-scatter of the gradient
+        buffer (launched as soon as a bucket's last gradient exists, overlapping the rest of backward), one fused AdamW
+        over the owned chunks, one all-gather of the bf16 parameters per bucket.  This is the combiner taken
+        to its conclusion; the per-tensor collectives of the plan become virtual.  Variables the planner treated
+        differently (stored sharded, gradient re-laid-out by all-to-all, ...) keep the general per-tensor path."""
+        apply_nodes = [n for n in g.nodes if n.op.startswith("apply_")]
+        if not apply_nodes:
+            return None
         skip: set = set()
         binding: Dict[Tuple[int, int], int] = {}
+        regular_apply: set = set()
+        irregular_params: set = set()
         level = num = None
-
-        def param_of(v: Value) -> Optional[int]:
-            nd = g.nodes[v.node]
+        for a in apply_nodes:
+            nd = g.nodes[a.inputs[0].node]
+            local_skip = set()
             if nd.op == "parameter":
-                return nd.id
-            if nd.op == "dynamic_slice" and g.nodes[nd.inputs[0].node].op == "parameter":
-                skip.add(nd.id)
-                return nd.inputs[0].node
-            return None
-
-        for a in self.apply_nodes:
-            pid = param_of(a.inputs[0])
+                pid = nd.id
+            elif nd.op == "dynamic_slice" and g.nodes[nd.inputs[0].node].op == "parameter":
+                pid = nd.inputs[0].node
+                local_skip.add(nd.id)
+            else:
+                pid = None
             c = g.nodes[a.inputs[1].node]
-            if pid is None or c.op not in ("reduce_scatter", "all_reduce"):
-                return
-            l, k = int(c.attrs["level"]), int(c.attrs["num"])
-            if level is None:
-                level, num = l, k
-            elif (level, num) != (l, k):
-                return
+            ok = pid is not None and c.op in ("reduce_scatter", "all_reduce")
+            if ok:
+                # the variable must be stored whole (a shard-shaped parameter is a different ownership scheme)
+                ok = "shard_dims" not in g.nodes[pid].attrs
+            if ok:
+                l, k = int(c.attrs["level"]), int(c.attrs["num"])
+                if level is None:
+                    level, num = l, k
+                ok = (level, num) == (l, k)
+            if not ok:
+                root = nd.id if nd.op == "parameter" else (nd.inputs[0].node if nd.inputs else None)
+                if root is not None and g.nodes[root].op == "parameter":
+                    irregular_params.add(root)
+                continue
             binding[c.inputs[0].key()] = pid
+            regular_apply.add(a.id)
+            skip |= local_skip
             skip.add(c.id)
             for v in a.inputs[2:]:
-                nd = g.nodes[v.node]
-                if nd.op == "dynamic_slice":
-                    skip.add(nd.id)
-        if level is None or num <= 1:
+                if g.nodes[v.node].op == "dynamic_slice":
+                    skip.add(v.node)
+        if level is None or num <= 1 or not regular_apply:
+            return None
+        # post-update nodes (all-gathers of updated shards ...) that only serve regular variables are virtual too
+        anc: Dict[int, set] = {}
+        for n in g.nodes:
+            s_: set = set()
+            if n.op.startswith("apply_"):
+                s_.add(n.id)
+            for v in n.inputs:
+                s_ |= anc.get(v.node, set())
+            if s_:
+                anc[n.id] = s_
+                if not n.op.startswith("apply_") and s_ <= regular_apply:
+                    skip.add(n.id)
+        return {"level": level, "num": num, "skip": skip, "binding": binding, "regular_apply": regular_apply,
+                "irregular_params": irregular_params}
+
+    def _detect_flat_zero(self) -> None:
+        fz = self._fz_static
+        if fz is None:
             return
-        # bucket ranges over the flat buffer, aligned so every rank's chunk stays 16-byte aligned
-        st = self.store
+        g, st = self.g, self.store
+        num = fz["num"]
         bucket_elems = int(self.opt.get("bucket_elems", 48 * 1024 * 1024))
         gran = num * _ALIGN
+        end = (st.regular_end + gran - 1) // gran * gran
+        if end > st.regular_end:
+            if st.regular_end != st.total:   # irregular tail present: cannot pad in the middle -> shift is not
+                # needed because every offset is _ALIGN aligned; pad only matters at the very end of the range
+                end = st.regular_end // gran * gran
+            else:
+                st.grow(end)
+        offs = sorted((st.offset[p], p) for p in st.order if p not in fz["irregular_params"])
+        tail_regular = [(o, p) for o, p in offs if o >= end]          # regular variables beyond the aligned range
+        offs = [(o, p) for o, p in offs if o < end]
+        if not offs:
+            return
         bounds = [0]
-        offs = sorted((st.offset[p], p) for p in st.order)
         for off, p in offs[1:]:
             if off - bounds[-1] >= bucket_elems and off % gran == 0:
                 bounds.append(off)
-        total = (st.total + gran - 1) // gran * gran
-        if total != st.total:
-            st.grow(total)
-        bounds.append(total)
+        bounds.append(end)
         buckets = [(bounds[i], bounds[i + 1]) for i in range(len(bounds) - 1)]
-        # a bucket is ready once the last producer of any gradient inside it has run
-        ready_at: Dict[int, List[int]] = {}
+        binding = {k: v for k, v in fz["binding"].items()}
+        regular_apply = set(fz["regular_apply"])
+        skip = set(fz["skip"])
+        if tail_regular:   # (a partially covered variable cannot be split across ownership schemes)
+            cut = {p for _, p in tail_regular}
+            # variables straddling `end` also fall back
+            for o, p in offs:
+                n_el = 1
+                for d in st.shape[p]:
+                    n_el *= d
+                if o + n_el > end:
+                    cut.add(p)
+            if cut:
+                self._fz_static = None
+                return
         prod_of_param = {pid: key[0] for key, pid in binding.items()}
+        ready_at: Dict[int, List[int]] = {}
         for bi, (s0, e0) in enumerate(buckets):
             last = max((prod_of_param[p] for off, p in offs if s0 <= off < e0 and p in prod_of_param), default=-1)
             ready_at.setdefault(last, []).append(bi)
         self.grad_binding = binding
-        self.flat_zero = {"level": level, "num": num, "skip": skip, "buckets": buckets, "ready_at": ready_at,
-                          "rank": self.coords.get(level, 0)}
-        self.fused_apply_ok = True  # gradients land in the flat buffer again
+        self.flat_zero = {"level": fz["level"], "num": num, "skip": skip, "buckets": buckets, "ready_at": ready_at,
+                          "rank": self.coords.get(fz["level"], 0), "regular_apply": regular_apply}
+        self.fused_apply_ok = True  # regular gradients land in the flat buffer again
 
     def _flat_zero_reduce(self, bi: int, pending: List[Any]) -> None:
         import torch.distributed as dist
@@ -411,6 +472,12 @@ class Executor:
                     self._flat_zero_reduce(bi, pending)   # overlaps with the remaining backward kernels
         if fz is not None:
             self._flat_zero_apply(pending)
+            for n in self.apply_nodes:
+                if n.id not in fz["regular_apply"]:
+                    self._apply_one(n, env)
+            for n in g.nodes:
+                if n.id in self.post_apply and not n.op.startswith("apply_") and n.id not in fz["skip"]:
+                    run_node(n)
             self._last_launches = ops.launch_count() - launches0
             return [env[v.key()] for v in g.outputs]
         if self.apply_nodes:
