@@ -57,7 +57,7 @@ GraphSketch BuildSketch(const Graph& g, bool fine_grained) {
     int r = -1;
     for (auto& v : n.inputs)
       if (rep[v.node] >= 0) { r = rep[v.node]; }
-    if (r < 0) r = last_core;
+    // light ops fed only by sources (re-layouts of variables / inputs) belong with their consumer: the next core
     if (r < 0) pending.push_back(n.id);
     else rep[n.id] = r;
   }
@@ -236,7 +236,9 @@ StagePlanResult PlanStages(Graph* gp, const StagePlanOptions& opt) {
   for (auto& n : g.nodes)
     if (sk.node_of[n.id] >= 0) {
       n.stage = r.sketch_stage[sk.node_of[n.id]];
-      if (n.group >= 0) group_stage[n.group] = n.stage;
+      // the op that OWNS the group decides where its gradient ops run (re-layout collectives inherit their
+      // producer's group id but may sit on the consumer's stage)
+      if (n.group >= 0 && !IsCollective(n.op) && !group_stage.count(n.group)) group_stage[n.group] = n.stage;
     }
   // backward ops: mirror stage of their forward group (logical 2S-1-s, same physical device s)
   for (auto& n : g.nodes)
@@ -244,22 +246,34 @@ StagePlanResult PlanStages(Graph* gp, const StagePlanOptions& opt) {
       auto it = group_stage.find(n.group);
       if (it != group_stage.end()) n.stage = it->second;
     }
-  // sources: stage of their first staged consumer
-  for (auto it = g.nodes.rbegin(); it != g.nodes.rend(); ++it) {
-    Node& n = *it;
-    if (n.stage >= 0) continue;
-    int s = -1;
-    for (int o = 0; o < (int)n.outputs.size(); ++o)
-      for (auto& u : g.users(ValueRef{n.id, o}))
-        if (g.nodes[u.node].stage >= 0) s = s < 0 ? g.nodes[u.node].stage : std::min(s, g.nodes[u.node].stage);
-    n.stage = s;
+  // everything else by fixpoint: compute nodes follow their staged operands (apply nodes, trailing collectives),
+  // sources (variables, optimizer slots, inputs, constants) follow their first staged consumer
+  for (int iter = 0; iter < 8; ++iter) {
+    bool changed = false;
+    for (auto& n : g.nodes) {
+      if (n.stage >= 0 || n.inputs.empty()) continue;
+      int s = -1;
+      bool all = true;
+      for (auto& v : n.inputs) {
+        const Node& p = g.nodes[v.node];
+        if (p.stage < 0) { if (!p.inputs.empty()) all = false; continue; }
+        s = std::max(s, p.stage);
+      }
+      if (all && s >= 0) { n.stage = s; changed = true; }
+    }
+    for (auto it = g.nodes.rbegin(); it != g.nodes.rend(); ++it) {
+      Node& n = *it;
+      if (n.stage >= 0) continue;
+      int s = -1;
+      for (int o = 0; o < (int)n.outputs.size(); ++o)
+        for (auto& u : g.users(ValueRef{n.id, o}))
+          if (g.nodes[u.node].stage >= 0) s = s < 0 ? g.nodes[u.node].stage : std::min(s, g.nodes[u.node].stage);
+      if (s >= 0) { n.stage = s; changed = true; }
+    }
+    if (!changed) break;
   }
-  for (auto& n : g.nodes) {  // anything still unplaced follows its operands (e.g. apply nodes, trailing collectives)
-    if (n.stage >= 0) continue;
-    int s = 0;
-    for (auto& v : n.inputs) s = std::max(s, g.nodes[v.node].stage);
-    n.stage = s;
-  }
+  for (auto& n : g.nodes)
+    if (n.stage < 0) n.stage = 0;
   for (auto& n : g.nodes)
     for (auto& d : n.dist) d.stage = n.stage;
   g.stage_split_ordinal = (int)g.split_nums.size();

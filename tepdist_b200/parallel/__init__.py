@@ -71,8 +71,110 @@ def classify_parallelism(info: Dict[str, Any], num: int) -> str:
     return f"{kind}{num}"
 
 
+def plan_pipeline(graph: Graph, world: int, stages: int, micro: int, options: Optional[Dict[str, Any]] = None):
+    """AutoParallel (config or exploration mode) -> (transformed ir.Graph with stages, plan info, per-device task lists)."""
+    from .. import _C
+    from ..planner import from_native, merge_client_attrs, to_native
+    cg = to_native(graph)
+    ap = _C.AutoParallelOptions()
+    ap.num_devices = world
+    if stages > 0:
+        ap.mode = "config"
+        ap.num_stages, ap.num_micro_batches = stages, micro
+    for k, v in (options or {}).items():
+        if hasattr(ap, k):
+            setattr(ap, k, v)
+    plan = _C.auto_parallel(cg, ap)
+    pr = plan.proposal
+    out = from_native(plan.graph)
+    merge_client_attrs(out, graph)
+    # task graph + 1F1B schedule (C++ runtime core)
+    hw = _C.HwProfile.b200()
+    sp = _C.PipelineSpec()
+    sp.num_stages, sp.num_micro, sp.spmd = pr.stages, pr.micro, pr.spmd
+    fl = list(plan.stage_plan.stage_flops) or [sum(plan.graph.node_flops(i) for i in range(plan.graph.num_nodes()))]
+    sp.fwd_seconds = [f / 3.0 / hw.flops for f in fl]
+    sp.bwd_seconds = [f * 2.0 / 3.0 / hw.flops for f in fl]
+    sp.ag_seconds = [1e-4] * pr.stages
+    sp.act_bytes = [1.0] * pr.stages
+    sp.boundary_bytes = [plan.stage_plan.cut_bytes / max(1, pr.stages - 1) / 2.0] * max(0, pr.stages - 1)
+    dag = _C.build_pipeline_task_dag(sp)
+    sch = _C.schedule_tasks(dag, sp, _C.ScheduleOptions())
+    tasks = {int(dev): [{"type": dag.nodes[t].type.name, "micro": dag.nodes[t].micro, "backward": dag.nodes[t].backward,
+                         "stage": dag.nodes[t].stage, "name": dag.nodes[t].name} for t in lst]
+             for dev, lst in sch.device_tasks.items()}
+    info = {"stages": pr.stages, "micro": pr.micro, "spmd": pr.spmd, "log": plan.log, "eval": repr(plan.eval),
+            "makespan_est": sch.makespan, "bubble_est": sch.bubble_ratio, "cut_bytes": plan.stage_plan.cut_bytes,
+            "stage_method": plan.stage_plan.method, "candidates": list(plan.candidates)}
+    return out, info, tasks
+
+
+class PipelineRunner:
+    """Adapter exposing the Executor-like `step(feeds)` interface for a pipeline stage worker."""
+
+    def __init__(self, worker, tasks, device):
+        self.worker, self.tasks, self.device = worker, tasks, device
+        self.store = worker.exec.store
+
+    def step(self, feeds):
+        from ..runtime.pipeline import run_pipeline_step
+        loss = run_pipeline_step(self.worker, self.tasks, feeds)
+        t = torch.tensor([loss if loss is not None else 0.0], dtype=torch.float32, device=self.device)
+        # the loss lives on the last stage: share it so every rank reports the same number
+        import torch.distributed as dist
+        dist.broadcast(t, src=dist.get_world_size() - 1)
+        return [t.reshape(())]
+
+
+def build_pipeline(graph: Graph, trainer, stages: int, micro: int, comm_mode: str, seed: int):
+    from ..runtime.pipeline import StageWorker
+    from .collectives import CollectiveRunner
+    from .mesh import DeviceMesh
+    world, rank = trainer.world, trainer.rank
+    payload = [None]
+    if rank == 0:
+        g2, info, tasks = plan_pipeline(graph, world, stages, micro)
+        payload[0] = json.dumps({"graph": g2.to_dict(), "info": info, "tasks": tasks})
+    dist.broadcast_object_list(payload, src=0)
+    d = json.loads(payload[0])
+    g2 = Graph.from_dict(d["graph"])
+    info = d["info"]
+    S, M, n = info["stages"], info["micro"], info["spmd"]
+    trainer.plan_info.update({k: v for k, v in info.items() if k != "log"})
+    trainer.plan_info["parallelism"] = f"pp{S}" + (f"xspmd{n}" if n > 1 else "") + f"/micro{M}"
+    levels, shared = [], []
+    if M > 1:
+        levels.append(M); shared.append(True)
+    if n > 1:
+        levels.append(n); shared.append(False)
+    levels.append(S); shared.append(False)
+    stage_level = len(levels) - 1
+    layout = [stage_level] + [l for l in range(len(levels)) if l != stage_level]
+    mesh = DeviceMesh(levels, shared, layout, rank=rank, world=world)
+    mesh.build_process_groups()
+    trainer.mesh = mesh
+    coords = mesh.coords()
+    stage = coords[stage_level]
+    for l, sh in enumerate(shared):
+        if sh:
+            coords[l] = 0
+    base = mesh.base[stage_level]
+    worker = StageWorker(g2, stage, S, M, 0 if M > 1 else -1, trainer.device, rank - base if stage > 0 else None,
+                         rank + base if stage < S - 1 else None, seed=seed, collective=CollectiveRunner(mesh), coords=coords,
+                         comm_mode=comm_mode)
+    worker.plan_transfers()
+    tasks = d["tasks"][str(stage * n)]
+    return PipelineRunner(worker, tasks, trainer.device)
+
+
 def plan_and_build(graph: Graph, trainer, strategy: str, comm_mode: str, use_cuda_graph: bool, seed: int):
     from ..runtime.executor import Executor
+    if strategy.startswith("pp"):   # "pp<S>" or "pp<S>m<M>": config-mode pipeline (NUM_STAGES / NUM_MICRO_BATCHES)
+        body = strategy[2:]
+        S_, _, M_ = body.partition("m")
+        stages = int(S_)
+        micro = int(M_) if M_ else max(2, 2 * stages)
+        return build_pipeline(graph, trainer, stages, micro, comm_mode, seed)
     from .collectives import CollectiveRunner
     from .mesh import DeviceMesh
     world, rank = trainer.world, trainer.rank
@@ -90,4 +192,4 @@ def plan_and_build(graph: Graph, trainer, strategy: str, comm_mode: str, use_cud
     trainer.mesh = mesh
     runner = CollectiveRunner(mesh)
     return Executor(sharded, trainer.device, seed=seed, use_cuda_graph=use_cuda_graph, collective=runner,
-                    coords=mesh.coords())
+                    coords=mesh.coords(), comm_mode=comm_mode)

@@ -1,0 +1,112 @@
+"""Symmetric (peer-mapped) device memory for the fused NVLink kernels (ops/csrc/comm_sm100.cu).
+
+Every rank allocates the same-sized buffer, exports a CUDA IPC handle, and maps all peers' buffers; kernels then
+read / write peer memory directly over NVLink (P2P loads/stores), replacing NCCL for the hot collectives.
+"""
+from __future__ import annotations
+
+import ctypes
+from typing import List, Optional
+
+import torch
+import torch.distributed as dist
+
+from .. import ops
+
+
+class _CudaArray:
+    def __init__(self, ptr: int, nbytes: int):
+        self.__cuda_array_interface__ = {"shape": (nbytes,), "typestr": "|u1", "data": (ptr, False), "version": 3}
+
+
+def _sigs(lib):
+    vp, i, ll, f = ctypes.c_void_p, ctypes.c_int, ctypes.c_longlong, ctypes.c_float
+    pp = ctypes.POINTER(ctypes.c_void_p)
+    table = {
+        "tepd_symm_alloc": [ll, pp], "tepd_symm_free": [vp], "tepd_ipc_get_handle": [vp, vp], "tepd_ipc_open": [vp, pp],
+        "tepd_ipc_close": [vp], "tepd_ipc_handle_size": [],
+        "tepd_symm_barrier": [pp, i, i, vp, vp],
+        "tepd_fused_rs_adamw_ag": [pp, pp, vp, vp, vp, i, ll, ll, ll, f, f, f, f, vp, i, vp],
+        "tepd_p2p_reduce_scatter": [pp, vp, i, ll, ll, i, vp],
+        "tepd_p2p_all_gather": [pp, i, i, ll, ll, i, vp],
+    }
+    for k, a in table.items():
+        fn = getattr(lib, k)
+        fn.restype = ctypes.c_int
+        fn.argtypes = a
+
+
+class SymmetricBuffer:
+    """nbytes of device memory on every rank of `group`, mutually mapped."""
+
+    def __init__(self, nbytes: int, group=None):
+        self.lib = ops.lib()
+        _sigs(self.lib)
+        self.group = group
+        self.world = dist.get_world_size(group)
+        self.rank = dist.get_rank(group)
+        self.nbytes = (nbytes + 255) // 256 * 256
+        p = ctypes.c_void_p()
+        rc = self.lib.tepd_symm_alloc(self.nbytes, ctypes.byref(p))
+        if rc:
+            raise RuntimeError(f"symmetric alloc failed ({rc})")
+        self.local_ptr = p.value
+        hs = self.lib.tepd_ipc_handle_size()
+        h = ctypes.create_string_buffer(hs)
+        rc = self.lib.tepd_ipc_get_handle(self.local_ptr, h)
+        if rc:
+            raise RuntimeError(f"cudaIpcGetMemHandle failed ({rc})")
+        handles: List[Optional[bytes]] = [None] * self.world
+        dist.all_gather_object(handles, bytes(h.raw), group=group)
+        self.ptrs: List[int] = []
+        for r, hb in enumerate(handles):
+            if r == self.rank:
+                self.ptrs.append(self.local_ptr)
+                continue
+            q = ctypes.c_void_p()
+            rc = self.lib.tepd_ipc_open(ctypes.create_string_buffer(hb, hs), ctypes.byref(q))
+            if rc:
+                raise RuntimeError(f"cudaIpcOpenMemHandle(rank {r}) failed ({rc})")
+            self.ptrs.append(q.value)
+        self.ptr_array = (ctypes.c_void_p * self.world)(*self.ptrs)
+
+    def tensor(self, dtype: torch.dtype, numel: Optional[int] = None, offset_bytes: int = 0) -> torch.Tensor:
+        """Zero-copy torch view of the LOCAL buffer."""
+        t = torch.as_tensor(_CudaArray(self.local_ptr + offset_bytes, self.nbytes - offset_bytes), device="cuda")
+        t = t.view(dtype)
+        return t if numel is None else t[:numel]
+
+    def shifted_ptr_array(self, offset_bytes: int):
+        return (ctypes.c_void_p * self.world)(*[p + offset_bytes for p in self.ptrs])
+
+
+class SymmBarrier:
+    """Cross-rank barrier through peer memory (one tiny kernel; CUDA-graph capturable)."""
+
+    def __init__(self, group=None):
+        self.buf = SymmetricBuffer(256, group)
+        self.epoch = torch.zeros(1, dtype=torch.int32, device="cuda")
+
+    def __call__(self, stream: Optional[int] = None) -> None:
+        s = torch.cuda.current_stream().cuda_stream if stream is None else stream
+        rc = self.buf.lib.tepd_symm_barrier(self.buf.ptr_array, self.buf.world, self.buf.rank, self.epoch.data_ptr(), s)
+        if rc:
+            raise RuntimeError(f"symm_barrier failed ({rc})")
+        ops._count()
+
+
+class FusedShardedOptimizer:
+    """reduce-scatter(grad) + AdamW(owned shard) + bf16 all-gather(param) as one peer-memory kernel per bucket."""
+
+    def __init__(self, grad_buf: SymmetricBuffer, param_buf: SymmetricBuffer, group=None):
+        self.g, self.p = grad_buf, param_buf
+        self.barrier = SymmBarrier(group)
+        self.world, self.rank = grad_buf.world, grad_buf.rank
+
+    def step(self, master, m, v, begin: int, end: int, n_decay: int, hyper, beta1, beta2, eps, wd, ctas: int = 0) -> None:
+        rc = self.g.lib.tepd_fused_rs_adamw_ag(self.g.ptr_array, self.p.ptr_array, master.data_ptr(), m.data_ptr(), v.data_ptr(),
+                                               self.world, begin, end, n_decay, beta1, beta2, eps, wd, hyper.data_ptr(), ctas,
+                                               torch.cuda.current_stream().cuda_stream)
+        if rc:
+            raise RuntimeError(f"fused_rs_adamw_ag failed ({rc})")
+        ops._count()

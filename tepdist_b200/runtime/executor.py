@@ -104,6 +104,18 @@ class VariableStore:
         self.total = total
         self.state.clear()
 
+    def make_symmetric(self, group) -> None:
+        """Move the gradient and bf16 parameter buffers into peer-mapped memory (fused NVLink kernels)."""
+        from ..parallel.symm import SymmetricBuffer
+        gb = SymmetricBuffer(self.total * 4, group)
+        pb = SymmetricBuffer(self.total * 2, group)
+        g = gb.tensor(torch.float32, self.total)
+        c = pb.tensor(torch.bfloat16, self.total)
+        g.copy_(self.grad)
+        c.copy_(self.compute)
+        self.grad, self.compute = g, c
+        self.symm_grad, self.symm_param = gb, pb
+
     def ensure_slots(self) -> None:
         if self.m is None:
             self.m = torch.zeros_like(self.master)
@@ -167,16 +179,18 @@ class Executor:
     def __init__(self, graph: Graph, device: Optional[torch.device] = None, seed: int = 0,
                  grad_sync: Optional[Callable[[torch.Tensor], None]] = None, use_cuda_graph: bool = False,
                  collective: Optional[Any] = None, store: Optional[VariableStore] = None,
-                 coords: Optional[Dict[int, int]] = None):
+                 coords: Optional[Dict[int, int]] = None, comm_mode: str = "nccl"):
         self.g = graph
         self.device = device or torch.device("cuda" if torch.cuda.is_available() else "cpu")
         self.coords = coords or {}
+        self.comm_mode = comm_mode
         self._fz_static = self._analyze_flat_zero(graph) if collective is not None else None
         tail = self._fz_static["irregular_params"] if self._fz_static else set()
         self.store = store or VariableStore(graph, self.device, seed, self.coords, tail=tail)
         self.grad_sync = grad_sync
         self.collective = collective
         self.step_count = 0
+        self._tag = 0   # micro-batch tag for per-micro-batch side tables (pipeline interleaves micro-batches)
         self.use_cuda_graph = use_cuda_graph and self.device.type == "cuda"
         self._graph: Optional[torch.cuda.CUDAGraph] = None
         self._static_in: Dict[str, torch.Tensor] = {}
@@ -345,12 +359,19 @@ class Executor:
             ready_at.setdefault(last, []).append(bi)
         self.grad_binding = binding
         self.flat_zero = {"level": fz["level"], "num": num, "skip": skip, "buckets": buckets, "ready_at": ready_at,
-                          "rank": self.coords.get(fz["level"], 0), "regular_apply": regular_apply}
+                          "rank": self.coords.get(fz["level"], 0), "regular_apply": regular_apply, "fused": None}
+        if (self.comm_mode == "fused" and st.master.is_cuda and self.opt.get("kind") == "adamw" and num <= 8):
+            from ..parallel.symm import FusedShardedOptimizer
+            pg = self.collective.mesh.group(fz["level"])
+            st.make_symmetric(pg)
+            self.flat_zero["fused"] = FusedShardedOptimizer(st.symm_grad, st.symm_param, pg)
         self.fused_apply_ok = True  # regular gradients land in the flat buffer again
 
     def _flat_zero_reduce(self, bi: int, pending: List[Any]) -> None:
         import torch.distributed as dist
         fz, st = self.flat_zero, self.store
+        if fz["fused"] is not None:
+            return  # the fused kernel pulls every peer's gradients itself (after the barrier in _flat_zero_apply)
         s0, e0 = fz["buckets"][bi]
         n, r = fz["num"], fz["rank"]
         chunk = (e0 - s0) // n
@@ -368,6 +389,15 @@ class Executor:
         for w in pending:
             w.wait()
         n, r = fz["num"], fz["rank"]
+        if fz["fused"] is not None:
+            fo = fz["fused"]
+            fo.barrier()        # every rank's gradients are complete
+            for (s0, e0) in fz["buckets"]:
+                chunk = (e0 - s0) // n
+                fo.step(st.master, st.m, st.v, s0 + r * chunk, s0 + (r + 1) * chunk, st.n_decay, self.hyper,
+                        o.get("beta1", 0.9), o.get("beta2", 0.999), o.get("eps", 1e-8), o.get("weight_decay", 0.0))
+            fo.barrier()        # every rank's parameter shards have landed everywhere
+            return
         pg = self.collective.mesh.group(fz["level"])
         works = []
         for (s0, e0) in fz["buckets"]:
@@ -436,25 +466,7 @@ class Executor:
         launches0 = ops.launch_count()
 
         def run_node(n: Node) -> None:
-            ins = [env[v.key()] for v in n.inputs]
-            outs = self._exec(n, ins, feeds)
-            for i, t in enumerate(outs):
-                env[(n.id, i)] = t
-                pid = self.grad_binding.get((n.id, i))
-                if pid is not None and self.fused_apply_ok:  # a variable's final gradient lands in the flat buffer
-                    gv = self.store.grad_view(pid)
-                    if t.data_ptr() != gv.data_ptr():
-                        gv.add_(t.reshape(gv.shape).to(gv.dtype))
-                var = self.update_target.get((n.id, i))
-                if var is not None and g.nodes[var].op == "parameter":  # e.g. all-gathered updated shards
-                    dst = self.store.compute_view(var)
-                    if t.data_ptr() != dst.data_ptr():
-                        dst.copy_(t.reshape(dst.shape))
-                        if dst.data_ptr() != self.store.master_view(var).data_ptr() and False:
-                            pass
-            for k in self.free_after.get(n.id, ()):
-                if k not in self.grad_binding:
-                    env.pop(k, None)
+            self._run_node(n, env, feeds)
 
         fz = self.flat_zero
         pending: List[Any] = []
@@ -470,31 +482,60 @@ class Executor:
             if fz is not None and n.id in fz["ready_at"]:
                 for bi in fz["ready_at"][n.id]:
                     self._flat_zero_reduce(bi, pending)   # overlaps with the remaining backward kernels
+        self.run_optimizer(env, feeds, pending if fz is not None else None)
+        self._last_launches = ops.launch_count() - launches0
+        return [env[v.key()] for v in g.outputs]
+
+    def _run_node(self, n: Node, env: Dict[Tuple[int, int], torch.Tensor], feeds: Dict[str, torch.Tensor]) -> None:
+        g = self.g
+        ins = [env[v.key()] for v in n.inputs]
+        outs = self._exec(n, ins, feeds)
+        for i, t in enumerate(outs):
+            env[(n.id, i)] = t
+            pid = self.grad_binding.get((n.id, i))
+            if pid is not None and self.fused_apply_ok:  # a variable's final gradient lands in the flat buffer
+                gv = self.store.grad_view(pid)
+                if t.data_ptr() != gv.data_ptr():
+                    gv.add_(t.reshape(gv.shape).to(gv.dtype))
+            var = self.update_target.get((n.id, i))
+            if var is not None and g.nodes[var].op == "parameter":  # e.g. all-gathered updated shards
+                dst = self.store.compute_view(var)
+                if t.data_ptr() != dst.data_ptr():
+                    dst.copy_(t.reshape(dst.shape))
+        for k in self.free_after.get(n.id, ()):
+            if k not in self.grad_binding:
+                env.pop(k, None)
+
+    def run_optimizer(self, env: Dict[Tuple[int, int], torch.Tensor], feeds: Dict[str, torch.Tensor], pending: Optional[List[Any]] = None) -> None:
+        """Gradient sync + optimizer update + post-update nodes, for whichever execution scheme is active."""
+        g, fz = self.g, self.flat_zero
+        if not self.apply_nodes:
+            return
         if fz is not None:
+            if pending is None:
+                pending = []
+                for bi in range(len(fz["buckets"])):
+                    self._flat_zero_reduce(bi, pending)
             self._flat_zero_apply(pending)
             for n in self.apply_nodes:
                 if n.id not in fz["regular_apply"]:
                     self._apply_one(n, env)
             for n in g.nodes:
                 if n.id in self.post_apply and not n.op.startswith("apply_") and n.id not in fz["skip"]:
-                    run_node(n)
-            self._last_launches = ops.launch_count() - launches0
-            return [env[v.key()] for v in g.outputs]
-        if self.apply_nodes:
-            if self.grad_sync is not None:
-                self.grad_sync(self.store.grad)
-            if self.fused_apply_ok:
-                self._fused_apply()
-                for n in self.apply_nodes:
-                    env[(n.id, 0)] = self.store.compute_view(n.inputs[0].node)
-            else:
-                for n in self.apply_nodes:
-                    self._apply_one(n, env)
+                    self._run_node(n, env, feeds)
+            return
+        if self.grad_sync is not None:
+            self.grad_sync(self.store.grad)
+        if self.fused_apply_ok:
+            self._fused_apply()
+            for n in self.apply_nodes:
+                env[(n.id, 0)] = self.store.compute_view(n.inputs[0].node)
+        else:
+            for n in self.apply_nodes:
+                self._apply_one(n, env)
         for n in g.nodes:
             if n.id in self.post_apply and not n.op.startswith("apply_"):
-                run_node(n)
-        self._last_launches = ops.launch_count() - launches0
-        return [env[v.key()] for v in g.outputs]
+                self._run_node(n, env, feeds)
 
     def _apply_one(self, n: Node, env: Dict[Tuple[int, int], torch.Tensor]) -> None:
         """General (un-fused) optimizer update of one variable or one shard of it (ZeRO-style plans: the update acts
@@ -570,6 +611,8 @@ class Executor:
             return [self.store.compute_view(n.id)]
         if op == "state":
             return [self.store.state[n.id]]
+        if op == "boundary":
+            raise RuntimeError("boundary values are filled by pipeline Recv tasks")
         if op == "input":
             t = feeds[n.name]
             if t.device != dev:
@@ -588,10 +631,10 @@ class Executor:
             return [dwte, dwpe]
         if op == "layernorm":
             y, mean, rstd = ops.layernorm_fwd(ins[0].contiguous(), ins[1], ins[2], a.get("eps", 1e-5))
-            self.ln_stats[(n.inputs[0].key(), n.inputs[1].key())] = (mean, rstd)
+            self.ln_stats[(self._tag, n.inputs[0].key(), n.inputs[1].key())] = (mean, rstd)
             return [y]
         if op == "layernorm_bwd":
-            key = (n.inputs[1].key(), n.inputs[2].key())
+            key = (self._tag, n.inputs[1].key(), n.inputs[2].key())
             if key in self.ln_stats:
                 mean, rstd = self.ln_stats.pop(key)
             else:

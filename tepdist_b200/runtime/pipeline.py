@@ -1,0 +1,279 @@
+"""Pipeline-parallel worker: executes this rank's ordered task list (1F1B schedule from the C++ scheduler).
+
+Reference parity: DAPPLEExecutable::ExecuteTaskList — per task: Input (wait recv),
+Compute (enqueue the stage executable), Output, Send / Recv (NCCL p2p on side streams, event-synchronised), GAInit / GA,
+and the optimizer (AG) on the last micro-batch.  Ranks execute their static lists in lock-step order, which is what
+makes the send/recv pairing deadlock-free (no dynamic dependency tracking at run time).
+"""
+from __future__ import annotations
+
+from typing import Any, Dict, List, Optional, Tuple
+
+import torch
+import torch.distributed as dist
+
+from .. import ops
+from ..ir import Graph, Node, Value
+from .executor import Executor, shard_of
+
+
+def elide_shared_level_collectives(g: Graph, shared_levels: List[int]) -> Tuple[Graph, List[Tuple[int, int]]]:
+    """Collectives on a time-multiplexed (micro-batch) level are not communication: the reduction over micro-batches
+    is gradient accumulation (GA).  Rewire their users to the operand; return the fetches that must be SUMMED over
+    micro-batches (e.g. the loss)."""
+    alias: Dict[Tuple[int, int], Value] = {}
+
+    def res(v: Value) -> Value:
+        while v.key() in alias:
+            v = alias[v.key()]
+        return v
+
+    out = Graph(g.name)
+    out.meta = dict(g.meta)
+    idmap: Dict[int, int] = {}
+    summed: List[Tuple[int, int]] = []
+    for n in g.nodes:
+        if n.op in ("all_reduce", "reduce_scatter", "all_gather", "dynamic_slice") and int(n.attrs.get("level", -1)) in shared_levels \
+                and n.op == "all_reduce":
+            alias[(n.id, 0)] = n.inputs[0]
+            continue
+        ins = []
+        for v in n.inputs:
+            r = res(v)
+            ins.append(Value(idmap[r.node], r.idx))
+        nn = out.add(n.op, ins, n.outputs, dict(n.attrs), n.name, n.group, n.backward)
+        nn.stage = n.stage
+        idmap[n.id] = nn.id
+    for v in g.outputs:
+        r = res(v)
+        if r.key() != v.key():
+            summed.append((idmap[r.node], r.idx))
+        out.outputs.append(Value(idmap[r.node], r.idx))
+    for var, v in g.updates.items():
+        r = res(v)
+        out.updates[idmap[var]] = Value(idmap[r.node], r.idx)
+    for n in out.nodes:
+        if "slot_of" in n.attrs and n.attrs["slot_of"] in idmap:
+            n.attrs["slot_of"] = idmap[n.attrs["slot_of"]]
+    out._next_group = g._next_group
+    return out, summed
+
+
+class StageWorker:
+    """One pipeline stage on one rank."""
+
+    def __init__(self, graph: Graph, stage: int, num_stages: int, num_micro: int, micro_level: int, device: torch.device,
+                 peer_prev: Optional[int], peer_next: Optional[int], seed: int = 0, collective: Any = None,
+                 coords: Optional[Dict[int, int]] = None, comm_mode: str = "nccl"):
+        self.stage, self.S, self.M, self.micro_level = stage, num_stages, num_micro, micro_level
+        self.peer_prev, self.peer_next = peer_prev, peer_next
+        g, self.summed = elide_shared_level_collectives(graph, [micro_level] if num_micro > 1 else [])
+        # this stage's slice of the program: sources it owns + its compute nodes
+        self.full = g
+        mine = [n for n in g.nodes if n.stage == stage]
+        self.sub, self.idmap = self._extract(g, mine)
+        self.exec = Executor(self.sub, device, seed=seed, collective=collective, coords=dict(coords or {}), comm_mode=comm_mode)
+        ex = self.exec
+        self.fwd_nodes = [n for n in self.sub.nodes if not n.backward and n.op not in ("state", "boundary") and n.id not in ex.post_apply]
+        self.bwd_nodes = [n for n in self.sub.nodes if n.backward and n.id not in ex.post_apply and not n.op.startswith("apply_")]
+        self.env: Dict[int, Dict[Tuple[int, int], torch.Tensor]] = {}
+        self.loss_acc: Optional[torch.Tensor] = None
+        # values the optimizer phase reads from the environment (gradients of variables that are not flat-bound, and
+        # anything else the apply / post-apply nodes consume from the per-micro-batch part)
+        pre = {n.id for n in self.fwd_nodes} | {n.id for n in self.bwd_nodes}
+        self.acc_keys = set()
+        for n in self.sub.nodes:
+            if n.id in ex.post_apply or n.op.startswith("apply_"):
+                for v in n.inputs:
+                    if v.node in pre and v.key() not in ex.grad_binding and self.sub.nodes[v.node].op not in ("parameter", "state"):
+                        self.acc_keys.add(v.key())
+        self.acc_env: Dict[Tuple[int, int], torch.Tensor] = {}
+
+    # ------------------------------------------------------------------ sub-graph extraction
+    def _extract(self, g: Graph, mine: List[Node]):
+        """Copy this stage's nodes; values produced on other stages become `boundary` placeholder nodes that are filled
+        by Recv tasks (threaded through intermediate stages by the transfer plan)."""
+        sub = Graph(f"{g.name}.stage{self.stage}")
+        sub.meta = dict(g.meta)
+        idmap: Dict[int, int] = {}
+        self.boundary_in: Dict[Tuple[int, int], int] = {}   # full-graph value -> placeholder node id in sub
+        mine_ids = {n.id for n in mine}
+        for n in mine:
+            ins = []
+            for v in n.inputs:
+                if v.node in mine_ids:
+                    ins.append(Value(idmap[v.node], v.idx))
+                else:
+                    key = v.key()
+                    if key not in self.boundary_in:
+                        bn = sub.add("boundary", [], [g.type_of(v)], {"src": list(key)}, f"recv_{v.node}_{v.idx}", -1,
+                                     g.nodes[v.node].backward)
+                        self.boundary_in[key] = bn.id
+                    ins.append(Value(self.boundary_in[key], 0))
+            nn = sub.add(n.op, ins, n.outputs, dict(n.attrs), n.name, n.group, n.backward)
+            nn.stage = n.stage
+            idmap[n.id] = nn.id
+        for v in g.outputs:
+            if v.node in mine_ids:
+                sub.outputs.append(Value(idmap[v.node], v.idx))
+        for var, v in g.updates.items():
+            if var in mine_ids and v.node in mine_ids:
+                sub.updates[idmap[var]] = Value(idmap[v.node], v.idx)
+        for n in sub.nodes:
+            if "slot_of" in n.attrs and n.attrs["slot_of"] in idmap:
+                n.attrs["slot_of"] = idmap[n.attrs["slot_of"]]
+        return sub, idmap
+
+    # ------------------------------------------------------------------ transfer plan (neighbour-only, B4)
+    def plan_transfers(self) -> None:
+        """For every boundary (s, s+1) and direction, the ordered list of full-graph values that cross it (values
+        consumed k stages away hop through each intermediate stage).  Every rank derives the same lists."""
+        g = self.full
+        fwd: Dict[int, List[Tuple[int, int]]] = {b: [] for b in range(self.S - 1)}   # boundary b: stage b -> b+1
+        bwd: Dict[int, List[Tuple[int, int]]] = {b: [] for b in range(self.S - 1)}   # boundary b: stage b+1 -> b
+        seen = set()
+        for n in g.nodes:
+            if n.op in ("parameter", "state"):
+                continue
+            for v in n.inputs:
+                p = g.nodes[v.node]
+                if p.op in ("parameter", "state", "constant") or p.stage < 0 or n.stage < 0 or p.stage == n.stage:
+                    continue
+                a, b = p.stage, n.stage
+                step = 1 if b > a else -1
+                for s in range(a, b, step):
+                    key = (v.node, v.idx, s, s + step)
+                    if key in seen:
+                        continue
+                    seen.add(key)
+                    (fwd[s] if step > 0 else bwd[s + step]).append(v.key())
+        self.xfer_fwd, self.xfer_bwd = fwd, bwd
+
+    # ------------------------------------------------------------------ phases
+    def _micro_env(self, m: int) -> Dict[Tuple[int, int], torch.Tensor]:
+        return self.env.setdefault(m, {})
+
+    def _run_nodes(self, nodes: List[Node], m: int, feeds: Dict[str, torch.Tensor]) -> None:
+        ex = self.exec
+        ex.coords[self.micro_level] = m
+        ex._tag = m
+        env = self._micro_env(m)
+        for n in nodes:
+            if n.op == "boundary":
+                continue
+            try:
+                ins = [env[v.key()] for v in n.inputs]
+            except KeyError as e:
+                miss = self.sub.nodes[e.args[0][0]]
+                raise RuntimeError(f"stage {self.stage} micro {m}: node {n.id} {n.op} '{n.name}' needs value of node {miss.id} "
+                                   f"{miss.op} '{miss.name}' (backward={miss.backward}, post_apply={miss.id in ex.post_apply}) "
+                                   f"which has not been produced") from e
+            outs = ex._exec(n, ins, feeds)
+            for i, t in enumerate(outs):
+                env[(n.id, i)] = t
+                pid = ex.grad_binding.get((n.id, i))
+                if pid is not None and ex.fused_apply_ok:
+                    gv = ex.store.grad_view(pid)
+                    if t.data_ptr() != gv.data_ptr():
+                        gv.add_(t.reshape(gv.shape).to(gv.dtype))
+                if (n.id, i) in self.acc_keys:   # gradients outside the flat buffer: accumulate over micro-batches (GA)
+                    if (n.id, i) in self.acc_env:
+                        self.acc_env[(n.id, i)] = self.acc_env[(n.id, i)] + t
+                    else:
+                        self.acc_env[(n.id, i)] = t.clone()
+
+    def begin_step(self) -> None:
+        self.exec.step_count += 1
+        self.exec._set_hyper()
+        self.exec.store.grad.zero_()       # GAInit
+        self.env.clear()
+        self.acc_env = {}
+        self.loss_acc = None
+
+    def forward(self, m: int, feeds: Dict[str, torch.Tensor]) -> None:
+        self._run_nodes(self.fwd_nodes, m, feeds)
+
+    def backward(self, m: int, feeds: Dict[str, torch.Tensor]) -> None:
+        self._run_nodes(self.bwd_nodes, m, feeds)
+        env = self._micro_env(m)
+        for v in self.sub.outputs:   # fetches (loss) are summed over micro-batches
+            if v.key() in env:
+                t = env[v.key()].detach().float()
+                self.loss_acc = t.clone() if self.loss_acc is None else self.loss_acc + t
+
+    def release(self, m: int) -> None:
+        """GC: every activation of micro-batch m is dead (its backward ran and its gradients were sent)."""
+        self.env.pop(m, None)
+        self._threaded.pop(m, None)
+
+    def apply(self, feeds: Dict[str, torch.Tensor]) -> None:
+        """AG: gradient sync over the SPMD level (if any) + optimizer + post-update re-layouts, once per step."""
+        self.exec.run_optimizer(self.acc_env, feeds)
+
+    # ------------------------------------------------------------------ p2p
+    def _values_for(self, boundary: int, backward: bool) -> List[Tuple[int, int]]:
+        return (self.xfer_bwd if backward else self.xfer_fwd)[boundary]
+
+    def _lookup(self, m: int, key: Tuple[int, int]) -> torch.Tensor:
+        env = self._micro_env(m)
+        if key[0] in self.idmap:                       # produced here
+            return env[(self.idmap[key[0]], key[1])]
+        return env[(self.boundary_in[key], 0)] if key in self.boundary_in else self._threaded[m][key]
+
+    def send(self, m: int, backward: bool) -> List[Any]:
+        boundary = self.stage - 1 if backward else self.stage
+        peer = self.peer_prev if backward else self.peer_next
+        works = []
+        for key in self._values_for(boundary, backward):
+            t = self._lookup(m, key).contiguous()
+            works.append((dist.isend(t, peer), t))   # keep the payload alive until the send completes
+        return works
+
+    def recv(self, m: int, backward: bool) -> List[Any]:
+        boundary = self.stage if backward else self.stage - 1
+        peer = self.peer_next if backward else self.peer_prev
+        env = self._micro_env(m)
+        works = []
+        dev = self.exec.device
+        from .executor import torch_dtype
+        for key in self._values_for(boundary, backward):
+            tt = self.full.type_of(Value(*key))
+            buf = torch.empty(tt.shape, dtype=torch_dtype(tt.dtype, dev), device=dev)
+            works.append(dist.irecv(buf, peer))
+            if key in self.boundary_in:
+                env[(self.boundary_in[key], 0)] = buf
+            self._threaded.setdefault(m, {})[key] = buf   # may only pass through to the next stage
+        return works
+
+    _threaded: Dict[int, Dict[Tuple[int, int], torch.Tensor]] = {}
+
+
+def run_pipeline_step(worker: StageWorker, task_list: List[Dict[str, Any]], feeds: Dict[str, torch.Tensor]) -> Optional[float]:
+    """Execute one training step by walking this device's ordered task list."""
+    worker.begin_step()
+    worker._threaded = {}
+    pending_recv: Dict[Tuple[int, bool], List[Any]] = {}
+    pending_send: List[Any] = []
+    for t in task_list:
+        kind, m, bwd = t["type"], t["micro"], t["backward"]
+        if kind == "Recv":
+            pending_recv[(m, bwd)] = worker.recv(m, bwd)
+        elif kind == "Input":
+            for w in pending_recv.pop((m, bwd), []):
+                w.wait()
+        elif kind == "Compute":
+            (worker.backward if bwd else worker.forward)(m, feeds)
+            if bwd and worker.stage == 0:
+                worker.release(m)
+        elif kind == "Send":
+            pending_send += worker.send(m, bwd)   # (work, payload) pairs: payloads stay referenced until waited
+            if bwd:
+                worker.release(m)
+        elif kind == "AG":
+            for w, _ in pending_send:
+                w.wait()
+            pending_send = []
+            worker.apply(feeds)
+    for w, _ in pending_send:
+        w.wait()
+    return None if worker.loss_acc is None else float(worker.loss_acc)
