@@ -1,0 +1,96 @@
+"""Distributed (sharded) checkpointing.
+
+Reference parity: every worker writes ONLY its shards (flattened slices in the reference's
+tensor-bundle format; plain tensor files + a JSON manifest here), directories `ckpt_<rank>_of_<n>/`, `max_to_keep`
+rotation with a persisted prefix queue, "lazy save" when requested before the first step, restore by global step
+reading only the slices this rank needs.
+"""
+from __future__ import annotations
+
+import json
+import os
+import shutil
+from typing import Any, Dict, List, Optional
+
+import torch
+
+
+class CheckpointManager:
+    def __init__(self, root: str, rank: int, world: int, max_to_keep: int = 5):
+        self.dir = os.path.join(root, f"ckpt_{rank}_of_{world}")
+        self.rank, self.world, self.max_to_keep = rank, world, max_to_keep
+        os.makedirs(self.dir, exist_ok=True)
+        self.queue_file = os.path.join(self.dir, "checkpoint_queue.json")
+        self.queue: List[int] = json.load(open(self.queue_file)) if os.path.exists(self.queue_file) else []
+        self.lazy_request: Optional[int] = None
+
+    # ------------------------------------------------------------------ save
+    def request_save(self, global_step: int, warmed_up: bool) -> bool:
+        """Returns True if the save can happen now; before the first step it is deferred (lazy save)."""
+        if not warmed_up:
+            self.lazy_request = global_step
+            return False
+        return True
+
+    def save(self, executor, global_step: int, extra: Optional[Dict[str, Any]] = None) -> str:
+        st = executor.store
+        g = executor.g
+        prefix = os.path.join(self.dir, f"step_{global_step}")
+        tmp = prefix + ".tmp"
+        os.makedirs(tmp, exist_ok=True)
+        manifest: Dict[str, Any] = {"global_step": global_step, "rank": self.rank, "world": self.world, "vars": {},
+                                    "step_count": executor.step_count, "extra": extra or {}}
+        tensors: Dict[str, torch.Tensor] = {}
+        for pid in st.order:
+            n = g.nodes[pid]
+            name = st.names[pid]
+            tensors[name] = st.master_view(pid).detach().cpu().reshape(-1).clone()     # flattened shard, as the reference
+            manifest["vars"][name] = {
+                "shard_shape": list(st.shape[pid]), "full_shape": list(n.attrs.get("full_shape", st.shape[pid])),
+                "shard_dims": list(n.attrs.get("shard_dims", [])), "shard_nums": list(n.attrs.get("shard_nums", [])),
+                "shard_levels": list(n.attrs.get("shard_levels", [])), "coords": {str(k): v for k, v in executor.coords.items()},
+            }
+            if st.m is not None:
+                tensors[name + "/m"] = st._view(st.m, pid).detach().cpu().reshape(-1).clone()
+                tensors[name + "/v"] = st._view(st.v, pid).detach().cpu().reshape(-1).clone()
+        torch.save(tensors, os.path.join(tmp, "shards.pt"))
+        json.dump(manifest, open(os.path.join(tmp, "manifest.json"), "w"))
+        if os.path.exists(prefix):
+            shutil.rmtree(prefix)
+        os.replace(tmp, prefix)     # atomic publish
+        self.queue.append(global_step)
+        while len(self.queue) > self.max_to_keep:
+            old = self.queue.pop(0)
+            shutil.rmtree(os.path.join(self.dir, f"step_{old}"), ignore_errors=True)
+        json.dump(self.queue, open(self.queue_file, "w"))
+        self.lazy_request = None
+        return prefix
+
+    def maybe_lazy_save(self, executor) -> Optional[str]:
+        if self.lazy_request is not None:
+            return self.save(executor, self.lazy_request)
+        return None
+
+    # ------------------------------------------------------------------ restore
+    def latest(self) -> Optional[int]:
+        return self.queue[-1] if self.queue else None
+
+    def restore(self, executor, global_step: Optional[int] = None) -> int:
+        step = self.latest() if global_step is None else global_step
+        if step is None:
+            raise FileNotFoundError("no checkpoint to restore")
+        prefix = os.path.join(self.dir, f"step_{step}")
+        manifest = json.load(open(os.path.join(prefix, "manifest.json")))
+        tensors = torch.load(os.path.join(prefix, "shards.pt"))
+        st = executor.store
+        for pid in st.order:
+            name = st.names[pid]
+            meta = manifest["vars"][name]
+            assert tuple(meta["shard_shape"]) == tuple(st.shape[pid]), f"{name}: checkpoint shard shape differs from the current plan"
+            st.master_view(pid).copy_(tensors[name].reshape(st.shape[pid]).to(st.device))
+            if st.m is not None and name + "/m" in tensors:
+                st._view(st.m, pid).copy_(tensors[name + "/m"].reshape(st.shape[pid]).to(st.device))
+                st._view(st.v, pid).copy_(tensors[name + "/v"].reshape(st.shape[pid]).to(st.device))
+        st.sync_compute()
+        executor.step_count = int(manifest.get("step_count", step))
+        return step

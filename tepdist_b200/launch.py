@@ -1,0 +1,58 @@
+"""Server launcher (reference tf_tepdist/launch_worker.sh + config_*worker_template.json).
+
+    python -m tepdist_b200.launch --cluster cluster.json --task-index 0
+
+cluster.json: {"master": {"ip": "...", "port": 2222, "gpu_ids": [0,1,2,3]}, "workers": [{"ip":..., "port":..., "gpu_ids": [...]}]}
+The entry selected by --task-index decides CUDA_VISIBLE_DEVICES and the gRPC endpoint; one process per listed GPU is
+spawned through torch.distributed.run (all entries must list the same number of GPUs, as in the reference).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+
+
+def entry_for(spec: dict, task_index: int) -> dict:
+    entries = [spec["master"]] + list(spec.get("workers", []))
+    counts = {len(e["gpu_ids"]) for e in entries}
+    if len(counts) != 1:
+        raise ValueError("all workers must have equal GPU counts")
+    return entries[task_index]
+
+
+def main(argv=None):
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--cluster", required=True)
+    ap.add_argument("--task-index", type=int, default=0)
+    ap.add_argument("--platform", default="cuda", choices=["cuda", "cpu"])
+    ap.add_argument("--strategy", default="auto")
+    ap.add_argument("--serve-rank", action="store_true", help=argparse.SUPPRESS)
+    ap.add_argument("--ip", default=None)
+    ap.add_argument("--port", type=int, default=None)
+    args = ap.parse_args(argv)
+    spec = json.load(open(args.cluster))
+    e = entry_for(spec, args.task_index)
+    if args.serve_rank:   # inside torchrun: one process per GPU
+        import torch
+        from .rpc.service import serve
+        dev = torch.device("cpu") if args.platform == "cpu" else None
+        serve(args.ip or e["ip"], args.port or e["port"], block=True, strategy=args.strategy, device=dev)
+        return 0
+    env = dict(os.environ, CLUSTER_SPEC=os.path.abspath(args.cluster), FRONTEND="torch")
+    if args.platform == "cuda":
+        env["CUDA_VISIBLE_DEVICES"] = ",".join(str(g) for g in e["gpu_ids"])
+        env.setdefault("NCCL_DEBUG", "WARN")
+    else:
+        env["CUDA_VISIBLE_DEVICES"] = ""
+    n = len(e["gpu_ids"])
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={n}", "--master-addr", "127.0.0.1",
+           "--master-port", str(29400 + args.task_index), "-m", "tepdist_b200.launch", "--cluster", args.cluster,
+           "--task-index", str(args.task_index), "--platform", args.platform, "--strategy", args.strategy, "--serve-rank"]
+    return subprocess.call(cmd, env=env)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -1,0 +1,25 @@
+"""Needs >= 2 GPUs: fused peer-memory optimizer path == NCCL path == single GPU (loss trajectories)."""
+import json
+import os
+import subprocess
+import sys
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
+def test_fused_dp_matches_nccl_and_single(tmp_path):
+    out = str(tmp_path / "o.json")
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
+           "--master-port", "29741", os.path.join(HERE, "multi_gpu_worker.py"), out]
+    pr = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+    assert pr.returncode == 0, pr.stderr[-3000:]
+    r = json.load(open(out))
+    assert r["fused_fused_active"] and not r["nccl_fused_active"]
+    for a, b, c in zip(r["fused"], r["nccl"], r["single"]):
+        assert abs(a - b) < 2e-2 * abs(b) and abs(a - c) < 2e-2 * abs(c), r
+    assert r["fused"][-1] < r["fused"][0]

@@ -1,0 +1,88 @@
+"""CPU tests: client -> gRPC -> service -> planner -> runtime round trip, checkpoint save / rotate / lazy / restore."""
+import json
+import os
+import threading
+
+import torch
+
+from tepdist_b200.models.gpt2 import CONFIGS, build_gpt2_graph
+from tepdist_b200.rpc.client import Client
+from tepdist_b200.rpc.service import serve
+
+
+def _start(tmp_path, **kw):
+    impl, server, port = serve("127.0.0.1", 0, block=False, device=torch.device("cpu"), ckpt_root=str(tmp_path), **kw)
+    return impl, server, Client(f"127.0.0.1:{port}")
+
+
+def test_client_server_training_and_fetch(tmp_path):
+    impl, server, cl = _start(tmp_path)
+    cfg = CONFIGS["tiny"]
+    g = build_gpt2_graph(cfg)
+    r = cl.build_execution_plan(g)
+    assert r["handle"] >= 1
+    torch.manual_seed(0)
+    tok = torch.randint(0, cfg.n_vocab, (cfg.batch, cfg.n_ctx), dtype=torch.int32)
+    lab = torch.roll(tok, -1, 1)
+    cl.transfer_to_server_host("tokens", tok)
+    cl.transfer_to_server_host("labels", lab)
+    cl.transfer_to_server_host("model/wte", shape=[cfg.padded_vocab, cfg.n_embd], dtype="bf16", variable=True)   # shape only
+    losses = [cl.execute_plan()["loss"] for _ in range(3)]           # inputs registered on the server host
+    losses += [cl.execute_plan({"tokens": tok, "labels": lab})["loss"]]
+    assert losses[-1] < losses[0]
+    v = cl.fetch_resource_vars(["model/ln_f/g"])
+    assert v["model/ln_f/g"].shape == (cfg.n_embd,)
+    out = cl.execute_plan({"tokens": tok, "labels": lab}, fetch_vars=["model/ln_f/b"])
+    assert "model/ln_f/b" in out["vars"] and out["duration_ms"] > 0
+    info = cl.server_info()
+    assert info["world"] == 1 and "OPT_LEVEL" in info["config"] and info["steps"] == 5
+    server.stop(0)
+
+
+def test_checkpoint_lazy_save_rotate_restore(tmp_path):
+    impl, server, cl = _start(tmp_path)
+    cfg = CONFIGS["tiny"]
+    cl.build_execution_plan(build_gpt2_graph(cfg), max_to_keep=2)
+    tok = torch.randint(0, cfg.n_vocab, (cfg.batch, cfg.n_ctx), dtype=torch.int32)
+    feeds = {"tokens": tok, "labels": torch.roll(tok, -1, 1)}
+    assert cl.do_remote_save(0)["result"] == "lazy"           # before the first step: deferred
+    l0 = cl.execute_plan(feeds)["loss"]                       # warm-up step performs the lazy save
+    ck = os.path.join(str(tmp_path), "ckpt_0_of_1")
+    assert os.path.isdir(os.path.join(ck, "step_0"))
+    for s in (1, 2, 3):
+        cl.execute_plan(feeds)
+        cl.do_remote_save(s, max_to_keep=2)
+    assert sorted(d for d in os.listdir(ck) if d.startswith("step_")) == ["step_2", "step_3"]      # rotation
+    assert json.load(open(os.path.join(ck, "checkpoint_queue.json"))) == [2, 3]
+    w_before = cl.fetch_resource_vars(["model/h0/mlp/c_fc/w"])["model/h0/mlp/c_fc/w"].clone()
+    l_a = cl.execute_plan(feeds)["loss"]
+    cl.do_remote_restore(3)                                   # takes effect at the next ExecutePlan
+    l_b = cl.execute_plan(feeds)["loss"]
+    assert abs(l_a - l_b) < 1e-6                              # same state => same loss as the step right after save 3
+    manifest = json.load(open(os.path.join(ck, "step_3", "manifest.json")))
+    assert manifest["vars"]["model/h0/mlp/c_fc/w"]["full_shape"] == [4 * cfg.n_embd, cfg.n_embd]
+    server.stop(0)
+
+
+def test_step_pipelining_env(tmp_path, monkeypatch):
+    monkeypatch.setenv("NUM_PARALLEL_RPC_STEPS", "2")
+    impl, server, cl = _start(tmp_path)
+    cfg = CONFIGS["tiny"]
+    cl.build_execution_plan(build_gpt2_graph(cfg))
+    tok = torch.randint(0, cfg.n_vocab, (cfg.batch, cfg.n_ctx), dtype=torch.int32)
+    futs = [cl.execute_plan({"tokens": tok, "labels": torch.roll(tok, -1, 1)}) for _ in range(4)]
+    losses = [f.result()["loss"] for f in futs]
+    assert len(losses) == 4 and losses[-1] < losses[0]
+    server.stop(0)
+
+
+def test_launcher_cluster_spec(tmp_path):
+    from tepdist_b200.launch import entry_for
+    spec = {"master": {"ip": "10.0.0.1", "port": 2222, "gpu_ids": [0, 1]}, "workers": [{"ip": "10.0.0.2", "port": 2223, "gpu_ids": [2, 3]}]}
+    assert entry_for(spec, 1)["port"] == 2223
+    spec["workers"][0]["gpu_ids"] = [2]
+    try:
+        entry_for(spec, 0)
+        assert False
+    except ValueError:
+        pass
