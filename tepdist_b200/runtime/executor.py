@@ -363,8 +363,14 @@ class Executor:
         if (self.comm_mode == "fused" and st.master.is_cuda and self.opt.get("kind") == "adamw" and num <= 8):
             from ..parallel.symm import FusedShardedOptimizer
             pg = self.collective.mesh.group(fz["level"])
-            st.make_symmetric(pg)
-            self.flat_zero["fused"] = FusedShardedOptimizer(st.symm_grad, st.symm_param, pg)
+            try:
+                st.make_symmetric(pg)
+                self.flat_zero["fused"] = FusedShardedOptimizer(st.symm_grad, st.symm_param, pg)
+            except RuntimeError as e:   # e.g. CUDA IPC unavailable in this container: keep the NCCL path, loudly
+                import warnings
+                warnings.warn(f"fused peer-memory optimizer unavailable ({e}); falling back to NCCL collectives")
+                self.flat_zero["fused"] = None
+                self.comm_mode = "nccl"
         self.fused_apply_ok = True  # regular gradients land in the flat buffer again
 
     def _flat_zero_reduce(self, bi: int, pending: List[Any]) -> None:
