@@ -377,7 +377,25 @@ class Executor:
         import torch.distributed as dist
         fz, st = self.flat_zero, self.store
         if fz["fused"] is not None:
-            return  # the fused kernel pulls every peer's gradients itself (after the barrier in _flat_zero_apply)
+            # fused mode: as soon as the bucket's gradients exist, a side stream runs
+            #   barrier -> [P2P reduce-scatter + AdamW + bf16 P2P all-gather] for this bucket
+            # with a small CTA budget so it overlaps the remaining backward GEMMs instead of displacing them
+            fo, o = fz["fused"], self.opt
+            if fz.get("comm_stream") is None:
+                fz["comm_stream"] = torch.cuda.Stream()
+            cs = fz["comm_stream"]
+            cs.wait_stream(torch.cuda.current_stream())
+            s0, e0 = fz["buckets"][bi]
+            n, r = fz["num"], fz["rank"]
+            chunk = (e0 - s0) // n
+            last = len(pending) == len(fz["buckets"]) - 1
+            with torch.cuda.stream(cs):
+                fo.barrier()
+                fo.step(st.master, st.m, st.v, s0 + r * chunk, s0 + (r + 1) * chunk, st.n_decay, self.hyper,
+                        o.get("beta1", 0.9), o.get("beta2", 0.999), o.get("eps", 1e-8), o.get("weight_decay", 0.0),
+                        ctas=0 if last else int(o.get("overlap_ctas", 24)))
+            pending.append(None)
+            return
         s0, e0 = fz["buckets"][bi]
         n, r = fz["num"], fz["rank"]
         chunk = (e0 - s0) // n
@@ -392,18 +410,17 @@ class Executor:
     def _flat_zero_apply(self, pending: List[Any]) -> None:
         import torch.distributed as dist
         fz, st, o = self.flat_zero, self.store, self.opt
-        for w in pending:
-            w.wait()
         n, r = fz["num"], fz["rank"]
         if fz["fused"] is not None:
             fo = fz["fused"]
-            fo.barrier()        # every rank's gradients are complete
-            for (s0, e0) in fz["buckets"]:
-                chunk = (e0 - s0) // n
-                fo.step(st.master, st.m, st.v, s0 + r * chunk, s0 + (r + 1) * chunk, st.n_decay, self.hyper,
-                        o.get("beta1", 0.9), o.get("beta2", 0.999), o.get("eps", 1e-8), o.get("weight_decay", 0.0))
-            fo.barrier()        # every rank's parameter shards have landed everywhere
+            cs = fz.get("comm_stream")
+            if cs is not None:
+                with torch.cuda.stream(cs):
+                    fo.barrier()    # every rank's parameter shards have landed everywhere
+                torch.cuda.current_stream().wait_stream(cs)
             return
+        for w in pending:
+            w.wait()
         pg = self.collective.mesh.group(fz["level"])
         works = []
         for (s0, e0) in fz["buckets"]:
