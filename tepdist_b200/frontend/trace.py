@@ -1,0 +1,172 @@
+"""PyTorch client frontend: torch.fx -> planner IR.
+
+The reference's client is patched TensorFlow that clusters the whole training step into one XLA computation
+(SURVEY §2.F F1-F4).  Here an `nn.Module` is symbolically traced with torch.fx, shapes are propagated, every call is
+mapped onto a planner-IR op, the loss is attached, and `build_training_step` appends backward + optimizer so the server
+receives ONE graph per training step.  Module parameters become `parameter` nodes whose initial values are shipped as
+init specs (random-init models) or loaded afterwards through `load_state_dict`.
+"""
+from __future__ import annotations
+
+import math
+import operator
+from typing import Any, Callable, Dict, Optional, Sequence, Tuple
+
+import torch
+import torch.fx as fx
+import torch.nn as nn
+import torch.nn.functional as F
+from torch.fx.passes.shape_prop import ShapeProp
+
+from ..ir import Graph, Value
+from .builder import GraphBuilder, build_training_step
+
+_DT = {torch.float32: "f32", torch.bfloat16: "bf16", torch.float16: "f16", torch.int32: "i32", torch.int64: "i64", torch.bool: "bool"}
+
+
+class TraceResult:
+    def __init__(self, graph: Graph, param_names: Dict[str, str]):
+        self.graph = graph
+        self.param_names = param_names   # IR parameter name -> module state_dict key
+
+    def load_state_dict_into(self, executor, state_dict: Dict[str, torch.Tensor]) -> None:
+        """Copy a module's weights into a built executor's variable store (same values as the eager module)."""
+        sd = {}
+        for ir_name, key in self.param_names.items():
+            sd[ir_name] = state_dict[key].detach().float()
+        executor.store.load_state_dict(sd)
+
+
+def trace(module: nn.Module, example_inputs: Dict[str, torch.Tensor], loss: str = "cross_entropy", label_name: str = "labels",
+          label_example: Optional[torch.Tensor] = None, optimizer: str = "adamw", compute_dtype: str = "f32", **hp) -> TraceResult:
+    """`module(**example_inputs)` must return logits / predictions; `loss` in {"cross_entropy", "mse"}."""
+    gm = fx.symbolic_trace(module)
+    names = list(example_inputs)
+    ShapeProp(gm).propagate(*[example_inputs[k] for k in names])
+    b = GraphBuilder(type(module).__name__, compute_dtype=compute_dtype)
+    env: Dict[str, Any] = {}
+    pnames: Dict[str, str] = {}
+    mods = dict(gm.named_modules())
+    params = dict(gm.named_parameters())
+
+    def dt(t: torch.dtype) -> str:
+        d = _DT[t]
+        return compute_dtype if d in ("f32", "bf16", "f16") else ("i32" if d == "i64" else d)
+
+    def param(key: str, shape, kind="normal", std=0.02, value=0.0, transpose=False) -> Value:
+        if key in env:
+            return env[key]
+        init = {"kind": "constant", "value": value} if kind == "constant" else {"kind": kind, "std": std}
+        v = b.parameter(key.replace(".", "/"), tuple(shape), init)
+        pnames[key.replace(".", "/")] = key
+        env[key] = v
+        return v
+
+    def val(a):
+        if isinstance(a, fx.Node):
+            return env[a.name]
+        return a
+
+    for node in gm.graph.nodes:
+        tm = node.meta.get("tensor_meta")
+        if node.op == "placeholder":
+            t = example_inputs[node.name]
+            env[node.name] = b.input(node.name, tuple(t.shape), dt(t.dtype))
+        elif node.op == "get_attr":
+            p = params[node.target]
+            env[node.name] = param(node.target, p.shape, std=float(p.std()) if p.numel() > 1 else 0.02)
+        elif node.op == "call_module":
+            m = mods[node.target]
+            x = val(node.args[0])
+            key = node.target
+            if isinstance(m, nn.Linear):
+                w = param(key + ".weight", m.weight.shape, std=1.0 / math.sqrt(m.in_features))
+                bias = param(key + ".bias", m.bias.shape, "constant") if m.bias is not None else None
+                env[node.name] = b.linear(x, w, bias, name=key.replace(".", "/"))
+            elif isinstance(m, nn.LayerNorm):
+                g = param(key + ".weight", m.weight.shape, "constant", value=1.0)
+                be = param(key + ".bias", m.bias.shape, "constant")
+                env[node.name] = b.layernorm(x, g, be, m.eps, name=key.replace(".", "/"))
+            elif isinstance(m, nn.GELU):
+                env[node.name] = b.gelu(x)
+            elif isinstance(m, nn.ReLU):
+                env[node.name] = b.relu(x)
+            elif isinstance(m, nn.Tanh):
+                env[node.name] = b.tanh(x)
+            elif isinstance(m, nn.Embedding):
+                w = param(key + ".weight", m.weight.shape, std=0.02)
+                env[node.name] = b.gather_rows(w, x, name=key.replace(".", "/"))
+            elif isinstance(m, nn.Conv2d):
+                w = param(key + ".weight", m.weight.shape, std=math.sqrt(2.0 / (m.in_channels * m.kernel_size[0] * m.kernel_size[1])))
+                y = b.conv2d(x, w, m.stride[0], m.padding[0], name=key.replace(".", "/"))
+                if m.bias is not None:
+                    bias = param(key + ".bias", m.bias.shape, "constant")
+                    y = b.add(y, b.broadcast(bias, b.t(y).shape, [1]))
+                env[node.name] = y
+            elif isinstance(m, nn.BatchNorm2d):
+                g = param(key + ".weight", m.weight.shape, "constant", value=1.0)
+                be = param(key + ".bias", m.bias.shape, "constant")
+                env[node.name] = b.batchnorm(x, g, be, m.eps, name=key.replace(".", "/"))
+            elif isinstance(m, nn.MaxPool2d):
+                k = m.kernel_size if isinstance(m.kernel_size, int) else m.kernel_size[0]
+                s = m.stride if isinstance(m.stride, int) else m.stride[0]
+                p = m.padding if isinstance(m.padding, int) else m.padding[0]
+                env[node.name] = b.maxpool2d(x, k, s, p)
+            elif isinstance(m, nn.AdaptiveAvgPool2d):
+                env[node.name] = b.reshape(b.global_avgpool(x), tuple(tm.shape))
+            elif isinstance(m, (nn.Dropout, nn.Identity)):
+                env[node.name] = x       # (the reference's dropout is a no-op as well)
+            elif isinstance(m, nn.Flatten):
+                env[node.name] = b.reshape(x, tuple(tm.shape))
+            else:
+                raise NotImplementedError(f"module {type(m).__name__}")
+        elif node.op in ("call_function", "call_method"):
+            t = node.target
+            a = [val(x) for x in node.args]
+            if t in (operator.add, torch.add, "add"):
+                env[node.name] = b.add(a[0], a[1]) if isinstance(a[1], Value) else b.add(a[0], b.constant(float(a[1])))
+            elif t in (operator.sub, torch.sub):
+                env[node.name] = b.sub(a[0], a[1])
+            elif t in (operator.mul, torch.mul, "mul"):
+                env[node.name] = b.mul(a[0], a[1]) if isinstance(a[1], Value) else b.scale(a[0], float(a[1]))
+            elif t in (operator.truediv, torch.div):
+                env[node.name] = b.div(a[0], a[1]) if isinstance(a[1], Value) else b.scale(a[0], 1.0 / float(a[1]))
+            elif t in (torch.matmul, operator.matmul, "matmul"):
+                env[node.name] = b.matmul(a[0], a[1])
+            elif t in (F.relu, torch.relu, "relu"):
+                env[node.name] = b.relu(a[0])
+            elif t in (F.gelu,):
+                env[node.name] = b.gelu(a[0])
+            elif t in (torch.tanh, "tanh"):
+                env[node.name] = b.tanh(a[0])
+            elif t in (F.softmax, torch.softmax, "softmax"):
+                dim = node.kwargs.get("dim", a[1] if len(a) > 1 else -1)
+                env[node.name] = b.softmax(a[0], dim)
+            elif t in ("view", "reshape", torch.reshape, torch.flatten, "flatten"):
+                env[node.name] = b.reshape(a[0], tuple(tm.shape))
+            elif t in ("transpose", torch.transpose):
+                r = len(b.t(a[0]).shape)
+                perm = list(range(r))
+                d0, d1 = a[1] % r, a[2] % r
+                perm[d0], perm[d1] = perm[d1], perm[d0]
+                env[node.name] = b.transpose(a[0], perm)
+            elif t in ("permute", torch.permute):
+                perm = a[1] if isinstance(a[1], (list, tuple)) else a[1:]
+                env[node.name] = b.transpose(a[0], list(perm))
+            elif t in ("contiguous", "float", "to"):
+                env[node.name] = a[0]
+            else:
+                raise NotImplementedError(f"function {t}")
+        elif node.op == "output":
+            out = val(node.args[0])
+            if loss == "cross_entropy":
+                lab = b.input(label_name, tuple(label_example.shape), "i32")
+                loss_v = b.softmax_xent(out, lab, name="loss")
+            elif loss == "mse":
+                tgt = b.input(label_name, tuple(label_example.shape), compute_dtype)
+                d = b.sub(out, tgt)
+                loss_v = b.reduce_mean(b.mul(d, d), list(range(len(b.t(out).shape))), name="loss")
+            else:
+                raise ValueError(loss)
+    g = build_training_step(b, loss_v, optimizer, **hp)
+    return TraceResult(g, pnames)

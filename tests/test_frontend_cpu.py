@@ -60,3 +60,33 @@ def test_autodiff_matches_torch_autograd_mlp():
     assert abs(float(l) - float(ref)) < 1e-5
     assert torch.allclose(ex.store.master_view(w1.node), W1.detach() - 0.5 * W1.grad, atol=1e-5)
     assert torch.allclose(ex.store.master_view(w2.node), W2.detach() - 0.5 * W2.grad, atol=1e-5)
+
+
+def test_fx_trace_matches_eager_torch_training():
+    """torch.fx client frontend: traced nn.Module trains identically to eager PyTorch + torch.optim.SGD."""
+    import torch.nn as nn
+    from tepdist_b200.frontend.trace import trace
+
+    class Net(nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.fc1 = nn.Linear(16, 32)
+            self.ln = nn.LayerNorm(32)
+            self.fc2 = nn.Linear(32, 8)
+
+        def forward(self, x):
+            return self.fc2(torch.tanh(self.ln(self.fc1(x))))
+
+    torch.manual_seed(0)
+    net = Net()
+    x, y = torch.randn(8, 16), torch.randn(8, 8)
+    tr = trace(net, {"x": x}, loss="mse", label_name="t", label_example=y, optimizer="sgd", lr=0.1)
+    ex = Executor(tr.graph, torch.device("cpu"))
+    tr.load_state_dict_into(ex, net.state_dict())
+    opt = torch.optim.SGD(net.parameters(), lr=0.1)
+    for _ in range(3):
+        ref = ((net(x) - y) ** 2).mean()
+        opt.zero_grad(); ref.backward(); opt.step()
+        (l,) = ex.step({"x": x, "t": y})
+        assert abs(float(l) - float(ref)) < 1e-5
+    assert torch.allclose(ex.store.state_dict()["fc1/weight"], net.fc1.weight.detach(), atol=1e-5)
