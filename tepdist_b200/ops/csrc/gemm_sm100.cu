@@ -36,6 +36,19 @@ struct GemmParams {
   int bias_bf16;
 };
 
+// Peer-memory fusion (tensor parallel):
+//   mode 1  GEMM -> reduce-scatter : output rows [r*rows_per_owner, (r+1)*rows_per_owner) are reduced into rank r's fp32
+//           buffer with red.add over NVLink straight from the epilogue (no separate collective, overlaps tile by tile)
+//   mode 2  all-gather -> GEMM     : A rows are fetched by TMA directly from the rank that owns them (peer-mapped shards)
+constexpr int MAX_PEERS = 8;
+struct PeerArgs {
+  int mode, n, rank, rows_per_owner;
+  void* out[MAX_PEERS];
+};
+struct TmapArray {
+  CUtensorMap m[MAX_PEERS];
+};
+
 __device__ __forceinline__ float gelu_tanh(float x) {
   const float k0 = 0.7978845608028654f, k1 = 0.044715f;
   float u = k0 * (x + k1 * x * x * x);
@@ -54,10 +67,9 @@ struct Cfg {
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
 };
 
-template <int BLOCK_N, bool A_MN, bool B_MN>
-__global__ void __launch_bounds__(NUM_THREADS, 1)
-gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
-                 const GemmParams p) {
+template <int BLOCK_N, bool A_MN, bool B_MN, bool PEER>
+__device__ __forceinline__ void gemm_body(const CUtensorMap& tmap_a, const CUtensorMap& tmap_b, const GemmParams& p,
+                                          const PeerArgs* pa, const TmapArray* tmaps_a) {
   using C = Cfg<BLOCK_N, A_MN, B_MN>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -103,19 +115,31 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
       uint32_t phase = 0;
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
         int t = tile;
-        const int m_blk = t % p.m_blocks; t /= p.m_blocks;
+        int m_blk = t % p.m_blocks; t /= p.m_blocks;
         const int n_blk = t % p.n_blocks; t /= p.n_blocks;
         const int b = t % p.batch;
         const int split = t / p.batch;
         const int kb0 = split * kb_per_split;
         const int kb1 = min(p.k_blocks, kb0 + kb_per_split);
+        const CUtensorMap* ta = &tmap_a;
+        int a_row = m_blk * BLOCK_M;
+        if constexpr (PEER) {
+          // start every rank on its own rows so the n ranks hit n different NVLink destinations at any time
+          m_blk = (m_blk + pa->rank * (p.m_blocks / pa->n)) % p.m_blocks;
+          a_row = m_blk * BLOCK_M;
+          if (pa->mode == 2) {
+            const int owner = a_row / pa->rows_per_owner;
+            ta = &tmaps_a->m[owner];
+            a_row -= owner * pa->rows_per_owner;
+          }
+        }
         for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
           uint8_t* sa = smem + stage * C::STAGE_BYTES;
           uint8_t* sb = sa + C::A_BYTES;
           mbar_expect_tx(&full_bar[stage], C::STAGE_BYTES);
           if constexpr (!A_MN) {
-            tma_load_3d(sa, &tmap_a, &full_bar[stage], kb * BLOCK_K, m_blk * BLOCK_M, b);
+            tma_load_3d(sa, ta, &full_bar[stage], kb * BLOCK_K, a_row, b);
           } else {
 #pragma unroll
             for (int j = 0; j < BLOCK_M / 64; ++j)
@@ -177,12 +201,13 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     uint32_t acc_phase = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
       int t = tile;
-      const int m_blk = t % p.m_blocks; t /= p.m_blocks;
+      int m_blk = t % p.m_blocks; t /= p.m_blocks;
       const int n_blk = t % p.n_blocks; t /= p.n_blocks;
       const int b = t % p.batch;
       const int split = t / p.batch;
       const int kb0 = split * kb_per_split;
       const bool has_k = kb0 < p.k_blocks;  // (always true for valid split configs)
+      if constexpr (PEER) m_blk = (m_blk + pa->rank * (p.m_blocks / pa->n)) % p.m_blocks;
       mbar_wait(&tmem_full[acc], acc_phase);
       tc_fence_after();
       const int row = m_blk * BLOCK_M + quarter * 32 + lane;
@@ -254,6 +279,12 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
               if (col0 + q * 4 < p.N) dp[q] = make_float4(v[q * 4], v[q * 4 + 1], v[q * 4 + 2], v[q * 4 + 3]);
           } else {
             float* dp = reinterpret_cast<float*>(p.D) + off;
+            if constexpr (PEER) {
+              if (pa->mode == 1) {  // reduce-scatter: this row belongs to rank `owner`; add into ITS buffer over NVLink
+                const int owner = row / pa->rows_per_owner;
+                dp = reinterpret_cast<float*>(pa->out[owner]) + (long long)(row - owner * pa->rows_per_owner) * p.ldd + col0;
+              }
+            }
 #pragma unroll
             for (int q = 0; q < 8; ++q) {
               if (col0 + q * 4 < p.N) {
@@ -278,6 +309,20 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     tc_fence_after();
     tmem_dealloc(tmem_base, C::TMEM_COLS);
   }
+}
+
+template <int BLOCK_N, bool A_MN, bool B_MN>
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
+                 const GemmParams p) {
+  gemm_body<BLOCK_N, A_MN, B_MN, false>(tmap_a, tmap_b, p, nullptr, nullptr);
+}
+
+template <int BLOCK_N, bool B_MN>
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+gemm_bf16_peer_kernel(const __grid_constant__ TmapArray tmaps_a, const __grid_constant__ CUtensorMap tmap_b,
+                      const GemmParams p, const __grid_constant__ PeerArgs pa) {
+  gemm_body<BLOCK_N, false, B_MN, true>(tmaps_a.m[pa.rank], tmap_b, p, &pa, &tmaps_a);
 }
 
 // ------------------------------------------------------------------ host side
@@ -379,4 +424,62 @@ extern "C" int tepd_gemm_bf16(const void* A, const void* B, void* D, const void*
   return launch_gemm<BN, true, true>(ta, tb, p, num_sms, s);
   if (block_n == 256) { DISPATCH(256) } else { DISPATCH(128) }
 #undef DISPATCH
+}
+
+
+template <int BLOCK_N, bool B_MN>
+static int launch_gemm_peer(const TmapArray& ta, const CUtensorMap& tb, const GemmParams& p, const PeerArgs& pa, int num_sms,
+                            cudaStream_t stream) {
+  using C = Cfg<BLOCK_N, false, B_MN>;
+  auto kern = gemm_bf16_peer_kernel<BLOCK_N, B_MN>;
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES);
+    if (e != cudaSuccess) return (int)e;
+    configured = true;
+  }
+  int total = p.m_blocks * p.n_blocks * p.batch * p.split_k;
+  int grid = total < num_sms ? total : num_sms;
+  kern<<<grid, NUM_THREADS, C::SMEM_BYTES, stream>>>(ta, tb, p, pa);
+  return (int)cudaGetLastError();
+}
+
+// Tensor-parallel fused GEMMs over peer memory.
+//   mode 1 (GEMM -> reduce-scatter): A [M, K_local] local, B local; out_ptrs[r] = rank r's fp32 [M/n, N] buffer (pre-zeroed).
+//   mode 2 (all-gather -> GEMM)    : a_ptrs[r] = rank r's bf16 shard [M/n, K]; D local [M, N] (bf16 or fp32).
+extern "C" int tepd_gemm_bf16_peer(int mode, void* const* a_ptrs, const void* B, void* D, void* const* out_ptrs, const void* bias,
+                                   int M, int N, int K, long long lda, long long ldb, long long ldd, int b_mn, int out_fp32,
+                                   int n_peers, int rank, int block_n, int num_sms, void* stream) {
+  if (N % 8 != 0 || K % 8 != 0 || n_peers < 1 || n_peers > MAX_PEERS || M % n_peers) return -2;
+  const int rows_per_owner = M / n_peers;
+  if (rows_per_owner % BLOCK_M) return -3;
+  GemmParams p;
+  p.M = M; p.N = N; p.K = K; p.batch = 1;
+  if (block_n != 128 && block_n != 256) block_n = (N % 256 == 0 || N > 1024) ? 256 : 128;
+  p.m_blocks = M / BLOCK_M;
+  p.n_blocks = (N + block_n - 1) / block_n;
+  p.k_blocks = (K + BLOCK_K - 1) / BLOCK_K;
+  p.split_k = 1;
+  p.ldd = ldd; p.stride_d = 0; p.ld_res = 0; p.stride_res = 0;
+  p.D = D; p.bias = mode == 2 ? bias : nullptr; p.residual = nullptr; p.alpha = 1.0f;
+  p.out_fp32 = mode == 1 ? 1 : out_fp32; p.accumulate = mode == 1 ? 1 : 0; p.act = 0; p.bias_bf16 = 0;
+  PeerArgs pa;
+  pa.mode = mode; pa.n = n_peers; pa.rank = rank; pa.rows_per_owner = rows_per_owner;
+  for (int i = 0; i < MAX_PEERS; ++i) pa.out[i] = (mode == 1 && i < n_peers) ? out_ptrs[i] : nullptr;
+  TmapArray ta;
+  int rc;
+  for (int r = 0; r < n_peers; ++r) {
+    if (mode == 2) rc = tepd_make_tmap_bf16_3d(&ta.m[r], a_ptrs[r], K, rows_per_owner, 1, lda, 0, BLOCK_K, BLOCK_M);
+    else           rc = tepd_make_tmap_bf16_3d(&ta.m[r], a_ptrs[0], K, M, 1, lda, 0, BLOCK_K, BLOCK_M);
+    if (rc) return 100 + rc;
+  }
+  for (int r = n_peers; r < MAX_PEERS; ++r) ta.m[r] = ta.m[0];
+  CUtensorMap tb;
+  if (!b_mn) rc = tepd_make_tmap_bf16_3d(&tb, B, K, N, 1, ldb, 0, BLOCK_K, block_n);
+  else       rc = tepd_make_tmap_bf16_3d(&tb, B, N, K, 1, ldb, 0, 64, BLOCK_K);
+  if (rc) return 200 + rc;
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  if (num_sms <= 0) num_sms = 148;
+  if (block_n == 256) return b_mn ? launch_gemm_peer<256, true>(ta, tb, p, pa, num_sms, s) : launch_gemm_peer<256, false>(ta, tb, p, pa, num_sms, s);
+  return b_mn ? launch_gemm_peer<128, true>(ta, tb, p, pa, num_sms, s) : launch_gemm_peer<128, false>(ta, tb, p, pa, num_sms, s);
 }

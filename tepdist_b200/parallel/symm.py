@@ -110,3 +110,49 @@ class FusedShardedOptimizer:
         if rc:
             raise RuntimeError(f"fused_rs_adamw_ag failed ({rc})")
         ops._count()
+
+
+# ------------------------------------------------------------------------------------------------ tensor-parallel fused GEMMs
+def _peer_sig(lib):
+    vp, i, ll = ctypes.c_void_p, ctypes.c_int, ctypes.c_longlong
+    pp = ctypes.POINTER(ctypes.c_void_p)
+    fn = lib.tepd_gemm_bf16_peer
+    fn.restype = ctypes.c_int
+    fn.argtypes = [i, pp, vp, vp, pp, vp, i, i, i, ll, ll, ll, i, i, i, i, i, i, vp]
+
+
+def gemm_reduce_scatter(x: torch.Tensor, w: torch.Tensor, out: SymmetricBuffer, N: int, b_mn: bool = False,
+                        block_n: int = 0) -> torch.Tensor:
+    """Row-parallel linear fused with its reduce-scatter: every rank multiplies its K-shard (x [M, K/n], w [N, K/n]) and
+    the epilogue adds each output row block straight into the OWNER rank's fp32 buffer over NVLink.  `out` is a
+    zero-initialised symmetric fp32 buffer of [M/n, N] per rank; after a barrier the owner holds sum_r x_r w_r^T."""
+    lib = out.lib
+    _peer_sig(lib)
+    M, K = x.shape
+    rc = lib.tepd_gemm_bf16_peer(1, (ctypes.c_void_p * out.world)(*([x.data_ptr()] * out.world)), w.data_ptr(), None, out.ptr_array,
+                                 None, M, N, K, x.stride(0), w.stride(0), N, int(b_mn), 1, out.world, out.rank, block_n,
+                                 ops._sms(), torch.cuda.current_stream().cuda_stream)
+    if rc:
+        raise RuntimeError(f"gemm_reduce_scatter failed ({rc})")
+    ops._count()
+    return out.tensor(torch.float32, (M // out.world) * N).view(M // out.world, N)
+
+
+def all_gather_gemm(x_shard: SymmetricBuffer, rows_per_rank: int, K: int, w: torch.Tensor, bias: Optional[torch.Tensor] = None,
+                    out_dtype: torch.dtype = torch.bfloat16, b_mn: bool = False, block_n: int = 0) -> torch.Tensor:
+    """Column-parallel linear fused with the all-gather of its input: the activation is row-sharded across ranks
+    (x_shard holds [rows_per_rank, K] bf16 on every rank); TMA loads fetch each A tile from the rank that owns it."""
+    lib = x_shard.lib
+    _peer_sig(lib)
+    n = x_shard.world
+    M = rows_per_rank * n
+    N = w.shape[1] if b_mn else w.shape[0]
+    d = torch.empty(M, N, dtype=out_dtype, device=w.device)
+    rc = lib.tepd_gemm_bf16_peer(2, x_shard.ptr_array, w.data_ptr(), d.data_ptr(), (ctypes.c_void_p * n)(*([None] * n)),
+                                 None if bias is None else bias.data_ptr(), M, N, K, K, w.stride(0), N, int(b_mn),
+                                 int(out_dtype == torch.float32), n, x_shard.rank, block_n, ops._sms(),
+                                 torch.cuda.current_stream().cuda_stream)
+    if rc:
+        raise RuntimeError(f"all_gather_gemm failed ({rc})")
+    ops._count()
+    return d

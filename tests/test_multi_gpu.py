@@ -23,3 +23,14 @@ def test_fused_dp_matches_nccl_and_single(tmp_path):
     for a, b, c in zip(r["fused"], r["nccl"], r["single"]):
         assert abs(a - b) < 2e-2 * abs(b) and abs(a - c) < 2e-2 * abs(c), r
     assert r["fused"][-1] < r["fused"][0]
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
+def test_tp_fused_gemm_kernels(tmp_path):
+    out = str(tmp_path / "tp.json")
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
+           "--master-port", "29742", os.path.join(HERE, "tp_fused_worker.py"), out]
+    pr = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+    assert pr.returncode == 0, pr.stderr[-3000:]
+    r = json.load(open(out))
+    assert r["gemm_rs_relerr"] < 1e-2 and r["ag_gemm_relerr"] < 1e-2, r
