@@ -67,7 +67,7 @@ class _Sig:
     tepd_gemm_bf16 = [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _ll, _ll, _ll, _ll, _ll, _ll, _ll, _ll,
                       _i, _i, _i, _i, _i, _i, _f, _i, _i, _i, _vp]
     tepd_layernorm_fwd = [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _f, _vp]
-    tepd_layernorm_bwd = [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _vp]
+    tepd_layernorm_bwd = [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _vp]
     tepd_gelu_fwd = [_vp, _vp, _ll, _vp]
     tepd_gelu_bwd = [_vp, _vp, _vp, _ll, _vp]
     tepd_colsum = [_vp, _vp, _i, _i, _vp]
@@ -196,8 +196,9 @@ def layernorm_fwd(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, eps:
     return y, mean, rstd
 
 
-def layernorm_bwd(dy, x, gamma, mean, rstd, dgamma_acc: torch.Tensor, dbeta_acc: torch.Tensor):
-    """Returns dx; accumulates dgamma/dbeta into the given fp32 buffers."""
+def layernorm_bwd(dy, x, gamma, mean, rstd, dgamma_acc: torch.Tensor, dbeta_acc: torch.Tensor,
+                  dres: Optional[torch.Tensor] = None):
+    """Returns dx (+ dres when given: fused residual-stream gradient add); accumulates dgamma/dbeta (fp32)."""
     C = x.shape[-1]
     rows = x.numel() // C
     if not x.is_cuda:
@@ -207,11 +208,14 @@ def layernorm_bwd(dy, x, gamma, mean, rstd, dgamma_acc: torch.Tensor, dbeta_acc:
         dx = rstd.unsqueeze(-1) * (g - g.mean(-1, keepdim=True) - xh * (g * xh).mean(-1, keepdim=True))
         dgamma_acc.add_((dyf * xh).sum(0))
         dbeta_acc.add_(dyf.sum(0))
+        if dres is not None:
+            dx = dx + dres.float().reshape(rows, C)
         return dx.to(x.dtype).reshape(x.shape)
     dy = dy.contiguous()
     dx = torch.empty_like(x)
     _check(lib().tepd_layernorm_bwd(dy.data_ptr(), x.data_ptr(), gamma.data_ptr(), mean.data_ptr(), rstd.data_ptr(),
-                                    dx.data_ptr(), dgamma_acc.data_ptr(), dbeta_acc.data_ptr(), rows, C, _stream()),
+                                    dx.data_ptr(), dgamma_acc.data_ptr(), dbeta_acc.data_ptr(),
+                                    None if dres is None else dres.contiguous().data_ptr(), rows, C, _stream()),
            "layernorm_bwd")
     _count()
     return dx

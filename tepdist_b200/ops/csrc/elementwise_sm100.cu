@@ -104,24 +104,22 @@ __global__ void __launch_bounds__(256) layernorm_fwd_kernel(const bf16* __restri
 // Backward: dx per row; dgamma / dbeta accumulated per lane over a grid-strided set of rows, reduced
 // across the block's warps in shared memory and added (fp32 red) to the gradient buffers.
 template <int MAXV>
-__global__ void __launch_bounds__(256) layernorm_bwd_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ x,
+__global__ void __launch_bounds__(256, (MAXV <= 4) ? 2 : 1) layernorm_bwd_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ x,
                                                            const float* __restrict__ gamma,
                                                            const float* __restrict__ mean_in,
                                                            const float* __restrict__ rstd_in, bf16* __restrict__ dx,
                                                            float* __restrict__ dgamma, float* __restrict__ dbeta,
-                                                           int rows, int C) {
+                                                           const bf16* __restrict__ dres, int rows, int C) {
   extern __shared__ float red[];  // [8][C] used twice
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int nvec = C >> 3;
-  float dg[MAXV][8], db[MAXV][8], gg[MAXV][8];
+  float dg[MAXV][8], db[MAXV][8];
 #pragma unroll
   for (int i = 0; i < MAXV; ++i) {
-    const int vi = i * 32 + lane;
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
       dg[i][j] = 0.f;
       db[i][j] = 0.f;
-      gg[i][j] = (vi < nvec) ? __ldg(gamma + vi * 8 + j) : 0.f;
     }
   }
   for (int row = blockIdx.x * 8 + warp; row < rows; row += gridDim.x * 8) {
@@ -137,10 +135,13 @@ __global__ void __launch_bounds__(256) layernorm_bwd_kernel(const bf16* __restri
         float xv[8], dv[8];
         unpack8(__ldg(xr + vi), xv);
         unpack8(__ldg(dyr + vi), dv);
+        const float4 g0 = __ldg(reinterpret_cast<const float4*>(gamma + vi * 8));
+        const float4 g1 = __ldg(reinterpret_cast<const float4*>(gamma + vi * 8) + 1);
+        const float gg[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
           xh[i][j] = (xv[j] - mean) * rstd;
-          g[i][j] = dv[j] * gg[i][j];
+          g[i][j] = dv[j] * gg[j];
           s1 += g[i][j];
           s2 += g[i][j] * xh[i][j];
           dg[i][j] += dv[j] * xh[i][j];
@@ -158,6 +159,12 @@ __global__ void __launch_bounds__(256) layernorm_bwd_kernel(const bf16* __restri
         float o[8];
 #pragma unroll
         for (int j = 0; j < 8; ++j) o[j] = rstd * (g[i][j] - s1 - xh[i][j] * s2);
+        if (dres) {  // fused residual-stream gradient add: dx_total = dx + dres
+          float rr[8];
+          unpack8(__ldg(reinterpret_cast<const uint4*>(dres + (size_t)row * C) + vi), rr);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) o[j] += rr[j];
+        }
         dxr[vi] = pack8(o);
       }
     }
@@ -228,7 +235,20 @@ __global__ void __launch_bounds__(256) colsum_kernel(const bf16* __restrict__ in
   const int r1 = min(rows, r0 + rows_per_block);
   float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
   if (col0 < C) {
-    for (int r = r0 + warp; r < r1; r += 8) {
+    int r = r0 + warp;
+    for (; r + 24 < r1; r += 32) {   // 4 rows in flight per lane
+      uint4 u[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) u[k] = __ldg(reinterpret_cast<const uint4*>(in + (size_t)(r + 8 * k) * C + col0));
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        float f[8];
+        unpack8(u[k], f);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[j] += f[j];
+      }
+    }
+    for (; r < r1; r += 8) {
       float f[8];
       unpack8(__ldg(reinterpret_cast<const uint4*>(in + (size_t)r * C + col0)), f);
 #pragma unroll
@@ -445,16 +465,16 @@ extern "C" int tepd_layernorm_fwd(const void* x, const void* gamma, const void* 
 }
 
 extern "C" int tepd_layernorm_bwd(const void* dy, const void* x, const void* gamma, const void* mean, const void* rstd,
-                                  void* dx, void* dgamma, void* dbeta, int rows, int C, void* stream) {
+                                  void* dx, void* dgamma, void* dbeta, const void* dres, int rows, int C, void* stream) {
   if (C % 8 || C > 2048) return -2;
-  int grid = 148 * 2;
+  int grid = 148 * 4;
   if (grid > (rows + 7) / 8) grid = (rows + 7) / 8;
   size_t smem = (size_t)8 * C * sizeof(float);
 #define LN_BWD(MV)                                                                                          \
   {                                                                                                         \
     static bool cfg = false;                                                                                \
     if (!cfg) { cudaFuncSetAttribute(layernorm_bwd_kernel<MV>, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * 2048 * 4); cfg = true; } \
-    layernorm_bwd_kernel<MV><<<grid, 256, smem, CS(stream)>>>((const bf16*)dy, (const bf16*)x, (const float*)gamma, (const float*)mean, (const float*)rstd, (bf16*)dx, (float*)dgamma, (float*)dbeta, rows, C); \
+    layernorm_bwd_kernel<MV><<<grid, 256, smem, CS(stream)>>>((const bf16*)dy, (const bf16*)x, (const float*)gamma, (const float*)mean, (const float*)rstd, (bf16*)dx, (float*)dgamma, (float*)dbeta, (const bf16*)dres, rows, C); \
   }
   if (C <= 1024) LN_BWD(4) else LN_BWD(8)
 #undef LN_BWD
@@ -473,7 +493,7 @@ extern "C" int tepd_gelu_bwd(const void* dy, const void* x, void* dx, long long 
 }
 extern "C" int tepd_colsum(const void* in, void* out, int rows, int C, void* stream) {
   if (C % 8) return -2;
-  int rpb = 128;
+  int rpb = 64;
   dim3 grid((C + 255) / 256, (rows + rpb - 1) / rpb);
   colsum_kernel<<<grid, 256, 0, CS(stream)>>>((const bf16*)in, (float*)out, rows, C, rpb);
   return (int)cudaGetLastError();

@@ -242,6 +242,27 @@ class Executor:
         self.flat_zero: Optional[Dict[str, Any]] = None
         if not self.fused_apply_ok and self.collective is not None:
             self._detect_flat_zero()
+        # peephole: dX_total = add(dX_residual, layernorm_bwd.dx) -> the LN-backward kernel adds the residual gradient
+        self.ln_fuse: Dict[int, Tuple[int, int]] = {}
+        self.alias_of: Dict[int, Tuple[int, int]] = {}
+        users = g.users()
+        for n in g.nodes:
+            if n.op != "add" or len(n.inputs) != 2:
+                continue
+            for k in (0, 1):
+                v, o = n.inputs[k], n.inputs[1 - k]
+                p_ = g.nodes[v.node]
+                if (p_.op == "layernorm_bwd" and v.idx == 0 and len(users.get(v.key(), [])) == 1 and o.node < p_.id
+                        and tuple(g.type_of(o).shape) == tuple(g.type_of(v).shape) and p_.id not in self.ln_fuse
+                        and v.key() not in {x.key() for x in g.outputs}):
+                    self.ln_fuse[p_.id] = o.key()
+                    self.alias_of[n.id] = v.key()
+                    last_use[o.key()] = max(last_use.get(o.key(), 0), p_.id)
+                    break
+        self.free_after = {}
+        for k_, nid in last_use.items():
+            if nid < len(g.nodes):
+                self.free_after.setdefault(nid, []).append(k_)
         self.ln_stats: Dict[Tuple[Tuple[int, int], Tuple[int, int]], Tuple[torch.Tensor, torch.Tensor]] = {}
         self.input_names = [n.name for n in g.inputs()]
 
@@ -511,8 +532,12 @@ class Executor:
 
     def _run_node(self, n: Node, env: Dict[Tuple[int, int], torch.Tensor], feeds: Dict[str, torch.Tensor]) -> None:
         g = self.g
-        ins = [env[v.key()] for v in n.inputs]
-        outs = self._exec(n, ins, feeds)
+        if n.id in self.alias_of:        # fused into the producer (see ln_fuse)
+            outs = [env[self.alias_of[n.id]]]
+        else:
+            ins = [env[v.key()] for v in n.inputs]
+            self._env = env
+            outs = self._exec(n, ins, feeds)
         for i, t in enumerate(outs):
             env[(n.id, i)] = t
             pid = self.grad_binding.get((n.id, i))
@@ -664,7 +689,10 @@ class Executor:
                 _, mean, rstd = ops.layernorm_fwd(ins[1].contiguous(), ins[2], torch.zeros_like(ins[2]), a.get("eps", 1e-5))
             dg = self._grad_out(n, 1, n.outputs[1].shape)
             db = self._grad_out(n, 2, n.outputs[2].shape)
-            dx = ops.layernorm_bwd(ins[0], ins[1], ins[2], mean, rstd, dg, db)
+            dres = None
+            if n.id in self.ln_fuse and getattr(self, "_env", None) is not None:
+                dres = self._env.get(self.ln_fuse[n.id])
+            dx = ops.layernorm_bwd(ins[0], ins[1], ins[2], mean, rstd, dg, db, dres)
             return [dx, dg, db]
         if op == "linear":
             x, w = ins[0], ins[1]

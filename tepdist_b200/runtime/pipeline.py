@@ -168,7 +168,11 @@ class StageWorker:
                 raise RuntimeError(f"stage {self.stage} micro {m}: node {n.id} {n.op} '{n.name}' needs value of node {miss.id} "
                                    f"{miss.op} '{miss.name}' (backward={miss.backward}, post_apply={miss.id in ex.post_apply}) "
                                    f"which has not been produced") from e
-            outs = ex._exec(n, ins, feeds)
+            if n.id in ex.alias_of:
+                outs = [env[ex.alias_of[n.id]]]
+            else:
+                ex._env = env
+                outs = ex._exec(n, ins, feeds)
             for i, t in enumerate(outs):
                 env[(n.id, i)] = t
                 pid = ex.grad_binding.get((n.id, i))
