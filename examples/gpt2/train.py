@@ -1,0 +1,43 @@
+#!/usr/bin/env python
+"""GPT-2 training with synthetic `fake_input` (reference examples/GPT2/main.py: "Train loop took X s")."""
+import argparse
+import os
+import sys
+import time
+
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
+from tepdist_b200.api import Trainer  # noqa: E402
+from tepdist_b200.models.gpt2 import CONFIGS, build_gpt2_graph  # noqa: E402
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--model", default="345M", choices=list(CONFIGS))
+    ap.add_argument("--batch", type=int, default=4, help="sequences per GPU")
+    ap.add_argument("--train-steps", type=int, default=10)
+    ap.add_argument("--strategy", default="auto")
+    ap.add_argument("--comm", default="fused", choices=["fused", "nccl"])
+    a = ap.parse_args()
+    cfg = CONFIGS[a.model]
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    g = build_gpt2_graph(cfg, batch=a.batch * world)
+    tr = Trainer(g, strategy=a.strategy, comm_mode=a.comm)
+    gen = torch.Generator().manual_seed(0)
+    tok = torch.randint(0, cfg.n_vocab, (a.batch * world, cfg.n_ctx), generator=gen, dtype=torch.int32)
+    feeds = {"tokens": tok, "labels": torch.roll(tok, -1, 1)}
+    t0 = time.time()
+    for i in range(a.train_steps):
+        loss = tr.step(feeds)
+        if tr.rank == 0:
+            print(f"step {i} loss {loss:.4f}")
+    if tr.rank == 0:
+        dt = time.time() - t0
+        print(f"Train loop took {dt:.2f} s  ({a.train_steps * a.batch * world * cfg.n_ctx / dt:.0f} tokens/s incl. planning + warm-up); "
+              f"plan: {tr.plan_info.get('parallelism', 'single')}")
+    os._exit(0)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,40 @@
+#!/usr/bin/env python
+"""GPT-MoE (reference examples/gpt_moe/run_moe.sh: 8 layers, hidden 768, 8 experts, top-2 gating, capacity 256)."""
+import argparse
+import os
+import sys
+import time
+
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
+from tepdist_b200.api import Trainer  # noqa: E402
+from tepdist_b200.models.gpt_moe import MoEConfig, build_gpt_moe_graph  # noqa: E402
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--batch", type=int, default=8)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--strategy", default="auto")
+    ap.add_argument("--tiny", action="store_true")
+    a = ap.parse_args()
+    cfg = MoEConfig(batch=a.batch)
+    if a.tiny:
+        cfg = MoEConfig(n_layer=2, hidden=128, ffn=256, n_head=2, experts=4, capacity=64, groups=4, seq=128, batch=a.batch, vocab=1000)
+    tr = Trainer(build_gpt_moe_graph(cfg), strategy=a.strategy, use_cuda_graph=False)
+    gen = torch.Generator().manual_seed(0)
+    tok = torch.randint(0, cfg.vocab, (cfg.batch, cfg.seq), generator=gen, dtype=torch.int32)
+    feeds = {"tokens": tok, "labels": torch.roll(tok, -1, 1)}
+    t0 = time.time()
+    for i in range(a.steps):
+        loss = tr.step(feeds)
+        if tr.rank == 0:
+            print(f"step {i} loss {loss:.4f}")
+    if tr.rank == 0:
+        print(f"{a.steps} steps in {time.time() - t0:.2f}s; plan: {tr.plan_info.get('parallelism', 'single')}")
+    os._exit(0)
+
+
+if __name__ == "__main__":
+    main()
