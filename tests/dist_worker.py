@@ -36,10 +36,24 @@ def case_mlp(strategy):
     return {"losses": losses, "parallelism": tr.plan_info.get("parallelism"), "collectives": tr.plan_info.get("collectives")}
 
 
+def case_moe(strategy):
+    """GPT-MoE tiny: with weights forced sharded the planner picks expert parallelism (all-to-all dispatch/combine)."""
+    from tepdist_b200.api import Trainer
+    from tepdist_b200.models.gpt_moe import build_moe_ffn_graph
+    g = build_moe_ffn_graph(groups=4, tokens_per_group=32, model=32, hidden=64, experts=4, capacity=16)
+    if strategy == "ep":
+        strategy = "tp"     # var_mem_limit=1 => weights must be stored sharded; expert dim is the cheapest split
+    tr = Trainer(g, strategy=strategy, device=torch.device("cpu"), use_cuda_graph=False)
+    torch.manual_seed(0)
+    x, t = torch.randn(4, 32, 32), torch.randn(4, 32, 32)
+    losses = [tr.step({"x": x, "t": t}) for _ in range(4)]
+    return {"losses": losses, "parallelism": tr.plan_info.get("parallelism"), "collectives": tr.plan_info.get("collectives")}
+
+
 if __name__ == "__main__":
     case, out = sys.argv[1], sys.argv[2]
     name, _, strat = case.partition(":")
-    res = {"gpt2": case_gpt2, "mlp": case_mlp}[name](strat or "auto")
+    res = {"gpt2": case_gpt2, "mlp": case_mlp, "moe": case_moe}[name](strat or "auto")
     if int(os.environ.get("RANK", "0")) == 0:
         json.dump(res, open(out, "w"))
     if dist.is_initialized():

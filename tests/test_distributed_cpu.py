@@ -34,16 +34,20 @@ def _single(case):
     sys.path.insert(0, HERE)
     import dist_worker
     name, _, strat = case.partition(":")
-    return {"gpt2": dist_worker.case_gpt2, "mlp": dist_worker.case_mlp}[name]("auto")
+    return {"gpt2": dist_worker.case_gpt2, "mlp": dist_worker.case_mlp, "moe": dist_worker.case_moe}[name]("auto")
 
 
-@pytest.mark.parametrize("case", ["mlp:auto", "mlp:dp", "gpt2:auto", "gpt2:tp"])
+@pytest.mark.parametrize("case", ["mlp:auto", "mlp:dp", "gpt2:auto", "gpt2:tp", "gpt2:pp2m2", "moe:ep"])
 def test_spmd_world2_matches_single_process(case, tmp_path):
     ref = _single(case)
     got = _run(case, 2, tmp_path)
     assert got["losses"][-1] < got["losses"][0]
     for a, b in zip(got["losses"], ref["losses"]):
         assert abs(a - b) <= 2e-4 * max(1.0, abs(b)), (case, got, ref)
+    if case == "moe:ep":
+        assert got["collectives"].get("all_to_all", 0) >= 2, got      # expert-parallel dispatch / combine
+    if case == "gpt2:pp2m2":
+        assert got["parallelism"].startswith("pp2"), got
     if case == "gpt2:tp":
         assert got["parallelism"].startswith("tp"), got
     if case in ("mlp:dp", "gpt2:auto"):  # (mlp:auto legitimately prefers a 128-byte activation all-reduce over gradient sync)
