@@ -65,7 +65,7 @@ _vp, _i, _ll, _f = ctypes.c_void_p, ctypes.c_int, ctypes.c_longlong, ctypes.c_fl
 
 class _Sig:
     tepd_gemm_bf16 = [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _ll, _ll, _ll, _ll, _ll, _ll, _ll, _ll,
-                      _i, _i, _i, _i, _i, _i, _f, _i, _i, _i, _vp]
+                      _i, _i, _i, _i, _i, _i, _f, _i, _i, _i, _vp, _vp, _vp]
     tepd_layernorm_fwd = [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _f, _vp]
     tepd_layernorm_bwd = [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _vp]
     tepd_gelu_fwd = [_vp, _vp, _ll, _vp]
@@ -108,12 +108,15 @@ def gemm(a: torch.Tensor, b: torch.Tensor, *, a_mn: bool = False, b_mn: bool = F
          bias: Optional[torch.Tensor] = None, residual: Optional[torch.Tensor] = None,
          act: Optional[str] = None, out: Optional[torch.Tensor] = None,
          out_dtype: torch.dtype = torch.bfloat16, accumulate: bool = False, alpha: float = 1.0,
-         split_k: int = 0, block_n: int = 0) -> torch.Tensor:
+         split_k: int = 0, block_n: int = 0, out2: Optional[torch.Tensor] = None,
+         aux: Optional[torch.Tensor] = None) -> torch.Tensor:
     """D = act(alpha * A @ B + bias) + residual with A:(M,K), B:(K,N) as *logical* shapes.
 
     Storage: ``a`` is [.., M, K] (a_mn=False) or [.., K, M] (a_mn=True); ``b`` is [.., N, K]
     (b_mn=False, i.e. nn.Linear weight layout) or [.., K, N] (b_mn=True).  Optional leading batch dim.
     ``accumulate`` adds into an fp32 ``out`` (gradient accumulation / split-K reduction target).
+    ``act="gelu"`` with ``out2``: ``out`` receives the pre-activation, ``out2`` the activated value (one pass).
+    ``act="gelu_bwd"`` with ``aux`` (pre-activation): the result is multiplied by GELU'(aux) in the epilogue.
     """
     assert a.dim() == b.dim() and a.dim() in (2, 3)
     batched = a.dim() == 3
@@ -138,7 +141,16 @@ def gemm(a: torch.Tensor, b: torch.Tensor, *, a_mn: bool = False, b_mn: bool = F
         if bias is not None:
             d = d + bias.float()
         if act == "gelu":
-            d = torch.nn.functional.gelu(d, approximate="tanh")
+            if out2 is not None:
+                out2.reshape(d.shape).copy_(torch.nn.functional.gelu(d, approximate="tanh").to(out2.dtype))
+            else:
+                d = torch.nn.functional.gelu(d, approximate="tanh")
+        if act == "gelu_bwd":
+            xa = aux.float().reshape(d.shape).detach().requires_grad_(True)
+            with torch.enable_grad():
+                ya = torch.nn.functional.gelu(xa, approximate="tanh")
+            (ga,) = torch.autograd.grad(ya, xa, torch.ones_like(ya))
+            d = d * ga
         if residual is not None:
             d = d + residual.float().reshape(d.shape)
         if accumulate:
@@ -168,8 +180,9 @@ def gemm(a: torch.Tensor, b: torch.Tensor, *, a_mn: bool = False, b_mn: bool = F
         a3.stride(0), b3.stride(0), out3.stride(0),
         res3.stride(1) if res3 is not None else 0, res3.stride(0) if res3 is not None else 0,
         int(a_mn), int(b_mn), int(out.dtype == torch.float32), int(accumulate),
-        1 if act == "gelu" else 0, int(bias is not None and bias.dtype == torch.bfloat16),
-        float(alpha), int(split_k), int(block_n), _sms(), _stream())
+        {None: 0, "gelu": 1, "gelu_bwd": 2}[act], int(bias is not None and bias.dtype == torch.bfloat16),
+        float(alpha), int(split_k), int(block_n), _sms(), _stream(), _p(out2),
+        _p(aux.reshape(out3.shape) if aux is not None else None))
     _check(rc, "gemm_bf16")
     _count()
     return out

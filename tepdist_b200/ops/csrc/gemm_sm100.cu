@@ -32,8 +32,10 @@ struct GemmParams {
   float alpha;
   int out_fp32;    // 0: bf16 output, 1: fp32 output
   int accumulate;  // 1: red.add into fp32 output (split-K / gradient accumulation)
-  int act;         // 0 none, 1 tanh-GELU
+  int act;         // 0 none, 1 tanh-GELU, 2 multiply by GELU'(aux)  (fused gelu backward on a dgrad GEMM)
   int bias_bf16;
+  void* D2;        // act 1: when set, D receives the pre-activation and D2 the activated value (saved for backward)
+  const void* aux; // act 2: bf16 [b, M, N] pre-activation
 };
 
 // Peer-memory fusion (tensor parallel):
@@ -49,6 +51,12 @@ struct TmapArray {
   CUtensorMap m[MAX_PEERS];
 };
 
+__device__ __forceinline__ float gelu_tanh_grad(float x) {
+  const float k0 = 0.7978845608028654f, k1 = 0.044715f;
+  float t;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(k0 * (x + k1 * x * x * x)));
+  return 0.5f * (1.0f + t) + 0.5f * x * (1.0f - t * t) * k0 * (1.0f + 3.0f * k1 * x * x);
+}
 __device__ __forceinline__ float gelu_tanh(float x) {
   const float k0 = 0.7978845608028654f, k1 = 0.044715f;
   float u = k0 * (x + k1 * x * x * x);
@@ -236,9 +244,39 @@ __device__ __forceinline__ void gemm_body(const CUtensorMap& tmap_a, const CUten
               for (int j = 0; j < 32; ++j) if (col0 + j < p.N) v[j] += __ldg(bp + j);
             }
           }
+          const long long off = (long long)b * p.stride_d + (long long)row * p.ldd + col0;
           if (p.act == 1) {
+            if (p.D2 != nullptr) {  // dual output: pre-activation (for backward) to D, activated value to D2
+              uint4* dp0 = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.D) + off);
+#pragma unroll
+              for (int q = 0; q < 4; ++q) {
+                if (col0 + q * 8 < p.N) {
+                  uint4 u;
+                  u.x = pack_bf16x2(v[q * 8 + 0], v[q * 8 + 1]);
+                  u.y = pack_bf16x2(v[q * 8 + 2], v[q * 8 + 3]);
+                  u.z = pack_bf16x2(v[q * 8 + 4], v[q * 8 + 5]);
+                  u.w = pack_bf16x2(v[q * 8 + 6], v[q * 8 + 7]);
+                  dp0[q] = u;
+                }
+              }
+            }
 #pragma unroll
             for (int j = 0; j < 32; ++j) v[j] = gelu_tanh(v[j]);
+          } else if (p.act == 2) {
+            const uint4* ap = reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(p.aux) + off);
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              if (col0 + q * 8 < p.N) {
+                uint4 u = __ldg(ap + q);
+                const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                  float2 f = __bfloat1622float2(h[e]);
+                  v[q * 8 + e * 2] *= gelu_tanh_grad(f.x);
+                  v[q * 8 + e * 2 + 1] *= gelu_tanh_grad(f.y);
+                }
+              }
+            }
           }
           if (add_res) {
             const uint4* rp = reinterpret_cast<const uint4*>(
@@ -258,9 +296,8 @@ __device__ __forceinline__ void gemm_body(const CUtensorMap& tmap_a, const CUten
               }
             }
           }
-          const long long off = (long long)b * p.stride_d + (long long)row * p.ldd + col0;
           if (!p.out_fp32) {
-            uint4* dp = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.D) + off);
+            uint4* dp = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.D2 != nullptr && p.act == 1 ? p.D2 : p.D) + off);
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
               if (col0 + q * 8 < p.N) {
@@ -385,8 +422,10 @@ extern "C" int tepd_gemm_bf16(const void* A, const void* B, void* D, const void*
                               int M, int N, int K, int batch, long long lda, long long ldb, long long ldd,
                               long long stride_a, long long stride_b, long long stride_d, long long ld_res,
                               long long stride_res, int a_mn, int b_mn, int out_fp32, int accumulate, int act,
-                              int bias_bf16, float alpha, int split_k, int block_n, int num_sms, void* stream) {
+                              int bias_bf16, float alpha, int split_k, int block_n, int num_sms, void* stream, void* D2,
+                              const void* aux) {
   if (N % 8 != 0 || K % 8 != 0 || M <= 0) return -2;
+  if ((D2 || aux) && out_fp32) return -5;
   if ((a_mn && (M % 8)) || (accumulate && !out_fp32)) return -3;
   GemmParams p;
   p.M = M; p.N = N; p.K = K; p.batch = batch;
@@ -406,6 +445,7 @@ extern "C" int tepd_gemm_bf16(const void* A, const void* B, void* D, const void*
   p.ldd = ldd; p.stride_d = stride_d; p.ld_res = ld_res; p.stride_res = stride_res;
   p.D = D; p.bias = bias; p.residual = residual; p.alpha = alpha;
   p.out_fp32 = out_fp32; p.accumulate = accumulate; p.act = act; p.bias_bf16 = bias_bf16;
+  p.D2 = D2; p.aux = aux;
 
   CUtensorMap ta, tb;
   int rc;
@@ -463,6 +503,7 @@ extern "C" int tepd_gemm_bf16_peer(int mode, void* const* a_ptrs, const void* B,
   p.ldd = ldd; p.stride_d = 0; p.ld_res = 0; p.stride_res = 0;
   p.D = D; p.bias = mode == 2 ? bias : nullptr; p.residual = nullptr; p.alpha = 1.0f;
   p.out_fp32 = mode == 1 ? 1 : out_fp32; p.accumulate = mode == 1 ? 1 : 0; p.act = 0; p.bias_bf16 = 0;
+  p.D2 = nullptr; p.aux = nullptr;
   PeerArgs pa;
   pa.mode = mode; pa.n = n_peers; pa.rank = rank; pa.rows_per_owner = rows_per_owner;
   for (int i = 0; i < MAX_PEERS; ++i) pa.out[i] = (mode == 1 && i < n_peers) ? out_ptrs[i] : nullptr;

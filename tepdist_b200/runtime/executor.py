@@ -260,6 +260,30 @@ class Executor:
                     self.alias_of[n.id] = v.key()
                     last_use[o.key()] = max(last_use.get(o.key(), 0), p_.id)
                     break
+        # peephole: gelu(linear(x)) -> one GEMM writing pre-activation + activation; gelu_bwd(linear_dgrad(dz), f) ->
+        # the dgrad GEMM multiplies by GELU'(f) in its epilogue (GPU only: these are epilogues of the tcgen05 kernel)
+        self.gelu_dual: Dict[int, int] = {}
+        self.gelu_bwd_fuse: Dict[int, Tuple[int, int]] = {}
+        if self.device.type == "cuda":
+            for n in g.nodes:
+                if n.op == "gelu":
+                    v = n.inputs[0]
+                    L = g.nodes[v.node]
+                    us = users.get(v.key(), [])
+                    if (L.op == "linear" and not L.attrs.get("residual") and L.id not in self.gelu_dual
+                            and all(g.nodes[u].op in ("gelu", "gelu_bwd") for u, _ in us) and sum(g.nodes[u].op == "gelu" for u, _ in us) == 1
+                            and g.type_of(v).dtype == "bf16"):
+                        self.gelu_dual[L.id] = n.id
+                        self.alias_of[n.id] = (L.id, 1)
+                        last_use[(L.id, 1)] = last_use.get((n.id, 0), n.id)
+                elif n.op == "gelu_bwd":
+                    dy, f = n.inputs
+                    D = g.nodes[dy.node]
+                    if (D.op == "linear_dgrad" and len(users.get(dy.key(), [])) == 1 and f.node < D.id and D.id not in self.gelu_bwd_fuse
+                            and g.type_of(dy).dtype == "bf16"):
+                        self.gelu_bwd_fuse[D.id] = f.key()
+                        self.alias_of[n.id] = dy.key()
+                        last_use[f.key()] = max(last_use.get(f.key(), 0), n.id)
         self.free_after = {}
         for k_, nid in last_use.items():
             if nid < len(g.nodes):
@@ -704,13 +728,23 @@ class Executor:
             if a.get("residual"):
                 res = ins[k]
             x2 = x.reshape(-1, x.shape[-1])
+            if n.id in self.gelu_dual:
+                pre = torch.empty(x2.shape[0], w.shape[0], dtype=x.dtype, device=dev)
+                act = torch.empty_like(pre)
+                ops.gemm(x2, w, bias=bias, act="gelu", out=pre, out2=act)
+                shp = (*x.shape[:-1], w.shape[0])
+                return [pre.view(shp), act.view(shp)]
             y = ops.gemm(x2, w, bias=bias, residual=None if res is None else res.reshape(-1, w.shape[0]),
                          out_dtype=x.dtype)
             return [y.view(*x.shape[:-1], w.shape[0])]
         if op == "linear_dgrad":
             dy, w = ins
             dy2 = dy.reshape(-1, dy.shape[-1])
-            dx = ops.gemm(dy2, w, b_mn=True, out_dtype=dy.dtype)
+            if n.id in self.gelu_bwd_fuse:
+                f = self._env[self.gelu_bwd_fuse[n.id]]
+                dx = ops.gemm(dy2, w, b_mn=True, out_dtype=dy.dtype, act="gelu_bwd", aux=f.reshape(-1, w.shape[1]).contiguous())
+            else:
+                dx = ops.gemm(dy2, w, b_mn=True, out_dtype=dy.dtype)
             return [dx.view(*dy.shape[:-1], w.shape[1])]
         if op == "linear_wgrad":
             dy, x = ins

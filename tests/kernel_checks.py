@@ -97,6 +97,18 @@ def check_gemm_epilogues():
     acc = torch.zeros(N, K, device="cuda", dtype=torch.float32)
     ops.gemm(dY, X, a_mn=True, b_mn=True, out=acc, accumulate=True)
     out["wgrad"] = _rel_err(acc, dY.float().t() @ X.float())
+    # dual-output GELU (pre-activation + activation in one pass) and fused GELU backward on a dgrad-layout GEMM
+    pre, act = torch.empty(M, N, device="cuda", dtype=torch.bfloat16), torch.empty(M, N, device="cuda", dtype=torch.bfloat16)
+    ops.gemm(A, W, bias=bias, act="gelu", out=pre, out2=act)
+    out["gelu_dual_pre"] = _rel_err(pre, ref)
+    out["gelu_dual_act"] = _rel_err(act, torch.nn.functional.gelu(ref, approximate="tanh"))
+    dz = torch.randn(M, N, device="cuda", dtype=torch.bfloat16)
+    Wd = torch.randn(N, K, device="cuda", dtype=torch.bfloat16) * 0.05     # dgrad: dx[M,K] = dz[M,N] @ Wd[N,K]
+    f = torch.randn(M, K, device="cuda", dtype=torch.bfloat16)
+    fr = f.float().requires_grad_(True)
+    torch.nn.functional.gelu(fr, approximate="tanh").backward(dz.float() @ Wd.float())
+    d = ops.gemm(dz, Wd, b_mn=True, act="gelu_bwd", aux=f)
+    out["gelu_bwd_fused"] = _rel_err(d, fr.grad)
     # batched
     Ab = torch.randn(6, 256, 64, device="cuda", dtype=torch.bfloat16)
     Bb = torch.randn(6, 384, 64, device="cuda", dtype=torch.bfloat16)
