@@ -66,6 +66,7 @@ _vp, _i, _ll, _f = ctypes.c_void_p, ctypes.c_int, ctypes.c_longlong, ctypes.c_fl
 class _Sig:
     tepd_gemm_bf16 = [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _ll, _ll, _ll, _ll, _ll, _ll, _ll, _ll,
                       _i, _i, _i, _i, _i, _i, _f, _i, _i, _i, _vp, _vp, _vp]
+    tepd_gemm2_bf16 = [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _ll, _ll, _ll, _ll, _i, _i, _i, _f, _i, _vp]
     tepd_layernorm_fwd = [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _f, _vp]
     tepd_layernorm_bwd = [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _vp]
     tepd_gelu_fwd = [_vp, _vp, _ll, _vp]
@@ -161,6 +162,12 @@ def gemm(a: torch.Tensor, b: torch.Tensor, *, a_mn: bool = False, b_mn: bool = F
 
     assert a.dtype == torch.bfloat16 and b.dtype == torch.bfloat16
     assert a3.stride(2) == 1 and b3.stride(2) == 1 and out3.stride(2) == 1
+    if (USE_GEMM2 and not batched and not a_mn and not accumulate and out.dtype == torch.bfloat16 and M >= 256 and N >= 256
+            and block_n == 0 and split_k <= 1):
+        res2 = None if residual is None else residual.reshape(M, N)
+        gemm2(a, b, b_mn=b_mn, bias=bias, residual=res2, act=act, out=out, out2=out2,
+              aux=None if aux is None else aux.reshape(M, N), alpha=alpha)
+        return out
     if bias is not None:
         assert bias.dtype in (torch.float32, torch.bfloat16) and bias.is_contiguous()
     res3 = None
@@ -184,6 +191,27 @@ def gemm(a: torch.Tensor, b: torch.Tensor, *, a_mn: bool = False, b_mn: bool = F
         float(alpha), int(split_k), int(block_n), _sms(), _stream(), _p(out2),
         _p(aux.reshape(out3.shape) if aux is not None else None))
     _check(rc, "gemm_bf16")
+    _count()
+    return out
+
+
+USE_GEMM2 = os.environ.get("TEPDIST_GEMM2", "0") == "1"   # 2-CTA (cta_group::2) kernel for eligible shapes
+
+
+def gemm2(a: torch.Tensor, b: torch.Tensor, *, b_mn: bool = False, bias: Optional[torch.Tensor] = None,
+          residual: Optional[torch.Tensor] = None, act: Optional[str] = None, out: Optional[torch.Tensor] = None,
+          out2: Optional[torch.Tensor] = None, aux: Optional[torch.Tensor] = None, alpha: float = 1.0) -> torch.Tensor:
+    """2-CTA tcgen05 GEMM (256x256 tile per CTA pair): a [M,K] bf16, b [N,K] (or [K,N] with b_mn), bf16 output."""
+    M, K = a.shape
+    N = b.shape[1] if b_mn else b.shape[0]
+    if out is None:
+        out = torch.empty(M, N, dtype=torch.bfloat16, device=a.device)
+    assert a.is_cuda and a.dtype == torch.bfloat16 and a.stride(1) == 1 and b.stride(1) == 1 and out.stride(1) == 1
+    rc = lib().tepd_gemm2_bf16(a.data_ptr(), b.data_ptr(), out.data_ptr(), _p(out2), _p(bias), _p(residual), _p(aux), M, N, K,
+                               a.stride(0), b.stride(0), out.stride(0), residual.stride(0) if residual is not None else 0,
+                               int(b_mn), {None: 0, "gelu": 1, "gelu_bwd": 2}[act],
+                               int(bias is not None and bias.dtype == torch.bfloat16), float(alpha), _sms(), _stream())
+    _check(rc, "gemm2_bf16")
     _count()
     return out
 

@@ -1,0 +1,336 @@
+// 2-CTA (cta_group::2) persistent bf16 GEMM for sm_100a: a cluster of two CTAs on one TPC computes a 256 x 256
+// output tile with tcgen05.mma.cta_group::2 (UMMA M = 256).  Each CTA stages its own 128 rows of A and HALF of the B
+// tile, so shared-memory read traffic per MAC drops by a third versus the 1-CTA kernel (gemm_sm100.cu), which is what
+// limits that kernel at ~75 % of the smem port.  Warp roles per CTA: warp0 TMA producer, warp1 MMA issuer (leader
+// CTA only) + TMEM allocation, warps 2-5 epilogue.  Synchronisation across the pair:
+//   full[stage]   lives in the LEADER's smem; both CTAs' TMA loads complete_tx on it (cta_group::2 TMA)
+//   empty[stage]  tcgen05.commit multicast to both CTAs (each producer waits on its own copy)
+//   tmem_full     tcgen05.commit multicast to both CTAs; tmem_empty: 8 remote/local arrivals on the leader's copy
+// A is K-major ([M,K]); B is K-major ([N,K], forward) or MN-major ([K,N], dgrad).
+#include "sm100_ptx.cuh"
+#include <stdio.h>
+
+using namespace sm100;
+
+namespace {
+
+constexpr int BM = 128;      // rows per CTA (256 per pair)
+constexpr int BN = 256;      // columns per pair (each CTA stages 128 of them)
+constexpr int BK = 64;
+constexpr int UK = 16;
+constexpr int THREADS = 192;
+constexpr int A_BYTES = BM * BK * 2;        // 16 KB
+constexpr int B_BYTES = (BN / 2) * BK * 2;  // 16 KB (this CTA's half of B)
+constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+constexpr int STAGES = 6;
+constexpr int TMEM_COLS = 2 * BN;           // double-buffered accumulator
+constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 + 256;
+
+struct Gemm2Params {
+  int M, N, K;
+  int m_pairs, n_blocks, k_blocks;
+  long long ldd, ld_res;
+  void* D;
+  void* D2;
+  const void* bias;
+  const void* residual;
+  const void* aux;
+  float alpha;
+  int act;        // 0 none, 1 gelu (dual output when D2), 2 multiply by gelu'(aux)
+  int bias_bf16;
+};
+
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ uint32_t mapa_rank(uint32_t smem_addr, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(smem_addr), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+__device__ __forceinline__ void tma_load_3d_2sm(void* smem_dst, const CUtensorMap* m, uint32_t leader_bar, int c0, int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes"
+      " [%0], [%1, {%3, %4, %5}], [%2];"
+      ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(leader_bar), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
+__device__ __forceinline__ void umma_f16_ss_2sm(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}\n" ::"r"(tmem_d),
+      "l"(da), "l"(db), "r"(idesc), "r"(acc)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit_2sm(uint64_t* bar) {
+  asm volatile(
+      "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(smem_u32(bar)),
+      "h"((uint16_t)3)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_alloc_2sm(uint32_t* slot, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(slot)), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void tmem_relinquish_2sm() {
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc_2sm(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+
+__device__ __forceinline__ float gelu_f(float x) {
+  const float k0 = 0.7978845608028654f, k1 = 0.044715f;
+  float t;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(k0 * (x + k1 * x * x * x)));
+  return 0.5f * x * (1.0f + t);
+}
+__device__ __forceinline__ float gelu_grad_f(float x) {
+  const float k0 = 0.7978845608028654f, k1 = 0.044715f;
+  float t;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(k0 * (x + k1 * x * x * x)));
+  return 0.5f * (1.0f + t) + 0.5f * x * (1.0f - t * t) * k0 * (1.0f + 3.0f * k1 * x * x);
+}
+
+template <bool B_MN>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1)
+gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b, const Gemm2Params p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);
+  uint64_t* empty_bar = full_bar + STAGES;
+  uint64_t* tmem_full = empty_bar + STAGES;
+  uint64_t* tmem_empty = tmem_full + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t cta = cluster_ctarank();
+  const bool leader = cta == 0;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmap_a);
+    tma_prefetch_desc(&tmap_b);
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(&full_bar[s], 1);    // leader's copy is the live one: one arrive.expect_tx + 2 CTAs' TMA bytes
+      mbar_init(&empty_bar[s], 1);   // one multicast commit per phase
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&tmem_full[s], 1);   // one multicast commit
+      mbar_init(&tmem_empty[s], 8);  // 4 epilogue warps x 2 CTAs (leader's copy is the live one)
+    }
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    tmem_alloc_2sm(tmem_slot, TMEM_COLS);
+    tmem_relinquish_2sm();
+  }
+  tc_fence_before();
+  cluster_sync();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const int num_clusters = gridDim.x >> 1;
+  const int cluster_id = blockIdx.x >> 1;
+  const int total_tiles = p.m_pairs * p.n_blocks;
+
+  if (warp == 0) {
+    // ===================== TMA producer (both CTAs) =====================
+    if (elect_one()) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = cluster_id; tile < total_tiles; tile += num_clusters) {
+        const int m_pair = tile % p.m_pairs, n_blk = tile / p.m_pairs;
+        const int row0 = m_pair * 2 * BM + cta * BM;
+        const int col0 = n_blk * BN + cta * (BN / 2);
+        for (int kb = 0; kb < p.k_blocks; ++kb) {
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          uint8_t* sa = smem + stage * STAGE_BYTES;
+          uint8_t* sb = sa + A_BYTES;
+          const uint32_t lbar = mapa_rank(smem_u32(&full_bar[stage]), 0);   // the leader's barrier
+          if (leader) mbar_expect_tx(&full_bar[stage], 2 * STAGE_BYTES);
+          tma_load_3d_2sm(sa, &tmap_a, lbar, kb * BK, row0, 0);
+          if constexpr (!B_MN) {
+            tma_load_3d_2sm(sb, &tmap_b, lbar, kb * BK, col0, 0);
+          } else {
+#pragma unroll
+            for (int j = 0; j < (BN / 2) / 64; ++j)
+              tma_load_3d_2sm(sb + j * (64 * BK * 2), &tmap_b, lbar, col0 + j * 64, kb * BK, 0);
+          }
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer (leader CTA only) =====================
+    if (leader && elect_one()) {
+      constexpr uint32_t idesc = make_idesc(UMMA_BF16, UMMA_BF16, 2 * BM, BN, 0, B_MN ? 1 : 0);
+      int stage = 0, acc = 0;
+      uint32_t phase = 0, acc_phase = 0;
+      for (int tile = cluster_id; tile < total_tiles; tile += num_clusters) {
+        mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * BN;
+        for (int kb = 0; kb < p.k_blocks; ++kb) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(smem + stage * STAGE_BYTES);
+          const uint32_t sb = sa + A_BYTES;
+#pragma unroll
+          for (int k = 0; k < BK / UK; ++k) {
+            const uint64_t da = make_smem_desc_sw128(sa + k * UK * 2, 0, 1024);
+            uint64_t db;
+            if constexpr (!B_MN) db = make_smem_desc_sw128(sb + k * UK * 2, 0, 1024);
+            else                 db = make_smem_desc_sw128(sb + k * UK * 128, 64 * BK * 2, 1024);
+            umma_f16_ss_2sm(d_tmem, da, db, idesc, (kb > 0 || k > 0) ? 1u : 0u);
+          }
+          umma_commit_2sm(&empty_bar[stage]);   // frees the stage in BOTH CTAs
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+        umma_commit_2sm(&tmem_full[acc]);       // accumulators ready in BOTH CTAs
+        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+      }
+    }
+  } else {
+    // ===================== epilogue (4 warps per CTA; each CTA drains its own 128 TMEM lanes) =====================
+    const int quarter = warp & 3;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int tile = cluster_id; tile < total_tiles; tile += num_clusters) {
+      const int m_pair = tile % p.m_pairs, n_blk = tile / p.m_pairs;
+      mbar_wait(&tmem_full[acc], acc_phase);
+      tc_fence_after();
+      const int row = m_pair * 2 * BM + cta * BM + quarter * 32 + lane;
+      const bool row_ok = row < p.M;
+      const uint32_t t_row = tmem_base + (uint32_t(quarter * 32) << 16) + acc * BN;
+#pragma unroll 1
+      for (int c = 0; c < BN / 32; ++c) {
+        uint32_t r[32];
+        tmem_ld_32x32(t_row + c * 32, r);
+        tmem_ld_wait();
+        const int col0 = n_blk * BN + c * 32;
+        if (row_ok && col0 < p.N) {
+          float v[32];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]) * p.alpha;
+          if (p.bias != nullptr) {
+            if (p.bias_bf16) {
+              const __nv_bfloat16* bp = reinterpret_cast<const __nv_bfloat16*>(p.bias) + col0;
+#pragma unroll
+              for (int j = 0; j < 32; ++j) if (col0 + j < p.N) v[j] += __bfloat162float(bp[j]);
+            } else {
+              const float* bp = reinterpret_cast<const float*>(p.bias) + col0;
+#pragma unroll
+              for (int j = 0; j < 32; ++j) if (col0 + j < p.N) v[j] += __ldg(bp + j);
+            }
+          }
+          const long long off = (long long)row * p.ldd + col0;
+          auto store = [&](void* base) {
+            uint4* dp = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(base) + off);
+#pragma unroll
+            for (int q = 0; q < 4; ++q)
+              if (col0 + q * 8 < p.N) {
+                uint4 u;
+                u.x = pack_bf16x2(v[q * 8 + 0], v[q * 8 + 1]);
+                u.y = pack_bf16x2(v[q * 8 + 2], v[q * 8 + 3]);
+                u.z = pack_bf16x2(v[q * 8 + 4], v[q * 8 + 5]);
+                u.w = pack_bf16x2(v[q * 8 + 6], v[q * 8 + 7]);
+                dp[q] = u;
+              }
+          };
+          if (p.act == 1) {
+            if (p.D2 != nullptr) store(p.D);
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = gelu_f(v[j]);
+          } else if (p.act == 2) {
+            const uint4* ap = reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(p.aux) + off);
+#pragma unroll
+            for (int q = 0; q < 4; ++q)
+              if (col0 + q * 8 < p.N) {
+                uint4 u = __ldg(ap + q);
+                const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                  float2 f = __bfloat1622float2(h[e]);
+                  v[q * 8 + e * 2] *= gelu_grad_f(f.x);
+                  v[q * 8 + e * 2 + 1] *= gelu_grad_f(f.y);
+                }
+              }
+          }
+          if (p.residual != nullptr) {
+            const uint4* rp = reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(p.residual) +
+                                                             (long long)row * p.ld_res + col0);
+#pragma unroll
+            for (int q = 0; q < 4; ++q)
+              if (col0 + q * 8 < p.N) {
+                uint4 u = __ldg(rp + q);
+                const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                  float2 f = __bfloat1622float2(h[e]);
+                  v[q * 8 + e * 2] += f.x;
+                  v[q * 8 + e * 2 + 1] += f.y;
+                }
+              }
+          }
+          store(p.D2 != nullptr && p.act == 1 ? p.D2 : p.D);
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_cluster(mapa_rank(smem_u32(&tmem_empty[acc]), 0));   // always the leader's barrier
+      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+    }
+  }
+
+  tc_fence_before();
+  cluster_sync();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc_2sm(tmem_base, TMEM_COLS);
+  }
+}
+
+}  // namespace
+
+extern "C" int tepd_make_tmap_bf16_3d(CUtensorMap* out, const void* ptr, long long inner, long long rows, long long batch,
+                                      long long ld_elems, long long batch_stride_elems, int box_inner, int box_rows);
+
+// D[M,N] = epilogue(alpha * A[M,K] @ B) with B = [N,K] (b_mn=0) or [K,N] (b_mn=1); bf16 in / bf16 out.
+extern "C" int tepd_gemm2_bf16(const void* A, const void* B, void* D, void* D2, const void* bias, const void* residual,
+                               const void* aux, int M, int N, int K, long long lda, long long ldb, long long ldd, long long ld_res,
+                               int b_mn, int act, int bias_bf16, float alpha, int num_sms, void* stream) {
+  if (N % 8 != 0 || K % 8 != 0 || M <= 0) return -2;
+  Gemm2Params p;
+  p.M = M; p.N = N; p.K = K;
+  p.m_pairs = (M + 2 * BM - 1) / (2 * BM);
+  p.n_blocks = (N + BN - 1) / BN;
+  p.k_blocks = (K + BK - 1) / BK;
+  p.ldd = ldd; p.ld_res = ld_res;
+  p.D = D; p.D2 = D2; p.bias = bias; p.residual = residual; p.aux = aux; p.alpha = alpha; p.act = act; p.bias_bf16 = bias_bf16;
+  CUtensorMap ta, tb;
+  int rc = tepd_make_tmap_bf16_3d(&ta, A, K, M, 1, lda, 0, BK, BM);
+  if (rc) return 100 + rc;
+  if (!b_mn) rc = tepd_make_tmap_bf16_3d(&tb, B, K, N, 1, ldb, 0, BK, BN / 2);
+  else       rc = tepd_make_tmap_bf16_3d(&tb, B, N, K, 1, ldb, 0, 64, BK);
+  if (rc) return 200 + rc;
+  if (num_sms <= 0) num_sms = 148;
+  const int total = p.m_pairs * p.n_blocks;
+  int clusters = total < num_sms / 2 ? total : num_sms / 2;
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  static bool cfg0 = false, cfg1 = false;
+  if (!b_mn) {
+    if (!cfg0) { if (cudaFuncSetAttribute(gemm2_bf16_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES) != cudaSuccess) return -6; cfg0 = true; }
+    gemm2_bf16_kernel<false><<<2 * clusters, THREADS, SMEM_BYTES, s>>>(ta, tb, p);
+  } else {
+    if (!cfg1) { if (cudaFuncSetAttribute(gemm2_bf16_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES) != cudaSuccess) return -6; cfg1 = true; }
+    gemm2_bf16_kernel<true><<<2 * clusters, THREADS, SMEM_BYTES, s>>>(ta, tb, p);
+  }
+  return (int)cudaGetLastError();
+}

@@ -120,6 +120,45 @@ def check_gemm_epilogues():
     return out
 
 
+def check_gemm2():
+    """2-CTA (cta_group::2) kernel: numerics vs fp32 reference for both B layouts + fused epilogues, then throughput."""
+    from tepdist_b200 import ops
+    out = {}
+    torch.manual_seed(7)
+    for (M, N, K) in [(256, 256, 64), (512, 768, 256), (1024, 1024, 1024), (384, 520, 200)]:
+        A = torch.randn(M, K, device="cuda", dtype=torch.bfloat16)
+        Bm = torch.randn(K, N, device="cuda", dtype=torch.bfloat16)
+        ref = A.float() @ Bm.float()
+        for b_mn in (False, True):
+            b = Bm if b_mn else Bm.t().contiguous()
+            d = ops.gemm2(A, b, b_mn=b_mn)
+            torch.cuda.synchronize()
+            out[f"{M}x{N}x{K}_bmn{int(b_mn)}"] = _rel_err(d, ref)
+            assert out[f"{M}x{N}x{K}_bmn{int(b_mn)}"] < 1e-2, out
+    M, N, K = 512, 768, 256
+    A = torch.randn(M, K, device="cuda", dtype=torch.bfloat16)
+    W = torch.randn(N, K, device="cuda", dtype=torch.bfloat16) * 0.05
+    bias = torch.randn(N, device="cuda")
+    res = torch.randn(M, N, device="cuda", dtype=torch.bfloat16)
+    ref = A.float() @ W.float().t() + bias
+    out["bias_res"] = _rel_err(ops.gemm2(A, W, bias=bias, residual=res), ref + res.float())
+    pre, act = torch.empty(M, N, device="cuda", dtype=torch.bfloat16), torch.empty(M, N, device="cuda", dtype=torch.bfloat16)
+    ops.gemm2(A, W, bias=bias, act="gelu", out=pre, out2=act)
+    out["gelu_dual_pre"] = _rel_err(pre, ref)
+    out["gelu_dual_act"] = _rel_err(act, torch.nn.functional.gelu(ref, approximate="tanh"))
+    for k, v in out.items():
+        assert v < 1e-2, (k, v)
+    for (M, N, K) in [(8192, 8192, 8192), (4096, 4096, 1024), (4096, 1024, 4096), (4096, 3072, 1024)]:
+        A = torch.randn(M, K, device="cuda", dtype=torch.bfloat16)
+        W = torch.randn(N, K, device="cuda", dtype=torch.bfloat16)
+        ms2 = _time_ms(lambda: ops.gemm2(A, W))
+        ms1 = _time_ms(lambda: ops.gemm(A, W, block_n=256))
+        msc = _time_ms(lambda: torch.matmul(A, W.t()))
+        f = 2.0 * M * N * K / 1e9
+        out[f"tflops_{M}x{N}x{K}"] = {"gemm2": f / ms2, "gemm1": f / ms1, "cublas": f / msc}
+    return out
+
+
 def check_gemm_perf():
     from tepdist_b200 import ops
     out = {}
@@ -313,6 +352,7 @@ CHECKS = {
     "attn_fwd": check_attn_fwd,
     "attn_bwd": check_attn_bwd,
     "gemm_perf": check_gemm_perf,
+    "gemm2": check_gemm2,
     "attn_perf": check_attn_perf,
 }
 
@@ -333,7 +373,7 @@ if __name__ == "__main__":
     for n in names:
         t0 = time.time()
         try:
-            pr = subprocess.run([sys.executable, __file__, "--one", n], capture_output=True, text=True, timeout=300)
+            pr = subprocess.run([sys.executable, __file__, "--one", n], capture_output=True, text=True, timeout=120)
             res = None
             for line in pr.stdout.splitlines():
                 if line.startswith("RESULT "):
