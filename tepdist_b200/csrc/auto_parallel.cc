@@ -362,13 +362,19 @@ ParallelPlan AutoParallelRun(const Graph& g, const AutoParallelOptions& opt) {
     if (p.spmd > 1) {
       SpmdOptions so = opt.spmd;
       so.num = p.spmd;
-      SpmdPlan plan = opt.mode == "rule" ? PlanSpmdByRules(&cur, so) : PlanSpmdLevel(&cur, so);
+      const bool rule = opt.mode == "rule" || opt.spmd_rule_mode;
+      if (rule) {
+        so.ignore_annotation = false;
+        for (auto& n : cur.nodes)   // sample inputs are split on their batch dim unless the user annotated otherwise
+          if (n.op == "input" && !n.has("shard_dim") && n.outputs[0].rank() > 0) n.attrs["shard_dim"] = (int64_t)0;
+      }
+      SpmdPlan plan = rule ? PlanSpmdByRules(&cur, so) : PlanSpmdLevel(&cur, so);
       cand.spmd_stats = plan.stats;
       spmd_comm = plan.stats.comm_bytes;
       cur.record_split(p.spmd, false);
       TransformStats ts;
       Graph t = SpmdTransform(cur, plan, level, p.spmd, &ts);
-      if (opt.mode == "rule") spmd_comm = ts.comm_bytes;
+      if (rule) spmd_comm = ts.comm_bytes;
       cur = std::move(t);
       ++level;
     }

@@ -98,6 +98,7 @@ struct AutoParallelOptions {
   SpmdOptions spmd;
   double unbalanced_ratio = 0.08;
   bool allow_pipeline = true;
+  bool spmd_rule_mode = false;   // SPMD level by annotation propagation (batch split) instead of the cost-based planner
   HwProfile hw;
 };
 struct ParallelPlan {

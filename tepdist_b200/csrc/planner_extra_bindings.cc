@@ -113,6 +113,7 @@ void BindPlannerExtra(py::module_& m) {
       .def_readwrite("spmd", &AutoParallelOptions::spmd)
       .def_readwrite("unbalanced_ratio", &AutoParallelOptions::unbalanced_ratio)
       .def_readwrite("allow_pipeline", &AutoParallelOptions::allow_pipeline)
+      .def_readwrite("spmd_rule_mode", &AutoParallelOptions::spmd_rule_mode)
       .def_readwrite("hw", &AutoParallelOptions::hw);
   py::class_<ParallelPlan>(m, "ParallelPlan")
       .def_readonly("proposal", &ParallelPlan::proposal).def_readonly("graph", &ParallelPlan::graph)

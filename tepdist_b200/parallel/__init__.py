@@ -81,6 +81,9 @@ def plan_pipeline(graph: Graph, world: int, stages: int, micro: int, options: Op
     if stages > 0:
         ap.mode = "config"
         ap.num_stages, ap.num_micro_batches = stages, micro
+    import os
+    if os.environ.get("TEPDIST_SPMD_RULE_MODE") == "1":
+        ap.spmd_rule_mode = True
     for k, v in (options or {}).items():
         if hasattr(ap, k):
             setattr(ap, k, v)

@@ -241,7 +241,7 @@ class Executor:
             self.grad_binding = {}  # general path: gradients flow through the environment, not the flat buffer
         self.update_target: Dict[Tuple[int, int], int] = {v.key(): var for var, v in g.updates.items()}
         self.flat_zero: Optional[Dict[str, Any]] = None
-        if not self.fused_apply_ok and self.collective is not None:
+        if self._fz_static is not None and self.collective is not None:
             self._detect_flat_zero()
         # peephole: dX_total = add(dX_residual, layernorm_bwd.dx) -> the LN-backward kernel adds the residual gradient
         self.ln_fuse: Dict[int, Tuple[int, int]] = {}
@@ -910,7 +910,7 @@ class Executor:
             return [(x / (H * W)).view(N, C, 1, 1).expand(N, C, H, W).contiguous()]
         if op in ("all_reduce", "all_gather", "reduce_scatter", "all_to_all", "dynamic_slice", "send", "recv"):
             assert self.collective is not None, f"collective op {op} without a communicator"
-            pid = self.grad_binding.get((n.id, 0))
-            out = self.store.grad_view(pid) if (pid is not None and op in ("all_reduce", "reduce_scatter")) else None
-            return self.collective.run(n, ins, out)
+            # (a bound gradient is ADDED into the flat buffer by the caller: with micro-batching the collective runs once
+            #  per micro-batch and must accumulate, so it never writes the buffer in place)
+            return self.collective.run(n, ins, None)
         raise NotImplementedError(op)

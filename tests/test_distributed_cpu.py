@@ -52,3 +52,12 @@ def test_spmd_world2_matches_single_process(case, tmp_path):
         assert got["parallelism"].startswith("tp"), got
     if case in ("mlp:dp", "gpt2:auto"):  # (mlp:auto legitimately prefers a 128-byte activation all-reduce over gradient sync)
         assert got["parallelism"].startswith("dp"), got
+
+
+def test_hybrid_pipeline_x_spmd_world4(tmp_path):
+    """PP2 x SPMD2 x 2 micro-batches on 4 processes == single process (BASELINE config 5 in miniature)."""
+    ref = _single("gpt2:auto")
+    got = _run("gpt2:pp2m2", 4, tmp_path)
+    assert got["parallelism"] == "pp2xspmd2/micro2", got
+    for a, b in zip(got["losses"], ref["losses"]):
+        assert abs(a - b) <= 2e-4 * max(1.0, abs(b)), (got, ref)
