@@ -439,7 +439,7 @@ class Executor:
                 fo.barrier()
                 fo.step(st.master, st.m, st.v, s0 + r * chunk, s0 + (r + 1) * chunk, st.n_decay, self.hyper,
                         o.get("beta1", 0.9), o.get("beta2", 0.999), o.get("eps", 1e-8), o.get("weight_decay", 0.0),
-                        ctas=0 if last else int(os.environ.get("TEPDIST_OVERLAP_CTAS", o.get("overlap_ctas", 148))))
+                        ctas=0 if last else int(os.environ.get("TEPDIST_OVERLAP_CTAS", o.get("overlap_ctas", 296))))
             pending.append(None)
             return
         s0, e0 = fz["buckets"][bi]
