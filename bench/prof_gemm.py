@@ -12,6 +12,12 @@ if which == "gemm":
     W = torch.randn(N, K, device="cuda", dtype=torch.bfloat16)
     for _ in range(12):
         ops.gemm(A, W, block_n=256)
+elif which == "gemm2":
+    M, N, K = 4096, 4096, 1024
+    A = torch.randn(M, K, device="cuda", dtype=torch.bfloat16)
+    W = torch.randn(N, K, device="cuda", dtype=torch.bfloat16)
+    for _ in range(12):
+        ops.gemm2(A, W)
 elif which == "attn":
     qkv = torch.randn(4, 1024, 16, 3, 64, device="cuda", dtype=torch.bfloat16)
     q, k, v = qkv[:, :, :, 0], qkv[:, :, :, 1], qkv[:, :, :, 2]
