@@ -72,9 +72,9 @@ def attention_bwd(do: torch.Tensor, q, k, v, o, lse, scale: float | None = None,
     from . import lib, _check, _count, _stream
     do = do.contiguous()
     assert o.is_contiguous() and do.is_contiguous()
-    dq_acc = torch.zeros(B, S, H, D, dtype=torch.float32, device=q.device)
+    # dq accumulator: persistent self-clearing fp32 workspace inside the library (no per-call memset)
     _check(lib().tepd_attn_bwd(do.data_ptr(), q.data_ptr(), k.data_ptr(), v.data_ptr(), o.data_ptr(), lse.data_ptr(),
-                               dq_acc.data_ptr(), dq.data_ptr(), dk.data_ptr(), dv.data_ptr(), B, H, S, D,
+                               None, dq.data_ptr(), dk.data_ptr(), dv.data_ptr(), B, H, S, D,
                                float(scale), int(causal), q.stride(0), q.stride(1), q.stride(2),
                                dq.stride(0), dq.stride(1), dq.stride(2), _stream()), "attn_bwd")
     _count(3)

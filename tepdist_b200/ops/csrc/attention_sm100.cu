@@ -511,24 +511,33 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
   }
 }
 
-// delta[b,h,s] = sum_d dO * O ; one warp per (b, s, h) row of 64 elements.
+// delta[b,h,s] = sum_d dO * O ; 8 lanes per (b, s, h) row of 64 elements (one 16-byte load per lane and tensor).
 __global__ void attn_delta_kernel(const __nv_bfloat16* __restrict__ dO, const __nv_bfloat16* __restrict__ O,
                                   float* __restrict__ delta, int B, int S, int H) {
-  const int gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  const int lane = threadIdx.x & 31;
-  if (gw >= B * S * H) return;
-  const int hh = gw % H, s = (gw / H) % S, bb = gw / (H * S);
-  const __nv_bfloat162 a = reinterpret_cast<const __nv_bfloat162*>(dO + (size_t)gw * HD)[lane];
-  const __nv_bfloat162 c = reinterpret_cast<const __nv_bfloat162*>(O + (size_t)gw * HD)[lane];
-  float2 fa = __bfloat1622float2(a), fc = __bfloat1622float2(c);
-  float v = fa.x * fc.x + fa.y * fc.y;
+  const long long gid = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  const long long row = gid >> 3;
+  const int sub = (int)(gid & 7);
+  if (row >= (long long)B * S * H) return;
+  const int hh = row % H, s = (row / H) % S, bb = row / ((long long)H * S);
+  const uint4 a = __ldg(reinterpret_cast<const uint4*>(dO + row * HD) + sub);
+  const uint4 c = __ldg(reinterpret_cast<const uint4*>(O + row * HD) + sub);
+  const __nv_bfloat162* ha = reinterpret_cast<const __nv_bfloat162*>(&a);
+  const __nv_bfloat162* hc = reinterpret_cast<const __nv_bfloat162*>(&c);
+  float v = 0.f;
 #pragma unroll
-  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-  if (lane == 0) delta[((size_t)bb * H + hh) * S + s] = v;
+  for (int i = 0; i < 4; ++i) {
+    float2 fa = __bfloat1622float2(ha[i]), fc = __bfloat1622float2(hc[i]);
+    v += fa.x * fc.x + fa.y * fc.y;
+  }
+  v += __shfl_xor_sync(0xffffffffu, v, 4);
+  v += __shfl_xor_sync(0xffffffffu, v, 2);
+  v += __shfl_xor_sync(0xffffffffu, v, 1);
+  if (sub == 0) delta[((size_t)bb * H + hh) * S + s] = v;
 }
 
 // dq (bf16, strided) = dq_acc (fp32 contiguous [B,S,H,D])
-__global__ void attn_dq_cast_kernel(const float* __restrict__ acc, __nv_bfloat16* __restrict__ dq, int B, int S, int H,
+// (the accumulator is zeroed again on the way out, so the persistent workspace never needs a separate memset)
+__global__ void attn_dq_cast_kernel(float* __restrict__ acc, __nv_bfloat16* __restrict__ dq, int B, int S, int H,
                                     long long sb, long long ss, long long sh) {
   const size_t n8 = (size_t)B * S * H * (HD / 8);
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n8; i += (size_t)gridDim.x * blockDim.x) {
@@ -541,6 +550,8 @@ __global__ void attn_dq_cast_kernel(const float* __restrict__ acc, __nv_bfloat16
     uint4 u;
     u.x = pack_bf16x2(x.x, x.y); u.y = pack_bf16x2(x.z, x.w); u.z = pack_bf16x2(y.x, y.y); u.w = pack_bf16x2(y.z, y.w);
     *reinterpret_cast<uint4*>(dq + (size_t)bb * sb + (size_t)s * ss + (size_t)hh * sh + v * 8) = u;
+    reinterpret_cast<float4*>(acc)[i * 2] = make_float4(0.f, 0.f, 0.f, 0.f);
+    reinterpret_cast<float4*>(acc)[i * 2 + 1] = make_float4(0.f, 0.f, 0.f, 0.f);
   }
 }
 
@@ -627,8 +638,21 @@ extern "C" int tepd_attn_bwd(const void* dO, const void* q, const void* k, const
     delta_cap = need;
   }
   {
-    const int rows = B * S * H;
-    attn_delta_kernel<<<(rows * 32 + 255) / 256, 256, 0, st>>>((const __nv_bfloat16*)dO, (const __nv_bfloat16*)o, delta_buf, B, S, H);
+    const long long rows = (long long)B * S * H;
+    attn_delta_kernel<<<(unsigned)((rows * 8 + 255) / 256), 256, 0, st>>>((const __nv_bfloat16*)dO, (const __nv_bfloat16*)o, delta_buf, B, S, H);
+  }
+  // persistent, self-clearing fp32 dQ accumulator (used when the caller passes no buffer)
+  static float* dq_ws = nullptr;
+  static size_t dq_cap = 0;
+  if (dq_acc == nullptr) {
+    const size_t needq = (size_t)B * S * H * HD;
+    if (needq > dq_cap) {
+      if (dq_ws) cudaFree(dq_ws);
+      if (cudaMalloc(&dq_ws, needq * sizeof(float)) != cudaSuccess) return -6;
+      cudaMemsetAsync(dq_ws, 0, needq * sizeof(float), st);
+      dq_cap = needq;
+    }
+    dq_acc = dq_ws;
   }
   static bool cfg = false;
   if (!cfg) {
@@ -641,6 +665,6 @@ extern "C" int tepd_attn_bwd(const void* dO, const void* q, const void* k, const
   p.dstride_b = dstride_b; p.dstride_s = dstride_s; p.dstride_h = dstride_h;
   p.B = B; p.H = H; p.S = S; p.causal = causal; p.scale = scale; p.scale_log2 = scale * 1.4426950408889634f;
   attn_bwd_kernel<<<(S / BKV) * B * H, BWD_THREADS, BWD_SMEM, st>>>(tq, tk, tv, tdo, p);
-  attn_dq_cast_kernel<<<148 * 4, 256, 0, st>>>((const float*)dq_acc, (__nv_bfloat16*)dq, B, S, H, dstride_b, dstride_s, dstride_h);
+  attn_dq_cast_kernel<<<148 * 4, 256, 0, st>>>((float*)dq_acc, (__nv_bfloat16*)dq, B, S, H, dstride_b, dstride_s, dstride_h);
   return (int)cudaGetLastError();
 }
