@@ -101,52 +101,61 @@ __global__ void __launch_bounds__(256) layernorm_fwd_kernel(const bf16* __restri
   }
 }
 
-// Backward: dx per row; dgamma / dbeta accumulated per lane over a grid-strided set of rows, reduced
-// across the block's warps in shared memory and added (fp32 red) to the gradient buffers.
+// Backward: dx per row (one warp per row, grid-strided); dgamma / dbeta are accumulated in per-warp SHARED-memory
+// rows (no atomics inside the CTA, no 64-register accumulator arrays => 3 CTAs/SM keep enough loads in flight to
+// approach HBM bandwidth), reduced across the 8 warps at the end and added (fp32 red) to the gradient buffers.
+// Optional dres: fused residual-stream gradient add (dx_total = dx + dres).
 template <int MAXV>
-__global__ void __launch_bounds__(256, (MAXV <= 4) ? 2 : 1) layernorm_bwd_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ x,
+__global__ void __launch_bounds__(256, (MAXV <= 4) ? 3 : 1) layernorm_bwd_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ x,
                                                            const float* __restrict__ gamma,
                                                            const float* __restrict__ mean_in,
                                                            const float* __restrict__ rstd_in, bf16* __restrict__ dx,
                                                            float* __restrict__ dgamma, float* __restrict__ dbeta,
                                                            const bf16* __restrict__ dres, int rows, int C) {
-  extern __shared__ float red[];  // [8][C] used twice
+  extern __shared__ float red[];  // [2][8][C]: dgamma rows then dbeta rows, one per warp
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int nvec = C >> 3;
-  float dg[MAXV][8], db[MAXV][8];
-#pragma unroll
-  for (int i = 0; i < MAXV; ++i) {
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      dg[i][j] = 0.f;
-      db[i][j] = 0.f;
-    }
-  }
+  float* my_dg = red + (size_t)warp * C;
+  float* my_db = red + (size_t)(8 + warp) * C;
+  for (int c = lane; c < C; c += 32) { my_dg[c] = 0.f; my_db[c] = 0.f; }
+  __syncwarp();
   for (int row = blockIdx.x * 8 + warp; row < rows; row += gridDim.x * 8) {
     const uint4* xr = reinterpret_cast<const uint4*>(x + (size_t)row * C);
     const uint4* dyr = reinterpret_cast<const uint4*>(dy + (size_t)row * C);
     const float mean = mean_in[row], rstd = rstd_in[row];
-    float xh[MAXV][8], g[MAXV][8];
+    uint4 xu[MAXV], du[MAXV];
+#pragma unroll
+    for (int i = 0; i < MAXV; ++i) {   // all loads of the row first: 2*MAXV independent 16-byte requests per lane
+      const int vi = i * 32 + lane;
+      if (vi < nvec) { xu[i] = __ldg(xr + vi); du[i] = __ldg(dyr + vi); }
+    }
     float s1 = 0.f, s2 = 0.f;
 #pragma unroll
     for (int i = 0; i < MAXV; ++i) {
       const int vi = i * 32 + lane;
       if (vi < nvec) {
         float xv[8], dv[8];
-        unpack8(__ldg(xr + vi), xv);
-        unpack8(__ldg(dyr + vi), dv);
+        unpack8(xu[i], xv);
+        unpack8(du[i], dv);
         const float4 g0 = __ldg(reinterpret_cast<const float4*>(gamma + vi * 8));
         const float4 g1 = __ldg(reinterpret_cast<const float4*>(gamma + vi * 8) + 1);
         const float gg[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+        float4* pg = reinterpret_cast<float4*>(my_dg + vi * 8);
+        float4* pb = reinterpret_cast<float4*>(my_db + vi * 8);
+        float4 a0 = pg[0], a1 = pg[1], b0 = pb[0], b1 = pb[1];
+        float ag[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+        float ab[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
-          xh[i][j] = (xv[j] - mean) * rstd;
-          g[i][j] = dv[j] * gg[j];
-          s1 += g[i][j];
-          s2 += g[i][j] * xh[i][j];
-          dg[i][j] += dv[j] * xh[i][j];
-          db[i][j] += dv[j];
+          const float xh = (xv[j] - mean) * rstd;
+          const float g = dv[j] * gg[j];
+          s1 += g;
+          s2 += g * xh;
+          ag[j] += dv[j] * xh;
+          ab[j] += dv[j];
         }
+        pg[0] = make_float4(ag[0], ag[1], ag[2], ag[3]); pg[1] = make_float4(ag[4], ag[5], ag[6], ag[7]);
+        pb[0] = make_float4(ab[0], ab[1], ab[2], ab[3]); pb[1] = make_float4(ab[4], ab[5], ab[6], ab[7]);
       }
     }
     s1 = warp_sum(s1) / C;
@@ -156,10 +165,15 @@ __global__ void __launch_bounds__(256, (MAXV <= 4) ? 2 : 1) layernorm_bwd_kernel
     for (int i = 0; i < MAXV; ++i) {
       const int vi = i * 32 + lane;
       if (vi < nvec) {
-        float o[8];
+        float xv[8], dv[8], o[8];
+        unpack8(xu[i], xv);
+        unpack8(du[i], dv);
+        const float4 g0 = __ldg(reinterpret_cast<const float4*>(gamma + vi * 8));
+        const float4 g1 = __ldg(reinterpret_cast<const float4*>(gamma + vi * 8) + 1);
+        const float gg[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
 #pragma unroll
-        for (int j = 0; j < 8; ++j) o[j] = rstd * (g[i][j] - s1 - xh[i][j] * s2);
-        if (dres) {  // fused residual-stream gradient add: dx_total = dx + dres
+        for (int j = 0; j < 8; ++j) o[j] = rstd * (dv[j] * gg[j] - s1 - (xv[j] - mean) * rstd * s2);
+        if (dres) {  // fused residual-stream gradient add
           float rr[8];
           unpack8(__ldg(reinterpret_cast<const uint4*>(dres + (size_t)row * C) + vi), rr);
 #pragma unroll
@@ -169,25 +183,13 @@ __global__ void __launch_bounds__(256, (MAXV <= 4) ? 2 : 1) layernorm_bwd_kernel
       }
     }
   }
-  // block reduce: dgamma then dbeta
-  for (int pass = 0; pass < 2; ++pass) {
-    __syncthreads();
+  __syncthreads();
+  for (int c = threadIdx.x; c < C; c += 256) {
+    float sg = 0.f, sb = 0.f;
 #pragma unroll
-    for (int i = 0; i < MAXV; ++i) {
-      const int vi = i * 32 + lane;
-      if (vi < nvec) {
-#pragma unroll
-        for (int j = 0; j < 8; ++j) red[warp * C + vi * 8 + j] = pass == 0 ? dg[i][j] : db[i][j];
-      }
-    }
-    __syncthreads();
-    float* out = pass == 0 ? dgamma : dbeta;
-    for (int c = threadIdx.x; c < C; c += 256) {
-      float s = 0.f;
-#pragma unroll
-      for (int w = 0; w < 8; ++w) s += red[w * C + c];
-      atomicAdd(out + c, s);
-    }
+    for (int w = 0; w < 8; ++w) { sg += red[(size_t)w * C + c]; sb += red[(size_t)(8 + w) * C + c]; }
+    atomicAdd(dgamma + c, sg);
+    atomicAdd(dbeta + c, sb);
   }
 }
 
@@ -467,13 +469,13 @@ extern "C" int tepd_layernorm_fwd(const void* x, const void* gamma, const void* 
 extern "C" int tepd_layernorm_bwd(const void* dy, const void* x, const void* gamma, const void* mean, const void* rstd,
                                   void* dx, void* dgamma, void* dbeta, const void* dres, int rows, int C, void* stream) {
   if (C % 8 || C > 2048) return -2;
-  int grid = 148 * 4;
+  int grid = 148 * 3;
   if (grid > (rows + 7) / 8) grid = (rows + 7) / 8;
-  size_t smem = (size_t)8 * C * sizeof(float);
+  size_t smem = (size_t)16 * C * sizeof(float);
 #define LN_BWD(MV)                                                                                          \
   {                                                                                                         \
     static bool cfg = false;                                                                                \
-    if (!cfg) { cudaFuncSetAttribute(layernorm_bwd_kernel<MV>, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * 2048 * 4); cfg = true; } \
+    if (!cfg) { cudaFuncSetAttribute(layernorm_bwd_kernel<MV>, cudaFuncAttributeMaxDynamicSharedMemorySize, 16 * 2048 * 4); cfg = true; } \
     layernorm_bwd_kernel<MV><<<grid, 256, smem, CS(stream)>>>((const bf16*)dy, (const bf16*)x, (const float*)gamma, (const float*)mean, (const float*)rstd, (bf16*)dx, (float*)dgamma, (float*)dbeta, (const bf16*)dres, rows, C); \
   }
   if (C <= 1024) LN_BWD(4) else LN_BWD(8)
