@@ -82,7 +82,10 @@ def main():
     W = max(args.warmup, 3)
     K = args.steps
     cfg = CONFIGS[args.model]
-    graph = build_gpt2_graph(cfg, batch=args.batch)
+    world_env = int(os.environ.get("WORLD_SIZE", "1"))
+    # weak scaling: the planner sees the GLOBAL step (batch = per-GPU batch x GPUs) and shards it; every rank then
+    # feeds its own [per-GPU batch, seq] shard
+    graph = build_gpt2_graph(cfg, batch=args.batch * world_env)
     trainer = Trainer(graph, strategy=args.strategy, use_cuda_graph=not args.no_graph, comm_mode=args.comm)
     rank, world = trainer.rank, trainer.world
     assert world == args.gpus, f"--gpus {args.gpus} but WORLD_SIZE={world} (launch with torch.distributed.run)"
