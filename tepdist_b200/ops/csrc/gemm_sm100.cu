@@ -42,11 +42,31 @@ struct GemmParams {
 //   mode 1  GEMM -> reduce-scatter : output rows [r*rows_per_owner, (r+1)*rows_per_owner) are reduced into rank r's fp32
 //           buffer with red.add over NVLink straight from the epilogue (no separate collective, overlaps tile by tile)
 //   mode 2  all-gather -> GEMM     : A rows are fetched by TMA directly from the rank that owns them (peer-mapped shards)
+//   mode 3  GEMM -> reduce-scatter : partial rows are written as bf16 with plain 16-byte stores into slot [src rank] of the
+//           owner's staging buffer (no atomics on the wire); slot_reduce (comm_sm100.cu) sums the n slots on the owner
+//   mode 4  all-gather -> GEMM     : a concurrent copy kernel (p2p_gather_chunks) pulls the peers' shards into a local
+//           staging buffer chunk by chunk and publishes a flag per chunk; the TMA producer starts on the local shard and
+//           waits on a chunk's flag just before its first tile of that chunk, so the NVLink transfer hides under the MMAs
+// Peer tiles are walked chunk-major (own rows first, then rank+1's, ...), so at any moment the n ranks talk to n
+// different peers and mode 4 meets its chunks in the order the copy kernel delivers them.
 constexpr int MAX_PEERS = 8;
 struct PeerArgs {
   int mode, n, rank, rows_per_owner;
   void* out[MAX_PEERS];
+  const uint32_t* flags;  // mode 4: flags[owner] == *epoch once owner's rows are staged locally
+  const uint32_t* epoch;
 };
+
+__device__ __forceinline__ void peer_tile(const PeerArgs* pa, int m_blocks, int n_blocks, int tile, int& m_blk, int& n_blk) {
+  const int mpc = m_blocks / pa->n;  // m-blocks per owner chunk
+  const int per_chunk = mpc * n_blocks;
+  const int chunk = tile / per_chunk;
+  const int rem = tile - chunk * per_chunk;
+  n_blk = rem / mpc;
+  int owner = pa->rank + chunk;
+  if (owner >= pa->n) owner -= pa->n;
+  m_blk = owner * mpc + (rem - n_blk * mpc);
+}
 struct TmapArray {
   CUtensorMap m[MAX_PEERS];
 };
@@ -121,10 +141,12 @@ __device__ __forceinline__ void gemm_body(const CUtensorMap& tmap_a, const CUten
     if (elect_one()) {
       int stage = 0;
       uint32_t phase = 0;
+      int peer_ready = -1;
+      (void)peer_ready;
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
         int t = tile;
         int m_blk = t % p.m_blocks; t /= p.m_blocks;
-        const int n_blk = t % p.n_blocks; t /= p.n_blocks;
+        int n_blk = t % p.n_blocks; t /= p.n_blocks;
         const int b = t % p.batch;
         const int split = t / p.batch;
         const int kb0 = split * kb_per_split;
@@ -132,13 +154,30 @@ __device__ __forceinline__ void gemm_body(const CUtensorMap& tmap_a, const CUten
         const CUtensorMap* ta = &tmap_a;
         int a_row = m_blk * BLOCK_M;
         if constexpr (PEER) {
-          // start every rank on its own rows so the n ranks hit n different NVLink destinations at any time
-          m_blk = (m_blk + pa->rank * (p.m_blocks / pa->n)) % p.m_blocks;
+          peer_tile(pa, p.m_blocks, p.n_blocks, tile, m_blk, n_blk);
           a_row = m_blk * BLOCK_M;
           if (pa->mode == 2) {
             const int owner = a_row / pa->rows_per_owner;
             ta = &tmaps_a->m[owner];
             a_row -= owner * pa->rows_per_owner;
+          } else if (pa->mode == 4) {
+            const int owner = a_row / pa->rows_per_owner;
+            if (owner == pa->rank) {  // own shard: read it where it lives
+              a_row -= owner * pa->rows_per_owner;
+            } else {                  // staged copy of a peer's shard: wait until the copy kernel published it
+              ta = &tmaps_a->m[(pa->rank + 1) % pa->n];
+              if (owner != peer_ready) {
+                const uint32_t want = *reinterpret_cast<const volatile uint32_t*>(pa->epoch);
+                uint32_t got;
+                const long long t0 = clock64();
+                do {
+                  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(got) : "l"(pa->flags + owner) : "memory");
+                  if (got != want && clock64() - t0 > 4000000000LL) __trap();  // copy kernel never ran: fail loudly, don't hang
+                } while (got != want);
+                asm volatile("fence.proxy.async;" ::: "memory");
+                peer_ready = owner;
+              }
+            }
           }
         }
         for (int kb = kb0; kb < kb1; ++kb) {
@@ -210,12 +249,12 @@ __device__ __forceinline__ void gemm_body(const CUtensorMap& tmap_a, const CUten
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
       int t = tile;
       int m_blk = t % p.m_blocks; t /= p.m_blocks;
-      const int n_blk = t % p.n_blocks; t /= p.n_blocks;
+      int n_blk = t % p.n_blocks; t /= p.n_blocks;
       const int b = t % p.batch;
       const int split = t / p.batch;
       const int kb0 = split * kb_per_split;
       const bool has_k = kb0 < p.k_blocks;  // (always true for valid split configs)
-      if constexpr (PEER) m_blk = (m_blk + pa->rank * (p.m_blocks / pa->n)) % p.m_blocks;
+      if constexpr (PEER) peer_tile(pa, p.m_blocks, p.n_blocks, tile, m_blk, n_blk);
       mbar_wait(&tmem_full[acc], acc_phase);
       tc_fence_after();
       const int row = m_blk * BLOCK_M + quarter * 32 + lane;
@@ -298,6 +337,13 @@ __device__ __forceinline__ void gemm_body(const CUtensorMap& tmap_a, const CUten
           }
           if (!p.out_fp32) {
             uint4* dp = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.D2 != nullptr && p.act == 1 ? p.D2 : p.D) + off);
+            if constexpr (PEER) {
+              if (pa->mode == 3) {  // partial rows -> slot [my rank] of the owner's staging buffer (plain stores over NVLink)
+                const int owner = row / pa->rows_per_owner;
+                dp = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(pa->out[owner]) +
+                                              ((long long)pa->rank * pa->rows_per_owner + (row - owner * pa->rows_per_owner)) * p.ldd + col0);
+              }
+            }
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
               if (col0 + q * 8 < p.N) {
@@ -487,9 +533,13 @@ static int launch_gemm_peer(const TmapArray& ta, const CUtensorMap& tb, const Ge
 // Tensor-parallel fused GEMMs over peer memory.
 //   mode 1 (GEMM -> reduce-scatter): A [M, K_local] local, B local; out_ptrs[r] = rank r's fp32 [M/n, N] buffer (pre-zeroed).
 //   mode 2 (all-gather -> GEMM)    : a_ptrs[r] = rank r's bf16 shard [M/n, K]; D local [M, N] (bf16 or fp32).
+//   mode 3 (GEMM -> reduce-scatter): as mode 1 but out_ptrs[r] = rank r's bf16 slot buffer [n, M/n, N]; follow with slot_reduce.
+//   mode 4 (all-gather -> GEMM)    : a_ptrs[rank] = own shard [M/n, K]; a_ptrs[(rank+1)%n] = local staging buffer [M, K] that
+//                                    p2p_gather_chunks fills; flags / epoch as published by that kernel.
 extern "C" int tepd_gemm_bf16_peer(int mode, void* const* a_ptrs, const void* B, void* D, void* const* out_ptrs, const void* bias,
                                    int M, int N, int K, long long lda, long long ldb, long long ldd, int b_mn, int out_fp32,
-                                   int n_peers, int rank, int block_n, int num_sms, void* stream) {
+                                   int n_peers, int rank, int block_n, int num_sms, void* stream, const void* flags,
+                                   const void* epoch) {
   if (N % 8 != 0 || K % 8 != 0 || n_peers < 1 || n_peers > MAX_PEERS || M % n_peers) return -2;
   const int rows_per_owner = M / n_peers;
   if (rows_per_owner % BLOCK_M) return -3;
@@ -501,17 +551,22 @@ extern "C" int tepd_gemm_bf16_peer(int mode, void* const* a_ptrs, const void* B,
   p.k_blocks = (K + BLOCK_K - 1) / BLOCK_K;
   p.split_k = 1;
   p.ldd = ldd; p.stride_d = 0; p.ld_res = 0; p.stride_res = 0;
-  p.D = D; p.bias = mode == 2 ? bias : nullptr; p.residual = nullptr; p.alpha = 1.0f;
-  p.out_fp32 = mode == 1 ? 1 : out_fp32; p.accumulate = mode == 1 ? 1 : 0; p.act = 0; p.bias_bf16 = 0;
+  const bool gather = mode == 2 || mode == 4;
+  p.D = D; p.bias = gather ? bias : nullptr; p.residual = nullptr; p.alpha = 1.0f;
+  p.out_fp32 = mode == 1 ? 1 : (mode == 3 ? 0 : out_fp32); p.accumulate = mode == 1 ? 1 : 0; p.act = 0; p.bias_bf16 = 0;
   p.D2 = nullptr; p.aux = nullptr;
   PeerArgs pa;
   pa.mode = mode; pa.n = n_peers; pa.rank = rank; pa.rows_per_owner = rows_per_owner;
-  for (int i = 0; i < MAX_PEERS; ++i) pa.out[i] = (mode == 1 && i < n_peers) ? out_ptrs[i] : nullptr;
+  pa.flags = reinterpret_cast<const uint32_t*>(flags); pa.epoch = reinterpret_cast<const uint32_t*>(epoch);
+  if (mode == 4 && n_peers > 1 && (!flags || !epoch)) return -4;
+  for (int i = 0; i < MAX_PEERS; ++i) pa.out[i] = ((mode == 1 || mode == 3) && i < n_peers) ? out_ptrs[i] : nullptr;
   TmapArray ta;
   int rc;
   for (int r = 0; r < n_peers; ++r) {
-    if (mode == 2) rc = tepd_make_tmap_bf16_3d(&ta.m[r], a_ptrs[r], K, rows_per_owner, 1, lda, 0, BLOCK_K, BLOCK_M);
-    else           rc = tepd_make_tmap_bf16_3d(&ta.m[r], a_ptrs[0], K, M, 1, lda, 0, BLOCK_K, BLOCK_M);
+    if (mode == 2)      rc = tepd_make_tmap_bf16_3d(&ta.m[r], a_ptrs[r], K, rows_per_owner, 1, lda, 0, BLOCK_K, BLOCK_M);
+    else if (mode == 4) rc = r == rank ? tepd_make_tmap_bf16_3d(&ta.m[r], a_ptrs[r], K, rows_per_owner, 1, lda, 0, BLOCK_K, BLOCK_M)
+                                       : tepd_make_tmap_bf16_3d(&ta.m[r], a_ptrs[(rank + 1) % n_peers], K, M, 1, lda, 0, BLOCK_K, BLOCK_M);
+    else                rc = tepd_make_tmap_bf16_3d(&ta.m[r], a_ptrs[0], K, M, 1, lda, 0, BLOCK_K, BLOCK_M);
     if (rc) return 100 + rc;
   }
   for (int r = n_peers; r < MAX_PEERS; ++r) ta.m[r] = ta.m[0];

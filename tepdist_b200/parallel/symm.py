@@ -29,6 +29,8 @@ def _sigs(lib):
         "tepd_fused_rs_adamw_ag": [pp, pp, vp, vp, vp, i, ll, ll, ll, f, f, f, f, vp, i, vp],
         "tepd_p2p_reduce_scatter": [pp, vp, i, ll, ll, i, vp],
         "tepd_p2p_all_gather": [pp, i, i, ll, ll, i, vp],
+        "tepd_slot_reduce": [vp, i, ll, i, vp, vp, vp, vp, i, vp],
+        "tepd_p2p_gather_chunks": [pp, vp, i, i, ll, vp, vp, vp, i, vp],
     }
     for k, a in table.items():
         fn = getattr(lib, k)
@@ -118,7 +120,7 @@ def _peer_sig(lib):
     pp = ctypes.POINTER(ctypes.c_void_p)
     fn = lib.tepd_gemm_bf16_peer
     fn.restype = ctypes.c_int
-    fn.argtypes = [i, pp, vp, vp, pp, vp, i, i, i, ll, ll, ll, i, i, i, i, i, i, vp]
+    fn.argtypes = [i, pp, vp, vp, pp, vp, i, i, i, ll, ll, ll, i, i, i, i, i, i, vp, vp, vp]
 
 
 def gemm_reduce_scatter(x: torch.Tensor, w: torch.Tensor, out: SymmetricBuffer, N: int, b_mn: bool = False,
@@ -131,7 +133,7 @@ def gemm_reduce_scatter(x: torch.Tensor, w: torch.Tensor, out: SymmetricBuffer, 
     M, K = x.shape
     rc = lib.tepd_gemm_bf16_peer(1, (ctypes.c_void_p * out.world)(*([x.data_ptr()] * out.world)), w.data_ptr(), None, out.ptr_array,
                                  None, M, N, K, x.stride(0), w.stride(0), N, int(b_mn), 1, out.world, out.rank, block_n,
-                                 ops._sms(), torch.cuda.current_stream().cuda_stream)
+                                 ops._sms(), torch.cuda.current_stream().cuda_stream, None, None)
     if rc:
         raise RuntimeError(f"gemm_reduce_scatter failed ({rc})")
     ops._count()
@@ -151,8 +153,113 @@ def all_gather_gemm(x_shard: SymmetricBuffer, rows_per_rank: int, K: int, w: tor
     rc = lib.tepd_gemm_bf16_peer(2, x_shard.ptr_array, w.data_ptr(), d.data_ptr(), (ctypes.c_void_p * n)(*([None] * n)),
                                  None if bias is None else bias.data_ptr(), M, N, K, K, w.stride(0), N, int(b_mn),
                                  int(out_dtype == torch.float32), n, x_shard.rank, block_n, ops._sms(),
-                                 torch.cuda.current_stream().cuda_stream)
+                                 torch.cuda.current_stream().cuda_stream, None, None)
     if rc:
         raise RuntimeError(f"all_gather_gemm failed ({rc})")
     ops._count()
     return d
+
+
+class GemmReduceScatter:
+    """Row-parallel linear + reduce-scatter without atomics on the wire: the GEMM epilogue writes each bf16 partial row
+    block into slot [my rank] of the OWNER's staging buffer with plain 16-byte NVLink stores (gemm_sm100.cu peer mode 3),
+    one flag barrier later the owner sums its n slots (+ bias + residual) in a single pass (slot_reduce).  Two staging
+    buffers alternate so the barrier that publishes round i also protects the slots of round i-1 from being overwritten
+    early.  Replaces the reference's dot -> in-stream NCCL all-reduce pair (service/gpu/
+    dapple_all_reduce_thunk.cc:60-120)."""
+
+    def __init__(self, M: int, N: int, group=None, barrier: Optional[SymmBarrier] = None):
+        self.M, self.N = M, N
+        self.world = dist.get_world_size(group)
+        self.rank = dist.get_rank(group)
+        self.rows = M // self.world
+        self.slots = [SymmetricBuffer(self.world * self.rows * N * 2, group) for _ in range(2)]
+        self.barrier = barrier or SymmBarrier(group)
+        self.turn = 0
+
+    def __call__(self, x: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = None,
+                 residual: Optional[torch.Tensor] = None, out_dtype: torch.dtype = torch.bfloat16, b_mn: bool = False,
+                 block_n: int = 0) -> torch.Tensor:
+        buf = self.slots[self.turn]
+        self.turn ^= 1
+        lib = buf.lib
+        _peer_sig(lib)
+        M, K = x.shape
+        s = torch.cuda.current_stream().cuda_stream
+        rc = lib.tepd_gemm_bf16_peer(3, (ctypes.c_void_p * self.world)(*([x.data_ptr()] * self.world)), w.data_ptr(), None,
+                                     buf.ptr_array, None, M, self.N, K, x.stride(0), w.stride(0), self.N, int(b_mn), 0,
+                                     self.world, self.rank, block_n, ops._sms(), s, None, None)
+        if rc:
+            raise RuntimeError(f"gemm_reduce_scatter(slots) failed ({rc})")
+        ops._count()
+        self.barrier()
+        out = torch.empty(self.rows, self.N, dtype=out_dtype, device=x.device)
+        bf = out_dtype == torch.bfloat16
+        rc = lib.tepd_slot_reduce(buf.local_ptr, self.world, self.rows, self.N, None if bias is None else bias.data_ptr(),
+                                  None if residual is None else residual.data_ptr(), out.data_ptr() if bf else None,
+                                  None if bf else out.data_ptr(), 0, s)
+        if rc:
+            raise RuntimeError(f"slot_reduce failed ({rc})")
+        ops._count()
+        return out
+
+
+class AllGatherGemm:
+    """Column-parallel linear fused with the all-gather of its row-sharded input.  A small copy kernel on a side stream
+    pulls the peers' shards into a local staging buffer chunk by chunk (p2p_gather_chunks) while the persistent GEMM
+    (peer mode 4) starts on the local shard at once and waits, per chunk, on the flag the copy kernel publishes -- the
+    NVLink transfer hides under the tensor-core work of the previous chunk."""
+
+    def __init__(self, rows_per_rank: int, K: int, group=None, barrier: Optional[SymmBarrier] = None, copy_ctas: int = 32):
+        self.rows, self.K = rows_per_rank, K
+        self.world = dist.get_world_size(group)
+        self.rank = dist.get_rank(group)
+        # two shard buffers alternate: a peer may still be copying round i's shard while round i+1's is being produced
+        self.shards = [SymmetricBuffer(rows_per_rank * K * 2, group) for _ in range(2)]
+        self.turn = 0
+        self.barrier = barrier or SymmBarrier(group)
+        dev = torch.device("cuda", torch.cuda.current_device())
+        self.full = torch.empty(rows_per_rank * self.world, K, dtype=torch.bfloat16, device=dev)
+        self.flags = torch.zeros(16, dtype=torch.int32, device=dev)       # [0:8] ready flags, [8:16] arrival counters
+        self.side = torch.cuda.Stream()
+        self.copy_ctas = copy_ctas
+        self._ev0, self._ev1 = torch.cuda.Event(), torch.cuda.Event()
+
+    def input(self) -> torch.Tensor:
+        """The local shard [rows_per_rank, K] (bf16) the producer of the activation writes into before the next call."""
+        return self.shards[self.turn].tensor(torch.bfloat16, self.rows * self.K).view(self.rows, self.K)
+
+    def __call__(self, w: torch.Tensor, bias: Optional[torch.Tensor] = None, out_dtype: torch.dtype = torch.bfloat16,
+                 b_mn: bool = False, block_n: int = 0) -> torch.Tensor:
+        shard = self.shards[self.turn]
+        self.turn ^= 1
+        lib = shard.lib
+        _peer_sig(lib)
+        n = self.world
+        M = self.rows * n
+        N = w.shape[1] if b_mn else w.shape[0]
+        main = torch.cuda.current_stream()
+        self.barrier()                      # every rank's shard is written (and last round's staging reads are done)
+        if n > 1:
+            self._ev0.record(main)
+            self.side.wait_event(self._ev0)
+            rc = lib.tepd_p2p_gather_chunks(shard.ptr_array, self.full.data_ptr(), n, self.rank, self.rows * self.K * 2,
+                                            self.flags.data_ptr(), self.flags.data_ptr() + 32, self.barrier.epoch.data_ptr(),
+                                            self.copy_ctas, self.side.cuda_stream)
+            if rc:
+                raise RuntimeError(f"p2p_gather_chunks failed ({rc})")
+            ops._count()
+        d = torch.empty(M, N, dtype=out_dtype, device=w.device)
+        a_ptrs = [self.full.data_ptr()] * n
+        a_ptrs[self.rank] = shard.local_ptr
+        rc = lib.tepd_gemm_bf16_peer(4, (ctypes.c_void_p * n)(*a_ptrs), w.data_ptr(), d.data_ptr(),
+                                     (ctypes.c_void_p * n)(*([None] * n)), None if bias is None else bias.data_ptr(), M, N,
+                                     self.K, self.K, w.stride(0), N, int(b_mn), int(out_dtype == torch.float32), n, self.rank,
+                                     block_n, ops._sms(), main.cuda_stream, self.flags.data_ptr(), self.barrier.epoch.data_ptr())
+        if rc:
+            raise RuntimeError(f"all_gather_gemm(staged) failed ({rc})")
+        ops._count()
+        if n > 1:
+            self._ev1.record(self.side)
+            main.wait_event(self._ev1)
+        return d

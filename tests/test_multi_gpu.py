@@ -30,10 +30,11 @@ def test_tp_fused_gemm_kernels(tmp_path):
     out = str(tmp_path / "tp.json")
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
            "--master-port", "29742", os.path.join(HERE, "tp_fused_worker.py"), out]
-    pr = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+    pr = subprocess.run(cmd, capture_output=True, text=True, timeout=240)
     assert pr.returncode == 0, pr.stderr[-3000:]
     r = json.load(open(out))
     assert r["gemm_rs_relerr"] < 1e-2 and r["ag_gemm_relerr"] < 1e-2, r
+    assert r["gemm_rs_slots_relerr"] < 1e-2 and r["ag_gemm_staged_relerr"] < 1e-2, r
 
 
 @pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")

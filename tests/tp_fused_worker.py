@@ -28,7 +28,8 @@ def main():
     out = sys.argv[1]
     from tepdist_b200 import ops
     from tepdist_b200.api import init_distributed
-    from tepdist_b200.parallel.symm import SymmBarrier, SymmetricBuffer, all_gather_gemm, gemm_reduce_scatter
+    from tepdist_b200.parallel.symm import (AllGatherGemm, GemmReduceScatter, SymmBarrier, SymmetricBuffer, all_gather_gemm,
+                                            gemm_reduce_scatter)
     ctx = init_distributed()
     rank, n = ctx["rank"], ctx["world"]
     dev = torch.device("cuda", ctx["local_rank"])
@@ -63,6 +64,24 @@ def main():
 
     res["gemm_rs_fused_ms"] = ev_ms(fused)
     res["gemm_rs_nccl_ms"] = ev_ms(nccl)
+    # slot variant: bf16 partials pushed with plain stores, summed on the owner together with bias + residual
+    grs = GemmReduceScatter(M, N, barrier=bar)
+    bias = torch.randn(N, device=dev, dtype=torch.float32)
+    resid = torch.randn(M // n, N, device=dev, dtype=torch.bfloat16)
+    for _ in range(3):                       # exercise both staging buffers
+        y3 = grs(xs, ws, bias=bias, residual=resid)
+    torch.cuda.synchronize()
+    ref3 = ref + bias + resid.float()
+    res["gemm_rs_slots_relerr"] = float((y3.float() - ref3).norm() / ref3.norm())
+    res["gemm_rs_slots_ms"] = ev_ms(lambda: grs(xs, ws, bias=bias, residual=resid))
+
+    def nccl_full():
+        torch.matmul(xs, ws.t(), out=part)
+        dist.reduce_scatter_tensor(shard, part)
+        torch.add(shard, resid, out=shard)
+        shard.add_(bias.to(torch.bfloat16))
+
+    res["gemm_rs_nccl_bias_res_ms"] = ev_ms(nccl_full)
     # ---- all-gather -> GEMM (column-parallel c_fc with row-sharded activations)
     M2, K2, N2 = 4096, 1024, 4096 // n
     A = torch.randn(M2, K2, device=dev, dtype=torch.bfloat16) * 0.5
@@ -84,6 +103,14 @@ def main():
 
     res["ag_gemm_fused_ms"] = ev_ms(lambda: (bar(), all_gather_gemm(sh, M2 // n, K2, Wc)))
     res["ag_gemm_nccl_ms"] = ev_ms(nccl2)
+    # staged variant: copy kernel + flag-gated persistent GEMM
+    agg = AllGatherGemm(M2 // n, K2, barrier=bar)
+    for it in range(3):
+        agg.input().copy_(A[rank * (M2 // n):(rank + 1) * (M2 // n)] * (it + 1))
+        d4 = agg(Wc)
+    torch.cuda.synchronize()
+    res["ag_gemm_staged_relerr"] = float((d4.float() - 3 * ref2).norm() / (3 * ref2).norm())
+    res["ag_gemm_staged_ms"] = ev_ms(lambda: agg(Wc))
     res["world"] = n
     if rank == 0:
         json.dump(res, open(out, "w"))
