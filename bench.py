@@ -55,7 +55,9 @@ def main():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
-    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference", "library"],
+                    help="ours | reference (unmodified upstream; unavailable offline) | library (reference-semantics "
+                         "baseline: cuBLAS/SDPA through torch + per-tensor in-stream NCCL all-reduce, bench/torch_baseline.py)")
     ap.add_argument("--model", default="345M")
     ap.add_argument("--batch", type=int, default=4, help="sequences per GPU per step (reference config: 4)")
     ap.add_argument("--strategy", default="auto")
@@ -83,13 +85,36 @@ def main():
     K = args.steps
     cfg = CONFIGS[args.model]
     world_env = int(os.environ.get("WORLD_SIZE", "1"))
-    # weak scaling: the planner sees the GLOBAL step (batch = per-GPU batch x GPUs) and shards it; every rank then
-    # feeds its own [per-GPU batch, seq] shard
-    graph = build_gpt2_graph(cfg, batch=args.batch * world_env)
-    trainer = Trainer(graph, strategy=args.strategy, use_cuda_graph=not args.no_graph, comm_mode=args.comm)
-    rank, world = trainer.rank, trainer.world
+    library = args.impl == "library"
+    if library:
+        import importlib.util
+        spec = importlib.util.spec_from_file_location(
+            "torch_baseline", os.path.join(os.path.dirname(os.path.abspath(__file__)), "bench", "torch_baseline.py"))
+        mod = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(mod)
+        LibraryTrainer = mod.LibraryTrainer
+        rank, world = int(os.environ.get("RANK", "0")), world_env
+        dev = torch.device("cuda", int(os.environ.get("LOCAL_RANK", "0")))
+        torch.cuda.set_device(dev)
+        if world > 1:
+            dist.init_process_group("nccl", device_id=dev)
+        lt = LibraryTrainer(cfg, dev, world, use_graph=not args.no_graph)
+        step_dev = lambda tok, lab: lt.step(tok, lab)
+
+        def step_host(tok, lab):
+            return float(lt.step(tok.to(dev, non_blocking=True), lab.to(dev, non_blocking=True)))
+        parallelism, local_rank = f"dp{world}", dev.index
+    else:
+        # weak scaling: the planner sees the GLOBAL step (batch = per-GPU batch x GPUs) and shards it; every rank then
+        # feeds its own [per-GPU batch, seq] shard
+        graph = build_gpt2_graph(cfg, batch=args.batch * world_env)
+        trainer = Trainer(graph, strategy=args.strategy, use_cuda_graph=not args.no_graph, comm_mode=args.comm)
+        rank, world = trainer.rank, trainer.world
+        dev = trainer.device
+        step_dev = lambda tok, lab: trainer.step_async({"tokens": tok, "labels": lab})
+        step_host = lambda tok, lab: trainer.step({"tokens": tok, "labels": lab})
+        local_rank = trainer.ctx["local_rank"]
     assert world == args.gpus, f"--gpus {args.gpus} but WORLD_SIZE={world} (launch with torch.distributed.run)"
-    dev = trainer.device
     B, S = args.batch, cfg.n_ctx
     gen = torch.Generator().manual_seed(1234 + rank)
     # synthetic fake_input: random tokens, labels = tokens shifted by one (reference: examples/GPT2/inputs.py:42-55)
@@ -106,10 +131,10 @@ def main():
 
     # ---------------- device-timed region (inputs resident on device) ----------------
     for i in range(W):
-        trainer.step_async({"tokens": dev_tok[i % nbuf], "labels": dev_lab[i % nbuf]})
+        step_dev(dev_tok[i % nbuf], dev_lab[i % nbuf])
     barrier()
     stop, samples = threading.Event(), []
-    th = threading.Thread(target=clocks_sampler, args=(stop, samples, trainer.ctx["local_rank"]), daemon=True)
+    th = threading.Thread(target=clocks_sampler, args=(stop, samples, local_rank), daemon=True)
     if rank == 0:
         th.start()
     ops.reset_launch_count()
@@ -118,7 +143,7 @@ def main():
     e0.record()
     loss = None
     for i in range(K):
-        loss = trainer.step_async({"tokens": dev_tok[i % nbuf], "labels": dev_lab[i % nbuf]})
+        loss = step_dev(dev_tok[i % nbuf], dev_lab[i % nbuf])
     e1.record()
     barrier()
     ms = e0.elapsed_time(e1)
@@ -130,7 +155,7 @@ def main():
     f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     f0.record()
     for i in range(K):
-        trainer.step({"tokens": host_tok[i % nbuf], "labels": host_lab[i % nbuf]})
+        step_host(host_tok[i % nbuf], host_lab[i % nbuf])
     f1.record()
     barrier()
     ms_e2e = f0.elapsed_time(f1)
@@ -155,11 +180,11 @@ def main():
             "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": (value / REF_BASELINE_TOKENS_PER_S) if REF_BASELINE_TOKENS_PER_S else None,
             "dtype": "bf16", "data": "synthetic (random tokens, labels=shift; random-init weights)",
-            "impl": "ours",
+            "impl": "library-baseline (torch cuBLAS/SDPA kernels, per-tensor NCCL all-reduce in-stream, no kernels of this repo)" if library else "ours",
             "config": {"model": cfg.name, "n_layer": cfg.n_layer, "n_embd": cfg.n_embd, "n_head": cfg.n_head,
                        "global_batch": B * world, "per_gpu_batch": B, "seq_len": S, "vocab": cfg.n_vocab,
-                       "optimizer": "AdamW (fp32 master + moments)", "parallelism": trainer.plan_info.get("parallelism", f"dp{world}"),
-                       "cuda_graph": not args.no_graph, "comm": args.comm,
+                       "optimizer": "AdamW (fp32 master + moments)", "parallelism": parallelism if library else trainer.plan_info.get("parallelism", f"dp{world}"),
+                       "cuda_graph": (lt.use_graph if library else not args.no_graph), "comm": "nccl-per-tensor" if library else args.comm,
                        "l2": "working set per step >> 126 MB L2 (0.7 GB bf16 weights + 5.7 GB fp32 optimizer state touched every step)"},
             "e2e": {"value": e2e, "unit": "tokens/s", "ms_per_step": ms_e2e / K, "h2d_bytes_per_step": 2 * B * S * 4 * world,
                     "d2h_bytes_per_step": 4 * world},

@@ -195,7 +195,7 @@ def gemm(a: torch.Tensor, b: torch.Tensor, *, a_mn: bool = False, b_mn: bool = F
     return out
 
 
-USE_GEMM2 = os.environ.get("TEPDIST_GEMM2", "0") == "1"   # 2-CTA (cta_group::2) kernel for eligible shapes
+USE_GEMM2 = os.environ.get("TEPDIST_GEMM2", "1") == "1"   # 2-CTA (cta_group::2) kernel for eligible shapes (measured +1.7 % on the GPT-2 step)
 
 
 def gemm2(a: torch.Tensor, b: torch.Tensor, *, b_mn: bool = False, bias: Optional[torch.Tensor] = None,

@@ -28,6 +28,18 @@ class CollectiveRunner:
     def _gloo(self, t: torch.Tensor) -> bool:
         return not t.is_cuda
 
+    def gather_input(self, t: torch.Tensor) -> torch.Tensor:
+        """Concatenate every rank's batch shard of a fed input along dim 0 (world rank order)."""
+        tc = t.contiguous()
+        w = self.mesh.world
+        if self._gloo(tc):
+            parts = [torch.empty_like(tc) for _ in range(w)]
+            dist.all_gather(parts, tc)
+            return torch.cat(parts, 0)
+        buf = torch.empty((w * tc.shape[0],) + tuple(tc.shape[1:]), dtype=tc.dtype, device=tc.device)
+        dist.all_gather_into_tensor(buf.view(-1), tc.view(-1))
+        return buf
+
     def run(self, n, ins: List[torch.Tensor], out: Optional[torch.Tensor] = None) -> List[torch.Tensor]:
         op, a = n.op, n.attrs
         x = ins[0]

@@ -690,8 +690,20 @@ class Executor:
             t = feeds[n.name]
             if t.device != dev:
                 t = t.to(dev, non_blocking=True)
-            if tuple(t.shape) != tuple(n.outputs[0].shape):  # fed the global batch: take this rank's shard
-                t = shard_of(t, a, self.coords).contiguous()
+            want = tuple(n.outputs[0].shape)
+            if tuple(t.shape) != want:
+                full = tuple(a.get("full_shape", want))
+                world = self.collective.mesh.world if self.collective is not None else 1
+                if tuple(t.shape) == full:      # fed the global batch: take this rank's shard
+                    t = shard_of(t, a, self.coords).contiguous()
+                elif (want == full and world > 1 and t.dim() >= 1 and t.shape[0] * world == full[0]
+                      and tuple(t.shape[1:]) == full[1:]):
+                    # the plan keeps this input replicated but every rank fed only its own batch shard (the usual
+                    # data-loader contract): assemble the global batch in rank order
+                    t = self.collective.gather_input(t)
+                else:
+                    raise ValueError(f"input '{n.name}': fed shape {tuple(t.shape)}, expected this rank's shard {want} "
+                                     f"or the global tensor {full}")
             return [t]
         if op == "constant":
             return [torch.full(n.outputs[0].shape, a["value"], dtype=torch_dtype(n.outputs[0].dtype, dev), device=dev)]

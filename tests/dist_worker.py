@@ -9,7 +9,7 @@ import torch.distributed as dist
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 
 
-def case_gpt2(strategy):
+def case_gpt2(strategy, feed_shards=False):
     from tepdist_b200.api import Trainer
     from tepdist_b200.models.gpt2 import CONFIGS, build_gpt2_graph
     cfg = CONFIGS["tiny"]
@@ -20,7 +20,10 @@ def case_gpt2(strategy):
     torch.manual_seed(0)
     tok = torch.randint(0, cfg.n_vocab, (4, cfg.n_ctx), dtype=torch.int32)
     lab = torch.roll(tok, -1, 1)
-    losses = [tr.step({"tokens": tok, "labels": lab}) for _ in range(4)]   # global batch fed; ranks take shards
+    if feed_shards and tr.world > 1:   # data-loader contract: every rank feeds only its own sequences
+        per = 4 // tr.world
+        tok, lab = tok[tr.rank * per:(tr.rank + 1) * per], lab[tr.rank * per:(tr.rank + 1) * per]
+    losses = [tr.step({"tokens": tok, "labels": lab}) for _ in range(4)]   # global batch fed: ranks take their shards
     return {"losses": losses, "parallelism": tr.plan_info.get("parallelism"), "collectives": tr.plan_info.get("collectives")}
 
 
@@ -53,7 +56,7 @@ def case_moe(strategy):
 if __name__ == "__main__":
     case, out = sys.argv[1], sys.argv[2]
     name, _, strat = case.partition(":")
-    res = {"gpt2": case_gpt2, "mlp": case_mlp, "moe": case_moe}[name](strat or "auto")
+    res = {"gpt2": case_gpt2, "gpt2s": lambda st: case_gpt2(st, True), "mlp": case_mlp, "moe": case_moe}[name](strat or "auto")
     if int(os.environ.get("RANK", "0")) == 0:
         json.dump(res, open(out, "w"))
     if dist.is_initialized():

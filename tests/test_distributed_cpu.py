@@ -34,10 +34,11 @@ def _single(case):
     sys.path.insert(0, HERE)
     import dist_worker
     name, _, strat = case.partition(":")
-    return {"gpt2": dist_worker.case_gpt2, "mlp": dist_worker.case_mlp, "moe": dist_worker.case_moe}[name]("auto")
+    return {"gpt2": dist_worker.case_gpt2, "gpt2s": dist_worker.case_gpt2, "mlp": dist_worker.case_mlp,
+            "moe": dist_worker.case_moe}[name]("auto")
 
 
-@pytest.mark.parametrize("case", ["mlp:auto", "mlp:dp", "gpt2:auto", "gpt2:tp", "gpt2:pp2m2", "moe:ep"])
+@pytest.mark.parametrize("case", ["mlp:auto", "mlp:dp", "gpt2:auto", "gpt2s:auto", "gpt2:tp", "gpt2:pp2m2", "moe:ep"])
 def test_spmd_world2_matches_single_process(case, tmp_path):
     ref = _single(case)
     got = _run(case, 2, tmp_path)

@@ -9,17 +9,40 @@ import torch.distributed as dist
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 
 
-def ev_ms(fn, iters=20, warm=5):
+def ev_ms(fn, iters=20, warm=5, graph=True):
+    """Device time per call, max over ranks.  The calls are replayed from a CUDA graph (20 per replay) so the number
+    is the kernels' time, not the Python launch path's (every variant issues 3-4 launches per call)."""
     for _ in range(warm):
         fn()
     dist.barrier(); torch.cuda.synchronize()
+    g = None
+    if graph:
+        try:
+            s = torch.cuda.Stream()
+            s.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(s):
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g, stream=s):
+                    for _ in range(iters):
+                        fn()
+            torch.cuda.current_stream().wait_stream(s)
+            g.replay()
+        except Exception as e:  # noqa: BLE001
+            print("graph capture failed, timing eager:", type(e).__name__, e, flush=True)
+            g = None
+    dist.barrier(); torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    reps = 3 if g is not None else 1
     e0.record()
-    for _ in range(iters):
-        fn()
+    for _ in range(reps):
+        if g is not None:
+            g.replay()
+        else:
+            for _ in range(iters):
+                fn()
     e1.record()
     torch.cuda.synchronize()
-    t = torch.tensor([e0.elapsed_time(e1) / iters], device="cuda")
+    t = torch.tensor([e0.elapsed_time(e1) / (iters * reps)], device="cuda")
     dist.all_reduce(t, op=dist.ReduceOp.MAX)
     return float(t)
 
