@@ -63,6 +63,7 @@ def main():
     ap.add_argument("--strategy", default="auto")
     ap.add_argument("--comm", default="fused", choices=["fused", "nccl"])
     ap.add_argument("--no-graph", action="store_true")
+    ap.add_argument("--no-exposed", action="store_true", help="skip the exposed-communication measurement (N > 1)")
     args = ap.parse_args()
 
     if args.impl == "reference":
@@ -161,10 +162,28 @@ def main():
     ms_e2e = f0.elapsed_time(f1)
     stop.set()
 
-    t = torch.tensor([ms, ms_e2e], dtype=torch.float64, device=dev)
+    # ---------------- exposed communication: the same sharded step with every collective replaced by a local stand-in
+    # (TEPDIST_DRY_COMM, timing only); exposed comm = ms/step - ms/step(dry).  BASELINE.md north-star metric.
+    ms_dry = 0.0
+    if world > 1 and not library and not args.no_exposed:
+        os.environ["TEPDIST_DRY_COMM"] = "1"
+        dry = Trainer(graph, strategy=args.strategy, use_cuda_graph=not args.no_graph, comm_mode=args.comm)
+        del os.environ["TEPDIST_DRY_COMM"]
+        for i in range(W):
+            dry.step_async({"tokens": dev_tok[i % nbuf], "labels": dev_lab[i % nbuf]})
+        barrier()
+        g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        g0.record()
+        for i in range(K):
+            dry.step_async({"tokens": dev_tok[i % nbuf], "labels": dev_lab[i % nbuf]})
+        g1.record()
+        barrier()
+        ms_dry = g0.elapsed_time(g1)
+
+    t = torch.tensor([ms, ms_e2e, ms_dry], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms, ms_e2e = t.tolist()
+    ms, ms_e2e, ms_dry = t.tolist()
     if rank == 0:
         tokens = B * S * world * K
         value = tokens / (ms / 1e3)
@@ -189,6 +208,8 @@ def main():
             "e2e": {"value": e2e, "unit": "tokens/s", "ms_per_step": ms_e2e / K, "h2d_bytes_per_step": 2 * B * S * 4 * world,
                     "d2h_bytes_per_step": 4 * world},
             "gpu_launches": launches,
+            "exposed_comm_ms_per_step": ((ms - ms_dry) / K) if ms_dry > 0 else (0.0 if world == 1 else None),
+            "compute_only_ms_per_step": (ms_dry / K) if ms_dry > 0 else None,
             "model_tflops_per_gpu": fl / world / 1e12,
             "mfu_of_measured_sustained_peak": (fl / world / 1e12) / peaks["bf16_tflops_sustained"] if peaks.get("bf16_tflops_sustained") else None,
             "final_loss": final_loss,

@@ -21,6 +21,7 @@ class CollectiveRunner:
         self.mesh = mesh
         self.comm_dtype = comm_dtype  # FP16_COMM equivalent (bf16 on B200)
         self.bytes_moved = 0
+        self.dry = False  # timing-only stand-ins (no communication), see Executor.dry_comm
 
     def _g(self, n):
         return self.mesh.group(int(n.attrs["level"]))
@@ -32,6 +33,8 @@ class CollectiveRunner:
         """Concatenate every rank's batch shard of a fed input along dim 0 (world rank order)."""
         tc = t.contiguous()
         w = self.mesh.world
+        if self.dry:
+            return tc.repeat((w,) + (1,) * (tc.dim() - 1))
         if self._gloo(tc):
             parts = [torch.empty_like(tc) for _ in range(w)]
             dist.all_gather(parts, tc)
@@ -48,6 +51,19 @@ class CollectiveRunner:
         if num == 1 or self.mesh.world == 1:
             return [x]
         pg = self._g(n)
+        if self.dry and op != "dynamic_slice":
+            if op == "all_reduce":
+                return [x if out is None else out.copy_(x)]
+            if op == "all_gather":
+                d = int(a["dim"])
+                return [x.repeat(tuple(num if i == d else 1 for i in range(x.dim())))]
+            if op == "reduce_scatter":
+                d = int(a["dim"])
+                y = x.narrow(d, 0, x.shape[d] // num).contiguous()
+                return [y if out is None else out.copy_(y.view(out.shape))]
+            if op == "all_to_all":
+                sd, cd = int(a["split_dim"]), int(a["concat_dim"])
+                return [torch.cat(list(x.split(x.shape[sd] // num, dim=sd)), dim=cd)]
         if op == "dynamic_slice":
             d = int(a["dim"])
             sz = x.shape[d] // num

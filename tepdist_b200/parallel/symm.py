@@ -102,12 +102,20 @@ class FusedShardedOptimizer:
 
     def __init__(self, grad_buf: SymmetricBuffer, param_buf: SymmetricBuffer, group=None):
         self.g, self.p = grad_buf, param_buf
-        self.barrier = SymmBarrier(group)
+        self._barrier = SymmBarrier(group)
         self.world, self.rank = grad_buf.world, grad_buf.rank
+        self.dry = False     # timing-only: same kernel on local memory alone (exposed-communication measurement)
+
+    def barrier(self) -> None:
+        if not self.dry:
+            self._barrier()
 
     def step(self, master, m, v, begin: int, end: int, n_decay: int, hyper, beta1, beta2, eps, wd, ctas: int = 0) -> None:
-        rc = self.g.lib.tepd_fused_rs_adamw_ag(self.g.ptr_array, self.p.ptr_array, master.data_ptr(), m.data_ptr(), v.data_ptr(),
-                                               self.world, begin, end, n_decay, beta1, beta2, eps, wd, hyper.data_ptr(), ctas,
+        gp, pp, n = self.g.ptr_array, self.p.ptr_array, self.world
+        if self.dry:
+            gp, pp, n = (ctypes.c_void_p * 1)(self.g.local_ptr), (ctypes.c_void_p * 1)(self.p.local_ptr), 1
+        rc = self.g.lib.tepd_fused_rs_adamw_ag(gp, pp, master.data_ptr(), m.data_ptr(), v.data_ptr(),
+                                               n, begin, end, n_decay, beta1, beta2, eps, wd, hyper.data_ptr(), ctas,
                                                torch.cuda.current_stream().cuda_stream)
         if rc:
             raise RuntimeError(f"fused_rs_adamw_ag failed ({rc})")

@@ -190,6 +190,11 @@ class Executor:
         self.store = store or VariableStore(graph, self.device, seed, self.coords, tail=tail)
         self.grad_sync = grad_sync
         self.collective = collective
+        # timing-only mode (bench.py's exposed-communication measurement): every collective is replaced by a local
+        # stand-in of the same output shape, the sharded optimizer touches only local memory.  Numerics are meaningless.
+        self.dry_comm = os.environ.get("TEPDIST_DRY_COMM") == "1"
+        if self.dry_comm and collective is not None:
+            collective.dry = True
         self.step_count = 0
         self._tag = 0   # micro-batch tag for per-micro-batch side tables (pipeline interleaves micro-batches)
         self.use_cuda_graph = use_cuda_graph and self.device.type == "cuda"
@@ -412,6 +417,7 @@ class Executor:
             try:
                 st.make_symmetric(pg)
                 self.flat_zero["fused"] = FusedShardedOptimizer(st.symm_grad, st.symm_param, pg)
+                self.flat_zero["fused"].dry = self.dry_comm
             except RuntimeError as e:   # e.g. CUDA IPC unavailable in this container: keep the NCCL path, loudly
                 import warnings
                 warnings.warn(f"fused peer-memory optimizer unavailable ({e}); falling back to NCCL collectives")
@@ -448,7 +454,9 @@ class Executor:
         pg = self.collective.mesh.group(fz["level"])
         buf = st.grad[s0:e0]
         own = st.grad[s0 + r * chunk:s0 + (r + 1) * chunk]
-        if buf.is_cuda:
+        if self.dry_comm:
+            pending.append(None)
+        elif buf.is_cuda:
             pending.append(dist.reduce_scatter_tensor(own, buf, group=pg, async_op=True))
         else:  # gloo has no reduce-scatter
             pending.append(dist.all_reduce(buf, group=pg, async_op=True))
@@ -466,7 +474,8 @@ class Executor:
                 torch.cuda.current_stream().wait_stream(cs)
             return
         for w in pending:
-            w.wait()
+            if w is not None:
+                w.wait()
         pg = self.collective.mesh.group(fz["level"])
         works = []
         for (s0, e0) in fz["buckets"]:
@@ -482,7 +491,8 @@ class Executor:
             elif kind == "sgd":
                 ops.sgd_step(st.master[a:b], st.grad[a:b], comp, o.get("lr", 1e-2))
             tgt = st.compute if st.compute is not None else st.master
-            works.append(dist.all_gather_into_tensor(tgt[s0:e0], tgt[a:b], group=pg, async_op=True))
+            if not self.dry_comm:
+                works.append(dist.all_gather_into_tensor(tgt[s0:e0], tgt[a:b], group=pg, async_op=True))
         for w in works:
             w.wait()
 

@@ -9,16 +9,16 @@ import torch.distributed as dist
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 
 
-def case_gpt2(strategy, feed_shards=False):
+def case_gpt2(strategy, feed_shards=False, batch=4):
     from tepdist_b200.api import Trainer
     from tepdist_b200.models.gpt2 import CONFIGS, build_gpt2_graph
     cfg = CONFIGS["tiny"]
     if strategy.startswith("pp") and int(os.environ.get("WORLD_SIZE", "1")) == 1:
         strategy = "auto"   # single-process oracle
-    g = build_gpt2_graph(cfg, batch=4)
+    g = build_gpt2_graph(cfg, batch=batch)
     tr = Trainer(g, strategy=strategy, device=torch.device("cpu"), use_cuda_graph=False)
     torch.manual_seed(0)
-    tok = torch.randint(0, cfg.n_vocab, (4, cfg.n_ctx), dtype=torch.int32)
+    tok = torch.randint(0, cfg.n_vocab, (batch, cfg.n_ctx), dtype=torch.int32)
     lab = torch.roll(tok, -1, 1)
     if feed_shards and tr.world > 1:   # data-loader contract: every rank feeds only its own sequences
         per = 4 // tr.world
@@ -56,7 +56,7 @@ def case_moe(strategy):
 if __name__ == "__main__":
     case, out = sys.argv[1], sys.argv[2]
     name, _, strat = case.partition(":")
-    res = {"gpt2": case_gpt2, "gpt2s": lambda st: case_gpt2(st, True), "mlp": case_mlp, "moe": case_moe}[name](strat or "auto")
+    res = {"gpt2": case_gpt2, "gpt2s": lambda st: case_gpt2(st, True), "gpt2b1": lambda st: case_gpt2(st, False, 1), "mlp": case_mlp, "moe": case_moe}[name](strat or "auto")
     if int(os.environ.get("RANK", "0")) == 0:
         json.dump(res, open(out, "w"))
     if dist.is_initialized():

@@ -20,9 +20,9 @@ def _free_port():
     return p
 
 
-def _run(case, world, tmp_path):
+def _run(case, world, tmp_path, extra_env=None):
     out = str(tmp_path / "out.json")
-    env = dict(os.environ, CUDA_VISIBLE_DEVICES="", OMP_NUM_THREADS="2")
+    env = dict(os.environ, CUDA_VISIBLE_DEVICES="", OMP_NUM_THREADS="2", **(extra_env or {}))
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}", "--master-addr", "127.0.0.1",
            "--master-port", str(_free_port()), os.path.join(HERE, "dist_worker.py"), case, out]
     pr = subprocess.run(cmd, capture_output=True, text=True, timeout=600, env=env)
@@ -35,7 +35,7 @@ def _single(case):
     import dist_worker
     name, _, strat = case.partition(":")
     return {"gpt2": dist_worker.case_gpt2, "gpt2s": dist_worker.case_gpt2, "mlp": dist_worker.case_mlp,
-            "moe": dist_worker.case_moe}[name]("auto")
+            "gpt2b1": lambda st: dist_worker.case_gpt2(st, False, 1), "moe": dist_worker.case_moe}[name]("auto")
 
 
 @pytest.mark.parametrize("case", ["mlp:auto", "mlp:dp", "gpt2:auto", "gpt2s:auto", "gpt2:tp", "gpt2:pp2m2", "moe:ep"])
@@ -55,6 +55,17 @@ def test_spmd_world2_matches_single_process(case, tmp_path):
         assert got["parallelism"].startswith("dp"), got
 
 
+def test_long_context_plan_batch1_head_seq_all_to_all(tmp_path):
+    """One sequence per step leaves no batch dim to split: the planner shards attention over heads and everything
+    token-wise over the sequence, resharding between the two with all-to-all (the Ulysses / Megatron-SP pattern emerges
+    from the generic split->split' reshard; reference: 'token parallel' README.md:22)."""
+    ref = _single("gpt2b1:auto")
+    got = _run("gpt2b1:auto", 2, tmp_path)
+    assert got["collectives"].get("all_to_all", 0) >= 2, got
+    for a, b in zip(got["losses"], ref["losses"]):
+        assert abs(a - b) <= 2e-4 * max(1.0, abs(b)), (got, ref)
+
+
 def test_hybrid_pipeline_x_spmd_world4(tmp_path):
     """PP2 x SPMD2 x 2 micro-batches on 4 processes == single process (BASELINE config 5 in miniature)."""
     ref = _single("gpt2:auto")
@@ -62,3 +73,11 @@ def test_hybrid_pipeline_x_spmd_world4(tmp_path):
     assert got["parallelism"] == "pp2xspmd2/micro2", got
     for a, b in zip(got["losses"], ref["losses"]):
         assert abs(a - b) <= 2e-4 * max(1.0, abs(b)), (got, ref)
+
+
+def test_dry_comm_timing_mode_runs(tmp_path):
+    """TEPDIST_DRY_COMM=1 (bench.py's exposed-communication measurement) executes the sharded step with local stand-ins
+    for every collective: shapes must still line up (numerics are meaningless by design)."""
+    for case in ("gpt2:auto", "gpt2:tp"):
+        got = _run(case, 2, tmp_path, {"TEPDIST_DRY_COMM": "1"})
+        assert len(got["losses"]) == 4 and all(l == l for l in got["losses"]), got
