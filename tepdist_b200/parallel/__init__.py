@@ -137,6 +137,10 @@ def build_pipeline(graph: Graph, trainer, stages: int, micro: int, comm_mode: st
     payload = [None]
     if rank == 0:
         g2, info, tasks = plan_pipeline(graph, world, stages, micro)
+        from ..utils import trace
+        trace.log_plan(info, f"pp{info['stages']}x spmd{info['spmd']} micro{info['micro']}")
+        if trace.debug_enabled():
+            trace.dump_plan_artifacts(g2, info, extra={"local-task-lists.json": json.dumps(tasks, indent=1)})
         payload[0] = json.dumps({"graph": g2.to_dict(), "info": info, "tasks": tasks})
     dist.broadcast_object_list(payload, src=0)
     d = json.loads(payload[0])
@@ -184,6 +188,10 @@ def plan_and_build(graph: Graph, trainer, strategy: str, comm_mode: str, use_cud
     payload = [None]
     if rank == 0:
         sharded, info = plan_spmd(graph, world, strategy)
+        from ..utils import trace
+        trace.log_plan(info, classify_parallelism(info, world))
+        if trace.debug_enabled():
+            trace.dump_plan_artifacts(sharded, info)
         payload[0] = json.dumps({"graph": sharded.to_dict(), "info": {k: v for k, v in info.items() if k != "strategies_txt"}})
     dist.broadcast_object_list(payload, src=0)   # master -> workers plan dispatch (reference DispatchPlan RPC)
     d = json.loads(payload[0])

@@ -165,3 +165,26 @@ def test_service_env_load_order(tmp_path, monkeypatch):
     env.set("NUM_STAGES", "0"); env.set("RULE_MODE", "false"); env.set("COST_FACTOR", "1.0")
     with pytest.raises(IndexError):
         env.get("NOPE")
+
+
+def test_profile_and_plan_artifact_dumps(tmp_path):
+    """Executor.profile gives a per-node / per-op time table + chrome trace; DEBUG artefacts are written."""
+    import torch
+    from tepdist_b200.models.gpt2 import CONFIGS, build_gpt2_graph
+    from tepdist_b200.parallel import plan_spmd
+    from tepdist_b200.runtime.executor import Executor
+    from tepdist_b200.utils import trace
+    cfg = CONFIGS["tiny"]
+    g = build_gpt2_graph(cfg, batch=2)
+    ex = Executor(g, torch.device("cpu"), use_cuda_graph=False)
+    tok = torch.randint(0, cfg.n_vocab, (2, cfg.n_ctx), dtype=torch.int32)
+    prof = ex.profile({"tokens": tok, "labels": torch.roll(tok, -1, 1)}, chrome_trace=str(tmp_path / "trace.json"))
+    assert prof["total_ms"] > 0 and "linear" in prof["by_op"] and "optimizer" in prof["by_op"]
+    assert sum(prof["by_op"].values()) <= prof["total_ms"] * 1.05
+    ev = json.load(open(tmp_path / "trace.json"))["traceEvents"]
+    assert len(ev) == len(prof["nodes"]) > 20
+    sharded, info = plan_spmd(g, 2, "auto")
+    d = trace.dump_plan_artifacts(sharded, info, str(tmp_path / "dump"))
+    for f in ("strategies.txt", "plan.json", "step_graph.dot"):
+        assert os.path.getsize(os.path.join(d, f)) > 0
+    assert "all_reduce" in open(os.path.join(d, "step_graph.dot")).read() or "reduce_scatter" in open(os.path.join(d, "step_graph.dot")).read()
