@@ -43,13 +43,17 @@ def init_distributed(backend: Optional[str] = None) -> Dict[str, int]:
 
 class Trainer:
     def __init__(self, graph: Graph, strategy: str = "auto", device: Optional[torch.device] = None,
-                 use_cuda_graph: bool = True, seed: int = 0, comm_mode: str = "fused"):
+                 use_cuda_graph: bool = True, seed: int = 0, comm_mode: Optional[str] = None):
         self.ctx = init_distributed()
         self.world, self.rank = self.ctx["world"], self.ctx["rank"]
         if device is None:
             device = torch.device("cuda", self.ctx["local_rank"]) if torch.cuda.is_available() else torch.device("cpu")
         self.device = device
+        from . import config
+        comm_mode = config.comm_mode(comm_mode)
         self.strategy = strategy
+        self._fake_input = config.fake_input()   # FAKE_INPUT: cache the first step's inputs and reuse them
+        self._fake_feeds: Optional[Dict[str, torch.Tensor]] = None
         grad_sync = None
         self.plan_info: Dict[str, Any] = {"strategy": strategy, "world": self.world}
         if self.world > 1:
@@ -63,9 +67,14 @@ class Trainer:
     def step(self, feeds: Dict[str, torch.Tensor]) -> float:
         """One training step on this rank's shard of the batch; returns the (local) loss as a python float.
         Host tensors are copied to the device (async from pinned memory); the loss is read back."""
-        dev_feeds = {}
-        for k, t in feeds.items():
-            dev_feeds[k] = t if t.device == self.device else t.to(self.device, non_blocking=True)
+        if self._fake_input and self._fake_feeds is not None:
+            dev_feeds = self._fake_feeds
+        else:
+            dev_feeds = {}
+            for k, t in feeds.items():
+                dev_feeds[k] = t if t.device == self.device else t.to(self.device, non_blocking=True)
+            if self._fake_input:
+                self._fake_feeds = dev_feeds
         out = self.exec.step(dev_feeds)
         loss = out[0]
         if self._loss_host is not None:

@@ -29,7 +29,8 @@ def plan_spmd(graph: Graph, num: int, strategy: str = "auto", options: Optional[
         o.ignore_annotation = False
     if strategy == "tp":
         o.var_mem_limit = 1.0  # force every weight to be stored sharded -> tensor parallel
-    for k, v in options.items():
+    from .. import config
+    for k, v in {**config.spmd_overrides(), **options}.items():   # flags (ServiceEnv) < explicit call arguments
         if hasattr(o, k):
             setattr(o, k, v)
     # "dp" / "rule": annotation-driven rule mode (reference FastSpmdStrategy, RULE_MODE=true): the batch split on the
@@ -84,7 +85,8 @@ def plan_pipeline(graph: Graph, world: int, stages: int, micro: int, options: Op
     import os
     if os.environ.get("TEPDIST_SPMD_RULE_MODE") == "1":
         ap.spmd_rule_mode = True
-    for k, v in (options or {}).items():
+    from .. import config
+    for k, v in {**config.auto_parallel_overrides(), **(options or {})}.items():
         if hasattr(ap, k):
             setattr(ap, k, v)
     plan = _C.auto_parallel(cg, ap)
@@ -102,7 +104,10 @@ def plan_pipeline(graph: Graph, world: int, stages: int, micro: int, options: Op
     sp.act_bytes = [1.0] * pr.stages
     sp.boundary_bytes = [plan.stage_plan.cut_bytes / max(1, pr.stages - 1) / 2.0] * max(0, pr.stages - 1)
     dag = _C.build_pipeline_task_dag(sp)
-    sch = _C.schedule_tasks(dag, sp, _C.ScheduleOptions())
+    so = _C.ScheduleOptions()
+    for k, v in config.schedule_overrides().items():
+        setattr(so, k, v)
+    sch = _C.schedule_tasks(dag, sp, so)
     tasks = {int(dev): [{"type": dag.nodes[t].type.name, "micro": dag.nodes[t].micro, "backward": dag.nodes[t].backward,
                          "stage": dag.nodes[t].stage, "name": dag.nodes[t].name} for t in lst]
              for dev, lst in sch.device_tasks.items()}
@@ -176,6 +181,8 @@ def build_pipeline(graph: Graph, trainer, stages: int, micro: int, comm_mode: st
 
 def plan_and_build(graph: Graph, trainer, strategy: str, comm_mode: str, use_cuda_graph: bool, seed: int):
     from ..runtime.executor import Executor
+    from .. import config
+    strategy = config.resolve_strategy(strategy)
     if strategy.startswith("pp"):   # "pp<S>" or "pp<S>m<M>": config-mode pipeline (NUM_STAGES / NUM_MICRO_BATCHES)
         body = strategy[2:]
         S_, _, M_ = body.partition("m")
@@ -201,6 +208,6 @@ def plan_and_build(graph: Graph, trainer, strategy: str, comm_mode: str, use_cud
     mesh = DeviceMesh([world], [False], rank=rank, world=world)
     mesh.build_process_groups()
     trainer.mesh = mesh
-    runner = CollectiveRunner(mesh)
+    runner = CollectiveRunner(mesh, comm_dtype=config.comm_dtype())
     return Executor(sharded, trainer.device, seed=seed, use_cuda_graph=use_cuda_graph, collective=runner,
                     coords=mesh.coords(), comm_mode=comm_mode)

@@ -33,7 +33,10 @@ def logger() -> logging.Logger:
 
 
 def debug_enabled() -> bool:
-    return os.environ.get("TEPDIST_DEBUG", "0") == "1" or os.environ.get("DEBUG", "").lower() in ("1", "true")
+    if os.environ.get("TEPDIST_DEBUG", "0") == "1":
+        return True
+    from .. import config
+    return config.debug()
 
 
 def graph_to_dot(graph, max_nodes: int = 4000) -> str:

@@ -86,3 +86,41 @@ def test_launcher_cluster_spec(tmp_path):
         assert False
     except ValueError:
         pass
+
+
+def test_service_env_flags_drive_planner(monkeypatch, tmp_path):
+    """ServiceEnv keys set in the environment / CONFIG_FILE reach the planner (reference service_env.h:46-74)."""
+    import json as _json
+    from tepdist_b200 import config
+    from tepdist_b200.models.gpt2 import CONFIGS, build_gpt2_graph
+    from tepdist_b200.parallel import classify_parallelism, plan_spmd
+    g = build_gpt2_graph(CONFIGS["tiny"], batch=4)
+    # defaults: nothing explicit -> data parallel
+    for k in ("VAR_MEM_LIMIT", "RULE_MODE", "NUM_STAGES", "NUM_MICRO_BATCHES", "FP16_COMM", "CONFIG_FILE"):
+        monkeypatch.delenv(k, raising=False)
+    monkeypatch.chdir(tmp_path)
+    config.env(reload=True)
+    assert config.spmd_overrides() == {} and config.resolve_strategy("auto") == "auto" and config.comm_dtype() is None
+    _, info = plan_spmd(g, 2, "auto")
+    assert classify_parallelism(info, 2).startswith("dp")
+    # VAR_MEM_LIMIT from the environment forces weights to be stored sharded -> tensor parallel
+    monkeypatch.setenv("VAR_MEM_LIMIT", "1")
+    config.env(reload=True)
+    assert config.spmd_overrides()["var_mem_limit"] == 1.0
+    _, info = plan_spmd(g, 2, "auto")
+    assert classify_parallelism(info, 2).startswith("tp")
+    monkeypatch.delenv("VAR_MEM_LIMIT")
+    # JSON config file: pipeline config mode + 16-bit communication; environment beats the file
+    cfg = tmp_path / "cfg.json"
+    cfg.write_text(_json.dumps({"NUM_STAGES": "2", "NUM_MICRO_BATCHES": "4", "FP16_COMM": "true", "RULE_MODE": "false"}))
+    monkeypatch.setenv("CONFIG_FILE", str(cfg))
+    config.env(reload=True)
+    assert config.resolve_strategy("auto") == "pp2m4" and config.resolve_strategy("tp") == "tp"
+    import torch
+    assert config.comm_dtype() == torch.bfloat16
+    monkeypatch.setenv("NUM_STAGES", "1")
+    monkeypatch.setenv("RULE_MODE", "true")
+    config.env(reload=True)
+    assert config.resolve_strategy("auto") == "rule"
+    monkeypatch.delenv("CONFIG_FILE"); monkeypatch.delenv("NUM_STAGES"); monkeypatch.delenv("RULE_MODE")
+    config.env(reload=True)
