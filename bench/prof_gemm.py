@@ -25,3 +25,25 @@ elif which == "attn":
         o, lse = ops.attention_fwd(q, k, v)
         ops.attention_bwd(torch.randn_like(o), q, k, v, o, lse)
 torch.cuda.synchronize()
+if which == "wgrad":
+    T, N, K = 4096, 4096, 1024
+    dY = torch.randn(T, N, device="cuda", dtype=torch.bfloat16)
+    X = torch.randn(T, K, device="cuda", dtype=torch.bfloat16)
+    acc = torch.zeros(N, K, device="cuda", dtype=torch.float32)
+    for _ in range(12):
+        ops.gemm(dY, X, a_mn=True, b_mn=True, out=acc, accumulate=True)
+elif which == "adamw":
+    n = 64 << 20
+    p, g = torch.randn(n, device="cuda"), torch.randn(n, device="cuda")
+    m, v = torch.zeros(n, device="cuda"), torch.zeros(n, device="cuda")
+    pb = torch.empty(n, device="cuda", dtype=torch.bfloat16)
+    for i in range(6):
+        ops.adamw_step(p, g, m, v, pb, n, 1e-4, 0.9, 0.999, 1e-8, 0.01, i + 1)
+elif which == "ln":
+    x = torch.randn(4096, 1024, device="cuda", dtype=torch.bfloat16)
+    gmm, bta = torch.ones(1024, device="cuda"), torch.zeros(1024, device="cuda")
+    dg, db = torch.zeros(1024, device="cuda"), torch.zeros(1024, device="cuda")
+    for _ in range(6):
+        y, mean, rstd = ops.layernorm_fwd(x, gmm, bta)
+        ops.layernorm_bwd(torch.randn_like(y), x, gmm, mean, rstd, dg, db, dres=x)
+torch.cuda.synchronize()

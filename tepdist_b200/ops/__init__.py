@@ -162,8 +162,15 @@ def gemm(a: torch.Tensor, b: torch.Tensor, *, a_mn: bool = False, b_mn: bool = F
 
     assert a.dtype == torch.bfloat16 and b.dtype == torch.bfloat16
     assert a3.stride(2) == 1 and b3.stride(2) == 1 and out3.stride(2) == 1
+    if STREAM_K_FWD and split_k == 0 and block_n == 0 and not batched and not accumulate and K >= 512:
+        # wave quantisation check for the persistent 128x256 schedule: below ~93 % SM occupancy the stream-K schedule
+        # (equal k-block ranges per SM + workspace fix-up of split tiles) wins over both tile-parallel kernels
+        tiles = ((M + 127) // 128) * ((N + 255) // 256)
+        waves = -(-tiles // _sms())
+        if tiles / (waves * _sms()) < 0.93:
+            split_k = -1
     if (USE_GEMM2 and not batched and not a_mn and not accumulate and out.dtype == torch.bfloat16 and M >= 256 and N >= 256
-            and block_n == 0 and split_k <= 1):
+            and block_n == 0 and split_k in (0, 1)):
         res2 = None if residual is None else residual.reshape(M, N)
         gemm2(a, b, b_mn=b_mn, bias=bias, residual=res2, act=act, out=out, out2=out2,
               aux=None if aux is None else aux.reshape(M, N), alpha=alpha)
@@ -179,8 +186,11 @@ def gemm(a: torch.Tensor, b: torch.Tensor, *, a_mn: bool = False, b_mn: bool = F
         if accumulate and out.dtype == torch.float32:
             tiles = ((M + 127) // 128) * ((N + 255) // 256) * batch
             kb = (K + 63) // 64
-            while tiles * split_k * 2 <= _sms() and split_k * 2 <= max(1, kb // 4):
-                split_k *= 2
+            if STREAM_K and tiles * kb >= 4 * _sms():
+                split_k = -1    # stream-K: every SM gets the same number of k-blocks (fp32 red.add flush per tile)
+            else:
+                while tiles * split_k * 2 <= _sms() and split_k * 2 <= max(1, kb // 4):
+                    split_k *= 2
     rc = lib().tepd_gemm_bf16(
         a3.data_ptr(), b3.data_ptr(), out3.data_ptr(), _p(bias), _p(res3),
         M, N, K, batch, a3.stride(1), b3.stride(1), out3.stride(1),
@@ -195,6 +205,8 @@ def gemm(a: torch.Tensor, b: torch.Tensor, *, a_mn: bool = False, b_mn: bool = F
     return out
 
 
+STREAM_K_FWD = os.environ.get("TEPDIST_STREAM_K_FWD", "0") == "1"   # stream-K + fix-up for bf16-output GEMMs (opt-in)
+STREAM_K = os.environ.get("TEPDIST_STREAM_K", "1") == "1"  # stream-K scheduling for fp32-accumulate GEMMs (weight gradients)
 USE_GEMM2 = os.environ.get("TEPDIST_GEMM2", "1") == "1"   # 2-CTA (cta_group::2) kernel for eligible shapes (measured +1.7 % on the GPT-2 step)
 
 

@@ -36,7 +36,54 @@ struct GemmParams {
   int bias_bf16;
   void* D2;        // act 1: when set, D receives the pre-activation and D2 the activated value (saved for backward)
   const void* aux; // act 2: bf16 [b, M, N] pre-activation
+  float* sk_ws;        // stream-K fix-up workspace: [slot][BLOCK_M][BLOCK_N] fp32, all zero between launches
+  unsigned* sk_cnt;    // per slot: k-blocks accumulated so far
+  int stream_k;    // > 0: stream-K -- CTA c owns the contiguous range [c, c+1) * stream_k of the (tile, k-block) iteration
+                   // space and flushes its accumulator with red.add at every tile boundary (fp32 accumulate outputs only):
+                   // every SM gets the same number of k-blocks whatever the tile count (no wave quantisation)
 };
+
+// One unit of work for a CTA: k-blocks [kb0, kb1) of output tile (m_blk, n_blk, b).  `lead` = this unit holds k-block 0
+// (it adds bias / residual).  Data-parallel + split-K: cursor walks tile indices blockIdx.x, +gridDim.x, ...;
+// stream-K: cursor walks this CTA's iteration range and a unit ends at the tile boundary or at the end of the range.
+struct Work {
+  int m_blk, n_blk, b, kb0, kb1;
+  bool lead;
+};
+__device__ __forceinline__ void work_range(const GemmParams& p, int& cursor, int& end) {
+  if (p.stream_k > 0) {
+    const long long total = (long long)p.m_blocks * p.n_blocks * p.batch * p.k_blocks;
+    const long long c0 = (long long)blockIdx.x * p.stream_k;
+    cursor = (int)(c0 < total ? c0 : total);
+    end = (int)(c0 + p.stream_k < total ? c0 + p.stream_k : total);
+  } else {
+    cursor = blockIdx.x;
+    end = p.m_blocks * p.n_blocks * p.batch * p.split_k;
+  }
+}
+__device__ __forceinline__ void next_work(const GemmParams& p, int& cursor, int end, Work& w) {
+  int t;
+  if (p.stream_k > 0) {
+    t = cursor / p.k_blocks;
+    w.kb0 = cursor - t * p.k_blocks;
+    w.kb1 = min(p.k_blocks, w.kb0 + (end - cursor));
+    w.lead = w.kb0 == 0;
+    cursor += w.kb1 - w.kb0;
+  } else {
+    t = cursor;
+    cursor += gridDim.x;
+  }
+  w.m_blk = t % p.m_blocks; t /= p.m_blocks;
+  w.n_blk = t % p.n_blocks; t /= p.n_blocks;
+  w.b = t % p.batch;
+  if (p.stream_k <= 0) {
+    const int split = t / p.batch;
+    const int per = (p.k_blocks + p.split_k - 1) / p.split_k;
+    w.kb0 = split * per;
+    w.kb1 = min(p.k_blocks, w.kb0 + per);
+    w.lead = split == 0;
+  }
+}
 
 // Peer-memory fusion (tensor parallel):
 //   mode 1  GEMM -> reduce-scatter : output rows [r*rows_per_owner, (r+1)*rows_per_owner) are reduced into rank r's fp32
@@ -95,6 +142,118 @@ struct Cfg {
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
 };
 
+// Epilogue math + store for 32 consecutive columns of one output row.  v[] already holds alpha * accumulator.
+template <bool PEER>
+__device__ __forceinline__ void epilogue_chunk(float (&v)[32], const GemmParams& p, const PeerArgs* pa, int row, int col0, int b,
+                                               bool add_bias, bool add_res) {
+    if (add_bias) {
+      if (p.bias_bf16) {
+        const __nv_bfloat16* bp = reinterpret_cast<const __nv_bfloat16*>(p.bias) + col0;
+#pragma unroll
+        for (int j = 0; j < 32; ++j) if (col0 + j < p.N) v[j] += __bfloat162float(bp[j]);
+      } else {
+        const float* bp = reinterpret_cast<const float*>(p.bias) + col0;
+#pragma unroll
+        for (int j = 0; j < 32; ++j) if (col0 + j < p.N) v[j] += __ldg(bp + j);
+      }
+    }
+    const long long off = (long long)b * p.stride_d + (long long)row * p.ldd + col0;
+    if (p.act == 1) {
+      if (p.D2 != nullptr) {  // dual output: pre-activation (for backward) to D, activated value to D2
+        uint4* dp0 = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.D) + off);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          if (col0 + q * 8 < p.N) {
+            uint4 u;
+            u.x = pack_bf16x2(v[q * 8 + 0], v[q * 8 + 1]);
+            u.y = pack_bf16x2(v[q * 8 + 2], v[q * 8 + 3]);
+            u.z = pack_bf16x2(v[q * 8 + 4], v[q * 8 + 5]);
+            u.w = pack_bf16x2(v[q * 8 + 6], v[q * 8 + 7]);
+            dp0[q] = u;
+          }
+        }
+      }
+#pragma unroll
+      for (int j = 0; j < 32; ++j) v[j] = gelu_tanh(v[j]);
+    } else if (p.act == 2) {
+      const uint4* ap = reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(p.aux) + off);
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        if (col0 + q * 8 < p.N) {
+          uint4 u = __ldg(ap + q);
+          const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            float2 f = __bfloat1622float2(h[e]);
+            v[q * 8 + e * 2] *= gelu_tanh_grad(f.x);
+            v[q * 8 + e * 2 + 1] *= gelu_tanh_grad(f.y);
+          }
+        }
+      }
+    }
+    if (add_res) {
+      const uint4* rp = reinterpret_cast<const uint4*>(
+          reinterpret_cast<const __nv_bfloat16*>(p.residual) + (long long)b * p.stride_res +
+          (long long)row * p.ld_res + col0);
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        if (col0 + q * 8 < p.N) {
+          uint4 u = __ldg(rp + q);
+          const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            float2 f = __bfloat1622float2(h[e]);
+            v[q * 8 + e * 2] += f.x;
+            v[q * 8 + e * 2 + 1] += f.y;
+          }
+        }
+      }
+    }
+    if (!p.out_fp32) {
+      uint4* dp = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.D2 != nullptr && p.act == 1 ? p.D2 : p.D) + off);
+      if constexpr (PEER) {
+        if (pa->mode == 3) {  // partial rows -> slot [my rank] of the owner's staging buffer (plain stores over NVLink)
+          const int owner = row / pa->rows_per_owner;
+          dp = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(pa->out[owner]) +
+                                        ((long long)pa->rank * pa->rows_per_owner + (row - owner * pa->rows_per_owner)) * p.ldd + col0);
+        }
+      }
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        if (col0 + q * 8 < p.N) {
+          uint4 u;
+          u.x = pack_bf16x2(v[q * 8 + 0], v[q * 8 + 1]);
+          u.y = pack_bf16x2(v[q * 8 + 2], v[q * 8 + 3]);
+          u.z = pack_bf16x2(v[q * 8 + 4], v[q * 8 + 5]);
+          u.w = pack_bf16x2(v[q * 8 + 6], v[q * 8 + 7]);
+          dp[q] = u;
+        }
+      }
+    } else if (!p.accumulate) {
+      float4* dp = reinterpret_cast<float4*>(reinterpret_cast<float*>(p.D) + off);
+#pragma unroll
+      for (int q = 0; q < 8; ++q)
+        if (col0 + q * 4 < p.N) dp[q] = make_float4(v[q * 4], v[q * 4 + 1], v[q * 4 + 2], v[q * 4 + 3]);
+    } else {
+      float* dp = reinterpret_cast<float*>(p.D) + off;
+      if constexpr (PEER) {
+        if (pa->mode == 1) {  // reduce-scatter: this row belongs to rank `owner`; add into ITS buffer over NVLink
+          const int owner = row / pa->rows_per_owner;
+          dp = reinterpret_cast<float*>(pa->out[owner]) + (long long)(row - owner * pa->rows_per_owner) * p.ldd + col0;
+        }
+      }
+#pragma unroll
+      for (int q = 0; q < 8; ++q) {
+        if (col0 + q * 4 < p.N) {
+          asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dp + q * 4),
+                       "f"(v[q * 4]), "f"(v[q * 4 + 1]), "f"(v[q * 4 + 2]), "f"(v[q * 4 + 3])
+                       : "memory");
+        }
+      }
+    }
+
+}
+
 template <int BLOCK_N, bool A_MN, bool B_MN, bool PEER>
 __device__ __forceinline__ void gemm_body(const CUtensorMap& tmap_a, const CUtensorMap& tmap_b, const GemmParams& p,
                                           const PeerArgs* pa, const TmapArray* tmaps_a) {
@@ -106,6 +265,7 @@ __device__ __forceinline__ void gemm_body(const CUtensorMap& tmap_a, const CUten
   uint64_t* tmem_full = empty_bar + C::STAGES;
   uint64_t* tmem_empty = tmem_full + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+  uint32_t* sk_flag = tmem_slot + 1;
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -132,9 +292,6 @@ __device__ __forceinline__ void gemm_body(const CUtensorMap& tmap_a, const CUten
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  const int tiles_per_batch = p.m_blocks * p.n_blocks;
-  const int total_tiles = tiles_per_batch * p.batch * p.split_k;
-  const int kb_per_split = (p.k_blocks + p.split_k - 1) / p.split_k;
 
   if (warp == 0) {
     // ===================== TMA producer =====================
@@ -143,14 +300,14 @@ __device__ __forceinline__ void gemm_body(const CUtensorMap& tmap_a, const CUten
       uint32_t phase = 0;
       int peer_ready = -1;
       (void)peer_ready;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-        int t = tile;
-        int m_blk = t % p.m_blocks; t /= p.m_blocks;
-        int n_blk = t % p.n_blocks; t /= p.n_blocks;
-        const int b = t % p.batch;
-        const int split = t / p.batch;
-        const int kb0 = split * kb_per_split;
-        const int kb1 = min(p.k_blocks, kb0 + kb_per_split);
+      int cursor, cend;
+      work_range(p, cursor, cend);
+      while (cursor < cend) {
+        const int tile = cursor;
+        Work w;
+        next_work(p, cursor, cend, w);
+        int m_blk = w.m_blk, n_blk = w.n_blk;
+        const int b = w.b, kb0 = w.kb0, kb1 = w.kb1;
         const CUtensorMap* ta = &tmap_a;
         int a_row = m_blk * BLOCK_M;
         if constexpr (PEER) {
@@ -213,10 +370,12 @@ __device__ __forceinline__ void gemm_body(const CUtensorMap& tmap_a, const CUten
       uint32_t phase = 0;
       int acc = 0;
       uint32_t acc_phase = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-        int t = tile / (tiles_per_batch * p.batch);
-        const int kb0 = t * kb_per_split;
-        const int kb1 = min(p.k_blocks, kb0 + kb_per_split);
+      int cursor, cend;
+      work_range(p, cursor, cend);
+      while (cursor < cend) {
+        Work w;
+        next_work(p, cursor, cend, w);
+        const int kb0 = w.kb0, kb1 = w.kb1;
         mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + acc * BLOCK_N;
@@ -246,22 +405,31 @@ __device__ __forceinline__ void gemm_body(const CUtensorMap& tmap_a, const CUten
     const int quarter = warp & 3;
     int acc = 0;
     uint32_t acc_phase = 0;
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-      int t = tile;
-      int m_blk = t % p.m_blocks; t /= p.m_blocks;
-      int n_blk = t % p.n_blocks; t /= p.n_blocks;
-      const int b = t % p.batch;
-      const int split = t / p.batch;
-      const int kb0 = split * kb_per_split;
-      const bool has_k = kb0 < p.k_blocks;  // (always true for valid split configs)
+    int cursor, cend;
+    work_range(p, cursor, cend);
+    while (cursor < cend) {
+      const int tile = cursor;
+      Work w;
+      next_work(p, cursor, cend, w);
+      int m_blk = w.m_blk, n_blk = w.n_blk;
+      const int b = w.b;
+      const bool has_k = w.kb0 < w.kb1;
       if constexpr (PEER) peer_tile(pa, p.m_blocks, p.n_blocks, tile, m_blk, n_blk);
       mbar_wait(&tmem_full[acc], acc_phase);
       tc_fence_after();
       const int row = m_blk * BLOCK_M + quarter * 32 + lane;
       const bool row_ok = row < p.M;
       const uint32_t t_row = tmem_base + (uint32_t(quarter * 32) << 16) + acc * BLOCK_N;
-      const bool add_bias = p.bias != nullptr && split == 0;
-      const bool add_res = p.residual != nullptr && split == 0;
+      const bool add_bias = p.bias != nullptr && w.lead;
+      const bool add_res = p.residual != nullptr && w.lead;
+      const bool fixup = p.stream_k > 0 && !p.accumulate && !(w.kb0 == 0 && w.kb1 == p.k_blocks);
+      int slot = 0;
+      float* ws_row = nullptr;
+      if (fixup) {  // this unit is one of several that make up the tile: partial sums meet in a workspace slot
+        const int tile_it0 = (tile - w.kb0);  // first iteration index of this tile (cursor before next_work = tile's it + kb0)
+        slot = tile_it0 / p.stream_k + 1;     // index of the first CTA-range boundary strictly inside the tile
+        ws_row = p.sk_ws + ((long long)slot * BLOCK_M + quarter * 32 + lane) * BLOCK_N;
+      }
 #pragma unroll 1
       for (int c = 0; c < BLOCK_N / 32; ++c) {
         uint32_t r[32];
@@ -272,116 +440,54 @@ __device__ __forceinline__ void gemm_body(const CUtensorMap& tmap_a, const CUten
           float v[32];
 #pragma unroll
           for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]) * p.alpha;
-          if (add_bias) {
-            if (p.bias_bf16) {
-              const __nv_bfloat16* bp = reinterpret_cast<const __nv_bfloat16*>(p.bias) + col0;
-#pragma unroll
-              for (int j = 0; j < 32; ++j) if (col0 + j < p.N) v[j] += __bfloat162float(bp[j]);
-            } else {
-              const float* bp = reinterpret_cast<const float*>(p.bias) + col0;
-#pragma unroll
-              for (int j = 0; j < 32; ++j) if (col0 + j < p.N) v[j] += __ldg(bp + j);
-            }
-          }
-          const long long off = (long long)b * p.stride_d + (long long)row * p.ldd + col0;
-          if (p.act == 1) {
-            if (p.D2 != nullptr) {  // dual output: pre-activation (for backward) to D, activated value to D2
-              uint4* dp0 = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.D) + off);
-#pragma unroll
-              for (int q = 0; q < 4; ++q) {
-                if (col0 + q * 8 < p.N) {
-                  uint4 u;
-                  u.x = pack_bf16x2(v[q * 8 + 0], v[q * 8 + 1]);
-                  u.y = pack_bf16x2(v[q * 8 + 2], v[q * 8 + 3]);
-                  u.z = pack_bf16x2(v[q * 8 + 4], v[q * 8 + 5]);
-                  u.w = pack_bf16x2(v[q * 8 + 6], v[q * 8 + 7]);
-                  dp0[q] = u;
-                }
-              }
-            }
-#pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] = gelu_tanh(v[j]);
-          } else if (p.act == 2) {
-            const uint4* ap = reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(p.aux) + off);
-#pragma unroll
-            for (int q = 0; q < 4; ++q) {
-              if (col0 + q * 8 < p.N) {
-                uint4 u = __ldg(ap + q);
-                const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
-#pragma unroll
-                for (int e = 0; e < 4; ++e) {
-                  float2 f = __bfloat1622float2(h[e]);
-                  v[q * 8 + e * 2] *= gelu_tanh_grad(f.x);
-                  v[q * 8 + e * 2 + 1] *= gelu_tanh_grad(f.y);
-                }
-              }
-            }
-          }
-          if (add_res) {
-            const uint4* rp = reinterpret_cast<const uint4*>(
-                reinterpret_cast<const __nv_bfloat16*>(p.residual) + (long long)b * p.stride_res +
-                (long long)row * p.ld_res + col0);
-#pragma unroll
-            for (int q = 0; q < 4; ++q) {
-              if (col0 + q * 8 < p.N) {
-                uint4 u = __ldg(rp + q);
-                const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
-#pragma unroll
-                for (int e = 0; e < 4; ++e) {
-                  float2 f = __bfloat1622float2(h[e]);
-                  v[q * 8 + e * 2] += f.x;
-                  v[q * 8 + e * 2 + 1] += f.y;
-                }
-              }
-            }
-          }
-          if (!p.out_fp32) {
-            uint4* dp = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.D2 != nullptr && p.act == 1 ? p.D2 : p.D) + off);
-            if constexpr (PEER) {
-              if (pa->mode == 3) {  // partial rows -> slot [my rank] of the owner's staging buffer (plain stores over NVLink)
-                const int owner = row / pa->rows_per_owner;
-                dp = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(pa->out[owner]) +
-                                              ((long long)pa->rank * pa->rows_per_owner + (row - owner * pa->rows_per_owner)) * p.ldd + col0);
-              }
-            }
-#pragma unroll
-            for (int q = 0; q < 4; ++q) {
-              if (col0 + q * 8 < p.N) {
-                uint4 u;
-                u.x = pack_bf16x2(v[q * 8 + 0], v[q * 8 + 1]);
-                u.y = pack_bf16x2(v[q * 8 + 2], v[q * 8 + 3]);
-                u.z = pack_bf16x2(v[q * 8 + 4], v[q * 8 + 5]);
-                u.w = pack_bf16x2(v[q * 8 + 6], v[q * 8 + 7]);
-                dp[q] = u;
-              }
-            }
-          } else if (!p.accumulate) {
-            float4* dp = reinterpret_cast<float4*>(reinterpret_cast<float*>(p.D) + off);
+          if (!fixup) {
+            epilogue_chunk<PEER>(v, p, pa, row, col0, b, add_bias, add_res);
+          } else {
+            float* wp = ws_row + c * 32;
 #pragma unroll
             for (int q = 0; q < 8; ++q)
-              if (col0 + q * 4 < p.N) dp[q] = make_float4(v[q * 4], v[q * 4 + 1], v[q * 4 + 2], v[q * 4 + 3]);
-          } else {
-            float* dp = reinterpret_cast<float*>(p.D) + off;
-            if constexpr (PEER) {
-              if (pa->mode == 1) {  // reduce-scatter: this row belongs to rank `owner`; add into ITS buffer over NVLink
-                const int owner = row / pa->rows_per_owner;
-                dp = reinterpret_cast<float*>(pa->out[owner]) + (long long)(row - owner * pa->rows_per_owner) * p.ldd + col0;
-              }
-            }
-#pragma unroll
-            for (int q = 0; q < 8; ++q) {
-              if (col0 + q * 4 < p.N) {
-                asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dp + q * 4),
-                             "f"(v[q * 4]), "f"(v[q * 4 + 1]), "f"(v[q * 4 + 2]), "f"(v[q * 4 + 3])
-                             : "memory");
-              }
-            }
+              asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(wp + q * 4), "f"(v[q * 4]), "f"(v[q * 4 + 1]),
+                           "f"(v[q * 4 + 2]), "f"(v[q * 4 + 3]) : "memory");
           }
         }
       }
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+      if (fixup) {
+        // the last unit to arrive (k-blocks add up to the full K) reads the summed tile back and runs the real epilogue
+        __threadfence();
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        if (threadIdx.x == 64) {
+          const int mine = w.kb1 - w.kb0;
+          const unsigned prev = atomicAdd(p.sk_cnt + slot, (unsigned)mine);
+          *sk_flag = (prev + mine == (unsigned)p.k_blocks) ? 1u : 0u;
+        }
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        const bool finisher = *reinterpret_cast<volatile uint32_t*>(sk_flag) != 0;
+        if (finisher) {
+          __threadfence();
+          const bool ab = p.bias != nullptr, ar = p.residual != nullptr;
+#pragma unroll 1
+          for (int c = 0; c < BLOCK_N / 32; ++c) {
+            const int col0 = n_blk * BLOCK_N + c * 32;
+            if (row_ok && col0 < p.N) {
+              float v[32];
+              float4* wp = reinterpret_cast<float4*>(ws_row + c * 32);
+#pragma unroll
+              for (int q = 0; q < 8; ++q) {
+                float4 t;
+                asm volatile("ld.global.cg.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(t.x), "=f"(t.y), "=f"(t.z), "=f"(t.w) : "l"(wp + q));
+                v[q * 4] = t.x; v[q * 4 + 1] = t.y; v[q * 4 + 2] = t.z; v[q * 4 + 3] = t.w;
+                wp[q] = make_float4(0.f, 0.f, 0.f, 0.f);   // leave the slot clean for the next launch
+              }
+              epilogue_chunk<PEER>(v, p, pa, row, col0, b, ab, ar);
+            }
+          }
+        }
+        asm volatile("bar.sync 1, 128;" ::: "memory");   // sk_flag is reused by the next unit
+        if (finisher && threadIdx.x == 64) p.sk_cnt[slot] = 0;
+      }
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
   }
@@ -459,6 +565,10 @@ static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const GemmP
   }
   int total = p.m_blocks * p.n_blocks * p.batch * p.split_k;
   int grid = total < num_sms ? total : num_sms;
+  if (p.stream_k > 0) {
+    const long long iters = (long long)p.m_blocks * p.n_blocks * p.batch * p.k_blocks;
+    grid = (int)((iters + p.stream_k - 1) / p.stream_k);
+  }
   kern<<<grid, NUM_THREADS, C::SMEM_BYTES, stream>>>(ta, tb, p);
   return (int)cudaGetLastError();
 }
@@ -479,6 +589,35 @@ extern "C" int tepd_gemm_bf16(const void* A, const void* B, void* D, const void*
   p.m_blocks = (M + BLOCK_M - 1) / BLOCK_M;
   p.n_blocks = (N + block_n - 1) / block_n;
   p.k_blocks = (K + BLOCK_K - 1) / BLOCK_K;
+  p.stream_k = 0; p.sk_ws = nullptr; p.sk_cnt = nullptr;
+  if (num_sms <= 0) num_sms = 148;
+  if (split_k < 0) {  // stream-K requested: equal k-block ranges per SM
+    const long long iters = (long long)p.m_blocks * p.n_blocks * batch * p.k_blocks;
+    long long per = (iters + num_sms - 1) / num_sms;
+    if (per < 4) per = 4;   // do not shred tiny problems into sub-4-k-block units
+    p.stream_k = (int)per;
+    split_k = 1;
+    if (!(out_fp32 && accumulate)) {
+      // outputs with a real epilogue: partial tiles meet in a per-device fp32 workspace (one slot per CTA-range
+      // boundary); allocated once, kept all-zero between launches by the finishing CTA.  GEMMs of one device must not
+      // run concurrently on two streams in this mode.
+      constexpr int kSlots = 160;
+      static float* ws[16] = {nullptr};
+      static unsigned* cnt[16] = {nullptr};
+      int dev = 0;
+      cudaGetDevice(&dev);
+      if (num_sms + 1 > kSlots || dev >= 16) return -6;
+      if (ws[dev] == nullptr) {
+        const size_t bytes = (size_t)kSlots * BLOCK_M * 256 * sizeof(float);
+        if (cudaMalloc(&ws[dev], bytes) != cudaSuccess) return -7;
+        if (cudaMalloc(&cnt[dev], kSlots * sizeof(unsigned)) != cudaSuccess) return -7;
+        cudaMemset(ws[dev], 0, bytes);
+        cudaMemset(cnt[dev], 0, kSlots * sizeof(unsigned));
+        cudaDeviceSynchronize();
+      }
+      p.sk_ws = ws[dev]; p.sk_cnt = cnt[dev];
+    }
+  }
   if (split_k < 1) split_k = 1;
   if (split_k > p.k_blocks) split_k = p.k_blocks;
   if (split_k > 1) {
@@ -502,7 +641,6 @@ extern "C" int tepd_gemm_bf16(const void* A, const void* B, void* D, const void*
   else       rc = tepd_make_tmap_bf16_3d(&tb, B, N, K, batch, ldb, stride_b, 64, BLOCK_K);
   if (rc) return 200 + rc;
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
-  if (num_sms <= 0) num_sms = 148;
 #define DISPATCH(BN)                                                                   \
   if (!a_mn && !b_mn) return launch_gemm<BN, false, false>(ta, tb, p, num_sms, s);     \
   if (!a_mn && b_mn) return launch_gemm<BN, false, true>(ta, tb, p, num_sms, s);       \
@@ -549,7 +687,7 @@ extern "C" int tepd_gemm_bf16_peer(int mode, void* const* a_ptrs, const void* B,
   p.m_blocks = M / BLOCK_M;
   p.n_blocks = (N + block_n - 1) / block_n;
   p.k_blocks = (K + BLOCK_K - 1) / BLOCK_K;
-  p.split_k = 1;
+  p.split_k = 1; p.stream_k = 0; p.sk_ws = nullptr; p.sk_cnt = nullptr;
   p.ldd = ldd; p.stride_d = 0; p.ld_res = 0; p.stride_res = 0;
   const bool gather = mode == 2 || mode == 4;
   p.D = D; p.bias = gather ? bias : nullptr; p.residual = nullptr; p.alpha = 1.0f;

@@ -97,6 +97,38 @@ def check_gemm_epilogues():
     acc = torch.zeros(N, K, device="cuda", dtype=torch.float32)
     ops.gemm(dY, X, a_mn=True, b_mn=True, out=acc, accumulate=True)
     out["wgrad"] = _rel_err(acc, dY.float().t() @ X.float())
+    # stream-K scheduling (split_k=-1) on tile counts that do not divide the SM count, incl. ragged edges, + bias on the
+    # leading unit only; and the explicit data-parallel schedule for comparison
+    for (Ns, Ks, Ts) in [(3072, 1024, 4096), (1024, 1024, 4096), (1000, 520, 1096), (384, 256, 8192)]:
+        dYs = torch.randn(Ts, Ns, device="cuda", dtype=torch.bfloat16)
+        Xs = torch.randn(Ts, Ks, device="cuda", dtype=torch.bfloat16)
+        refs = dYs.float().t() @ Xs.float()
+        for sk in (-1, 1):
+            acc = torch.ones(Ns, Ks, device="cuda", dtype=torch.float32)
+            ops.gemm(dYs, Xs, a_mn=True, b_mn=True, out=acc, accumulate=True, split_k=sk)
+            out[f"streamk{sk}_{Ns}x{Ks}x{Ts}"] = _rel_err(acc, 1.0 + refs)
+    bs = torch.randn(N, device="cuda", dtype=torch.float32)
+    acc = torch.zeros(M, N, device="cuda", dtype=torch.float32)
+    ops.gemm(A, W, bias=bs, out=acc, accumulate=True, split_k=-1)
+    out["streamk_bias"] = _rel_err(acc, A.float() @ W.float().t() + bs)
+    # stream-K with workspace fix-up for outputs that have a real epilogue (bf16 / fp32 stores, bias, GELU, residual);
+    # run every case twice: the second launch only passes if the finisher left the workspace clean
+    for (Ms, Ns, Ks) in [(4096, 1024, 1024), (4096, 3072, 1024), (1000, 520, 2048), (384, 256, 4096)]:
+        As = torch.randn(Ms, Ks, device="cuda", dtype=torch.bfloat16)
+        Ws = torch.randn(Ns, Ks, device="cuda", dtype=torch.bfloat16) * 0.05
+        bss = torch.randn(Ns, device="cuda", dtype=torch.float32)
+        rs = torch.randn(Ms, Ns, device="cuda", dtype=torch.bfloat16)
+        refs = As.float() @ Ws.float().t() + bss
+        for rep in range(2):
+            d = ops.gemm(As, Ws, bias=bss, residual=rs, split_k=-1)
+            out[f"skfix_res_{Ms}x{Ns}x{Ks}_{rep}"] = _rel_err(d, refs + rs.float())
+        d = ops.gemm(As, Ws, bias=bss, act="gelu", split_k=-1)
+        out[f"skfix_gelu_{Ms}x{Ns}x{Ks}"] = _rel_err(d, torch.nn.functional.gelu(refs, approximate="tanh"))
+        d = ops.gemm(As, Ws, out_dtype=torch.float32, split_k=-1)
+        out[f"skfix_fp32_{Ms}x{Ns}x{Ks}"] = _rel_err(d, refs - bss)
+        Wt = Ws.t().contiguous()                        # dgrad layout: B stored [K, N]
+        d = ops.gemm(As, Wt, b_mn=True, split_k=-1)
+        out[f"skfix_bmn_{Ms}x{Ns}x{Ks}"] = _rel_err(d, refs - bss)
     # dual-output GELU (pre-activation + activation in one pass) and fused GELU backward on a dgrad-layout GEMM
     pre, act = torch.empty(M, N, device="cuda", dtype=torch.bfloat16), torch.empty(M, N, device="cuda", dtype=torch.bfloat16)
     ops.gemm(A, W, bias=bias, act="gelu", out=pre, out2=act)
@@ -179,6 +211,34 @@ def check_gemm_perf():
     out["ours_wgrad_4096tok_1024x4096_tflops"] = 2.0 * T * N * K / ms / 1e9
     ms = _time_ms(lambda: torch.matmul(dY.t(), X))
     out["cublas_wgrad_tflops"] = 2.0 * T * N * K / ms / 1e9
+    # stream-K + fix-up vs the tile-parallel 1-CTA / 2-CTA kernels and cuBLAS on the forward and dgrad shapes
+    for (M, N, K, bmn) in [(4096, 3072, 1024, False), (4096, 1024, 1024, False), (4096, 4096, 1024, False), (4096, 1024, 4096, False),
+                           (4096, 1024, 3072, True), (4096, 1024, 4096, True), (4096, 4096, 1024, True)]:
+        A = torch.randn(M, K, device="cuda", dtype=torch.bfloat16)
+        W = torch.randn(K, N, device="cuda", dtype=torch.bfloat16) if bmn else torch.randn(N, K, device="cuda", dtype=torch.bfloat16)
+        tag = f"{M}x{N}x{K}{'_bmn' if bmn else ''}"
+        ms = _time_ms(lambda: ops.gemm(A, W, b_mn=bmn, split_k=-1))
+        out[f"streamk_fix_{tag}_tflops"] = 2.0 * M * N * K / ms / 1e9
+        ms = _time_ms(lambda: ops.gemm(A, W, b_mn=bmn, block_n=256))
+        out[f"cta1_{tag}_tflops"] = 2.0 * M * N * K / ms / 1e9
+        ms = _time_ms(lambda: ops.gemm2(A, W, b_mn=bmn))
+        out[f"cta2_{tag}_tflops"] = 2.0 * M * N * K / ms / 1e9
+        ms = _time_ms(lambda: torch.matmul(A, W if bmn else W.t()))
+        out[f"cublas_{tag}_tflops"] = 2.0 * M * N * K / ms / 1e9
+    # stream-K vs the data-parallel / split-K schedule on the four GPT-2 345M weight-gradient shapes (4096 tokens)
+    for (N, K) in [(3072, 1024), (1024, 1024), (4096, 1024), (1024, 4096)]:
+        dY = torch.randn(T, N, device="cuda", dtype=torch.bfloat16)
+        X = torch.randn(T, K, device="cuda", dtype=torch.bfloat16)
+        acc = torch.zeros(N, K, device="cuda", dtype=torch.float32)
+        for tag, sk in (("streamk", -1), ("dp", 1), ("auto_old", 0)):
+            if tag == "auto_old":
+                ops.STREAM_K, prev = False, ops.STREAM_K
+            ms = _time_ms(lambda: ops.gemm(dY, X, a_mn=True, b_mn=True, out=acc, accumulate=True, split_k=sk))
+            if tag == "auto_old":
+                ops.STREAM_K = prev
+            out[f"wgrad_{N}x{K}_{tag}_tflops"] = 2.0 * T * N * K / ms / 1e9
+        ms = _time_ms(lambda: torch.matmul(dY.t(), X))
+        out[f"wgrad_{N}x{K}_cublas_tflops"] = 2.0 * T * N * K / ms / 1e9
     return out
 
 
