@@ -24,6 +24,9 @@ from .. import ops
 from ..ir import SOURCE_OPS, Graph, Node, TensorType, Value
 from ..utils.init import init_tensor
 
+# weight gradients with a single producer are written with plain stores instead of fp32 atomics into a zero-filled slot
+WGRAD_PLAIN_STORE = os.environ.get("TEPDIST_WGRAD_STORE", "1") == "1"
+
 _TORCH_DTYPE = {"bf16": torch.bfloat16, "f16": torch.float16, "f32": torch.float32, "i32": torch.int32,
                 "i64": torch.int64, "bool": torch.bool}
 _ALIGN = 128  # elements; keeps every variable slice 16-B aligned in every dtype
@@ -295,6 +298,8 @@ class Executor:
                 self.free_after.setdefault(nid, []).append(k_)
         self.ln_stats: Dict[Tuple[Tuple[int, int], Tuple[int, int]], Tuple[torch.Tensor, torch.Tensor]] = {}
         self.input_names = [n.name for n in g.inputs()]
+        self.grad_accumulate = False   # True when gradients add up over micro-batches (pipeline stage workers)
+        self._plan_store_init()
 
     @staticmethod
     def _analyze_flat_zero(g: Graph) -> Optional[Dict[str, Any]]:
@@ -382,9 +387,14 @@ class Executor:
         offs = [(o, p) for o, p in offs if o < end]
         if not offs:
             return
+        # graded bucket sizes: the variables at the front of the flat buffer belong to the first layers, whose gradients
+        # are produced LAST by the backward pass -- whatever is still in flight when backward ends is exposed, so the
+        # buckets that become ready last are small (4M elements, doubling up to bucket_elems)
+        first = int(self.opt.get("first_bucket_elems", os.environ.get("TEPDIST_FIRST_BUCKET", 4 * 1024 * 1024)))
         bounds = [0]
         for off, p in offs[1:]:
-            if off - bounds[-1] >= bucket_elems and off % gran == 0:
+            want = min(bucket_elems, first << min(len(bounds) - 1, 16))
+            if off - bounds[-1] >= want and off % gran == 0:
                 bounds.append(off)
         bounds.append(end)
         buckets = [(bounds[i], bounds[i + 1]) for i in range(len(bounds) - 1)]
@@ -541,7 +551,7 @@ class Executor:
     def _run(self, feeds: Dict[str, torch.Tensor]) -> List[torch.Tensor]:
         g = self.g
         env: Dict[Tuple[int, int], torch.Tensor] = {}
-        self.store.grad.zero_()  # GAInit
+        self._zero_grads()  # GAInit
         launches0 = ops.launch_count()
 
         def run_node(n: Node) -> None:
@@ -741,6 +751,46 @@ class Executor:
         elif kind == "sgd":
             ops.sgd_step(st.master, st.grad, st.compute, o.get("lr", 1e-2))
 
+    def _plan_store_init(self) -> None:
+        """Gradient slots whose only writer is a weight-gradient GEMM can be written with plain stores (beta = 0) and need
+        no zero-fill; everything else (bias / LayerNorm / embedding gradients: accumulating kernels) is zero-filled as
+        contiguous ranges of the flat gradient buffer."""
+        self._store_init: set = set()
+        self._zero_ranges: Optional[List[Tuple[int, int]]] = None
+        if not WGRAD_PLAIN_STORE or self.grad_accumulate or not self.store.master.is_cuda:
+            return
+        st = self.store
+        self_init_params = set()
+        for (nid, idx), pid in self.grad_binding.items():
+            n = self.g.nodes[nid]
+            if n.op == "linear_wgrad" and idx == 0 and n.id not in self.alias_of:
+                self._store_init.add((nid, idx))
+                self_init_params.add(pid)
+        for n in self.g.nodes:   # unbound weight gradients (general path) are fresh tensors anyway
+            if n.op == "linear_wgrad" and (n.id, 0) not in self.grad_binding:
+                self._store_init.add((n.id, 0))
+        ranges: List[Tuple[int, int]] = []
+        cur = 0
+        for pid in st.order:
+            if pid in self_init_params:
+                n_el = 1
+                for d in st.shape[pid]:
+                    n_el *= d
+                if st.offset[pid] > cur:
+                    ranges.append((cur, st.offset[pid]))
+                cur = st.offset[pid] + n_el
+        if cur < st.grad.numel():
+            ranges.append((cur, st.grad.numel()))
+        self._zero_ranges = ranges
+
+    def _zero_grads(self) -> None:
+        zr = getattr(self, "_zero_ranges", None)
+        if zr is None:
+            self.store.grad.zero_()
+            return
+        for a, b in zr:
+            self.store.grad[a:b].zero_()
+
     # ------------------------------------------------------------------ node dispatch
     def _grad_out(self, n: Node, idx: int, shape) -> torch.Tensor:
         pid = self.grad_binding.get((n.id, idx))
@@ -831,8 +881,15 @@ class Executor:
             return [dx.view(*dy.shape[:-1], w.shape[1])]
         if op == "linear_wgrad":
             dy, x = ins
-            out = self._grad_out(n, 0, n.outputs[0].shape)
-            ops.gemm(dy.reshape(-1, dy.shape[-1]), x.reshape(-1, x.shape[-1]), a_mn=True, b_mn=True, out=out, accumulate=True)
+            acc = self.grad_accumulate or (n.id, 0) not in self._store_init
+            if not acc and (n.id, 0) not in self.grad_binding:
+                out = torch.empty(n.outputs[0].shape, dtype=torch.float32, device=dev)
+            else:
+                out = self._grad_out(n, 0, n.outputs[0].shape)
+            # sole producer of this gradient in a step without micro-batch accumulation: plain fp32 stores (beta = 0),
+            # no atomics and no zero-fill of the slot beforehand
+            ops.gemm(dy.reshape(-1, dy.shape[-1]), x.reshape(-1, x.shape[-1]), a_mn=True, b_mn=True, out=out, accumulate=acc,
+                     split_k=0 if acc else 1)
             return [out]
         if op == "colsum":
             out = self._grad_out(n, 0, n.outputs[0].shape)

@@ -73,6 +73,8 @@ class StageWorker:
         mine = [n for n in g.nodes if n.stage == stage]
         self.sub, self.idmap = self._extract(g, mine)
         self.exec = Executor(self.sub, device, seed=seed, collective=collective, coords=dict(coords or {}), comm_mode=comm_mode)
+        self.exec.grad_accumulate = True    # gradients accumulate over micro-batches: atomically-added, zero-filled slots
+        self.exec._plan_store_init()
         ex = self.exec
         self.fwd_nodes = [n for n in self.sub.nodes if not n.backward and n.op not in ("state", "boundary") and n.id not in ex.post_apply]
         self.bwd_nodes = [n for n in self.sub.nodes if n.backward and n.id not in ex.post_apply and not n.op.startswith("apply_")]

@@ -225,11 +225,23 @@ def check_gemm_perf():
         out[f"cta2_{tag}_tflops"] = 2.0 * M * N * K / ms / 1e9
         ms = _time_ms(lambda: torch.matmul(A, W if bmn else W.t()))
         out[f"cublas_{tag}_tflops"] = 2.0 * M * N * K / ms / 1e9
+    # wave-quantisation probe: 37 m-blocks x {4, 16} n-blocks = exact multiples of 148 tiles vs the 32 m-block shapes
+    for (M, N, K) in [(4736, 1024, 4096), (4736, 4096, 1024), (4736, 3072, 1024)]:
+        A = torch.randn(M, K, device="cuda", dtype=torch.bfloat16)
+        W = torch.randn(N, K, device="cuda", dtype=torch.bfloat16)
+        ms = _time_ms(lambda: ops.gemm(A, W, block_n=256))
+        out[f"probe_cta1_{M}x{N}x{K}_tflops"] = 2.0 * M * N * K / ms / 1e9
+        ms = _time_ms(lambda: ops.gemm2(A, W))
+        out[f"probe_cta2_{M}x{N}x{K}_tflops"] = 2.0 * M * N * K / ms / 1e9
+        ms = _time_ms(lambda: torch.matmul(A, W.t()))
+        out[f"probe_cublas_{M}x{N}x{K}_tflops"] = 2.0 * M * N * K / ms / 1e9
     # stream-K vs the data-parallel / split-K schedule on the four GPT-2 345M weight-gradient shapes (4096 tokens)
     for (N, K) in [(3072, 1024), (1024, 1024), (4096, 1024), (1024, 4096)]:
         dY = torch.randn(T, N, device="cuda", dtype=torch.bfloat16)
         X = torch.randn(T, K, device="cuda", dtype=torch.bfloat16)
         acc = torch.zeros(N, K, device="cuda", dtype=torch.float32)
+        ms = _time_ms(lambda: ops.gemm(dY, X, a_mn=True, b_mn=True, out=acc, accumulate=False, split_k=1))
+        out[f"wgrad_{N}x{K}_plainstore_tflops"] = 2.0 * T * N * K / ms / 1e9
         for tag, sk in (("streamk", -1), ("dp", 1), ("auto_old", 0)):
             if tag == "auto_old":
                 ops.STREAM_K, prev = False, ops.STREAM_K
