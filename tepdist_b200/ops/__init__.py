@@ -66,7 +66,7 @@ _vp, _i, _ll, _f = ctypes.c_void_p, ctypes.c_int, ctypes.c_longlong, ctypes.c_fl
 class _Sig:
     tepd_gemm_bf16 = [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _ll, _ll, _ll, _ll, _ll, _ll, _ll, _ll,
                       _i, _i, _i, _i, _i, _i, _f, _i, _i, _i, _vp, _vp, _vp]
-    tepd_gemm2_bf16 = [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _ll, _ll, _ll, _ll, _i, _i, _i, _f, _i, _vp]
+    tepd_gemm2_bf16 = [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _ll, _ll, _ll, _ll, _i, _i, _i, _f, _i, _vp, _i, _i, _i]
     tepd_layernorm_fwd = [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _f, _vp]
     tepd_layernorm_bwd = [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _vp]
     tepd_gelu_fwd = [_vp, _vp, _ll, _vp]
@@ -175,6 +175,10 @@ def gemm(a: torch.Tensor, b: torch.Tensor, *, a_mn: bool = False, b_mn: bool = F
         gemm2(a, b, b_mn=b_mn, bias=bias, residual=res2, act=act, out=out, out2=out2,
               aux=None if aux is None else aux.reshape(M, N), alpha=alpha)
         return out
+    if (USE_GEMM2 and not batched and a_mn and b_mn and not accumulate and out.dtype == torch.float32 and M >= 256 and N >= 256
+            and block_n == 0 and split_k in (0, 1) and bias is None and residual is None and act is None):
+        gemm2(a, b, a_mn=True, b_mn=True, out=out, alpha=alpha)     # weight gradient with plain stores
+        return out
     if bias is not None:
         assert bias.dtype in (torch.float32, torch.bfloat16) and bias.is_contiguous()
     res3 = None
@@ -210,19 +214,42 @@ STREAM_K = os.environ.get("TEPDIST_STREAM_K", "1") == "1"  # stream-K scheduling
 USE_GEMM2 = os.environ.get("TEPDIST_GEMM2", "1") == "1"   # 2-CTA (cta_group::2) kernel for eligible shapes (measured +1.7 % on the GPT-2 step)
 
 
-def gemm2(a: torch.Tensor, b: torch.Tensor, *, b_mn: bool = False, bias: Optional[torch.Tensor] = None,
+def wgrad_prefers_store(n_out: int, k_in: int) -> bool:
+    """Weight gradient [n_out, k_in]: plain-store 2-CTA GEMM when the 256x256 tiles fill at least half of the CTA pairs;
+    smaller outputs are better off split over K with fp32 red.add into a zero-filled slot (1-CTA kernel)."""
+    tiles = ((n_out + 255) // 256) * ((k_in + 255) // 256)
+    return USE_GEMM2 and n_out >= 256 and k_in >= 256 and n_out % 8 == 0 and k_in % 8 == 0 and tiles * 2 >= _sms() // 2
+
+
+def _gemm2_stream_k(M: int, N: int, K: int, fp32_out: bool) -> bool:
+    """Measured (profiles/kernel_checks_trip22.json): the stream-K schedule of the 2-CTA kernel only pays for very large
+    plain-store outputs (lm_head weight gradient 50304x1024: 1466 vs 1245 TFLOP/s); on the 64..256-tile transformer shapes
+    the fix-up of split tiles (uncoalesced fp32 partial tiles through L2) costs more than the idle tail wave it removes."""
+    if not STREAM_K or not fp32_out:
+        return False
+    tiles = ((M + 255) // 256) * ((N + 255) // 256)
+    return tiles >= 8 * (_sms() // 2)
+
+
+def gemm2(a: torch.Tensor, b: torch.Tensor, *, a_mn: bool = False, b_mn: bool = False, bias: Optional[torch.Tensor] = None,
           residual: Optional[torch.Tensor] = None, act: Optional[str] = None, out: Optional[torch.Tensor] = None,
-          out2: Optional[torch.Tensor] = None, aux: Optional[torch.Tensor] = None, alpha: float = 1.0) -> torch.Tensor:
-    """2-CTA tcgen05 GEMM (256x256 tile per CTA pair): a [M,K] bf16, b [N,K] (or [K,N] with b_mn), bf16 output."""
-    M, K = a.shape
+          out2: Optional[torch.Tensor] = None, aux: Optional[torch.Tensor] = None, alpha: float = 1.0,
+          out_dtype: torch.dtype = torch.bfloat16, stream_k: Optional[bool] = None) -> torch.Tensor:
+    """2-CTA tcgen05 GEMM (256x256 tile per CTA pair): a [M,K] (or [K,M] with a_mn), b [N,K] (or [K,N] with b_mn);
+    bf16 output with the fused epilogues or fp32 plain stores.  stream_k: None = decide from the wave occupancy."""
+    M, K = (a.shape[1], a.shape[0]) if a_mn else a.shape
     N = b.shape[1] if b_mn else b.shape[0]
     if out is None:
-        out = torch.empty(M, N, dtype=torch.bfloat16, device=a.device)
+        out = torch.empty(M, N, dtype=out_dtype, device=a.device)
     assert a.is_cuda and a.dtype == torch.bfloat16 and a.stride(1) == 1 and b.stride(1) == 1 and out.stride(1) == 1
+    assert out.dtype in (torch.bfloat16, torch.float32)
+    if stream_k is None:
+        stream_k = _gemm2_stream_k(M, N, K, out.dtype == torch.float32)
     rc = lib().tepd_gemm2_bf16(a.data_ptr(), b.data_ptr(), out.data_ptr(), _p(out2), _p(bias), _p(residual), _p(aux), M, N, K,
                                a.stride(0), b.stride(0), out.stride(0), residual.stride(0) if residual is not None else 0,
                                int(b_mn), {None: 0, "gelu": 1, "gelu_bwd": 2}[act],
-                               int(bias is not None and bias.dtype == torch.bfloat16), float(alpha), _sms(), _stream())
+                               int(bias is not None and bias.dtype == torch.bfloat16), float(alpha), _sms(), _stream(),
+                               int(a_mn), int(out.dtype == torch.float32), int(bool(stream_k)))
     _check(rc, "gemm2_bf16")
     _count()
     return out

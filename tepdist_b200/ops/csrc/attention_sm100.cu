@@ -7,6 +7,7 @@
 // The reference gets attention from XLA-fused batched dots + softmax fusions;
 // this kernel is the B200-native replacement.
 #include "sm100_ptx.cuh"
+#include "launch.cuh"
 #include <stdio.h>
 
 using namespace sm100;
@@ -85,6 +86,8 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();      // (launch.cuh) the prologue above ran under the previous kernel's tail
+  pdl_trigger();
   const uint32_t TM_S = tmem_base;          // 2 x 128 columns
   const uint32_t TM_PV = tmem_base + 256;   // 64 columns
 
@@ -332,6 +335,8 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();
+  pdl_trigger();
   const uint32_t TM_S = tmem_base, TM_DP = tmem_base + 128, TM_DV = tmem_base + 256, TM_DK = tmem_base + 320,
                  TM_DQ = tmem_base + 384;
 
@@ -517,6 +522,7 @@ __global__ void attn_delta_kernel(const __nv_bfloat16* __restrict__ dO, const __
   const long long gid = blockIdx.x * (long long)blockDim.x + threadIdx.x;
   const long long row = gid >> 3;
   const int sub = (int)(gid & 7);
+  pdl_wait();
   if (row >= (long long)B * S * H) return;
   const int hh = row % H, s = (row / H) % S, bb = row / ((long long)H * S);
   const uint4 a = __ldg(reinterpret_cast<const uint4*>(dO + row * HD) + sub);
@@ -540,6 +546,7 @@ __global__ void attn_delta_kernel(const __nv_bfloat16* __restrict__ dO, const __
 __global__ void attn_dq_cast_kernel(float* __restrict__ acc, __nv_bfloat16* __restrict__ dq, int B, int S, int H,
                                     long long sb, long long ss, long long sh) {
   const size_t n8 = (size_t)B * S * H * (HD / 8);
+  pdl_wait();
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n8; i += (size_t)gridDim.x * blockDim.x) {
     const int v = i % (HD / 8);
     size_t r = i / (HD / 8);
@@ -609,8 +616,7 @@ extern "C" int tepd_attn_fwd(const void* q, const void* k, const void* v, void* 
   p.O = o; p.lse = (float*)lse; p.B = B; p.H = H; p.S = S; p.causal = causal;
   p.scale = scale; p.scale_log2 = scale * 1.4426950408889634f;
   int grid = (S / BQ) * B * H;
-  attn_fwd_kernel<<<grid, FWD_THREADS, FWD_SMEM, reinterpret_cast<cudaStream_t>(stream)>>>(tq, tk, tv, p);
-  return (int)cudaGetLastError();
+  return (int)tepd::launch(attn_fwd_kernel, dim3(grid), dim3(FWD_THREADS), FWD_SMEM, reinterpret_cast<cudaStream_t>(stream), tq, tk, tv, p);
 }
 
 // do, o: contiguous [B,S,H,D]; q/k/v strided views; dq/dk/dv strided views (shared strides).
@@ -639,7 +645,9 @@ extern "C" int tepd_attn_bwd(const void* dO, const void* q, const void* k, const
   }
   {
     const long long rows = (long long)B * S * H;
-    attn_delta_kernel<<<(unsigned)((rows * 8 + 255) / 256), 256, 0, st>>>((const __nv_bfloat16*)dO, (const __nv_bfloat16*)o, delta_buf, B, S, H);
+    cudaError_t le = tepd::launch(attn_delta_kernel, dim3((unsigned)((rows * 8 + 255) / 256)), dim3(256), 0, st,
+                                  (const __nv_bfloat16*)dO, (const __nv_bfloat16*)o, delta_buf, B, S, H);
+    if (le != cudaSuccess) return (int)le;
   }
   // persistent, self-clearing fp32 dQ accumulator (used when the caller passes no buffer)
   static float* dq_ws = nullptr;
@@ -664,7 +672,8 @@ extern "C" int tepd_attn_bwd(const void* dO, const void* q, const void* k, const
   p.lse = (const float*)lse; p.delta = delta_buf; p.dq_acc = (float*)dq_acc; p.dk = dk; p.dv = dv;
   p.dstride_b = dstride_b; p.dstride_s = dstride_s; p.dstride_h = dstride_h;
   p.B = B; p.H = H; p.S = S; p.causal = causal; p.scale = scale; p.scale_log2 = scale * 1.4426950408889634f;
-  attn_bwd_kernel<<<(S / BKV) * B * H, BWD_THREADS, BWD_SMEM, st>>>(tq, tk, tv, tdo, p);
-  attn_dq_cast_kernel<<<148 * 4, 256, 0, st>>>((float*)dq_acc, (__nv_bfloat16*)dq, B, S, H, dstride_b, dstride_s, dstride_h);
-  return (int)cudaGetLastError();
+  cudaError_t le = tepd::launch(attn_bwd_kernel, dim3((S / BKV) * B * H), dim3(BWD_THREADS), BWD_SMEM, st, tq, tk, tv, tdo, p);
+  if (le != cudaSuccess) return (int)le;
+  return (int)tepd::launch(attn_dq_cast_kernel, dim3(148 * 4), dim3(256), 0, st, (float*)dq_acc, (__nv_bfloat16*)dq, B, S, H,
+                           dstride_b, dstride_s, dstride_h);
 }

@@ -4,6 +4,7 @@
 #include <cuda_runtime.h>
 #include <cuda_bf16.h>
 #include <stdint.h>
+#include "launch.cuh"
 
 namespace {
 
@@ -41,6 +42,11 @@ __device__ __forceinline__ float tanh_fast(float x) {
   return t;
 }
 
+// programmatic dependent launch (launch.cuh): every kernel below is launched through tepd::launch and therefore waits for
+// its predecessor here, before its first global access
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
 // ------------------------------------------------------------------ LayerNorm
 // One warp per row; each lane owns 8-element vectors at columns (i*32 + lane)*8.
 template <int MAXV>  // max vectors per lane (C <= MAXV*256)
@@ -50,6 +56,7 @@ __global__ void __launch_bounds__(256) layernorm_fwd_kernel(const bf16* __restri
                                                            int rows, int C, float eps) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int row = blockIdx.x * 8 + warp;
+  pdl_wait();
   if (row >= rows) return;
   const int nvec = C >> 3;
   const uint4* xr = reinterpret_cast<const uint4*>(x + (size_t)row * C);
@@ -99,6 +106,7 @@ __global__ void __launch_bounds__(256) layernorm_fwd_kernel(const bf16* __restri
     mean_out[row] = mean;
     rstd_out[row] = rstd;
   }
+  pdl_trigger();
 }
 
 // Backward: dx per row (one warp per row, grid-strided); dgamma / dbeta are accumulated in per-warp SHARED-memory
@@ -119,6 +127,7 @@ __global__ void __launch_bounds__(256, (MAXV <= 4) ? 3 : 1) layernorm_bwd_kernel
   float* my_db = red + (size_t)(8 + warp) * C;
   for (int c = lane; c < C; c += 32) { my_dg[c] = 0.f; my_db[c] = 0.f; }
   __syncwarp();
+  pdl_wait();
   for (int row = blockIdx.x * 8 + warp; row < rows; row += gridDim.x * 8) {
     const uint4* xr = reinterpret_cast<const uint4*>(x + (size_t)row * C);
     const uint4* dyr = reinterpret_cast<const uint4*>(dy + (size_t)row * C);
@@ -205,6 +214,7 @@ __device__ __forceinline__ float gelu_grad_f(float x) {
   return 0.5f * (1.f + t) + 0.5f * x * dt;
 }
 __global__ void gelu_fwd_kernel(const uint4* __restrict__ x, uint4* __restrict__ y, size_t nvec) {
+  pdl_wait();
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < nvec; i += (size_t)gridDim.x * blockDim.x) {
     float f[8];
     unpack8(__ldg(x + i), f);
@@ -216,6 +226,7 @@ __global__ void gelu_fwd_kernel(const uint4* __restrict__ x, uint4* __restrict__
 // dx = dy * gelu'(x);  optionally also accumulates the column sums of dx? (no: bias grad handled by colsum)
 __global__ void gelu_bwd_kernel(const uint4* __restrict__ dy, const uint4* __restrict__ x, uint4* __restrict__ dx,
                                 size_t nvec) {
+  pdl_wait();
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < nvec; i += (size_t)gridDim.x * blockDim.x) {
     float f[8], d[8];
     unpack8(__ldg(x + i), f);
@@ -236,6 +247,7 @@ __global__ void __launch_bounds__(256) colsum_kernel(const bf16* __restrict__ in
   const int r0 = blockIdx.y * rows_per_block;
   const int r1 = min(rows, r0 + rows_per_block);
   float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  pdl_wait();
   if (col0 < C) {
     int r = r0 + warp;
     for (; r + 24 < r1; r += 32) {   // 4 rows in flight per lane
@@ -460,10 +472,9 @@ extern "C" int tepd_layernorm_fwd(const void* x, const void* gamma, const void* 
                                   int rows, int C, float eps, void* stream) {
   if (C % 8 || C > 4096) return -2;
   dim3 grid((rows + 7) / 8);
-#define LN_FWD(MV) layernorm_fwd_kernel<MV><<<grid, 256, 0, CS(stream)>>>((const bf16*)x, (const float*)gamma, (const float*)beta, (bf16*)y, (float*)mean, (float*)rstd, rows, C, eps)
+#define LN_FWD(MV) return (int)tepd::launch(layernorm_fwd_kernel<MV>, grid, dim3(256), 0, CS(stream), (const bf16*)x, (const float*)gamma, (const float*)beta, (bf16*)y, (float*)mean, (float*)rstd, rows, C, eps)
   if (C <= 1024) LN_FWD(4); else if (C <= 2048) LN_FWD(8); else LN_FWD(16);
 #undef LN_FWD
-  return (int)cudaGetLastError();
 }
 
 extern "C" int tepd_layernorm_bwd(const void* dy, const void* x, const void* gamma, const void* mean, const void* rstd,
@@ -476,28 +487,25 @@ extern "C" int tepd_layernorm_bwd(const void* dy, const void* x, const void* gam
   {                                                                                                         \
     static bool cfg = false;                                                                                \
     if (!cfg) { cudaFuncSetAttribute(layernorm_bwd_kernel<MV>, cudaFuncAttributeMaxDynamicSharedMemorySize, 16 * 2048 * 4); cfg = true; } \
-    layernorm_bwd_kernel<MV><<<grid, 256, smem, CS(stream)>>>((const bf16*)dy, (const bf16*)x, (const float*)gamma, (const float*)mean, (const float*)rstd, (bf16*)dx, (float*)dgamma, (float*)dbeta, (const bf16*)dres, rows, C); \
+    return (int)tepd::launch(layernorm_bwd_kernel<MV>, dim3(grid), dim3(256), smem, CS(stream), (const bf16*)dy, (const bf16*)x, (const float*)gamma, (const float*)mean, (const float*)rstd, (bf16*)dx, (float*)dgamma, (float*)dbeta, (const bf16*)dres, rows, C); \
   }
   if (C <= 1024) LN_BWD(4) else LN_BWD(8)
 #undef LN_BWD
-  return (int)cudaGetLastError();
 }
 
 extern "C" int tepd_gelu_fwd(const void* x, void* y, long long n, void* stream) {
   if (n % 8) return -2;
-  gelu_fwd_kernel<<<grid_for(n / 8, 256), 256, 0, CS(stream)>>>((const uint4*)x, (uint4*)y, n / 8);
-  return (int)cudaGetLastError();
+  return (int)tepd::launch(gelu_fwd_kernel, dim3(grid_for(n / 8, 256)), dim3(256), 0, CS(stream), (const uint4*)x, (uint4*)y, (size_t)(n / 8));
 }
 extern "C" int tepd_gelu_bwd(const void* dy, const void* x, void* dx, long long n, void* stream) {
   if (n % 8) return -2;
-  gelu_bwd_kernel<<<grid_for(n / 8, 256), 256, 0, CS(stream)>>>((const uint4*)dy, (const uint4*)x, (uint4*)dx, n / 8);
-  return (int)cudaGetLastError();
+  return (int)tepd::launch(gelu_bwd_kernel, dim3(grid_for(n / 8, 256)), dim3(256), 0, CS(stream), (const uint4*)dy, (const uint4*)x, (uint4*)dx, (size_t)(n / 8));
 }
 extern "C" int tepd_colsum(const void* in, void* out, int rows, int C, void* stream) {
   if (C % 8) return -2;
   int rpb = 64;
   dim3 grid((C + 255) / 256, (rows + rpb - 1) / rpb);
-  colsum_kernel<<<grid, 256, 0, CS(stream)>>>((const bf16*)in, (float*)out, rows, C, rpb);
+  return (int)tepd::launch(colsum_kernel, grid, dim3(256), 0, CS(stream), (const bf16*)in, (float*)out, rows, C, rpb);
   return (int)cudaGetLastError();
 }
 extern "C" int tepd_embedding_fwd(const void* tok, const void* wte, const void* wpe, void* out, int T, int S, int C,

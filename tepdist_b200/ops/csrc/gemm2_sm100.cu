@@ -6,8 +6,16 @@
 //   full[stage]   lives in the LEADER's smem; both CTAs' TMA loads complete_tx on it (cta_group::2 TMA)
 //   empty[stage]  tcgen05.commit multicast to both CTAs (each producer waits on its own copy)
 //   tmem_full     tcgen05.commit multicast to both CTAs; tmem_empty: 8 remote/local arrivals on the leader's copy
-// A is K-major ([M,K]); B is K-major ([N,K], forward) or MN-major ([K,N], dgrad).
+// A is K-major ([M,K]) or MN-major ([K,M], weight gradients); B is K-major ([N,K], forward) or MN-major ([K,N], dgrad /
+// wgrad).  Output bf16 with the fused epilogues, or fp32 plain stores (weight gradients).
+// Scheduling: tile-parallel (pair c takes tiles c, c+P, ...) or STREAM-K (pair c owns the contiguous range
+// [c, c+1) * stream_k of the (tile, k-block) iteration space): with 74 pairs and power-of-two tile counts the tile-parallel
+// schedule idles 14 % of the machine in its last wave on every GPT-2 shape; stream-K gives every pair the same number of
+// k-blocks.  A unit that starts mid-tile (always a pair's first) stores its fp32 partial tile to a workspace slot and
+// raises a flag; the unit holding k-block 0 (always a pair's last) waits for the flags of the pairs that follow it
+// inside the tile, adds their partials and runs the real epilogue.
 #include "sm100_ptx.cuh"
+#include "launch.cuh"
 #include <stdio.h>
 
 using namespace sm100;
@@ -38,6 +46,56 @@ struct Gemm2Params {
   float alpha;
   int act;        // 0 none, 1 gelu (dual output when D2), 2 multiply by gelu'(aux)
   int bias_bf16;
+  int out_fp32;   // 1: plain fp32 stores (no activation / residual)
+  int stream_k;   // > 0: k-block iterations per pair (stream-K)
+  float* sk_ws;       // [CTA][BM][BN] fp32 partial tiles
+  unsigned* sk_flag;  // [CTA] 1 = partial complete (reset by its consumer)
+};
+
+// Units of work of a pair.  Tile-parallel: unit s = tile cluster_id + s * num_clusters, all k-blocks.  Stream-K: the pair
+// owns iterations [it0, it1) of the (tile, k-block) space = [tail part of a tile shared with the previous pair] + full
+// tiles + [head part of a tile shared with the next pair].  The head part is this pair's FINISHER unit (it collects the
+// partials of the pairs that follow it inside the tile; its epilogue is latency-bound on those loads), so it is
+// scheduled second to last: its epilogue then runs under the MMAs of the last full tile instead of at the very end.
+struct Units {
+  int stream_k, k_blocks, num_clusters, cluster_id, total_tiles;
+  int it0, it1;          // stream-K range
+  int tail_len;          // k-blocks of the leading partial unit (0 = none)
+  int n_full, head_len;  // full tiles, k-blocks of the trailing partial unit (0 = none)
+  int count;
+  __device__ __forceinline__ void init(const Gemm2Params& p, int cid, int nclusters, int total) {
+    stream_k = p.stream_k; k_blocks = p.k_blocks; num_clusters = nclusters; cluster_id = cid; total_tiles = total;
+    if (stream_k > 0) {
+      const long long iters = (long long)total * k_blocks;
+      const long long c0 = (long long)cid * stream_k;
+      it0 = (int)(c0 < iters ? c0 : iters);
+      it1 = (int)(c0 + stream_k < iters ? c0 + stream_k : iters);
+      const int r = it0 % k_blocks;
+      tail_len = r == 0 ? 0 : min(k_blocks - r, it1 - it0);
+      const int rest = it1 - it0 - tail_len;
+      n_full = rest / k_blocks;
+      head_len = rest - n_full * k_blocks;
+      count = (tail_len > 0) + n_full + (head_len > 0);
+    } else {
+      it0 = it1 = tail_len = n_full = head_len = 0;
+      count = cid < total ? (total - cid + nclusters - 1) / nclusters : 0;
+    }
+  }
+  // unit number s (0 .. count-1) in EXECUTION order
+  __device__ __forceinline__ void get(int s, int& tile, int& kb0, int& kb1) const {
+    if (stream_k <= 0) { tile = cluster_id + s * num_clusters; kb0 = 0; kb1 = k_blocks; return; }
+    const int has_tail = tail_len > 0;
+    int u = s;   // position in natural (ascending) order
+    if (head_len > 0 && n_full >= 1) {            // natural: [tail] f0 .. f(n-1) head   ->   [tail] f0 .. f(n-2) head f(n-1)
+      if (s == count - 2) u = count - 1;
+      else if (s == count - 1) u = count - 2;
+    }
+    if (has_tail && u == 0) { tile = it0 / k_blocks; kb0 = it0 % k_blocks; kb1 = kb0 + tail_len; return; }
+    const int f = u - has_tail;
+    const int first_full = (it0 + tail_len) / k_blocks;
+    if (f < n_full) { tile = first_full + f; kb0 = 0; kb1 = k_blocks; return; }
+    tile = first_full + n_full; kb0 = 0; kb1 = head_len;
+  }
 };
 
 __device__ __forceinline__ uint32_t cluster_ctarank() {
@@ -99,7 +157,7 @@ __device__ __forceinline__ float gelu_grad_f(float x) {
   return 0.5f * (1.0f + t) + 0.5f * x * (1.0f - t * t) * k0 * (1.0f + 3.0f * k1 * x * x);
 }
 
-template <bool B_MN>
+template <bool A_MN, bool B_MN>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1)
 gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b, const Gemm2Params p) {
   extern __shared__ uint8_t smem_raw[];
@@ -135,6 +193,8 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
   cluster_sync();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();
+  pdl_trigger();
 
   const int num_clusters = gridDim.x >> 1;
   const int cluster_id = blockIdx.x >> 1;
@@ -145,17 +205,27 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
     if (elect_one()) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int tile = cluster_id; tile < total_tiles; tile += num_clusters) {
+      Units un;
+      un.init(p, cluster_id, num_clusters, total_tiles);
+      for (int s = 0; s < un.count; ++s) {
+        int tile, kb0, kb1;
+        un.get(s, tile, kb0, kb1);
         const int m_pair = tile % p.m_pairs, n_blk = tile / p.m_pairs;
         const int row0 = m_pair * 2 * BM + cta * BM;
         const int col0 = n_blk * BN + cta * (BN / 2);
-        for (int kb = 0; kb < p.k_blocks; ++kb) {
+        for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
           uint8_t* sa = smem + stage * STAGE_BYTES;
           uint8_t* sb = sa + A_BYTES;
           const uint32_t lbar = mapa_rank(smem_u32(&full_bar[stage]), 0);   // the leader's barrier
           if (leader) mbar_expect_tx(&full_bar[stage], 2 * STAGE_BYTES);
-          tma_load_3d_2sm(sa, &tmap_a, lbar, kb * BK, row0, 0);
+          if constexpr (!A_MN) {
+            tma_load_3d_2sm(sa, &tmap_a, lbar, kb * BK, row0, 0);
+          } else {
+#pragma unroll
+            for (int j = 0; j < BM / 64; ++j)
+              tma_load_3d_2sm(sa + j * (64 * BK * 2), &tmap_a, lbar, row0 + j * 64, kb * BK, 0);
+          }
           if constexpr (!B_MN) {
             tma_load_3d_2sm(sb, &tmap_b, lbar, kb * BK, col0, 0);
           } else {
@@ -170,25 +240,30 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
   } else if (warp == 1) {
     // ===================== MMA issuer (leader CTA only) =====================
     if (leader && elect_one()) {
-      constexpr uint32_t idesc = make_idesc(UMMA_BF16, UMMA_BF16, 2 * BM, BN, 0, B_MN ? 1 : 0);
+      constexpr uint32_t idesc = make_idesc(UMMA_BF16, UMMA_BF16, 2 * BM, BN, A_MN ? 1 : 0, B_MN ? 1 : 0);
       int stage = 0, acc = 0;
       uint32_t phase = 0, acc_phase = 0;
-      for (int tile = cluster_id; tile < total_tiles; tile += num_clusters) {
+      Units un;
+      un.init(p, cluster_id, num_clusters, total_tiles);
+      for (int s = 0; s < un.count; ++s) {
+        int tile, kb0, kb1;
+        un.get(s, tile, kb0, kb1);
         mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + acc * BN;
-        for (int kb = 0; kb < p.k_blocks; ++kb) {
+        for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(&full_bar[stage], phase);
           tc_fence_after();
           const uint32_t sa = smem_u32(smem + stage * STAGE_BYTES);
           const uint32_t sb = sa + A_BYTES;
 #pragma unroll
           for (int k = 0; k < BK / UK; ++k) {
-            const uint64_t da = make_smem_desc_sw128(sa + k * UK * 2, 0, 1024);
-            uint64_t db;
+            uint64_t da, db;
+            if constexpr (!A_MN) da = make_smem_desc_sw128(sa + k * UK * 2, 0, 1024);
+            else                 da = make_smem_desc_sw128(sa + k * UK * 128, 64 * BK * 2, 1024);
             if constexpr (!B_MN) db = make_smem_desc_sw128(sb + k * UK * 2, 0, 1024);
             else                 db = make_smem_desc_sw128(sb + k * UK * 128, 64 * BK * 2, 1024);
-            umma_f16_ss_2sm(d_tmem, da, db, idesc, (kb > 0 || k > 0) ? 1u : 0u);
+            umma_f16_ss_2sm(d_tmem, da, db, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
           }
           umma_commit_2sm(&empty_bar[stage]);   // frees the stage in BOTH CTAs
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
@@ -202,8 +277,32 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
     const int quarter = warp & 3;
     int acc = 0;
     uint32_t acc_phase = 0;
-    for (int tile = cluster_id; tile < total_tiles; tile += num_clusters) {
+    Units un;
+    un.init(p, cluster_id, num_clusters, total_tiles);
+    for (int s = 0; s < un.count; ++s) {
+      int tile, kb0, kb1;
+      un.get(s, tile, kb0, kb1);
       const int m_pair = tile % p.m_pairs, n_blk = tile / p.m_pairs;
+      const bool sk_part = p.stream_k > 0 && !(kb0 == 0 && kb1 == p.k_blocks);
+      const bool sk_store = sk_part && kb0 > 0;    // first unit of this pair: hand the partial tile to the finisher
+      const bool sk_finish = sk_part && kb0 == 0;  // last unit of this pair: collect the partials of the pairs that follow
+      const int row_in_tile = quarter * 32 + lane;
+      int partner_end = cluster_id + 1;
+      if (sk_finish) {
+        const int tile_end = (tile + 1) * p.k_blocks;
+        while (partner_end < num_clusters && partner_end * p.stream_k < tile_end) ++partner_end;
+        if (threadIdx.x == 64) {
+          for (int j = cluster_id + 1; j < partner_end; ++j) {
+            unsigned f;
+            const long long t0 = clock64();
+            do {
+              asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(f) : "l"(p.sk_flag + 2 * j + cta) : "memory");
+              if (f == 0u && clock64() - t0 > 4000000000LL) __trap();   // a partner never arrived: fail loudly
+            } while (f == 0u);
+          }
+        }
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+      }
       mbar_wait(&tmem_full[acc], acc_phase);
       tc_fence_after();
       const int row = m_pair * 2 * BM + cta * BM + quarter * 32 + lane;
@@ -219,6 +318,30 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
           float v[32];
 #pragma unroll
           for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]) * p.alpha;
+          if (sk_store) {
+            float4* wp = reinterpret_cast<float4*>(p.sk_ws + ((long long)blockIdx.x * BM + row_in_tile) * BN + c * 32);
+#pragma unroll
+            for (int q = 0; q < 8; ++q) wp[q] = make_float4(v[q * 4], v[q * 4 + 1], v[q * 4 + 2], v[q * 4 + 3]);
+            continue;
+          }
+          if (sk_finish) {
+            for (int j = cluster_id + 1; j < partner_end; ++j) {
+              const float4* wp = reinterpret_cast<const float4*>(p.sk_ws + ((long long)(2 * j + cta) * BM + row_in_tile) * BN + c * 32);
+#pragma unroll
+              for (int q = 0; q < 8; ++q) {
+                float4 t;
+                asm volatile("ld.global.cg.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(t.x), "=f"(t.y), "=f"(t.z), "=f"(t.w) : "l"(wp + q));
+                v[q * 4] += t.x; v[q * 4 + 1] += t.y; v[q * 4 + 2] += t.z; v[q * 4 + 3] += t.w;
+              }
+            }
+          }
+          if (p.out_fp32) {
+            float4* dp = reinterpret_cast<float4*>(reinterpret_cast<float*>(p.D) + (long long)row * p.ldd + col0);
+#pragma unroll
+            for (int q = 0; q < 8; ++q)
+              if (col0 + q * 4 < p.N) dp[q] = make_float4(v[q * 4], v[q * 4 + 1], v[q * 4 + 2], v[q * 4 + 3]);
+            continue;
+          }
           if (p.bias != nullptr) {
             if (p.bias_bf16) {
               const __nv_bfloat16* bp = reinterpret_cast<const __nv_bfloat16*>(p.bias) + col0;
@@ -285,6 +408,17 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive_cluster(mapa_rank(smem_u32(&tmem_empty[acc]), 0));   // always the leader's barrier
+      if (sk_part) {
+        if (sk_store) __threadfence();
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        if (threadIdx.x == 64) {
+          if (sk_store) {
+            asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p.sk_flag + blockIdx.x), "r"(1u) : "memory");
+          } else {
+            for (int j = cluster_id + 1; j < partner_end; ++j) p.sk_flag[2 * j + cta] = 0u;   // consumed
+          }
+        }
+      }
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
   }
@@ -302,11 +436,15 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
 extern "C" int tepd_make_tmap_bf16_3d(CUtensorMap* out, const void* ptr, long long inner, long long rows, long long batch,
                                       long long ld_elems, long long batch_stride_elems, int box_inner, int box_rows);
 
-// D[M,N] = epilogue(alpha * A[M,K] @ B) with B = [N,K] (b_mn=0) or [K,N] (b_mn=1); bf16 in / bf16 out.
+// D[M,N] = epilogue(alpha * A @ B): A = [M,K] (a_mn=0) or [K,M] (a_mn=1); B = [N,K] (b_mn=0) or [K,N] (b_mn=1); bf16 in;
+// bf16 out with epilogues, or fp32 plain stores (out_fp32).  stream_k != 0 selects the stream-K schedule.
 extern "C" int tepd_gemm2_bf16(const void* A, const void* B, void* D, void* D2, const void* bias, const void* residual,
                                const void* aux, int M, int N, int K, long long lda, long long ldb, long long ldd, long long ld_res,
-                               int b_mn, int act, int bias_bf16, float alpha, int num_sms, void* stream) {
-  if (N % 8 != 0 || K % 8 != 0 || M <= 0) return -2;
+                               int b_mn, int act, int bias_bf16, float alpha, int num_sms, void* stream, int a_mn, int out_fp32,
+                               int stream_k) {
+  if (N % 8 != 0 || K % 8 != 0 || M <= 0 || (a_mn && (M % 8))) return -2;
+  if (out_fp32 && (act || residual || D2 || aux)) return -5;
+  if (a_mn && !b_mn) return -8;   // (weight gradients are MN-major on both sides; the mixed case has no user)
   Gemm2Params p;
   p.M = M; p.N = N; p.K = K;
   p.m_pairs = (M + 2 * BM - 1) / (2 * BM);
@@ -314,23 +452,54 @@ extern "C" int tepd_gemm2_bf16(const void* A, const void* B, void* D, void* D2, 
   p.k_blocks = (K + BK - 1) / BK;
   p.ldd = ldd; p.ld_res = ld_res;
   p.D = D; p.D2 = D2; p.bias = bias; p.residual = residual; p.aux = aux; p.alpha = alpha; p.act = act; p.bias_bf16 = bias_bf16;
+  p.out_fp32 = out_fp32; p.stream_k = 0; p.sk_ws = nullptr; p.sk_flag = nullptr;
   CUtensorMap ta, tb;
-  int rc = tepd_make_tmap_bf16_3d(&ta, A, K, M, 1, lda, 0, BK, BM);
+  int rc;
+  if (!a_mn) rc = tepd_make_tmap_bf16_3d(&ta, A, K, M, 1, lda, 0, BK, BM);
+  else       rc = tepd_make_tmap_bf16_3d(&ta, A, M, K, 1, lda, 0, 64, BK);
   if (rc) return 100 + rc;
   if (!b_mn) rc = tepd_make_tmap_bf16_3d(&tb, B, K, N, 1, ldb, 0, BK, BN / 2);
   else       rc = tepd_make_tmap_bf16_3d(&tb, B, N, K, 1, ldb, 0, 64, BK);
   if (rc) return 200 + rc;
   if (num_sms <= 0) num_sms = 148;
   const int total = p.m_pairs * p.n_blocks;
-  int clusters = total < num_sms / 2 ? total : num_sms / 2;
-  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
-  static bool cfg0 = false, cfg1 = false;
-  if (!b_mn) {
-    if (!cfg0) { if (cudaFuncSetAttribute(gemm2_bf16_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES) != cudaSuccess) return -6; cfg0 = true; }
-    gemm2_bf16_kernel<false><<<2 * clusters, THREADS, SMEM_BYTES, s>>>(ta, tb, p);
-  } else {
-    if (!cfg1) { if (cudaFuncSetAttribute(gemm2_bf16_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES) != cudaSuccess) return -6; cfg1 = true; }
-    gemm2_bf16_kernel<true><<<2 * clusters, THREADS, SMEM_BYTES, s>>>(ta, tb, p);
+  const int pairs = num_sms / 2;
+  int clusters = total < pairs ? total : pairs;
+  if (stream_k) {
+    const long long iters = (long long)total * p.k_blocks;
+    long long per = (iters + pairs - 1) / pairs;
+    if (per < 4) per = 4;
+    constexpr int kSlots = 160;
+    static float* ws[16] = {nullptr};
+    static unsigned* flags[16] = {nullptr};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (num_sms > kSlots || dev >= 16) return -6;
+    if (ws[dev] == nullptr) {   // first use must happen outside CUDA-graph capture (the executor warms up eagerly)
+      const size_t bytes = (size_t)kSlots * BM * BN * sizeof(float);
+      if (cudaMalloc(&ws[dev], bytes) != cudaSuccess) return -7;
+      if (cudaMalloc(&flags[dev], kSlots * sizeof(unsigned)) != cudaSuccess) return -7;
+      cudaMemset(flags[dev], 0, kSlots * sizeof(unsigned));
+      cudaDeviceSynchronize();
+    }
+    p.stream_k = (int)per; p.sk_ws = ws[dev]; p.sk_flag = flags[dev];
+    clusters = (int)((iters + per - 1) / per);
   }
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+#define LAUNCH2(AM, BMN)                                                                                                        \
+  {                                                                                                                             \
+    static bool cfg = false;                                                                                                    \
+    auto kern = gemm2_bf16_kernel<AM, BMN>;                                                                                     \
+    if (!cfg) {                                                                                                                 \
+      if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES) != cudaSuccess) return -6;        \
+      cfg = true;                                                                                                               \
+    }                                                                                                                           \
+    cudaError_t le = tepd::launch(kern, dim3(2 * clusters), dim3(THREADS), SMEM_BYTES, s, ta, tb, p);                           \
+    if (le != cudaSuccess) return (int)le;                                                                                      \
+  }
+  if (a_mn) LAUNCH2(true, true)
+  else if (b_mn) LAUNCH2(false, true)
+  else LAUNCH2(false, false)
+#undef LAUNCH2
   return (int)cudaGetLastError();
 }

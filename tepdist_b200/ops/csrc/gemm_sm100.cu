@@ -10,6 +10,7 @@
 //   B K-major : memory [b, N, K] (K contiguous)       B MN-major: memory [b, K, N] (N contiguous)
 // which covers forward (x @ W^T), dgrad (dy @ W) and wgrad (dy^T @ x) without any transposes.
 #include "sm100_ptx.cuh"
+#include "launch.cuh"
 #include <stdio.h>
 
 using namespace sm100;
@@ -36,8 +37,8 @@ struct GemmParams {
   int bias_bf16;
   void* D2;        // act 1: when set, D receives the pre-activation and D2 the activated value (saved for backward)
   const void* aux; // act 2: bf16 [b, M, N] pre-activation
-  float* sk_ws;        // stream-K fix-up workspace: [slot][BLOCK_M][BLOCK_N] fp32, all zero between launches
-  unsigned* sk_cnt;    // per slot: k-blocks accumulated so far
+  float* sk_ws;        // stream-K fix-up workspace: [CTA][BLOCK_M][BLOCK_N] fp32 partial tiles
+  unsigned* sk_cnt;    // per CTA: 1 = its partial tile is complete (reset to 0 by the consumer)
   int stream_k;    // > 0: stream-K -- CTA c owns the contiguous range [c, c+1) * stream_k of the (tile, k-block) iteration
                    // space and flushes its accumulator with red.add at every tile boundary (fp32 accumulate outputs only):
                    // every SM gets the same number of k-blocks whatever the tile count (no wave quantisation)
@@ -265,7 +266,7 @@ __device__ __forceinline__ void gemm_body(const CUtensorMap& tmap_a, const CUten
   uint64_t* tmem_full = empty_bar + C::STAGES;
   uint64_t* tmem_empty = tmem_full + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
-  uint32_t* sk_flag = tmem_slot + 1;
+
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -291,6 +292,8 @@ __device__ __forceinline__ void gemm_body(const CUtensorMap& tmap_a, const CUten
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();      // everything above overlapped the previous kernel's tail; its outputs are visible from here on
+  pdl_trigger();   // persistent grid: the next kernel may be scheduled as these CTAs retire
 
 
   if (warp == 0) {
@@ -422,13 +425,31 @@ __device__ __forceinline__ void gemm_body(const CUtensorMap& tmap_a, const CUten
       const uint32_t t_row = tmem_base + (uint32_t(quarter * 32) << 16) + acc * BLOCK_N;
       const bool add_bias = p.bias != nullptr && w.lead;
       const bool add_res = p.residual != nullptr && w.lead;
-      const bool fixup = p.stream_k > 0 && !p.accumulate && !(w.kb0 == 0 && w.kb1 == p.k_blocks);
-      int slot = 0;
-      float* ws_row = nullptr;
-      if (fixup) {  // this unit is one of several that make up the tile: partial sums meet in a workspace slot
-        const int tile_it0 = (tile - w.kb0);  // first iteration index of this tile (cursor before next_work = tile's it + kb0)
-        slot = tile_it0 / p.stream_k + 1;     // index of the first CTA-range boundary strictly inside the tile
-        ws_row = p.sk_ws + ((long long)slot * BLOCK_M + quarter * 32 + lane) * BLOCK_N;
+      // stream-K units that cover only part of a tile's K range (outputs with a real epilogue): a unit that starts
+      // mid-tile (always a CTA's FIRST unit) stores its fp32 partial tile into workspace slot [blockIdx.x] and raises
+      // flag[blockIdx.x]; the unit that holds k-block 0 (always a CTA's LAST unit) is the finisher: it waits for the
+      // flags of the CTAs that follow it inside the tile, adds their partials to its own accumulator and runs the real
+      // epilogue.  Producers never wait and finish their part first, so the wait is short and cannot deadlock.
+      const bool sk_part = p.stream_k > 0 && !p.accumulate && !(w.kb0 == 0 && w.kb1 == p.k_blocks);
+      const bool sk_store = sk_part && w.kb0 > 0;
+      const bool sk_finish = sk_part && w.kb0 == 0;
+      const int row_in_tile = quarter * 32 + lane;
+      int partner_end = 0;   // finisher: partners are CTAs blockIdx.x+1 .. partner_end-1
+      if (sk_finish) {
+        const int tile_end = tile + p.k_blocks;   // (cursor before next_work == first iteration of the tile)
+        partner_end = blockIdx.x + 1;
+        while (partner_end < (int)gridDim.x && partner_end * p.stream_k < tile_end) ++partner_end;
+        if (threadIdx.x == 64) {
+          for (int j = blockIdx.x + 1; j < partner_end; ++j) {
+            unsigned f;
+            const long long t0 = clock64();
+            do {
+              asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(f) : "l"(p.sk_cnt + j) : "memory");
+              if (f == 0u && clock64() - t0 > 4000000000LL) __trap();   // a partner never arrived: fail loudly
+            } while (f == 0u);
+          }
+        }
+        asm volatile("bar.sync 1, 128;" ::: "memory");
       }
 #pragma unroll 1
       for (int c = 0; c < BLOCK_N / 32; ++c) {
@@ -440,53 +461,39 @@ __device__ __forceinline__ void gemm_body(const CUtensorMap& tmap_a, const CUten
           float v[32];
 #pragma unroll
           for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]) * p.alpha;
-          if (!fixup) {
-            epilogue_chunk<PEER>(v, p, pa, row, col0, b, add_bias, add_res);
-          } else {
-            float* wp = ws_row + c * 32;
+          if (sk_store) {
+            float4* wp = reinterpret_cast<float4*>(p.sk_ws + ((long long)blockIdx.x * BLOCK_M + row_in_tile) * BLOCK_N + c * 32);
 #pragma unroll
-            for (int q = 0; q < 8; ++q)
-              asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(wp + q * 4), "f"(v[q * 4]), "f"(v[q * 4 + 1]),
-                           "f"(v[q * 4 + 2]), "f"(v[q * 4 + 3]) : "memory");
+            for (int q = 0; q < 8; ++q) wp[q] = make_float4(v[q * 4], v[q * 4 + 1], v[q * 4 + 2], v[q * 4 + 3]);
+          } else {
+            if (sk_finish) {
+              for (int j = blockIdx.x + 1; j < partner_end; ++j) {
+                const float4* wp = reinterpret_cast<const float4*>(p.sk_ws + ((long long)j * BLOCK_M + row_in_tile) * BLOCK_N + c * 32);
+#pragma unroll
+                for (int q = 0; q < 8; ++q) {
+                  float4 t;
+                  asm volatile("ld.global.cg.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(t.x), "=f"(t.y), "=f"(t.z), "=f"(t.w) : "l"(wp + q));
+                  v[q * 4] += t.x; v[q * 4 + 1] += t.y; v[q * 4 + 2] += t.z; v[q * 4 + 3] += t.w;
+                }
+              }
+            }
+            epilogue_chunk<PEER>(v, p, pa, row, col0, b, add_bias, add_res);
           }
         }
       }
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tmem_empty[acc]);
-      if (fixup) {
-        // the last unit to arrive (k-blocks add up to the full K) reads the summed tile back and runs the real epilogue
-        __threadfence();
+      if (sk_part) {
+        if (sk_store) __threadfence();
         asm volatile("bar.sync 1, 128;" ::: "memory");
         if (threadIdx.x == 64) {
-          const int mine = w.kb1 - w.kb0;
-          const unsigned prev = atomicAdd(p.sk_cnt + slot, (unsigned)mine);
-          *sk_flag = (prev + mine == (unsigned)p.k_blocks) ? 1u : 0u;
-        }
-        asm volatile("bar.sync 1, 128;" ::: "memory");
-        const bool finisher = *reinterpret_cast<volatile uint32_t*>(sk_flag) != 0;
-        if (finisher) {
-          __threadfence();
-          const bool ab = p.bias != nullptr, ar = p.residual != nullptr;
-#pragma unroll 1
-          for (int c = 0; c < BLOCK_N / 32; ++c) {
-            const int col0 = n_blk * BLOCK_N + c * 32;
-            if (row_ok && col0 < p.N) {
-              float v[32];
-              float4* wp = reinterpret_cast<float4*>(ws_row + c * 32);
-#pragma unroll
-              for (int q = 0; q < 8; ++q) {
-                float4 t;
-                asm volatile("ld.global.cg.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(t.x), "=f"(t.y), "=f"(t.z), "=f"(t.w) : "l"(wp + q));
-                v[q * 4] = t.x; v[q * 4 + 1] = t.y; v[q * 4 + 2] = t.z; v[q * 4 + 3] = t.w;
-                wp[q] = make_float4(0.f, 0.f, 0.f, 0.f);   // leave the slot clean for the next launch
-              }
-              epilogue_chunk<PEER>(v, p, pa, row, col0, b, ab, ar);
-            }
+          if (sk_store) {
+            asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p.sk_cnt + blockIdx.x), "r"(1u) : "memory");
+          } else {
+            for (int j = blockIdx.x + 1; j < partner_end; ++j) p.sk_cnt[j] = 0u;   // consumed: clean for the next launch
           }
         }
-        asm volatile("bar.sync 1, 128;" ::: "memory");   // sk_flag is reused by the next unit
-        if (finisher && threadIdx.x == 64) p.sk_cnt[slot] = 0;
       }
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
@@ -569,8 +576,7 @@ static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const GemmP
     const long long iters = (long long)p.m_blocks * p.n_blocks * p.batch * p.k_blocks;
     grid = (int)((iters + p.stream_k - 1) / p.stream_k);
   }
-  kern<<<grid, NUM_THREADS, C::SMEM_BYTES, stream>>>(ta, tb, p);
-  return (int)cudaGetLastError();
+  return (int)tepd::launch(kern, dim3(grid), dim3(NUM_THREADS), C::SMEM_BYTES, stream, ta, tb, p);
 }
 
 // C ABI entry (called from Python via ctypes).  All leading dims / strides are in elements.
@@ -598,9 +604,9 @@ extern "C" int tepd_gemm_bf16(const void* A, const void* B, void* D, const void*
     p.stream_k = (int)per;
     split_k = 1;
     if (!(out_fp32 && accumulate)) {
-      // outputs with a real epilogue: partial tiles meet in a per-device fp32 workspace (one slot per CTA-range
-      // boundary); allocated once, kept all-zero between launches by the finishing CTA.  GEMMs of one device must not
-      // run concurrently on two streams in this mode.
+      // outputs with a real epilogue: partial tiles travel through a per-device fp32 workspace (one slot per CTA);
+      // allocated once; flags are reset by their consumer.  GEMMs of one device must not run concurrently on two
+      // streams in this mode.
       constexpr int kSlots = 160;
       static float* ws[16] = {nullptr};
       static unsigned* cnt[16] = {nullptr};
@@ -664,8 +670,7 @@ static int launch_gemm_peer(const TmapArray& ta, const CUtensorMap& tb, const Ge
   }
   int total = p.m_blocks * p.n_blocks * p.batch * p.split_k;
   int grid = total < num_sms ? total : num_sms;
-  kern<<<grid, NUM_THREADS, C::SMEM_BYTES, stream>>>(ta, tb, p, pa);
-  return (int)cudaGetLastError();
+  return (int)tepd::launch(kern, dim3(grid), dim3(NUM_THREADS), C::SMEM_BYTES, stream, ta, tb, p, pa);
 }
 
 // Tensor-parallel fused GEMMs over peer memory.

@@ -18,6 +18,11 @@ __device__ __forceinline__ uint32_t lane_id() {
   return l;
 }
 
+// programmatic dependent launch (see launch.cuh): block until the prerequisite grids have completed and their memory
+// operations are visible / allow the dependent grid to be scheduled
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
 __device__ __forceinline__ bool elect_one() {
   uint32_t pred = 0;
   asm volatile(

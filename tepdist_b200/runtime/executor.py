@@ -763,11 +763,15 @@ class Executor:
         self_init_params = set()
         for (nid, idx), pid in self.grad_binding.items():
             n = self.g.nodes[nid]
-            if n.op == "linear_wgrad" and idx == 0 and n.id not in self.alias_of:
+            shp = n.outputs[0].shape
+            if (n.op == "linear_wgrad" and idx == 0 and n.id not in self.alias_of and len(shp) == 2
+                    and ops.wgrad_prefers_store(shp[0], shp[1])):
                 self._store_init.add((nid, idx))
                 self_init_params.add(pid)
         for n in self.g.nodes:   # unbound weight gradients (general path) are fresh tensors anyway
-            if n.op == "linear_wgrad" and (n.id, 0) not in self.grad_binding:
+            shp = n.outputs[0].shape if n.outputs else ()
+            if (n.op == "linear_wgrad" and (n.id, 0) not in self.grad_binding and len(shp) == 2
+                    and ops.wgrad_prefers_store(shp[0], shp[1])):
                 self._store_init.add((n.id, 0))
         ranges: List[Tuple[int, int]] = []
         cur = 0

@@ -178,8 +178,55 @@ def check_gemm2():
     ops.gemm2(A, W, bias=bias, act="gelu", out=pre, out2=act)
     out["gelu_dual_pre"] = _rel_err(pre, ref)
     out["gelu_dual_act"] = _rel_err(act, torch.nn.functional.gelu(ref, approximate="tanh"))
+    # stream-K schedule (forced) on shapes whose tiles are split 2 and 3+ ways, every B layout, epilogues, twice in a row
+    for (M, N, K) in [(4096, 1024, 1024), (4096, 3072, 1024), (1000, 520, 2048), (512, 512, 8192), (384, 520, 200)]:
+        A = torch.randn(M, K, device="cuda", dtype=torch.bfloat16)
+        W = torch.randn(N, K, device="cuda", dtype=torch.bfloat16) * 0.05
+        bias = torch.randn(N, device="cuda")
+        res = torch.randn(M, N, device="cuda", dtype=torch.bfloat16)
+        ref = A.float() @ W.float().t() + bias
+        for rep in range(2):
+            out[f"sk_res_{M}x{N}x{K}_{rep}"] = _rel_err(ops.gemm2(A, W, bias=bias, residual=res, stream_k=True), ref + res.float())
+        out[f"sk_gelu_{M}x{N}x{K}"] = _rel_err(ops.gemm2(A, W, bias=bias, act="gelu", stream_k=True),
+                                               torch.nn.functional.gelu(ref, approximate="tanh"))
+        out[f"sk_bmn_{M}x{N}x{K}"] = _rel_err(ops.gemm2(A, W.t().contiguous(), b_mn=True, stream_k=True), ref - bias)
+    # weight-gradient layout: A [T, N] and B [T, K] both MN-major, fp32 plain stores; tile-parallel and stream-K
+    for (T, N, K) in [(4096, 1024, 1024), (4096, 3072, 1024), (1096, 1000, 520), (8192, 384, 256)]:
+        dY = torch.randn(T, N, device="cuda", dtype=torch.bfloat16)
+        X = torch.randn(T, K, device="cuda", dtype=torch.bfloat16)
+        ref = dY.float().t() @ X.float()
+        for sk in (False, True):
+            d = ops.gemm2(dY, X, a_mn=True, b_mn=True, out_dtype=torch.float32, stream_k=sk)
+            out[f"wgrad_{N}x{K}x{T}_sk{int(sk)}"] = _rel_err(d, ref)
     for k, v in out.items():
         assert v < 1e-2, (k, v)
+    perf = {}
+    for (M, N, K, bmn) in [(4096, 3072, 1024, False), (4096, 1024, 1024, False), (4096, 4096, 1024, False), (4096, 1024, 4096, False),
+                           (4096, 1024, 3072, True), (4096, 1024, 4096, True), (4096, 4096, 1024, True), (4096, 50304, 1024, False)]:
+        A = torch.randn(M, K, device="cuda", dtype=torch.bfloat16)
+        W = torch.randn(K, N, device="cuda", dtype=torch.bfloat16) if bmn else torch.randn(N, K, device="cuda", dtype=torch.bfloat16)
+        tag = f"{M}x{N}x{K}{'_bmn' if bmn else ''}"
+        perf[tag] = {}
+        for nm, sk in (("tile", False), ("streamk", True)):
+            ms = _time_ms(lambda: ops.gemm2(A, W, b_mn=bmn, stream_k=sk))
+            perf[tag][nm] = round(2.0 * M * N * K / ms / 1e9, 1)
+        ms = _time_ms(lambda: torch.matmul(A, W if bmn else W.t()))
+        perf[tag]["cublas"] = round(2.0 * M * N * K / ms / 1e9, 1)
+    T = 4096
+    for (N, K) in [(3072, 1024), (1024, 1024), (4096, 1024), (1024, 4096), (50304, 1024)]:
+        dY = torch.randn(T, N, device="cuda", dtype=torch.bfloat16)
+        X = torch.randn(T, K, device="cuda", dtype=torch.bfloat16)
+        acc = torch.zeros(N, K, device="cuda", dtype=torch.float32)
+        tag = f"wgrad_{N}x{K}"
+        perf[tag] = {}
+        for nm, sk in (("tile", False), ("streamk", True)):
+            ms = _time_ms(lambda: ops.gemm2(dY, X, a_mn=True, b_mn=True, out=acc, stream_k=sk))
+            perf[tag][nm] = round(2.0 * T * N * K / ms / 1e9, 1)
+        ms = _time_ms(lambda: ops.gemm(dY, X, a_mn=True, b_mn=True, out=acc, accumulate=True, split_k=1))
+        perf[tag]["cta1_redadd"] = round(2.0 * T * N * K / ms / 1e9, 1)
+        ms = _time_ms(lambda: torch.matmul(dY.t(), X))
+        perf[tag]["cublas"] = round(2.0 * T * N * K / ms / 1e9, 1)
+    out["perf_tflops"] = perf
     for (M, N, K) in [(8192, 8192, 8192), (4096, 4096, 1024), (4096, 1024, 4096), (4096, 3072, 1024)]:
         A = torch.randn(M, K, device="cuda", dtype=torch.bfloat16)
         W = torch.randn(N, K, device="cuda", dtype=torch.bfloat16)
