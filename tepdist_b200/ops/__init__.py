@@ -72,6 +72,8 @@ class _Sig:
     tepd_gelu_fwd = [_vp, _vp, _ll, _vp]
     tepd_gelu_bwd = [_vp, _vp, _vp, _ll, _vp]
     tepd_colsum = [_vp, _vp, _i, _i, _vp]
+    tepd_im2col_nhwc = [_vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _vp]
+    tepd_col2im_nhwc = [_vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _vp]
     tepd_embedding_fwd = [_vp, _vp, _vp, _vp, _i, _i, _i, _vp]
     tepd_embedding_bwd = [_vp, _vp, _vp, _vp, _i, _i, _i, _vp]
     tepd_xent_fwd_bwd = [_vp, _vp, _vp, _vp, _i, _i, _i, _f, _vp]
@@ -253,6 +255,86 @@ def gemm2(a: torch.Tensor, b: torch.Tensor, *, a_mn: bool = False, b_mn: bool = 
     _check(rc, "gemm2_bf16")
     _count()
     return out
+
+
+# --------------------------------------------------------------------------------------------- convolution
+CONV_NATIVE = os.environ.get("TEPDIST_CONV", "native") != "cudnn"   # "cudnn": library path (the reference's K9)
+
+
+def conv_native_ok(x: torch.Tensor, w: torch.Tensor) -> bool:
+    """Own path: NHWC im2col / col2im kernels (conv_sm100.cu) around the tcgen05 GEMMs."""
+    return CONV_NATIVE and x.is_cuda and x.dtype == torch.bfloat16 and w.shape[0] % 8 == 0
+
+
+def _conv_geom(x_shape, w_shape, stride: int, pad: int):
+    N, C, H, W = x_shape
+    Cout, Cin, kh, kw = w_shape
+    Ho, Wo = (H + 2 * pad - kh) // stride + 1, (W + 2 * pad - kw) // stride + 1
+    Kpad = (kh * kw * C + 7) // 8 * 8
+    direct = kh == 1 and kw == 1 and stride == 1 and pad == 0 and C % 8 == 0     # the convolution IS a GEMM
+    return N, C, H, W, Cout, kh, kw, Ho, Wo, Kpad, direct
+
+
+def _nhwc(x: torch.Tensor) -> torch.Tensor:
+    """[N, C, H, W] (any strides) -> contiguous [N, H, W, C] view of channels_last memory."""
+    return x.contiguous(memory_format=torch.channels_last).permute(0, 2, 3, 1)
+
+
+def _conv_weight_matrix(w: torch.Tensor, Kpad: int) -> torch.Tensor:
+    """OIHW -> [Cout, (tap, cin)] bf16, K padded with zeros (tap-major columns match im2col)."""
+    Cout = w.shape[0]
+    m = w.permute(0, 2, 3, 1).reshape(Cout, -1).to(torch.bfloat16)
+    if m.shape[1] != Kpad:
+        m = torch.nn.functional.pad(m, (0, Kpad - m.shape[1]))
+    return m.contiguous()
+
+
+def _im2col(xn: torch.Tensor, g) -> torch.Tensor:
+    N, C, H, W, Cout, kh, kw, Ho, Wo, Kpad, direct = g
+    if direct:
+        return xn.reshape(N * H * W, C)
+    col = torch.empty(N * Ho * Wo, Kpad, dtype=torch.bfloat16, device=xn.device)
+    return col
+
+
+def conv2d_fwd(x: torch.Tensor, w: torch.Tensor, stride: int, pad: int) -> torch.Tensor:
+    """x [N,C,H,W] bf16, w [Cout,Cin,kh,kw] -> y [N,Cout,Ho,Wo] (channels_last memory)."""
+    g = _conv_geom(x.shape, w.shape, stride, pad)
+    N, C, H, W, Cout, kh, kw, Ho, Wo, Kpad, direct = g
+    xn = _nhwc(x)
+    col = _im2col(xn, g)
+    if not direct:
+        _check(lib().tepd_im2col_nhwc(xn.data_ptr(), col.data_ptr(), N, H, W, C, Ho, Wo, kh, kw, stride, pad, Kpad, _stream()), "im2col")
+        _count()
+    y = gemm(col, _conv_weight_matrix(w, Kpad))
+    return y.view(N, Ho, Wo, Cout).permute(0, 3, 1, 2)
+
+
+def conv2d_dgrad(dy: torch.Tensor, w: torch.Tensor, x_shape, stride: int, pad: int) -> torch.Tensor:
+    g = _conv_geom(x_shape, w.shape, stride, pad)
+    N, C, H, W, Cout, kh, kw, Ho, Wo, Kpad, direct = g
+    dyn = _nhwc(dy).reshape(N * Ho * Wo, Cout)
+    dcol = gemm(dyn, _conv_weight_matrix(w, Kpad), b_mn=True)            # [rows, Kpad]
+    if direct:
+        return dcol.view(N, H, W, C).permute(0, 3, 1, 2)
+    dx = torch.empty(N, H, W, C, dtype=torch.bfloat16, device=dy.device)
+    _check(lib().tepd_col2im_nhwc(dcol.data_ptr(), dx.data_ptr(), N, H, W, C, Ho, Wo, kh, kw, stride, pad, Kpad, _stream()), "col2im")
+    _count()
+    return dx.permute(0, 3, 1, 2)
+
+
+def conv2d_wgrad(dy: torch.Tensor, x: torch.Tensor, w_shape, stride: int, pad: int) -> torch.Tensor:
+    """fp32 [Cout, Cin, kh, kw] = dY^T . im2col(x)."""
+    g = _conv_geom(x.shape, w_shape, stride, pad)
+    N, C, H, W, Cout, kh, kw, Ho, Wo, Kpad, direct = g
+    xn = _nhwc(x)
+    col = _im2col(xn, g)
+    if not direct:
+        _check(lib().tepd_im2col_nhwc(xn.data_ptr(), col.data_ptr(), N, H, W, C, Ho, Wo, kh, kw, stride, pad, Kpad, _stream()), "im2col")
+        _count()
+    dyn = _nhwc(dy).reshape(N * Ho * Wo, Cout)
+    gw = gemm(dyn, col, a_mn=True, b_mn=True, out_dtype=torch.float32)   # [Cout, Kpad]
+    return gw[:, :kh * kw * C].reshape(Cout, kh, kw, C).permute(0, 3, 1, 2)
 
 
 # --------------------------------------------------------------------------------------------- LayerNorm

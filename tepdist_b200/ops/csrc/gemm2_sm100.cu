@@ -319,18 +319,19 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
 #pragma unroll
           for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]) * p.alpha;
           if (sk_store) {
-            float4* wp = reinterpret_cast<float4*>(p.sk_ws + ((long long)blockIdx.x * BM + row_in_tile) * BN + c * 32);
+            // workspace layout is thread-major ([chunk][quad][thread] float4): a warp writes 512 contiguous bytes per store
+            float4* wp = reinterpret_cast<float4*>(p.sk_ws + (long long)blockIdx.x * BM * BN) + (c * 8) * 128 + row_in_tile;
 #pragma unroll
-            for (int q = 0; q < 8; ++q) wp[q] = make_float4(v[q * 4], v[q * 4 + 1], v[q * 4 + 2], v[q * 4 + 3]);
+            for (int q = 0; q < 8; ++q) wp[q * 128] = make_float4(v[q * 4], v[q * 4 + 1], v[q * 4 + 2], v[q * 4 + 3]);
             continue;
           }
           if (sk_finish) {
             for (int j = cluster_id + 1; j < partner_end; ++j) {
-              const float4* wp = reinterpret_cast<const float4*>(p.sk_ws + ((long long)(2 * j + cta) * BM + row_in_tile) * BN + c * 32);
+              const float4* wp = reinterpret_cast<const float4*>(p.sk_ws + (long long)(2 * j + cta) * BM * BN) + (c * 8) * 128 + row_in_tile;
 #pragma unroll
               for (int q = 0; q < 8; ++q) {
                 float4 t;
-                asm volatile("ld.global.cg.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(t.x), "=f"(t.y), "=f"(t.z), "=f"(t.w) : "l"(wp + q));
+                asm volatile("ld.global.cg.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(t.x), "=f"(t.y), "=f"(t.z), "=f"(t.w) : "l"(wp + q * 128));
                 v[q * 4] += t.x; v[q * 4 + 1] += t.y; v[q * 4 + 2] += t.z; v[q * 4 + 3] += t.w;
               }
             }
@@ -442,7 +443,7 @@ extern "C" int tepd_gemm2_bf16(const void* A, const void* B, void* D, void* D2, 
                                const void* aux, int M, int N, int K, long long lda, long long ldb, long long ldd, long long ld_res,
                                int b_mn, int act, int bias_bf16, float alpha, int num_sms, void* stream, int a_mn, int out_fp32,
                                int stream_k) {
-  if (N % 8 != 0 || K % 8 != 0 || M <= 0 || (a_mn && (M % 8))) return -2;
+  if (N % 8 != 0 || M <= 0 || (a_mn && (M % 8)) || (K % 8 != 0 && !(a_mn && b_mn))) return -2;
   if (out_fp32 && (act || residual || D2 || aux)) return -5;
   if (a_mn && !b_mn) return -8;   // (weight gradients are MN-major on both sides; the mixed case has no user)
   Gemm2Params p;

@@ -586,7 +586,8 @@ extern "C" int tepd_gemm_bf16(const void* A, const void* B, void* D, const void*
                               long long stride_res, int a_mn, int b_mn, int out_fp32, int accumulate, int act,
                               int bias_bf16, float alpha, int split_k, int block_n, int num_sms, void* stream, void* D2,
                               const void* aux) {
-  if (N % 8 != 0 || K % 8 != 0 || M <= 0) return -2;
+  // K % 8 is a TMA row-pitch requirement of K-major operands only (MN-major operands have K as the outer dimension)
+  if (N % 8 != 0 || M <= 0 || (K % 8 != 0 && !(a_mn && b_mn))) return -2;
   if ((D2 || aux) && out_fp32) return -5;
   if ((a_mn && (M % 8)) || (accumulate && !out_fp32)) return -3;
   GemmParams p;

@@ -1015,13 +1015,23 @@ class Executor:
             if tb: B = B.transpose(-1, -2)
             return [torch.matmul(A, B)]
         if op == "einsum": return [torch.einsum(a["eq"], ins[0], ins[1])]
-        if op == "conv2d": return [F.conv2d(ins[0], ins[1], stride=a["stride"], padding=a["padding"])]
+        # convolutions: own path = NHWC im2col / col2im kernels + tcgen05 GEMMs (ops/csrc/conv_sm100.cu); cuDNN through torch
+        # is the reference-semantics path (TEPDIST_CONV=cudnn) and the CPU oracle
+        if op == "conv2d":
+            if ops.conv_native_ok(ins[0], ins[1]):
+                return [ops.conv2d_fwd(ins[0], ins[1], a["stride"], a["padding"])]
+            return [F.conv2d(ins[0], ins[1], stride=a["stride"], padding=a["padding"])]
         if op == "conv2d_dgrad":
             dy, w = ins
+            if ops.conv_native_ok(dy, w):
+                return [ops.conv2d_dgrad(dy, w, n.outputs[0].shape, a["stride"], a["padding"])]
             return [torch.nn.grad.conv2d_input(n.outputs[0].shape, w, dy, stride=a["stride"], padding=a["padding"])]
         if op == "conv2d_wgrad":
             dy, xx = ins
-            gw = torch.nn.grad.conv2d_weight(xx, n.outputs[0].shape, dy, stride=a["stride"], padding=a["padding"])
+            if ops.conv_native_ok(xx, dy.new_empty((n.outputs[0].shape[0], 1, 1, 1))):
+                gw = ops.conv2d_wgrad(dy, xx, n.outputs[0].shape, a["stride"], a["padding"])
+            else:
+                gw = torch.nn.grad.conv2d_weight(xx, n.outputs[0].shape, dy, stride=a["stride"], padding=a["padding"])
             out = self._grad_out(n, 0, n.outputs[0].shape)
             out.add_(gw.float())
             return [out]

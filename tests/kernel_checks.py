@@ -301,6 +301,42 @@ def check_gemm_perf():
     return out
 
 
+def check_conv():
+    """NHWC im2col / col2im kernels + tcgen05 GEMMs vs torch (cuDNN) convolutions in fp32 on the same bf16 inputs."""
+    import torch.nn.functional as F
+    from tepdist_b200 import ops
+    out = {}
+    torch.manual_seed(3)
+    cases = [  # N, Cin, H, Cout, k, stride, pad
+        (4, 64, 56, 160, 1, 1, 0), (4, 160, 56, 320, 3, 1, 1), (4, 320, 28, 640, 3, 2, 1), (4, 256, 56, 512, 1, 2, 0),
+        (4, 3, 224, 64, 7, 2, 3), (4, 640, 7, 1280, 3, 1, 1), (2, 1280, 7, 2560, 1, 1, 0),
+    ]
+    for (N, C, H, Co, k, st, pd) in cases:
+        x = torch.randn(N, C, H, H, device="cuda", dtype=torch.bfloat16)
+        w = (torch.randn(Co, C, k, k, device="cuda") * (2.0 / (C * k * k)) ** 0.5).to(torch.bfloat16)
+        tag = f"N{N}C{C}H{H}Co{Co}k{k}s{st}"
+        y = ops.conv2d_fwd(x, w, st, pd)
+        ref = F.conv2d(x.float(), w.float(), stride=st, padding=pd)
+        out[f"fwd_{tag}"] = _rel_err(y, ref)
+        dy = torch.randn_like(ref).to(torch.bfloat16)
+        gw = ops.conv2d_wgrad(dy, x, w.shape, st, pd)
+        out[f"wgrad_{tag}"] = _rel_err(gw, torch.nn.grad.conv2d_weight(x.float(), w.shape, dy.float(), stride=st, padding=pd))
+        if C % 8 == 0:
+            dx = ops.conv2d_dgrad(dy, w, x.shape, st, pd)
+            out[f"dgrad_{tag}"] = _rel_err(dx, torch.nn.grad.conv2d_input(x.shape, w.float(), dy.float(), stride=st, padding=pd))
+    for k_, v in out.items():
+        assert v < 1.5e-2, (k_, v)
+    # timing vs cuDNN (channels_last bf16) on the two dominant Wide-ResNet-250M shapes
+    for (N, C, H, Co, k, st, pd) in [(4, 160, 56, 320, 3, 1, 1), (4, 320, 56, 640, 1, 1, 0)]:
+        x = torch.randn(N, C, H, H, device="cuda", dtype=torch.bfloat16).contiguous(memory_format=torch.channels_last)
+        w = torch.randn(Co, C, k, k, device="cuda", dtype=torch.bfloat16)
+        wc = w.contiguous(memory_format=torch.channels_last)
+        fl = 2.0 * N * (H // st) ** 2 * Co * C * k * k / 1e9
+        out[f"tflops_ours_C{C}k{k}"] = fl / _time_ms(lambda: ops.conv2d_fwd(x, w, st, pd))
+        out[f"tflops_cudnn_C{C}k{k}"] = fl / _time_ms(lambda: F.conv2d(x, wc, stride=st, padding=pd))
+    return out
+
+
 # ------------------------------------------------------------------------------------------ elementwise
 def check_layernorm():
     from tepdist_b200 import ops
@@ -471,6 +507,7 @@ CHECKS = {
     "attn_fwd": check_attn_fwd,
     "attn_bwd": check_attn_bwd,
     "gemm_perf": check_gemm_perf,
+    "conv": check_conv,
     "gemm2": check_gemm2,
     "attn_perf": check_attn_perf,
 }
