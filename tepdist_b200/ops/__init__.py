@@ -72,6 +72,8 @@ class _Sig:
     tepd_gelu_fwd = [_vp, _vp, _ll, _vp]
     tepd_gelu_bwd = [_vp, _vp, _vp, _ll, _vp]
     tepd_colsum = [_vp, _vp, _i, _i, _vp]
+    tepd_bn_fwd_nhwc = [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _f, _i, _vp]
+    tepd_bn_bwd_nhwc = [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _vp]
     tepd_im2col_nhwc = [_vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _vp]
     tepd_col2im_nhwc = [_vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _vp]
     tepd_embedding_fwd = [_vp, _vp, _vp, _vp, _i, _i, _i, _vp]
@@ -335,6 +337,36 @@ def conv2d_wgrad(dy: torch.Tensor, x: torch.Tensor, w_shape, stride: int, pad: i
     dyn = _nhwc(dy).reshape(N * Ho * Wo, Cout)
     gw = gemm(dyn, col, a_mn=True, b_mn=True, out_dtype=torch.float32)   # [Cout, Kpad]
     return gw[:, :kh * kw * C].reshape(Cout, kh, kw, C).permute(0, 3, 1, 2)
+
+
+def bn_native_ok(x: torch.Tensor) -> bool:
+    return CONV_NATIVE and x.is_cuda and x.dtype == torch.bfloat16 and x.dim() == 4 and x.shape[1] % 8 == 0
+
+
+def batchnorm_fwd(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, eps: float, relu: bool = False):
+    """Training-mode batch norm over (N, H, W) of x [N,C,H,W] in channels_last memory -> (y, mean[C], rstd[C])."""
+    N, C, H, W = x.shape
+    xn = _nhwc(x)
+    y = torch.empty_like(xn)
+    ws = torch.zeros(2, C, dtype=torch.float32, device=x.device)
+    mean = torch.empty(C, dtype=torch.float32, device=x.device)
+    rstd = torch.empty(C, dtype=torch.float32, device=x.device)
+    _check(lib().tepd_bn_fwd_nhwc(xn.data_ptr(), gamma.data_ptr(), beta.data_ptr(), y.data_ptr(), mean.data_ptr(), rstd.data_ptr(),
+                                  ws.data_ptr(), N * H * W, C, float(eps), int(relu), _stream()), "bn_fwd")
+    _count(2)
+    return y.permute(0, 3, 1, 2), mean, rstd
+
+
+def batchnorm_bwd(dy: torch.Tensor, x: torch.Tensor, gamma: torch.Tensor, mean: torch.Tensor, rstd: torch.Tensor):
+    """-> (dx [N,C,H,W] channels_last, dgamma[C] fp32, dbeta[C] fp32)."""
+    N, C, H, W = x.shape
+    xn, dyn = _nhwc(x), _nhwc(dy)
+    dx = torch.empty_like(xn)
+    ws = torch.zeros(2, C, dtype=torch.float32, device=x.device)     # [sum(dy), sum(dy * xhat)] = [dbeta, dgamma]
+    _check(lib().tepd_bn_bwd_nhwc(dyn.data_ptr(), xn.data_ptr(), gamma.data_ptr(), mean.data_ptr(), rstd.data_ptr(), dx.data_ptr(),
+                                  ws.data_ptr(), N * H * W, C, _stream()), "bn_bwd")
+    _count(2)
+    return dx.permute(0, 3, 1, 2), ws[1], ws[0]
 
 
 # --------------------------------------------------------------------------------------------- LayerNorm

@@ -237,6 +237,106 @@ __global__ void gelu_bwd_kernel(const uint4* __restrict__ dy, const uint4* __res
   }
 }
 
+// ------------------------------------------------------------------ BatchNorm (training mode) on NHWC rows
+// x is [rows = N*H*W, C] (channels_last memory).  Two passes each way, both column-parallel like colsum:
+//   forward : bn_reduce2 accumulates sum(x) and sum(x^2) per channel (fp32 atomics over row strips), bn_fwd_apply turns
+//             them into mean / rstd and writes y = (x - mean) * rstd * gamma + beta (+ ReLU);
+//   backward: bn_reduce2 with dy accumulates sum(dy) and sum(dy * xhat), bn_bwd_apply writes
+//             dx = gamma * rstd * (dy - mean(dy) - xhat * mean(dy * xhat)).
+// MODE 0: (x, x^2); MODE 1: (dy, dy * xhat) with xhat recomputed from x, mean, rstd.
+template <int MODE>
+__global__ void __launch_bounds__(256) bn_reduce2_kernel(const bf16* __restrict__ a, const bf16* __restrict__ x,
+                                                        const float* __restrict__ mean, const float* __restrict__ rstd,
+                                                        float* __restrict__ out0, float* __restrict__ out1, int rows, int C,
+                                                        int rows_per_block) {
+  __shared__ float red[2][8][256];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int col0 = blockIdx.x * 256 + lane * 8;
+  const int r0 = blockIdx.y * rows_per_block;
+  const int r1 = min(rows, r0 + rows_per_block);
+  float s0[8] = {0, 0, 0, 0, 0, 0, 0, 0}, s1[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  pdl_wait();
+  if (col0 < C) {
+    float mu[8], rs[8];
+    if (MODE == 1) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) { mu[j] = mean[col0 + j]; rs[j] = rstd[col0 + j]; }
+    }
+    for (int r = r0 + warp; r < r1; r += 8) {
+      float f[8];
+      unpack8(__ldg(reinterpret_cast<const uint4*>(a + (size_t)r * C + col0)), f);
+      if (MODE == 0) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) { s0[j] += f[j]; s1[j] += f[j] * f[j]; }
+      } else {
+        float xv[8];
+        unpack8(__ldg(reinterpret_cast<const uint4*>(x + (size_t)r * C + col0)), xv);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) { s0[j] += f[j]; s1[j] += f[j] * (xv[j] - mu[j]) * rs[j]; }
+      }
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < 8; ++j) { red[0][warp][lane * 8 + j] = s0[j]; red[1][warp][lane * 8 + j] = s1[j]; }
+  __syncthreads();
+  const int c = threadIdx.x;
+  if (blockIdx.x * 256 + c < C) {
+    float t0 = 0.f, t1 = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) { t0 += red[0][w][c]; t1 += red[1][w][c]; }
+    atomicAdd(out0 + blockIdx.x * 256 + c, t0);
+    atomicAdd(out1 + blockIdx.x * 256 + c, t1);
+  }
+}
+
+// sums = [sum(x), sum(x^2)] -> mean, rstd (written by block row 0) and y
+__global__ void __launch_bounds__(256) bn_fwd_apply_kernel(const bf16* __restrict__ x, const float* __restrict__ sum,
+                                                          const float* __restrict__ sumsq, const float* __restrict__ gamma,
+                                                          const float* __restrict__ beta, bf16* __restrict__ y,
+                                                          float* __restrict__ mean_out, float* __restrict__ rstd_out, int rows,
+                                                          int C, float eps, int relu) {
+  pdl_wait();
+  const int cv = C >> 3;
+  const float inv = 1.f / rows;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < (size_t)rows * cv; i += (size_t)gridDim.x * blockDim.x) {
+    const int c0 = (int)(i % cv) * 8;
+    float f[8], o[8];
+    unpack8(__ldg(reinterpret_cast<const uint4*>(x) + i), f);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float mu = sum[c0 + j] * inv;
+      const float var = fmaxf(sumsq[c0 + j] * inv - mu * mu, 0.f);
+      const float rs = rsqrtf(var + eps);
+      float v = (f[j] - mu) * rs * gamma[c0 + j] + beta[c0 + j];
+      o[j] = relu ? fmaxf(v, 0.f) : v;
+      if (i < (size_t)cv) { mean_out[c0 + j] = mu; rstd_out[c0 + j] = rs; }
+    }
+    reinterpret_cast<uint4*>(y)[i] = pack8(o);
+  }
+}
+
+__global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ x,
+                                                          const float* __restrict__ gamma, const float* __restrict__ mean,
+                                                          const float* __restrict__ rstd, const float* __restrict__ sum_dy,
+                                                          const float* __restrict__ sum_dyxh, bf16* __restrict__ dx, int rows, int C) {
+  pdl_wait();
+  const int cv = C >> 3;
+  const float inv = 1.f / rows;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < (size_t)rows * cv; i += (size_t)gridDim.x * blockDim.x) {
+    const int c0 = (int)(i % cv) * 8;
+    float d[8], f[8], o[8];
+    unpack8(__ldg(reinterpret_cast<const uint4*>(dy) + i), d);
+    unpack8(__ldg(reinterpret_cast<const uint4*>(x) + i), f);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float rs = rstd[c0 + j];
+      const float xh = (f[j] - mean[c0 + j]) * rs;
+      o[j] = gamma[c0 + j] * rs * (d[j] - sum_dy[c0 + j] * inv - xh * sum_dyxh[c0 + j] * inv);
+    }
+    reinterpret_cast<uint4*>(dx)[i] = pack8(o);
+  }
+}
+
 // ------------------------------------------------------------------ column sum (bias gradients)
 // out[c] += sum_r in[r, c];  block handles 256 columns (32 lanes x 8) x a strip of rows.
 __global__ void __launch_bounds__(256) colsum_kernel(const bf16* __restrict__ in, float* __restrict__ out, int rows, int C,
@@ -547,4 +647,33 @@ extern "C" int tepd_axpy_f32(void* acc, const void* g, long long n, float a, voi
 extern "C" int tepd_cast_f32_bf16(const void* in, void* out, long long n, void* stream) {
   cast_f32_bf16_kernel<<<grid_for(n, 256), 256, 0, CS(stream)>>>((const float*)in, (bf16*)out, n);
   return (int)cudaGetLastError();
+}
+
+// ---- BatchNorm NHWC.  ws: fp32 [2, C] scratch, zeroed by the caller (sum / sumsq, or sum(dy) / sum(dy*xhat) which the
+// backward ALSO adds into dbeta / dgamma: the caller points ws at zero-filled temporaries and accumulates them itself).
+extern "C" int tepd_bn_fwd_nhwc(const void* x, const void* gamma, const void* beta, void* y, void* mean, void* rstd, void* ws,
+                                int rows, int C, float eps, int relu, void* stream) {
+  if (C % 8) return -2;
+  const int rpb = 128;
+  dim3 grid((C + 255) / 256, (rows + rpb - 1) / rpb);
+  float* w = (float*)ws;
+  cudaError_t e = tepd::launch(bn_reduce2_kernel<0>, grid, dim3(256), 0, CS(stream), (const bf16*)x, (const bf16*)nullptr,
+                               (const float*)nullptr, (const float*)nullptr, w, w + C, rows, C, rpb);
+  if (e != cudaSuccess) return (int)e;
+  return (int)tepd::launch(bn_fwd_apply_kernel, dim3(grid_for((size_t)rows * C / 8, 256)), dim3(256), 0, CS(stream), (const bf16*)x,
+                           (const float*)w, (const float*)(w + C), (const float*)gamma, (const float*)beta, (bf16*)y, (float*)mean,
+                           (float*)rstd, rows, C, eps, relu);
+}
+extern "C" int tepd_bn_bwd_nhwc(const void* dy, const void* x, const void* gamma, const void* mean, const void* rstd, void* dx,
+                                void* ws, int rows, int C, void* stream) {
+  if (C % 8) return -2;
+  const int rpb = 128;
+  dim3 grid((C + 255) / 256, (rows + rpb - 1) / rpb);
+  float* w = (float*)ws;
+  cudaError_t e = tepd::launch(bn_reduce2_kernel<1>, grid, dim3(256), 0, CS(stream), (const bf16*)dy, (const bf16*)x,
+                               (const float*)mean, (const float*)rstd, w, w + C, rows, C, rpb);
+  if (e != cudaSuccess) return (int)e;
+  return (int)tepd::launch(bn_bwd_apply_kernel, dim3(grid_for((size_t)rows * C / 8, 256)), dim3(256), 0, CS(stream), (const bf16*)dy,
+                           (const bf16*)x, (const float*)gamma, (const float*)mean, (const float*)rstd, (const float*)w,
+                           (const float*)(w + C), (bf16*)dx, rows, C);
 }

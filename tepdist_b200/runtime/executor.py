@@ -297,6 +297,7 @@ class Executor:
             if nid < len(g.nodes):
                 self.free_after.setdefault(nid, []).append(k_)
         self.ln_stats: Dict[Tuple[Tuple[int, int], Tuple[int, int]], Tuple[torch.Tensor, torch.Tensor]] = {}
+        self.bn_stats: Dict[Tuple[int, Tuple[int, int]], Tuple[torch.Tensor, torch.Tensor]] = {}
         self.input_names = [n.name for n in g.inputs()]
         self.grad_accumulate = False   # True when gradients add up over micro-batches (pipeline stage workers)
         self._plan_store_init()
@@ -1037,9 +1038,19 @@ class Executor:
             return [out]
         if op == "batchnorm":
             xx, gm, bt = ins
+            if ops.bn_native_ok(xx) and gm.dtype == torch.float32:
+                y, mean, rstd = ops.batchnorm_fwd(xx, gm, bt, a["eps"])
+                self.bn_stats[(self._tag, n.inputs[0].key())] = (mean, rstd)     # consumed by the matching batchnorm_bwd
+                return [y]
             return [F.batch_norm(xx, None, None, gm.to(xx.dtype), bt.to(xx.dtype), True, 0.0, a["eps"])]
         if op == "batchnorm_bwd":
             dy, xx, gm = ins
+            st_ = self.bn_stats.pop((self._tag, n.inputs[1].key()), None)
+            if st_ is not None and ops.bn_native_ok(xx) and gm.dtype == torch.float32:
+                dx, dgm, dbt = ops.batchnorm_bwd(dy, xx, gm, st_[0], st_[1])
+                dg = self._grad_out(n, 1, n.outputs[1].shape); dg.add_(dgm)
+                db = self._grad_out(n, 2, n.outputs[2].shape); db.add_(dbt)
+                return [dx, dg, db]
             xf, dyf = xx.float(), dy.float()
             mean = xf.mean((0, 2, 3), keepdim=True)
             var = xf.var((0, 2, 3), unbiased=False, keepdim=True)

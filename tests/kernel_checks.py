@@ -324,6 +324,24 @@ def check_conv():
         if C % 8 == 0:
             dx = ops.conv2d_dgrad(dy, w, x.shape, st, pd)
             out[f"dgrad_{tag}"] = _rel_err(dx, torch.nn.grad.conv2d_input(x.shape, w.float(), dy.float(), stride=st, padding=pd))
+    # BatchNorm (training mode) NHWC kernels vs fp32 torch
+    for (N, C, H) in [(4, 320, 28), (4, 64, 112), (2, 1280, 7)]:
+        x = (torch.randn(N, C, H, H, device="cuda") * 2.0 + 0.5).to(torch.bfloat16)
+        gm, bt = torch.rand(C, device="cuda") + 0.5, torch.randn(C, device="cuda")
+        y, mean, rstd = ops.batchnorm_fwd(x, gm, bt, 1e-5)
+        xf = x.float()
+        mu, var = xf.mean((0, 2, 3)), xf.var((0, 2, 3), unbiased=False)
+        ref = (xf - mu.view(1, -1, 1, 1)) * torch.rsqrt(var + 1e-5).view(1, -1, 1, 1) * gm.view(1, -1, 1, 1) + bt.view(1, -1, 1, 1)
+        out[f"bn_fwd_C{C}H{H}"] = _rel_err(y, ref)
+        out[f"bn_mean_C{C}H{H}"] = _rel_err(mean, mu)
+        dy = torch.randn_like(ref).to(torch.bfloat16)
+        dx, dgm, dbt = ops.batchnorm_bwd(dy, x, gm, mean, rstd)
+        xr = xf.clone().requires_grad_(True)
+        gr, br = gm.clone().requires_grad_(True), bt.clone().requires_grad_(True)
+        F.batch_norm(xr, None, None, gr, br, True, 0.0, 1e-5).backward(dy.float())
+        out[f"bn_dx_C{C}H{H}"] = _rel_err(dx, xr.grad)
+        out[f"bn_dgamma_C{C}H{H}"] = _rel_err(dgm, gr.grad)
+        out[f"bn_dbeta_C{C}H{H}"] = _rel_err(dbt, br.grad)
     for k_, v in out.items():
         assert v < 1.5e-2, (k_, v)
     # timing vs cuDNN (channels_last bf16) on the two dominant Wide-ResNet-250M shapes
