@@ -194,8 +194,9 @@ def gemm(a: torch.Tensor, b: torch.Tensor, *, a_mn: bool = False, b_mn: bool = F
         if accumulate and out.dtype == torch.float32:
             tiles = ((M + 127) // 128) * ((N + 255) // 256) * batch
             kb = (K + 63) // 64
-            if STREAM_K and tiles * kb >= 4 * _sms():
-                split_k = -1    # stream-K: every SM gets the same number of k-blocks (fp32 red.add flush per tile)
+            if STREAM_K and tiles >= _sms():
+                split_k = -1    # stream-K: every SM gets the same number of k-blocks (fp32 red.add flush per tile); measured
+                                # neutral-to-better from one full wave of tiles up, worse than plain split-K below that
             else:
                 while tiles * split_k * 2 <= _sms() and split_k * 2 <= max(1, kb // 4):
                     split_k *= 2

@@ -63,8 +63,8 @@ struct Units {
   int tail_len;          // k-blocks of the leading partial unit (0 = none)
   int n_full, head_len;  // full tiles, k-blocks of the trailing partial unit (0 = none)
   int count;
-  __device__ __forceinline__ void init(const Gemm2Params& p, int cid, int nclusters, int total) {
-    stream_k = p.stream_k; k_blocks = p.k_blocks; num_clusters = nclusters; cluster_id = cid; total_tiles = total;
+  __device__ __forceinline__ void init(const Gemm2Params& p, int cid, int nclusters, int total, bool ext) {
+    stream_k = ext ? p.stream_k : 0; k_blocks = p.k_blocks; num_clusters = nclusters; cluster_id = cid; total_tiles = total;
     if (stream_k > 0) {
       const long long iters = (long long)total * k_blocks;
       const long long c0 = (long long)cid * stream_k;
@@ -157,7 +157,10 @@ __device__ __forceinline__ float gelu_grad_f(float x) {
   return 0.5f * (1.0f + t) + 0.5f * x * (1.0f - t * t) * k0 * (1.0f + 3.0f * k1 * x * x);
 }
 
-template <bool A_MN, bool B_MN>
+// EXT = false is the lean instantiation used for every bf16-output forward / dgrad GEMM (tile-parallel schedule, no
+// stream-K or fp32 branches in the epilogue: measured 5 % faster on the GPT-2 step than carrying them); EXT = true adds
+// the stream-K schedule, MN-major A and fp32 plain stores (weight gradients).
+template <bool A_MN, bool B_MN, bool EXT>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1)
 gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b, const Gemm2Params p) {
   extern __shared__ uint8_t smem_raw[];
@@ -206,7 +209,7 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
       int stage = 0;
       uint32_t phase = 0;
       Units un;
-      un.init(p, cluster_id, num_clusters, total_tiles);
+      un.init(p, cluster_id, num_clusters, total_tiles, EXT);
       for (int s = 0; s < un.count; ++s) {
         int tile, kb0, kb1;
         un.get(s, tile, kb0, kb1);
@@ -244,7 +247,7 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
       int stage = 0, acc = 0;
       uint32_t phase = 0, acc_phase = 0;
       Units un;
-      un.init(p, cluster_id, num_clusters, total_tiles);
+      un.init(p, cluster_id, num_clusters, total_tiles, EXT);
       for (int s = 0; s < un.count; ++s) {
         int tile, kb0, kb1;
         un.get(s, tile, kb0, kb1);
@@ -278,12 +281,12 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
     int acc = 0;
     uint32_t acc_phase = 0;
     Units un;
-    un.init(p, cluster_id, num_clusters, total_tiles);
+    un.init(p, cluster_id, num_clusters, total_tiles, EXT);
     for (int s = 0; s < un.count; ++s) {
       int tile, kb0, kb1;
       un.get(s, tile, kb0, kb1);
       const int m_pair = tile % p.m_pairs, n_blk = tile / p.m_pairs;
-      const bool sk_part = p.stream_k > 0 && !(kb0 == 0 && kb1 == p.k_blocks);
+      const bool sk_part = EXT && p.stream_k > 0 && !(kb0 == 0 && kb1 == p.k_blocks);
       const bool sk_store = sk_part && kb0 > 0;    // first unit of this pair: hand the partial tile to the finisher
       const bool sk_finish = sk_part && kb0 == 0;  // last unit of this pair: collect the partials of the pairs that follow
       const int row_in_tile = quarter * 32 + lane;
@@ -336,7 +339,7 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
               }
             }
           }
-          if (p.out_fp32) {
+          if (EXT && p.out_fp32) {
             float4* dp = reinterpret_cast<float4*>(reinterpret_cast<float*>(p.D) + (long long)row * p.ldd + col0);
 #pragma unroll
             for (int q = 0; q < 8; ++q)
@@ -487,10 +490,10 @@ extern "C" int tepd_gemm2_bf16(const void* A, const void* B, void* D, void* D2, 
     clusters = (int)((iters + per - 1) / per);
   }
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
-#define LAUNCH2(AM, BMN)                                                                                                        \
+#define LAUNCH2(AM, BMN, EX)                                                                                                    \
   {                                                                                                                             \
     static bool cfg = false;                                                                                                    \
-    auto kern = gemm2_bf16_kernel<AM, BMN>;                                                                                     \
+    auto kern = gemm2_bf16_kernel<AM, BMN, EX>;                                                                                     \
     if (!cfg) {                                                                                                                 \
       if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES) != cudaSuccess) return -6;        \
       cfg = true;                                                                                                               \
@@ -498,9 +501,10 @@ extern "C" int tepd_gemm2_bf16(const void* A, const void* B, void* D, void* D2, 
     cudaError_t le = tepd::launch(kern, dim3(2 * clusters), dim3(THREADS), SMEM_BYTES, s, ta, tb, p);                           \
     if (le != cudaSuccess) return (int)le;                                                                                      \
   }
-  if (a_mn) LAUNCH2(true, true)
-  else if (b_mn) LAUNCH2(false, true)
-  else LAUNCH2(false, false)
+  const bool ext = p.stream_k > 0 || out_fp32;
+  if (a_mn) LAUNCH2(true, true, true)
+  else if (b_mn) { if (ext) LAUNCH2(false, true, true) else LAUNCH2(false, true, false) }
+  else { if (ext) LAUNCH2(false, false, true) else LAUNCH2(false, false, false) }
 #undef LAUNCH2
   return (int)cudaGetLastError();
 }
