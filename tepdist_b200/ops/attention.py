@@ -10,6 +10,8 @@ import math
 
 import torch
 
+_HD = 64   # head dim of the tcgen05 kernels (attention_sm100.cu)
+
 
 def _ref_fwd(q, k, v, scale, causal):
     # q,k,v: [B,S,H,D] -> fp32 math in [B,H,S,D]
@@ -34,6 +36,13 @@ def attention_fwd(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, scale: floa
     if not q.is_cuda:
         o, lse, _ = _ref_fwd(q, k, v, scale, causal)
         return o, lse
+    if D != _HD or S % 128:
+        if D < _HD and S % 128 == 0:   # e.g. GPT-MoE's 48-wide heads: zero-pad the head dim, the kernel math is unchanged
+            qp, kp, vp = (torch.nn.functional.pad(t, (0, _HD - D)) for t in (q, k, v))
+            o, lse = attention_fwd(qp, kp, vp, scale, causal)
+            return o[..., :D].contiguous(), lse
+        o, lse, _ = _ref_fwd(q, k, v, scale, causal)   # shapes the tcgen05 kernel does not cover: plain torch math
+        return o, lse
     from . import lib, _check, _count, _stream
     assert q.dtype == torch.bfloat16 and q.stride(3) == 1
     assert q.stride() == k.stride() == v.stride(), "q/k/v must share strides (slices of one qkv buffer)"
@@ -55,7 +64,12 @@ def attention_bwd(do: torch.Tensor, q, k, v, o, lse, scale: float | None = None,
     if dqkv_out is None:
         dqkv_out = torch.empty(B, S, H, 3, D, dtype=q.dtype, device=q.device)
     dq, dk, dv = dqkv_out[:, :, :, 0], dqkv_out[:, :, :, 1], dqkv_out[:, :, :, 2]
-    if not q.is_cuda:
+    if q.is_cuda and D < _HD and S % 128 == 0:
+        pad = lambda t: torch.nn.functional.pad(t, (0, _HD - D))
+        gq, gk, gv = attention_bwd(pad(do), pad(q), pad(k), pad(v), pad(o), lse, scale, causal)
+        dq.copy_(gq[..., :D]); dk.copy_(gk[..., :D]); dv.copy_(gv[..., :D])
+        return dq, dk, dv
+    if not q.is_cuda or D != _HD or S % 128:
         _, _, p = _ref_fwd(q, k, v, scale, causal)
         dof = do.float().permute(0, 2, 1, 3)
         qf, kf, vf = (t.float().permute(0, 2, 1, 3) for t in (q, k, v))

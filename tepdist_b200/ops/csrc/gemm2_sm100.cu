@@ -157,10 +157,10 @@ __device__ __forceinline__ float gelu_grad_f(float x) {
   return 0.5f * (1.0f + t) + 0.5f * x * (1.0f - t * t) * k0 * (1.0f + 3.0f * k1 * x * x);
 }
 
-// EXT = false is the lean instantiation used for every bf16-output forward / dgrad GEMM (tile-parallel schedule, no
-// stream-K or fp32 branches in the epilogue: measured 5 % faster on the GPT-2 step than carrying them); EXT = true adds
-// the stream-K schedule, MN-major A and fp32 plain stores (weight gradients).
-template <bool A_MN, bool B_MN, bool EXT>
+// F32 = fp32 plain-store epilogue (weight gradients) instead of the bf16 epilogues; SK = stream-K schedule.  Both are
+// compile-time: carrying the stream-K / fp32 branches in the bf16 tile-parallel kernel cost 5 % of the GPT-2 step
+// (154 vs 93 registers, trip 24 / 25 A/B), so every combination that is used gets its own lean instantiation.
+template <bool A_MN, bool B_MN, bool F32, bool SK>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1)
 gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b, const Gemm2Params p) {
   extern __shared__ uint8_t smem_raw[];
@@ -209,7 +209,7 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
       int stage = 0;
       uint32_t phase = 0;
       Units un;
-      un.init(p, cluster_id, num_clusters, total_tiles, EXT);
+      un.init(p, cluster_id, num_clusters, total_tiles, SK);
       for (int s = 0; s < un.count; ++s) {
         int tile, kb0, kb1;
         un.get(s, tile, kb0, kb1);
@@ -247,7 +247,7 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
       int stage = 0, acc = 0;
       uint32_t phase = 0, acc_phase = 0;
       Units un;
-      un.init(p, cluster_id, num_clusters, total_tiles, EXT);
+      un.init(p, cluster_id, num_clusters, total_tiles, SK);
       for (int s = 0; s < un.count; ++s) {
         int tile, kb0, kb1;
         un.get(s, tile, kb0, kb1);
@@ -281,12 +281,12 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
     int acc = 0;
     uint32_t acc_phase = 0;
     Units un;
-    un.init(p, cluster_id, num_clusters, total_tiles, EXT);
+    un.init(p, cluster_id, num_clusters, total_tiles, SK);
     for (int s = 0; s < un.count; ++s) {
       int tile, kb0, kb1;
       un.get(s, tile, kb0, kb1);
       const int m_pair = tile % p.m_pairs, n_blk = tile / p.m_pairs;
-      const bool sk_part = EXT && p.stream_k > 0 && !(kb0 == 0 && kb1 == p.k_blocks);
+      const bool sk_part = SK && p.stream_k > 0 && !(kb0 == 0 && kb1 == p.k_blocks);
       const bool sk_store = sk_part && kb0 > 0;    // first unit of this pair: hand the partial tile to the finisher
       const bool sk_finish = sk_part && kb0 == 0;  // last unit of this pair: collect the partials of the pairs that follow
       const int row_in_tile = quarter * 32 + lane;
@@ -339,7 +339,7 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
               }
             }
           }
-          if (EXT && p.out_fp32) {
+          if (F32) {
             float4* dp = reinterpret_cast<float4*>(reinterpret_cast<float*>(p.D) + (long long)row * p.ldd + col0);
 #pragma unroll
             for (int q = 0; q < 8; ++q)
@@ -490,10 +490,10 @@ extern "C" int tepd_gemm2_bf16(const void* A, const void* B, void* D, void* D2, 
     clusters = (int)((iters + per - 1) / per);
   }
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
-#define LAUNCH2(AM, BMN, EX)                                                                                                    \
+#define LAUNCH2(AM, BMN, F, SKK)                                                                                                \
   {                                                                                                                             \
     static bool cfg = false;                                                                                                    \
-    auto kern = gemm2_bf16_kernel<AM, BMN, EX>;                                                                                     \
+    auto kern = gemm2_bf16_kernel<AM, BMN, F, SKK>;                                                                                     \
     if (!cfg) {                                                                                                                 \
       if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES) != cudaSuccess) return -6;        \
       cfg = true;                                                                                                               \
@@ -501,10 +501,16 @@ extern "C" int tepd_gemm2_bf16(const void* A, const void* B, void* D, void* D2, 
     cudaError_t le = tepd::launch(kern, dim3(2 * clusters), dim3(THREADS), SMEM_BYTES, s, ta, tb, p);                           \
     if (le != cudaSuccess) return (int)le;                                                                                      \
   }
-  const bool ext = p.stream_k > 0 || out_fp32;
-  if (a_mn) LAUNCH2(true, true, true)
-  else if (b_mn) { if (ext) LAUNCH2(false, true, true) else LAUNCH2(false, true, false) }
-  else { if (ext) LAUNCH2(false, false, true) else LAUNCH2(false, false, false) }
+  const bool sk = p.stream_k > 0;
+#define PICK2(AM, BMN)                                                                   \
+  {                                                                                      \
+    if (out_fp32) { if (sk) LAUNCH2(AM, BMN, true, true) else LAUNCH2(AM, BMN, true, false) }   \
+    else          { if (sk) LAUNCH2(AM, BMN, false, true) else LAUNCH2(AM, BMN, false, false) } \
+  }
+  if (a_mn) PICK2(true, true)
+  else if (b_mn) PICK2(false, true)
+  else PICK2(false, false)
+#undef PICK2
 #undef LAUNCH2
   return (int)cudaGetLastError();
 }

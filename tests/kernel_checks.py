@@ -464,6 +464,19 @@ def check_attn_fwd():
         out["o_" + tag] = _rel_err(o, o_ref)
         out["lse_" + tag] = _rel_err(lse, lse_ref)
         assert out["o_" + tag] < 2e-2 and out["lse_" + tag] < 1e-3, out
+    # 48-wide heads (GPT-MoE): zero-padded to the kernel's head dim, forward and backward
+    qkv, q, k, v = _qkv(2, 256, 4, 48)
+    o, lse = ops.attention_fwd(q, k, v, causal=True)
+    o_ref, lse_ref, _ = _ref_fwd(q, k, v, 48 ** -0.5, True)
+    out["o_d48"], out["lse_d48"] = _rel_err(o, o_ref), _rel_err(lse, lse_ref)
+    do = torch.randn_like(o)
+    dq, dk, dv = ops.attention_bwd(do, q, k, v, o, lse, causal=True)
+    qf, kf, vf = (t.float().detach().requires_grad_(True) for t in (q, k, v))
+    s = torch.einsum("bshd,bthd->bhst", qf, kf) * 48 ** -0.5
+    s = s.masked_fill(~torch.ones(256, 256, dtype=torch.bool, device="cuda").tril(), float("-inf"))
+    torch.einsum("bhst,bthd->bshd", torch.softmax(s, -1), vf).backward(do.float())
+    out["dq_d48"], out["dk_d48"], out["dv_d48"] = _rel_err(dq, qf.grad), _rel_err(dk, kf.grad), _rel_err(dv, vf.grad)
+    assert max(out["o_d48"], out["dq_d48"], out["dk_d48"], out["dv_d48"]) < 3e-2 and out["lse_d48"] < 1e-3, out
     return out
 
 
