@@ -69,7 +69,7 @@ __global__ void __launch_bounds__(256) fused_rs_adamw_ag_kernel(PeerPtrs grads, 
                                                                 float* __restrict__ mom, float* __restrict__ var, int n,
                                                                 long long begin, long long end, long long n_decay, float b1,
                                                                 float b2, float eps, float wd, const float* __restrict__ hyper,
-                                                                int comm_bf16) {
+                                                                int n_grad) {
   const float lr = hyper[0], bc1 = hyper[1], bc2 = hyper[2], gscale = hyper[3];
   const long long nvec = (end - begin) >> 2;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < nvec; i += (long long)gridDim.x * blockDim.x) {
@@ -77,7 +77,7 @@ __global__ void __launch_bounds__(256) fused_rs_adamw_ag_kernel(PeerPtrs grads, 
     float4 g = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
     for (int r = 0; r < MAX_PEERS; ++r) {
-      if (r < n) {
+      if (r < n_grad) {   // n_grad == n: reduce-scatter; n_grad == 1: the gradient is already complete on every rank
         float4 x = ld_peer_f4(reinterpret_cast<const float*>(grads.p[r]) + e);
         g.x += x.x; g.y += x.y; g.z += x.z; g.w += x.w;
       }
@@ -100,7 +100,6 @@ __global__ void __launch_bounds__(256) fused_rs_adamw_ag_kernel(PeerPtrs grads, 
     for (int r = 0; r < MAX_PEERS; ++r)
       if (r < n) *reinterpret_cast<uint2*>(reinterpret_cast<bf16*>(params.p[r]) + e) = u;  // all-gather by P2P store
   }
-  (void)comm_bf16;
 }
 
 // out[begin:end) (local fp32) = sum_r in_r[begin:end)
@@ -265,11 +264,13 @@ extern "C" int tepd_symm_barrier(void* const* flag_ptrs, int n, int rank, void* 
 }
 extern "C" int tepd_fused_rs_adamw_ag(void* const* grad_ptrs, void* const* param_ptrs, void* master, void* m, void* v, int n,
                                       long long begin, long long end, long long n_decay, float b1, float b2, float eps, float wd,
-                                      const void* hyper, int ctas, void* stream) {
+                                      const void* hyper, int ctas, void* stream, int n_grad) {
   if (n > MAX_PEERS || (begin & 3) || (end & 3)) return -2;
   if (ctas <= 0) ctas = 148 * 2;
-  fused_rs_adamw_ag_kernel<<<ctas, 256, 0, CS(stream)>>>(MakePtrs(grad_ptrs, n), MakePtrs(param_ptrs, n), (float*)master, (float*)m,
-                                                        (float*)v, n, begin, end, n_decay, b1, b2, eps, wd, (const float*)hyper, 0);
+  if (n_grad <= 0 || n_grad > n) n_grad = n;   // grad_ptrs[0 .. n_grad) are read (n_grad == 1: grad_ptrs[0] must be local)
+  fused_rs_adamw_ag_kernel<<<ctas, 256, 0, CS(stream)>>>(MakePtrs(grad_ptrs, n_grad), MakePtrs(param_ptrs, n), (float*)master,
+                                                        (float*)m, (float*)v, n, begin, end, n_decay, b1, b2, eps, wd,
+                                                        (const float*)hyper, n_grad);
   return (int)cudaGetLastError();
 }
 extern "C" int tepd_p2p_reduce_scatter(void* const* in_ptrs, void* out, int n, long long begin, long long end, int ctas, void* stream) {

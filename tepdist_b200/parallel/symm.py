@@ -26,7 +26,7 @@ def _sigs(lib):
         "tepd_symm_alloc": [ll, pp], "tepd_symm_free": [vp], "tepd_ipc_get_handle": [vp, vp], "tepd_ipc_open": [vp, pp],
         "tepd_ipc_close": [vp], "tepd_ipc_handle_size": [],
         "tepd_symm_barrier": [pp, i, i, vp, vp],
-        "tepd_fused_rs_adamw_ag": [pp, pp, vp, vp, vp, i, ll, ll, ll, f, f, f, f, vp, i, vp],
+        "tepd_fused_rs_adamw_ag": [pp, pp, vp, vp, vp, i, ll, ll, ll, f, f, f, f, vp, i, vp, i],
         "tepd_p2p_reduce_scatter": [pp, vp, i, ll, ll, i, vp],
         "tepd_p2p_all_gather": [pp, i, i, ll, ll, i, vp],
         "tepd_slot_reduce": [vp, i, ll, i, vp, vp, vp, vp, i, vp],
@@ -110,13 +110,19 @@ class FusedShardedOptimizer:
         if not self.dry:
             self._barrier()
 
-    def step(self, master, m, v, begin: int, end: int, n_decay: int, hyper, beta1, beta2, eps, wd, ctas: int = 0) -> None:
+    def step(self, master, m, v, begin: int, end: int, n_decay: int, hyper, beta1, beta2, eps, wd, ctas: int = 0,
+             local_grad: bool = False) -> None:
+        """local_grad: the gradient of [begin, end) is already complete on every rank (replicated computation): only the
+        update is sharded -- the owner reads its local gradient and still stores the new bf16 values to every peer."""
         gp, pp, n = self.g.ptr_array, self.p.ptr_array, self.world
+        n_grad = n
+        if local_grad:
+            gp, n_grad = (ctypes.c_void_p * 1)(self.g.local_ptr), 1
         if self.dry:
-            gp, pp, n = (ctypes.c_void_p * 1)(self.g.local_ptr), (ctypes.c_void_p * 1)(self.p.local_ptr), 1
+            gp, pp, n, n_grad = (ctypes.c_void_p * 1)(self.g.local_ptr), (ctypes.c_void_p * 1)(self.p.local_ptr), 1, 1
         rc = self.g.lib.tepd_fused_rs_adamw_ag(gp, pp, master.data_ptr(), m.data_ptr(), v.data_ptr(),
                                                n, begin, end, n_decay, beta1, beta2, eps, wd, hyper.data_ptr(), ctas,
-                                               torch.cuda.current_stream().cuda_stream)
+                                               torch.cuda.current_stream().cuda_stream, n_grad)
         if rc:
             raise RuntimeError(f"fused_rs_adamw_ag failed ({rc})")
         ops._count()

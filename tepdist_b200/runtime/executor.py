@@ -21,7 +21,7 @@ from typing import Any, Callable, Dict, List, Optional, Sequence, Tuple
 import torch
 
 from .. import ops
-from ..ir import SOURCE_OPS, Graph, Node, TensorType, Value
+from ..ir import COLLECTIVE_OPS, SOURCE_OPS, Graph, Node, TensorType, Value
 from ..utils.init import init_tensor
 
 # weight gradients with a single producer are written with plain stores instead of fp32 atomics into a zero-filled slot
@@ -318,6 +318,7 @@ class Executor:
         binding: Dict[Tuple[int, int], int] = {}
         regular_apply: set = set()
         irregular_params: set = set()
+        replicated: Dict[int, Tuple[int, Tuple[int, int]]] = {}   # apply node -> (param, gradient value)
         level = num = None
         for a in apply_nodes:
             nd = g.nodes[a.inputs[0].node]
@@ -343,6 +344,11 @@ class Executor:
                 root = nd.id if nd.op == "parameter" else (nd.inputs[0].node if nd.inputs else None)
                 if root is not None and g.nodes[root].op == "parameter":
                     irregular_params.add(root)
+                    # whole variable, whole slots, gradient computed redundantly on every rank (no collective in front of
+                    # the apply): the update can still be sharded -- owner updates its chunk and stores it to every peer
+                    if (nd.op == "parameter" and c.op not in COLLECTIVE_OPS and "shard_dims" not in nd.attrs
+                            and all(g.nodes[v.node].op == "state" for v in a.inputs[2:])):
+                        replicated[a.id] = (root, a.inputs[1].key())
                 continue
             binding[c.inputs[0].key()] = pid
             regular_apply.add(a.id)
@@ -366,7 +372,7 @@ class Executor:
                 if not n.op.startswith("apply_") and s_ <= regular_apply:
                     skip.add(n.id)
         return {"level": level, "num": num, "skip": skip, "binding": binding, "regular_apply": regular_apply,
-                "irregular_params": irregular_params}
+                "irregular_params": irregular_params, "replicated": replicated}
 
     def _detect_flat_zero(self) -> None:
         fz = self._fz_static
@@ -429,6 +435,17 @@ class Executor:
                 st.make_symmetric(pg)
                 self.flat_zero["fused"] = FusedShardedOptimizer(st.symm_grad, st.symm_param, pg)
                 self.flat_zero["fused"].dry = self.dry_comm
+                # replicated-gradient variables (e.g. embeddings whose backward the plan replicates): gradient lands in
+                # the flat buffer, update sharded over the ranks by the same fused kernel (local gradient, P2P stores)
+                rep = {}
+                for aid, (pid, gkey) in fz.get("replicated", {}).items():
+                    n_el = 1
+                    for d in st.shape[pid]:
+                        n_el *= d
+                    if n_el % (4 * num) == 0 and st.offset[pid] % 4 == 0 and g.nodes[aid].op == "apply_adamw":
+                        rep[aid] = (pid, st.offset[pid], n_el, bool(g.nodes[aid].attrs.get("decay", True)))
+                        self.grad_binding[gkey] = pid
+                self.flat_zero["replicated_apply"] = rep
             except RuntimeError as e:   # e.g. CUDA IPC unavailable in this container: keep the NCCL path, loudly
                 import warnings
                 warnings.warn(f"fused peer-memory optimizer unavailable ({e}); falling back to NCCL collectives")
@@ -479,8 +496,18 @@ class Executor:
         if fz["fused"] is not None:
             fo = fz["fused"]
             cs = fz.get("comm_stream")
+            rep = fz.get("replicated_apply") or {}
+            if cs is None and rep:
+                cs = fz["comm_stream"] = torch.cuda.Stream()
             if cs is not None:
+                if rep:
+                    cs.wait_stream(torch.cuda.current_stream())     # their gradients are the last thing backward produces
                 with torch.cuda.stream(cs):
+                    for aid, (pid, off, n_el, decay) in rep.items():
+                        chunk = n_el // n
+                        fo.step(st.master, st.m, st.v, off + r * chunk, off + (r + 1) * chunk, off + n_el if decay else off,
+                                self.hyper, o.get("beta1", 0.9), o.get("beta2", 0.999), o.get("eps", 1e-8),
+                                o.get("weight_decay", 0.0), ctas=0, local_grad=True)
                     fo.barrier()    # every rank's parameter shards have landed everywhere
                 torch.cuda.current_stream().wait_stream(cs)
             return
@@ -672,8 +699,9 @@ class Executor:
                 for bi in range(len(fz["buckets"])):
                     self._flat_zero_reduce(bi, pending)
             self._flat_zero_apply(pending)
+            done = fz.get("replicated_apply") or {}
             for n in self.apply_nodes:
-                if n.id not in fz["regular_apply"]:
+                if n.id not in fz["regular_apply"] and n.id not in done:
                     self._apply_one(n, env)
             for n in g.nodes:
                 if n.id in self.post_apply and not n.op.startswith("apply_") and n.id not in fz["skip"]:
