@@ -47,3 +47,23 @@ elif which == "ln":
         y, mean, rstd = ops.layernorm_fwd(x, gmm, bta)
         ops.layernorm_bwd(torch.randn_like(y), x, gmm, mean, rstd, dg, db, dres=x)
 torch.cuda.synchronize()
+if which == "gemm2_final":      # the three hot instantiations of the 2-CTA kernel as the GPT-2 step uses them
+    M, N, K = 4096, 4096, 1024
+    A = torch.randn(M, K, device="cuda", dtype=torch.bfloat16)
+    W = torch.randn(N, K, device="cuda", dtype=torch.bfloat16)
+    Wt = torch.randn(K, N, device="cuda", dtype=torch.bfloat16)
+    dY = torch.randn(M, N, device="cuda", dtype=torch.bfloat16)
+    X = torch.randn(M, K, device="cuda", dtype=torch.bfloat16)
+    acc = torch.empty(N, K, device="cuda", dtype=torch.float32)
+    for _ in range(4):
+        ops.gemm(A, W)                                                   # forward, bf16 epilogue
+        ops.gemm(A, Wt, b_mn=True)                                       # dgrad layout
+        ops.gemm(dY, X, a_mn=True, b_mn=True, out=acc, split_k=1)        # weight gradient, fp32 plain stores
+    torch.cuda.synchronize()
+elif which == "conv":
+    x = torch.randn(4, 160, 56, 56, device="cuda", dtype=torch.bfloat16)
+    w = torch.randn(320, 160, 3, 3, device="cuda", dtype=torch.bfloat16)
+    for _ in range(4):
+        y = ops.conv2d_fwd(x, w, 1, 1)
+        ops.conv2d_dgrad(y, w, x.shape, 1, 1)
+    torch.cuda.synchronize()
