@@ -464,6 +464,14 @@ def check_attn_fwd():
         out["o_" + tag] = _rel_err(o, o_ref)
         out["lse_" + tag] = _rel_err(lse, lse_ref)
         assert out["o_" + tag] < 2e-2 and out["lse_" + tag] < 1e-3, out
+    return out
+
+
+def check_attn_d48():
+    """Head dims below 64 run on the same kernels through zero padding (ops/attention.py)."""
+    from tepdist_b200 import ops
+    from tepdist_b200.ops.attention import _ref_fwd
+    out = {}
     # 48-wide heads (GPT-MoE): zero-padded to the kernel's head dim, forward and backward
     qkv, q, k, v = _qkv(2, 256, 4, 48)
     o, lse = ops.attention_fwd(q, k, v, causal=True)
@@ -539,6 +547,7 @@ CHECKS = {
     "attn_bwd": check_attn_bwd,
     "gemm_perf": check_gemm_perf,
     "conv": check_conv,
+    "attn_d48": check_attn_d48,
     "gemm2": check_gemm2,
     "attn_perf": check_attn_perf,
 }
