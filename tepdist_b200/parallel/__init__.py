@@ -183,6 +183,17 @@ def plan_and_build(graph: Graph, trainer, strategy: str, comm_mode: str, use_cud
     from ..runtime.executor import Executor
     from .. import config
     strategy = config.resolve_strategy(strategy)
+    if strategy == "explore":
+        # AutoParallel exploration mode (reference auto_parallel.cc:236-324): every device-mesh proposal (stages x
+        # micro-batches x SPMD) is planned and scored by the evaluator; the winner is then built like a configured plan
+        payload = [None]
+        if trainer.rank == 0:
+            _, xinfo, _ = plan_pipeline(graph, trainer.world, 0, 0)
+            payload[0] = json.dumps({"stages": xinfo["stages"], "micro": xinfo["micro"], "spmd": xinfo["spmd"]})
+        dist.broadcast_object_list(payload, src=0)
+        x = json.loads(payload[0])
+        trainer.plan_info["explored"] = x
+        strategy = f"pp{x['stages']}m{x['micro']}" if x["stages"] > 1 else "auto"
     if strategy.startswith("pp"):   # "pp<S>" or "pp<S>m<M>": config-mode pipeline (NUM_STAGES / NUM_MICRO_BATCHES)
         body = strategy[2:]
         S_, _, M_ = body.partition("m")

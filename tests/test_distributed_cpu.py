@@ -38,7 +38,7 @@ def _single(case):
             "gpt2b1": lambda st: dist_worker.case_gpt2(st, False, 1), "moe": dist_worker.case_moe}[name]("auto")
 
 
-@pytest.mark.parametrize("case", ["mlp:auto", "mlp:dp", "gpt2:auto", "gpt2s:auto", "gpt2:tp", "gpt2:pp2m2", "moe:ep"])
+@pytest.mark.parametrize("case", ["mlp:auto", "mlp:dp", "gpt2:auto", "gpt2s:auto", "gpt2:explore", "gpt2:tp", "gpt2:pp2m2", "moe:ep"])
 def test_spmd_world2_matches_single_process(case, tmp_path):
     ref = _single(case)
     got = _run(case, 2, tmp_path)
@@ -51,7 +51,7 @@ def test_spmd_world2_matches_single_process(case, tmp_path):
         assert got["parallelism"].startswith("pp2"), got
     if case == "gpt2:tp":
         assert got["parallelism"].startswith("tp"), got
-    if case in ("mlp:dp", "gpt2:auto"):  # (mlp:auto legitimately prefers a 128-byte activation all-reduce over gradient sync)
+    if case in ("mlp:dp", "gpt2:auto", "gpt2:explore"):  # (mlp:auto legitimately prefers a 128-byte activation all-reduce over gradient sync)
         assert got["parallelism"].startswith("dp"), got
 
 
