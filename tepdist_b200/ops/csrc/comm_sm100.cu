@@ -132,9 +132,12 @@ __global__ void __launch_bounds__(256) p2p_all_gather_kernel(PeerPtrs bufs, int 
 
 // out[i] = sum_s slots[s][i] (+ bias[col] + residual[i]); slots is THIS rank's staging buffer [n, rows, N] bf16 that the
 // peers' GEMM epilogues (gemm_sm100.cu peer mode 3) filled with plain stores.  8 elements (16 B) per thread per step.
+// `bcast`: when n_bcast > 0 the bf16 result is ALSO stored into every peer's buffer bcast.p[r] at element offset
+// bcast_off (GEMM -> ALL-reduce: each rank reduces the row block it owns and publishes it to everybody).
 __global__ void __launch_bounds__(256) slot_reduce_kernel(const bf16* __restrict__ slots, int n, long long per_slot, int N,
                                                           const float* __restrict__ bias, const bf16* __restrict__ residual,
-                                                          bf16* __restrict__ out_bf16, float* __restrict__ out_f32) {
+                                                          bf16* __restrict__ out_bf16, float* __restrict__ out_f32,
+                                                          PeerPtrs bcast, int n_bcast, long long bcast_off) {
   const long long nvec = per_slot >> 3;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < nvec; i += (long long)gridDim.x * blockDim.x) {
     float acc[8];
@@ -174,6 +177,15 @@ __global__ void __launch_bounds__(256) slot_reduce_kernel(const bf16* __restrict
 #pragma unroll
       for (int e = 0; e < 4; ++e) h[e] = __floats2bfloat162_rn(acc[2 * e], acc[2 * e + 1]);
       *reinterpret_cast<uint4*>(out_bf16 + (i << 3)) = u;
+    }
+    if (n_bcast > 0) {
+      uint4 u;
+      __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&u);
+#pragma unroll
+      for (int e = 0; e < 4; ++e) h[e] = __floats2bfloat162_rn(acc[2 * e], acc[2 * e + 1]);
+#pragma unroll
+      for (int r = 0; r < MAX_PEERS; ++r)
+        if (r < n_bcast) *reinterpret_cast<uint4*>(reinterpret_cast<bf16*>(bcast.p[r]) + bcast_off + (i << 3)) = u;
     }
     if (out_f32 != nullptr) {
       *reinterpret_cast<float4*>(out_f32 + (i << 3)) = make_float4(acc[0], acc[1], acc[2], acc[3]);
@@ -292,8 +304,20 @@ extern "C" int tepd_slot_reduce(const void* slots, int n, long long rows, int N,
                                 void* out_bf16, void* out_f32, int ctas, void* stream) {
   if (n > MAX_PEERS || (N & 7)) return -2;
   if (ctas <= 0) ctas = 148 * 4;
+  PeerPtrs none;
+  for (int i = 0; i < MAX_PEERS; ++i) none.p[i] = nullptr;
   slot_reduce_kernel<<<ctas, 256, 0, CS(stream)>>>((const bf16*)slots, n, rows * N, N, (const float*)bias, (const bf16*)residual,
-                                                  (bf16*)out_bf16, (float*)out_f32);
+                                                  (bf16*)out_bf16, (float*)out_f32, none, 0, 0);
+  return (int)cudaGetLastError();
+}
+// GEMM -> all-reduce tail: sum this rank's n slots (+ bias + residual rows) and store the bf16 rows into EVERY peer's
+// [M, N] buffer at row block `rank` (out_ptrs[r] + rank * rows * N).
+extern "C" int tepd_slot_reduce_bcast(const void* slots, int n, long long rows, int N, const void* bias, const void* residual,
+                                      void* const* out_ptrs, int rank, int ctas, void* stream) {
+  if (n > MAX_PEERS || (N & 7)) return -2;
+  if (ctas <= 0) ctas = 148 * 4;
+  slot_reduce_kernel<<<ctas, 256, 0, CS(stream)>>>((const bf16*)slots, n, rows * N, N, (const float*)bias, (const bf16*)residual,
+                                                  nullptr, nullptr, MakePtrs(out_ptrs, n), n, (long long)rank * rows * N);
   return (int)cudaGetLastError();
 }
 extern "C" int tepd_p2p_gather_chunks(void* const* shard_ptrs, void* full, int n, int rank, long long chunk_bytes, void* flags,

@@ -31,6 +31,7 @@ def _sigs(lib):
         "tepd_p2p_all_gather": [pp, i, i, ll, ll, i, vp],
         "tepd_slot_reduce": [vp, i, ll, i, vp, vp, vp, vp, i, vp],
         "tepd_p2p_gather_chunks": [pp, vp, i, i, ll, vp, vp, vp, i, vp],
+        "tepd_slot_reduce_bcast": [vp, i, ll, i, vp, vp, pp, i, i, vp],
     }
     for k, a in table.items():
         fn = getattr(lib, k)
@@ -216,6 +217,59 @@ class GemmReduceScatter:
             raise RuntimeError(f"slot_reduce failed ({rc})")
         ops._count()
         return out
+
+
+class GemmAllReduce:
+    """Row-parallel linear + ALL-reduce in two kernels and two flag barriers, no NCCL: the GEMM epilogue pushes every bf16
+    partial row block into the owner's slot (peer mode 3), the owner sums its slots together with bias + residual and
+    stores the finished rows into EVERY rank's output buffer (slot_reduce with broadcast).  The transfer of partials
+    overlaps the GEMM tile by tile; what is left after the GEMM is one pass over M/n rows.  Replaces the reference's
+    dot -> in-stream ncclAllReduce pair of tensor-parallel plans (dapple_all_reduce_thunk.cc:136-159).
+    One instance serves every call site of a given [M, N] (slot buffers alternate; each call site owns its symmetric
+    output buffer, allocate with `new_output()`)."""
+
+    def __init__(self, M: int, N: int, group=None, barrier: Optional[SymmBarrier] = None):
+        self.M, self.N, self.group = M, N, group
+        self.world = dist.get_world_size(group)
+        self.rank = dist.get_rank(group)
+        assert M % self.world == 0
+        self.rows = M // self.world
+        self.slots = [SymmetricBuffer(self.world * self.rows * N * 2, group) for _ in range(2)]
+        self.barrier = barrier or SymmBarrier(group)
+        self.turn = 0
+
+    def new_output(self) -> SymmetricBuffer:
+        return SymmetricBuffer(self.M * self.N * 2, self.group)
+
+    def __call__(self, x: torch.Tensor, w: torch.Tensor, out: SymmetricBuffer, bias: Optional[torch.Tensor] = None,
+                 residual: Optional[torch.Tensor] = None, b_mn: bool = False, block_n: int = 0) -> torch.Tensor:
+        """x [M, K_local] bf16, w [N, K_local] (or [K_local, N] with b_mn); bias fp32 [N]; residual bf16 [M, N] (replicated:
+        only this rank's row block is read).  Returns the [M, N] view of `out` (valid after the second barrier, which is
+        enqueued here)."""
+        buf = self.slots[self.turn]
+        self.turn ^= 1
+        lib = buf.lib
+        _peer_sig(lib)
+        M, K = x.shape
+        s = torch.cuda.current_stream().cuda_stream
+        rc = lib.tepd_gemm_bf16_peer(3, (ctypes.c_void_p * self.world)(*([x.data_ptr()] * self.world)), w.data_ptr(), None,
+                                     buf.ptr_array, None, M, self.N, K, x.stride(0), w.stride(0), self.N, int(b_mn), 0,
+                                     self.world, self.rank, block_n, ops._sms(), s, None, None)
+        if rc:
+            raise RuntimeError(f"gemm_all_reduce: GEMM failed ({rc})")
+        ops._count()
+        self.barrier()          # every peer's partial rows for my block have landed in my slots
+        res_ptr = None
+        if residual is not None:
+            assert residual.is_contiguous() and residual.dtype == torch.bfloat16
+            res_ptr = residual.data_ptr() + self.rank * self.rows * self.N * 2
+        rc = lib.tepd_slot_reduce_bcast(buf.local_ptr, self.world, self.rows, self.N, None if bias is None else bias.data_ptr(),
+                                        res_ptr, out.ptr_array, self.rank, 0, s)
+        if rc:
+            raise RuntimeError(f"gemm_all_reduce: slot_reduce failed ({rc})")
+        ops._count()
+        self.barrier()          # every rank's row block is in everybody's output
+        return out.tensor(torch.bfloat16, self.M * self.N).view(self.M, self.N)
 
 
 class AllGatherGemm:

@@ -24,6 +24,9 @@ from .. import ops
 from ..ir import COLLECTIVE_OPS, SOURCE_OPS, Graph, Node, TensorType, Value
 from ..utils.init import init_tensor
 
+# tensor-parallel plans: run `linear -> all_reduce [-> + bias] [-> + residual]` as GEMM -> all-reduce over peer memory
+# (parallel/symm.py GemmAllReduce) instead of cuBLAS-free GEMM + NCCL.  Opt-in until validated on multi-GPU hardware.
+TP_FUSED = os.environ.get("TEPDIST_TP_FUSED", "0") == "1"
 # weight gradients with a single producer are written with plain stores instead of fp32 atomics into a zero-filled slot
 WGRAD_PLAIN_STORE = os.environ.get("TEPDIST_WGRAD_STORE", "1") == "1"
 
@@ -301,6 +304,9 @@ class Executor:
         self.input_names = [n.name for n in g.inputs()]
         self.grad_accumulate = False   # True when gradients add up over micro-batches (pipeline stage workers)
         self._plan_store_init()
+        self.tp_fuse: Dict[int, Dict[str, Any]] = {}
+        if TP_FUSED and self.comm_mode == "fused" and self.collective is not None and device.type == "cuda":
+            self._plan_tp_fusion()
 
     @staticmethod
     def _analyze_flat_zero(g: Graph) -> Optional[Dict[str, Any]]:
@@ -780,6 +786,87 @@ class Executor:
         elif kind == "sgd":
             ops.sgd_step(st.master, st.grad, st.compute, o.get("lr", 1e-2))
 
+    @staticmethod
+    def find_tp_chains(g: Graph, skip: Optional[set] = None) -> Dict[int, Dict[str, Any]]:
+        """LIN (linear / linear_dgrad, no fused epilogue) -> all_reduce(sum) [-> add(bias [N])] [-> add(residual)] chains in
+        which every link has exactly one user: {LIN id: {ar, M, N, level, num, bias key, res key, chain node ids}}."""
+        users = g.users()
+        skip = skip or set()
+
+        def sole_user(nid: int):
+            us = users.get((nid, 0), [])
+            return g.nodes[us[0][0]] if len(us) == 1 else None
+
+        found: Dict[int, Dict[str, Any]] = {}
+        for ar in g.nodes:
+            if ar.op != "all_reduce" or int(ar.attrs.get("reduce", 0)) != 0:
+                continue
+            lin = g.nodes[ar.inputs[0].node]
+            if lin.op not in ("linear", "linear_dgrad") or len(lin.inputs) != 2 or sole_user(lin.id) is not ar or lin.id in skip:
+                continue
+            num, lvl = int(ar.attrs["num"]), int(ar.attrs["level"])
+            shp = tuple(lin.outputs[0].shape)
+            N = shp[-1]
+            M = 1
+            for d in shp[:-1]:
+                M *= d
+            if num < 2 or num > 8 or lin.outputs[0].dtype != "bf16" or N % 8 or M % (128 * num):
+                continue
+            info: Dict[str, Any] = {"ar": ar.id, "M": M, "N": N, "level": lvl, "num": num, "bias": None, "res": None,
+                                    "chain": [ar.id]}
+            nxt = sole_user(ar.id)
+            if nxt is not None and nxt.op == "add" and len(nxt.inputs) == 2:
+                other = nxt.inputs[1] if nxt.inputs[0].node == ar.id else nxt.inputs[0]
+                if tuple(g.type_of(other).shape) == (N,):
+                    info["bias"] = other.key()
+                    info["chain"].append(nxt.id)
+                    nn = sole_user(nxt.id)
+                    if nn is not None and nn.op == "add" and len(nn.inputs) == 2:
+                        o2 = nn.inputs[1] if nn.inputs[0].node == nxt.id else nn.inputs[0]
+                        if tuple(g.type_of(o2).shape) == shp and g.type_of(o2).dtype == "bf16":
+                            info["res"] = o2.key()
+                            info["chain"].append(nn.id)
+            found[lin.id] = info
+        return found
+
+    def _plan_tp_fusion(self) -> None:
+        """Execute every chain found by find_tp_chains as ONE GemmAllReduce call at LIN; the downstream nodes of the chain
+        alias its result."""
+        if self.dry_comm:
+            return
+        mesh = self.collective.mesh
+        self.tp_fuse = self.find_tp_chains(self.g, set(self.gelu_dual) | set(self.gelu_bwd_fuse) | set(self.alias_of))
+        if not self.tp_fuse:
+            return
+        from ..parallel.symm import GemmAllReduce, SymmBarrier
+        self._tp_ops: Dict[Tuple[int, int, int], Any] = {}
+        bar: Dict[int, Any] = {}
+        for lid, info in self.tp_fuse.items():
+            key = (info["level"], info["M"], info["N"])
+            if key not in self._tp_ops:
+                pg = mesh.group(info["level"])
+                if info["level"] not in bar:
+                    bar[info["level"]] = SymmBarrier(pg)
+                self._tp_ops[key] = GemmAllReduce(info["M"], info["N"], pg, bar[info["level"]])
+            info["op"] = self._tp_ops[key]
+            info["out"] = info["op"].new_output()        # symmetric [M, N] bf16, written by every rank
+            for nid in info["chain"]:
+                self.alias_of[nid] = (lid, 0)
+
+    def _run_tp_fused(self, n: Node, ins: List[torch.Tensor]) -> List[torch.Tensor]:
+        info = self.tp_fuse[n.id]
+        x, w = ins
+        x2 = x.reshape(-1, x.shape[-1])
+        bias = res = None
+        if info["bias"] is not None:
+            bias = self._env[info["bias"]]
+            if bias.dtype != torch.float32:
+                bias = bias.float()
+        if info["res"] is not None:
+            res = self._env[info["res"]].reshape(info["M"], info["N"]).contiguous()
+        y = info["op"](x2.contiguous(), w, info["out"], bias=bias, residual=res, b_mn=(n.op == "linear_dgrad"))
+        return [y.view(tuple(n.outputs[0].shape))]
+
     def _plan_store_init(self) -> None:
         """Gradient slots whose only writer is a weight-gradient GEMM can be written with plain stores (beta = 0) and need
         no zero-fill; everything else (bias / LayerNorm / embedding gradients: accumulating kernels) is zero-filled as
@@ -885,6 +972,8 @@ class Executor:
                 dres = self._env.get(self.ln_fuse[n.id])
             dx = ops.layernorm_bwd(ins[0], ins[1], ins[2], mean, rstd, dg, db, dres)
             return [dx, dg, db]
+        if op in ("linear", "linear_dgrad") and n.id in self.tp_fuse:
+            return self._run_tp_fused(n, ins)
         if op == "linear":
             x, w = ins[0], ins[1]
             k = 2

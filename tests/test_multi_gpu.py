@@ -46,3 +46,17 @@ def test_fused_moe_expert_parallel_fp8(tmp_path):
     assert pr.returncode == 0, pr.stderr[-3000:]
     r = json.load(open(out))
     assert r["relerr"] < 6e-2, r          # e4m3 activations x e4m3 weights
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2 or os.environ.get("TEPDIST_TEST_EXPERIMENTAL") != "1",
+                    reason="needs 2 GPUs; opt-in (TEPDIST_TEST_EXPERIMENTAL=1) until the fused TP path is validated on hardware")
+def test_tp_plan_fused_all_reduce_matches_nccl(tmp_path):
+    out = str(tmp_path / "tpplan.json")
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
+           "--master-port", "29744", os.path.join(HERE, "tp_plan_worker.py"), out]
+    pr = subprocess.run(cmd, capture_output=True, text=True, timeout=300)
+    assert pr.returncode == 0, pr.stderr[-3000:]
+    r = json.load(open(out))
+    assert r["fused_chains"] > 0 and r["nccl_chains"] == 0, r
+    for a, b, c in zip(r["fused"], r["nccl"], r["single"]):
+        assert abs(a - b) < 2e-2 * abs(b) and abs(a - c) < 2e-2 * abs(c), r

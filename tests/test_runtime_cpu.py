@@ -188,3 +188,23 @@ def test_profile_and_plan_artifact_dumps(tmp_path):
     for f in ("strategies.txt", "plan.json", "step_graph.dot"):
         assert os.path.getsize(os.path.join(d, f)) > 0
     assert "all_reduce" in open(os.path.join(d, "step_graph.dot")).read() or "reduce_scatter" in open(os.path.join(d, "step_graph.dot")).read()
+
+
+def test_tp_all_reduce_chains_are_found_for_fusion():
+    """Megatron plan of GPT-2: every row-parallel projection is linear -> all_reduce -> +bias -> +residual, every
+    column-parallel input gradient is linear_dgrad -> all_reduce; these are the chains the fused GEMM -> all-reduce path
+    (parallel/symm.py GemmAllReduce, TEPDIST_TP_FUSED=1) takes over."""
+    from tepdist_b200.models.gpt2 import CONFIGS, build_gpt2_graph
+    from tepdist_b200.parallel import plan_spmd
+    from tepdist_b200.runtime.executor import Executor
+    cfg = CONFIGS["tiny"]
+    sharded, info = plan_spmd(build_gpt2_graph(cfg, batch=4), 2, "tp")
+    chains = Executor.find_tp_chains(sharded)
+    fwd = [c for lid, c in chains.items() if sharded.nodes[lid].op == "linear"]
+    bwd = [c for lid, c in chains.items() if sharded.nodes[lid].op == "linear_dgrad"]
+    assert len(fwd) == 2 * cfg.n_layer, (len(fwd), info["collectives"])
+    assert all(c["bias"] is not None and c["res"] is not None and len(c["chain"]) == 3 for c in fwd)
+    assert len(bwd) >= 2 * cfg.n_layer and all(c["M"] == 4 * cfg.n_ctx and c["num"] == 2 for c in bwd)
+    # a data-parallel plan has nothing to fuse
+    dp, _ = plan_spmd(build_gpt2_graph(cfg, batch=4), 2, "auto")
+    assert Executor.find_tp_chains(dp) == {}
