@@ -155,6 +155,44 @@ def trace(module: nn.Module, example_inputs: Dict[str, torch.Tensor], loss: str 
                 env[node.name] = b.transpose(a[0], list(perm))
             elif t in ("contiguous", "float", "to"):
                 env[node.name] = a[0]
+            elif t is F.scaled_dot_product_attention:
+                # q, k, v: [B, H, S, D] -> the fused attention op (one tcgen05 flash-attention kernel on the GPU) on the
+                # heads-major packed layout [B, S, H, 3, D]
+                if node.kwargs.get("attn_mask") is not None or node.kwargs.get("dropout_p", 0.0):
+                    raise NotImplementedError("scaled_dot_product_attention: attn_mask / dropout are not supported")
+                q, k, v = a[0], a[1], a[2]
+                B_, H_, S_, D_ = b.t(q).shape
+                pk = [b.reshape(b.transpose(x_, [0, 2, 1, 3]), (B_, S_, H_, 1, D_)) for x_ in (q, k, v)]
+                qkv = b.reshape(b.concat(pk, 3), (B_, S_, 3 * H_ * D_))
+                o = b.attention(qkv, heads=H_, causal=bool(node.kwargs.get("is_causal", False)), name=node.name)
+                env[node.name] = b.transpose(b.reshape(o, (B_, S_, H_, D_)), [0, 2, 1, 3])
+            elif t in ("chunk", torch.chunk, "split", torch.split):
+                src = a[0]
+                shp = b.t(src).shape
+                dim = node.kwargs.get("dim", a[2] if len(a) > 2 else (0 if t in ("split", torch.split) else 0))
+                dim = dim % len(shp)
+                if t in ("chunk", torch.chunk):
+                    n_ = int(a[1])
+                    sizes = [shp[dim] // n_] * n_
+                else:
+                    sz = a[1]
+                    sizes = list(sz) if isinstance(sz, (list, tuple)) else [int(sz)] * (shp[dim] // int(sz))
+                parts, off = [], 0
+                for sz_ in sizes:
+                    st_ = [0] * len(shp)
+                    li_ = list(shp)
+                    st_[dim], li_[dim] = off, off + sz_
+                    parts.append(b.slice(src, st_, li_))
+                    off += sz_
+                env[node.name] = tuple(parts)
+            elif t is operator.getitem:
+                if isinstance(a[0], tuple):
+                    env[node.name] = a[0][a[1]]
+                else:
+                    raise NotImplementedError("getitem on a tensor")
+            elif t in ("size",):
+                shp = b.t(a[0]).shape
+                env[node.name] = shp if len(a) == 1 else shp[a[1]]
             else:
                 raise NotImplementedError(f"function {t}")
         elif node.op == "output":

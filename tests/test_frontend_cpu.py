@@ -90,3 +90,46 @@ def test_fx_trace_matches_eager_torch_training():
         (l,) = ex.step({"x": x, "t": y})
         assert abs(float(l) - float(ref)) < 1e-5
     assert torch.allclose(ex.store.state_dict()["fc1/weight"], net.fc1.weight.detach(), atol=1e-5)
+
+
+def test_fx_trace_transformer_block_with_sdpa():
+    """A torch transformer block written with F.scaled_dot_product_attention traces onto the fused attention op and
+    trains like eager PyTorch (chunk / getitem / view / transpose plumbing included)."""
+    import torch.nn as nn
+    import torch.nn.functional as F
+    from tepdist_b200.frontend.trace import trace
+
+    class Block(nn.Module):
+        def __init__(self, C=32, H=2, V=50):
+            super().__init__()
+            self.H = H
+            self.emb = nn.Embedding(V, C)
+            self.ln1, self.ln2 = nn.LayerNorm(C), nn.LayerNorm(C)
+            self.qkv, self.proj = nn.Linear(C, 3 * C), nn.Linear(C, C)
+            self.fc, self.out = nn.Linear(C, 4 * C), nn.Linear(4 * C, C)
+            self.head = nn.Linear(C, V, bias=False)
+
+        def forward(self, tokens):
+            x = self.emb(tokens)
+            B, S, C = 2, 16, 32
+            q, k, v = self.qkv(self.ln1(x)).chunk(3, dim=-1)
+            q, k, v = (t.view(B, S, self.H, C // self.H).transpose(1, 2) for t in (q, k, v))
+            a = F.scaled_dot_product_attention(q, k, v, is_causal=True).transpose(1, 2).reshape(B, S, C)
+            x = x + self.proj(a)
+            x = x + self.out(F.gelu(self.fc(self.ln2(x)), approximate="tanh"))
+            return self.head(x)
+
+    torch.manual_seed(0)
+    net = Block()
+    tok = torch.randint(0, 50, (2, 16))
+    lab = torch.randint(0, 50, (2, 16))
+    tr = trace(net, {"tokens": tok}, loss="cross_entropy", label_example=lab.int(), optimizer="sgd", lr=0.1)
+    assert any(n.op == "attention" for n in tr.graph.nodes)
+    ex = Executor(tr.graph, torch.device("cpu"))
+    tr.load_state_dict_into(ex, net.state_dict())
+    opt = torch.optim.SGD(net.parameters(), lr=0.1)
+    for _ in range(3):
+        ref = F.cross_entropy(net(tok).view(-1, 50), lab.view(-1))
+        opt.zero_grad(); ref.backward(); opt.step()
+        (l,) = ex.step({"tokens": tok.int(), "labels": lab.int()})
+        assert abs(float(l) - float(ref)) < 2e-4, (float(l), float(ref))
