@@ -61,6 +61,51 @@ def plan_spmd(graph: Graph, num: int, strategy: str = "auto", options: Optional[
     return out, info
 
 
+def plan_spmd_mesh(graph: Graph, nums, kinds):
+    """Multi-dimensional SPMD mesh (reference: one split ordinal per mesh dimension, dist_spec.h:130-227): plan and transform
+    level 0 over nums[0] devices, then level 1 over nums[1] devices on the already sharded graph, ...  `kinds[i]` is
+    "dp" (cost-based, memory unconstrained: batch split wins), "tp" (weights forced sharded) or "auto".
+    Returns (sharded ir.Graph, info)."""
+    from .. import _C, config
+    from ..planner import from_native, merge_client_attrs, to_native
+    cg = to_native(graph)
+    cg.split_nums = [int(n) for n in nums]
+    cg.share_dev = [False] * len(nums)
+    colls: Dict[str, int] = {}
+    comm = 0.0
+    secs = 0.0
+    for lvl, (num, kind) in enumerate(zip(nums, kinds)):
+        o = _C.SpmdOptions()
+        o.num = int(num)
+        for k, v in config.spmd_overrides().items():
+            if hasattr(o, k):
+                setattr(o, k, v)
+        if kind == "tp":
+            o.var_mem_limit = 1.0
+        plan = _C.plan_spmd_level(cg, o)
+        cg, _ = _C.spmd_transform(cg, plan, lvl, int(num))
+        for k, v in dict(plan.stats.collectives).items():
+            colls[k] = colls.get(k, 0) + int(v)
+        comm += plan.stats.comm_bytes
+        secs += plan.stats.solve_seconds
+    out = from_native(cg)
+    merge_client_attrs(out, graph)
+    info = {"collectives": colls, "comm_bytes": comm, "solve_seconds": secs, "mesh": [int(n) for n in nums], "kinds": list(kinds)}
+    return out, info
+
+
+def _parse_mesh_strategy(strategy: str):
+    """"dp4tp2" / "tp2dp4" / "dp2tp2dp2" -> ([4, 2], ["dp", "tp"]) ; None when `strategy` is not a mesh spec."""
+    import re
+    parts = re.findall(r"(dp|tp|auto)(\d+)", strategy)
+    if len(parts) < 2 or "".join(k + n for k, n in parts) != strategy:
+        return None
+    # tensor-parallel levels are planned first: the data-parallel level (with its ZeRO-style optimizer sharding) then acts
+    # on the already tensor-sharded variables, which is the nesting the executor's in-place sharded update understands
+    parts.sort(key=lambda kn: 0 if kn[0] == "tp" else 1)
+    return [int(n) for _, n in parts], [k for k, _ in parts]
+
+
 def classify_parallelism(info: Dict[str, Any], num: int) -> str:
     t = info.get("dot_strategies", {})
     if not t:
@@ -203,6 +248,32 @@ def plan_and_build(graph: Graph, trainer, strategy: str, comm_mode: str, use_cud
     from .collectives import CollectiveRunner
     from .mesh import DeviceMesh
     world, rank = trainer.world, trainer.rank
+    mesh_spec = _parse_mesh_strategy(strategy)
+    if mesh_spec is not None:      # multi-dimensional SPMD mesh, e.g. "dp4tp2": data parallel over 4 x tensor parallel over 2
+        nums, kinds = mesh_spec
+        total = 1
+        for n_ in nums:
+            total *= n_
+        assert total == world, f"strategy {strategy} needs {total} devices, world is {world}"
+        payload = [None]
+        if rank == 0:
+            sharded, info = plan_spmd_mesh(graph, nums, kinds)
+            from ..utils import trace
+            trace.log_plan(info, strategy)
+            if trace.debug_enabled():
+                trace.dump_plan_artifacts(sharded, info)
+            payload[0] = json.dumps({"graph": sharded.to_dict(), "info": info})
+        dist.broadcast_object_list(payload, src=0)
+        d = json.loads(payload[0])
+        sharded = Graph.from_dict(d["graph"])
+        trainer.plan_info.update(d["info"])
+        trainer.plan_info["parallelism"] = "x".join(f"{k}{n}" for k, n in zip(kinds, nums))
+        mesh = DeviceMesh(nums, [False] * len(nums), rank=rank, world=world)
+        mesh.build_process_groups()
+        trainer.mesh = mesh
+        runner = CollectiveRunner(mesh, comm_dtype=config.comm_dtype())
+        return Executor(sharded, trainer.device, seed=seed, use_cuda_graph=use_cuda_graph, collective=runner,
+                        coords=mesh.coords(), comm_mode=comm_mode)
     payload = [None]
     if rank == 0:
         sharded, info = plan_spmd(graph, world, strategy)

@@ -743,7 +743,7 @@ class Executor:
             if src.op in ("parameter", "state"):
                 return base(src)
             assert src.op == "dynamic_slice", src.op
-            b = base(g.nodes[src.inputs[0].node])
+            b = storage(src.inputs[0], which)       # (nested: one dynamic_slice per mesh level that shards the variable)
             d, num = int(src.attrs["dim"]), int(src.attrs["num"])
             sz = b.shape[d] // num
             return b.narrow(d, self.coords.get(int(src.attrs["level"]), 0) * sz, sz)

@@ -81,3 +81,13 @@ def test_dry_comm_timing_mode_runs(tmp_path):
     for case in ("gpt2:auto", "gpt2:tp"):
         got = _run(case, 2, tmp_path, {"TEPDIST_DRY_COMM": "1"})
         assert len(got["losses"]) == 4 and all(l == l for l in got["losses"]), got
+
+
+def test_two_dimensional_spmd_mesh_world4(tmp_path):
+    """dp2 x tp2 on 4 processes (one split ordinal per mesh dimension) == single process."""
+    ref = _single("gpt2:auto")
+    got = _run("gpt2:dp2tp2", 4, tmp_path)
+    assert got["parallelism"] == "tp2xdp2", got          # (tensor-parallel level is planned first)
+    assert got["collectives"].get("all_reduce", 0) > 0 and got["collectives"].get("reduce_scatter", 0) > 0, got
+    for a, b in zip(got["losses"], ref["losses"]):
+        assert abs(a - b) <= 2e-4 * max(1.0, abs(b)), (got, ref)
