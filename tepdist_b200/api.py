@@ -89,3 +89,19 @@ class Trainer:
 
     def state_dict(self):
         return self.exec.store.state_dict()
+
+    # ------------------------------------------------------------------ sharded checkpoints (reference DoRemoteSave / Restore)
+    def _ckpt(self, root: str, max_to_keep: int = 5):
+        from .ckpt import CheckpointManager
+        key = (os.path.abspath(root), max_to_keep)
+        if getattr(self, "_ckpt_mgr", None) is None or self._ckpt_key != key:
+            self._ckpt_mgr, self._ckpt_key = CheckpointManager(root, self.rank, self.world, max_to_keep), key
+        return self._ckpt_mgr
+
+    def save(self, root: str, global_step: int, max_to_keep: int = 5) -> str:
+        """Every rank writes its own shards (master weights + optimizer moments) under root/ckpt_<rank>_of_<world>/."""
+        return self._ckpt(root, max_to_keep).save(self.exec, global_step)
+
+    def restore(self, root: str, global_step: Optional[int] = None) -> int:
+        """Load this rank's shards of `global_step` (default: the latest kept step); returns the restored step."""
+        return self._ckpt(root).restore(self.exec, global_step)

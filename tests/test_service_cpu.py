@@ -124,3 +124,29 @@ def test_service_env_flags_drive_planner(monkeypatch, tmp_path):
     assert config.resolve_strategy("auto") == "rule"
     monkeypatch.delenv("CONFIG_FILE"); monkeypatch.delenv("NUM_STAGES"); monkeypatch.delenv("RULE_MODE")
     config.env(reload=True)
+
+
+def test_trainer_save_restore_resumes_identically(tmp_path):
+    """Trainer.save / restore: resuming from a checkpoint reproduces the loss trajectory (weights + AdamW moments + step)."""
+    import torch
+    from tepdist_b200.api import Trainer
+    from tepdist_b200.models.gpt2 import CONFIGS, build_gpt2_graph
+    cfg = CONFIGS["tiny"]
+    g = build_gpt2_graph(cfg, batch=2)
+    torch.manual_seed(0)
+    tok = torch.randint(0, cfg.n_vocab, (2, cfg.n_ctx), dtype=torch.int32)
+    feeds = {"tokens": tok, "labels": torch.roll(tok, -1, 1)}
+    tr = Trainer(g, device=torch.device("cpu"), use_cuda_graph=False)
+    for _ in range(2):
+        tr.step(feeds)
+    tr.save(str(tmp_path), global_step=2, max_to_keep=2)
+    after = [tr.step(feeds) for _ in range(3)]
+    tr2 = Trainer(g, device=torch.device("cpu"), use_cuda_graph=False, seed=123)     # different init: everything must come from disk
+    assert tr2.restore(str(tmp_path)) == 2
+    resumed = [tr2.step(feeds) for _ in range(3)]
+    for a, b in zip(after, resumed):
+        assert abs(a - b) < 1e-5 * max(1.0, abs(a)), (after, resumed)
+    for s in (3, 4, 5):
+        tr.save(str(tmp_path), global_step=s, max_to_keep=2)
+    kept = sorted(os.listdir(os.path.join(str(tmp_path), "ckpt_0_of_1")))
+    assert [k for k in kept if k.startswith("step_")] == ["step_4", "step_5"], kept
