@@ -78,19 +78,91 @@ class CheckpointManager:
     def restore(self, executor, global_step: Optional[int] = None) -> int:
         step = self.latest() if global_step is None else global_step
         if step is None:
+            step = self._latest_any_layout()
+        if step is None:
             raise FileNotFoundError("no checkpoint to restore")
         prefix = os.path.join(self.dir, f"step_{step}")
-        manifest = json.load(open(os.path.join(prefix, "manifest.json")))
-        tensors = torch.load(os.path.join(prefix, "shards.pt"))
         st = executor.store
+        same_layout = os.path.exists(os.path.join(prefix, "manifest.json"))
+        if same_layout:
+            manifest = json.load(open(os.path.join(prefix, "manifest.json")))
+            same_layout = all(tuple(manifest["vars"].get(st.names[pid], {}).get("shard_shape", ())) == tuple(st.shape[pid])
+                              and manifest["vars"][st.names[pid]].get("coords") == {str(k): v for k, v in executor.coords.items()}
+                              for pid in st.order)
+        if not same_layout:
+            return self._restore_resharded(executor, step)
+        tensors = torch.load(os.path.join(prefix, "shards.pt"))
         for pid in st.order:
             name = st.names[pid]
-            meta = manifest["vars"][name]
-            assert tuple(meta["shard_shape"]) == tuple(st.shape[pid]), f"{name}: checkpoint shard shape differs from the current plan"
             st.master_view(pid).copy_(tensors[name].reshape(st.shape[pid]).to(st.device))
             if st.m is not None and name + "/m" in tensors:
                 st._view(st.m, pid).copy_(tensors[name + "/m"].reshape(st.shape[pid]).to(st.device))
                 st._view(st.v, pid).copy_(tensors[name + "/v"].reshape(st.shape[pid]).to(st.device))
         st.sync_compute()
         executor.step_count = int(manifest.get("step_count", step))
+        return step
+
+    # ------------------------------------------------------------------ restore into a DIFFERENT plan / world size
+    def _all_rank_dirs(self) -> List[str]:
+        root = os.path.dirname(self.dir)
+        return sorted(os.path.join(root, d) for d in os.listdir(root) if d.startswith("ckpt_") and "_of_" in d)
+
+    def _latest_any_layout(self) -> Optional[int]:
+        best = None
+        for d in self._all_rank_dirs():
+            qf = os.path.join(d, "checkpoint_queue.json")
+            if os.path.exists(qf):
+                q = json.load(open(qf))
+                if q:
+                    best = q[-1] if best is None else max(best, q[-1])
+        return best
+
+    def _restore_resharded(self, executor, step: int) -> int:
+        """The checkpoint was written by a different plan (other world size / sharding): rebuild every variable from the
+        shards of ALL writer ranks (each shard is placed by its recorded shard_dims / nums / levels / coords), then cut out
+        what THIS rank's plan stores.  Needs the writers' directories on a shared filesystem (one box: always true)."""
+        writers = []
+        for d in self._all_rank_dirs():
+            pf = os.path.join(d, f"step_{step}")
+            if os.path.exists(os.path.join(pf, "manifest.json")):
+                writers.append((json.load(open(os.path.join(pf, "manifest.json"))), torch.load(os.path.join(pf, "shards.pt"))))
+        if not writers:
+            raise FileNotFoundError(f"no shards of step {step} under {os.path.dirname(self.dir)}")
+        world_w = writers[0][0]["world"]
+        writers = [w for w in writers if w[0]["world"] == world_w]
+        if len(writers) != world_w:
+            raise FileNotFoundError(f"step {step}: found {len(writers)} of {world_w} writer shards")
+        st, g = executor.store, executor.g
+
+        def assemble(name: str, suffix: str) -> Optional[torch.Tensor]:
+            full = None
+            for man, tens in writers:
+                meta = man["vars"].get(name)
+                if meta is None or name + suffix not in tens:
+                    return None
+                if full is None:
+                    full = torch.zeros(meta["full_shape"], dtype=torch.float32)
+                view = full
+                for d_, n_, l_ in zip(meta["shard_dims"], meta["shard_nums"], meta["shard_levels"]):
+                    sz = view.shape[d_] // n_
+                    view = view.narrow(d_, int(meta["coords"].get(str(l_), 0)) * sz, sz)
+                view.copy_(tens[name + suffix].reshape(meta["shard_shape"]))
+            return full
+
+        from ..runtime.executor import shard_of
+        for pid in st.order:
+            name = st.names[pid]
+            attrs = g.nodes[pid].attrs
+            for suffix, dst in (("", st.master_view(pid)), ("/m", None if st.m is None else st._view(st.m, pid)),
+                                ("/v", None if st.v is None else st._view(st.v, pid))):
+                if dst is None:
+                    continue
+                full = assemble(name, suffix)
+                if full is None:
+                    if suffix == "":
+                        raise KeyError(f"variable {name} missing from checkpoint step {step}")
+                    continue
+                dst.copy_(shard_of(full, attrs, executor.coords).reshape(dst.shape).to(st.device))
+        st.sync_compute()
+        executor.step_count = int(writers[0][0].get("step_count", step))
         return step

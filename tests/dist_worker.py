@@ -27,6 +27,22 @@ def case_gpt2(strategy, feed_shards=False, batch=4):
     return {"losses": losses, "parallelism": tr.plan_info.get("parallelism"), "collectives": tr.plan_info.get("collectives")}
 
 
+def case_ckpt(strategy):
+    """Train 2 steps under `strategy`, save a sharded checkpoint into $TEPDIST_TEST_CKPT, train 2 more steps."""
+    from tepdist_b200.api import Trainer
+    from tepdist_b200.models.gpt2 import CONFIGS, build_gpt2_graph
+    cfg = CONFIGS["tiny"]
+    g = build_gpt2_graph(cfg, batch=4)
+    tr = Trainer(g, strategy=strategy, device=torch.device("cpu"), use_cuda_graph=False)
+    torch.manual_seed(0)
+    tok = torch.randint(0, cfg.n_vocab, (4, cfg.n_ctx), dtype=torch.int32)
+    feeds = {"tokens": tok, "labels": torch.roll(tok, -1, 1)}
+    before = [tr.step(feeds) for _ in range(2)]
+    tr.save(os.environ["TEPDIST_TEST_CKPT"], global_step=2)
+    after = [tr.step(feeds) for _ in range(2)]
+    return {"losses": before + after, "parallelism": tr.plan_info.get("parallelism"), "collectives": tr.plan_info.get("collectives")}
+
+
 def case_mlp(strategy):
     """examples/smoke_testing-style 2-layer MLP; planner emits a DP shard on CPU/gloo world_size=2 (BASELINE config 1)."""
     from tepdist_b200.api import Trainer
@@ -56,7 +72,7 @@ def case_moe(strategy):
 if __name__ == "__main__":
     case, out = sys.argv[1], sys.argv[2]
     name, _, strat = case.partition(":")
-    res = {"gpt2": case_gpt2, "gpt2s": lambda st: case_gpt2(st, True), "gpt2b1": lambda st: case_gpt2(st, False, 1), "mlp": case_mlp, "moe": case_moe}[name](strat or "auto")
+    res = {"gpt2": case_gpt2, "gpt2s": lambda st: case_gpt2(st, True), "gpt2b1": lambda st: case_gpt2(st, False, 1), "mlp": case_mlp, "moe": case_moe, "ckpt": case_ckpt}[name](strat or "auto")
     if int(os.environ.get("RANK", "0")) == 0:
         json.dump(res, open(out, "w"))
     if dist.is_initialized():

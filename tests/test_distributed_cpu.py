@@ -91,3 +91,24 @@ def test_two_dimensional_spmd_mesh_world4(tmp_path):
     assert got["collectives"].get("all_reduce", 0) > 0 and got["collectives"].get("reduce_scatter", 0) > 0, got
     for a, b in zip(got["losses"], ref["losses"]):
         assert abs(a - b) <= 2e-4 * max(1.0, abs(b)), (got, ref)
+
+
+def test_checkpoint_written_by_tp2_restores_into_one_process(tmp_path):
+    """Sharded checkpoint of a 2-rank tensor-parallel run (weights split over ranks) is re-assembled and re-cut for a
+    different plan: a single process resumes with the same losses the 2-rank job produced after saving."""
+    import torch
+    ck = str(tmp_path / "ck")
+    got = _run("ckpt:tp", 2, tmp_path, {"TEPDIST_TEST_CKPT": ck})
+    assert got["parallelism"].startswith("tp"), got
+    sys.path.insert(0, HERE)
+    from tepdist_b200.api import Trainer
+    from tepdist_b200.models.gpt2 import CONFIGS, build_gpt2_graph
+    cfg = CONFIGS["tiny"]
+    tr = Trainer(build_gpt2_graph(cfg, batch=4), device=torch.device("cpu"), use_cuda_graph=False, seed=77)
+    assert tr.restore(ck) == 2
+    torch.manual_seed(0)
+    tok = torch.randint(0, cfg.n_vocab, (4, cfg.n_ctx), dtype=torch.int32)
+    feeds = {"tokens": tok, "labels": torch.roll(tok, -1, 1)}
+    resumed = [tr.step(feeds) for _ in range(2)]
+    for a, b in zip(resumed, got["losses"][2:]):
+        assert abs(a - b) <= 2e-4 * max(1.0, abs(b)), (resumed, got)
