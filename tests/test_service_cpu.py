@@ -150,3 +150,51 @@ def test_trainer_save_restore_resumes_identically(tmp_path):
         tr.save(str(tmp_path), global_step=s, max_to_keep=2)
     kept = sorted(os.listdir(os.path.join(str(tmp_path), "ckpt_0_of_1")))
     assert [k for k in kept if k.startswith("step_")] == ["step_4", "step_5"], kept
+
+
+def test_two_rank_server_job_via_launcher(tmp_path):
+    """launch.py starts a 2-process server job from a cluster spec (master rank serves gRPC, the other rank sits in the
+    worker loop); a client builds a plan (the master plans and dispatches it), trains, saves a sharded checkpoint and shuts
+    the job down.  Losses equal the single-process run (reference: ExecutionCoordinator + ExecuteRemotePlan, E2-E6)."""
+    import socket
+    import subprocess
+    import sys
+    import time
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
+    spec = tmp_path / "cluster.json"
+    spec.write_text(json.dumps({"master": {"ip": "127.0.0.1", "port": port, "gpu_ids": [0, 1]}, "workers": []}))
+    env = dict(os.environ, OMP_NUM_THREADS="2", PYTHONPATH=os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    cwd = str(tmp_path)
+    job = subprocess.Popen([sys.executable, "-m", "tepdist_b200.launch", "--cluster", str(spec), "--task-index", "0", "--platform", "cpu"],
+                           env=env, cwd=cwd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    try:
+        deadline = time.time() + 120
+        while time.time() < deadline:
+            try:
+                socket.create_connection(("127.0.0.1", port), timeout=0.5).close()
+                break
+            except OSError:
+                assert job.poll() is None, job.stdout.read()[-3000:]
+                time.sleep(0.5)
+        cl = Client(f"127.0.0.1:{port}")
+        cfg = CONFIGS["tiny"]
+        g = build_gpt2_graph(cfg, batch=4)
+        r = cl.build_execution_plan(g, strategy="auto")
+        assert r["plan_info"]["world"] == 2 and r["plan_info"]["parallelism"].startswith("dp"), r
+        torch.manual_seed(0)
+        tok = torch.randint(0, cfg.n_vocab, (4, cfg.n_ctx), dtype=torch.int32)
+        feeds = {"tokens": tok, "labels": torch.roll(tok, -1, 1)}
+        losses = [cl.execute_plan(feeds)["loss"] for _ in range(3)]
+        assert cl.server_info()["world"] == 2
+        cl.do_remote_save(3)
+        cl.shutdown()
+        job.wait(timeout=60)
+    finally:
+        if job.poll() is None:
+            job.kill()
+    from tepdist_b200.runtime.executor import Executor
+    ref = Executor(g, torch.device("cpu"), use_cuda_graph=False)
+    for a in losses:
+        b = float(ref.step(feeds)[0])
+        assert abs(a - b) <= 2e-4 * max(1.0, abs(b)), (losses, b)
+    assert os.path.isdir(tmp_path / "ckpt_0_of_2" / "step_3") and os.path.isdir(tmp_path / "ckpt_1_of_2" / "step_3")
