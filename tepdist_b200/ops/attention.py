@@ -13,6 +13,20 @@ import torch
 _HD = 64   # head dim of the tcgen05 kernels (attention_sm100.cu)
 
 
+def _can_pad(S: int, D: int, causal: bool) -> bool:
+    """Shapes that run on the D = 64 / S % 128 == 0 kernels through zero padding, exactly:
+       * narrower heads: padded q.k terms are zero, padded V / O columns are dropped;
+       * a ragged sequence length under a CAUSAL mask: padded keys sit after every real query (masked), padded query rows
+         are dropped, and their zero dO makes their contribution to dK / dV vanish."""
+    return D <= _HD and (S % 128 == 0 or causal)
+
+
+def _pad_sd(t: torch.Tensor, S: int, D: int) -> torch.Tensor:
+    """[B, S, H, D] -> zero-padded contiguous [B, ceil128(S), H, 64]."""
+    Sp = (S + 127) // 128 * 128
+    return torch.nn.functional.pad(t, (0, _HD - D, 0, 0, 0, Sp - S))
+
+
 def _ref_fwd(q, k, v, scale, causal):
     # q,k,v: [B,S,H,D] -> fp32 math in [B,H,S,D]
     qf, kf, vf = (t.float().permute(0, 2, 1, 3) for t in (q, k, v))
@@ -37,10 +51,10 @@ def attention_fwd(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, scale: floa
         o, lse, _ = _ref_fwd(q, k, v, scale, causal)
         return o, lse
     if D != _HD or S % 128:
-        if D < _HD and S % 128 == 0:   # e.g. GPT-MoE's 48-wide heads: zero-pad the head dim, the kernel math is unchanged
-            qp, kp, vp = (torch.nn.functional.pad(t, (0, _HD - D)) for t in (q, k, v))
+        if _can_pad(S, D, causal):
+            qp, kp, vp = (_pad_sd(t, S, D) for t in (q, k, v))
             o, lse = attention_fwd(qp, kp, vp, scale, causal)
-            return o[..., :D].contiguous(), lse
+            return o[:, :S, :, :D].contiguous(), lse[:, :, :S].contiguous()
         o, lse, _ = _ref_fwd(q, k, v, scale, causal)   # shapes the tcgen05 kernel does not cover: plain torch math
         return o, lse
     from . import lib, _check, _count, _stream
@@ -64,10 +78,12 @@ def attention_bwd(do: torch.Tensor, q, k, v, o, lse, scale: float | None = None,
     if dqkv_out is None:
         dqkv_out = torch.empty(B, S, H, 3, D, dtype=q.dtype, device=q.device)
     dq, dk, dv = dqkv_out[:, :, :, 0], dqkv_out[:, :, :, 1], dqkv_out[:, :, :, 2]
-    if q.is_cuda and D < _HD and S % 128 == 0:
-        pad = lambda t: torch.nn.functional.pad(t, (0, _HD - D))
-        gq, gk, gv = attention_bwd(pad(do), pad(q), pad(k), pad(v), pad(o), lse, scale, causal)
-        dq.copy_(gq[..., :D]); dk.copy_(gk[..., :D]); dv.copy_(gv[..., :D])
+    if q.is_cuda and (D != _HD or S % 128) and _can_pad(S, D, causal):
+        Sp = (S + 127) // 128 * 128
+        lse_p = lse if Sp == S else torch.nn.functional.pad(lse, (0, Sp - S))
+        gq, gk, gv = attention_bwd(_pad_sd(do, S, D), _pad_sd(q, S, D), _pad_sd(k, S, D), _pad_sd(v, S, D), _pad_sd(o, S, D),
+                                   lse_p, scale, causal)
+        dq.copy_(gq[:, :S, :, :D]); dk.copy_(gk[:, :S, :, :D]); dv.copy_(gv[:, :S, :, :D])
         return dq, dk, dv
     if not q.is_cuda or D != _HD or S % 128:
         _, _, p = _ref_fwd(q, k, v, scale, causal)

@@ -485,6 +485,19 @@ def check_attn_d48():
     torch.einsum("bhst,bthd->bshd", torch.softmax(s, -1), vf).backward(do.float())
     out["dq_d48"], out["dk_d48"], out["dv_d48"] = _rel_err(dq, qf.grad), _rel_err(dk, kf.grad), _rel_err(dv, vf.grad)
     assert max(out["o_d48"], out["dq_d48"], out["dk_d48"], out["dv_d48"]) < 3e-2 and out["lse_d48"] < 1e-3, out
+    # ragged causal sequence (S = 200) with 64-wide heads: padded to 256 around the kernel
+    qkv, q, k, v = _qkv(2, 200, 3, 64)
+    o, lse = ops.attention_fwd(q, k, v, causal=True)
+    o_ref, lse_ref, _ = _ref_fwd(q, k, v, 0.125, True)
+    out["o_s200"], out["lse_s200"] = _rel_err(o, o_ref), _rel_err(lse, lse_ref)
+    do = torch.randn_like(o)
+    dq, dk, dv = ops.attention_bwd(do, q, k, v, o, lse, causal=True)
+    qf, kf, vf = (t.float().detach().requires_grad_(True) for t in (q, k, v))
+    s = torch.einsum("bshd,bthd->bhst", qf, kf) * 0.125
+    s = s.masked_fill(~torch.ones(200, 200, dtype=torch.bool, device="cuda").tril(), float("-inf"))
+    torch.einsum("bhst,bthd->bshd", torch.softmax(s, -1), vf).backward(do.float())
+    out["dq_s200"], out["dk_s200"], out["dv_s200"] = _rel_err(dq, qf.grad), _rel_err(dk, kf.grad), _rel_err(dv, vf.grad)
+    assert max(out["o_s200"], out["dq_s200"], out["dk_s200"], out["dv_s200"]) < 3e-2 and out["lse_s200"] < 1e-3, out
     return out
 
 
