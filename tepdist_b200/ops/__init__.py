@@ -55,6 +55,16 @@ def reset_launch_count() -> None:
     _launches = 0
 
 
+_warned: set = set()
+
+
+def _warn_once(msg: str) -> None:
+    if msg not in _warned:
+        _warned.add(msg)
+        import warnings
+        warnings.warn(msg)
+
+
 def _count(n: int = 1) -> None:
     global _launches
     _launches += n
@@ -139,7 +149,12 @@ def gemm(a: torch.Tensor, b: torch.Tensor, *, a_mn: bool = False, b_mn: bool = F
         assert not accumulate
     out3 = out.unsqueeze(0) if out.dim() == 2 else out
 
-    if not a.is_cuda:  # reference path (CPU tests / oracle)
+    odd = a.is_cuda and (N % 8 != 0 or (a_mn and M % 8 != 0) or (K % 8 != 0 and not (a_mn and b_mn))
+                         or a.dtype != torch.bfloat16 or b.dtype != torch.bfloat16)
+    if odd:
+        _warn_once(f"gemm {M}x{N}x{K} ({a.dtype}): shape / dtype outside the TMA alignment rules of the tcgen05 kernels, "
+                   "running this one through torch.matmul")
+    if not a.is_cuda or odd:  # reference path (CPU tests / oracle; odd shapes on the GPU)
         A = a3.float().transpose(1, 2) if a_mn else a3.float()
         B = b3.float() if b_mn else b3.float().transpose(1, 2)
         d = alpha * torch.matmul(A, B)
@@ -374,14 +389,14 @@ def batchnorm_bwd(dy: torch.Tensor, x: torch.Tensor, gamma: torch.Tensor, mean: 
 def layernorm_fwd(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, eps: float = 1e-5):
     C = x.shape[-1]
     rows = x.numel() // C
-    if not x.is_cuda:
+    if not x.is_cuda or x.dtype != torch.bfloat16 or C % 8 or C > 4096 or gamma.dtype != torch.float32:
         xf = x.float()
         mean = xf.mean(-1)
         var = xf.var(-1, unbiased=False)
         rstd = torch.rsqrt(var + eps)
         y = ((xf - mean.unsqueeze(-1)) * rstd.unsqueeze(-1) * gamma.float() + beta.float()).to(x.dtype)
         return y, mean.reshape(rows), rstd.reshape(rows)
-    assert x.dtype == torch.bfloat16 and x.is_contiguous() and gamma.dtype == torch.float32
+    x = x.contiguous()
     y = torch.empty_like(x)
     mean = torch.empty(rows, dtype=torch.float32, device=x.device)
     rstd = torch.empty(rows, dtype=torch.float32, device=x.device)
@@ -396,7 +411,7 @@ def layernorm_bwd(dy, x, gamma, mean, rstd, dgamma_acc: torch.Tensor, dbeta_acc:
     """Returns dx (+ dres when given: fused residual-stream gradient add); accumulates dgamma/dbeta (fp32)."""
     C = x.shape[-1]
     rows = x.numel() // C
-    if not x.is_cuda:
+    if not x.is_cuda or x.dtype != torch.bfloat16 or C % 8 or C > 2048 or gamma.dtype != torch.float32:
         xf, dyf = x.float().reshape(rows, C), dy.float().reshape(rows, C)
         xh = (xf - mean.unsqueeze(-1)) * rstd.unsqueeze(-1)
         g = dyf * gamma.float()
@@ -418,9 +433,9 @@ def layernorm_bwd(dy, x, gamma, mean, rstd, dgamma_acc: torch.Tensor, dbeta_acc:
 
 # --------------------------------------------------------------------------------------------- GELU / colsum
 def gelu_fwd(x: torch.Tensor) -> torch.Tensor:
-    if not x.is_cuda:
+    if not x.is_cuda or x.dtype != torch.bfloat16 or x.numel() % 8:
         return torch.nn.functional.gelu(x.float(), approximate="tanh").to(x.dtype)
-    assert x.is_contiguous() and x.dtype == torch.bfloat16
+    x = x.contiguous()
     y = torch.empty_like(x)
     _check(lib().tepd_gelu_fwd(x.data_ptr(), y.data_ptr(), x.numel(), _stream()), "gelu_fwd")
     _count()
@@ -428,7 +443,7 @@ def gelu_fwd(x: torch.Tensor) -> torch.Tensor:
 
 
 def gelu_bwd(dy: torch.Tensor, x: torch.Tensor) -> torch.Tensor:
-    if not x.is_cuda:
+    if not x.is_cuda or x.dtype != torch.bfloat16 or dy.dtype != torch.bfloat16 or x.numel() % 8:
         xf = x.float().detach().requires_grad_(True)
         with torch.enable_grad():
             y = torch.nn.functional.gelu(xf, approximate="tanh")
@@ -445,7 +460,7 @@ def colsum_acc(x: torch.Tensor, out_acc: torch.Tensor) -> None:
     """out_acc[c] += sum_r x[r, c] (bias gradients, fp32 accumulate)."""
     C = x.shape[-1]
     rows = x.numel() // C
-    if not x.is_cuda:
+    if not x.is_cuda or x.dtype != torch.bfloat16 or C % 8:
         out_acc.add_(x.float().reshape(rows, C).sum(0))
         return
     x = x.contiguous()
