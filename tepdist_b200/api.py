@@ -88,6 +88,9 @@ class Trainer:
         return self.exec.step(dev_feeds)[0]
 
     def state_dict(self):
+        """Master weights (+ optimizer moments).  Collective under sharded-optimizer plans: every rank must call it."""
+        if hasattr(self.exec, "materialize_full_state"):
+            self.exec.materialize_full_state()
         return self.exec.store.state_dict()
 
     # ------------------------------------------------------------------ sharded checkpoints (reference DoRemoteSave / Restore)

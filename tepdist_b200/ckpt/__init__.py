@@ -33,6 +33,8 @@ class CheckpointManager:
         return True
 
     def save(self, executor, global_step: int, extra: Optional[Dict[str, Any]] = None) -> str:
+        if hasattr(executor, "materialize_full_state"):
+            executor.materialize_full_state()      # sharded-optimizer runs: make master / m / v whole before writing
         st = executor.store
         g = executor.g
         prefix = os.path.join(self.dir, f"step_{global_step}")

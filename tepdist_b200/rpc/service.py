@@ -130,6 +130,12 @@ class ServiceImpl:
             return self.ckpt.save(tr.exec, msg["global_step"])
         return "lazy"
 
+    def _do_sync_state(self, msg):
+        """Make fp32 master weights / moments whole on every rank (sharded-optimizer plans keep only the owned chunk fresh)."""
+        tr = self.cache.get(msg["handle"])
+        if hasattr(tr.exec, "materialize_full_state"):
+            tr.exec.materialize_full_state()
+
     def _do_restore(self, msg):
         self.restore_request = msg.get("global_step", -1)
         return "pending"
@@ -163,6 +169,10 @@ class ServiceImpl:
         self.step_log.append(dt)
         out = {"loss": loss, "duration_ms": dt}
         if m.get("fetch_vars"):
+            with self.exec_lock:
+                msg = {"cmd": "sync_state", "handle": m["handle"]}
+                self._bcast(msg)
+                self._do_sync_state(msg)
             sd = tr.exec.store.state_dict()
             out["vars"] = {k: sd[k].cpu() for k in m["fetch_vars"] if k in sd}
         return pack(out)
@@ -170,6 +180,10 @@ class ServiceImpl:
     def FetchResourceVars(self, req: bytes, ctx) -> bytes:
         m = unpack(req)
         tr = self.cache.get(m["handle"])
+        with self.exec_lock:
+            msg = {"cmd": "sync_state", "handle": m["handle"]}
+            self._bcast(msg)
+            self._do_sync_state(msg)
         sd = tr.exec.store.state_dict()
         names = m.get("names") or [k for k in sd if not k.endswith(("/m", "/v"))]
         return pack({k: sd[k].cpu() for k in names if k in sd})

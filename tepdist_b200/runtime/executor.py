@@ -434,6 +434,20 @@ class Executor:
         self.grad_binding = binding
         self.flat_zero = {"level": fz["level"], "num": num, "skip": skip, "buckets": buckets, "ready_at": ready_at,
                           "rank": self.coords.get(fz["level"], 0), "regular_apply": regular_apply, "fused": None}
+        # replicated-gradient variables (e.g. embeddings whose backward the plan replicates on every rank): the gradient
+        # lands in the flat buffer and the UPDATE is still sharded -- the owner updates its chunk from the local gradient
+        # and publishes it (fused mode: P2P stores from the same kernel; NCCL mode: all-gather).  (N-1)/N less AdamW
+        # traffic, and the replicas stay bit-identical (redundant fp32 atomics would let them drift apart).
+        rep = {}
+        if self.opt.get("kind") == "adamw" and st.m is not None:
+            for aid, (pid, gkey) in fz.get("replicated", {}).items():
+                n_el = 1
+                for d in st.shape[pid]:
+                    n_el *= d
+                if n_el % (4 * num) == 0 and st.offset[pid] % 4 == 0 and g.nodes[aid].op == "apply_adamw":
+                    rep[aid] = (pid, st.offset[pid], n_el, bool(g.nodes[aid].attrs.get("decay", True)))
+                    self.grad_binding[gkey] = pid
+        self.flat_zero["replicated_apply"] = rep
         if (self.comm_mode == "fused" and st.master.is_cuda and self.opt.get("kind") == "adamw" and num <= 8):
             from ..parallel.symm import FusedShardedOptimizer
             pg = self.collective.mesh.group(fz["level"])
@@ -441,17 +455,6 @@ class Executor:
                 st.make_symmetric(pg)
                 self.flat_zero["fused"] = FusedShardedOptimizer(st.symm_grad, st.symm_param, pg)
                 self.flat_zero["fused"].dry = self.dry_comm
-                # replicated-gradient variables (e.g. embeddings whose backward the plan replicates): gradient lands in
-                # the flat buffer, update sharded over the ranks by the same fused kernel (local gradient, P2P stores)
-                rep = {}
-                for aid, (pid, gkey) in fz.get("replicated", {}).items():
-                    n_el = 1
-                    for d in st.shape[pid]:
-                        n_el *= d
-                    if n_el % (4 * num) == 0 and st.offset[pid] % 4 == 0 and g.nodes[aid].op == "apply_adamw":
-                        rep[aid] = (pid, st.offset[pid], n_el, bool(g.nodes[aid].attrs.get("decay", True)))
-                        self.grad_binding[gkey] = pid
-                self.flat_zero["replicated_apply"] = rep
             except RuntimeError as e:   # e.g. CUDA IPC unavailable in this container: keep the NCCL path, loudly
                 import warnings
                 warnings.warn(f"fused peer-memory optimizer unavailable ({e}); falling back to NCCL collectives")
@@ -537,8 +540,40 @@ class Executor:
             tgt = st.compute if st.compute is not None else st.master
             if not self.dry_comm:
                 works.append(dist.all_gather_into_tensor(tgt[s0:e0], tgt[a:b], group=pg, async_op=True))
+        for aid, (pid, off, n_el, decay) in (fz.get("replicated_apply") or {}).items():
+            chunk = n_el // n
+            a, b = off + r * chunk, off + (r + 1) * chunk
+            comp = None if st.compute is None else st.compute[a:b]
+            ops.adamw_step(st.master[a:b], st.grad[a:b], st.m[a:b], st.v[a:b], comp, (b - a) if decay else 0, o.get("lr", 1e-3),
+                           o.get("beta1", 0.9), o.get("beta2", 0.999), o.get("eps", 1e-8), o.get("weight_decay", 0.0),
+                           self.step_count, hyper=self.hyper if st.master.is_cuda else None)
+            tgt = st.compute if st.compute is not None else st.master
+            if not self.dry_comm:
+                works.append(dist.all_gather_into_tensor(tgt[off:off + n_el], tgt[a:b], group=pg, async_op=True))
         for w in works:
             w.wait()
+
+    def materialize_full_state(self) -> None:
+        """ZeRO-style execution updates the fp32 master weights and moments only in the chunk each rank owns; outside it
+        they go stale (only the bf16 compute copy is all-gathered every step).  Before a checkpoint / state_dict every rank
+        gathers the owners' chunks so master, m and v are whole and identical everywhere.  Collective: all ranks call it."""
+        fz = self.flat_zero
+        if fz is None:
+            return
+        import torch.distributed as dist
+        st = self.store
+        n, r = fz["num"], fz["rank"]
+        pg = self.collective.mesh.group(fz["level"])
+        ranges = [(s0, e0) for (s0, e0) in fz["buckets"]]
+        ranges += [(off, off + n_el) for (_, off, n_el, _) in (fz.get("replicated_apply") or {}).values()]
+        if st.master.is_cuda:
+            torch.cuda.synchronize()
+        for buf in (st.master, st.m, st.v):
+            if buf is None:
+                continue
+            for (s0, e0) in ranges:
+                chunk = (e0 - s0) // n
+                dist.all_gather_into_tensor(buf[s0:e0], buf[s0 + r * chunk:s0 + (r + 1) * chunk].clone(), group=pg)
 
     # ------------------------------------------------------------------ running
     def step(self, feeds: Dict[str, torch.Tensor]) -> List[torch.Tensor]:

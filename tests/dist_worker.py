@@ -43,6 +43,29 @@ def case_ckpt(strategy):
     return {"losses": before + after, "parallelism": tr.plan_info.get("parallelism"), "collectives": tr.plan_info.get("collectives")}
 
 
+def case_state(strategy):
+    """After a few sharded-optimizer steps every rank's state_dict must hold the SAME, fully updated master weights."""
+    from tepdist_b200.api import Trainer
+    from tepdist_b200.models.gpt2 import CONFIGS, build_gpt2_graph
+    cfg = CONFIGS["tiny"]
+    tr = Trainer(build_gpt2_graph(cfg, batch=4), strategy=strategy, device=torch.device("cpu"), use_cuda_graph=False)
+    torch.manual_seed(0)
+    tok = torch.randint(0, cfg.n_vocab, (4, cfg.n_ctx), dtype=torch.int32)
+    feeds = {"tokens": tok, "labels": torch.roll(tok, -1, 1)}
+    losses = [tr.step(feeds) for _ in range(3)]
+    sd = tr.state_dict()
+    keys = sorted(k for k in sd if not k.endswith(("/m", "/v")))
+    sig = torch.tensor([float(sd[k].double().sum()) for k in keys] + [float(sd[k].double().abs().sum()) for k in keys], dtype=torch.float64)
+    spread = 0.0
+    if dist.is_initialized():
+        lo, hi = sig.clone(), sig.clone()
+        dist.all_reduce(lo, op=dist.ReduceOp.MIN)
+        dist.all_reduce(hi, op=dist.ReduceOp.MAX)
+        spread = float((hi - lo).abs().max())
+    return {"losses": losses, "signature": sig.tolist(), "rank_spread": spread, "parallelism": tr.plan_info.get("parallelism"),
+            "collectives": tr.plan_info.get("collectives")}
+
+
 def case_mlp(strategy):
     """examples/smoke_testing-style 2-layer MLP; planner emits a DP shard on CPU/gloo world_size=2 (BASELINE config 1)."""
     from tepdist_b200.api import Trainer
@@ -72,7 +95,7 @@ def case_moe(strategy):
 if __name__ == "__main__":
     case, out = sys.argv[1], sys.argv[2]
     name, _, strat = case.partition(":")
-    res = {"gpt2": case_gpt2, "gpt2s": lambda st: case_gpt2(st, True), "gpt2b1": lambda st: case_gpt2(st, False, 1), "mlp": case_mlp, "moe": case_moe, "ckpt": case_ckpt}[name](strat or "auto")
+    res = {"gpt2": case_gpt2, "gpt2s": lambda st: case_gpt2(st, True), "gpt2b1": lambda st: case_gpt2(st, False, 1), "mlp": case_mlp, "moe": case_moe, "ckpt": case_ckpt, "state": case_state}[name](strat or "auto")
     if int(os.environ.get("RANK", "0")) == 0:
         json.dump(res, open(out, "w"))
     if dist.is_initialized():

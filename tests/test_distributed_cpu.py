@@ -112,3 +112,14 @@ def test_checkpoint_written_by_tp2_restores_into_one_process(tmp_path):
     resumed = [tr.step(feeds) for _ in range(2)]
     for a, b in zip(resumed, got["losses"][2:]):
         assert abs(a - b) <= 2e-4 * max(1.0, abs(b)), (resumed, got)
+
+
+def test_state_dict_is_whole_and_identical_on_every_rank(tmp_path):
+    """ZeRO-1 execution keeps only the owned chunk of the fp32 master fresh; state_dict() gathers the owners' chunks."""
+    sys.path.insert(0, HERE)
+    import dist_worker
+    ref = dist_worker.case_state("auto")
+    got = _run("state:auto", 2, tmp_path)
+    assert got["parallelism"].startswith("dp") and got["rank_spread"] == 0.0, got
+    for a, b in zip(got["signature"], ref["signature"]):
+        assert abs(a - b) <= 1e-3 * max(1.0, abs(b)), (got["signature"][:4], ref["signature"][:4])
