@@ -14,6 +14,15 @@ using namespace sm100;
 
 namespace {
 
+inline bool exp_poly_enabled() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("TEPDIST_ATTN_EXP_POLY");
+    v = (e && e[0] == '1') ? 1 : 0;
+  }
+  return v == 1;
+}
+
 constexpr int HD = 64;        // head dim
 constexpr int BQ = 128;       // query rows per CTA
 constexpr int BKV = 128;      // kv rows per iteration
@@ -37,10 +46,27 @@ struct AttnFwdParams {
   float scale;
 };
 
+// 2^x on the FMA / ALU pipes (no MUFU): round-to-nearest split x = n + f with the 1.5 * 2^23 magic constant, degree-4
+// polynomial for 2^f on [-0.5, 0.5] (rel. error 4e-5, below bf16 resolution), exponent spliced in with integer adds.
+// The softmax of D = 64 attention is MUFU-bound (16 ex2 / clk / SM vs 128 FMA lanes): evaluating every second exponential
+// this way (POLY = 1 instantiations, TEPDIST_ATTN_EXP_POLY=1) trades 1 MUFU op for ~8 FMA / ALU ops on idle pipes.
+__device__ __forceinline__ float exp2_poly(float x) {
+  x = fmaxf(x, -125.f);
+  const float magic = 12582912.f;
+  const float t = x + magic;
+  const float f = x - (t - magic);
+  float p = fmaf(0.0096181291f, f, 0.0555041087f);
+  p = fmaf(p, f, 0.2402265070f);
+  p = fmaf(p, f, 0.6931471806f);
+  p = fmaf(p, f, 1.0f);
+  return __int_as_float(__float_as_int(p) + (__float_as_int(t) << 23));
+}
+
 __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
 
+template <int POLY>
 __global__ void __launch_bounds__(FWD_THREADS, 1)
 attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_k,
                 const __grid_constant__ CUtensorMap tmap_v, const AttnFwdParams p) {
@@ -187,7 +213,8 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
 #pragma unroll
       for (int i = 0; i < 32; ++i) {
         const float p0 = exp2f(fmaf(s[2 * i], p.scale_log2, -mb));
-        const float p1 = exp2f(fmaf(s[2 * i + 1], p.scale_log2, -mb));
+        const float x1 = fmaf(s[2 * i + 1], p.scale_log2, -mb);
+        const float p1 = POLY ? exp2_poly(x1) : exp2f(x1);
         lsum += p0 + p1;
         pk[i] = pack_bf16x2(p0, p1);
       }
@@ -287,6 +314,7 @@ struct AttnBwdParams {
   float scale_log2, scale;
 };
 
+template <int POLY>
 __global__ void __launch_bounds__(BWD_THREADS, 1)
 attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_k,
                 const __grid_constant__ CUtensorMap tmap_v, const __grid_constant__ CUtensorMap tmap_do,
@@ -443,7 +471,8 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
             const int idx = 2 * e + u;
             const float sv_ = __uint_as_float(c == 0 ? rs0[idx] : rs1[idx]);
             const float dpv = __uint_as_float(c == 0 ? rd0[idx] : rd1[idx]);
-            float pe = exp2f(fmaf(sv_, p.scale_log2, -lse2));
+            const float xe = fmaf(sv_, p.scale_log2, -lse2);
+            float pe = (POLY && u == 1) ? exp2_poly(xe) : exp2f(xe);
             if (diag && (kv0 + c * 32 + idx > q_global)) pe = 0.f;
             pv[u] = pe;
             dsv[u] = pe * (dpv - delta);
@@ -608,7 +637,8 @@ extern "C" int tepd_attn_fwd(const void* q, const void* k, const void* v, void* 
   if (rc) return 300 + rc;
   static bool cfg = false;
   if (!cfg) {
-    cudaError_t e = cudaFuncSetAttribute(attn_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FWD_SMEM);
+    cudaError_t e = cudaFuncSetAttribute(attn_fwd_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, FWD_SMEM);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(attn_fwd_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, FWD_SMEM);
     if (e != cudaSuccess) return (int)e;
     cfg = true;
   }
@@ -616,9 +646,12 @@ extern "C" int tepd_attn_fwd(const void* q, const void* k, const void* v, void* 
   p.O = o; p.lse = (float*)lse; p.B = B; p.H = H; p.S = S; p.causal = causal;
   p.scale = scale; p.scale_log2 = scale * 1.4426950408889634f;
   int grid = (S / BQ) * B * H;
-  return (int)tepd::launch(attn_fwd_kernel, dim3(grid), dim3(FWD_THREADS), FWD_SMEM, reinterpret_cast<cudaStream_t>(stream), tq, tk, tv, p);
+  if (exp_poly_enabled())
+    return (int)tepd::launch(attn_fwd_kernel<1>, dim3(grid), dim3(FWD_THREADS), FWD_SMEM, reinterpret_cast<cudaStream_t>(stream), tq, tk, tv, p);
+  return (int)tepd::launch(attn_fwd_kernel<0>, dim3(grid), dim3(FWD_THREADS), FWD_SMEM, reinterpret_cast<cudaStream_t>(stream), tq, tk, tv, p);
 }
 
+// (host) TEPDIST_ATTN_EXP_POLY=1 selects the POLY = 1 instantiations
 // do, o: contiguous [B,S,H,D]; q/k/v strided views; dq/dk/dv strided views (shared strides).
 extern "C" int tepd_attn_bwd(const void* dO, const void* q, const void* k, const void* v, const void* o, const void* lse,
                              void* dq_acc, void* dq, void* dk, void* dv, int B, int H, int S, int D, float scale,
@@ -664,7 +697,8 @@ extern "C" int tepd_attn_bwd(const void* dO, const void* q, const void* k, const
   }
   static bool cfg = false;
   if (!cfg) {
-    cudaError_t e = cudaFuncSetAttribute(attn_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, BWD_SMEM);
+    cudaError_t e = cudaFuncSetAttribute(attn_bwd_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, BWD_SMEM);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(attn_bwd_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, BWD_SMEM);
     if (e != cudaSuccess) return (int)e;
     cfg = true;
   }
@@ -672,7 +706,9 @@ extern "C" int tepd_attn_bwd(const void* dO, const void* q, const void* k, const
   p.lse = (const float*)lse; p.delta = delta_buf; p.dq_acc = (float*)dq_acc; p.dk = dk; p.dv = dv;
   p.dstride_b = dstride_b; p.dstride_s = dstride_s; p.dstride_h = dstride_h;
   p.B = B; p.H = H; p.S = S; p.causal = causal; p.scale = scale; p.scale_log2 = scale * 1.4426950408889634f;
-  cudaError_t le = tepd::launch(attn_bwd_kernel, dim3((S / BKV) * B * H), dim3(BWD_THREADS), BWD_SMEM, st, tq, tk, tv, tdo, p);
+  cudaError_t le = exp_poly_enabled()
+                       ? tepd::launch(attn_bwd_kernel<1>, dim3((S / BKV) * B * H), dim3(BWD_THREADS), BWD_SMEM, st, tq, tk, tv, tdo, p)
+                       : tepd::launch(attn_bwd_kernel<0>, dim3((S / BKV) * B * H), dim3(BWD_THREADS), BWD_SMEM, st, tq, tk, tv, tdo, p);
   if (le != cudaSuccess) return (int)le;
   return (int)tepd::launch(attn_dq_cast_kernel, dim3(148 * 4), dim3(256), 0, st, (float*)dq_acc, (__nv_bfloat16*)dq, B, S, H,
                            dstride_b, dstride_s, dstride_h);

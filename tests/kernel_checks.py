@@ -501,6 +501,18 @@ def check_attn_d48():
     return out
 
 
+def check_attn_poly():
+    """POLY instantiations (every second exponential on the FMA pipes, TEPDIST_ATTN_EXP_POLY=1): same numerics checks as the
+    default kernels + timing.  Run as its own process (the switch is read once): python tests/kernel_checks.py attn_poly"""
+    os.environ["TEPDIST_ATTN_EXP_POLY"] = "1"
+    out = {"fwd": check_attn_fwd(), "bwd": check_attn_bwd()}
+    try:
+        out["perf"] = check_attn_perf()
+    except Exception as e:  # noqa: BLE001
+        out["perf"] = repr(e)
+    return out
+
+
 def check_attn_bwd():
     from tepdist_b200 import ops
     from tepdist_b200.ops.attention import _ref_fwd
@@ -561,6 +573,7 @@ CHECKS = {
     "gemm_perf": check_gemm_perf,
     "conv": check_conv,
     "attn_d48": check_attn_d48,
+    "attn_poly": check_attn_poly,
     "gemm2": check_gemm2,
     "attn_perf": check_attn_perf,
 }
