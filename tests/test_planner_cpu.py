@@ -323,3 +323,24 @@ def test_evaluator_and_exploration():
     plan = _C.auto_parallel(cg, ap)
     assert len(plan.candidates) >= 3 and "[Strategy]" in plan.log
     assert plan.eval.total_duration == pytest.approx(min(d for _, d in plan.candidates))
+
+
+def test_gpt2_1p5b_plans_quickly_in_every_mode():
+    """GPT-2 1.5B (48 layers, 3.6k nodes) on 8 devices: cost-based SPMD, forced tensor parallel, exploration and a configured
+    4-stage pipeline all plan in about a second thanks to structural memoisation of identical layers (the reference's ILP
+    needs minutes, ILP_TIME_LIMIT defaults to 5)."""
+    import time
+    from tepdist_b200.models.gpt2 import CONFIGS, build_gpt2_graph
+    from tepdist_b200.parallel import classify_parallelism, plan_pipeline, plan_spmd
+    g = build_gpt2_graph(CONFIGS["1.5B"], batch=32)
+    t0 = time.time()
+    _, info = plan_spmd(g, 8, "auto")
+    assert classify_parallelism(info, 8) == "dp8+zero1" and info["collectives"].get("reduce_scatter", 0) > 500
+    _, info = plan_spmd(g, 8, "tp")
+    assert classify_parallelism(info, 8) == "tp8"
+    _, pinfo, _ = plan_pipeline(g, 8, 0, 0)                       # exploration: everything fits -> no pipeline
+    assert (pinfo["stages"], pinfo["spmd"]) == (1, 8)
+    _, pinfo, tasks = plan_pipeline(g, 8, 4, 8)                   # config mode: 4 stages x 8 micro-batches x SPMD 2
+    assert (pinfo["stages"], pinfo["micro"], pinfo["spmd"]) == (4, 8, 2) and len(tasks) >= 4
+    assert 0.0 < pinfo["bubble_est"] < 0.5
+    assert time.time() - t0 < 60.0
