@@ -23,6 +23,15 @@ inline bool exp_poly_enabled() {
   return v == 1;
 }
 
+inline bool fwd2_enabled() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("TEPDIST_ATTN_FWD2");
+    v = (e && e[0] == '1') ? 1 : 0;
+  }
+  return v == 1;
+}
+
 constexpr int HD = 64;        // head dim
 constexpr int BQ = 128;       // query rows per CTA
 constexpr int BKV = 128;      // kv rows per iteration
@@ -285,6 +294,257 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
   }
 }
 
+
+// =====================================================================================================
+// Forward, two query tiles per CTA (EXPERIMENTAL, TEPDIST_ATTN_FWD2=1; not yet run on hardware).
+//
+// The kernel above is bound by the softmax, not by the tensor pipe: 128 x 128 exponentials per KV block at 16 MUFU / clk /
+// SM are 1024 clk, and its 8 softmax warps all walk the same phases (TMEM load, row max, exchange, exp, fold, store) in
+// lock-step, so the MUFU pipe idles about half of the time.  Here one CTA owns TWO 128-row query tiles (A, B) that share
+// every K / V stage; each tile has its own 4 softmax warps (one thread per query row: no cross-warp max exchange), its own
+// S accumulator (single-buffered) and its own O accumulator in TMEM.  The MMA warp serves the tiles alternately
+// (PV_A(j), S_A(j+1), PV_B(j), S_B(j+1), ...), so while tile A waits for its next S the MUFU pipe works on tile B.
+// O stays in TMEM across KV blocks (PV accumulates); the running maximum is only a REFERENCE that is raised -- and O / l
+// rescaled in place with tcgen05.ld / st -- when the block maximum exceeds it by more than 2^8 (exact: every P of a row is
+// relative to the same reference at the end, nothing overflows below 2^8).
+// TMEM: S_A [0,128) S_B [128,256) O_A [256,320) O_B [320,384).  smem: Q_A Q_B | K x3 | V x3 | P_A P_B = 192 KB.
+// =====================================================================================================
+constexpr int F2_THREADS = 64 + 256;
+constexpr int F2_Q = 0;                                   // 2 tiles
+constexpr int F2_K = F2_Q + 2 * TILE_BYTES;
+constexpr int F2_V = F2_K + KV_STAGES * TILE_BYTES;
+constexpr int F2_P = F2_V + KV_STAGES * TILE_BYTES;       // 2 tiles x 2 chunks
+constexpr int F2_BAR = F2_P + 4 * TILE_BYTES;
+constexpr int F2_SMEM = F2_BAR + 256 + 1024;
+
+__global__ void __launch_bounds__(F2_THREADS, 1)
+attn_fwd2_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_k,
+                 const __grid_constant__ CUtensorMap tmap_v, const AttnFwdParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + F2_BAR);
+  uint64_t* q_full = bars + 0;
+  uint64_t* kv_full = bars + 1;     // [3]
+  uint64_t* kv_empty = bars + 4;    // [3]
+  uint64_t* s_full = bars + 7;      // [2] per tile
+  uint64_t* s_empty = bars + 9;     // [2]
+  uint64_t* p_full = bars + 11;     // [2]
+  uint64_t* pv_full = bars + 13;    // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 15);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int nq2 = p.S / 256;
+  const int BH = p.B * p.H;
+  const int qb2 = nq2 - 1 - (int)(blockIdx.x / BH);   // heavy rows first
+  const int bh = blockIdx.x % BH;
+  const int b = bh / p.H, h = bh % p.H;
+  const int nkv_t[2] = {p.causal ? 2 * qb2 + 1 : p.S / BKV, p.causal ? 2 * qb2 + 2 : p.S / BKV};
+  const int nkv = nkv_t[1];
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmap_q);
+    tma_prefetch_desc(&tmap_k);
+    tma_prefetch_desc(&tmap_v);
+    mbar_init(q_full, 1);
+    for (int i = 0; i < KV_STAGES; ++i) { mbar_init(&kv_full[i], 1); mbar_init(&kv_empty[i], 1); }
+    for (int t = 0; t < 2; ++t) {
+      mbar_init(&s_full[t], 1);
+      mbar_init(&s_empty[t], 4);
+      mbar_init(&p_full[t], 4);
+      mbar_init(&pv_full[t], 1);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_slot, 512);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();
+  pdl_trigger();
+
+  if (warp == 0) {
+    if (elect_one()) {
+      mbar_expect_tx(q_full, 2 * TILE_BYTES);
+      tma_load_4d(smem + F2_Q, &tmap_q, q_full, 0, qb2 * 256, h, b);
+      tma_load_4d(smem + F2_Q + TILE_BYTES, &tmap_q, q_full, 0, qb2 * 256 + 128, h, b);
+      for (int j = 0; j < nkv; ++j) {
+        const int st = j % KV_STAGES;
+        mbar_wait(&kv_empty[st], ((j / KV_STAGES) & 1) ^ 1);
+        mbar_expect_tx(&kv_full[st], 2 * TILE_BYTES);
+        tma_load_4d(smem + F2_K + st * TILE_BYTES, &tmap_k, &kv_full[st], 0, j * BKV, h, b);
+        tma_load_4d(smem + F2_V + st * TILE_BYTES, &tmap_v, &kv_full[st], 0, j * BKV, h, b);
+      }
+    }
+  } else if (warp == 1) {
+    if (elect_one()) {
+      constexpr uint32_t idesc_s = make_idesc(UMMA_BF16, UMMA_BF16, 128, 128, 0, 0);
+      constexpr uint32_t idesc_pv = make_idesc(UMMA_BF16, UMMA_BF16, 128, 64, 0, 1);
+      auto issue_s = [&](int t, int j) {     // S_t(j) = Q_t K(j)^T ; needs K stage j and the tile's S buffer drained
+        const int st = j % KV_STAGES;
+        mbar_wait(&kv_full[st], (j / KV_STAGES) & 1);
+        if (j > 0) mbar_wait(&s_empty[t], (j - 1) & 1);
+        tc_fence_after();
+        const uint32_t sq = smem_u32(smem + F2_Q + t * TILE_BYTES);
+        const uint32_t sk = smem_u32(smem + F2_K + st * TILE_BYTES);
+#pragma unroll
+        for (int k = 0; k < HD / 16; ++k)
+          umma_f16_ss(tmem_base + t * 128, make_smem_desc_sw128(sq + k * 32, 0, 1024), make_smem_desc_sw128(sk + k * 32, 0, 1024),
+                      idesc_s, k > 0 ? 1u : 0u);
+        umma_commit(&s_full[t]);
+      };
+      auto issue_pv = [&](int t, int j) {    // O_t += P_t(j) V(j)
+        mbar_wait(&p_full[t], j & 1);
+        tc_fence_after();
+        const uint32_t sp = smem_u32(smem + F2_P + t * 2 * TILE_BYTES);
+        const uint32_t sv = smem_u32(smem + F2_V + (j % KV_STAGES) * TILE_BYTES);
+#pragma unroll
+        for (int k = 0; k < BKV / 16; ++k)
+          umma_f16_ss(tmem_base + 256 + t * 64, make_smem_desc_sw128(sp + (k >> 2) * TILE_BYTES + (k & 3) * 32, 0, 1024),
+                      make_smem_desc_sw128(sv + k * 2048, TILE_BYTES, 1024), idesc_pv, (j > 0 || k > 0) ? 1u : 0u);
+        umma_commit(&pv_full[t]);
+      };
+      mbar_wait(q_full, 0);
+      issue_s(0, 0);
+      issue_s(1, 0);
+      for (int j = 0; j < nkv; ++j) {
+        for (int t = 0; t < 2; ++t) {
+          if (j < nkv_t[t]) {
+            issue_pv(t, j);
+            if (j + 1 < nkv_t[t]) issue_s(t, j + 1);
+          }
+        }
+        umma_commit(&kv_empty[j % KV_STAGES]);   // every MMA that reads stage j has been issued
+      }
+    }
+  } else {
+    // ===================== softmax: warps 2-5 tile A, warps 6-9 tile B; one thread per query row =====================
+    const int t = (warp - 2) >> 2;
+    const int quarter = warp & 3;
+    const int row = quarter * 32 + lane;
+    const int q_global = qb2 * 256 + t * 128 + row;
+    const uint32_t lane_addr = uint32_t(quarter * 32) << 16;
+    const uint32_t TM_S = tmem_base + lane_addr + t * 128;
+    const uint32_t TM_O = tmem_base + lane_addr + 256 + t * 64;
+    const int n_mine = nkv_t[t];
+    float m_ref = -INFINITY, l_run = 0.f;
+    for (int j = 0; j < n_mine; ++j) {
+      mbar_wait(&s_full[t], j & 1);
+      tc_fence_after();
+      const bool diag = p.causal && j == n_mine - 1;
+      // ---- pass 1: row maximum
+      float mx = -INFINITY;
+#pragma unroll 1
+      for (int c = 0; c < 4; ++c) {
+        uint32_t r[32];
+        tmem_ld_32x32(TM_S + c * 32, r);
+        tmem_ld_wait();
+        const int col0 = j * BKV + c * 32;
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+          float v = __uint_as_float(r[i]);
+          if (diag && col0 + i > q_global) v = -INFINITY;
+          mx = fmaxf(mx, v);
+        }
+      }
+      // ---- reference maximum: raise it (and rescale O, l) only when the block exceeds it by more than 2^8
+      float alpha = 1.f;
+      bool raise = false;
+      if (j == 0) {
+        m_ref = mx;
+      } else if ((mx - m_ref) * p.scale_log2 > 8.f) {
+        alpha = exp2f((m_ref - mx) * p.scale_log2);
+        raise = true;
+      }
+      if (j > 0) {   // PV(j-1) done: the P buffer may be overwritten and O is stable
+        mbar_wait(&pv_full[t], (j - 1) & 1);
+        tc_fence_after();
+      }
+      if (__any_sync(0xffffffffu, raise)) {   // tcgen05.ld / st are warp-collective: lanes that keep their reference use alpha = 1
+#pragma unroll 1
+        for (int c = 0; c < 2; ++c) {
+          uint32_t r[32];
+          tmem_ld_32x32(TM_O + c * 32, r);
+          tmem_ld_wait();
+#pragma unroll
+          for (int i = 0; i < 32; ++i) r[i] = __float_as_uint(__uint_as_float(r[i]) * alpha);
+          tmem_st_32x32(TM_O + c * 32, r);
+        }
+        tmem_st_wait();
+        if (raise) { l_run *= alpha; m_ref = mx; }
+      }
+      const float mb = m_ref * p.scale_log2;
+      // ---- pass 2: P = 2^(s*c - mb) -> bf16 -> smem (SW128 K-major, chunk = 64 columns), row sum
+      float lsum = 0.f;
+      uint8_t* prow = smem + F2_P + t * 2 * TILE_BYTES + row * 128;
+#pragma unroll 1
+      for (int c = 0; c < 4; ++c) {
+        uint32_t r[32];
+        tmem_ld_32x32(TM_S + c * 32, r);
+        tmem_ld_wait();
+        if (c == 3) {   // S fully consumed: the MMA warp may overwrite it with S(j+1)
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&s_empty[t]);
+        }
+        const int col0 = j * BKV + c * 32;
+        uint32_t pk[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          float v0 = __uint_as_float(r[2 * i]), v1 = __uint_as_float(r[2 * i + 1]);
+          if (diag && col0 + 2 * i > q_global) v0 = -INFINITY;
+          if (diag && col0 + 2 * i + 1 > q_global) v1 = -INFINITY;
+          const float p0 = exp2f(fmaf(v0, p.scale_log2, -mb));
+          const float p1 = exp2f(fmaf(v1, p.scale_log2, -mb));
+          lsum += p0 + p1;
+          pk[i] = pack_bf16x2(p0, p1);
+        }
+        uint8_t* pc = prow + (c >> 1) * TILE_BYTES;     // columns 0-63 -> chunk 0, 64-127 -> chunk 1
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+          const int gran = (c & 1) * 4 + g;              // 16-byte granule inside the 128-byte row
+          *reinterpret_cast<uint4*>(pc + ((gran ^ (row & 7)) << 4)) = make_uint4(pk[4 * g], pk[4 * g + 1], pk[4 * g + 2], pk[4 * g + 3]);
+        }
+      }
+      l_run += lsum;
+      fence_proxy_async();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&p_full[t]);
+    }
+    // ---- epilogue: O / l
+    mbar_wait(&pv_full[t], (n_mine - 1) & 1);
+    tc_fence_after();
+    const float inv = 1.f / l_run;
+    __nv_bfloat16* orow = reinterpret_cast<__nv_bfloat16*>(p.O) + (((size_t)b * p.S + q_global) * p.H + h) * HD;
+#pragma unroll 1
+    for (int c = 0; c < 2; ++c) {
+      uint32_t r[32];
+      tmem_ld_32x32(TM_O + c * 32, r);
+      tmem_ld_wait();
+#pragma unroll
+      for (int g = 0; g < 4; ++g) {
+        uint4 u;
+        u.x = pack_bf16x2(__uint_as_float(r[8 * g + 0]) * inv, __uint_as_float(r[8 * g + 1]) * inv);
+        u.y = pack_bf16x2(__uint_as_float(r[8 * g + 2]) * inv, __uint_as_float(r[8 * g + 3]) * inv);
+        u.z = pack_bf16x2(__uint_as_float(r[8 * g + 4]) * inv, __uint_as_float(r[8 * g + 5]) * inv);
+        u.w = pack_bf16x2(__uint_as_float(r[8 * g + 6]) * inv, __uint_as_float(r[8 * g + 7]) * inv);
+        reinterpret_cast<uint4*>(orow + c * 32)[g] = u;
+      }
+    }
+    p.lse[((size_t)b * p.H + h) * p.S + q_global] = m_ref * p.scale + __logf(l_run);
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
 
 // =====================================================================================================
 // Backward.  One CTA per (kv block j, batch, head); loops over query blocks i (>= j when causal).
@@ -645,6 +905,16 @@ extern "C" int tepd_attn_fwd(const void* q, const void* k, const void* v, void* 
   AttnFwdParams p;
   p.O = o; p.lse = (float*)lse; p.B = B; p.H = H; p.S = S; p.causal = causal;
   p.scale = scale; p.scale_log2 = scale * 1.4426950408889634f;
+  if (fwd2_enabled() && S % 256 == 0) {   // experimental two-tile kernel
+    static bool cfg2 = false;
+    if (!cfg2) {
+      cudaError_t e = cudaFuncSetAttribute(attn_fwd2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, F2_SMEM);
+      if (e != cudaSuccess) return (int)e;
+      cfg2 = true;
+    }
+    return (int)tepd::launch(attn_fwd2_kernel, dim3((S / 256) * B * H), dim3(F2_THREADS), F2_SMEM, reinterpret_cast<cudaStream_t>(stream),
+                             tq, tk, tv, p);
+  }
   int grid = (S / BQ) * B * H;
   if (exp_poly_enabled())
     return (int)tepd::launch(attn_fwd_kernel<1>, dim3(grid), dim3(FWD_THREADS), FWD_SMEM, reinterpret_cast<cudaStream_t>(stream), tq, tk, tv, p);

@@ -513,6 +513,18 @@ def check_attn_poly():
     return out
 
 
+def check_attn_fwd2():
+    """Experimental two-query-tile forward (TEPDIST_ATTN_FWD2=1): numerics of check_attn_fwd on the S % 256 == 0 cases +
+    timing.  Own process: python tests/kernel_checks.py attn_fwd2"""
+    os.environ["TEPDIST_ATTN_FWD2"] = "1"
+    out = {"fwd": check_attn_fwd()}
+    try:
+        out["perf"] = check_attn_perf()
+    except Exception as e:  # noqa: BLE001
+        out["perf"] = repr(e)
+    return out
+
+
 def check_attn_bwd():
     from tepdist_b200 import ops
     from tepdist_b200.ops.attention import _ref_fwd
@@ -574,6 +586,7 @@ CHECKS = {
     "conv": check_conv,
     "attn_d48": check_attn_d48,
     "attn_poly": check_attn_poly,
+    "attn_fwd2": check_attn_fwd2,
     "gemm2": check_gemm2,
     "attn_perf": check_attn_perf,
 }
