@@ -27,6 +27,10 @@ from ..utils.init import init_tensor
 # tensor-parallel plans: run `linear -> all_reduce [-> + bias] [-> + residual]` as GEMM -> all-reduce over peer memory
 # (parallel/symm.py GemmAllReduce) instead of cuBLAS-free GEMM + NCCL.  Opt-in until validated on multi-GPU hardware.
 TP_FUSED = os.environ.get("TEPDIST_TP_FUSED", "0") == "1"
+# test hook: a factory (M, N, group, barrier) -> object with new_output() / __call__(x, w, out, bias, residual, b_mn) that
+# stands in for parallel.symm.GemmAllReduce, so the executor-side chain fusion can be exercised on CPU (gloo) where the
+# peer-memory kernels cannot run
+TP_FUSED_IMPL = None
 # weight gradients with a single producer are written with plain stores instead of fp32 atomics into a zero-filled slot
 WGRAD_PLAIN_STORE = os.environ.get("TEPDIST_WGRAD_STORE", "1") == "1"
 
@@ -305,7 +309,7 @@ class Executor:
         self.grad_accumulate = False   # True when gradients add up over micro-batches (pipeline stage workers)
         self._plan_store_init()
         self.tp_fuse: Dict[int, Dict[str, Any]] = {}
-        if TP_FUSED and self.comm_mode == "fused" and self.collective is not None and device.type == "cuda":
+        if TP_FUSED and self.collective is not None and ((self.comm_mode == "fused" and self.device.type == "cuda") or TP_FUSED_IMPL):
             self._plan_tp_fusion()
 
     @staticmethod
@@ -873,7 +877,10 @@ class Executor:
         self.tp_fuse = self.find_tp_chains(self.g, set(self.gelu_dual) | set(self.gelu_bwd_fuse) | set(self.alias_of))
         if not self.tp_fuse:
             return
-        from ..parallel.symm import GemmAllReduce, SymmBarrier
+        if TP_FUSED_IMPL is not None:
+            GemmAllReduce, SymmBarrier = TP_FUSED_IMPL, (lambda pg: None)
+        else:
+            from ..parallel.symm import GemmAllReduce, SymmBarrier
         self._tp_ops: Dict[Tuple[int, int, int], Any] = {}
         bar: Dict[int, Any] = {}
         for lid, info in self.tp_fuse.items():
@@ -885,8 +892,12 @@ class Executor:
                 self._tp_ops[key] = GemmAllReduce(info["M"], info["N"], pg, bar[info["level"]])
             info["op"] = self._tp_ops[key]
             info["out"] = info["op"].new_output()        # symmetric [M, N] bf16, written by every rank
+            # each chain node aliases its immediate predecessor (lin -> ar -> +bias -> +res): that is the dataflow the
+            # liveness pass saw, so every key is still in the environment when the next link looks it up
+            prev = lid
             for nid in info["chain"]:
-                self.alias_of[nid] = (lid, 0)
+                self.alias_of[nid] = (prev, 0)
+                prev = nid
 
     def _run_tp_fused(self, n: Node, ins: List[torch.Tensor]) -> List[torch.Tensor]:
         info = self.tp_fuse[n.id]

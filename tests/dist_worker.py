@@ -66,6 +66,38 @@ def case_state(strategy):
             "collectives": tr.plan_info.get("collectives")}
 
 
+class _EmulatedGemmAllReduce:
+    """CPU stand-in for parallel.symm.GemmAllReduce with the same call contract: row-parallel partial GEMM, sum over the
+    group, + bias + residual.  Lets the EXECUTOR side of the fused tensor-parallel path (chain detection, aliasing of the
+    all_reduce / add nodes, bias / residual plumbing, liveness) run under gloo; the peer-memory kernels are not involved."""
+    calls = 0
+
+    def __init__(self, M, N, group, barrier):
+        self.M, self.N, self.group = M, N, group
+
+    def new_output(self):
+        return torch.empty(self.M, self.N)
+
+    def __call__(self, x, w, out, bias=None, residual=None, b_mn=False, block_n=0):
+        type(self).calls += 1
+        y = x.float() @ (w.float() if b_mn else w.float().t())
+        dist.all_reduce(y, group=self.group)
+        if bias is not None:
+            y = y + bias.float()
+        if residual is not None:
+            y = y + residual.float().reshape(self.M, self.N)
+        out.copy_(y.to(out.dtype))
+        return out
+
+
+def case_tpfused(strategy):
+    from tepdist_b200.runtime import executor as ex_mod
+    ex_mod.TP_FUSED, ex_mod.TP_FUSED_IMPL = True, _EmulatedGemmAllReduce
+    res = case_gpt2("tp")
+    res["fused_calls"] = _EmulatedGemmAllReduce.calls
+    return res
+
+
 def case_mlp(strategy):
     """examples/smoke_testing-style 2-layer MLP; planner emits a DP shard on CPU/gloo world_size=2 (BASELINE config 1)."""
     from tepdist_b200.api import Trainer
@@ -95,7 +127,7 @@ def case_moe(strategy):
 if __name__ == "__main__":
     case, out = sys.argv[1], sys.argv[2]
     name, _, strat = case.partition(":")
-    res = {"gpt2": case_gpt2, "gpt2s": lambda st: case_gpt2(st, True), "gpt2b1": lambda st: case_gpt2(st, False, 1), "mlp": case_mlp, "moe": case_moe, "ckpt": case_ckpt, "state": case_state}[name](strat or "auto")
+    res = {"gpt2": case_gpt2, "gpt2s": lambda st: case_gpt2(st, True), "gpt2b1": lambda st: case_gpt2(st, False, 1), "mlp": case_mlp, "moe": case_moe, "ckpt": case_ckpt, "state": case_state, "tpfused": case_tpfused}[name](strat or "auto")
     if int(os.environ.get("RANK", "0")) == 0:
         json.dump(res, open(out, "w"))
     if dist.is_initialized():

@@ -126,3 +126,15 @@ def test_state_dict_is_whole_and_identical_on_every_rank(tmp_path):
     assert got["parallelism"].startswith("dp") and got["rank_spread"] == 0.0, got
     for a, b in zip(got["signature"], ref["signature"]):
         assert abs(a - b) <= 1e-3 * max(1.0, abs(b)), (got["signature"][:4], ref["signature"][:4])
+
+
+def test_executor_side_of_fused_tp_all_reduce_with_emulated_kernel(tmp_path):
+    """The executor's fusion of `linear -> all_reduce [-> + bias] [-> + residual]` chains (TEPDIST_TP_FUSED) with an EMULATED
+    GemmAllReduce (matmul + gloo all-reduce): chain aliasing, bias / residual plumbing and liveness must reproduce the
+    single-process losses.  This validates the executor logic only -- the CUDA kernels behind the real GemmAllReduce
+    (peer-mode-3 GEMM + slot_reduce with broadcast) have still never been executed."""
+    ref = _single("gpt2:auto")
+    got = _run("tpfused:tp", 2, tmp_path)
+    assert got["parallelism"].startswith("tp") and got["fused_calls"] > 0, got
+    for a, b in zip(got["losses"], ref["losses"]):
+        assert abs(a - b) <= 2e-4 * max(1.0, abs(b)), (got, ref)
