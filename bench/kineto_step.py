@@ -34,9 +34,12 @@ with profile(activities=[ProfilerActivity.CUDA]) as prof:
     torch.cuda.synchronize()
 agg = collections.defaultdict(lambda: [0, 0.0])
 for ka in prof.key_averages():
-    us = getattr(ka, "device_time_total", None)
+    # SELF device time: summing the inclusive field would count a kernel again under any parent range that got recorded
+    us = getattr(ka, "self_device_time_total", None)
     if us is None:
-        us = getattr(ka, "cuda_time_total", 0.0)
+        us = getattr(ka, "self_cuda_time_total", None)
+    if us is None:
+        us = getattr(ka, "device_time_total", 0.0)
     if not us:
         continue
     name = re.sub(r"^void ", "", ka.key)
