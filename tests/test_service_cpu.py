@@ -198,3 +198,30 @@ def test_two_rank_server_job_via_launcher(tmp_path):
         b = float(ref.step(feeds)[0])
         assert abs(a - b) <= 2e-4 * max(1.0, abs(b)), (losses, b)
     assert os.path.isdir(tmp_path / "ckpt_0_of_2" / "step_3") and os.path.isdir(tmp_path / "ckpt_1_of_2" / "step_3")
+
+
+def test_every_flag_override_key_exists_on_its_cxx_options_struct(monkeypatch, tmp_path):
+    """parallel/__init__.py applies config overrides with `if hasattr(o, k)`: a key that does not exist on the pybind options
+    object would be dropped silently and the flag would do nothing.  Set every flag and check every emitted key lands."""
+    from tepdist_b200 import _C, config
+    monkeypatch.chdir(tmp_path)
+    for k, v in {"VAR_MEM_LIMIT": "123", "COST_FACTOR": "2.0", "OPT_LEVEL": "1", "IGNORE_ANNOTATION": "false", "AUX_AFFINITY": "true",
+                 "FORWARD_SUB_GRAPH_NUM": "3", "ILP_TIME_LIMIT": "2", "UNBALANCED_RATIO": "0.2", "RULE_MODE": "true",
+                 "MICRO_NUM_LIMIT": "3", "EARLY_GA": "true", "BUFFER_SAVE": "false", "GROUP_SCHED_COUNT": "4"}.items():
+        monkeypatch.setenv(k, v)
+    monkeypatch.delenv("CONFIG_FILE", raising=False)
+    config.env(reload=True)
+    try:
+        for overrides, obj in ((config.spmd_overrides(), _C.SpmdOptions()), (config.auto_parallel_overrides(), _C.AutoParallelOptions()),
+                               (config.schedule_overrides(), _C.ScheduleOptions())):
+            assert overrides, type(obj).__name__
+            for k, v in overrides.items():
+                assert hasattr(obj, k), f"{type(obj).__name__} has no field '{k}': the flag would be ignored"
+                setattr(obj, k, v)
+                got = getattr(obj, k)
+                assert got == v or abs(float(got) - float(v)) < 1e-9, (k, got, v)
+        so = config.spmd_overrides()
+        assert so["var_mem_limit"] == 123.0 and so["opt_level"] == 1 and so["ilp_time_limit_s"] == 120.0 and so["aux_affinity"] is True
+    finally:
+        monkeypatch.undo()
+        config.env(reload=True)
