@@ -3,8 +3,12 @@
     python -m tepdist_b200.launch --cluster cluster.json --task-index 0
 
 cluster.json: {"master": {"ip": "...", "port": 2222, "gpu_ids": [0,1,2,3]}, "workers": [{"ip":..., "port":..., "gpu_ids": [...]}]}
-The entry selected by --task-index decides CUDA_VISIBLE_DEVICES and the gRPC endpoint; one process per listed GPU is
-spawned through torch.distributed.run (all entries must list the same number of GPUs, as in the reference).
+Run it once per entry (task index 0 = master, 1.. = workers): the entry decides CUDA_VISIBLE_DEVICES, one process per listed
+GPU is spawned through torch.distributed.run and ALL entries join one rendezvous hosted by the master entry, so the spec
+describes a single server job; global rank 0 (on the master entry) serves the gRPC endpoint master.ip:master.port (all
+entries must list the same number of GPUs, as in the reference).
+Tested with two entries on localhost (CPU / gloo).  Entries on different machines are untested; the peer-memory kernels rely
+on CUDA IPC and are intra-node only, so such a job would have to run with COMM_MODE=nccl.
 """
 from __future__ import annotations
 
@@ -48,9 +52,16 @@ def main(argv=None):
     else:
         env["CUDA_VISIBLE_DEVICES"] = ""
     n = len(e["gpu_ids"])
-    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={n}", "--master-addr", "127.0.0.1",
-           "--master-port", str(29400 + args.task_index), "-m", "tepdist_b200.launch", "--cluster", args.cluster,
-           "--task-index", str(args.task_index), "--platform", args.platform, "--strategy", args.strategy, "--serve-rank"]
+    entries = [spec["master"]] + list(spec.get("workers", []))
+    # ONE job over all entries (reference: launch_worker.sh is run once per task index and the servers find each other through
+    # the cluster spec): entry i is node i of a torchrun rendezvous hosted by the master entry; the gRPC endpoint is served
+    # by global rank 0 only, i.e. on the master entry.  `rdzv_port` may be given in the spec (default: master port + 1000).
+    master = spec["master"]
+    rdzv_port = int(spec.get("rdzv_port", int(master["port"]) + 1000))
+    cmd = [sys.executable, "-m", "torch.distributed.run", f"--nnodes={len(entries)}", f"--node-rank={args.task_index}",
+           f"--nproc-per-node={n}", "--master-addr", str(master["ip"]), "--master-port", str(rdzv_port),
+           "-m", "tepdist_b200.launch", "--cluster", args.cluster, "--task-index", str(args.task_index), "--platform", args.platform,
+           "--strategy", args.strategy, "--serve-rank", "--ip", str(master["ip"]), "--port", str(master["port"])]
     return subprocess.call(cmd, env=env)
 
 

@@ -225,3 +225,54 @@ def test_every_flag_override_key_exists_on_its_cxx_options_struct(monkeypatch, t
     finally:
         monkeypatch.undo()
         config.env(reload=True)
+
+
+def test_cluster_spec_with_a_worker_entry_forms_one_job(tmp_path):
+    """Two launcher invocations (task index 0 = master entry, 1 = worker entry, one process each) must join ONE server job:
+    the client sees world == 2 and trains with single-process parity."""
+    import socket
+    import subprocess
+    import sys
+    import time
+
+    def free_port():
+        s = socket.socket(); s.bind(("127.0.0.1", 0)); p = s.getsockname()[1]; s.close()
+        return p
+    port, rdzv = free_port(), free_port()
+    spec = tmp_path / "cluster.json"
+    spec.write_text(json.dumps({"master": {"ip": "127.0.0.1", "port": port, "gpu_ids": [0]},
+                                "workers": [{"ip": "127.0.0.1", "port": port + 1, "gpu_ids": [0]}], "rdzv_port": rdzv}))
+    env = dict(os.environ, OMP_NUM_THREADS="2", PYTHONPATH=os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    jobs = [subprocess.Popen([sys.executable, "-m", "tepdist_b200.launch", "--cluster", str(spec), "--task-index", str(i), "--platform", "cpu"],
+                             env=env, cwd=str(tmp_path), stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True) for i in (0, 1)]
+    try:
+        deadline = time.time() + 120
+        while time.time() < deadline:
+            try:
+                socket.create_connection(("127.0.0.1", port), timeout=0.5).close()
+                break
+            except OSError:
+                for j in jobs:
+                    assert j.poll() is None, j.stdout.read()[-3000:]
+                time.sleep(0.5)
+        cl = Client(f"127.0.0.1:{port}")
+        cfg = CONFIGS["tiny"]
+        g = build_gpt2_graph(cfg, batch=4)
+        r = cl.build_execution_plan(g, strategy="auto")
+        assert r["plan_info"]["world"] == 2, r
+        torch.manual_seed(0)
+        tok = torch.randint(0, cfg.n_vocab, (4, cfg.n_ctx), dtype=torch.int32)
+        feeds = {"tokens": tok, "labels": torch.roll(tok, -1, 1)}
+        losses = [cl.execute_plan(feeds)["loss"] for _ in range(2)]
+        cl.shutdown()
+        for j in jobs:
+            j.wait(timeout=60)
+    finally:
+        for j in jobs:
+            if j.poll() is None:
+                j.kill()
+    from tepdist_b200.runtime.executor import Executor
+    ref = Executor(g, torch.device("cpu"), use_cuda_graph=False)
+    for a in losses:
+        b = float(ref.step(feeds)[0])
+        assert abs(a - b) <= 2e-4 * max(1.0, abs(b)), (losses, b)
