@@ -79,7 +79,39 @@ def schedule_overrides() -> Dict[str, Any]:
     _take(o, "early_ga", "EARLY_GA", "bool")
     _take(o, "buffer_save", "BUFFER_SAVE", "bool")
     _take(o, "group_sched_count", "GROUP_SCHED_COUNT", "int")
+    _take(o, "reorder_send", "MULTI_REORDER", "bool")      # the scheduler's send hoisting (closest counterpart)
     return o
+
+
+def hw_profile():
+    """HW_PROFILE: cost-model constants of the planner / evaluator -- "b200" (default) or "reference_v100" (the reference's
+    15 TFLOP/s / 300 GB/s constants, evaluator.h:47-56)."""
+    from . import _C
+    name = env().get("HW_PROFILE") if is_set("HW_PROFILE") else "b200"
+    if name not in ("b200", "reference_v100"):
+        raise ValueError(f"HW_PROFILE={name!r}: expected 'b200' or 'reference_v100'")
+    return _C.HwProfile.reference_v100() if name == "reference_v100" else _C.HwProfile.b200()
+
+
+def pp_bandwidth() -> Optional[float]:
+    """PP_BANDWIDTH (GB/s) for pipeline send/recv cost in the task scheduler; None = the hardware profile's link bandwidth."""
+    return env().get_double("PP_BANDWIDTH") * 1e9 if is_set("PP_BANDWIDTH") else None
+
+
+def check_num_gradients(n_apply: int) -> None:
+    """NUM_GRADIENTS: the reference's sanity check that the client's training graph has the expected number of gradients."""
+    if is_set("NUM_GRADIENTS"):
+        want = int(env().get_int("NUM_GRADIENTS"))
+        if want > 0 and want != n_apply:
+            raise ValueError(f"NUM_GRADIENTS={want} but the training step updates {n_apply} variables")
+
+
+# Accepted for compatibility with the reference's config files but without effect here (and why):
+#   ILP_NUM_THREADS       the built-in simplex / branch-and-bound is single threaded
+#   ASYNC_SEND/ASYNC_RECV pipeline transfers are always isend / irecv on side streams; there is no synchronous mode
+#   DISABLE_BUFFER_ALIAS  variables are always updated in place in the flat store
+#   CLUSTER_SPEC, FRONTEND informational (set by the launcher)
+INERT_KEYS = ("ILP_NUM_THREADS", "ASYNC_SEND", "ASYNC_RECV", "DISABLE_BUFFER_ALIAS", "CLUSTER_SPEC", "FRONTEND")
 
 
 def resolve_strategy(strategy: str) -> str:

@@ -30,6 +30,8 @@ def plan_spmd(graph: Graph, num: int, strategy: str = "auto", options: Optional[
     if strategy == "tp":
         o.var_mem_limit = 1.0  # force every weight to be stored sharded -> tensor parallel
     from .. import config
+    o.hw = config.hw_profile()
+    config.check_num_gradients(sum(1 for n in graph.nodes if n.op.startswith("apply_")))
     for k, v in {**config.spmd_overrides(), **options}.items():   # flags (ServiceEnv) < explicit call arguments
         if hasattr(o, k):
             setattr(o, k, v)
@@ -131,6 +133,8 @@ def plan_pipeline(graph: Graph, world: int, stages: int, micro: int, options: Op
     if os.environ.get("TEPDIST_SPMD_RULE_MODE") == "1":
         ap.spmd_rule_mode = True
     from .. import config
+    ap.hw = config.hw_profile()
+    config.check_num_gradients(sum(1 for n in graph.nodes if n.op.startswith("apply_")))
     for k, v in {**config.auto_parallel_overrides(), **(options or {})}.items():
         if hasattr(ap, k):
             setattr(ap, k, v)
@@ -139,8 +143,10 @@ def plan_pipeline(graph: Graph, world: int, stages: int, micro: int, options: Op
     out = from_native(plan.graph)
     merge_client_attrs(out, graph)
     # task graph + 1F1B schedule (C++ runtime core)
-    hw = _C.HwProfile.b200()
+    hw = config.hw_profile()
     sp = _C.PipelineSpec()
+    if config.pp_bandwidth() is not None:
+        sp.p2p_bw = config.pp_bandwidth()
     sp.num_stages, sp.num_micro, sp.spmd = pr.stages, pr.micro, pr.spmd
     fl = list(plan.stage_plan.stage_flops) or [sum(plan.graph.node_flops(i) for i in range(plan.graph.num_nodes()))]
     sp.fwd_seconds = [f / 3.0 / hw.flops for f in fl]

@@ -3,6 +3,8 @@ import json
 import os
 import threading
 
+import pytest
+
 import torch
 
 from tepdist_b200.models.gpt2 import CONFIGS, build_gpt2_graph
@@ -276,3 +278,59 @@ def test_cluster_spec_with_a_worker_entry_forms_one_job(tmp_path):
     for a in losses:
         b = float(ref.step(feeds)[0])
         assert abs(a - b) <= 2e-4 * max(1.0, abs(b)), (losses, b)
+
+
+def test_newly_wired_flags_have_an_observable_effect_and_no_key_is_unaccounted(monkeypatch, tmp_path):
+    import re
+    from tepdist_b200 import config
+    from tepdist_b200.parallel import plan_pipeline, plan_spmd
+    monkeypatch.chdir(tmp_path)
+    for k in ("HW_PROFILE", "PP_BANDWIDTH", "NUM_GRADIENTS", "MULTI_REORDER", "CONFIG_FILE"):
+        monkeypatch.delenv(k, raising=False)
+    config.env(reload=True)
+    g = build_gpt2_graph(CONFIGS["tiny"], batch=8)
+    try:
+        # HW_PROFILE: the evaluator's estimate is computed with different constants
+        base = plan_pipeline(g, 4, 2, 4)[1]
+        assert config.hw_profile().name != "" and config.hw_profile().flops > 1e14
+        monkeypatch.setenv("HW_PROFILE", "reference_v100")
+        config.env(reload=True)
+        assert config.hw_profile().flops < 1e14
+        v100 = plan_pipeline(g, 4, 2, 4)[1]
+        # (strictly larger, not "N x": for this tiny model fixed per-stage terms dominate the scheduled makespan)
+        assert v100["makespan_est"] > base["makespan_est"], (base["makespan_est"], v100["makespan_est"])
+        monkeypatch.delenv("HW_PROFILE")
+        # PP_BANDWIDTH (GB/s): slower pipeline links stretch the scheduled makespan
+        monkeypatch.setenv("PP_BANDWIDTH", "0.001")
+        config.env(reload=True)
+        slow = plan_pipeline(g, 4, 2, 4)[1]
+        assert slow["makespan_est"] > base["makespan_est"], (base["makespan_est"], slow["makespan_est"])
+        monkeypatch.delenv("PP_BANDWIDTH")
+        # NUM_GRADIENTS: sanity check against the number of updated variables
+        n_apply = sum(1 for n in g.nodes if n.op.startswith("apply_"))
+        monkeypatch.setenv("NUM_GRADIENTS", str(n_apply))
+        config.env(reload=True)
+        plan_spmd(g, 2, "auto")
+        monkeypatch.setenv("NUM_GRADIENTS", str(n_apply + 1))
+        config.env(reload=True)
+        with pytest.raises(ValueError):
+            plan_spmd(g, 2, "auto")
+        monkeypatch.delenv("NUM_GRADIENTS")
+        # MULTI_REORDER reaches the scheduler options
+        monkeypatch.setenv("MULTI_REORDER", "false")
+        config.env(reload=True)
+        assert config.schedule_overrides() == {"reorder_send": False}
+        monkeypatch.delenv("MULTI_REORDER")
+        # every ServiceEnv key is either consumed by config.py / rpc/service.py or listed as inert, nothing in between
+        root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+        keys = set(re.findall(r"X\((\w+),", open(os.path.join(root, "tepdist_b200", "csrc", "service_env.h")).read()))
+        cfg_src = open(os.path.join(root, "tepdist_b200", "config.py")).read()
+        cfg_src = re.sub(r"# Accepted for compatibility.*?INERT_KEYS = \([^)]*\)", "", cfg_src, flags=re.S)   # the inert list itself
+        assert "INERT_KEYS" not in cfg_src
+        used_src = cfg_src + open(os.path.join(root, "tepdist_b200", "rpc", "service.py")).read()
+        consumed = {k for k in keys if re.search(r"""["']%s["']""" % k, used_src)}
+        assert consumed | set(config.INERT_KEYS) == keys, (sorted(keys - consumed - set(config.INERT_KEYS)), sorted(set(config.INERT_KEYS) - keys))
+        assert not (consumed & set(config.INERT_KEYS)), sorted(consumed & set(config.INERT_KEYS))
+    finally:
+        monkeypatch.undo()
+        config.env(reload=True)
