@@ -209,7 +209,7 @@ def test_every_flag_override_key_exists_on_its_cxx_options_struct(monkeypatch, t
     monkeypatch.chdir(tmp_path)
     for k, v in {"VAR_MEM_LIMIT": "123", "COST_FACTOR": "2.0", "OPT_LEVEL": "1", "IGNORE_ANNOTATION": "false", "AUX_AFFINITY": "true",
                  "FORWARD_SUB_GRAPH_NUM": "3", "ILP_TIME_LIMIT": "2", "UNBALANCED_RATIO": "0.2", "RULE_MODE": "true",
-                 "MICRO_NUM_LIMIT": "3", "EARLY_GA": "true", "BUFFER_SAVE": "false", "GROUP_SCHED_COUNT": "4"}.items():
+                 "MICRO_NUM_LIMIT": "3", "BUFFER_SAVE": "false", "MULTI_REORDER": "false"}.items():
         monkeypatch.setenv(k, v)
     monkeypatch.delenv("CONFIG_FILE", raising=False)
     config.env(reload=True)
