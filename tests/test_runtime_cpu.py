@@ -208,3 +208,45 @@ def test_tp_all_reduce_chains_are_found_for_fusion():
     # a data-parallel plan has nothing to fuse
     dp, _ = plan_spmd(build_gpt2_graph(cfg, batch=4), 2, "auto")
     assert Executor.find_tp_chains(dp) == {}
+
+
+def test_python_device_mesh_agrees_with_cxx_comm_dev_manager():
+    """The runtime addresses devices through parallel/mesh.py::DeviceMesh, a Python mirror of the C++ CommDevManager (which is
+    otherwise only unit-tested).  Two implementations of the same mixed-radix addressing must not drift: compare coordinates,
+    the communicator of every device at every level, rank-in-group and the inverse mapping for many meshes, with
+    time-multiplexed (share_dev) levels and non-trivial placement layouts -- including the shapes the runtime builds
+    (pure SPMD, dp x tp, micro x spmd x stage with the stage level outermost)."""
+    import itertools
+    from tepdist_b200.parallel.mesh import DeviceMesh
+    cases = []
+    for nums in ([2], [8], [2, 2], [4, 2], [2, 4], [2, 2, 2], [3, 2], [2, 3, 2]):
+        L = len(nums)
+        for shared in itertools.product([False, True], repeat=L):
+            if all(shared):
+                continue
+            for layout in itertools.permutations(range(L)):
+                cases.append((list(nums), list(shared), list(layout)))
+    cases.append(([4, 2, 2], [True, False, False], [2, 0, 1]))      # micro(shared) x spmd x stage, stage outermost (build_pipeline)
+    assert len(cases) >= 100
+    for nums, shared, layout in cases:
+        mgr = _C.CommDevManager()
+        mgr.build(nums, shared, layout)
+        world = mgr.total_devices()
+        for dev in range(world):
+            mesh = DeviceMesh(nums, shared, layout, rank=dev, world=world)
+            assert mesh.total_devices == world, (nums, shared, layout)
+            cc = mgr.coords(dev)
+            pc = mesh.coords()
+            for lvl in range(len(nums)):
+                if shared[lvl]:
+                    assert cc[lvl] == 0 and lvl not in pc, (nums, shared, layout, dev, lvl)
+                    continue
+                assert pc[lvl] == cc[lvl], (nums, shared, layout, dev, lvl, pc, cc)
+                assert mesh.group_ranks(lvl) == list(mgr.group_of(dev, lvl).devices), (nums, shared, layout, dev, lvl)
+                assert mesh.index_in_group(lvl) == mgr.rank_in_group(dev, lvl)
+            ids = [cc[l] for l in range(len(nums))]
+            assert mgr.global_device(ids) == dev == mesh.device_of({l: cc[l] for l in range(len(nums)) if not shared[l]})
+        for lvl in range(len(nums)):
+            if not shared[lvl]:
+                assert sorted(map(tuple, DeviceMesh(nums, shared, layout, rank=0, world=world).all_groups(lvl))) == \
+                    sorted(tuple(g.devices) for g in mgr.all_groups(lvl)), (nums, shared, layout, lvl)
