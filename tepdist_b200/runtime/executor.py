@@ -98,9 +98,9 @@ class VariableStore:
         self._state_nodes = [n for n in graph.nodes if n.op == "state"]
         for n in params:
             full = tuple(n.attrs.get("full_shape", self.shape[n.id]))
-            t = init_tensor(n.attrs.get("init", {"kind": "constant", "value": 0.0}), full, seed, n.name)
-            t = shard_of(t, n.attrs, self.coords)   # this rank's shard of the (identically seeded) full tensor
-            self.master_view(n.id).copy_(t.to(device))
+            # only this rank's shard is generated (bit-identical to slicing a fill of the full tensor, see utils/init.py)
+            t = init_tensor(n.attrs.get("init", {"kind": "constant", "value": 0.0}), full, seed, n.name, shard=(n.attrs, self.coords))
+            self.master_view(n.id).copy_(t.reshape(self.shape[n.id]).to(device))
         self.sync_compute()
 
     def grow(self, total: int) -> None:

@@ -250,3 +250,44 @@ def test_python_device_mesh_agrees_with_cxx_comm_dev_manager():
             if not shared[lvl]:
                 assert sorted(map(tuple, DeviceMesh(nums, shared, layout, rank=0, world=world).all_groups(lvl))) == \
                     sorted(tuple(g.devices) for g in mgr.all_groups(lvl)), (nums, shared, layout, lvl)
+
+
+def test_variable_store_fills_only_its_shard_bit_identically(monkeypatch):
+    """Sharded variables are generated shard-only (C++ SliceRuns + counter-based Philox) and must equal, bit for bit, the
+    slice of a full-tensor fill; and the full-size generator must not be touched for them (that is the point: the reference's
+    multi-billion-parameter configs do not fit a per-rank full copy)."""
+    import torch
+    from tepdist_b200.models.gpt2 import CONFIGS, build_gpt2_graph
+    from tepdist_b200.parallel import plan_spmd, plan_spmd_mesh
+    from tepdist_b200.runtime.executor import VariableStore, shard_of
+    from tepdist_b200.utils import init as init_mod
+    g = build_gpt2_graph(CONFIGS["tiny"], batch=4)
+    plans = [(plan_spmd(g, 2, "tp")[0], [{0: 0}, {0: 1}]),
+             (plan_spmd_mesh(g, [2, 2], ["tp", "dp"])[0], [{0: 0, 1: 0}, {0: 1, 1: 0}, {0: 0, 1: 1}, {0: 1, 1: 1}])]
+    for sharded, all_coords in plans:
+        n_sharded = sum(1 for n in sharded.params() if n.attrs.get("shard_dims"))
+        assert n_sharded > 4
+        for coords in all_coords:
+            full_calls = []
+            real_fill = init_mod.init_tensor
+
+            def spy(spec, shape, seed, name, shard=None):
+                if shard is None and spec.get("kind", "constant") != "constant":
+                    full_calls.append(name)
+                return real_fill(spec, shape, seed, name, shard)
+            monkeypatch.setattr("tepdist_b200.runtime.executor.init_tensor", spy)
+            # the shard branch has a fallback that regenerates the full tensor: make sure it is NOT what ran
+            full_sizes = []
+            real_philox = _C.philox_fill
+            monkeypatch.setattr(_C, "philox_fill", lambda kind, seed, off, n, *a: (full_sizes.append(n), real_philox(kind, seed, off, n, *a))[1])
+            st = VariableStore(sharded, torch.device("cpu"), seed=5, coords=coords)
+            monkeypatch.undo()
+            assert not full_calls, full_calls[:3]
+            whole = [int(np.prod(st.shape[n.id])) for n in sharded.params() if not n.attrs.get("shard_dims") and
+                     n.attrs.get("init", {}).get("kind", "constant") != "constant"]
+            assert sorted(full_sizes) == sorted(whole), "full-size Philox fills happened for sharded variables"
+            for n in sharded.params():
+                full = tuple(n.attrs.get("full_shape", st.shape[n.id]))
+                oracle = shard_of(init_mod.init_tensor(n.attrs.get("init", {"kind": "constant", "value": 0.0}), full, 5, n.name),
+                                  n.attrs, coords)
+                assert torch.equal(st.master_view(n.id), oracle.reshape(st.shape[n.id])), (n.name, coords)
