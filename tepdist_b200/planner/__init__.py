@@ -21,8 +21,10 @@ def to_native(g: Graph):
                     attrs["shard_num"] = int(s["num"])
                 continue
             attrs[k] = v
-        cg.add_node(n.op, [(v.node, v.idx) for v in n.inputs], [(list(t.shape), t.dtype) for t in n.outputs], attrs,
-                    n.name, n.group, n.backward)
+        nid = cg.add_node(n.op, [(v.node, v.idx) for v in n.inputs], [(list(t.shape), t.dtype) for t in n.outputs], attrs,
+                          n.name, n.group, n.backward)
+        if n.stage >= 0:      # (a planned graph converted back keeps its pipeline stages; from_native reads them)
+            cg.set_node_stage(n.id if nid is None else nid, n.stage)
     cg.set_outputs([(v.node, v.idx) for v in g.outputs])
     for var, v in g.updates.items():
         cg.set_update(var, v.node, v.idx)

@@ -344,3 +344,31 @@ def test_gpt2_1p5b_plans_quickly_in_every_mode():
     assert (pinfo["stages"], pinfo["micro"], pinfo["spmd"]) == (4, 8, 2) and len(tasks) >= 4
     assert 0.0 < pinfo["bubble_est"] < 0.5
     assert time.time() - t0 < 60.0
+
+
+def test_cxx_stage_decomposition_and_runtime_transfer_planning_agree():
+    """The pipeline runtime derives the values crossing each stage boundary itself (runtime/pipeline.py::plan_transfers); the
+    C++ StageDecompose pass computes the same thing but is not on the execution path.  They must agree -- per boundary, per
+    direction, multi-hop threading included -- on 2-stage, 4-stage and hybrid (pipeline x SPMD) plans.  Also pins that
+    planner.to_native keeps the pipeline stage of every node (it used to drop them, which made this comparison see 0 transfers)."""
+    import types
+    from tepdist_b200.models.gpt2 import CONFIGS, build_gpt2_graph
+    from tepdist_b200.parallel import plan_pipeline
+    from tepdist_b200.planner import from_native, to_native
+    from tepdist_b200.runtime.pipeline import StageWorker
+    g = build_gpt2_graph(CONFIGS["tiny"], batch=4)
+    for (world, S, M) in [(2, 2, 2), (4, 4, 4), (4, 2, 2)]:
+        g2, info, _ = plan_pipeline(g, world, S, M)
+        cg = to_native(g2)
+        assert [cg.node_stage(i) for i in range(cg.num_nodes())] == [n.stage for n in g2.nodes]
+        assert [n.stage for n in from_native(cg).nodes] == [n.stage for n in g2.nodes]
+        stub = types.SimpleNamespace(full=g2, S=info["stages"])
+        StageWorker.plan_transfers(stub)
+        py = {(v, b, b + 1) for b, vals in stub.xfer_fwd.items() for v in vals} | \
+             {(v, b + 1, b) for b, vals in stub.xfer_bwd.items() for v in vals}
+        d = _C.sync_free_decompose(cg, 0 if info["micro"] > 1 else -1)
+        cc = {(tuple(t.value), t.from_stage, t.to_stage) for t in _C.stage_decompose(cg, info["stages"], d)}
+        assert len(py) >= 2 * (info["stages"] - 1), (world, S, M, py)       # at least activation + gradient per boundary
+        assert py == cc, ((world, S, M), sorted(py - cc)[:4], sorted(cc - py)[:4])
+        for t in _C.stage_decompose(cg, info["stages"], _C.sync_free_decompose(cg, 0 if info["micro"] > 1 else -1)):
+            assert abs(t.to_stage - t.from_stage) == 1 and t.backward == (t.to_stage < t.from_stage) and t.bytes > 0
