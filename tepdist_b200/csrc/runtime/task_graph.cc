@@ -298,13 +298,19 @@ Schedule ScheduleTasks(TaskDAG* dagp, const PipelineSpec& sp, const ScheduleOpti
     }
   }
   if (opt.buffer_save) {
-    // recv buffers of the same (stage, direction) class rotate through `limit` slots
+    // recv buffers of the same (stage, direction) class rotate through a ring of `ring` slots (reference
+    // execution_plan.cc:203 BufferReuseAnalysis: ring size = GROUP_SCHED_COUNT, slot = occurrence index mod ring; a slot is
+    // "reused" from the (ring+1)-th receive of its class on and its receiver then has to wait for the previous user).
+    // group_sched_count == 0: size the ring by the in-flight limit, so that no receive ever finds its slot occupied.
+    const int ring = std::max(1, opt.group_sched_count > 0 ? opt.group_sched_count : limit);
     std::map<std::pair<int, bool>, int> counter;
     for (auto& kv : sch.device_tasks)
       for (int id : kv.second)
         if (dag.nodes[id].type == TaskType::kRecv) {
           auto key = std::make_pair(dag.nodes[id].stage, dag.nodes[id].backward);
-          dag.nodes[id].buffer_id = counter[key]++ % std::max(1, limit);
+          const int occ = counter[key]++;
+          dag.nodes[id].buffer_id = occ % ring;
+          dag.nodes[id].buffer_reused = occ >= ring;
         }
   }
   // GC plan per device

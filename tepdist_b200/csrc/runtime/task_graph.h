@@ -33,6 +33,7 @@ struct TaskNode {
   std::vector<int> parents, children;
   std::vector<int> mem_to_release;  // GC plan: task outputs that die after this task (D5 MakeTaskGraphGCPlan)
   int buffer_id = -1;     // recv-buffer reuse class slot (BUFFER_SAVE)
+  bool buffer_reused = false;  // slot had an earlier user this step: the receiver must wait for that user's release
   int def_ctx = -1;       // index of the DefContext this task executes
 };
 
@@ -66,7 +67,7 @@ struct ScheduleOptions {
   bool early_ga = false;         // EARLY_GA
   bool reorder_send = true;      // ReorderSend: hoist sends right after their producer
   bool buffer_save = true;       // BUFFER_SAVE: recv buffer reuse classes
-  int group_sched_count = 2;     // GROUP_SCHED_COUNT
+  int group_sched_count = 0;     // GROUP_SCHED_COUNT: receive-buffer ring size per class (0 => the in-flight limit)
 };
 struct Schedule {
   std::map<int, std::vector<int>> device_tasks;  // device -> ordered task ids

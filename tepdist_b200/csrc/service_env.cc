@@ -56,6 +56,11 @@ std::map<std::string, std::string> ParseFlatJson(const std::string& s) {
 
 std::vector<std::string> ServiceEnv::Load(const std::string& config_file) {
   std::vector<std::string> warnings;
+  // every load starts from the defaults: a key that was set by an earlier load (or Set) and is no longer in the file or
+  // the environment must not survive a reload
+#define X(name, def, help) values_[#name] = def;
+  TEPDIST_SERVICE_OPTIONS(X)
+#undef X
   std::string path = config_file;
   if (path.empty()) {
     const char* e = std::getenv("CONFIG_FILE");

@@ -159,8 +159,14 @@ def plan_pipeline(graph: Graph, world: int, stages: int, micro: int, options: Op
     for k, v in config.schedule_overrides().items():
         setattr(so, k, v)
     sch = _C.schedule_tasks(dag, sp, so)
+    def released_micros(t):
+        # GC plan of the scheduler (ComputeReleasePlan): the micro-batches whose LAST value on this device -- the output of
+        # the backward bundle -- dies after task t; the stage worker drops the whole micro-batch environment there
+        return [dag.nodes[r].micro for r in dag.nodes[t].mem_to_release
+                if dag.nodes[r].type == _C.TaskType.Output and dag.nodes[r].backward]
     tasks = {int(dev): [{"type": dag.nodes[t].type.name, "micro": dag.nodes[t].micro, "backward": dag.nodes[t].backward,
-                         "stage": dag.nodes[t].stage, "name": dag.nodes[t].name} for t in lst]
+                         "stage": dag.nodes[t].stage, "name": dag.nodes[t].name, "buffer_id": dag.nodes[t].buffer_id,
+                         "buffer_reused": dag.nodes[t].buffer_reused, "release": released_micros(t)} for t in lst]
              for dev, lst in sch.device_tasks.items()}
     info = {"stages": pr.stages, "micro": pr.micro, "spmd": pr.spmd, "log": plan.log, "eval": repr(plan.eval),
             "makespan_est": sch.makespan, "bubble_est": sch.bubble_ratio, "cut_bytes": plan.stage_plan.cut_bytes,

@@ -79,6 +79,10 @@ class StageWorker:
         self.fwd_nodes = [n for n in self.sub.nodes if not n.backward and n.op not in ("state", "boundary") and n.id not in ex.post_apply]
         self.bwd_nodes = [n for n in self.sub.nodes if n.backward and n.id not in ex.post_apply and not n.op.startswith("apply_")]
         self.env: Dict[int, Dict[Tuple[int, int], torch.Tensor]] = {}
+        # persistent receive buffers: (backward, value key, slot) -> (buffer, micro-batch that owns it this step)
+        self._ring: Dict[Tuple[bool, Tuple[int, int], int], Tuple[torch.Tensor, Optional[int]]] = {}
+        self.ring_stats = {"alloc": 0, "reuse": 0, "miss": 0}
+        self.pending_send: List[Any] = []
         self.loss_acc: Optional[torch.Tensor] = None
         # values the optimizer phase reads from the environment (gradients of variables that are not flat-bound, and
         # anything else the apply / post-apply nodes consume from the per-micro-batch part)
@@ -193,6 +197,8 @@ class StageWorker:
         self.exec._set_hyper()
         self.exec.store.grad.zero_()       # GAInit
         self.env.clear()
+        for rk, (buf, _) in list(self._ring.items()):   # every slot is free at a step boundary
+            self._ring[rk] = (buf, None)
         self.acc_env = {}
         self.loss_acc = None
 
@@ -208,7 +214,8 @@ class StageWorker:
                 self.loss_acc = t.clone() if self.loss_acc is None else self.loss_acc + t
 
     def release(self, m: int) -> None:
-        """GC: every activation of micro-batch m is dead (its backward ran and its gradients were sent)."""
+        """GC: every activation of micro-batch m is dead (its backward ran and its gradients were sent).  Called where
+        the task list says so (`release` entries, derived from the C++ GC plan -- reference D5 MakeTaskGraphGCPlan)."""
         self.env.pop(m, None)
         self._threaded.pop(m, None)
 
@@ -235,16 +242,44 @@ class StageWorker:
             works.append((dist.isend(t, peer), t))   # keep the payload alive until the send completes
         return works
 
-    def recv(self, m: int, backward: bool) -> List[Any]:
+    def _recv_buffer(self, m: int, backward: bool, key: Tuple[int, int], slot: int) -> torch.Tensor:
+        """Receive buffer for value `key` of micro-batch m.  slot >= 0 (BUFFER_SAVE): slot `slot` of the persistent ring of
+        this (direction, value) class, whose size the scheduler chose (GROUP_SCHED_COUNT, default the in-flight limit) --
+        reference execution_state.cc:219 recv_dapple_buffer_ptr_[key][buffer_id].  A slot whose previous micro-batch has
+        not been released yet cannot be waited for here (its release is later in THIS worker's task list; the reference
+        waits on the consumer's event from another thread), so such a receive gets a fresh buffer and is counted as a miss."""
+        from .executor import torch_dtype
+        dev = self.exec.device
+        tt = self.full.type_of(Value(*key))
+
+        def fresh():
+            return torch.empty(tt.shape, dtype=torch_dtype(tt.dtype, dev), device=dev)
+        if slot < 0:
+            return fresh()
+        rk = (backward, key, slot)
+        ent = self._ring.get(rk)
+        if ent is not None:
+            buf, owner = ent
+            if owner != m and (owner in self.env or owner in self._threaded):
+                self.ring_stats["miss"] += 1
+                return fresh()
+            for w, t in self.pending_send:          # a pass-through send may still be reading the slot
+                if t.data_ptr() == buf.data_ptr():
+                    w.wait()
+            self.ring_stats["reuse"] += 1
+        else:
+            buf = fresh()
+            self.ring_stats["alloc"] += 1
+        self._ring[rk] = (buf, m)
+        return buf
+
+    def recv(self, m: int, backward: bool, slot: int = -1) -> List[Any]:
         boundary = self.stage if backward else self.stage - 1
         peer = self.peer_next if backward else self.peer_prev
         env = self._micro_env(m)
         works = []
-        dev = self.exec.device
-        from .executor import torch_dtype
         for key in self._values_for(boundary, backward):
-            tt = self.full.type_of(Value(*key))
-            buf = torch.empty(tt.shape, dtype=torch_dtype(tt.dtype, dev), device=dev)
+            buf = self._recv_buffer(m, backward, key, slot)
             works.append(dist.irecv(buf, peer))
             if key in self.boundary_in:
                 env[(self.boundary_in[key], 0)] = buf
@@ -259,27 +294,25 @@ def run_pipeline_step(worker: StageWorker, task_list: List[Dict[str, Any]], feed
     worker.begin_step()
     worker._threaded = {}
     pending_recv: Dict[Tuple[int, bool], List[Any]] = {}
-    pending_send: List[Any] = []
+    pending_send = worker.pending_send = []
     for t in task_list:
         kind, m, bwd = t["type"], t["micro"], t["backward"]
         if kind == "Recv":
-            pending_recv[(m, bwd)] = worker.recv(m, bwd)
+            pending_recv[(m, bwd)] = worker.recv(m, bwd, t.get("buffer_id", -1))
         elif kind == "Input":
             for w in pending_recv.pop((m, bwd), []):
                 w.wait()
         elif kind == "Compute":
             (worker.backward if bwd else worker.forward)(m, feeds)
-            if bwd and worker.stage == 0:
-                worker.release(m)
         elif kind == "Send":
             pending_send += worker.send(m, bwd)   # (work, payload) pairs: payloads stay referenced until waited
-            if bwd:
-                worker.release(m)
         elif kind == "AG":
             for w, _ in pending_send:
                 w.wait()
-            pending_send = []
+            del pending_send[:]
             worker.apply(feeds)
+        for dead in t.get("release", ()):         # the scheduler's GC plan (task_graph.cc ComputeReleasePlan) decides
+            worker.release(dead)
     for w, _ in pending_send:
         w.wait()
     return None if worker.loss_acc is None else float(worker.loss_acc)

@@ -24,7 +24,13 @@ def case_gpt2(strategy, feed_shards=False, batch=4):
         per = 4 // tr.world
         tok, lab = tok[tr.rank * per:(tr.rank + 1) * per], lab[tr.rank * per:(tr.rank + 1) * per]
     losses = [tr.step({"tokens": tok, "labels": lab}) for _ in range(4)]   # global batch fed: ranks take their shards
-    return {"losses": losses, "parallelism": tr.plan_info.get("parallelism"), "collectives": tr.plan_info.get("collectives")}
+    res = {"losses": losses, "parallelism": tr.plan_info.get("parallelism"), "collectives": tr.plan_info.get("collectives")}
+    worker = getattr(tr.exec, "worker", None)
+    if worker is not None:   # pipeline: receive-buffer ring statistics of every stage worker
+        stats = [None] * tr.world
+        dist.all_gather_object(stats, dict(worker.ring_stats, stage=worker.stage))
+        res["ring"] = stats
+    return res
 
 
 def case_ckpt(strategy):

@@ -66,6 +66,26 @@ def test_long_context_plan_batch1_head_seq_all_to_all(tmp_path):
         assert abs(a - b) <= 2e-4 * max(1.0, abs(b)), (got, ref)
 
 
+def test_pipeline_receive_buffer_ring_follows_group_sched_count(tmp_path):
+    """BUFFER_SAVE / GROUP_SCHED_COUNT (reference execution_plan.cc:203 BufferReuseAnalysis, execution_state.cc:219): receives of
+    one (direction, value) class rotate through a persistent ring.  Default ring = in-flight limit: after the first step no
+    receive allocates.  GROUP_SCHED_COUNT=1 with several micro-batches in flight: occupied slots are detected and bypassed
+    (misses), never overwritten.  BUFFER_SAVE=0: no ring.  The losses must not depend on any of it."""
+    (tmp_path / "a").mkdir(); (tmp_path / "b").mkdir(); (tmp_path / "c").mkdir()
+    base = _run("gpt2:pp2m4", 2, tmp_path / "a")
+    one = _run("gpt2:pp2m4", 2, tmp_path / "b", {"GROUP_SCHED_COUNT": "1"})
+    off = _run("gpt2:pp2m4", 2, tmp_path / "c", {"BUFFER_SAVE": "0"})
+    assert base["parallelism"].startswith("pp2"), base
+    assert base["losses"] == one["losses"] == off["losses"], (base["losses"], one["losses"], off["losses"])
+    for st in base["ring"]:                      # 4 steps x 4 micro-batches per direction
+        assert st["miss"] == 0 and st["alloc"] > 0 and st["reuse"] >= 3 * st["alloc"], base["ring"]
+    assert all(st["alloc"] == st["reuse"] == st["miss"] == 0 for st in off["ring"]), off["ring"]
+    # stage 1 holds forward inputs of several micro-batches until their backward: a ring of one must report misses there
+    last = [st for st in one["ring"] if st["stage"] == 1][0]
+    assert last["miss"] > 0 and last["alloc"] >= 1, one["ring"]
+    assert sum(st["alloc"] for st in one["ring"]) < sum(st["alloc"] for st in base["ring"]), (one["ring"], base["ring"])
+
+
 def test_hybrid_pipeline_x_spmd_world4(tmp_path):
     """PP2 x SPMD2 x 2 micro-batches on 4 processes == single process (BASELINE config 5 in miniature)."""
     ref = _single("gpt2:auto")

@@ -154,6 +154,7 @@ def test_scheduler_reports_oom():
 # ------------------------------------------------------------------------------------------------ config
 def test_service_env_load_order(tmp_path, monkeypatch):
     env = _C.ServiceEnv.instance()
+    env.load(str(tmp_path / "none.json"))
     assert env.get_int("OPT_LEVEL") == 2 and env.get_bool("BUFFER_SAVE") and "VAR_MEM_LIMIT" in env.keys()
     cfg = tmp_path / "config.json"
     cfg.write_text(json.dumps({"NUM_STAGES": 4, "COST_FACTOR": 2.5, "RULE_MODE": True, "BOGUS": 1}))
@@ -162,9 +163,14 @@ def test_service_env_load_order(tmp_path, monkeypatch):
     assert env.get_int("NUM_STAGES") == 2 and env.get_double("COST_FACTOR") == 2.5 and env.get_bool("RULE_MODE")
     assert any("BOGUS" in w for w in warnings) and any("NUM_STAGES" in w for w in warnings)
     assert "NUM_STAGES=2" in env.dump()
-    env.set("NUM_STAGES", "0"); env.set("RULE_MODE", "false"); env.set("COST_FACTOR", "1.0")
     with pytest.raises(IndexError):
         env.get("NOPE")
+    # a reload starts from the defaults again: nothing of the previous load (or of set()) may linger
+    env.set("OPT_LEVEL", "0")
+    monkeypatch.delenv("NUM_STAGES")
+    env.load(str(tmp_path / "missing.json"))
+    assert env.get_int("NUM_STAGES") == 0 and env.get_double("COST_FACTOR") == 1.0 and not env.get_bool("RULE_MODE")
+    assert env.get_int("OPT_LEVEL") == 2
 
 
 def test_profile_and_plan_artifact_dumps(tmp_path):
