@@ -56,6 +56,10 @@ class Trainer:
         self._fake_feeds: Optional[Dict[str, torch.Tensor]] = None
         grad_sync = None
         self.plan_info: Dict[str, Any] = {"strategy": strategy, "world": self.world}
+        from .planner import liveness_optimize
+        graph, copies = liveness_optimize(graph)    # per-user copies of large convert(variable) results (B6)
+        if copies:
+            self.plan_info["liveness_copies"] = copies
         if self.world > 1:
             from .parallel import plan_and_build
             self.exec = plan_and_build(graph, self, strategy, comm_mode, use_cuda_graph, seed)

@@ -27,5 +27,7 @@ void BindPlanner(py::module_& m) {
   m.def("combine_gradient_collectives", [](Graph& g, int64_t bucket_bytes, int max_per_bucket) {
     return CombineGradientCollectives(&g, bucket_bytes, max_per_bucket);
   }, py::arg("graph"), py::arg("bucket_bytes"), py::arg("max_per_bucket") = 1 << 30);
+  m.def("liveness_optimize", [](Graph& g, int64_t min_bytes) { return LivenessOptimize(&g, min_bytes); }, py::arg("graph"),
+        py::arg("min_bytes") = 1 << 20);
   BindPlannerExtra(m);
 }

@@ -257,19 +257,69 @@ int CombineGradientCollectives(Graph* g, int64_t bucket_bytes, int max_per_bucke
   return any ? bucket + 1 : 0;
 }
 
-int LivenessOptimize(Graph* g) {
-  int dup = 0;
+int LivenessOptimize(Graph* g, int64_t min_bytes) {
+  // B6 (reference hlo_liveness_optimizer.cc:26-54): a converted copy of a variable that has several users -- typically one
+  // in the forward and one in the backward pass -- stays alive from its first to its last user, i.e. for most of the step.
+  // Give every user after the first its own copy of the convert, placed immediately in front of that user (same group /
+  // direction / stage as the user), so each copy lives only for the duration of one consumer and the run-time GC can
+  // free it right away.  Rebuilds the node list (ids change); returns the number of copies made.
   const int n0 = (int)g->nodes.size();
+  std::vector<char> target(n0, 0);
+  bool any = false;
+  for (int i = 0; i < n0; ++i) {
+    const Node& n = g->nodes[i];
+    if (n.op != "cast" || n.inputs.size() != 1 || g->nodes[n.inputs[0].node].op != "parameter") continue;
+    if (n.outputs[0].bytes() < min_bytes) continue;
+    std::set<int> user_nodes;
+    for (auto& u : g->users(ValueRef{i, 0})) user_nodes.insert(u.node);
+    if (user_nodes.size() > 1) target[i] = 1, any = true;
+  }
+  if (!any) return 0;
+  std::vector<Node> out;
+  out.reserve(n0 + 16);
+  std::vector<int> remap(n0, -1);
+  std::vector<char> used(n0, 0);
+  int dup = 0;
   for (int i = 0; i < n0; ++i) {
     Node n = g->nodes[i];
-    if (n.op != "cast" || g->nodes[n.inputs[0].node].op != "parameter") continue;
-    auto users = g->users(ValueRef{n.id, 0});
-    for (size_t u = 1; u < users.size(); ++u) {
-      // NOTE: appended clones keep topological validity only for users that come later; callers re-sort by stage.
-      (void)u;
-      ++dup;
+    std::map<int, int> local;   // target cast -> copy used by THIS node (several operands may read the same cast)
+    for (auto& v : n.inputs) {
+      const int src = v.node;
+      if (!target[src]) {
+        v.node = remap[src];
+        continue;
+      }
+      auto it = local.find(src);
+      if (it != local.end()) {
+        v.node = it->second;
+        continue;
+      }
+      int use = remap[src];
+      if (used[src]) {
+        Node c = g->nodes[src];
+        c.inputs[0].node = remap[c.inputs[0].node];
+        c.id = (int)out.size();
+        c.name += ".dup" + std::to_string(++dup);
+        c.group = n.group;
+        c.backward = n.backward;
+        c.stage = n.stage;
+        out.push_back(c);
+        use = c.id;
+      }
+      used[src] = 1;
+      local[src] = use;
+      v.node = use;
     }
+    n.id = (int)out.size();
+    remap[i] = n.id;
+    out.push_back(std::move(n));
   }
+  g->nodes = std::move(out);
+  for (auto& v : g->outputs) v.node = remap[v.node];
+  std::map<int, ValueRef> upd;
+  for (auto& kv : g->updates) upd[remap[kv.first]] = ValueRef{remap[kv.second.node], kv.second.idx};
+  g->updates = std::move(upd);
+  g->InvalidateUsers();
   return dup;
 }
 

@@ -35,6 +35,7 @@ Graph SpmdTransform(const Graph& g, const SpmdPlan& plan, int level, int num, Tr
 int CombineGradientCollectives(Graph* g, int64_t bucket_bytes, int max_per_bucket = 1 << 30);
 
 // B6: give every user of cast(parameter) its own cast so the casted copy is not live across the step.
-int LivenessOptimize(Graph* g);
+// B6: per-user copies of convert(parameter) results of at least `min_bytes` (see transform.cc).  Renumbers nodes.
+int LivenessOptimize(Graph* g, int64_t min_bytes = 1 << 20);
 
 }  // namespace tepdist

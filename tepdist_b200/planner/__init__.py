@@ -57,3 +57,27 @@ def merge_client_attrs(dst: Graph, src: Graph) -> None:
                 if isinstance(v, dict) and k not in n.attrs:
                     n.attrs[k] = v
     dst.meta.update({k: v for k, v in src.meta.items() if k not in dst.meta})
+
+
+def liveness_optimize(g: Graph, min_bytes: int = 1 << 20):
+    """B6 HloLivenessOptimizer (reference hlo_liveness_optimizer.cc:26-54; C++: transform.cc LivenessOptimize): give every user of
+    a large convert(parameter) its own copy of the convert, placed right in front of it, so a casted weight is not kept alive
+    from the forward to the backward pass.  Graphs built by models/ keep variables in compute precision in the flat store and
+    contain no such converts; graphs from the builder / torch.fx frontend with explicit mixed-precision casts do.
+    Returns (graph, number of copies); the input graph is returned unchanged when there is nothing to do."""
+    from .. import _C
+    users: Dict[int, set] = {}
+    for n in g.nodes:
+        for v in n.inputs:
+            src = g.nodes[v.node]
+            if src.op == "cast" and g.nodes[src.inputs[0].node].op == "parameter":
+                users.setdefault(src.id, set()).add(n.id)
+    if not any(len(u) > 1 for u in users.values()):
+        return g, 0
+    cg = to_native(g)
+    copies = int(_C.liveness_optimize(cg, int(min_bytes)))
+    if not copies:
+        return g, 0
+    out = from_native(cg)
+    merge_client_attrs(out, g)
+    return out, copies

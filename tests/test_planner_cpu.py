@@ -372,3 +372,59 @@ def test_cxx_stage_decomposition_and_runtime_transfer_planning_agree():
         assert py == cc, ((world, S, M), sorted(py - cc)[:4], sorted(cc - py)[:4])
         for t in _C.stage_decompose(cg, info["stages"], _C.sync_free_decompose(cg, 0 if info["micro"] > 1 else -1)):
             assert abs(t.to_stage - t.from_stage) == 1 and t.backward == (t.to_stage < t.from_stage) and t.bytes > 0
+
+
+def _mixed_precision_mlp(batch=8, d_in=16, d_h=32, d_out=4):
+    """f32 variables, explicit per-layer converts (the pattern B6 targets): each converted weight is read by the forward
+    matmul and again by the backward data gradient."""
+    from tepdist_b200.frontend.builder import GraphBuilder, build_training_step
+    b = GraphBuilder("mp_mlp", compute_dtype="f32")
+    x = b.input("x", (batch, d_in), "f32")
+    t = b.input("t", (batch, d_out), "f32")
+    w1 = b.parameter("w1", (d_in, d_h), {"kind": "normal", "std": 0.3})
+    w2 = b.parameter("w2", (d_h, d_out), {"kind": "normal", "std": 0.3})
+    h = b.tanh(b.matmul(b.cast(x, "bf16"), b.cast(w1, "bf16", name="w1c"), name="fc1"))
+    y = b.cast(b.matmul(h, b.cast(w2, "bf16", name="w2c"), name="fc2"), "f32")
+    d = b.sub(y, t)
+    loss = b.reduce_mean(b.mul(d, d), [0, 1], name="loss")
+    return build_training_step(b, loss, "sgd", lr=0.1)
+
+
+def test_liveness_optimizer_gives_each_user_its_own_convert_and_keeps_numerics():
+    """B6 (reference hlo_liveness_optimizer.cc:26-54).  After the pass every convert(variable) has exactly one user node, copies
+    sit directly in front of their user and inherit its direction, the live range of the forward copy ends in the forward
+    pass, node order stays topological, and training is bit-identical to the untouched graph."""
+    import torch
+    from tepdist_b200.planner import liveness_optimize
+    from tepdist_b200.runtime.executor import Executor
+    g = _mixed_precision_mlp()
+
+    def casts_of_params(gr):
+        return [n for n in gr.nodes if n.op == "cast" and gr.nodes[n.inputs[0].node].op == "parameter"]
+
+    def user_nodes(gr, nid):
+        return sorted({n.id for n in gr.nodes for v in n.inputs if v.node == nid})
+    before = casts_of_params(g)
+    assert before and any(len(user_nodes(g, c.id)) > 1 for c in before), "test graph lost the pattern the pass targets"
+    g2, copies = liveness_optimize(g, min_bytes=0)
+    assert copies >= 1 and len(g2.nodes) == len(g.nodes) + copies
+    first_bwd = min(n.id for n in g2.nodes if n.backward)
+    for c in casts_of_params(g2):
+        us = user_nodes(g2, c.id)
+        assert len(us) == 1, (c.name, us)
+        if ".dup" in c.name:
+            assert us[0] == c.id + 1 and c.backward == g2.nodes[us[0]].backward, (c.name, c.id, us)
+        else:
+            assert us[0] < first_bwd, "the original convert must die in the forward pass"
+    for n in g2.nodes:
+        assert all(v.node < n.id for v in n.inputs), n.name
+    assert {n.name for n in g2.nodes if n.op == "parameter"} == {n.name for n in g.nodes if n.op == "parameter"}
+    # a second application finds nothing left to do; the threshold protects small converts
+    assert liveness_optimize(g2, min_bytes=0)[1] == 0 and liveness_optimize(g, min_bytes=1 << 30)[1] == 0
+    torch.manual_seed(0)
+    feeds = {"x": torch.randn(8, 16), "t": torch.randn(8, 4)}
+    ea = Executor(g, torch.device("cpu"), seed=3, use_cuda_graph=False)
+    eb = Executor(g2, torch.device("cpu"), seed=3, use_cuda_graph=False)
+    la = [float(ea.step(feeds)[0]) for _ in range(4)]
+    lb = [float(eb.step(feeds)[0]) for _ in range(4)]
+    assert la == lb and la[-1] < la[0], (la, lb)
