@@ -577,15 +577,4 @@ def cast_f32_bf16(src: torch.Tensor, dst: torch.Tensor) -> None:
 
 
 # --------------------------------------------------------------------------------------------- attention
-def attention_ref(q, k, v, scale: float, causal: bool = True):
-    """fp32 reference: q,k,v [B, H, S, D]."""
-    s = torch.matmul(q.float(), k.float().transpose(-1, -2)) * scale
-    if causal:
-        S = q.shape[-2]
-        mask = torch.ones(S, S, dtype=torch.bool, device=q.device).tril()
-        s = s.masked_fill(~mask, float("-inf"))
-    p = torch.softmax(s, -1)
-    return torch.matmul(p, v.float())
-
-
 from .attention import attention_fwd, attention_bwd  # noqa: E402,F401

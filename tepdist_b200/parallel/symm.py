@@ -79,9 +79,6 @@ class SymmetricBuffer:
         t = t.view(dtype)
         return t if numel is None else t[:numel]
 
-    def shifted_ptr_array(self, offset_bytes: int):
-        return (ctypes.c_void_p * self.world)(*[p + offset_bytes for p in self.ptrs])
-
 
 class SymmBarrier:
     """Cross-rank barrier through peer memory (one tiny kernel; CUDA-graph capturable)."""

@@ -104,6 +104,31 @@ def case_tpfused(strategy):
     return res
 
 
+def case_manualdp(strategy):
+    """No planner: every rank runs the UNSHARDED graph on its half of the batch through a bare Executor, gradients are
+    averaged by the `grad_sync` hook (parallel/dp.py, bucketed all-reduce over the flat gradient buffer)."""
+    from tepdist_b200.api import init_distributed
+    from tepdist_b200.models.gpt2 import CONFIGS, build_gpt2_graph
+    from tepdist_b200.parallel.dp import make_nccl_grad_sync
+    from tepdist_b200.runtime.executor import Executor
+    ctx = init_distributed()
+    world, rank = ctx["world"], ctx["rank"]
+    cfg = CONFIGS["tiny"]
+    per = 4 // world
+    ex = Executor(build_gpt2_graph(cfg, batch=per), torch.device("cpu"), seed=0, use_cuda_graph=False,
+                  grad_sync=make_nccl_grad_sync(bucket_elems=10000) if world > 1 else None)
+    torch.manual_seed(0)
+    tok = torch.randint(0, cfg.n_vocab, (4, cfg.n_ctx), dtype=torch.int32)
+    lab = torch.roll(tok, -1, 1)
+    losses = []
+    for _ in range(4):
+        l = ex.step({"tokens": tok[rank * per:(rank + 1) * per], "labels": lab[rank * per:(rank + 1) * per]})[0].float().reshape(1)
+        if world > 1:
+            dist.all_reduce(l)
+        losses.append(float(l) / world)
+    return {"losses": losses, "parallelism": "manual-dp", "collectives": None}
+
+
 def case_mlp(strategy):
     """examples/smoke_testing-style 2-layer MLP; planner emits a DP shard on CPU/gloo world_size=2 (BASELINE config 1)."""
     from tepdist_b200.api import Trainer
@@ -133,7 +158,7 @@ def case_moe(strategy):
 if __name__ == "__main__":
     case, out = sys.argv[1], sys.argv[2]
     name, _, strat = case.partition(":")
-    res = {"gpt2": case_gpt2, "gpt2s": lambda st: case_gpt2(st, True), "gpt2b1": lambda st: case_gpt2(st, False, 1), "mlp": case_mlp, "moe": case_moe, "ckpt": case_ckpt, "state": case_state, "tpfused": case_tpfused}[name](strat or "auto")
+    res = {"gpt2": case_gpt2, "gpt2s": lambda st: case_gpt2(st, True), "gpt2b1": lambda st: case_gpt2(st, False, 1), "mlp": case_mlp, "moe": case_moe, "ckpt": case_ckpt, "state": case_state, "tpfused": case_tpfused, "manualdp": case_manualdp}[name](strat or "auto")
     if int(os.environ.get("RANK", "0")) == 0:
         json.dump(res, open(out, "w"))
     if dist.is_initialized():

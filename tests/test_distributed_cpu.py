@@ -66,6 +66,18 @@ def test_long_context_plan_batch1_head_seq_all_to_all(tmp_path):
         assert abs(a - b) <= 2e-4 * max(1.0, abs(b)), (got, ref)
 
 
+def test_manual_data_parallel_through_the_grad_sync_hook(tmp_path):
+    """The executor's `grad_sync` hook with the bucketed all-reduce of parallel/dp.py (the reference's plain DAPPLEAllReduce
+    semantics, no planner involved): two ranks on half batches == one process on the whole batch."""
+    sys.path.insert(0, HERE)
+    import dist_worker
+    ref = dist_worker.case_manualdp("auto")["losses"]
+    got = _run("manualdp:auto", 2, tmp_path)["losses"]
+    assert ref[-1] < ref[0]
+    for a, b in zip(got, ref):
+        assert abs(a - b) <= 2e-4 * max(1.0, abs(b)), (got, ref)
+
+
 def test_pipeline_receive_buffer_ring_follows_group_sched_count(tmp_path):
     """BUFFER_SAVE / GROUP_SCHED_COUNT (reference execution_plan.cc:203 BufferReuseAnalysis, execution_state.cc:219): receives of
     one (direction, value) class rotate through a persistent ring.  Default ring = in-flight limit: after the first step no

@@ -216,6 +216,24 @@ def test_user_annotation_is_honoured():
     assert plan2.stats.comm_bytes <= plan.stats.comm_bytes + 1e-6
 
 
+def test_replicate_annotation_is_honoured():
+    """xla_sharding.replicate equivalent (GraphBuilder.annotate_replicate): under memory pressure every weight would be stored
+    sharded; an annotated one must stay whole, and only with annotations enabled."""
+    from tepdist_b200.frontend.builder import GraphBuilder, build_training_step
+    b = GraphBuilder("repl", compute_dtype="f32")
+    x = b.input("x", (8, 16), "f32"); t = b.input("t", (8, 4), "f32")
+    w1 = b.parameter("w1", (16, 32), {"kind": "normal", "std": 0.3}); w2 = b.parameter("w2", (32, 4), {"kind": "normal", "std": 0.3})
+    b.annotate_replicate(w1)
+    d = b.sub(b.matmul(b.tanh(b.matmul(x, w1, name="fc1")), w2, name="fc2"), t)
+    g = build_training_step(b, b.reduce_mean(b.mul(d, d), [0, 1], name="loss"), "sgd", lr=0.1)
+    def stored(cg, plan, name):
+        return plan.choice[[i for i in range(cg.num_nodes()) if cg.node_name(i) == name][0]].outs[0]
+    cg, plan = _plan(g, 2, ignore_annotation=False, var_mem_limit=1.0)
+    assert stored(cg, plan, "w1").is_glue() and not stored(cg, plan, "w2").is_glue()
+    cg2, plan2 = _plan(g, 2, ignore_annotation=True, var_mem_limit=1.0)
+    assert not stored(cg2, plan2, "w1").is_glue()
+
+
 def test_rule_mode_propagates_batch_split():
     g = build_mlp_graph(batch=8)
     for n in g.nodes:
