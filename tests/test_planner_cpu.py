@@ -392,6 +392,48 @@ def test_cxx_stage_decomposition_and_runtime_transfer_planning_agree():
             assert abs(t.to_stage - t.from_stage) == 1 and t.backward == (t.to_stage < t.from_stage) and t.bytes > 0
 
 
+def test_cxx_def_contexts_match_the_phases_the_stage_workers_execute():
+    """B3 / C2 cross-check.  The stage workers split their slice of the program into a per-micro-batch forward list, a per-micro-
+    batch backward list and a once-per-step optimizer phase themselves (runtime/pipeline.py); the C++ SyncFreeDecompose +
+    StageDecompose passes build the DefContext tree CG_SLICE_<s>_F / _B / AG_SLICE_<s> for the same purpose but are not on the
+    execution path.  Node for node they must describe the same phases (the runtime additionally lists the source nodes --
+    variables, constants -- in its forward list; C++ keeps those in ENTRY)."""
+    import torch
+    from tepdist_b200.models.gpt2 import CONFIGS, build_gpt2_graph
+    from tepdist_b200.parallel import plan_pipeline
+    from tepdist_b200.runtime.pipeline import StageWorker
+    g = build_gpt2_graph(CONFIGS["tiny"], batch=4)
+    for (world, S, M) in [(2, 2, 2), (4, 4, 4)]:
+        g2, info, _ = plan_pipeline(g, world, S, M)
+        assert info["spmd"] == 1
+        ml = 0 if info["micro"] > 1 else -1
+        workers = [StageWorker(g2, s, S, M, ml, torch.device("cpu"), None, None) for s in range(S)]
+        full = workers[0].full                       # (micro-level collectives elided: ids differ from g2)
+        cg = to_native(full)
+        d = _C.sync_free_decompose(cg, ml)
+        _C.stage_decompose(cg, S, d)
+        cxx = {(c.kind, c.stage): set(c.nodes) for c in d.ctx if c.stage >= 0}
+        assert set(cxx) == {(k, s) for k in ("stage_fwd", "stage_bwd", "stage_ag") for s in range(S)}
+        sources = ("parameter", "state", "constant")     # (the samples -- `input` nodes -- are per-micro-batch on both sides)
+        covered = set()
+        for s, w in enumerate(workers):
+            inv = {v: k for k, v in w.idmap.items()}
+            fwd = {inv[n.id] for n in w.fwd_nodes if n.id in inv and n.op not in sources}
+            bwd = {inv[n.id] for n in w.bwd_nodes if n.id in inv}
+            opt = {inv[n.id] for n in w.sub.nodes if n.id in w.exec.post_apply or n.op.startswith("apply_")}
+            for kind, mine in (("stage_fwd", fwd), ("stage_bwd", bwd), ("stage_ag", opt)):
+                theirs = cxx[(kind, s)]
+                assert mine == theirs, ((world, S, M), s, kind, [full.nodes[i].name for i in sorted(mine ^ theirs)][:6])
+                assert mine and not (mine & covered)
+                covered |= mine
+        # together the contexts cover every non-source node exactly once
+        rest = {n.id for n in full.nodes if n.op not in sources}
+        # (the only source inside a phase is the backward pass's seed constant dloss = 1)
+        assert covered >= rest and all(full.nodes[i].op == "constant" and full.nodes[i].backward for i in covered - rest)
+        per_micro = {c.name: c.per_micro_batch for c in d.ctx}
+        assert per_micro["CG"] and not per_micro["AG"]
+
+
 def _mixed_precision_mlp(batch=8, d_in=16, d_h=32, d_out=4):
     """f32 variables, explicit per-layer converts (the pattern B6 targets): each converted weight is read by the forward
     matmul and again by the backward data gradient."""
