@@ -78,6 +78,7 @@ def schedule_overrides() -> Dict[str, Any]:
     _take(o, "micro_num_limit", "MICRO_NUM_LIMIT", "int")
     _take(o, "buffer_save", "BUFFER_SAVE", "bool")
     _take(o, "reorder_send", "MULTI_REORDER", "bool")      # the scheduler's send hoisting (closest counterpart)
+    _take(o, "early_ga", "EARLY_GA", "bool")               # default here: true (GA is where a micro-batch is released)
     _take(o, "group_sched_count", "GROUP_SCHED_COUNT", "int")   # receive-buffer ring size per class (execution_plan.cc:203)
     return o
 
@@ -106,13 +107,11 @@ def check_num_gradients(n_apply: int) -> None:
 
 
 # Accepted for compatibility with the reference's config files but without effect here (and why):
-#   EARLY_GA              the list scheduler ALWAYS gives gradient-accumulation tasks top priority (task_graph.cc, class 0):
-#                         there is no "late GA" mode for the flag to switch off
 #   ILP_NUM_THREADS       the built-in simplex / branch-and-bound is single threaded
 #   ASYNC_SEND/ASYNC_RECV pipeline transfers are always isend / irecv on side streams; there is no synchronous mode
 #   DISABLE_BUFFER_ALIAS  variables are always updated in place in the flat store
 #   CLUSTER_SPEC, FRONTEND informational (set by the launcher)
-INERT_KEYS = ("EARLY_GA", "ILP_NUM_THREADS", "ASYNC_SEND", "ASYNC_RECV", "DISABLE_BUFFER_ALIAS", "CLUSTER_SPEC", "FRONTEND")
+INERT_KEYS = ("ILP_NUM_THREADS", "ASYNC_SEND", "ASYNC_RECV", "DISABLE_BUFFER_ALIAS", "CLUSTER_SPEC", "FRONTEND")
 
 
 def resolve_strategy(strategy: str) -> str:

@@ -219,12 +219,13 @@ Schedule ScheduleTasks(TaskDAG* dagp, const PipelineSpec& sp, const ScheduleOpti
   }
   std::vector<double> ready_time(N, 0.0);
   int done = 0;
-  // priority key (smaller = earlier): GA, then backward compute bundles, then forward (by micro id), sends/recvs
-  // follow their producers, AG last
+  // priority key (smaller = earlier): GA (EARLY_GA, the default here; reference task_scheduler.cc:1367 ReorderGA hoists GA
+  // next to its micro-batch's output only when the flag is set), then backward compute bundles, then forward (by micro
+  // id), sends/recvs follow their producers, AG last
   auto prio = [&](const TaskNode& t) {
     int cls;
     switch (t.type) {
-      case TaskType::kGA: cls = 0; break;
+      case TaskType::kGA: cls = opt.early_ga ? 0 : 4; break;   // lazy: behind any ready compute of the device
       case TaskType::kGAInit: case TaskType::kSplit: cls = 0; break;
       case TaskType::kSend: cls = 1; break;
       case TaskType::kRecv: cls = 1; break;

@@ -64,7 +64,7 @@ TaskDAG BuildPipelineTaskDAG(const PipelineSpec& spec);
 
 struct ScheduleOptions {
   int micro_num_limit = 0;       // MICRO_NUM_LIMIT: forward micro-batches in flight per stage (0 => num_stages => 1F1B)
-  bool early_ga = false;         // EARLY_GA
+  bool early_ga = true;          // EARLY_GA: accumulate (and release the micro-batch) right after its backward; false: when idle
   bool reorder_send = true;      // ReorderSend: hoist sends right after their producer
   bool buffer_save = true;       // BUFFER_SAVE: recv buffer reuse classes
   int group_sched_count = 0;     // GROUP_SCHED_COUNT: receive-buffer ring size per class (0 => the in-flight limit)

@@ -29,7 +29,7 @@ namespace tepdist {
   X(ILP_TIME_LIMIT, "1", "minutes per exact solve before the greedy fallback")                     \
   X(ILP_NUM_THREADS, "1", "solver threads")                                                        \
   X(BUFFER_SAVE, "true", "reuse pipeline receive buffers")                                         \
-  X(EARLY_GA, "false", "schedule gradient accumulation as early as possible")                      \
+  X(EARLY_GA, "true", "schedule gradient accumulation right after each backward (reference default: false)")                      \
   X(ASYNC_RECV, "true", "receive on a side stream")                                                \
   X(ASYNC_SEND, "true", "send on a side stream")                                                   \
   X(MULTI_REORDER, "true", "iterate send/GA reordering to a fixpoint")                             \

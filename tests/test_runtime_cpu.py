@@ -144,6 +144,54 @@ def test_scheduler_is_1f1b_and_bounds_memory():
     assert any(n.buffer_id >= 0 for n in dag.nodes if n.type == _C.TaskType.Recv)
 
 
+def test_scheduler_early_ga_and_receive_ring_options():
+    """EARLY_GA (reference task_scheduler.cc:1367 ReorderGA; default on here): gradient accumulation of micro-batch m directly
+    follows its backward bundle, so the micro-batch is released at once; off: GA yields to any ready compute and ends up later
+    in the device order, at no cost in makespan.  GROUP_SCHED_COUNT: ring size of the receive-buffer slots per class."""
+    S_, M = 4, 8
+    sp = _spec(S_, M)
+
+    def run(**kw):
+        o = _C.ScheduleOptions()
+        for k, v in kw.items():
+            setattr(o, k, v)
+        dag = _C.build_pipeline_task_dag(sp)
+        return dag, _C.schedule_tasks(dag, sp, o)
+
+    def ga_lag(dag, sch):
+        lag = 0
+        for tasks in sch.device_tasks.values():
+            names = [dag.nodes[t].name for t in tasks]
+            for i, nme in enumerate(names):
+                if nme.startswith("ga."):
+                    s, m = nme.split(".")[1:]
+                    lag += i - names.index(f"out.B.{s}.{m}")
+        return lag
+    assert _C.ScheduleOptions().early_ga and _C.ScheduleOptions().group_sched_count == 0
+    d1, early = run()
+    d2, lazy = run(early_ga=False)
+    n_ga = S_ * M
+    assert ga_lag(d1, early) <= 2 * n_ga            # right behind out.B (a hoisted Send may sit in between)
+    assert ga_lag(d2, lazy) > ga_lag(d1, early)
+    assert abs(lazy.makespan - early.makespan) < 1e-4
+    for dag, sch in ((d1, early), (d2, lazy)):      # both are valid orders of the DAG
+        pos = {t: (dev, i) for dev, tasks in sch.device_tasks.items() for i, t in enumerate(tasks)}
+        assert all(pos[n.id][1] < pos[c][1] for n in dag.nodes for c in n.children if pos[n.id][0] == pos[c][0])
+    # receive ring: default = in-flight limit (= number of stages); explicit count is honoured; `buffer_reused` marks the
+    # receives that take over a slot from an earlier receive of their class
+    for count, ring in ((0, S_), (2, 2), (3, 3)):
+        dag, _ = run(group_sched_count=count)
+        for st in range(S_):
+            for bwd in (False, True):
+                rc = sorted((n.micro, n.buffer_id, n.buffer_reused) for n in dag.nodes
+                            if n.type == _C.TaskType.Recv and n.stage == st and n.backward == bwd)
+                if rc:
+                    assert {b for _, b, _ in rc} == set(range(min(ring, M)))
+                    assert sum(1 for _, _, r in rc if not r) == min(ring, M) and len(rc) == M
+    dag, _ = run(buffer_save=False)
+    assert all(n.buffer_id < 0 for n in dag.nodes)
+
+
 def test_scheduler_reports_oom():
     sp = _spec(2, 4)
     sp.mem_limit = 1.5e9
