@@ -19,10 +19,12 @@ def main():
     ap.add_argument("--train-steps", type=int, default=10)
     ap.add_argument("--strategy", default="auto")
     ap.add_argument("--comm", default="fused", choices=["fused", "nccl"])
+    ap.add_argument("--optimizer", default="adamw", choices=["adam", "adamw", "adafactor", "lamb", "sm3", "momentum", "sgd"],
+                    help='reference: "opt_name" adam | adafactor in examples/GPT2/*.json')
     a = ap.parse_args()
     cfg = CONFIGS[a.model]
     world = int(os.environ.get("WORLD_SIZE", "1"))
-    g = build_gpt2_graph(cfg, batch=a.batch * world)
+    g = build_gpt2_graph(cfg, batch=a.batch * world, optimizer=a.optimizer)
     tr = Trainer(g, strategy=a.strategy, comm_mode=a.comm)
     gen = torch.Generator().manual_seed(0)
     tok = torch.randint(0, cfg.n_vocab, (a.batch * world, cfg.n_ctx), generator=gen, dtype=torch.int32)

@@ -18,11 +18,13 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--strategy", default="auto")
     ap.add_argument("--tiny", action="store_true")
+    ap.add_argument("--optimizer", default="adamw", choices=["adamw", "adafactor", "lamb", "sm3"],
+                    help='reference: "optimizer" in examples/gpt_moe/pretrain_moe.json')
     a = ap.parse_args()
     cfg = MoEConfig(batch=a.batch)
     if a.tiny:
         cfg = MoEConfig(n_layer=2, hidden=128, ffn=256, n_head=2, experts=4, capacity=64, groups=4, seq=128, batch=a.batch, vocab=1000)
-    tr = Trainer(build_gpt_moe_graph(cfg), strategy=a.strategy, use_cuda_graph=False)
+    tr = Trainer(build_gpt_moe_graph(cfg, optimizer=a.optimizer), strategy=a.strategy, use_cuda_graph=False)
     gen = torch.Generator().manual_seed(0)
     tok = torch.randint(0, cfg.vocab, (cfg.batch, cfg.seq), generator=gen, dtype=torch.int32)
     feeds = {"tokens": tok, "labels": torch.roll(tok, -1, 1)}

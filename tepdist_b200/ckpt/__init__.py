@@ -43,6 +43,8 @@ class CheckpointManager:
         manifest: Dict[str, Any] = {"global_step": global_step, "rank": self.rank, "world": self.world, "vars": {},
                                     "step_count": executor.step_count, "extra": extra or {}}
         tensors: Dict[str, torch.Tensor] = {}
+        # variables whose first / second moments live in the flat m / v buffers (others keep them as separate slot tensors)
+        flat_moments = {n.attrs.get("slot_of") for n in getattr(st, "_state_nodes", []) if st.m is not None and st._flat_slot(n)}
         for pid in st.order:
             n = g.nodes[pid]
             name = st.names[pid]
@@ -51,10 +53,23 @@ class CheckpointManager:
                 "shard_shape": list(st.shape[pid]), "full_shape": list(n.attrs.get("full_shape", st.shape[pid])),
                 "shard_dims": list(n.attrs.get("shard_dims", [])), "shard_nums": list(n.attrs.get("shard_nums", [])),
                 "shard_levels": list(n.attrs.get("shard_levels", [])), "coords": {str(k): v for k, v in executor.coords.items()},
+                "flat_moments": pid in flat_moments,     # <name>/m, <name>/v below have the variable's shard shape
             }
-            if st.m is not None:
+            if pid in flat_moments:
                 tensors[name + "/m"] = st._view(st.m, pid).detach().cpu().reshape(-1).clone()
                 tensors[name + "/v"] = st._view(st.v, pid).detach().cpu().reshape(-1).clone()
+        # optimizer slots outside the flat m / v buffers (momentum, Adafactor row / column statistics, SM3 accumulators,
+        # separately stored shards of m / v): same shard description as a variable, under their own name
+        manifest["slots"] = {}
+        for n in getattr(st, "_state_nodes", []):
+            if n.id in st.state and not st._flat_slot(n):
+                t = st.state[n.id]
+                tensors[n.name] = t.detach().cpu().reshape(-1).clone()
+                manifest["slots"][n.name] = {
+                    "shard_shape": list(t.shape), "full_shape": list(n.attrs.get("full_shape", t.shape)),
+                    "shard_dims": list(n.attrs.get("shard_dims", [])), "shard_nums": list(n.attrs.get("shard_nums", [])),
+                    "shard_levels": list(n.attrs.get("shard_levels", [])), "coords": {str(k): v for k, v in executor.coords.items()},
+                }
         torch.save(tensors, os.path.join(tmp, "shards.pt"))
         json.dump(manifest, open(os.path.join(tmp, "manifest.json"), "w"))
         if os.path.exists(prefix):
@@ -97,9 +112,12 @@ class CheckpointManager:
         for pid in st.order:
             name = st.names[pid]
             st.master_view(pid).copy_(tensors[name].reshape(st.shape[pid]).to(st.device))
-            if st.m is not None and name + "/m" in tensors:
+            if st.m is not None and name + "/m" in tensors and manifest["vars"][name].get("flat_moments", True):
                 st._view(st.m, pid).copy_(tensors[name + "/m"].reshape(st.shape[pid]).to(st.device))
                 st._view(st.v, pid).copy_(tensors[name + "/v"].reshape(st.shape[pid]).to(st.device))
+        for n in getattr(st, "_state_nodes", []):
+            if n.name in manifest.get("slots", {}) and n.name in tensors and n.id in st.state and not st._flat_slot(n):
+                st.state[n.id].copy_(tensors[n.name].reshape(st.state[n.id].shape).to(st.device))
         st.sync_compute()
         executor.step_count = int(manifest.get("step_count", step))
         return step
@@ -136,12 +154,14 @@ class CheckpointManager:
             raise FileNotFoundError(f"step {step}: found {len(writers)} of {world_w} writer shards")
         st, g = executor.store, executor.g
 
-        def assemble(name: str, suffix: str) -> Optional[torch.Tensor]:
+        def assemble(name: str, suffix: str, section: str = "vars") -> Optional[torch.Tensor]:
             full = None
             for man, tens in writers:
-                meta = man["vars"].get(name)
+                meta = man.get(section, {}).get(name)
                 if meta is None or name + suffix not in tens:
                     return None
+                if suffix and not meta.get("flat_moments", True):
+                    return None      # (the writer kept its moments as separately sharded slots: see the "slots" section)
                 if full is None:
                     full = torch.zeros(meta["full_shape"], dtype=torch.float32)
                 view = full
@@ -165,6 +185,19 @@ class CheckpointManager:
                         raise KeyError(f"variable {name} missing from checkpoint step {step}")
                     continue
                 dst.copy_(shard_of(full, attrs, executor.coords).reshape(dst.shape).to(st.device))
+        # optimizer slots by name.  Writer and reader may disagree on WHERE a moment lives (flat m / v buffers vs a separately
+        # sharded slot tensor, e.g. LAMB under a ZeRO plan vs one process), so every reader slot looks in the writers' "slots"
+        # section first and, for <var>/m and <var>/v, in the variable section second.
+        if hasattr(st, "ensure_slots"):
+            st.ensure_slots()
+        for n in getattr(st, "_state_nodes", []):
+            if n.id not in st.state:
+                continue
+            full = assemble(n.name, "", "slots")
+            if full is None and (n.name.endswith("/m") or n.name.endswith("/v")):
+                full = assemble(n.name[:-2], n.name[-2:])
+            if full is not None:
+                st.state[n.id].copy_(shard_of(full, n.attrs, executor.coords).reshape(st.state[n.id].shape).to(st.device))
         st.sync_compute()
         executor.step_count = int(writers[0][0].get("step_count", step))
         return step

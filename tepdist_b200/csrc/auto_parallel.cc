@@ -307,7 +307,7 @@ int64_t BatchOf(const Graph& g) {
 double VarBytes(const Graph& g) {
   double b = 0;
   bool adam = false;
-  for (auto& n : g.nodes) adam |= n.op == "apply_adamw";
+  for (auto& n : g.nodes) adam |= n.op == "apply_adamw" || n.op == "apply_lamb";
   for (auto& n : g.nodes)
     if (n.op == "parameter") b += (double)n.outputs[0].numel() * (adam ? 18.0 : 10.0);
   return b;

@@ -357,6 +357,44 @@ void ApplyRule(Ctx& c) {  // optimizer update: every operand / output shares the
   c.add_glue();
 }
 
+// Optimizers with reduced-shape slots.  The variable (and gradient, and full-shaped slots) may be split on any dim d; a slot
+// that keeps dim d is split along with it, a slot that has reduced dim d away is replicated -- its reduction over d is then
+// completed across the shards by the executor (an all-reduce of a small vector), which is why these stay single nodes
+// instead of being expanded into primitive reductions.
+void AdafactorRule(Ctx& c) {
+  // (p, g, vr [..., R], vc [..., C]) for p [..., R, C], or (p, g, vf) un-factored
+  const TensorType& p = c.in(0);
+  const int r = p.rank();
+  const bool factored = c.nin() == 4;
+  for (int d = 0; d < r; ++d) {
+    if (!c.divisible(p, d)) continue;
+    std::vector<DS> st;
+    if (!factored) st = {c.S(d)};
+    else st = {d == r - 1 ? c.G() : c.S(d), d == r - 2 ? c.G() : (d == r - 1 ? c.S(r - 2) : c.S(d))};
+    std::vector<DS> ins = {c.S(d), c.S(d)}, outs = {c.S(d)};
+    for (auto& x : st) ins.push_back(x), outs.push_back(x);
+    c.add(ins, outs, "dim" + std::to_string(d));
+  }
+  c.add_glue();
+}
+void Sm3Rule(Ctx& c) {
+  // (p, g, acc_0 [d0], ..., acc_{r-1} [d_{r-1}] [, mom]) for rank >= 2; (p, g, acc [, mom]) with a full-shaped acc otherwise
+  const TensorType& p = c.in(0);
+  const int r = p.rank();
+  for (int d = 0; d < r; ++d) {
+    if (!c.divisible(p, d)) continue;
+    std::vector<DS> ins = {c.S(d), c.S(d)}, outs = {c.S(d)};
+    for (int i = 2; i < c.nin(); ++i) {
+      const TensorType& t = c.in(i);
+      DS x = t.rank() == r ? c.S(d) : (i - 2 == d ? c.S(0) : c.G());   // full-shaped (acc of a vector, momentum) or per-dim
+      ins.push_back(x);
+      outs.push_back(x);
+    }
+    c.add(ins, outs, "dim" + std::to_string(d));
+  }
+  c.add_glue();
+}
+
 }  // namespace
 
 std::vector<Candidate> EnumerateCandidates(const Graph& g, const Node& n, int num, const RuleOptions& opt) {
@@ -397,7 +435,9 @@ std::vector<Candidate> EnumerateCandidates(const Graph& g, const Node& n, int nu
   else if (op == "batchnorm") BatchNormRule(c);
   else if (op == "batchnorm_bwd") BatchNormBwdRule(c);
   else if (op == "maxpool2d" || op == "maxpool2d_bwd" || op == "global_avgpool" || op == "global_avgpool_bwd") Pool4dRule(c);
-  else if (op == "apply_adamw" || op == "apply_sgd") ApplyRule(c);
+  else if (op == "apply_adamw" || op == "apply_sgd" || op == "apply_momentum" || op == "apply_lamb") ApplyRule(c);
+  else if (op == "apply_adafactor") AdafactorRule(c);
+  else if (op == "apply_sm3") Sm3Rule(c);
   else if (op == "moe_dispatch_mask" || op == "moe_dispatch_mask_bwd") {  // gating is independent per token group
     bool ok = true;
     for (int i = 0; i < c.nin(); ++i) ok &= c.divisible(c.in(i), 0);

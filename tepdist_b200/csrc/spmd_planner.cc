@@ -34,6 +34,7 @@ struct Problem {
   std::vector<std::vector<double>> node_cost;
   std::vector<Edge> edges;
   std::vector<std::vector<int>> edges_of;  // node -> edge indices
+  std::set<int> forced;                    // nodes whose candidates were narrowed by the memory plan or a user annotation
 };
 
 void BuildProblem(Problem& p, SpmdStats* stats) {
@@ -43,7 +44,7 @@ void BuildProblem(Problem& p, SpmdStats* stats) {
   p.cands.resize(N);
   p.node_cost.resize(N);
   p.edges_of.assign(N, {});
-  const bool adam = std::any_of(g.nodes.begin(), g.nodes.end(), [](const Node& n) { return n.op == "apply_adamw"; });
+  const bool adam = std::any_of(g.nodes.begin(), g.nodes.end(), [](const Node& n) { return n.op == "apply_adamw" || n.op == "apply_lamb"; });
 
   // ---- memory plan (reference SplitPlanByMemCost): which variables MUST be stored sharded
   double var_bytes = 0;
@@ -77,6 +78,7 @@ void BuildProblem(Problem& p, SpmdStats* stats) {
   for (auto& n : g.nodes) {
     RuleOptions ro;
     ro.save_variable_mem = IsComputeIntensive(n.op) && mem_save_groups.count(n.group) > 0;
+    if (ro.save_variable_mem) p.forced.insert(n.id);   // (candidates restricted to the ones that keep the weight split)
     auto c = EnumerateCandidates(g, n, opt.num, ro);
     // user annotations (xla_sharding.split / replicate equivalents)
     if (!opt.ignore_annotation && n.has("shard_dim")) {
@@ -85,13 +87,17 @@ void BuildProblem(Problem& p, SpmdStats* stats) {
       std::vector<Candidate> f;
       for (auto& x : c)
         if (!x.outs.empty() && x.outs[0] == want) f.push_back(x);
-      if (!f.empty()) c = f;
+      if (!f.empty()) c = f, p.forced.insert(n.id);   // (a user annotation outranks a mirror pin as well)
     }
-    if (must_split.count(n.id) || (n.op == "state" && must_split.count((int)n.attr_i("slot_of", -1)))) {
+    // (slots with a reduced shape -- Adafactor row / column statistics, SM3 per-dim accumulators -- follow the apply node's
+    // candidate instead: whether they can be split depends on WHICH dim of the variable is split)
+    const bool full_slot = n.op == "state" && n.attr_i("slot_of", -1) >= 0 &&
+                           n.outputs[0].dims == g.nodes[(int)n.attr_i("slot_of", -1)].outputs[0].dims;
+    if (must_split.count(n.id) || (full_slot && must_split.count((int)n.attr_i("slot_of", -1)))) {
       std::vector<Candidate> f;
       for (auto& x : c)
         if (!x.outs[0].is_glue()) f.push_back(x);
-      if (!f.empty()) c = f;
+      if (!f.empty()) c = f, p.forced.insert(n.id);
     }
     p.cands[n.id] = c;
     auto& nc = p.node_cost[n.id];
@@ -124,7 +130,8 @@ void BuildProblem(Problem& p, SpmdStats* stats) {
     p.edges.push_back({kv.second.node, kv.second.idx, kv.first, -1, (double)g.type(kv.second).bytes()});
   if (opt.aux_affinity)
     for (auto& n : g.nodes)  // Var/Aux affinity: slots follow their variable (zero-byte edge with infinite mismatch)
-      if (n.op == "state" && n.has("slot_of")) p.edges.push_back({(int)n.attr_i("slot_of"), 0, n.id, -2, 0.0});
+      if (n.op == "state" && n.has("slot_of") && n.outputs[0].dims == g.nodes[(int)n.attr_i("slot_of")].outputs[0].dims)
+        p.edges.push_back({(int)n.attr_i("slot_of"), 0, n.id, -2, 0.0});   // (reduced-shape slots: see rules.cc AdafactorRule)
   for (int e = 0; e < (int)p.edges.size(); ++e) {
     p.edges_of[p.edges[e].prod].push_back(e);
     p.edges_of[p.edges[e].cons].push_back(e);
@@ -136,6 +143,11 @@ double EdgeCost(const Problem& p, const Edge& e, const Candidate& cp, const Cand
   const DimStrategy& from = cp.outs[e.out_idx];
   if (e.operand == -2) return from == cc.outs[0] ? 0.0 : kInfCost;  // aux affinity
   const DimStrategy& to = e.operand >= 0 ? cc.ins[e.operand] : cc.outs[0];
+  // an optimizer slot that is stored split is consumed by its update in exactly that layout: gathering it (or moving it to
+  // another split) every step would also leave the update's result in a layout the storage does not have
+  if (e.operand >= 2 && from.is_split() && !(from == to) && p.g.nodes[e.prod].op == "state" &&
+      p.g.nodes[e.cons].op.rfind("apply_", 0) == 0)
+    return kInfCost;
   return ReshardCost(from, to, e.bytes, p.opt.num, p.opt.cost_factor);
 }
 
@@ -163,7 +175,17 @@ SubSolution SolveSub(const Problem& p, const std::vector<int>& members, const st
       opt_index[m].push_back((int)i);
       c.push_back(p.node_cost[nid][i]);
     }
-    if (c.empty()) return sol;  // infeasible pin
+    if (c.empty() && pin != pin_member.end() && p.forced.count(nid)) {
+      // the pin cannot be honoured: a variable that MUST be stored split whose value leaves the sub-graph, for which the
+      // mirror layout is Glue: leave the node free -- the consumer in the other sub-graph then pays the re-layout, which
+      // the final accounting derives from the actual choices anyway.  (This used to make the whole sub-graph infeasible and
+      // silently fall back to candidate 0 for all of its nodes.)
+      for (size_t i = 0; i < p.cands[nid].size(); ++i) {
+        opt_index[m].push_back((int)i);
+        c.push_back(p.node_cost[nid][i]);
+      }
+    }
+    if (c.empty()) return sol;
     local[nid] = q.AddNode(c);
   }
   std::set<int> seen_edges;
@@ -411,8 +433,12 @@ SpmdPlan PlanSpmdLevel(Graph* gp, const SpmdOptions& opt) {
       if (dp[S - 1][i].cost < dp[S - 1][it].cost) it = i;
     for (int k = S - 1; k >= 0; --k) {
       const Cell& c = dp[k][it];
-      if (c.sol.choice.size() == members[k].size())
+      if (c.sol.choice.size() == members[k].size()) {
         for (size_t m = 0; m < members[k].size(); ++m) chosen[members[k][m]] = c.sol.choice[m];
+      } else {
+        ++plan.stats.infeasible_subgraphs;   // its nodes keep their first candidate; never silent (see SpmdStats)
+        plan.stats.optimal = false;
+      }
       it = std::max(0, c.prev);
     }
   }

@@ -446,27 +446,64 @@ def backward(b: GraphBuilder, loss: Value) -> Dict[int, Value]:
     return out
 
 
+OPTIMIZERS = ("sgd", "momentum", "adam", "adamw", "lamb", "adafactor", "sm3")
+
+
 def apply_optimizer(b: GraphBuilder, grads: Dict[int, Value], kind: str = "adamw", **hp) -> None:
-    """Appends one apply node per variable (+ its slot `state` nodes) and registers in/out aliases."""
+    """Appends one apply node per variable (+ its slot `state` nodes) and registers in/out aliases.
+
+    Optimizers of the reference's example suites (examples/GPT2/optimizers.py, examples/gpt_moe/optimizers/*):
+      sgd        p -= lr g
+      momentum   v = mu v + g; p -= lr v                                        (hp: lr, momentum)
+      adam       AdamW with weight_decay = 0
+      adamw      decoupled weight decay on variables with decay=True            (hp: lr, beta1, beta2, eps, weight_decay)
+      lamb       Adam direction (+ wd p), scaled per variable by |p| / |update| (lamb_weight_decay_optimizer.py:121-154)
+      adafactor  factored second moments for rank >= 2 (row / column means), update clipping by RMS, step scaled by
+                 RMS(p); decay rate 1 - t^-0.8                                   (adafactor.py:127-139 defaults)
+      sm3        one accumulator per dimension, nu = min_i acc_i + g^2, acc_i = max over the other dims (sm3.py:92-165)
+    Slots of the non-elementwise optimizers have reduced shapes; the planner's rules (rules.cc AdafactorRule / Sm3Rule) lay
+    them out consistently with the variable and the executor completes their reductions across shards."""
     g = b.g
+    if kind not in OPTIMIZERS:
+        raise ValueError(f"optimizer '{kind}': expected one of {OPTIMIZERS}")
+    if kind == "adam":
+        kind, hp = "adamw", {**hp, "weight_decay": 0.0}
     g.meta["optimizer"] = {"kind": kind, **hp}
+    zeros = {"kind": "constant", "value": 0.0}
+
+    def slot(pn, suffix, shape):
+        return g.add("state", [], [TensorType(tuple(shape), "f32")], {"init": zeros, "slot_of": pn.id}, pn.name + suffix, pn.group)
+
+    def finish(pn, op, slots, attrs):
+        n = g.add(op, [pn.out(), gv] + [s_.out() for s_ in slots], [TensorType(pn.outputs[0].shape, pn.outputs[0].dtype)] +
+                  [TensorType(s_.outputs[0].shape, "f32") for s_ in slots], attrs, pn.name + "/apply", pn.group, True)
+        g.updates[pn.id] = n.out(0)
+        for i, s_ in enumerate(slots):
+            g.updates[s_.id] = n.out(i + 1)
+
     for pid, gv in grads.items():
         pn = g.nodes[pid]
-        pt = TensorType(pn.outputs[0].shape, pn.outputs[0].dtype)
+        shape = tuple(pn.outputs[0].shape)
+        decay = pn.attrs.get("decay", True)
         if kind == "sgd":
-            n = g.add("apply_sgd", [pn.out(), gv], [pt], dict(hp), pn.name + "/apply", pn.group, True)
-            g.updates[pid] = n.out()
+            finish(pn, "apply_sgd", [], dict(hp))
+        elif kind == "momentum":
+            finish(pn, "apply_momentum", [slot(pn, "/mom", shape)], dict(hp))
         elif kind == "adamw":
-            st = TensorType(pt.shape, "f32")
-            m = g.add("state", [], [st], {"init": {"kind": "constant", "value": 0.0}, "slot_of": pid}, pn.name + "/m", pn.group)
-            v = g.add("state", [], [st], {"init": {"kind": "constant", "value": 0.0}, "slot_of": pid}, pn.name + "/v", pn.group)
-            n = g.add("apply_adamw", [pn.out(), gv, m.out(), v.out()], [pt, st, st],
-                      {**hp, "decay": pn.attrs.get("decay", True)}, pn.name + "/apply", pn.group, True)
-            g.updates[pid] = n.out(0)
-            g.updates[m.id] = n.out(1)
-            g.updates[v.id] = n.out(2)
-        else:
-            raise ValueError(kind)
+            finish(pn, "apply_adamw", [slot(pn, "/m", shape), slot(pn, "/v", shape)], {**hp, "decay": decay})
+        elif kind == "lamb":
+            finish(pn, "apply_lamb", [slot(pn, "/m", shape), slot(pn, "/v", shape)], {**hp, "decay": decay})
+        elif kind == "adafactor":
+            if len(shape) >= 2 and hp.get("factored", True):
+                slots = [slot(pn, "/vr", shape[:-1]), slot(pn, "/vc", shape[:-2] + shape[-1:])]
+            else:
+                slots = [slot(pn, "/vf", shape)]
+            finish(pn, "apply_adafactor", slots, {**hp, "decay": decay})
+        elif kind == "sm3":
+            slots = [slot(pn, f"/acc{i}", (d,)) for i, d in enumerate(shape)] if len(shape) > 1 else [slot(pn, "/acc", shape)]
+            if hp.get("momentum", 0.0) > 0:
+                slots.append(slot(pn, "/mom", shape))
+            finish(pn, "apply_sm3", slots, dict(hp))
 
 
 def build_training_step(b: GraphBuilder, loss: Value, optimizer: str = "adamw", **hp) -> Graph:

@@ -44,6 +44,9 @@ CONFIGS = {
     "117M": GPT2Config(12, 768, 12, 1024, 50257, 4, name="gpt2-117M"),
     "345M": GPT2Config(24, 1024, 16, 1024, 50257, 4, name="gpt2-345M"),
     "1.5B": GPT2Config(48, 1600, 25, 1024, 50257, 4, name="gpt2-1.5B"),
+    # examples/GPT2/PrettyBig.json, 175B.json (structural fields as given there, including the 175B file's n_ctx = 12288)
+    "PrettyBig": GPT2Config(25, 1024, 16, 1024, 50257, 4, lr=2.5e-4, name="gpt2-PrettyBig"),
+    "175B": GPT2Config(96, 12288, 96, 12288, 50257, 4, lr=2.5e-4, name="gpt2-175B"),
     "tiny": GPT2Config(2, 128, 2, 128, 1000, 2, name="gpt2-tiny"),
 }
 

@@ -63,7 +63,7 @@ def build_moe_ffn_graph(groups=8, tokens_per_group=64, model=64, hidden=256, exp
     return build_training_step(b, loss, "adamw", lr=1e-3, beta1=0.9, beta2=0.999, eps=1e-8, weight_decay=0.0)
 
 
-def build_gpt_moe_graph(cfg: MoEConfig, batch: int | None = None) -> Graph:
+def build_gpt_moe_graph(cfg: MoEConfig, batch: int | None = None, optimizer: str = "adamw") -> Graph:
     """Full GPT-MoE: every other layer's MLP is an MoE FFN (pretrain_moe.json: 8 layers, hidden 768, 16 heads x 48,
     8 experts, capacity 256, 8 local groups, seq 1024)."""
     B = batch or cfg.batch
@@ -101,4 +101,5 @@ def build_gpt_moe_graph(cfg: MoEConfig, batch: int | None = None) -> Graph:
         gf = b.parameter("ln_f/g", (C,), const(1.0)); bf2 = b.parameter("ln_f/b", (C,), const(0.0))
         logits = b.linear(b.layernorm(x, gf, bf2, name="ln_f"), b.parameter("output", (Vp, C), nrm(0.02)), name="lm_head")
         loss = b.softmax_xent(logits, labels, vocab=cfg.vocab, name="loss")
-    return build_training_step(b, loss, "adamw", lr=1e-4, beta1=0.9, beta2=0.999, eps=1e-8, weight_decay=0.01)
+    # (pretrain_moe.json "optimizer": adamw | adafactor | lamb | sm3 -- frontend/builder.py OPTIMIZERS)
+    return build_training_step(b, loss, optimizer, lr=1e-4, beta1=0.9, beta2=0.999, eps=1e-8, weight_decay=0.01)

@@ -534,7 +534,7 @@ def adamw_step(p: torch.Tensor, g: torch.Tensor, m: torch.Tensor, v: torch.Tenso
     n = p.numel()
     if not p.is_cuda:
         if hyper is not None:
-            lr, bc1, bc2, grad_scale = (float(x) for x in hyper.tolist())
+            lr, bc1, bc2, grad_scale = (float(x) for x in hyper[:4].tolist())
         gr = g * grad_scale
         m.mul_(beta1).add_(gr, alpha=1 - beta1)
         v.mul_(beta2).addcmul_(gr, gr, value=1 - beta2)

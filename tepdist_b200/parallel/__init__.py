@@ -38,6 +38,10 @@ def plan_spmd(graph: Graph, num: int, strategy: str = "auto", options: Optional[
     # "dp" / "rule": annotation-driven rule mode (reference FastSpmdStrategy, RULE_MODE=true): the batch split on the
     # sample inputs is propagated through the graph, variables stay replicated, gradients come out partial.
     plan = _C.plan_spmd_by_rules(cg, o) if strategy in ("rule", "dp") else _C.plan_spmd_level(cg, o)
+    if plan.stats.infeasible_subgraphs:
+        import warnings
+        warnings.warn(f"SPMD planner: {plan.stats.infeasible_subgraphs} sub-graph(s) without a consistent assignment; their nodes keep "
+                      "their first candidate (the plan is valid but not optimised there)")
     cg.split_nums = [num]
     cg.share_dev = [False]
     tg, st = _C.spmd_transform(cg, plan, 0, num)
@@ -58,7 +62,7 @@ def plan_spmd(graph: Graph, num: int, strategy: str = "auto", options: Optional[
         tags[kind] = tags.get(kind, 0) + 1
     info = {"comm_info": st.comm_info(), "comm_bytes": plan.stats.comm_bytes, "solve_seconds": plan.stats.solve_seconds,
             "subgraphs": plan.stats.num_subgraphs, "distinct_subgraphs": plan.stats.distinct_subgraphs,
-            "collectives": dict(plan.stats.collectives), "dot_strategies": tags, "grad_buckets": buckets,
+            "collectives": dict(plan.stats.collectives), "dot_strategies": tags, "grad_buckets": buckets, "infeasible_subgraphs": plan.stats.infeasible_subgraphs,
             "strategies_txt": _C.dump_strategies(cg, plan)}
     return out, info
 

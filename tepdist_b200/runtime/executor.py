@@ -37,6 +37,7 @@ WGRAD_PLAIN_STORE = os.environ.get("TEPDIST_WGRAD_STORE", "1") == "1"
 _TORCH_DTYPE = {"bf16": torch.bfloat16, "f16": torch.float16, "f32": torch.float32, "i32": torch.int32,
                 "i64": torch.int64, "bool": torch.bool}
 _ALIGN = 128  # elements; keeps every variable slice 16-B aligned in every dtype
+FLAT_APPLY = ("apply_adamw", "apply_sgd")   # elementwise updates: may run over the flat buffers / fused sharded-optimizer kernels
 
 
 def torch_dtype(name: str, device: torch.device) -> torch.dtype:
@@ -127,20 +128,24 @@ class VariableStore:
         self.grad, self.compute = g, c
         self.symm_grad, self.symm_param = gb, pb
 
+    def _flat_slot(self, n) -> bool:
+        """First / second moment slots with their variable's shape live in the flat m / v buffers."""
+        pid = n.attrs.get("slot_of")
+        return (pid in self.shape and self.shape[pid] == tuple(n.outputs[0].shape)
+                and (n.name.endswith("/m") or n.name.endswith("/v")))
+
     def ensure_slots(self) -> None:
-        if self.m is None:
+        if self.m is None and any(self._flat_slot(n) for n in self._state_nodes):
             self.m = torch.zeros_like(self.master)
             self.v = torch.zeros_like(self.master)
         for n in self._state_nodes:
             if n.id in self.state:
                 continue
-            pid = n.attrs.get("slot_of")
-            shape = tuple(n.outputs[0].shape)
-            if pid in self.shape and self.shape[pid] == shape:
+            if self._flat_slot(n):
                 buf = self.m if n.name.endswith("/m") else self.v
-                self.state[n.id] = self._view(buf, pid)
-            else:
-                self.state[n.id] = torch.zeros(shape, dtype=torch.float32, device=self.device)
+                self.state[n.id] = self._view(buf, n.attrs.get("slot_of"))
+            else:   # sharded slots of a replicated variable, reduced-shape slots (Adafactor, SM3), momentum
+                self.state[n.id] = torch.zeros(tuple(n.outputs[0].shape), dtype=torch.float32, device=self.device)
 
     def _view(self, buf: torch.Tensor, pid: int) -> torch.Tensor:
         o = self.offset[pid]
@@ -169,6 +174,9 @@ class VariableStore:
         if self.m is not None:
             out.update({self.names[p] + "/m": self._view(self.m, p).detach().clone() for p in self.order})
             out.update({self.names[p] + "/v": self._view(self.v, p).detach().clone() for p in self.order})
+        for n in self._state_nodes:     # slots outside the flat buffers
+            if n.id in self.state and not self._flat_slot(n):
+                out[n.name] = self.state[n.id].detach().clone()
         return out
 
     def load_state_dict(self, sd: Dict[str, torch.Tensor]) -> None:
@@ -180,6 +188,10 @@ class VariableStore:
                 self.ensure_slots()
                 self._view(self.m, p).copy_(sd[nm + "/m"].to(self.device))
                 self._view(self.v, p).copy_(sd[nm + "/v"].to(self.device))
+        for n in self._state_nodes:
+            if n.name in sd and not self._flat_slot(n):
+                self.ensure_slots()
+                self.state[n.id].copy_(sd[n.name].to(self.device).reshape(self.state[n.id].shape))
         self.sync_compute()
 
 
@@ -211,8 +223,10 @@ class Executor:
         self._graph: Optional[torch.cuda.CUDAGraph] = None
         self._static_in: Dict[str, torch.Tensor] = {}
         self._static_out: List[torch.Tensor] = []
-        self.hyper = torch.zeros(4, dtype=torch.float32, device=self.device)
-        self._hyper_host = torch.zeros(4, dtype=torch.float32).pin_memory() if self.device.type == "cuda" else torch.zeros(4)
+        from .optimizers import HYPER_SIZE    # (the CUDA kernels read the first four entries)
+        self.hyper = torch.zeros(HYPER_SIZE, dtype=torch.float32, device=self.device)
+        self._hyper_host = (torch.zeros(HYPER_SIZE, dtype=torch.float32).pin_memory() if self.device.type == "cuda"
+                            else torch.zeros(HYPER_SIZE))
         self.opt = dict(graph.meta.get("optimizer", {"kind": "none"}))
         self.lr_fn: Optional[Callable[[int], float]] = None
         self._plan()
@@ -238,7 +252,7 @@ class Executor:
             if g.nodes[pid].op == "parameter":
                 self.grad_binding[n.inputs[1].key()] = pid
         self.first_apply = self.apply_nodes[0].id if self.apply_nodes else None
-        if any(n.op == "apply_adamw" for n in self.apply_nodes):
+        if any(len(n.inputs) > 2 for n in self.apply_nodes):
             self.store.ensure_slots()
         # nodes that (transitively) consume an optimizer output run after the update phase
         self.post_apply: set = set()
@@ -251,7 +265,7 @@ class Executor:
                 return False
             return all(g.nodes[v.node].op == "state" and tuple(g.type_of(v).shape) == tuple(g.type_of(n.inputs[0]).shape)
                        for v in n.inputs[2:])
-        self.fused_apply_ok = all(_whole(n) for n in self.apply_nodes)
+        self.fused_apply_ok = all(_whole(n) and n.op in FLAT_APPLY for n in self.apply_nodes)
         if not self.fused_apply_ok:
             self.grad_binding = {}  # general path: gradients flow through the environment, not the flat buffer
         self.update_target: Dict[Tuple[int, int], int] = {v.key(): var for var, v in g.updates.items()}
@@ -322,8 +336,8 @@ class Executor:
         to its conclusion; the per-tensor collectives of the plan become virtual.  Variables the planner treated
         differently (stored sharded, gradient re-laid-out by all-to-all, ...) keep the general per-tensor path."""
         apply_nodes = [n for n in g.nodes if n.op.startswith("apply_")]
-        if not apply_nodes:
-            return None
+        if not apply_nodes or any(n.op not in FLAT_APPLY for n in apply_nodes):
+            return None     # (optimizers with per-variable reductions cannot be applied over flat, variable-straddling chunks)
         skip: set = set()
         binding: Dict[Tuple[int, int], int] = {}
         regular_apply: set = set()
@@ -612,9 +626,10 @@ class Executor:
 
     def _set_hyper(self) -> None:
         kind = self.opt.get("kind")
-        lr = float(self.lr_fn(self.step_count) if self.lr_fn else self.opt.get("lr", 1e-3))
-        b1, b2 = self.opt.get("beta1", 0.9), self.opt.get("beta2", 0.999)
-        vals = [lr, 1.0 - b1 ** self.step_count, 1.0 - b2 ** self.step_count, 1.0]
+        lr = self.lr_fn(self.step_count) if self.lr_fn else self.opt.get("lr", 1e-3)
+        lr = 0.0 if lr is None else float(lr)      # (lr=None: Adafactor's relative step size, hyper[H_AF_REL_LR])
+        from .optimizers import host_hyper
+        vals = host_hyper(self.opt, self.step_count, lr)
         if kind is None:
             return
         for i, x in enumerate(vals):
@@ -789,6 +804,31 @@ class Executor:
 
         master = storage(n.inputs[0], "master")
         comp = storage(n.inputs[0], "compute")
+        if n.op not in FLAT_APPLY:
+            # optimizers with per-variable reductions (runtime/optimizers.py): in place on this rank's view, reductions
+            # completed over the mesh levels that cut the view out of the variable
+            from .optimizers import STEP, Shards
+            chain: List[Tuple[int, int, int]] = []
+            src = g.nodes[n.inputs[0].node]
+            while src.op == "dynamic_slice":
+                chain.insert(0, (int(src.attrs["dim"]), int(src.attrs["num"]), int(src.attrs["level"])))
+                src = g.nodes[src.inputs[0].node]
+            chain = [(int(d_), int(k_), int(l_)) for d_, k_, l_ in zip(src.attrs.get("shard_dims", []), src.attrs.get("shard_nums", []),
+                                                                       src.attrs.get("shard_levels", []))] + chain
+
+            def all_reduce(t: torch.Tensor, level: int, op: str) -> None:
+                if self.collective is None or self.collective.dry or self.collective.mesh.world == 1:
+                    return
+                import torch.distributed as dist
+                dist.all_reduce(t, op=dist.ReduceOp.MAX if op == "max" else dist.ReduceOp.SUM, group=self.collective.mesh.group(level))
+            slots = [storage(v, "state") for v in n.inputs[2:]]
+            STEP[n.op](master, grad.reshape(master.shape), slots, o, self.hyper, Shards(chain, all_reduce), decay=bool(n.attrs.get("decay", True)))
+            if comp.data_ptr() != master.data_ptr():
+                comp.copy_(master.to(comp.dtype))
+            env[(n.id, 0)] = comp if comp.is_contiguous() else comp.contiguous()
+            for i, sl in enumerate(slots):
+                env[(n.id, i + 1)] = sl
+            return
         pm = master if master.is_contiguous() else master.contiguous()
         pc = comp if (comp.is_contiguous() and comp.dtype == torch.bfloat16) else (
             torch.empty(pm.shape, dtype=torch.bfloat16, device=pm.device) if pm.is_cuda else None)

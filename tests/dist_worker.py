@@ -38,7 +38,7 @@ def case_ckpt(strategy):
     from tepdist_b200.api import Trainer
     from tepdist_b200.models.gpt2 import CONFIGS, build_gpt2_graph
     cfg = CONFIGS["tiny"]
-    g = build_gpt2_graph(cfg, batch=4)
+    g = build_gpt2_graph(cfg, batch=4, optimizer=os.environ.get("TEPDIST_TEST_OPT", "adamw"))
     tr = Trainer(g, strategy=strategy, device=torch.device("cpu"), use_cuda_graph=False)
     torch.manual_seed(0)
     tok = torch.randint(0, cfg.n_vocab, (4, cfg.n_ctx), dtype=torch.int32)
@@ -129,6 +129,45 @@ def case_manualdp(strategy):
     return {"losses": losses, "parallelism": "manual-dp", "collectives": None}
 
 
+def case_opts(strategy):
+    """Every reduction-carrying optimizer under `strategy`: losses + how many updates acted on a shard of their variable."""
+    from tepdist_b200.api import Trainer
+    from test_optimizers_cpu import CASES, build_mlp
+    out = {}
+    for case in ("momentum", "lamb", "adafactor", "adafactor_relative_step", "sm3", "sm3_momentum"):
+        hp = CASES[case][0]
+        tr = Trainer(build_mlp(case.split("_")[0], **hp), strategy=strategy, device=torch.device("cpu"), use_cuda_graph=False, seed=5)
+        torch.manual_seed(1)
+        losses = [tr.step({"x": torch.randn(8, 16), "t": torch.randn(8, 4)}) for _ in range(6)]
+        g = getattr(tr.exec, "g", None)
+        sharded = 0
+        if g is not None:
+            for n in g.nodes:
+                if n.op.startswith("apply_"):
+                    src = g.nodes[n.inputs[0].node]
+                    sharded += int(src.op == "dynamic_slice" or "shard_dims" in src.attrs)
+        out[case] = {"losses": losses, "sharded_updates": sharded}
+    return {"losses": [], "parallelism": strategy, "collectives": None, "opts": out}
+
+
+def case_optsgpt(strategy):
+    """GPT-2 tiny with the reduction-carrying optimizers: the cost-based plan is data parallel with ZeRO-sharded updates
+    (reduce_scatter -> apply on dynamic_slice(variable) -> all_gather), i.e. the update sees a dim-0 chunk of every variable."""
+    from tepdist_b200.api import Trainer
+    from tepdist_b200.models.gpt2 import CONFIGS, build_gpt2_graph
+    cfg = CONFIGS["tiny"]
+    out = {}
+    for kind in ("lamb", "adafactor", "sm3"):
+        tr = Trainer(build_gpt2_graph(cfg, batch=4, optimizer=kind), strategy=strategy, device=torch.device("cpu"), use_cuda_graph=False)
+        torch.manual_seed(0)
+        tok = torch.randint(0, cfg.n_vocab, (4, cfg.n_ctx), dtype=torch.int32)
+        losses = [tr.step({"tokens": tok, "labels": torch.roll(tok, -1, 1)}) for _ in range(4)]
+        g = getattr(tr.exec, "g", None)
+        chunked = sum(1 for n in g.nodes if n.op.startswith("apply_") and g.nodes[n.inputs[0].node].op == "dynamic_slice") if g else 0
+        out[kind] = {"losses": losses, "sharded_updates": chunked}
+    return {"losses": [], "parallelism": strategy, "collectives": None, "opts": out}
+
+
 def case_mlp(strategy):
     """examples/smoke_testing-style 2-layer MLP; planner emits a DP shard on CPU/gloo world_size=2 (BASELINE config 1)."""
     from tepdist_b200.api import Trainer
@@ -158,9 +197,13 @@ def case_moe(strategy):
 if __name__ == "__main__":
     case, out = sys.argv[1], sys.argv[2]
     name, _, strat = case.partition(":")
-    res = {"gpt2": case_gpt2, "gpt2s": lambda st: case_gpt2(st, True), "gpt2b1": lambda st: case_gpt2(st, False, 1), "mlp": case_mlp, "moe": case_moe, "ckpt": case_ckpt, "state": case_state, "tpfused": case_tpfused, "manualdp": case_manualdp}[name](strat or "auto")
+    res = {"gpt2": case_gpt2, "gpt2s": lambda st: case_gpt2(st, True), "gpt2b1": lambda st: case_gpt2(st, False, 1), "mlp": case_mlp, "moe": case_moe, "ckpt": case_ckpt, "state": case_state, "tpfused": case_tpfused, "manualdp": case_manualdp, "opts": case_opts, "optsgpt": case_optsgpt}[name](strat or "auto")
     if int(os.environ.get("RANK", "0")) == 0:
         json.dump(res, open(out, "w"))
     if dist.is_initialized():
         dist.barrier()
-        dist.destroy_process_group()
+        # leave without tearing the process group down: destroying gloo groups while their worker threads are still draining
+        # aborted once under load ("terminate called without an active exception", exit -6) after the results were written
+        sys.stdout.flush()
+        sys.stderr.flush()
+        os._exit(0)

@@ -170,7 +170,7 @@ def test_gpt2_auto_is_data_parallel_with_sharded_optimizer():
     assert set(_tags(cg, plan, ("linear", "attention"))) == {"batch"}
     st = plan.stats
     assert st.collectives.get("reduce_scatter", 0) > 0 and st.collectives.get("all_gather", 0) > 0   # ZeRO-1 found
-    assert st.optimal and st.num_subgraphs > st.distinct_subgraphs >= 1   # identical layers are memoised
+    assert st.optimal and st.infeasible_subgraphs == 0 and st.num_subgraphs > st.distinct_subgraphs >= 1   # identical layers are memoised
     assert "all_to_all" not in st.collectives
 
 
@@ -184,6 +184,11 @@ def test_memory_limit_forces_tensor_parallel():
     att = _tags(cg, plan, ("attention",))
     assert set(att) == {"heads"}                                 # head split follows through attention
     assert plan.stats.forced_weight_splits > 0
+    # every sub-graph has a consistent assignment.  (Regression: a must-split weight whose value leaves its sub-graph used to be
+    # pinned to the replicated mirror layout, which made the tail sub-graphs infeasible; their nodes then silently kept candidate 0
+    # and the separator choice degenerated to "first option" -- the Megatron plan above came out by accident, with 23 % more
+    # traffic from stray all-to-alls.)
+    assert plan.stats.infeasible_subgraphs == 0 and "all_to_all" not in plan.stats.collectives, dict(plan.stats.collectives)
     # every weight matrix is stored sharded
     for i in range(cg.num_nodes()):
         if cg.node_op(i) == "parameter" and len(cg.node_outputs(i)[0][0]) == 2:
