@@ -80,6 +80,7 @@ def plan_spmd_mesh(graph: Graph, nums, kinds):
     colls: Dict[str, int] = {}
     comm = 0.0
     secs = 0.0
+    infeasible = 0
     for lvl, (num, kind) in enumerate(zip(nums, kinds)):
         o = _C.SpmdOptions()
         o.num = int(num)
@@ -89,6 +90,7 @@ def plan_spmd_mesh(graph: Graph, nums, kinds):
         if kind == "tp":
             o.var_mem_limit = 1.0
         plan = _C.plan_spmd_level(cg, o)
+        infeasible += plan.stats.infeasible_subgraphs
         cg, _ = _C.spmd_transform(cg, plan, lvl, int(num))
         for k, v in dict(plan.stats.collectives).items():
             colls[k] = colls.get(k, 0) + int(v)
@@ -96,7 +98,11 @@ def plan_spmd_mesh(graph: Graph, nums, kinds):
         secs += plan.stats.solve_seconds
     out = from_native(cg)
     merge_client_attrs(out, graph)
-    info = {"collectives": colls, "comm_bytes": comm, "solve_seconds": secs, "mesh": [int(n) for n in nums], "kinds": list(kinds)}
+    if infeasible:
+        import warnings
+        warnings.warn(f"SPMD planner: {infeasible} sub-graph(s) without a consistent assignment over the mesh levels")
+    info = {"collectives": colls, "comm_bytes": comm, "solve_seconds": secs, "mesh": [int(n) for n in nums], "kinds": list(kinds),
+            "infeasible_subgraphs": infeasible}
     return out, info
 
 

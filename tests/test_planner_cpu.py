@@ -493,3 +493,28 @@ def test_liveness_optimizer_gives_each_user_its_own_convert_and_keeps_numerics()
     la = [float(ea.step(feeds)[0]) for _ in range(4)]
     lb = [float(eb.step(feeds)[0]) for _ in range(4)]
     assert la == lb and la[-1] < la[0], (la, lb)
+
+
+def test_no_sub_graph_is_left_without_a_consistent_assignment():
+    """SpmdStats.infeasible_subgraphs must be 0 across model families, device counts and memory pressure: an infeasible sub-graph
+    keeps candidate 0 for all of its nodes and degrades the separator DP, which is valid but silently unoptimised."""
+    from tepdist_b200.models.gpt_moe import MoEConfig, build_gpt_moe_graph, build_moe_ffn_graph
+    from tepdist_b200.models.smoke import build_attention_graph, build_conv_graph
+    moe = MoEConfig(n_layer=2, hidden=128, ffn=256, n_head=2, experts=4, capacity=64, groups=4, seq=128, batch=4, vocab=1000)
+    cases = []
+    for num in (2, 4, 8):
+        for lim in (None, 1.0):
+            cases.append(("gpt2", build_gpt2_graph(CONFIGS["tiny"], batch=8), num, lim))
+        cases.append(("gpt2-b1", build_gpt2_graph(CONFIGS["tiny"], batch=1), num, None))
+    for opt in ("lamb", "adafactor", "sm3"):
+        cases.append(("gpt2-" + opt, build_gpt2_graph(CONFIGS["tiny"], batch=8, optimizer=opt), 2, 1.0))
+    for num in (2, 4):
+        for lim in (None, 1.0):
+            cases.append(("moe", build_gpt_moe_graph(moe), num, lim))
+    cases.append(("moe-ffn", build_moe_ffn_graph(groups=8, tokens_per_group=64, model=64, hidden=256, experts=8, capacity=16), 8, 1.0))
+    cases += [("mlp", build_mlp_graph(batch=8), 2, None), ("attention", build_attention_graph(), 2, None),
+              ("conv", build_conv_graph(), 2, None), ("conv", build_conv_graph(), 2, 1.0)]
+    for name, g, num, lim in cases:
+        kw = {} if lim is None else {"var_mem_limit": lim}
+        _, plan = _plan(g, num, **kw)
+        assert plan.stats.infeasible_subgraphs == 0, (name, num, lim, plan.stats.num_subgraphs)
