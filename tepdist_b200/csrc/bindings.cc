@@ -196,6 +196,7 @@ PYBIND11_MODULE(_C, m) {
       .def_readonly("var_bytes_per_device", &SpmdStats::var_bytes_per_device)
       .def_readonly("forced_weight_splits", &SpmdStats::forced_weight_splits)
       .def_readonly("infeasible_subgraphs", &SpmdStats::infeasible_subgraphs)
+      .def_readonly("ignored_annotations", &SpmdStats::ignored_annotations)
       .def_readonly("collectives", &SpmdStats::collectives);
   py::class_<SpmdPlan>(m, "SpmdPlan")
       .def_readonly("choice", &SpmdPlan::choice)

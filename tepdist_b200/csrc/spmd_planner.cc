@@ -88,6 +88,7 @@ void BuildProblem(Problem& p, SpmdStats* stats) {
       for (auto& x : c)
         if (!x.outs.empty() && x.outs[0] == want) f.push_back(x);
       if (!f.empty()) c = f, p.forced.insert(n.id);   // (a user annotation outranks a mirror pin as well)
+      else if (stats) ++stats->ignored_annotations;     // e.g. the annotated dim is not divisible by the device count
     }
     // (slots with a reduced shape -- Adafactor row / column statistics, SM3 per-dim accumulators -- follow the apply node's
     // candidate instead: whether they can be split depends on WHICH dim of the variable is split)

@@ -43,6 +43,7 @@ struct SpmdStats {
   bool optimal = true;
   double var_bytes_per_device = 0;
   int forced_weight_splits = 0;
+  int ignored_annotations = 0;   // user split / replicate annotations no candidate of the node can honour
   int infeasible_subgraphs = 0;  // sub-graphs without a consistent assignment (their nodes keep candidate 0): a planner defect if > 0
   std::map<std::string, int> collectives;  // kind -> count implied by the chosen plan
 };

@@ -38,6 +38,10 @@ def plan_spmd(graph: Graph, num: int, strategy: str = "auto", options: Optional[
     # "dp" / "rule": annotation-driven rule mode (reference FastSpmdStrategy, RULE_MODE=true): the batch split on the
     # sample inputs is propagated through the graph, variables stay replicated, gradients come out partial.
     plan = _C.plan_spmd_by_rules(cg, o) if strategy in ("rule", "dp") else _C.plan_spmd_level(cg, o)
+    if getattr(plan.stats, "ignored_annotations", 0):
+        import warnings
+        warnings.warn(f"SPMD planner: {plan.stats.ignored_annotations} sharding annotation(s) cannot be honoured by any strategy of "
+                      "their node (dimension not divisible by the device count?) and were ignored")
     if plan.stats.infeasible_subgraphs:
         import warnings
         warnings.warn(f"SPMD planner: {plan.stats.infeasible_subgraphs} sub-graph(s) without a consistent assignment; their nodes keep "

@@ -239,6 +239,27 @@ def test_replicate_annotation_is_honoured():
     assert not stored(cg2, plan2, "w1").is_glue()
 
 
+def test_unsatisfiable_annotation_is_reported_not_silently_dropped():
+    """split(w2, dim 1, 2 devices) on 5 columns: no candidate can honour it; the plan goes ahead and says so."""
+    import warnings
+    from tepdist_b200.frontend.builder import GraphBuilder, build_training_step
+    from tepdist_b200.parallel import plan_spmd
+    b = GraphBuilder("ann", compute_dtype="f32")
+    x = b.input("x", (8, 16), "f32"); t = b.input("t", (8, 5), "f32")
+    w1 = b.parameter("w1", (16, 32), {"kind": "normal", "std": 0.3}); w2 = b.parameter("w2", (32, 5), {"kind": "normal", "std": 0.3})
+    b.annotate_split(w2, 1, 2)
+    d = b.sub(b.matmul(b.tanh(b.matmul(x, w1)), w2), t)
+    g = build_training_step(b, b.reduce_mean(b.mul(d, d), [0, 1], name="loss"), "sgd", lr=0.1)
+    cg, plan = _plan(g, 2, ignore_annotation=False)
+    assert plan.stats.ignored_annotations == 1
+    with warnings.catch_warnings(record=True) as w:
+        warnings.simplefilter("always")
+        plan_spmd(g, 2, "auto", {"ignore_annotation": False})
+    assert any("annotation" in str(x.message) for x in w)
+    cg, plan = _plan(build_mlp_graph(batch=8, annotate=True, num=2), 2, ignore_annotation=False)
+    assert plan.stats.ignored_annotations == 0
+
+
 def test_rule_mode_propagates_batch_split():
     g = build_mlp_graph(batch=8)
     for n in g.nodes:
