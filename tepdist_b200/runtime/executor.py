@@ -134,8 +134,10 @@ class VariableStore:
         return (pid in self.shape and self.shape[pid] == tuple(n.outputs[0].shape)
                 and (n.name.endswith("/m") or n.name.endswith("/v")))
 
-    def ensure_slots(self) -> None:
-        if self.m is None and any(self._flat_slot(n) for n in self._state_nodes):
+    def ensure_slots(self, flat_moments: bool = False) -> None:
+        """`flat_moments`: the graph updates with AdamW, whose flat paths (fused whole-buffer update, sharded-optimizer
+        chunks) address m / v by FLAT offset even when every slot node of the plan is chunk-shaped -- always allocate them."""
+        if self.m is None and (flat_moments or any(self._flat_slot(n) for n in self._state_nodes)):
             self.m = torch.zeros_like(self.master)
             self.v = torch.zeros_like(self.master)
         for n in self._state_nodes:
@@ -184,8 +186,8 @@ class VariableStore:
             nm = self.names[p]
             if nm in sd:
                 self.master_view(p).copy_(sd[nm].to(self.device))
-            if nm + "/m" in sd:
-                self.ensure_slots()
+            if nm + "/m" in sd and tuple(sd[nm + "/m"].shape) == self.shape[p]:     # (else: a separately sharded slot, below)
+                self.ensure_slots(flat_moments=True)
                 self._view(self.m, p).copy_(sd[nm + "/m"].to(self.device))
                 self._view(self.v, p).copy_(sd[nm + "/v"].to(self.device))
         for n in self._state_nodes:
@@ -253,7 +255,7 @@ class Executor:
                 self.grad_binding[n.inputs[1].key()] = pid
         self.first_apply = self.apply_nodes[0].id if self.apply_nodes else None
         if any(len(n.inputs) > 2 for n in self.apply_nodes):
-            self.store.ensure_slots()
+            self.store.ensure_slots(flat_moments=any(n.op == "apply_adamw" for n in self.apply_nodes))
         # nodes that (transitively) consume an optimizer output run after the update phase
         self.post_apply: set = set()
         for n in g.nodes:
@@ -403,6 +405,8 @@ class Executor:
         if fz is None:
             return
         g, st = self.g, self.store
+        if self.opt.get("kind") == "adamw":
+            st.ensure_slots(flat_moments=True)      # the chunked update addresses m / v by flat offset
         num = fz["num"]
         bucket_elems = int(self.opt.get("bucket_elems", 48 * 1024 * 1024))
         gran = num * _ALIGN

@@ -192,6 +192,33 @@ def test_scheduler_early_ga_and_receive_ring_options():
     assert all(n.buffer_id < 0 for n in dag.nodes)
 
 
+def test_flat_moment_buffers_exist_for_adamw_even_when_every_slot_node_is_chunk_shaped():
+    """The sharded-optimizer path addresses m / v by flat offset.  In a plan where every variable is ZeRO-sharded all `state` nodes
+    have chunk shapes, so none of them maps onto the flat buffers -- the buffers must be allocated regardless (a refactoring of
+    ensure_slots briefly tied the allocation to the existence of a whole-shaped slot; the 8-GPU GPT-2 plan has next to none)."""
+    import torch
+    from tepdist_b200.frontend.builder import GraphBuilder, build_training_step
+    from tepdist_b200.ir import TensorType
+    from tepdist_b200.runtime.executor import Executor, VariableStore
+    b = GraphBuilder("chunked", compute_dtype="f32")
+    x = b.input("x", (4, 8), "f32")
+    w = b.parameter("w", (8, 8), {"kind": "normal", "std": 0.1})
+    g = build_training_step(b, b.reduce_mean(b.matmul(x, w), [0, 1], name="loss"), "adamw", lr=0.1)
+    for n in g.nodes:                       # what the SPMD transform does to the slots of a ZeRO-sharded variable
+        if n.op == "state":
+            n.outputs[0] = TensorType((4, 8), "f32")
+    st = VariableStore(g, torch.device("cpu"))
+    assert not any(st._flat_slot(n) for n in st._state_nodes)
+    st.ensure_slots()
+    assert st.m is None                     # no whole-shaped slot and nobody asked for flat moments
+    st.ensure_slots(flat_moments=True)
+    assert st.m is not None and st.v is not None and st.m.numel() == st.master.numel()
+    # the executor asks for them whenever the graph updates with AdamW
+    g2 = build_training_step(*(lambda bb: (bb, bb.reduce_mean(bb.matmul(bb.input("x", (4, 8), "f32"), bb.parameter("w", (8, 8), {"kind": "normal", "std": 0.1})), [0, 1], name="loss")))(GraphBuilder("whole", compute_dtype="f32")), "adamw", lr=0.1)
+    ex = Executor(g2, torch.device("cpu"), use_cuda_graph=False)
+    assert ex.store.m is not None
+
+
 def test_scheduler_reports_oom():
     sp = _spec(2, 4)
     sp.mem_limit = 1.5e9
