@@ -54,7 +54,8 @@ def main():
     net = TinyGPT(V=V, B=B, S=S)
     tok = torch.randint(0, V, (B, S))
     dev_cuda = torch.cuda.is_available()
-    tr = trace(net, {"tokens": tok}, loss="cross_entropy", label_example=tok.int(), optimizer="adamw", lr=1e-3,
+    opt = torch.optim.AdamW(net.parameters(), lr=1e-3, weight_decay=0.01)     # the user's own optimizer object, taken as it is
+    tr = trace(net, {"tokens": tok}, loss="cross_entropy", label_example=tok.int(), optimizer=opt,
                compute_dtype="bf16" if dev_cuda else "f32")
     trainer = Trainer(tr.graph, strategy=a.strategy, use_cuda_graph=False)
     tr.load_state_dict_into(trainer.exec, net.state_dict())       # start from the module's own weights

@@ -37,9 +37,42 @@ class TraceResult:
         executor.store.load_state_dict(sd)
 
 
+def optimizer_from_torch(opt: "torch.optim.Optimizer"):
+    """(kind, hyper-parameters) of frontend.builder.apply_optimizer for a torch.optim instance, so that a user's unmodified
+    optimizer object can be handed to `trace` (the reference's client likewise takes the user's TF optimizer as it is).
+    Supported: SGD (with / without momentum, Nesterov), Adam (without the coupled L2 term), AdamW; one parameter group."""
+    groups = opt.param_groups
+    keys = [k for k in groups[0] if k != "params"]
+    if any(any(g[k] != groups[0][k] for k in keys) for g in groups[1:]):
+        raise NotImplementedError("parameter groups with different hyper-parameters; mark variables with decay=False in the graph instead")
+    g = groups[0]
+    for flag in ("amsgrad", "maximize", "capturable_unsupported"):
+        if g.get(flag):
+            raise NotImplementedError(f"{type(opt).__name__}({flag}=True)")
+    if isinstance(opt, torch.optim.AdamW) or (isinstance(opt, torch.optim.Adam) and g.get("decoupled_weight_decay")):
+        return "adamw", dict(lr=g["lr"], beta1=g["betas"][0], beta2=g["betas"][1], eps=g["eps"], weight_decay=g["weight_decay"])
+    if isinstance(opt, torch.optim.Adam):
+        if g["weight_decay"]:
+            raise NotImplementedError("Adam(weight_decay != 0) adds an L2 term to the gradient; use AdamW (decoupled) instead")
+        return "adam", dict(lr=g["lr"], beta1=g["betas"][0], beta2=g["betas"][1], eps=g["eps"])
+    if isinstance(opt, torch.optim.SGD):
+        if g["weight_decay"] or g["dampening"]:
+            raise NotImplementedError("SGD(weight_decay / dampening != 0)")
+        if g["momentum"]:
+            return "momentum", dict(lr=g["lr"], momentum=g["momentum"], nesterov=bool(g["nesterov"]))
+        return "sgd", dict(lr=g["lr"])
+    raise NotImplementedError(f"{type(opt).__name__}: pass optimizer=<one of frontend.builder.OPTIMIZERS> and its hyper-parameters instead")
+
+
 def trace(module: nn.Module, example_inputs: Dict[str, torch.Tensor], loss: str = "cross_entropy", label_name: str = "labels",
-          label_example: Optional[torch.Tensor] = None, optimizer: str = "adamw", compute_dtype: str = "f32", **hp) -> TraceResult:
-    """`module(**example_inputs)` must return logits / predictions; `loss` in {"cross_entropy", "mse"}."""
+          label_example: Optional[torch.Tensor] = None, optimizer: Any = "adamw", compute_dtype: str = "f32", **hp) -> TraceResult:
+    """`module(**example_inputs)` must return logits / predictions; `loss` in {"cross_entropy", "mse"}.  `optimizer`: a kind
+    from frontend.builder.OPTIMIZERS with its hyper-parameters as keyword arguments, or a torch.optim instance."""
+    decay_all = False
+    if isinstance(optimizer, torch.optim.Optimizer):
+        optimizer, from_opt = optimizer_from_torch(optimizer)
+        hp = {**from_opt, **hp}
+        decay_all = True      # torch applies a group's weight_decay to every parameter of the group, biases and norms included
     gm = fx.symbolic_trace(module)
     names = list(example_inputs)
     ShapeProp(gm).propagate(*[example_inputs[k] for k in names])
@@ -206,5 +239,9 @@ def trace(module: nn.Module, example_inputs: Dict[str, torch.Tensor], loss: str 
                 loss_v = b.reduce_mean(b.mul(d, d), list(range(len(b.t(out).shape))), name="loss")
             else:
                 raise ValueError(loss)
+    if decay_all:
+        for n in b.g.nodes:
+            if n.op == "parameter":
+                n.attrs["decay"] = True
     g = build_training_step(b, loss_v, optimizer, **hp)
     return TraceResult(g, pnames)

@@ -1,4 +1,5 @@
 """CPU tests: IR construction, autodiff vs torch.autograd, executor training loop."""
+import pytest
 import torch
 
 from tepdist_b200.frontend.builder import GraphBuilder, build_training_step
@@ -90,6 +91,51 @@ def test_fx_trace_matches_eager_torch_training():
         (l,) = ex.step({"x": x, "t": y})
         assert abs(float(l) - float(ref)) < 1e-5
     assert torch.allclose(ex.store.state_dict()["fc1/weight"], net.fc1.weight.detach(), atol=1e-5)
+
+
+@pytest.mark.parametrize("make", [
+    lambda ps: torch.optim.AdamW(ps, lr=0.01, betas=(0.9, 0.95), eps=1e-8, weight_decay=0.1),
+    lambda ps: torch.optim.Adam(ps, lr=0.01, betas=(0.8, 0.99), eps=1e-7),
+    lambda ps: torch.optim.SGD(ps, lr=0.05, momentum=0.9),
+    lambda ps: torch.optim.SGD(ps, lr=0.05, momentum=0.9, nesterov=True),
+], ids=["adamw", "adam", "momentum", "nesterov"])
+def test_fx_trace_takes_the_users_torch_optimizer(make):
+    """`trace(..., optimizer=<torch.optim instance>)`: the traced step trains like eager PyTorch stepping that very optimizer."""
+    import torch.nn as nn
+    from tepdist_b200.frontend.trace import trace
+
+    class Net(nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.fc1, self.ln, self.fc2 = nn.Linear(16, 32), nn.LayerNorm(32), nn.Linear(32, 8)
+
+        def forward(self, x):
+            return self.fc2(torch.tanh(self.ln(self.fc1(x))))
+
+    torch.manual_seed(0)
+    net = Net()
+    x, y = torch.randn(8, 16), torch.randn(8, 8)
+    opt = make(net.parameters())
+    tr = trace(net, {"x": x}, loss="mse", label_name="t", label_example=y, optimizer=opt)
+    ex = Executor(tr.graph, torch.device("cpu"))
+    tr.load_state_dict_into(ex, net.state_dict())
+    for _ in range(4):
+        ref = ((net(x) - y) ** 2).mean()
+        opt.zero_grad(); ref.backward(); opt.step()
+        (l,) = ex.step({"x": x, "t": y})
+        assert abs(float(l) - float(ref)) < 2e-5
+    for name, p in net.named_parameters():
+        assert torch.allclose(ex.store.state_dict()[name.replace(".", "/")], p.detach(), atol=2e-5), name
+
+
+def test_fx_trace_rejects_optimizer_settings_it_cannot_reproduce():
+    import torch.nn as nn
+    from tepdist_b200.frontend.trace import optimizer_from_torch
+    ps = list(nn.Linear(4, 4).parameters())
+    for bad in (torch.optim.Adam(ps, weight_decay=0.1), torch.optim.SGD(ps, lr=0.1, weight_decay=0.1), torch.optim.RMSprop(ps),
+                torch.optim.AdamW([{"params": ps[:1], "weight_decay": 0.0}, {"params": ps[1:], "weight_decay": 0.1}])):
+        with pytest.raises(NotImplementedError):
+            optimizer_from_torch(bad)
 
 
 def test_fx_trace_transformer_block_with_sdpa():
