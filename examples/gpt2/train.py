@@ -19,6 +19,7 @@ def main():
     ap.add_argument("--train-steps", type=int, default=10)
     ap.add_argument("--strategy", default="auto")
     ap.add_argument("--comm", default="fused", choices=["fused", "nccl"])
+    ap.add_argument("--warmup-steps", type=int, default=0, help='linear warm-up then cosine decay over --train-steps (reference json: "warmup_steps")')
     ap.add_argument("--optimizer", default="adamw", choices=["adam", "adamw", "adafactor", "lamb", "sm3", "momentum", "sgd"],
                     help='reference: "opt_name" adam | adafactor in examples/GPT2/*.json')
     a = ap.parse_args()
@@ -26,6 +27,9 @@ def main():
     world = int(os.environ.get("WORLD_SIZE", "1"))
     g = build_gpt2_graph(cfg, batch=a.batch * world, optimizer=a.optimizer)
     tr = Trainer(g, strategy=a.strategy, comm_mode=a.comm)
+    if a.warmup_steps > 0:
+        from tepdist_b200.utils.schedules import warmup_cosine
+        tr.set_lr_schedule(warmup_cosine(cfg.lr, a.warmup_steps, a.train_steps))
     gen = torch.Generator().manual_seed(0)
     tok = torch.randint(0, cfg.n_vocab, (a.batch * world, cfg.n_ctx), generator=gen, dtype=torch.int32)
     feeds = {"tokens": tok, "labels": torch.roll(tok, -1, 1)}

@@ -91,6 +91,11 @@ class Trainer:
         """Device-resident variant (no host sync): returns the loss tensor."""
         return self.exec.step(dev_feeds)[0]
 
+    def set_lr_schedule(self, fn) -> None:
+        """`fn(step) -> lr` for the 1-based optimizer step (see utils/schedules.py); None = the graph's constant rate."""
+        ex = getattr(self.exec, "worker", None)
+        (ex.exec if ex is not None else self.exec).set_lr_schedule(fn)
+
     def state_dict(self):
         """Master weights (+ optimizer moments).  Collective under sharded-optimizer plans: every rank must call it."""
         if hasattr(self.exec, "materialize_full_state"):

@@ -231,6 +231,7 @@ class Executor:
                             else torch.zeros(HYPER_SIZE))
         self.opt = dict(graph.meta.get("optimizer", {"kind": "none"}))
         self.lr_fn: Optional[Callable[[int], float]] = None
+        self.lr_now = 0.0
         self._plan()
 
     # ------------------------------------------------------------------ planning
@@ -554,11 +555,11 @@ class Executor:
             kind = o.get("kind")
             comp = None if st.compute is None else st.compute[a:b]
             if kind == "adamw":
-                ops.adamw_step(st.master[a:b], st.grad[a:b], st.m[a:b], st.v[a:b], comp, nd, o.get("lr", 1e-3),
+                ops.adamw_step(st.master[a:b], st.grad[a:b], st.m[a:b], st.v[a:b], comp, nd, self._lr(1e-3),
                                o.get("beta1", 0.9), o.get("beta2", 0.999), o.get("eps", 1e-8), o.get("weight_decay", 0.0),
                                self.step_count, hyper=self.hyper if st.master.is_cuda else None)
             elif kind == "sgd":
-                ops.sgd_step(st.master[a:b], st.grad[a:b], comp, o.get("lr", 1e-2))
+                ops.sgd_step(st.master[a:b], st.grad[a:b], comp, self._lr(1e-2))
             tgt = st.compute if st.compute is not None else st.master
             if not self.dry_comm:
                 works.append(dist.all_gather_into_tensor(tgt[s0:e0], tgt[a:b], group=pg, async_op=True))
@@ -566,7 +567,7 @@ class Executor:
             chunk = n_el // n
             a, b = off + r * chunk, off + (r + 1) * chunk
             comp = None if st.compute is None else st.compute[a:b]
-            ops.adamw_step(st.master[a:b], st.grad[a:b], st.m[a:b], st.v[a:b], comp, (b - a) if decay else 0, o.get("lr", 1e-3),
+            ops.adamw_step(st.master[a:b], st.grad[a:b], st.m[a:b], st.v[a:b], comp, (b - a) if decay else 0, self._lr(1e-3),
                            o.get("beta1", 0.9), o.get("beta2", 0.999), o.get("eps", 1e-8), o.get("weight_decay", 0.0),
                            self.step_count, hyper=self.hyper if st.master.is_cuda else None)
             tgt = st.compute if st.compute is not None else st.master
@@ -632,6 +633,7 @@ class Executor:
         kind = self.opt.get("kind")
         lr = self.lr_fn(self.step_count) if self.lr_fn else self.opt.get("lr", 1e-3)
         lr = 0.0 if lr is None else float(lr)      # (lr=None: Adafactor's relative step size, hyper[H_AF_REL_LR])
+        self.lr_now = lr
         from .optimizers import host_hyper
         vals = host_hyper(self.opt, self.step_count, lr)
         if kind is None:
@@ -639,6 +641,19 @@ class Executor:
         for i, x in enumerate(vals):
             self._hyper_host[i] = x
         self.hyper.copy_(self._hyper_host, non_blocking=True)
+
+    def _lr(self, default: float) -> float:
+        """Learning rate for the update paths that take it as a host scalar (CPU fallbacks, the SGD kernel): the schedule's
+        value of this step when one is set, else the graph's constant.  (The AdamW kernels and the torch-op optimizers read
+        hyper[0] on the device instead, which is what keeps a schedule working under CUDA-graph replay.)"""
+        return self.lr_now if self.lr_fn is not None else self.opt.get("lr", default)
+
+    def set_lr_schedule(self, fn: Optional[Callable[[int], float]]) -> None:
+        """`fn(step)` -> learning rate of optimizer step `step` (1-based); None restores the graph's constant."""
+        if fn is not None and self.use_cuda_graph and self.opt.get("kind") == "sgd" and self.device.type == "cuda":
+            raise NotImplementedError("a learning-rate schedule with SGD under CUDA-graph replay: the SGD kernel takes the rate as a "
+                                      "launch argument, which a captured graph freezes; use use_cuda_graph=False or AdamW / momentum")
+        self.lr_fn = fn
 
     def _run(self, feeds: Dict[str, torch.Tensor]) -> List[torch.Tensor]:
         g = self.g
@@ -843,14 +858,14 @@ class Executor:
             v = v_st if v_st.is_contiguous() else v_st.contiguous()
             numel = pm.numel()
             ops.adamw_step(pm.view(-1), grad.view(-1), m.view(-1), v.view(-1), None if pc is None else pc.view(-1),
-                           numel if decay else 0, o.get("lr", 1e-3), o.get("beta1", 0.9), o.get("beta2", 0.999),
+                           numel if decay else 0, self._lr(1e-3), o.get("beta1", 0.9), o.get("beta2", 0.999),
                            o.get("eps", 1e-8), o.get("weight_decay", 0.0), self.step_count,
                            hyper=self.hyper if pm.is_cuda else None)
             if m.data_ptr() != m_st.data_ptr():
                 m_st.copy_(m); v_st.copy_(v)
             env[(n.id, 1)], env[(n.id, 2)] = m, v
         else:
-            ops.sgd_step(pm.view(-1), grad.view(-1), None if pc is None else pc.view(-1), o.get("lr", 1e-2))
+            ops.sgd_step(pm.view(-1), grad.view(-1), None if pc is None else pc.view(-1), self._lr(1e-2))
         if pm.data_ptr() != master.data_ptr():
             master.copy_(pm)
         if pc is not None and pc.data_ptr() != comp.data_ptr():
@@ -863,11 +878,11 @@ class Executor:
         st, o = self.store, self.opt
         kind = o.get("kind")
         if kind == "adamw":
-            ops.adamw_step(st.master, st.grad, st.m, st.v, st.compute, st.n_decay, o.get("lr", 1e-3), o.get("beta1", 0.9),
+            ops.adamw_step(st.master, st.grad, st.m, st.v, st.compute, st.n_decay, self._lr(1e-3), o.get("beta1", 0.9),
                            o.get("beta2", 0.999), o.get("eps", 1e-8), o.get("weight_decay", 0.0), self.step_count,
                            hyper=self.hyper)
         elif kind == "sgd":
-            ops.sgd_step(st.master, st.grad, st.compute, o.get("lr", 1e-2))
+            ops.sgd_step(st.master, st.grad, st.compute, self._lr(1e-2))
 
     @staticmethod
     def find_tp_chains(g: Graph, skip: Optional[set] = None) -> Dict[int, Dict[str, Any]]:

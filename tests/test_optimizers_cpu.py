@@ -181,3 +181,41 @@ def test_reduced_shape_slots_are_saved_and_restored():
         b.step_count = a.step_count
         for f in feeds[3:]:
             assert float(a.step(f)[0]) == float(b.step(f)[0])
+
+
+@pytest.mark.parametrize("kind", ["sgd", "momentum", "adamw", "lamb"])
+def test_learning_rate_schedule_matches_torch_lambda_lr(kind):
+    """Trainer.set_lr_schedule: warm-up + cosine decay evaluated per step; the same trajectory as torch.optim + LambdaLR
+    (LAMB: against the reference update rule with the rate set by hand)."""
+    from tepdist_b200.api import Trainer
+    from tepdist_b200.utils.schedules import warmup_cosine, warmup_linear_decay, rsqrt_decay
+    hp, make_ref = CASES[kind]
+    base = hp["lr"]
+    sched = warmup_cosine(base, warmup_steps=3, total_steps=8, end_ratio=0.1)
+    assert sched(1) == pytest.approx(base / 3) and sched(3) == pytest.approx(base) and sched(8) == pytest.approx(0.1 * base)
+    assert sched(100) == pytest.approx(0.1 * base)
+    lin = warmup_linear_decay(1.0, 2, 6)
+    assert [round(lin(s), 3) for s in (1, 2, 4, 6, 9)] == [0.5, 1.0, 0.5, 0.0, 0.0]
+    assert rsqrt_decay(1.0, 4)(2) == 0.5 and rsqrt_decay(1.0, 4)(16) == 0.5
+    tr = Trainer(build_mlp(kind, **hp), device=torch.device("cpu"), use_cuda_graph=False, seed=5)
+    tr.set_lr_schedule(sched)
+    params = {k: v.clone() for k, v in tr.exec.store.state_dict().items() if k in ("w1", "b1", "w2")}
+    ref = make_ref(params)
+    torch.manual_seed(3)
+    for step in range(1, 9):
+        feeds = {"x": torch.randn(8, 16), "t": torch.randn(8, 4)}
+        leaves = {k: v.clone().requires_grad_(True) for k, v in params.items()}
+        torch_loss(leaves, feeds["x"], feeds["t"]).backward()
+        if isinstance(ref, TorchOptim):
+            for gr in ref.opt.param_groups:
+                gr["lr"] = sched(step)
+        else:
+            ref.hp = (sched(step),) + tuple(ref.hp[1:])
+        tr.step(feeds)
+        with torch.no_grad():
+            ref.step({k: v.grad for k, v in leaves.items()})
+        mine = tr.exec.store.state_dict()
+        for k in params:
+            assert torch.allclose(mine[k], params[k], rtol=2e-4, atol=2e-6), (kind, step, k)
+    tr.set_lr_schedule(None)
+    assert tr.exec._lr(123.0) == hp["lr"]
