@@ -79,7 +79,9 @@ def schedule_overrides() -> Dict[str, Any]:
     _take(o, "buffer_save", "BUFFER_SAVE", "bool")
     _take(o, "reorder_send", "MULTI_REORDER", "bool")      # the scheduler's send hoisting (closest counterpart)
     _take(o, "early_ga", "EARLY_GA", "bool")               # default here: true (GA is where a micro-batch is released)
-    _take(o, "group_sched_count", "GROUP_SCHED_COUNT", "int")   # receive-buffer ring size per class (execution_plan.cc:203)
+    _take(o, "group_sched_count", "GROUP_SCHED_COUNT", "int")   # micro-batch groups with their own 1F1B window (task_scheduler.cc:125)
+    if os.environ.get("TEPDIST_RECV_RING"):                     # native knob: receive-buffer ring size per class (tests, experiments)
+        o["recv_ring"] = int(os.environ["TEPDIST_RECV_RING"])
     return o
 
 

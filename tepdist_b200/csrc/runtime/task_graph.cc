@@ -210,7 +210,11 @@ Schedule ScheduleTasks(TaskDAG* dagp, const PipelineSpec& sp, const ScheduleOpti
   std::vector<int> remaining(N);
   for (auto& n : dag.nodes) remaining[n.id] = (int)n.parents.size();
   std::map<int, double> dev_free;           // device -> time it becomes free
-  std::map<int, int> active_fwd;            // device -> forward micro-batches admitted but whose backward has not run
+  // GROUP_SCHED_COUNT (reference task_scheduler.cc:125 should_ignore_by_sched_id, :1313): micro-batch m belongs to group
+  // m % G; the reference schedules every group on its own and merges the per-device sequences, i.e. each group is an
+  // independent 1F1B stream.  Here one event-driven pass schedules all of them, with the admission window kept per group.
+  const int G = std::max(1, opt.group_sched_count);
+  std::map<std::pair<int, int>, int> active_fwd;   // (device, group) -> forward micro-batches admitted, backward not yet run
   std::map<int, double> live_bytes;
   std::set<int> ready;
   for (auto& n : dag.nodes) {
@@ -242,11 +246,12 @@ Schedule ScheduleTasks(TaskDAG* dagp, const PipelineSpec& sp, const ScheduleOpti
     for (int id : ready) {
       const TaskNode& t = dag.nodes[id];
       // 1F1B admission: a forward Input is held back while `limit` forward micro-batches are already in flight
-      if (t.type == TaskType::kInput && !t.backward && active_fwd[t.device] >= limit - t.stage && limit - t.stage > 0) {
+      const auto grp = std::make_pair(t.device, t.micro < 0 ? 0 : t.micro % G);
+      if (t.type == TaskType::kInput && !t.backward && active_fwd[grp] >= limit - t.stage && limit - t.stage > 0) {
         bool other_work = false;
         for (int o : ready)
           if (o != id && dag.nodes[o].device == t.device && !(dag.nodes[o].type == TaskType::kInput && !dag.nodes[o].backward)) other_work = true;
-        bool pending_bwd = active_fwd[t.device] > 0;
+        bool pending_bwd = active_fwd[grp] > 0;
         if (other_work || pending_bwd) continue;
       }
       const double avail = std::max(ready_time[id], dev_free[t.device]);
@@ -268,8 +273,9 @@ Schedule ScheduleTasks(TaskDAG* dagp, const PipelineSpec& sp, const ScheduleOpti
     sch.finish[best] = best_t + t.cost;
     if (!side) dev_free[t.device] = sch.finish[best];
     sch.device_tasks[t.device].push_back(best);
-    if (t.type == TaskType::kInput && !t.backward) active_fwd[t.device]++;
-    if (t.type == TaskType::kOutput && t.backward) active_fwd[t.device]--;
+    const auto tgrp = std::make_pair(t.device, t.micro < 0 ? 0 : t.micro % G);
+    if (t.type == TaskType::kInput && !t.backward) active_fwd[tgrp]++;
+    if (t.type == TaskType::kOutput && t.backward) active_fwd[tgrp]--;
     if (t.type == TaskType::kCompute) {
       if (!t.backward) live_bytes[t.device] += t.out_bytes;
       else live_bytes[t.device] -= (t.stage < (int)sp.act_bytes.size() ? sp.act_bytes[t.stage] : 0.0);
@@ -299,11 +305,13 @@ Schedule ScheduleTasks(TaskDAG* dagp, const PipelineSpec& sp, const ScheduleOpti
     }
   }
   if (opt.buffer_save) {
-    // recv buffers of the same (stage, direction) class rotate through a ring of `ring` slots (reference
-    // execution_plan.cc:203 BufferReuseAnalysis: ring size = GROUP_SCHED_COUNT, slot = occurrence index mod ring; a slot is
-    // "reused" from the (ring+1)-th receive of its class on and its receiver then has to wait for the previous user).
-    // group_sched_count == 0: size the ring by the in-flight limit, so that no receive ever finds its slot occupied.
-    const int ring = std::max(1, opt.group_sched_count > 0 ? opt.group_sched_count : limit);
+    // recv buffers of the same (stage, direction) class rotate through a ring of `ring` slots; slot = occurrence index mod
+    // ring; a slot is "reused" from the (ring+1)-th receive of its class on.  The reference sizes the ring with
+    // GROUP_SCHED_COUNT (execution_plan.cc:203: one buffer per group, consumed by the group's next Input); here a received
+    // activation stays referenced until its micro-batch's backward, so the ring has to cover everything in flight:
+    // groups x in-flight limit.  `recv_ring` overrides that (an undersized ring is legal: the stage worker bypasses an occupied
+    // slot with a fresh buffer and counts a miss).
+    const int ring = std::max(1, opt.recv_ring > 0 ? opt.recv_ring : G * limit);
     std::map<std::pair<int, bool>, int> counter;
     for (auto& kv : sch.device_tasks)
       for (int id : kv.second)

@@ -67,7 +67,9 @@ struct ScheduleOptions {
   bool early_ga = true;          // EARLY_GA: accumulate (and release the micro-batch) right after its backward; false: when idle
   bool reorder_send = true;      // ReorderSend: hoist sends right after their producer
   bool buffer_save = true;       // BUFFER_SAVE: recv buffer reuse classes
-  int group_sched_count = 0;     // GROUP_SCHED_COUNT: receive-buffer ring size per class (0 => the in-flight limit)
+  int group_sched_count = 0;     // GROUP_SCHED_COUNT: micro-batch m is scheduled in group m % count, each group with its own
+                                 // 1F1B admission window (0 / 1: one group)
+  int recv_ring = 0;             // receive-buffer ring size per class (0 => groups x in-flight limit: never undersized)
 };
 struct Schedule {
   std::map<int, std::vector<int>> device_tasks;  // device -> ordered task ids

@@ -55,7 +55,8 @@ void BindRuntime(py::module_& m) {
       .def(py::init<>())
       .def_readwrite("micro_num_limit", &ScheduleOptions::micro_num_limit).def_readwrite("early_ga", &ScheduleOptions::early_ga)
       .def_readwrite("reorder_send", &ScheduleOptions::reorder_send).def_readwrite("buffer_save", &ScheduleOptions::buffer_save)
-      .def_readwrite("group_sched_count", &ScheduleOptions::group_sched_count);
+      .def_readwrite("group_sched_count", &ScheduleOptions::group_sched_count)
+      .def_readwrite("recv_ring", &ScheduleOptions::recv_ring);
   py::class_<Schedule>(m, "Schedule")
       .def_readonly("device_tasks", &Schedule::device_tasks).def_readonly("start", &Schedule::start)
       .def_readonly("finish", &Schedule::finish).def_readonly("makespan", &Schedule::makespan)

@@ -147,7 +147,8 @@ def test_scheduler_is_1f1b_and_bounds_memory():
 def test_scheduler_early_ga_and_receive_ring_options():
     """EARLY_GA (reference task_scheduler.cc:1367 ReorderGA; default on here): gradient accumulation of micro-batch m directly
     follows its backward bundle, so the micro-batch is released at once; off: GA yields to any ready compute and ends up later
-    in the device order, at no cost in makespan.  GROUP_SCHED_COUNT: ring size of the receive-buffer slots per class."""
+    in the device order, at no cost in makespan.  GROUP_SCHED_COUNT: independent 1F1B windows per micro-batch group; the ring of
+    receive-buffer slots per class covers what can be in flight."""
     S_, M = 4, 8
     sp = _spec(S_, M)
 
@@ -177,10 +178,30 @@ def test_scheduler_early_ga_and_receive_ring_options():
     for dag, sch in ((d1, early), (d2, lazy)):      # both are valid orders of the DAG
         pos = {t: (dev, i) for dev, tasks in sch.device_tasks.items() for i, t in enumerate(tasks)}
         assert all(pos[n.id][1] < pos[c][1] for n in dag.nodes for c in n.children if pos[n.id][0] == pos[c][0])
-    # receive ring: default = in-flight limit (= number of stages); explicit count is honoured; `buffer_reused` marks the
+    # GROUP_SCHED_COUNT: micro-batch m is scheduled in group m % G, every group with its own 1F1B window -> up to G x (S - s)
+    # forward activations in flight on stage s, at no loss in makespan; a valid order of the DAG
+    def peak_in_flight(dag, sch, dev):
+        live = peak = 0
+        for t in sch.device_tasks[dev]:
+            n = dag.nodes[t]
+            if n.type == _C.TaskType.Compute:
+                live += -1 if n.backward else 1
+                peak = max(peak, live)
+        return peak
+    d1g, one = run(group_sched_count=1)
+    d2g, two = run(group_sched_count=2)
+    assert [dag_n.name for dag_n in (d1g.nodes[t] for t in one.device_tasks[0])] == [d1.nodes[t].name for t in early.device_tasks[0]]
+    for dev in range(S_):
+        assert peak_in_flight(d1g, one, dev) <= S_ - dev
+        assert peak_in_flight(d2g, two, dev) <= 2 * (S_ - dev)
+    assert peak_in_flight(d2g, two, 0) > peak_in_flight(d1g, one, 0)
+    assert two.makespan <= one.makespan * 1.02
+    pos = {t: (dev, i) for dev, tasks in two.device_tasks.items() for i, t in enumerate(tasks)}
+    assert all(pos[n.id][1] < pos[c][1] for n in d2g.nodes for c in n.children if pos[n.id][0] == pos[c][0])
+    # receive ring: default = groups x in-flight limit (never undersized); `recv_ring` overrides it; `buffer_reused` marks the
     # receives that take over a slot from an earlier receive of their class
-    for count, ring in ((0, S_), (2, 2), (3, 3)):
-        dag, _ = run(group_sched_count=count)
+    for kw, ring in (({}, S_), ({"group_sched_count": 2}, 2 * S_), ({"recv_ring": 2}, 2), ({"recv_ring": 3, "group_sched_count": 2}, 3)):
+        dag, _ = run(**kw)
         for st in range(S_):
             for bwd in (False, True):
                 rc = sorted((n.micro, n.buffer_id, n.buffer_reused) for n in dag.nodes
