@@ -24,7 +24,7 @@ namespace tepdist {
   X(NUM_MICRO_BATCHES, "0", "config mode: micro-batches")                                          \
   X(NUM_STAGES, "0", "config mode: pipeline stages")                                               \
   X(MICRO_NUM_LIMIT, "0", "forward micro-batches in flight per stage (0 = #stages => 1F1B)")       \
-  X(GROUP_SCHED_COUNT, "2", "micro-batch groups scheduled interleaved")                            \
+  X(GROUP_SCHED_COUNT, "1", "micro-batch groups (m % count) with their own 1F1B window (reference default: 2)")                            \
   X(PP_BANDWIDTH, "770", "GB/s assumed for pipeline p2p")                                          \
   X(ILP_TIME_LIMIT, "1", "minutes per exact solve before the greedy fallback")                     \
   X(ILP_NUM_THREADS, "1", "solver threads")                                                        \

@@ -244,7 +244,7 @@ class StageWorker:
 
     def _recv_buffer(self, m: int, backward: bool, key: Tuple[int, int], slot: int) -> torch.Tensor:
         """Receive buffer for value `key` of micro-batch m.  slot >= 0 (BUFFER_SAVE): slot `slot` of the persistent ring of
-        this (direction, value) class, whose size the scheduler chose (GROUP_SCHED_COUNT, default the in-flight limit) --
+        this (direction, value) class, whose size the scheduler chose (groups x in-flight limit, or TEPDIST_RECV_RING) --
         reference execution_state.cc:219 recv_dapple_buffer_ptr_[key][buffer_id].  A slot whose previous micro-batch has
         not been released yet cannot be waited for here (its release is later in THIS worker's task list; the reference
         waits on the consumer's event from another thread), so such a receive gets a fresh buffer and is counted as a miss."""
