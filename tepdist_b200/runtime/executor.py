@@ -232,6 +232,10 @@ class Executor:
         self.opt = dict(graph.meta.get("optimizer", {"kind": "none"}))
         self.lr_fn: Optional[Callable[[int], float]] = None
         self.lr_now = 0.0
+        _spec = (graph.meta.get("optimizer") or {}).get("schedule")
+        if _spec:      # a schedule that came with the graph (e.g. from a client over RPC); Trainer.set_lr_schedule overrides it
+            from ..utils.schedules import from_spec
+            self.lr_fn = from_spec(_spec, (graph.meta.get("optimizer") or {}).get("lr") or 0.0)
         self._plan()
 
     # ------------------------------------------------------------------ planning

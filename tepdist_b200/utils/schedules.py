@@ -44,3 +44,21 @@ def rsqrt_decay(lr: float, warmup_steps: int) -> Schedule:
         w = max(1, warmup_steps)
         return lr * min(step / w, math.sqrt(w / max(1, step)))
     return f
+
+
+def from_spec(spec: dict, base_lr: float) -> Schedule:
+    """Schedule from a plain dict, the form that travels with a graph (`build_training_step(..., schedule={...})` stores it in
+    graph.meta["optimizer"], which is part of the serialized graph a client sends to a server):
+    {"kind": "warmup_cosine" | "warmup_linear_decay" | "rsqrt_decay" | "constant", "warmup_steps": W, "total_steps": T,
+     "end_ratio": r}; `lr` defaults to the optimizer's rate."""
+    kind = spec.get("kind", "constant")
+    lr = float(spec.get("lr", base_lr))
+    if kind == "constant":
+        return constant(lr)
+    if kind == "warmup_cosine":
+        return warmup_cosine(lr, int(spec.get("warmup_steps", 0)), int(spec["total_steps"]), float(spec.get("end_ratio", 0.1)))
+    if kind == "warmup_linear_decay":
+        return warmup_linear_decay(lr, int(spec.get("warmup_steps", 0)), int(spec["total_steps"]), float(spec.get("end_ratio", 0.0)))
+    if kind == "rsqrt_decay":
+        return rsqrt_decay(lr, int(spec.get("warmup_steps", 1)))
+    raise ValueError(f"schedule kind '{kind}'")

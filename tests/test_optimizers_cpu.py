@@ -219,3 +219,26 @@ def test_learning_rate_schedule_matches_torch_lambda_lr(kind):
             assert torch.allclose(mine[k], params[k], rtol=2e-4, atol=2e-6), (kind, step, k)
     tr.set_lr_schedule(None)
     assert tr.exec._lr(123.0) == hp["lr"]
+
+
+def test_schedule_spec_travels_with_the_serialized_graph():
+    """`build_training_step(..., schedule={...})`: the spec sits in graph.meta["optimizer"], survives JSON serialization (what a
+    client sends to a server) and drives the executor's learning rate."""
+    import json
+    from tepdist_b200.ir import Graph
+    from tepdist_b200.utils.schedules import from_spec, warmup_cosine
+    spec = {"kind": "warmup_cosine", "warmup_steps": 2, "total_steps": 6, "end_ratio": 0.1}
+    g = build_mlp("adamw", lr=0.01, weight_decay=0.0, schedule=spec)
+    g2 = Graph.from_dict(json.loads(json.dumps(g.to_dict())))
+    assert g2.meta["optimizer"]["schedule"] == spec
+    want = warmup_cosine(0.01, 2, 6, 0.1)
+    assert [from_spec(spec, 0.01)(s) for s in range(1, 8)] == [want(s) for s in range(1, 8)]
+    ex = Executor(g2, torch.device("cpu"), seed=5, use_cuda_graph=False)
+    feeds = {"x": torch.randn(8, 16), "t": torch.randn(8, 4)}
+    seen = []
+    for _ in range(7):
+        ex.step(feeds)
+        seen.append(float(ex.hyper[0]))
+    assert seen == pytest.approx([want(s) for s in range(1, 8)], rel=1e-6)
+    with pytest.raises(ValueError):
+        from_spec({"kind": "nope"}, 0.1)
