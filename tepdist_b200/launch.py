@@ -19,7 +19,19 @@ import subprocess
 import sys
 
 
+def _normalise(spec: dict) -> dict:
+    """The reference's templates write `"gpu_ids": "0,1,2,3"` and `"port": "2222"` as strings; accept both forms."""
+    for e in [spec["master"]] + list(spec.get("workers", [])):
+        if isinstance(e.get("gpu_ids"), str):
+            e["gpu_ids"] = [int(x) for x in e["gpu_ids"].replace(" ", "").split(",") if x != ""]
+        e["port"] = int(e["port"])
+        if e.get("ip") == "localhost":
+            e["ip"] = "127.0.0.1"      # (the container's hostname resolution is not reliable; the loopback address is)
+    return spec
+
+
 def entry_for(spec: dict, task_index: int) -> dict:
+    _normalise(spec)
     entries = [spec["master"]] + list(spec.get("workers", []))
     counts = {len(e["gpu_ids"]) for e in entries}
     if len(counts) != 1:

@@ -88,6 +88,10 @@ def test_launcher_cluster_spec(tmp_path):
         assert False
     except ValueError:
         pass
+    # the reference's own template form (tf_tepdist/config_*_template.json): strings for the port and the GPU list, "localhost"
+    ref_form = {"master": {"ip": "localhost", "port": "2222", "gpu_ids": "1,2"}}
+    e = entry_for(ref_form, 0)
+    assert e == {"ip": "127.0.0.1", "port": 2222, "gpu_ids": [1, 2]}
 
 
 def test_service_env_flags_drive_planner(monkeypatch, tmp_path):
