@@ -66,18 +66,20 @@ def test_long_context_plan_batch1_head_seq_all_to_all(tmp_path):
         assert abs(a - b) <= 2e-4 * max(1.0, abs(b)), (got, ref)
 
 
-@pytest.mark.parametrize("case", ["opts", "optsgpt"])
-def test_reduction_optimizers_match_single_process_when_sharded(tmp_path, case):
+@pytest.mark.parametrize("case,strategy,world", [("opts", "auto", 2), ("optsgpt", "auto", 2), ("optsgpt", "dp2tp2", 4)])
+def test_reduction_optimizers_match_single_process_when_sharded(tmp_path, case, strategy, world):
     """LAMB / Adafactor / SM3 reduce over the variable (norms, row / column means, per-dimension maxima).  `opts`: an MLP that
     the planner splits Megatron-style over 2 devices -- w1 stored split on its LAST dim, w2 on its ROW dim, so both
     orientations of the factored Adafactor statistics and of the SM3 accumulators cross ranks.  `optsgpt`: GPT-2 tiny, whose
     plan is data parallel with ZeRO-sharded updates -- the update sees a dim-0 chunk (dynamic_slice) of every variable.
+    `dp2tp2` on 4 ranks: both at once -- variables stored split over the tensor-parallel level AND updated in ZeRO chunks over
+    the data-parallel level, so a reduction has to cross two mesh levels.
     The planner rules (rules.cc AdafactorRule / Sm3Rule) lay out the reduced-shape slots, the executor completes the reductions
     across ranks (runtime/optimizers.py Shards).  Losses must match one process updating whole variables."""
     sys.path.insert(0, HERE)
     import dist_worker
     ref = getattr(dist_worker, "case_" + case)("auto")["opts"]
-    got = _run(f"{case}:auto", 2, tmp_path)["opts"]
+    got = _run(f"{case}:{strategy}", world, tmp_path)["opts"]
     tol = 5e-6 if case == "opts" else 2e-5        # (summation order only; measured deviation ~1e-7)
     for kind, r in ref.items():
         assert r["sharded_updates"] == 0
