@@ -113,8 +113,12 @@ struct Rewriter {
       a["mean_divisor"] = n.has("mean_divisor") ? n.attr_i("mean_divisor") : cnt;
     }
     if ((op == "batchnorm" || op == "batchnorm_bwd") && c.tag == "batch") {
-      a["sync_level"] = (int64_t)level;
-      a["sync_num"] = (int64_t)num;
+      // the batch statistics span every level that splits the batch: the runtime completes them across those levels
+      std::vector<int64_t> lv = n.attr_v("sync_levels"), nm = n.attr_v("sync_nums");
+      lv.push_back((int64_t)level);
+      nm.push_back((int64_t)num);
+      a["sync_levels"] = lv;
+      a["sync_nums"] = nm;
     }
     if (IsSource(op) && op != "constant" && c.outs[0].is_split()) {
       // sharded variable / input: remember how this level cut the FULL tensor so init / feeding can slice

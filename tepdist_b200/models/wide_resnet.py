@@ -53,7 +53,7 @@ def _block(b: GraphBuilder, x: Value, cin: int, f: int, width: int, stride: int,
     return b.relu(b.add(y, sc, name=f"{name}/add"), name=f"{name}/out"), 4 * f
 
 
-def build_wide_resnet_graph(cfg: WideResNetConfig, dtype: str = "bf16") -> Graph:
+def build_wide_resnet_graph(cfg: WideResNetConfig, dtype: str = "bf16", optimizer: str = "adamw") -> Graph:
     C, W, blocks = cfg.spec
     b = GraphBuilder(f"wide_resnet_{cfg.model_type}", compute_dtype=dtype)
     x = b.input("images", (cfg.batch, 3, cfg.image, cfg.image), dtype)
@@ -70,6 +70,7 @@ def build_wide_resnet_graph(cfg: WideResNetConfig, dtype: str = "bf16") -> Graph
     bf = b.parameter("fc/b", (cfg.classes,), {"kind": "constant", "value": 0.0})
     logits = b.linear(feat, wf, bf, name="fc")
     loss = b.softmax_xent(logits, labels, vocab=cfg.classes, name="loss")
-    g = build_training_step(b, loss, "adamw", lr=cfg.lr, beta1=0.9, beta2=0.999, eps=1e-8, weight_decay=0.0)
+    # reference: train_imagenet.py:42 AdamOptimizer(0.1) (the default here), resnet_train.py:34 MomentumOptimizer(0.01, 0.9)
+    g = build_training_step(b, loss, optimizer, lr=cfg.lr, beta1=0.9, beta2=0.999, eps=1e-8, weight_decay=0.0, momentum=0.9)
     g.meta["model"] = {"family": "wide_resnet", "model_type": cfg.model_type, "batch": cfg.batch, "image": cfg.image}
     return g

@@ -326,6 +326,7 @@ class Executor:
                 self.free_after.setdefault(nid, []).append(k_)
         self.ln_stats: Dict[Tuple[Tuple[int, int], Tuple[int, int]], Tuple[torch.Tensor, torch.Tensor]] = {}
         self.bn_stats: Dict[Tuple[int, Tuple[int, int]], Tuple[torch.Tensor, torch.Tensor]] = {}
+        self.bn_sync_stats: Dict[Tuple[int, Tuple[int, int]], Tuple[torch.Tensor, torch.Tensor]] = {}
         self.input_names = [n.name for n in g.inputs()]
         self.grad_accumulate = False   # True when gradients add up over micro-batches (pipeline stage workers)
         self._plan_store_init()
@@ -878,6 +879,61 @@ class Executor:
             comp.copy_(master.to(comp.dtype))
         env[(n.id, 0)] = comp if comp.is_contiguous() else comp.contiguous()
 
+    def _bn_sync_levels(self, n: Node) -> List[Tuple[int, int]]:
+        """(level, num) pairs over which a batch-split BatchNorm has to complete its statistics: the levels the transform
+        recorded, minus time-multiplexed ones (micro-batches of a pipeline normalise on their own, as in the reference)."""
+        if self.collective is None or self.collective.mesh.world == 1:
+            return []
+        out = []
+        for lvl, num in zip(n.attrs.get("sync_levels", []), n.attrs.get("sync_nums", [])):
+            if int(num) > 1 and self.collective.mesh.group(int(lvl)) is not None:
+                out.append((int(lvl), int(num)))
+        return out
+
+    def _batchnorm_synced(self, n: Node, ins: List[torch.Tensor]) -> List[torch.Tensor]:
+        """Training-mode BatchNorm whose batch is split over devices: per-channel sums are completed across the splitting levels
+        (two small all-reduces forward -- mean, then centred second moment, i.e. the same two-pass variance as one device --
+        and one backward), so the result equals BatchNorm over the global batch.  The reference gets this from XLA's SPMD
+        treatment of the batch reductions; without it data-parallel conv nets silently train with per-shard statistics.
+        dgamma / dbeta stay LOCAL partial sums: the plan reduces them with the other gradients."""
+        import torch.distributed as dist
+        levels = self._bn_sync_levels(n)
+        mesh = self.collective.mesh
+
+        def allsum(t: torch.Tensor) -> torch.Tensor:
+            if not self.collective.dry:
+                for lvl, _ in levels:
+                    dist.all_reduce(t, group=mesh.group(lvl))
+            return t
+        a = n.attrs
+        if n.op == "batchnorm":
+            xx, gm, bt = ins
+        else:
+            dy, xx, gm = ins
+        xf = xx.float()
+        cnt = float(xf.numel() // xf.shape[1])
+        for _, num in levels:
+            cnt *= num
+        key = (self._tag, n.inputs[0 if n.op == "batchnorm" else 1].key())
+        st_ = self.bn_sync_stats.pop(key, None) if n.op == "batchnorm_bwd" else None
+        if st_ is None:
+            mean = allsum(xf.sum((0, 2, 3))) / cnt
+            var = allsum(((xf - mean.view(1, -1, 1, 1)) ** 2).sum((0, 2, 3))) / cnt
+            rstd = torch.rsqrt(var + a["eps"])
+        else:
+            mean, rstd = st_
+        xh = (xf - mean.view(1, -1, 1, 1)) * rstd.view(1, -1, 1, 1)
+        if n.op == "batchnorm":
+            self.bn_sync_stats[key] = (mean, rstd)      # consumed by the matching batchnorm_bwd
+            return [(xh * gm.float().view(1, -1, 1, 1) + bt.float().view(1, -1, 1, 1)).to(xx.dtype)]
+        dyf = dy.float()
+        g_ = dyf * gm.float().view(1, -1, 1, 1)
+        s = allsum(torch.stack([g_.sum((0, 2, 3)), (g_ * xh).sum((0, 2, 3))])) / cnt
+        dx = rstd.view(1, -1, 1, 1) * (g_ - s[0].view(1, -1, 1, 1) - xh * s[1].view(1, -1, 1, 1))
+        dg = self._grad_out(n, 1, n.outputs[1].shape); dg.add_((dyf * xh).sum((0, 2, 3)))
+        db = self._grad_out(n, 2, n.outputs[2].shape); db.add_(dyf.sum((0, 2, 3)))
+        return [dx.to(xx.dtype), dg, db]
+
     def _fused_apply(self) -> None:
         st, o = self.store, self.opt
         kind = o.get("kind")
@@ -1262,6 +1318,8 @@ class Executor:
             out = self._grad_out(n, 0, n.outputs[0].shape)
             out.add_(gw.float())
             return [out]
+        if op in ("batchnorm", "batchnorm_bwd") and self._bn_sync_levels(n):
+            return self._batchnorm_synced(n, ins)
         if op == "batchnorm":
             xx, gm, bt = ins
             if ops.bn_native_ok(xx) and gm.dtype == torch.float32:

@@ -168,6 +168,20 @@ def case_optsgpt(strategy):
     return {"losses": [], "parallelism": strategy, "collectives": None, "opts": out}
 
 
+def case_conv(strategy):
+    """Small conv net with BatchNorm (models/smoke.py): under a batch split the BN statistics must be completed across ranks."""
+    from tepdist_b200.api import Trainer
+    from tepdist_b200.models.smoke import build_conv_graph
+    g = build_conv_graph(batch=8)
+    tr = Trainer(g, strategy=strategy, device=torch.device("cpu"), use_cuda_graph=False)
+    torch.manual_seed(0)
+    feeds = {"x": torch.randn(8, 3, 16, 16), "t": torch.randn(8, 10)}
+    losses = [tr.step(feeds) for _ in range(4)]
+    gg = getattr(tr.exec, "g", None)
+    synced = sum(1 for n in gg.nodes if n.op.startswith("batchnorm") and n.attrs.get("sync_levels")) if gg is not None else 0
+    return {"losses": losses, "parallelism": tr.plan_info.get("parallelism"), "collectives": tr.plan_info.get("collectives"), "synced_bn": synced}
+
+
 def case_mlp(strategy):
     """examples/smoke_testing-style 2-layer MLP; planner emits a DP shard on CPU/gloo world_size=2 (BASELINE config 1)."""
     from tepdist_b200.api import Trainer
@@ -197,7 +211,7 @@ def case_moe(strategy):
 if __name__ == "__main__":
     case, out = sys.argv[1], sys.argv[2]
     name, _, strat = case.partition(":")
-    res = {"gpt2": case_gpt2, "gpt2s": lambda st: case_gpt2(st, True), "gpt2b1": lambda st: case_gpt2(st, False, 1), "mlp": case_mlp, "moe": case_moe, "ckpt": case_ckpt, "state": case_state, "tpfused": case_tpfused, "manualdp": case_manualdp, "opts": case_opts, "optsgpt": case_optsgpt}[name](strat or "auto")
+    res = {"gpt2": case_gpt2, "gpt2s": lambda st: case_gpt2(st, True), "gpt2b1": lambda st: case_gpt2(st, False, 1), "mlp": case_mlp, "moe": case_moe, "ckpt": case_ckpt, "state": case_state, "tpfused": case_tpfused, "manualdp": case_manualdp, "opts": case_opts, "optsgpt": case_optsgpt, "conv": case_conv}[name](strat or "auto")
     if int(os.environ.get("RANK", "0")) == 0:
         json.dump(res, open(out, "w"))
     if dist.is_initialized():

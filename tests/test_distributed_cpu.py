@@ -88,6 +88,23 @@ def test_reduction_optimizers_match_single_process_when_sharded(tmp_path, case, 
             assert abs(a - b) <= tol * max(1.0, abs(b)), (case, kind, got[kind]["losses"], r["losses"])
 
 
+@pytest.mark.parametrize("strategy,world", [("dp", 2), ("auto", 4), ("dp2tp2", 4)])
+def test_conv_net_with_batchnorm_matches_single_process(tmp_path, strategy, world):
+    """Training-mode BatchNorm under a batch split: the planner marks the levels that split the batch (transform.cc
+    sync_levels) and the executor completes the per-channel sums across them, so a data-parallel conv net trains like one
+    device on the global batch (the reference gets this from XLA's SPMD handling of the batch reductions).  Before this
+    existed the executor ignored the marks and every shard normalised with its own statistics: step-0 loss 1.1669 vs 1.1625."""
+    sys.path.insert(0, HERE)
+    import dist_worker
+    ref = dist_worker.case_conv("auto")
+    got = _run(f"conv:{strategy}", world, tmp_path)
+    assert ref["synced_bn"] == 0
+    if strategy == "dp":
+        assert got["synced_bn"] >= 2, got          # forward + backward node of the batch-split BatchNorm
+    for a, b in zip(got["losses"], ref["losses"]):
+        assert abs(a - b) <= 1e-5 * max(1.0, abs(b)), (strategy, got, ref["losses"])
+
+
 def test_manual_data_parallel_through_the_grad_sync_hook(tmp_path):
     """The executor's `grad_sync` hook with the bucketed all-reduce of parallel/dp.py (the reference's plain DAPPLEAllReduce
     semantics, no planner involved): two ranks on half batches == one process on the whole batch."""
