@@ -91,16 +91,22 @@ class Trainer:
         """Device-resident variant (no host sync): returns the loss tensor."""
         return self.exec.step(dev_feeds)[0]
 
+    def executor(self):
+        """The Executor that owns this rank's variables: the whole (sharded) step graph, or -- under a pipeline plan -- this
+        rank's stage."""
+        w = getattr(self.exec, "worker", None)
+        return w.exec if w is not None else self.exec
+
     def set_lr_schedule(self, fn) -> None:
         """`fn(step) -> lr` for the 1-based optimizer step (see utils/schedules.py); None = the graph's constant rate."""
-        ex = getattr(self.exec, "worker", None)
-        (ex.exec if ex is not None else self.exec).set_lr_schedule(fn)
+        self.executor().set_lr_schedule(fn)
 
     def state_dict(self):
         """Master weights (+ optimizer moments).  Collective under sharded-optimizer plans: every rank must call it."""
-        if hasattr(self.exec, "materialize_full_state"):
-            self.exec.materialize_full_state()
-        return self.exec.store.state_dict()
+        ex = self.executor()
+        if hasattr(ex, "materialize_full_state"):
+            ex.materialize_full_state()
+        return ex.store.state_dict()
 
     # ------------------------------------------------------------------ sharded checkpoints (reference DoRemoteSave / Restore)
     def _ckpt(self, root: str, max_to_keep: int = 5):
@@ -112,8 +118,8 @@ class Trainer:
 
     def save(self, root: str, global_step: int, max_to_keep: int = 5) -> str:
         """Every rank writes its own shards (master weights + optimizer moments) under root/ckpt_<rank>_of_<world>/."""
-        return self._ckpt(root, max_to_keep).save(self.exec, global_step)
+        return self._ckpt(root, max_to_keep).save(self.executor(), global_step)
 
     def restore(self, root: str, global_step: Optional[int] = None) -> int:
         """Load this rank's shards of `global_step` (default: the latest kept step); returns the restored step."""
-        return self._ckpt(root).restore(self.exec, global_step)
+        return self._ckpt(root).restore(self.executor(), global_step)

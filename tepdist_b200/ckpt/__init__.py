@@ -159,16 +159,21 @@ class CheckpointManager:
             for man, tens in writers:
                 meta = man.get(section, {}).get(name)
                 if meta is None or name + suffix not in tens:
-                    return None
+                    continue         # (a pipeline writer holds only its own stage's variables)
                 if suffix and not meta.get("flat_moments", True):
                     return None      # (the writer kept its moments as separately sharded slots: see the "slots" section)
                 if full is None:
                     full = torch.zeros(meta["full_shape"], dtype=torch.float32)
-                view = full
+                    covered = torch.zeros(meta["full_shape"], dtype=torch.bool)
+                view, cview = full, covered
                 for d_, n_, l_ in zip(meta["shard_dims"], meta["shard_nums"], meta["shard_levels"]):
                     sz = view.shape[d_] // n_
-                    view = view.narrow(d_, int(meta["coords"].get(str(l_), 0)) * sz, sz)
+                    o_ = int(meta["coords"].get(str(l_), 0)) * sz
+                    view, cview = view.narrow(d_, o_, sz), cview.narrow(d_, o_, sz)
                 view.copy_(tens[name + suffix].reshape(meta["shard_shape"]))
+                cview.fill_(True)
+            if full is not None and not bool(covered.all()):
+                raise FileNotFoundError(f"checkpoint step {step}: the shards found for {name + suffix} do not cover the whole tensor")
             return full
 
         from ..runtime.executor import shard_of

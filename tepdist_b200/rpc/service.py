@@ -114,27 +114,27 @@ class ServiceImpl:
                 self.fake_input_cache = feeds
             feeds = self.fake_input_cache
         if self.restore_request is not None:      # restore happens during warm-up of the next ExecutePlan
-            self.ckpt.restore(tr.exec if hasattr(tr.exec, "store") else tr.exec, self.restore_request if self.restore_request >= 0 else None)
+            self.ckpt.restore(tr.executor(), self.restore_request if self.restore_request >= 0 else None)
             self.restore_request = None
         loss = tr.step(feeds)
         if not self.warmed_up:
             self.warmed_up = True
             if self.ckpt is not None:
-                self.ckpt.maybe_lazy_save(tr.exec)
+                self.ckpt.maybe_lazy_save(tr.executor())
         return loss, tr
 
     def _do_save(self, msg):
         tr = self.cache.get(msg["handle"]) if msg.get("handle") else None
         self.ckpt.max_to_keep = msg.get("max_to_keep", self.ckpt.max_to_keep)
         if self.ckpt.request_save(msg["global_step"], self.warmed_up):
-            return self.ckpt.save(tr.exec, msg["global_step"])
+            return self.ckpt.save(tr.executor(), msg["global_step"])
         return "lazy"
 
     def _do_sync_state(self, msg):
         """Make fp32 master weights / moments whole on every rank (sharded-optimizer plans keep only the owned chunk fresh)."""
         tr = self.cache.get(msg["handle"])
-        if hasattr(tr.exec, "materialize_full_state"):
-            tr.exec.materialize_full_state()
+        if hasattr(tr.executor(), "materialize_full_state"):
+            tr.executor().materialize_full_state()
 
     def _do_restore(self, msg):
         self.restore_request = msg.get("global_step", -1)
@@ -173,7 +173,7 @@ class ServiceImpl:
                 msg = {"cmd": "sync_state", "handle": m["handle"]}
                 self._bcast(msg)
                 self._do_sync_state(msg)
-            sd = tr.exec.store.state_dict()
+            sd = tr.executor().store.state_dict()
             out["vars"] = {k: sd[k].cpu() for k in m["fetch_vars"] if k in sd}
         return pack(out)
 
@@ -184,7 +184,7 @@ class ServiceImpl:
             msg = {"cmd": "sync_state", "handle": m["handle"]}
             self._bcast(msg)
             self._do_sync_state(msg)
-        sd = tr.exec.store.state_dict()
+        sd = tr.executor().store.state_dict()
         names = m.get("names") or [k for k in sd if not k.endswith(("/m", "/v"))]
         return pack({k: sd[k].cpu() for k in names if k in sd})
 

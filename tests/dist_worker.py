@@ -49,6 +49,20 @@ def case_ckpt(strategy):
     return {"losses": before + after, "parallelism": tr.plan_info.get("parallelism"), "collectives": tr.plan_info.get("collectives")}
 
 
+def case_resume(strategy):
+    """Start a fresh job under `strategy` (different seed), restore the latest checkpoint in $TEPDIST_TEST_CKPT, train 2 steps."""
+    from tepdist_b200.api import Trainer
+    from tepdist_b200.models.gpt2 import CONFIGS, build_gpt2_graph
+    cfg = CONFIGS["tiny"]
+    tr = Trainer(build_gpt2_graph(cfg, batch=4, optimizer=os.environ.get("TEPDIST_TEST_OPT", "adamw")), strategy=strategy,
+                 device=torch.device("cpu"), use_cuda_graph=False, seed=123)
+    step = tr.restore(os.environ["TEPDIST_TEST_CKPT"])
+    torch.manual_seed(0)
+    tok = torch.randint(0, cfg.n_vocab, (4, cfg.n_ctx), dtype=torch.int32)
+    feeds = {"tokens": tok, "labels": torch.roll(tok, -1, 1)}
+    return {"losses": [tr.step(feeds) for _ in range(2)], "parallelism": tr.plan_info.get("parallelism"), "collectives": None, "step": step}
+
+
 def case_state(strategy):
     """After a few sharded-optimizer steps every rank's state_dict must hold the SAME, fully updated master weights."""
     from tepdist_b200.api import Trainer
@@ -211,7 +225,7 @@ def case_moe(strategy):
 if __name__ == "__main__":
     case, out = sys.argv[1], sys.argv[2]
     name, _, strat = case.partition(":")
-    res = {"gpt2": case_gpt2, "gpt2s": lambda st: case_gpt2(st, True), "gpt2b1": lambda st: case_gpt2(st, False, 1), "mlp": case_mlp, "moe": case_moe, "ckpt": case_ckpt, "state": case_state, "tpfused": case_tpfused, "manualdp": case_manualdp, "opts": case_opts, "optsgpt": case_optsgpt, "conv": case_conv}[name](strat or "auto")
+    res = {"gpt2": case_gpt2, "gpt2s": lambda st: case_gpt2(st, True), "gpt2b1": lambda st: case_gpt2(st, False, 1), "mlp": case_mlp, "moe": case_moe, "ckpt": case_ckpt, "state": case_state, "tpfused": case_tpfused, "manualdp": case_manualdp, "opts": case_opts, "optsgpt": case_optsgpt, "conv": case_conv, "resume": case_resume}[name](strat or "auto")
     if int(os.environ.get("RANK", "0")) == 0:
         json.dump(res, open(out, "w"))
     if dist.is_initialized():

@@ -220,6 +220,40 @@ def test_checkpoint_with_reduced_shape_optimizer_slots_restores_into_one_process
     assert any(abs(a - b) > 1e-5 * max(1.0, abs(b)) for a, b in zip(blind, resumed)), (opt, blind, resumed)
 
 
+def test_checkpoint_written_by_a_pipeline_restores_into_one_process_and_into_the_pipeline(tmp_path):
+    """Under a pipeline plan every rank owns only its stage's variables and writes just those (reference: every worker saves the
+    slices it holds).  The two stage checkpoints together restore (a) into a single process, which continues like the pipeline
+    did, and (b) into a fresh 2-stage pipeline job."""
+    import torch
+    ck = str(tmp_path / "ck")
+    (tmp_path / "w").mkdir(); (tmp_path / "r").mkdir()
+    got = _run("ckpt:pp2m2", 2, tmp_path / "w", {"TEPDIST_TEST_CKPT": ck})
+    assert got["parallelism"].startswith("pp2"), got
+    import json as _json
+    names = [set(_json.load(open(os.path.join(ck, f"ckpt_{r}_of_2", "step_2", "manifest.json")))["vars"]) for r in (0, 1)]
+    assert names[0] and names[1] and not (names[0] & names[1]), "each stage writes its own variables only"
+    from tepdist_b200.api import Trainer
+    from tepdist_b200.models.gpt2 import CONFIGS, build_gpt2_graph
+    cfg = CONFIGS["tiny"]
+    tr = Trainer(build_gpt2_graph(cfg, batch=4), device=torch.device("cpu"), use_cuda_graph=False, seed=77)
+    assert tr.restore(ck) == 2
+    torch.manual_seed(0)
+    tok = torch.randint(0, cfg.n_vocab, (4, cfg.n_ctx), dtype=torch.int32)
+    feeds = {"tokens": tok, "labels": torch.roll(tok, -1, 1)}
+    resumed = [tr.step(feeds) for _ in range(2)]
+    for a, b in zip(resumed, got["losses"][2:]):
+        assert abs(a - b) <= 2e-4 * max(1.0, abs(b)), (resumed, got["losses"])
+    again = _run("resume:pp2m2", 2, tmp_path / "r", {"TEPDIST_TEST_CKPT": ck})
+    for a, b in zip(again["losses"], got["losses"][2:]):
+        assert abs(a - b) <= 2e-5 * max(1.0, abs(b)), (again["losses"], got["losses"])
+    # a missing stage must be noticed, not filled with zeros
+    import shutil
+    shutil.rmtree(os.path.join(ck, "ckpt_1_of_2"))
+    tr2 = Trainer(build_gpt2_graph(cfg, batch=4), device=torch.device("cpu"), use_cuda_graph=False, seed=77)
+    with pytest.raises((FileNotFoundError, KeyError)):
+        tr2.restore(ck, 2)
+
+
 def test_state_dict_is_whole_and_identical_on_every_rank(tmp_path):
     """state_dict() must return the same, fully updated weights on every rank of a sharded-optimizer run.
     NOTE: on CPU the store has no separate bf16 compute copy (the master itself is all-gathered each step), so the
