@@ -101,6 +101,55 @@ class Trainer:
         """`fn(step) -> lr` for the 1-based optimizer step (see utils/schedules.py); None = the graph's constant rate."""
         self.executor().set_lr_schedule(fn)
 
+    def full_state_dict(self, moments: bool = False, dst: int = 0):
+        """WHOLE variables by name, whatever the plan did to them (ZeRO chunks, tensor-parallel shards, pipeline stages): every
+        rank contributes what it stores, rank `dst` assembles (coverage-checked) and returns the dict, the others return {}.
+        Collective: every rank must call it.  Meant for fetching / inspection (everything travels through host memory)."""
+        import torch.distributed as dist
+        ex = self.executor()
+        if hasattr(ex, "materialize_full_state"):
+            ex.materialize_full_state()
+        st, g = ex.store, ex.g
+        sd = st.state_dict()
+        mine = {}
+        for pid in st.order:
+            n, name = g.nodes[pid], st.names[pid]
+            meta = (list(n.attrs.get("full_shape", st.shape[pid])), list(n.attrs.get("shard_dims", [])), list(n.attrs.get("shard_nums", [])),
+                    [int(ex.coords.get(int(l), 0)) for l in n.attrs.get("shard_levels", [])])
+            keys = [name] + ([name + "/m", name + "/v"] if moments else [])
+            for k in keys:
+                if k in sd and tuple(sd[k].shape) == tuple(st.shape[pid]):
+                    mine[k] = (meta, sd[k].detach().cpu())
+        if moments:      # optimizer slots the execution keeps outside the flat buffers, with their own shard description
+            for n in st._state_nodes:
+                if st.slot_is_live(n):
+                    t = st.state[n.id]
+                    mine[n.name] = ((list(n.attrs.get("full_shape", t.shape)), list(n.attrs.get("shard_dims", [])),
+                                     list(n.attrs.get("shard_nums", [])),
+                                     [int(ex.coords.get(int(l), 0)) for l in n.attrs.get("shard_levels", [])]), t.detach().cpu())
+        if self.world == 1:
+            return {k: t for k, (_, t) in mine.items()}
+        parts = [None] * self.world if self.rank == dst else None
+        dist.gather_object(mine, parts, dst=dst)
+        if self.rank != dst:
+            return {}
+        out, covered = {}, {}
+        for part in parts:
+            for k, ((full_shape, dims, nums, idx), t) in part.items():
+                if k not in out:
+                    out[k] = torch.zeros(full_shape, dtype=t.dtype)
+                    covered[k] = torch.zeros(full_shape, dtype=torch.bool)
+                view, cview = out[k], covered[k]
+                for d_, n_, i_ in zip(dims, nums, idx):
+                    sz = view.shape[d_] // n_
+                    view, cview = view.narrow(d_, i_ * sz, sz), cview.narrow(d_, i_ * sz, sz)
+                view.copy_(t.reshape(view.shape))
+                cview.fill_(True)
+        bad = [k for k, c in covered.items() if not bool(c.all())]
+        if bad:
+            raise RuntimeError(f"full_state_dict: incomplete variables {bad[:4]}")
+        return out
+
     def state_dict(self):
         """Master weights (+ optimizer moments).  Collective under sharded-optimizer plans: every rank must call it."""
         ex = self.executor()

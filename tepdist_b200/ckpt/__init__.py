@@ -44,7 +44,7 @@ class CheckpointManager:
                                     "step_count": executor.step_count, "extra": extra or {}}
         tensors: Dict[str, torch.Tensor] = {}
         # variables whose first / second moments live in the flat m / v buffers (others keep them as separate slot tensors)
-        flat_moments = {n.attrs.get("slot_of") for n in getattr(st, "_state_nodes", []) if st.m is not None and st._flat_slot(n)}
+        flat_moments = {pid for pid in st.order if st.moments_flat(pid)} if hasattr(st, "moments_flat") else set()
         for pid in st.order:
             n = g.nodes[pid]
             name = st.names[pid]
@@ -62,7 +62,7 @@ class CheckpointManager:
         # separately stored shards of m / v): same shard description as a variable, under their own name
         manifest["slots"] = {}
         for n in getattr(st, "_state_nodes", []):
-            if n.id in st.state and not st._flat_slot(n):
+            if st.slot_is_live(n):
                 t = st.state[n.id]
                 tensors[n.name] = t.detach().cpu().reshape(-1).clone()
                 manifest["slots"][n.name] = {
@@ -116,7 +116,7 @@ class CheckpointManager:
                 st._view(st.m, pid).copy_(tensors[name + "/m"].reshape(st.shape[pid]).to(st.device))
                 st._view(st.v, pid).copy_(tensors[name + "/v"].reshape(st.shape[pid]).to(st.device))
         for n in getattr(st, "_state_nodes", []):
-            if n.name in manifest.get("slots", {}) and n.name in tensors and n.id in st.state and not st._flat_slot(n):
+            if n.name in manifest.get("slots", {}) and n.name in tensors and st.slot_is_live(n):
                 st.state[n.id].copy_(tensors[n.name].reshape(st.state[n.id].shape).to(st.device))
         st.sync_compute()
         executor.step_count = int(manifest.get("step_count", step))
@@ -185,6 +185,8 @@ class CheckpointManager:
                 if dst is None:
                     continue
                 full = assemble(name, suffix)
+                if full is None and suffix:
+                    full = assemble(name + suffix, "", "slots")      # the writer kept this moment as a separately sharded slot
                 if full is None:
                     if suffix == "":
                         raise KeyError(f"variable {name} missing from checkpoint step {step}")

@@ -133,8 +133,8 @@ class ServiceImpl:
     def _do_sync_state(self, msg):
         """Make fp32 master weights / moments whole on every rank (sharded-optimizer plans keep only the owned chunk fresh)."""
         tr = self.cache.get(msg["handle"])
-        if hasattr(tr.executor(), "materialize_full_state"):
-            tr.executor().materialize_full_state()
+        # whole variables on the master, whatever the plan did to them (ZeRO chunks, stored shards, pipeline stages)
+        self._full_state = tr.full_state_dict(moments=True, dst=0)
 
     def _do_restore(self, msg):
         self.restore_request = msg.get("global_step", -1)
@@ -173,7 +173,7 @@ class ServiceImpl:
                 msg = {"cmd": "sync_state", "handle": m["handle"]}
                 self._bcast(msg)
                 self._do_sync_state(msg)
-            sd = tr.executor().store.state_dict()
+            sd = self._full_state
             out["vars"] = {k: sd[k].cpu() for k in m["fetch_vars"] if k in sd}
         return pack(out)
 
@@ -184,7 +184,7 @@ class ServiceImpl:
             msg = {"cmd": "sync_state", "handle": m["handle"]}
             self._bcast(msg)
             self._do_sync_state(msg)
-        sd = tr.executor().store.state_dict()
+        sd = self._full_state
         names = m.get("names") or [k for k in sd if not k.endswith(("/m", "/v"))]
         return pack({k: sd[k].cpu() for k in names if k in sd})
 

@@ -90,6 +90,10 @@ class VariableStore:
         self.grad = torch.zeros(self.total, **f32)
         self.m: Optional[torch.Tensor] = None
         self.v: Optional[torch.Tensor] = None
+        # variables whose first / second moments the EXECUTION keeps in the flat m / v buffers (set by the executor once it
+        # knows its update scheme; None = every variable, the single-process fused update).  The sharded-optimizer path keeps
+        # them there even though the plan's slot nodes are chunk-shaped -- those slot tensors are then never touched.
+        self.flat_moment_pids: Optional[set] = None
         self.compute = (torch.zeros(self.total, dtype=torch.bfloat16, device=device)
                         if device.type == "cuda" else None)
         self.names = {n.id: n.name for n in params}
@@ -134,6 +138,16 @@ class VariableStore:
         return (pid in self.shape and self.shape[pid] == tuple(n.outputs[0].shape)
                 and (n.name.endswith("/m") or n.name.endswith("/v")))
 
+    def moments_flat(self, pid: int) -> bool:
+        return self.m is not None and (self.flat_moment_pids is None or pid in self.flat_moment_pids)
+
+    def slot_is_live(self, n) -> bool:
+        """A slot tensor outside the flat buffers that the execution really updates (not shadowed by flat moments)."""
+        if n.id not in self.state or self._flat_slot(n):
+            return False
+        pid = n.attrs.get("slot_of")
+        return not (self.moments_flat(pid) and (n.name.endswith("/m") or n.name.endswith("/v")))
+
     def ensure_slots(self, flat_moments: bool = False) -> None:
         """`flat_moments`: the graph updates with AdamW, whose flat paths (fused whole-buffer update, sharded-optimizer
         chunks) address m / v by FLAT offset even when every slot node of the plan is chunk-shaped -- always allocate them."""
@@ -174,10 +188,10 @@ class VariableStore:
     def state_dict(self) -> Dict[str, torch.Tensor]:
         out = {self.names[p]: self.master_view(p).detach().clone() for p in self.order}
         if self.m is not None:
-            out.update({self.names[p] + "/m": self._view(self.m, p).detach().clone() for p in self.order})
-            out.update({self.names[p] + "/v": self._view(self.v, p).detach().clone() for p in self.order})
+            out.update({self.names[p] + "/m": self._view(self.m, p).detach().clone() for p in self.order if self.moments_flat(p)})
+            out.update({self.names[p] + "/v": self._view(self.v, p).detach().clone() for p in self.order if self.moments_flat(p)})
         for n in self._state_nodes:     # slots outside the flat buffers
-            if n.id in self.state and not self._flat_slot(n):
+            if self.slot_is_live(n):
                 out[n.name] = self.state[n.id].detach().clone()
         return out
 
@@ -191,7 +205,7 @@ class VariableStore:
                 self._view(self.m, p).copy_(sd[nm + "/m"].to(self.device))
                 self._view(self.v, p).copy_(sd[nm + "/v"].to(self.device))
         for n in self._state_nodes:
-            if n.name in sd and not self._flat_slot(n):
+            if n.name in sd and not self._flat_slot(n) and tuple(sd[n.name].shape) == tuple(n.outputs[0].shape):
                 self.ensure_slots()
                 self.state[n.id].copy_(sd[n.name].to(self.device).reshape(self.state[n.id].shape))
         self.sync_compute()
@@ -279,6 +293,18 @@ class Executor:
         self.flat_zero: Optional[Dict[str, Any]] = None
         if self._fz_static is not None and self.collective is not None:
             self._detect_flat_zero()
+        # where each variable's moments really live (see VariableStore.flat_moment_pids)
+        if not (self.fused_apply_ok and self.flat_zero is None):
+            flat = {n_.attrs.get("slot_of") for n_ in self.store._state_nodes if self.store._flat_slot(n_)}
+            if self.flat_zero is not None:
+                def _root(v):
+                    nd_ = g.nodes[v.node]
+                    while nd_.op == "dynamic_slice":
+                        nd_ = g.nodes[nd_.inputs[0].node]
+                    return nd_.id
+                flat |= {_root(g.nodes[aid].inputs[0]) for aid in self.flat_zero["regular_apply"]}
+                flat |= {pid_ for (pid_, _, _, _) in (self.flat_zero.get("replicated_apply") or {}).values()}
+            self.store.flat_moment_pids = flat
         # peephole: dX_total = add(dX_residual, layernorm_bwd.dx) -> the LN-backward kernel adds the residual gradient
         self.ln_fuse: Dict[int, Tuple[int, int]] = {}
         self.alias_of: Dict[int, Tuple[int, int]] = {}

@@ -86,6 +86,25 @@ def case_state(strategy):
             "collectives": tr.plan_info.get("collectives")}
 
 
+def case_fullstate(strategy):
+    """Whole variables (+ moments) assembled on rank 0 by Trainer.full_state_dict after 3 steps: names, shapes and a value signature."""
+    from tepdist_b200.api import Trainer
+    from tepdist_b200.models.gpt2 import CONFIGS, build_gpt2_graph
+    cfg = CONFIGS["tiny"]
+    if strategy.startswith(("pp", "dp2")) and int(os.environ.get("WORLD_SIZE", "1")) == 1:
+        strategy = "auto"
+    tr = Trainer(build_gpt2_graph(cfg, batch=4), strategy=strategy, device=torch.device("cpu"), use_cuda_graph=False)
+    torch.manual_seed(0)
+    tok = torch.randint(0, cfg.n_vocab, (4, cfg.n_ctx), dtype=torch.int32)
+    feeds = {"tokens": tok, "labels": torch.roll(tok, -1, 1)}
+    losses = [tr.step(feeds) for _ in range(3)]
+    sd = tr.full_state_dict(moments=True)
+    keys = sorted(sd)
+    return {"losses": losses, "parallelism": tr.plan_info.get("parallelism"), "collectives": None, "keys": keys,
+            "shapes": [list(sd[k].shape) for k in keys],
+            "signature": [float(sd[k].double().sum()) for k in keys] + [float(sd[k].double().abs().sum()) for k in keys]}
+
+
 class _EmulatedGemmAllReduce:
     """CPU stand-in for parallel.symm.GemmAllReduce with the same call contract: row-parallel partial GEMM, sum over the
     group, + bias + residual.  Lets the EXECUTOR side of the fused tensor-parallel path (chain detection, aliasing of the
@@ -225,7 +244,7 @@ def case_moe(strategy):
 if __name__ == "__main__":
     case, out = sys.argv[1], sys.argv[2]
     name, _, strat = case.partition(":")
-    res = {"gpt2": case_gpt2, "gpt2s": lambda st: case_gpt2(st, True), "gpt2b1": lambda st: case_gpt2(st, False, 1), "mlp": case_mlp, "moe": case_moe, "ckpt": case_ckpt, "state": case_state, "tpfused": case_tpfused, "manualdp": case_manualdp, "opts": case_opts, "optsgpt": case_optsgpt, "conv": case_conv, "resume": case_resume}[name](strat or "auto")
+    res = {"gpt2": case_gpt2, "gpt2s": lambda st: case_gpt2(st, True), "gpt2b1": lambda st: case_gpt2(st, False, 1), "mlp": case_mlp, "moe": case_moe, "ckpt": case_ckpt, "state": case_state, "tpfused": case_tpfused, "manualdp": case_manualdp, "opts": case_opts, "optsgpt": case_optsgpt, "conv": case_conv, "resume": case_resume, "fullstate": case_fullstate}[name](strat or "auto")
     if int(os.environ.get("RANK", "0")) == 0:
         json.dump(res, open(out, "w"))
     if dist.is_initialized():

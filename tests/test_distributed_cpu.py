@@ -191,7 +191,7 @@ def test_checkpoint_written_by_tp2_restores_into_one_process(tmp_path):
         assert abs(a - b) <= 2e-4 * max(1.0, abs(b)), (resumed, got)
 
 
-@pytest.mark.parametrize("opt,strategy", [("adafactor", "auto"), ("sm3", "tp"), ("lamb", "auto")])
+@pytest.mark.parametrize("opt,strategy", [("adafactor", "auto"), ("sm3", "tp"), ("lamb", "auto"), ("adamw", "auto")])
 def test_checkpoint_with_reduced_shape_optimizer_slots_restores_into_one_process(tmp_path, opt, strategy):
     """Adafactor row / column statistics, SM3 per-dimension accumulators and LAMB moments of a 2-rank run (ZeRO chunks under the
     data-parallel plan, stored shards under tensor parallelism) are written per rank with their shard description and
@@ -252,6 +252,21 @@ def test_checkpoint_written_by_a_pipeline_restores_into_one_process_and_into_the
     tr2 = Trainer(build_gpt2_graph(cfg, batch=4), device=torch.device("cpu"), use_cuda_graph=False, seed=77)
     with pytest.raises((FileNotFoundError, KeyError)):
         tr2.restore(ck, 2)
+
+
+@pytest.mark.parametrize("strategy,world", [("auto", 2), ("tp", 2), ("pp2m2", 2), ("dp2tp2", 4)])
+def test_full_state_dict_assembles_whole_variables_under_every_plan(tmp_path, strategy, world):
+    """Trainer.full_state_dict (what the RPC server's FetchResourceVars returns): ZeRO chunks, stored tensor-parallel shards,
+    pipeline stages and their combination all come back as the same whole, fully updated variables and moments that one process
+    holds after the same three steps."""
+    sys.path.insert(0, HERE)
+    import dist_worker
+    ref = dist_worker.case_fullstate("auto")
+    got = _run(f"fullstate:{strategy}", world, tmp_path)
+    assert got["keys"] == ref["keys"] and got["shapes"] == ref["shapes"], (set(ref["keys"]) ^ set(got["keys"]))
+    assert any(k.endswith("/m") for k in got["keys"])
+    for a, b in zip(got["signature"], ref["signature"]):
+        assert abs(a - b) <= 1e-3 * max(1.0, abs(b)), (strategy, a, b)
 
 
 def test_state_dict_is_whole_and_identical_on_every_rank(tmp_path):
