@@ -286,7 +286,17 @@ class Executor:
                 return False
             return all(g.nodes[v.node].op == "state" and tuple(g.type_of(v).shape) == tuple(g.type_of(n.inputs[0]).shape)
                        for v in n.inputs[2:])
-        self.fused_apply_ok = all(_whole(n) and n.op in FLAT_APPLY for n in self.apply_nodes)
+        # gradient clipping (reference examples/gpt_moe/optimizers/__init__.py:150-159: clip_by_norm per tensor / clip_by_global_norm):
+        # needs every gradient in its final form before any update starts, so the updates run per variable on the general
+        # path (no flat fused / sharded-optimizer kernels, which consume gradients bucket by bucket during backward)
+        self.clip: Optional[Tuple[str, float]] = None
+        if self.opt.get("clip_norm"):
+            if self.opt["clip_norm"] not in ("global", "local"):
+                raise ValueError(f"clip_norm={self.opt['clip_norm']!r}: expected 'global' or 'local'")
+            self.clip = (self.opt["clip_norm"], float(self.opt.get("clip_norm_value", 1.0)))
+        self._clip_scales: Dict[int, torch.Tensor] = {}
+        self.pipeline_norm_divisor = 0       # set by a pipeline stage worker: SPMD replicas per stage (0 = not a pipeline)
+        self.fused_apply_ok = self.clip is None and all(_whole(n) and n.op in FLAT_APPLY for n in self.apply_nodes)
         if not self.fused_apply_ok:
             self.grad_binding = {}  # general path: gradients flow through the environment, not the flat buffer
         self.update_target: Dict[Tuple[int, int], int] = {v.key(): var for var, v in g.updates.items()}
@@ -370,8 +380,9 @@ class Executor:
         to its conclusion; the per-tensor collectives of the plan become virtual.  Variables the planner treated
         differently (stored sharded, gradient re-laid-out by all-to-all, ...) keep the general per-tensor path."""
         apply_nodes = [n for n in g.nodes if n.op.startswith("apply_")]
-        if not apply_nodes or any(n.op not in FLAT_APPLY for n in apply_nodes):
-            return None     # (optimizers with per-variable reductions cannot be applied over flat, variable-straddling chunks)
+        if not apply_nodes or any(n.op not in FLAT_APPLY for n in apply_nodes) or (g.meta.get("optimizer") or {}).get("clip_norm"):
+            return None     # (optimizers with per-variable reductions cannot be applied over flat, variable-straddling chunks;
+                            #  gradient clipping needs all gradients before the first update)
         skip: set = set()
         binding: Dict[Tuple[int, int], int] = {}
         regular_apply: set = set()
@@ -824,17 +835,66 @@ class Executor:
             for n in self.apply_nodes:
                 env[(n.id, 0)] = self.store.compute_view(n.inputs[0].node)
         else:
+            if self.clip is not None:
+                self._compute_clip_scales(env)
             for n in self.apply_nodes:
                 self._apply_one(n, env)
         for n in g.nodes:
             if n.id in self.post_apply and not n.op.startswith("apply_"):
                 self._run_node(n, env, feeds)
 
+    def _shard_chain(self, v: Value) -> List[Tuple[int, int, int]]:
+        """[(dim, num, level)] that cut this rank's view `v` (a variable or dynamic_slices of one) out of the full variable."""
+        g = self.g
+        chain: List[Tuple[int, int, int]] = []
+        src = g.nodes[v.node]
+        while src.op == "dynamic_slice":
+            chain.insert(0, (int(src.attrs["dim"]), int(src.attrs["num"]), int(src.attrs["level"])))
+            src = g.nodes[src.inputs[0].node]
+        return [(int(d_), int(k_), int(l_)) for d_, k_, l_ in zip(src.attrs.get("shard_dims", []), src.attrs.get("shard_nums", []),
+                                                                  src.attrs.get("shard_levels", []))] + chain
+
+    def _compute_clip_scales(self, env: Dict[Tuple[int, int], torch.Tensor]) -> None:
+        """Per apply node: the factor its gradient is multiplied with.  'global': min(1, c / |all gradients|), 'local':
+        min(1, c / |this gradient|).  Norms are over WHOLE variables: a gradient that is a shard of its variable contributes its
+        local sum of squares, completed over the levels that shard it (one all-reduce per distinct set of levels); pipeline
+        stages add theirs up over the whole job.  Device tensors throughout: nothing synchronises, the step stays capturable."""
+        import torch.distributed as dist
+        mode, c = self.clip
+        live = self.collective is not None and not self.collective.dry and self.collective.mesh.world > 1
+        sq: Dict[int, torch.Tensor] = {}
+        by_levels: Dict[Tuple[int, ...], List[int]] = {}
+        for n in self.apply_nodes:
+            gr = env[n.inputs[1].key()].float()
+            sq[n.id] = (gr * gr).sum().reshape(1)
+            lv = tuple(sorted({l for _, k, l in self._shard_chain(n.inputs[0]) if k > 1})) if live else ()
+            by_levels.setdefault(lv, []).append(n.id)
+        for lv, ids in by_levels.items():
+            if lv:
+                t = torch.cat([sq[i] for i in ids])
+                for l in lv:
+                    dist.all_reduce(t, group=self.collective.mesh.group(l))
+                for j, i in enumerate(ids):
+                    sq[i] = t[j:j + 1]
+        if mode == "local":
+            for n in self.apply_nodes:
+                self._clip_scales[n.id] = torch.clamp(c / (torch.sqrt(sq[n.id]) + 1e-6), max=1.0).reshape(())
+            return
+        total = torch.cat(list(sq.values())).sum().reshape(1)
+        if self.pipeline_norm_divisor and dist.is_initialized():
+            total = total / float(self.pipeline_norm_divisor)     # every SPMD replica of a stage holds the stage's full sum
+            dist.all_reduce(total)
+        scale = torch.clamp(c / (torch.sqrt(total) + 1e-6), max=1.0).reshape(())
+        for n in self.apply_nodes:
+            self._clip_scales[n.id] = scale
+
     def _apply_one(self, n: Node, env: Dict[Tuple[int, int], torch.Tensor]) -> None:
         """General (un-fused) optimizer update of one variable or one shard of it (ZeRO-style plans: the update acts
         on dynamic_slice(parameter) with sharded slots; the updated shard is all-gathered by a later node)."""
         g, st, o = self.g, self.store, self.opt
         grad = env[n.inputs[1].key()].float().contiguous()
+        if self.clip is not None:
+            grad = grad * self._clip_scales[n.id]
 
         def storage(v: Value, which: str) -> torch.Tensor:
             """Persistent storage behind `v` (a variable/slot, or this rank's dynamic_slice of one)."""

@@ -74,6 +74,10 @@ class StageWorker:
         self.sub, self.idmap = self._extract(g, mine)
         self.exec = Executor(self.sub, device, seed=seed, collective=collective, coords=dict(coords or {}), comm_mode=comm_mode)
         self.exec.grad_accumulate = True    # gradients accumulate over micro-batches: atomically-added, zero-filled slots
+        spmd = 1
+        if collective is not None:
+            spmd = max(1, collective.mesh.world // max(1, num_stages))
+        self.exec.pipeline_norm_divisor = spmd   # global-norm clipping: stage sums are added up over the whole job
         self.exec._plan_store_init()
         ex = self.exec
         self.fwd_nodes = [n for n in self.sub.nodes if not n.backward and n.op not in ("state", "boundary") and n.id not in ex.post_apply]

@@ -86,6 +86,27 @@ def case_state(strategy):
             "collectives": tr.plan_info.get("collectives")}
 
 
+def case_clip(strategy):
+    """GPT-2 tiny with global-norm and per-tensor gradient clipping at a threshold that bites on every step."""
+    from tepdist_b200.api import Trainer
+    from tepdist_b200.frontend import builder
+    from tepdist_b200.models.gpt2 import CONFIGS, build_gpt2_graph
+    cfg = CONFIGS["tiny"]
+    if strategy.startswith(("pp", "dp2")) and int(os.environ.get("WORLD_SIZE", "1")) == 1:
+        strategy = "auto"
+    out = {}
+    for mode in ("none", "global", "local"):     # (SGD: AdamW would be invariant to a uniform rescaling of the gradients)
+        g = build_gpt2_graph(cfg, batch=4, optimizer="sgd")
+        g.meta["optimizer"].update(lr=0.5)
+        if mode != "none":
+            g.meta["optimizer"].update(clip_norm=mode, clip_norm_value=0.05)
+        tr = Trainer(g, strategy=strategy, device=torch.device("cpu"), use_cuda_graph=False)
+        torch.manual_seed(0)
+        tok = torch.randint(0, cfg.n_vocab, (4, cfg.n_ctx), dtype=torch.int32)
+        out[mode] = [tr.step({"tokens": tok, "labels": torch.roll(tok, -1, 1)}) for _ in range(4)]
+    return {"losses": [], "parallelism": strategy, "collectives": None, "clip": out}
+
+
 def case_fullstate(strategy):
     """Whole variables (+ moments) assembled on rank 0 by Trainer.full_state_dict after 3 steps: names, shapes and a value signature."""
     from tepdist_b200.api import Trainer
@@ -244,7 +265,7 @@ def case_moe(strategy):
 if __name__ == "__main__":
     case, out = sys.argv[1], sys.argv[2]
     name, _, strat = case.partition(":")
-    res = {"gpt2": case_gpt2, "gpt2s": lambda st: case_gpt2(st, True), "gpt2b1": lambda st: case_gpt2(st, False, 1), "mlp": case_mlp, "moe": case_moe, "ckpt": case_ckpt, "state": case_state, "tpfused": case_tpfused, "manualdp": case_manualdp, "opts": case_opts, "optsgpt": case_optsgpt, "conv": case_conv, "resume": case_resume, "fullstate": case_fullstate}[name](strat or "auto")
+    res = {"gpt2": case_gpt2, "gpt2s": lambda st: case_gpt2(st, True), "gpt2b1": lambda st: case_gpt2(st, False, 1), "mlp": case_mlp, "moe": case_moe, "ckpt": case_ckpt, "state": case_state, "tpfused": case_tpfused, "manualdp": case_manualdp, "opts": case_opts, "optsgpt": case_optsgpt, "conv": case_conv, "resume": case_resume, "fullstate": case_fullstate, "clip": case_clip}[name](strat or "auto")
     if int(os.environ.get("RANK", "0")) == 0:
         json.dump(res, open(out, "w"))
     if dist.is_initialized():

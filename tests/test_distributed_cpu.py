@@ -105,6 +105,28 @@ def test_conv_net_with_batchnorm_matches_single_process(tmp_path, strategy, worl
         assert abs(a - b) <= 1e-5 * max(1.0, abs(b)), (strategy, got, ref["losses"])
 
 
+_CLIP_REF = {}
+
+
+@pytest.mark.parametrize("strategy,world", [("auto", 2), ("dp2tp2", 4), ("pp2m2", 4)])     # (tp-2 and pp2m2-2 pass as well)
+def test_gradient_clipping_matches_single_process_under_every_plan(tmp_path, strategy, world):
+    """The norms that clipping uses are norms of WHOLE gradients: sharded gradients (ZeRO chunks, tensor-parallel shards) contribute
+    their local sums of squares, completed over the levels that shard them; pipeline stages add theirs up over the job (with
+    SPMD replicas inside a stage counted once)."""
+    sys.path.insert(0, HERE)
+    import dist_worker
+    if not _CLIP_REF:
+        _CLIP_REF.update(dist_worker.case_clip("auto")["clip"])
+    ref = _CLIP_REF
+    for mode in ("global", "local"):
+        assert abs(ref[mode][-1] - ref["none"][-1]) > 1e-3, "the threshold does not bite: the test would prove nothing"
+    assert abs(ref["global"][-1] - ref["local"][-1]) > 1e-4
+    got = _run(f"clip:{strategy}", world, tmp_path)["clip"]
+    for mode in ("none", "global", "local"):
+        for a, b in zip(got[mode], ref[mode]):
+            assert abs(a - b) <= 2e-5 * max(1.0, abs(b)), (strategy, mode, got[mode], ref[mode])
+
+
 def test_manual_data_parallel_through_the_grad_sync_hook(tmp_path):
     """The executor's `grad_sync` hook with the bucketed all-reduce of parallel/dp.py (the reference's plain DAPPLEAllReduce
     semantics, no planner involved): two ranks on half batches == one process on the whole batch."""

@@ -242,3 +242,39 @@ def test_schedule_spec_travels_with_the_serialized_graph():
     assert seen == pytest.approx([want(s) for s in range(1, 8)], rel=1e-6)
     with pytest.raises(ValueError):
         from_spec({"kind": "nope"}, 0.1)
+
+
+@pytest.mark.parametrize("mode", ["global", "local"])
+@pytest.mark.parametrize("kind", ["adamw", "sgd", "lamb"])
+def test_gradient_clipping_matches_torch(kind, mode):
+    """clip_norm='global' == torch.nn.utils.clip_grad_norm_ over all gradients, 'local' == the same per tensor (reference
+    examples/gpt_moe/optimizers/__init__.py:150-159), applied before the update of every optimizer."""
+    hp, make_ref = CASES[kind]
+    c = 0.05
+    ex = Executor(build_mlp(kind, clip_norm=mode, clip_norm_value=c, **hp), torch.device("cpu"), seed=5, use_cuda_graph=False)
+    assert ex.clip == (mode, c) and not ex.fused_apply_ok
+    params = {k: v.clone() for k, v in ex.store.state_dict().items() if k in ("w1", "b1", "w2")}
+    ref = make_ref(params)
+    torch.manual_seed(1)
+    clipped_once = False
+    for step in range(5):
+        feeds = {"x": torch.randn(8, 16), "t": torch.randn(8, 4)}
+        leaves = {k: v.clone().requires_grad_(True) for k, v in params.items()}
+        torch_loss(leaves, feeds["x"], feeds["t"]).backward()
+        grads = {k: v.grad for k, v in leaves.items()}
+        if mode == "global":
+            total = torch.sqrt(sum((g_ * g_).sum() for g_ in grads.values()))
+            clipped_once |= bool(total > c)
+            grads = {k: g_ * min(1.0, c / (float(total) + 1e-6)) for k, g_ in grads.items()}
+        else:
+            clipped_once |= any(bool(g_.norm() > c) for g_ in grads.values())
+            grads = {k: g_ * min(1.0, c / (float(g_.norm()) + 1e-6)) for k, g_ in grads.items()}
+        ex.step(feeds)
+        with torch.no_grad():
+            ref.step(grads)
+        mine = ex.store.state_dict()
+        for k in params:
+            assert torch.allclose(mine[k], params[k], rtol=2e-4, atol=2e-6), (kind, mode, step, k)
+    assert clipped_once, "the threshold never bit: the test would prove nothing"
+    with pytest.raises(ValueError):
+        Executor(build_mlp(kind, clip_norm="sideways", **hp), torch.device("cpu"), use_cuda_graph=False)
