@@ -158,7 +158,8 @@ def test_trainer_save_restore_resumes_identically(tmp_path):
     assert [k for k in kept if k.startswith("step_")] == ["step_4", "step_5"], kept
 
 
-def test_two_rank_server_job_via_launcher(tmp_path):
+@pytest.mark.parametrize("strategy", ["auto", "pp2m2"])
+def test_two_rank_server_job_via_launcher(tmp_path, strategy):
     """launch.py starts a 2-process server job from a cluster spec (master rank serves gRPC, the other rank sits in the
     worker loop); a client builds a plan (the master plans and dispatches it), trains, saves a sharded checkpoint and shuts
     the job down.  Losses equal the single-process run (reference: ExecutionCoordinator + ExecuteRemotePlan, E2-E6)."""
@@ -185,13 +186,14 @@ def test_two_rank_server_job_via_launcher(tmp_path):
         cl = Client(f"127.0.0.1:{port}")
         cfg = CONFIGS["tiny"]
         g = build_gpt2_graph(cfg, batch=4)
-        r = cl.build_execution_plan(g, strategy="auto")
-        assert r["plan_info"]["world"] == 2 and r["plan_info"]["parallelism"].startswith("dp"), r
+        r = cl.build_execution_plan(g, strategy=strategy)
+        assert r["plan_info"]["world"] == 2 and r["plan_info"]["parallelism"].startswith("dp" if strategy == "auto" else "pp2"), r
         torch.manual_seed(0)
         tok = torch.randint(0, cfg.n_vocab, (4, cfg.n_ctx), dtype=torch.int32)
         feeds = {"tokens": tok, "labels": torch.roll(tok, -1, 1)}
         losses = [cl.execute_plan(feeds)["loss"] for _ in range(3)]
         assert cl.server_info()["world"] == 2
+        fetched = cl.fetch_resource_vars()          # whole variables, wherever the plan put their pieces (ZeRO chunks / stages)
         cl.do_remote_save(3)
         cl.shutdown()
         job.wait(timeout=60)
@@ -204,6 +206,10 @@ def test_two_rank_server_job_via_launcher(tmp_path):
         b = float(ref.step(feeds)[0])
         assert abs(a - b) <= 2e-4 * max(1.0, abs(b)), (losses, b)
     assert os.path.isdir(tmp_path / "ckpt_0_of_2" / "step_3") and os.path.isdir(tmp_path / "ckpt_1_of_2" / "step_3")
+    want = {k: v for k, v in ref.store.state_dict().items() if not k.endswith(("/m", "/v"))}
+    assert set(fetched) == set(want), set(fetched) ^ set(want)
+    for k, v in want.items():
+        assert tuple(fetched[k].shape) == tuple(v.shape) and torch.allclose(fetched[k].float(), v, atol=2e-4), k
 
 
 def test_every_flag_override_key_exists_on_its_cxx_options_struct(monkeypatch, tmp_path):
