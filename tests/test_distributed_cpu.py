@@ -291,6 +291,21 @@ def test_full_state_dict_assembles_whole_variables_under_every_plan(tmp_path, st
         assert abs(a - b) <= 1e-3 * max(1.0, abs(b)), (strategy, a, b)
 
 
+@pytest.mark.parametrize("strategy", ["auto", "pp2m2"])
+def test_single_process_checkpoint_restores_into_sharded_and_pipeline_jobs(tmp_path, strategy, monkeypatch):
+    """The other direction of cross-plan restore: one process writes whole variables and moments; a 2-rank ZeRO job cuts out its
+    chunks (moments into the flat buffers), a 2-stage pipeline takes the variables of its stage; both continue like the writer."""
+    sys.path.insert(0, HERE)
+    import dist_worker
+    ck = str(tmp_path / "ck")
+    monkeypatch.setenv("TEPDIST_TEST_CKPT", ck)
+    wrote = dist_worker.case_ckpt("auto")
+    got = _run(f"resume:{strategy}", 2, tmp_path, {"TEPDIST_TEST_CKPT": ck})
+    assert got["step"] == 2
+    for a, b in zip(got["losses"], wrote["losses"][2:]):
+        assert abs(a - b) <= 2e-5 * max(1.0, abs(b)), (strategy, got["losses"], wrote["losses"])
+
+
 def test_state_dict_is_whole_and_identical_on_every_rank(tmp_path):
     """state_dict() must return the same, fully updated weights on every rank of a sharded-optimizer run.
     NOTE: on CPU the store has no separate bf16 compute copy (the master itself is all-gathered each step), so the
