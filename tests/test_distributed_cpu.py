@@ -10,6 +10,13 @@ import pytest
 import torch
 
 HERE = os.path.dirname(os.path.abspath(__file__))
+# The default run keeps one representative per mechanism; TEPDIST_TEST_FULL=1 runs the whole plan x feature matrix (every
+# combination listed below passed when it was added).
+FULL = os.environ.get("TEPDIST_TEST_FULL") == "1"
+
+
+def _matrix(always, extra):
+    return always + (extra if FULL else [])
 
 
 def _free_port():
@@ -66,7 +73,7 @@ def test_long_context_plan_batch1_head_seq_all_to_all(tmp_path):
         assert abs(a - b) <= 2e-4 * max(1.0, abs(b)), (got, ref)
 
 
-@pytest.mark.parametrize("case,strategy,world", [("opts", "auto", 2), ("optsgpt", "auto", 2), ("optsgpt", "dp2tp2", 4)])
+@pytest.mark.parametrize("case,strategy,world", _matrix([("opts", "auto", 2), ("optsgpt", "dp2tp2", 4)], [("optsgpt", "auto", 2)]))
 def test_reduction_optimizers_match_single_process_when_sharded(tmp_path, case, strategy, world):
     """LAMB / Adafactor / SM3 reduce over the variable (norms, row / column means, per-dimension maxima).  `opts`: an MLP that
     the planner splits Megatron-style over 2 devices -- w1 stored split on its LAST dim, w2 on its ROW dim, so both
@@ -88,7 +95,7 @@ def test_reduction_optimizers_match_single_process_when_sharded(tmp_path, case, 
             assert abs(a - b) <= tol * max(1.0, abs(b)), (case, kind, got[kind]["losses"], r["losses"])
 
 
-@pytest.mark.parametrize("strategy,world", [("dp", 2), ("auto", 4), ("dp2tp2", 4)])
+@pytest.mark.parametrize("strategy,world", _matrix([("dp", 2), ("dp2tp2", 4)], [("auto", 4)]))
 def test_conv_net_with_batchnorm_matches_single_process(tmp_path, strategy, world):
     """Training-mode BatchNorm under a batch split: the planner marks the levels that split the batch (transform.cc
     sync_levels) and the executor completes the per-channel sums across them, so a data-parallel conv net trains like one
@@ -108,7 +115,7 @@ def test_conv_net_with_batchnorm_matches_single_process(tmp_path, strategy, worl
 _CLIP_REF = {}
 
 
-@pytest.mark.parametrize("strategy,world", [("auto", 2), ("dp2tp2", 4), ("pp2m2", 4)])     # (tp-2 and pp2m2-2 pass as well)
+@pytest.mark.parametrize("strategy,world", _matrix([("dp2tp2", 4), ("pp2m2", 4)], [("auto", 2), ("tp", 2), ("pp2m2", 2)]))
 def test_gradient_clipping_matches_single_process_under_every_plan(tmp_path, strategy, world):
     """The norms that clipping uses are norms of WHOLE gradients: sharded gradients (ZeRO chunks, tensor-parallel shards) contribute
     their local sums of squares, completed over the levels that shard them; pipeline stages add theirs up over the job (with
@@ -149,16 +156,17 @@ def test_pipeline_receive_buffer_ring_follows_group_sched_count(tmp_path):
         (tmp_path / d).mkdir()
     base = _run("gpt2:pp2m4", 2, tmp_path / "a")
     one = _run("gpt2:pp2m4", 2, tmp_path / "b", {"TEPDIST_RECV_RING": "1"})
-    off = _run("gpt2:pp2m4", 2, tmp_path / "c", {"BUFFER_SAVE": "0"})
+    off = _run("gpt2:pp2m4", 2, tmp_path / "c", {"BUFFER_SAVE": "0"}) if FULL else None
     two = _run("gpt2:pp2m4", 2, tmp_path / "d", {"GROUP_SCHED_COUNT": "2"})
     assert base["parallelism"].startswith("pp2"), base
-    assert base["losses"] == one["losses"] == off["losses"], (base["losses"], one["losses"], off["losses"])
+    assert base["losses"] == one["losses"], (base["losses"], one["losses"])
+    if off is not None:
+        assert base["losses"] == off["losses"] and all(st["alloc"] == st["reuse"] == st["miss"] == 0 for st in off["ring"]), off
     for a, b in zip(two["losses"], base["losses"]):      # (another micro-batch order: gradients are summed in another order)
         assert abs(a - b) <= 2e-5 * max(1.0, abs(b)), (two["losses"], base["losses"])
     for res in (base, two):                      # 4 steps x 4 micro-batches per direction
         for st in res["ring"]:
             assert st["miss"] == 0 and st["alloc"] > 0 and st["reuse"] >= 3 * st["alloc"], res["ring"]
-    assert all(st["alloc"] == st["reuse"] == st["miss"] == 0 for st in off["ring"]), off["ring"]
     # stage 1 holds forward inputs of several micro-batches until their backward: a ring of one must report misses there
     last = [st for st in one["ring"] if st["stage"] == 1][0]
     assert last["miss"] > 0 and last["alloc"] >= 1, one["ring"]
@@ -213,7 +221,7 @@ def test_checkpoint_written_by_tp2_restores_into_one_process(tmp_path):
         assert abs(a - b) <= 2e-4 * max(1.0, abs(b)), (resumed, got)
 
 
-@pytest.mark.parametrize("opt,strategy", [("adafactor", "auto"), ("sm3", "tp"), ("lamb", "auto"), ("adamw", "auto")])
+@pytest.mark.parametrize("opt,strategy", _matrix([("adafactor", "auto"), ("sm3", "tp"), ("adamw", "auto")], [("lamb", "auto")]))
 def test_checkpoint_with_reduced_shape_optimizer_slots_restores_into_one_process(tmp_path, opt, strategy):
     """Adafactor row / column statistics, SM3 per-dimension accumulators and LAMB moments of a 2-rank run (ZeRO chunks under the
     data-parallel plan, stored shards under tensor parallelism) are written per rank with their shard description and
@@ -276,7 +284,7 @@ def test_checkpoint_written_by_a_pipeline_restores_into_one_process_and_into_the
         tr2.restore(ck, 2)
 
 
-@pytest.mark.parametrize("strategy,world", [("auto", 2), ("tp", 2), ("pp2m2", 2), ("dp2tp2", 4)])
+@pytest.mark.parametrize("strategy,world", _matrix([("auto", 2), ("pp2m2", 2), ("dp2tp2", 4)], [("tp", 2)]))
 def test_full_state_dict_assembles_whole_variables_under_every_plan(tmp_path, strategy, world):
     """Trainer.full_state_dict (what the RPC server's FetchResourceVars returns): ZeRO chunks, stored tensor-parallel shards,
     pipeline stages and their combination all come back as the same whole, fully updated variables and moments that one process
