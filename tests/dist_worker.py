@@ -264,8 +264,13 @@ def case_moe(strategy):
 
 if __name__ == "__main__":
     case, out = sys.argv[1], sys.argv[2]
-    name, _, strat = case.partition(":")
-    res = {"gpt2": case_gpt2, "gpt2s": lambda st: case_gpt2(st, True), "gpt2b1": lambda st: case_gpt2(st, False, 1), "mlp": case_mlp, "moe": case_moe, "ckpt": case_ckpt, "state": case_state, "tpfused": case_tpfused, "manualdp": case_manualdp, "opts": case_opts, "optsgpt": case_optsgpt, "conv": case_conv, "resume": case_resume, "fullstate": case_fullstate, "clip": case_clip}[name](strat or "auto")
+    CASES_ = {"gpt2": case_gpt2, "gpt2s": lambda st: case_gpt2(st, True), "gpt2b1": lambda st: case_gpt2(st, False, 1), "mlp": case_mlp, "moe": case_moe, "ckpt": case_ckpt, "state": case_state, "tpfused": case_tpfused, "manualdp": case_manualdp, "opts": case_opts, "optsgpt": case_optsgpt, "conv": case_conv, "resume": case_resume, "fullstate": case_fullstate, "clip": case_clip}
+
+    def run_case(c):
+        name, _, strat = c.partition(":")
+        return CASES_[name](strat or "auto")
+    # "a:x+b:y": several cases in ONE job (the process start-up and the imports dominate a tiny case); results keyed by case
+    res = {c: run_case(c) for c in case.split("+")} if "+" in case else run_case(case)
     if int(os.environ.get("RANK", "0")) == 0:
         json.dump(res, open(out, "w"))
     if dist.is_initialized():

@@ -37,6 +37,26 @@ def _run(case, world, tmp_path, extra_env=None):
     return json.load(open(out))
 
 
+_BATCHES = {}
+
+
+def _batch(cases, world, tmp_path):
+    """Run several worker cases in ONE torchrun job (cached per module run): start-up and imports dominate a tiny case."""
+    key = ("+".join(cases), world)
+    if key not in _BATCHES:
+        _BATCHES[key] = _run(key[0], world, tmp_path)
+    return _BATCHES[key]
+
+
+# cases of the feature tests below that share one job per world size
+_SHARED = {2: ["fullstate:auto", "fullstate:pp2m2", "conv:dp", "opts:auto"],
+           4: ["fullstate:dp2tp2", "clip:dp2tp2", "clip:pp2m2", "conv:dp2tp2", "optsgpt:dp2tp2"]}
+
+
+def _get(case, world, tmp_path):
+    return _batch(_SHARED[world], world, tmp_path)[case] if case in _SHARED.get(world, []) else _run(case, world, tmp_path)
+
+
 def _single(case):
     sys.path.insert(0, HERE)
     import dist_worker
@@ -45,10 +65,13 @@ def _single(case):
             "gpt2b1": lambda st: dist_worker.case_gpt2(st, False, 1), "moe": dist_worker.case_moe}[name]("auto")
 
 
-@pytest.mark.parametrize("case", ["mlp:auto", "mlp:dp", "gpt2:auto", "gpt2s:auto", "gpt2:explore", "gpt2:tp", "gpt2:pp2m2", "moe:ep"])
+_WORLD2_CASES = ["mlp:auto", "mlp:dp", "gpt2:auto", "gpt2s:auto", "gpt2:explore", "gpt2:tp", "gpt2:pp2m2", "moe:ep"]
+
+
+@pytest.mark.parametrize("case", _WORLD2_CASES)
 def test_spmd_world2_matches_single_process(case, tmp_path):
     ref = _single(case)
-    got = _run(case, 2, tmp_path)
+    got = _batch(_WORLD2_CASES, 2, tmp_path)[case]
     assert got["losses"][-1] < got["losses"][0]
     for a, b in zip(got["losses"], ref["losses"]):
         assert abs(a - b) <= 2e-4 * max(1.0, abs(b)), (case, got, ref)
@@ -86,7 +109,7 @@ def test_reduction_optimizers_match_single_process_when_sharded(tmp_path, case, 
     sys.path.insert(0, HERE)
     import dist_worker
     ref = getattr(dist_worker, "case_" + case)("auto")["opts"]
-    got = _run(f"{case}:{strategy}", world, tmp_path)["opts"]
+    got = _get(f"{case}:{strategy}", world, tmp_path)["opts"]
     tol = 5e-6 if case == "opts" else 2e-5        # (summation order only; measured deviation ~1e-7)
     for kind, r in ref.items():
         assert r["sharded_updates"] == 0
@@ -104,7 +127,7 @@ def test_conv_net_with_batchnorm_matches_single_process(tmp_path, strategy, worl
     sys.path.insert(0, HERE)
     import dist_worker
     ref = dist_worker.case_conv("auto")
-    got = _run(f"conv:{strategy}", world, tmp_path)
+    got = _get(f"conv:{strategy}", world, tmp_path)
     assert ref["synced_bn"] == 0
     if strategy == "dp":
         assert got["synced_bn"] >= 2, got          # forward + backward node of the batch-split BatchNorm
@@ -128,7 +151,7 @@ def test_gradient_clipping_matches_single_process_under_every_plan(tmp_path, str
     for mode in ("global", "local"):
         assert abs(ref[mode][-1] - ref["none"][-1]) > 1e-3, "the threshold does not bite: the test would prove nothing"
     assert abs(ref["global"][-1] - ref["local"][-1]) > 1e-4
-    got = _run(f"clip:{strategy}", world, tmp_path)["clip"]
+    got = _get(f"clip:{strategy}", world, tmp_path)["clip"]
     for mode in ("none", "global", "local"):
         for a, b in zip(got[mode], ref[mode]):
             assert abs(a - b) <= 2e-5 * max(1.0, abs(b)), (strategy, mode, got[mode], ref[mode])
@@ -292,7 +315,7 @@ def test_full_state_dict_assembles_whole_variables_under_every_plan(tmp_path, st
     sys.path.insert(0, HERE)
     import dist_worker
     ref = dist_worker.case_fullstate("auto")
-    got = _run(f"fullstate:{strategy}", world, tmp_path)
+    got = _get(f"fullstate:{strategy}", world, tmp_path)
     assert got["keys"] == ref["keys"] and got["shapes"] == ref["shapes"], (set(ref["keys"]) ^ set(got["keys"]))
     assert any(k.endswith("/m") for k in got["keys"])
     for a, b in zip(got["signature"], ref["signature"]):
