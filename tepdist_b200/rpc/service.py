@@ -134,7 +134,7 @@ class ServiceImpl:
         """Make fp32 master weights / moments whole on every rank (sharded-optimizer plans keep only the owned chunk fresh)."""
         tr = self.cache.get(msg["handle"])
         # whole variables on the master, whatever the plan did to them (ZeRO chunks, stored shards, pipeline stages)
-        self._full_state = tr.full_state_dict(moments=True, dst=0)
+        self._full_state = tr.full_state_dict(moments=bool(msg.get("moments")), dst=0)
 
     def _do_restore(self, msg):
         self.restore_request = msg.get("global_step", -1)
@@ -170,7 +170,7 @@ class ServiceImpl:
         out = {"loss": loss, "duration_ms": dt}
         if m.get("fetch_vars"):
             with self.exec_lock:
-                msg = {"cmd": "sync_state", "handle": m["handle"]}
+                msg = {"cmd": "sync_state", "handle": m["handle"], "moments": any(k.endswith(("/m", "/v")) for k in m["fetch_vars"])}
                 self._bcast(msg)
                 self._do_sync_state(msg)
             sd = self._full_state
@@ -181,7 +181,7 @@ class ServiceImpl:
         m = unpack(req)
         tr = self.cache.get(m["handle"])
         with self.exec_lock:
-            msg = {"cmd": "sync_state", "handle": m["handle"]}
+            msg = {"cmd": "sync_state", "handle": m["handle"], "moments": any(k.endswith(("/m", "/v")) for k in (m.get("names") or []))}
             self._bcast(msg)
             self._do_sync_state(msg)
         sd = self._full_state
