@@ -22,10 +22,13 @@ def main():
     ap.add_argument("--warmup-steps", type=int, default=0, help='linear warm-up then cosine decay over --train-steps (reference json: "warmup_steps")')
     ap.add_argument("--optimizer", default="adamw", choices=["adam", "adamw", "adafactor", "lamb", "sm3", "momentum", "sgd"],
                     help='reference: "opt_name" adam | adafactor in examples/GPT2/*.json')
+    ap.add_argument("--clip-norm", default=None, choices=["global", "local"], help='gradient clipping (reference gpt_moe config: "clip_norm")')
+    ap.add_argument("--clip-norm-value", type=float, default=1.0)
     a = ap.parse_args()
+    clip = {"clip_norm": a.clip_norm, "clip_norm_value": a.clip_norm_value} if a.clip_norm else {}
     cfg = CONFIGS[a.model]
     world = int(os.environ.get("WORLD_SIZE", "1"))
-    g = build_gpt2_graph(cfg, batch=a.batch * world, optimizer=a.optimizer)
+    g = build_gpt2_graph(cfg, batch=a.batch * world, optimizer=a.optimizer, **clip)
     tr = Trainer(g, strategy=a.strategy, comm_mode=a.comm)
     if a.warmup_steps > 0:
         from tepdist_b200.utils.schedules import warmup_cosine

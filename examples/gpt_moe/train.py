@@ -20,11 +20,14 @@ def main():
     ap.add_argument("--tiny", action="store_true")
     ap.add_argument("--optimizer", default="adamw", choices=["adamw", "adafactor", "lamb", "sm3"],
                     help='reference: "optimizer" in examples/gpt_moe/pretrain_moe.json')
+    ap.add_argument("--clip-norm", default=None, choices=["global", "local"], help='gradient clipping (reference gpt_moe config: "clip_norm")')
+    ap.add_argument("--clip-norm-value", type=float, default=1.0)
     a = ap.parse_args()
+    clip = {"clip_norm": a.clip_norm, "clip_norm_value": a.clip_norm_value} if a.clip_norm else {}
     cfg = MoEConfig(batch=a.batch)
     if a.tiny:
         cfg = MoEConfig(n_layer=2, hidden=128, ffn=256, n_head=2, experts=4, capacity=64, groups=4, seq=128, batch=a.batch, vocab=1000)
-    tr = Trainer(build_gpt_moe_graph(cfg, optimizer=a.optimizer), strategy=a.strategy, use_cuda_graph=False)
+    tr = Trainer(build_gpt_moe_graph(cfg, optimizer=a.optimizer, **clip), strategy=a.strategy, use_cuda_graph=False)
     gen = torch.Generator().manual_seed(0)
     tok = torch.randint(0, cfg.vocab, (cfg.batch, cfg.seq), generator=gen, dtype=torch.int32)
     feeds = {"tokens": tok, "labels": torch.roll(tok, -1, 1)}

@@ -51,7 +51,7 @@ CONFIGS = {
 }
 
 
-def build_gpt2_graph(cfg: GPT2Config, batch: int | None = None, optimizer: str = "adamw") -> Graph:
+def build_gpt2_graph(cfg: GPT2Config, batch: int | None = None, optimizer: str = "adamw", **opt_hp) -> Graph:
     B = batch or cfg.batch
     S, C, H, V, Vp = cfg.n_ctx, cfg.n_embd, cfg.n_head, cfg.n_vocab, cfg.padded_vocab
     b = GraphBuilder(cfg.name)
@@ -84,7 +84,8 @@ def build_gpt2_graph(cfg: GPT2Config, batch: int | None = None, optimizer: str =
         w_out = b.parameter("output", (Vp, C), nrm(0.02))
         logits = b.linear(h, w_out, name="lm_head")
         loss = b.softmax_xent(logits, labels, vocab=V, name="loss")
-    g = build_training_step(b, loss, optimizer, lr=cfg.lr, beta1=0.9, beta2=0.999, eps=1e-8, weight_decay=cfg.weight_decay)
+    g = build_training_step(b, loss, optimizer, **{**dict(lr=cfg.lr, beta1=0.9, beta2=0.999, eps=1e-8, weight_decay=cfg.weight_decay),
+                                                     **opt_hp})      # (opt_hp: clip_norm / clip_norm_value / schedule / ...)
     g.meta["model"] = {"family": "gpt2", "name": cfg.name, "n_layer": cfg.n_layer, "n_embd": C, "n_head": H,
                        "n_ctx": S, "n_vocab": V, "batch": B}
     return g

@@ -63,7 +63,8 @@ def build_moe_ffn_graph(groups=8, tokens_per_group=64, model=64, hidden=256, exp
     return build_training_step(b, loss, "adamw", lr=1e-3, beta1=0.9, beta2=0.999, eps=1e-8, weight_decay=0.0)
 
 
-def build_gpt_moe_graph(cfg: MoEConfig, batch: int | None = None, optimizer: str = "adamw") -> Graph:
+def build_gpt_moe_graph(cfg: MoEConfig, batch: int | None = None, optimizer: str = "adamw", **opt_hp) -> Graph:
+    """`opt_hp`: further optimizer settings of pretrain_moe.json, e.g. clip_norm="global", clip_norm_value=1.0, schedule={...}."""
     """Full GPT-MoE: every other layer's MLP is an MoE FFN (pretrain_moe.json: 8 layers, hidden 768, 16 heads x 48,
     8 experts, capacity 256, 8 local groups, seq 1024)."""
     B = batch or cfg.batch
@@ -102,4 +103,4 @@ def build_gpt_moe_graph(cfg: MoEConfig, batch: int | None = None, optimizer: str
         logits = b.linear(b.layernorm(x, gf, bf2, name="ln_f"), b.parameter("output", (Vp, C), nrm(0.02)), name="lm_head")
         loss = b.softmax_xent(logits, labels, vocab=cfg.vocab, name="loss")
     # (pretrain_moe.json "optimizer": adamw | adafactor | lamb | sm3 -- frontend/builder.py OPTIMIZERS)
-    return build_training_step(b, loss, optimizer, lr=1e-4, beta1=0.9, beta2=0.999, eps=1e-8, weight_decay=0.01)
+    return build_training_step(b, loss, optimizer, **{**dict(lr=1e-4, beta1=0.9, beta2=0.999, eps=1e-8, weight_decay=0.01), **opt_hp})
