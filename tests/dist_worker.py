@@ -107,6 +107,25 @@ def case_clip(strategy):
     return {"losses": [], "parallelism": strategy, "collectives": None, "clip": out}
 
 
+def case_sched(strategy):
+    """Warm-up + cosine schedule that travels with the graph; AdamW (flat / sharded-optimizer kernels read the rate from the device
+    tensor) and SGD (host-scalar rate)."""
+    from tepdist_b200.api import Trainer
+    from tepdist_b200.models.gpt2 import CONFIGS, build_gpt2_graph
+    cfg = CONFIGS["tiny"]
+    if strategy.startswith("pp") and int(os.environ.get("WORLD_SIZE", "1")) == 1:
+        strategy = "auto"
+    out = {}
+    for opt, lr in (("adamw", 0.02), ("sgd", 0.5)):
+        g = build_gpt2_graph(cfg, batch=4, optimizer=opt, schedule={"kind": "warmup_cosine", "warmup_steps": 2, "total_steps": 5, "end_ratio": 0.1})
+        g.meta["optimizer"]["lr"] = lr
+        tr = Trainer(g, strategy=strategy, device=torch.device("cpu"), use_cuda_graph=False)
+        torch.manual_seed(0)
+        tok = torch.randint(0, cfg.n_vocab, (4, cfg.n_ctx), dtype=torch.int32)
+        out[opt] = [tr.step({"tokens": tok, "labels": torch.roll(tok, -1, 1)}) for _ in range(5)]
+    return {"losses": [], "parallelism": strategy, "collectives": None, "sched": out}
+
+
 def case_fullstate(strategy):
     """Whole variables (+ moments) assembled on rank 0 by Trainer.full_state_dict after 3 steps: names, shapes and a value signature."""
     from tepdist_b200.api import Trainer
@@ -264,7 +283,7 @@ def case_moe(strategy):
 
 if __name__ == "__main__":
     case, out = sys.argv[1], sys.argv[2]
-    CASES_ = {"gpt2": case_gpt2, "gpt2s": lambda st: case_gpt2(st, True), "gpt2b1": lambda st: case_gpt2(st, False, 1), "mlp": case_mlp, "moe": case_moe, "ckpt": case_ckpt, "state": case_state, "tpfused": case_tpfused, "manualdp": case_manualdp, "opts": case_opts, "optsgpt": case_optsgpt, "conv": case_conv, "resume": case_resume, "fullstate": case_fullstate, "clip": case_clip}
+    CASES_ = {"gpt2": case_gpt2, "gpt2s": lambda st: case_gpt2(st, True), "gpt2b1": lambda st: case_gpt2(st, False, 1), "mlp": case_mlp, "moe": case_moe, "ckpt": case_ckpt, "state": case_state, "tpfused": case_tpfused, "manualdp": case_manualdp, "opts": case_opts, "optsgpt": case_optsgpt, "conv": case_conv, "resume": case_resume, "fullstate": case_fullstate, "clip": case_clip, "sched": case_sched}
 
     def run_case(c):
         name, _, strat = c.partition(":")

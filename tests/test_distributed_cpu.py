@@ -49,7 +49,7 @@ def _batch(cases, world, tmp_path):
 
 
 # cases of the feature tests below that share one job per world size
-_SHARED = {2: ["fullstate:auto", "fullstate:pp2m2", "conv:dp", "opts:auto"],
+_SHARED = {2: ["fullstate:auto", "fullstate:pp2m2", "conv:dp", "opts:auto", "sched:auto", "sched:pp2m2"],
            4: ["fullstate:dp2tp2", "clip:dp2tp2", "clip:pp2m2", "conv:dp2tp2", "optsgpt:dp2tp2"]}
 
 
@@ -155,6 +155,23 @@ def test_gradient_clipping_matches_single_process_under_every_plan(tmp_path, str
     for mode in ("none", "global", "local"):
         for a, b in zip(got[mode], ref[mode]):
             assert abs(a - b) <= 2e-5 * max(1.0, abs(b)), (strategy, mode, got[mode], ref[mode])
+
+
+@pytest.mark.parametrize("strategy", ["auto", "pp2m2"])
+def test_learning_rate_schedule_is_followed_under_sharded_and_pipeline_plans(tmp_path, strategy):
+    """A schedule that came with the graph drives the rate on every path: the sharded-optimizer update (rate read from the device
+    tensor / host scalar on the gloo path), the pipeline stage workers, and the single process they are compared with."""
+    sys.path.insert(0, HERE)
+    import dist_worker
+    if "sched" not in _CLIP_REF:
+        _CLIP_REF["sched"] = dist_worker.case_sched("auto")["sched"]
+    ref = _CLIP_REF["sched"]
+    flat = dist_worker.case_gpt2("auto")["losses"]          # constant rate, other value: just has to differ
+    assert abs(ref["adamw"][2] - flat[2]) > 1e-3
+    got = _get(f"sched:{strategy}", 2, tmp_path)["sched"]
+    for opt in ("adamw", "sgd"):
+        for a, b in zip(got[opt], ref[opt]):
+            assert abs(a - b) <= 2e-5 * max(1.0, abs(b)), (strategy, opt, got[opt], ref[opt])
 
 
 def test_manual_data_parallel_through_the_grad_sync_hook(tmp_path):
