@@ -110,10 +110,11 @@ def check_num_gradients(n_apply: int) -> None:
 
 # Accepted for compatibility with the reference's config files but without effect here (and why):
 #   ILP_NUM_THREADS       the built-in simplex / branch-and-bound is single threaded
-#   ASYNC_SEND/ASYNC_RECV pipeline transfers are always isend / irecv on side streams; there is no synchronous mode
+#   ASYNC_SEND            pipeline sends are always isend: a blocking send can deadlock two stages that send to each other at the
+#                         same point of the 1F1B steady state (their receives are posted later in their own task lists)
 #   DISABLE_BUFFER_ALIAS  variables are always updated in place in the flat store
 #   CLUSTER_SPEC, FRONTEND informational (set by the launcher)
-INERT_KEYS = ("ILP_NUM_THREADS", "ASYNC_SEND", "ASYNC_RECV", "DISABLE_BUFFER_ALIAS", "CLUSTER_SPEC", "FRONTEND")
+INERT_KEYS = ("ILP_NUM_THREADS", "ASYNC_SEND", "DISABLE_BUFFER_ALIAS", "CLUSTER_SPEC", "FRONTEND")
 
 
 def resolve_strategy(strategy: str) -> str:
@@ -139,6 +140,13 @@ def comm_dtype():
     """FP16_COMM: fp32 sum-reductions travel in 16 bit (bf16 on B200; custom_collective_expander.cc FP16 wrap)."""
     import torch
     return torch.bfloat16 if is_set("FP16_COMM") and env().get_bool("FP16_COMM") else None
+
+
+def async_recv() -> bool:
+    """ASYNC_RECV (default true): a pipeline receive is posted at its Recv task and awaited at the Input task of its micro-batch.
+    false: awaited right at the Recv task (a debugging aid: serialises communication with compute; deadlock-free because the
+    scheduler places every Recv after the start of its Send)."""
+    return env().get_bool("ASYNC_RECV") if is_set("ASYNC_RECV") else True
 
 
 def fake_input() -> bool:

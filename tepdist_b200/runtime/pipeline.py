@@ -87,6 +87,9 @@ class StageWorker:
         self._ring: Dict[Tuple[bool, Tuple[int, int], int], Tuple[torch.Tensor, Optional[int]]] = {}
         self.ring_stats = {"alloc": 0, "reuse": 0, "miss": 0}
         self.pending_send: List[Any] = []
+        from .. import config
+        self.async_recv = config.async_recv()
+        self.sync_recvs = 0
         self.loss_acc: Optional[torch.Tensor] = None
         # values the optimizer phase reads from the environment (gradients of variables that are not flat-bound, and
         # anything else the apply / post-apply nodes consume from the per-micro-batch part)
@@ -303,6 +306,10 @@ def run_pipeline_step(worker: StageWorker, task_list: List[Dict[str, Any]], feed
         kind, m, bwd = t["type"], t["micro"], t["backward"]
         if kind == "Recv":
             pending_recv[(m, bwd)] = worker.recv(m, bwd, t.get("buffer_id", -1))
+            if not worker.async_recv:            # ASYNC_RECV=false: block here instead of at the Input task
+                for w in pending_recv.pop((m, bwd)):
+                    w.wait()
+                worker.sync_recvs += 1
         elif kind == "Input":
             for w in pending_recv.pop((m, bwd), []):
                 w.wait()

@@ -28,7 +28,7 @@ def case_gpt2(strategy, feed_shards=False, batch=4):
     worker = getattr(tr.exec, "worker", None)
     if worker is not None:   # pipeline: receive-buffer ring statistics of every stage worker
         stats = [None] * tr.world
-        dist.all_gather_object(stats, dict(worker.ring_stats, stage=worker.stage))
+        dist.all_gather_object(stats, dict(worker.ring_stats, stage=worker.stage, sync_recvs=worker.sync_recvs))
         res["ring"] = stats
     return res
 

@@ -197,7 +197,8 @@ def test_pipeline_receive_buffer_ring_follows_group_sched_count(tmp_path):
     base = _run("gpt2:pp2m4", 2, tmp_path / "a")
     one = _run("gpt2:pp2m4", 2, tmp_path / "b", {"TEPDIST_RECV_RING": "1"})
     off = _run("gpt2:pp2m4", 2, tmp_path / "c", {"BUFFER_SAVE": "0"}) if FULL else None
-    two = _run("gpt2:pp2m4", 2, tmp_path / "d", {"GROUP_SCHED_COUNT": "2"})
+    two = _run("gpt2:pp2m4", 2, tmp_path / "d", {"GROUP_SCHED_COUNT": "2", "ASYNC_RECV": "false"})   # (+ blocking receives)
+    assert all(st["sync_recvs"] > 0 for st in two["ring"]) and all(st["sync_recvs"] == 0 for st in base["ring"])
     assert base["parallelism"].startswith("pp2"), base
     assert base["losses"] == one["losses"], (base["losses"], one["losses"])
     if off is not None:
