@@ -130,6 +130,12 @@ class ServiceImpl:
             return self.ckpt.save(tr.executor(), msg["global_step"])
         return "lazy"
 
+    @staticmethod
+    def _wants_slots(tr, names) -> bool:
+        """Optimizer slots (moments, Adafactor / SM3 statistics) are gathered only when a requested name is not a variable."""
+        variables = set(tr.executor().store.names.values())
+        return any(k not in variables for k in names)
+
     def _do_sync_state(self, msg):
         """Make fp32 master weights / moments whole on every rank (sharded-optimizer plans keep only the owned chunk fresh)."""
         tr = self.cache.get(msg["handle"])
@@ -170,7 +176,7 @@ class ServiceImpl:
         out = {"loss": loss, "duration_ms": dt}
         if m.get("fetch_vars"):
             with self.exec_lock:
-                msg = {"cmd": "sync_state", "handle": m["handle"], "moments": any(k.endswith(("/m", "/v")) for k in m["fetch_vars"])}
+                msg = {"cmd": "sync_state", "handle": m["handle"], "moments": self._wants_slots(tr, m["fetch_vars"])}
                 self._bcast(msg)
                 self._do_sync_state(msg)
             sd = self._full_state
@@ -181,7 +187,7 @@ class ServiceImpl:
         m = unpack(req)
         tr = self.cache.get(m["handle"])
         with self.exec_lock:
-            msg = {"cmd": "sync_state", "handle": m["handle"], "moments": any(k.endswith(("/m", "/v")) for k in (m.get("names") or []))}
+            msg = {"cmd": "sync_state", "handle": m["handle"], "moments": self._wants_slots(tr, m.get("names") or [])}
             self._bcast(msg)
             self._do_sync_state(msg)
         sd = self._full_state

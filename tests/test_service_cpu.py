@@ -41,6 +41,28 @@ def test_client_server_training_and_fetch(tmp_path):
     server.stop(0)
 
 
+def test_optimizer_settings_travel_over_rpc(tmp_path):
+    """A graph with Adafactor in relative-step mode (lr = None), global-norm clipping and a schedule spec -- None values and nested
+    dicts in graph.meta -- is serialised to the server, trains there like it does locally, and its reduced-shape slots can be fetched."""
+    from tepdist_b200.runtime.executor import Executor
+    impl, server, cl = _start(tmp_path)
+    cfg = CONFIGS["tiny"]
+    g = build_gpt2_graph(cfg, optimizer="adafactor", clip_norm="global", clip_norm_value=0.5,
+                         schedule={"kind": "warmup_linear_decay", "warmup_steps": 2, "total_steps": 6})
+    g.meta["optimizer"]["lr"] = None
+    assert cl.build_execution_plan(g)["handle"] >= 1
+    torch.manual_seed(0)
+    tok = torch.randint(0, cfg.n_vocab, (cfg.batch, cfg.n_ctx), dtype=torch.int32)
+    feeds = {"tokens": tok, "labels": torch.roll(tok, -1, 1)}
+    remote = [cl.execute_plan(feeds)["loss"] for _ in range(3)]
+    local = Executor(g, torch.device("cpu"), use_cuda_graph=False)
+    for a in remote:
+        assert a == pytest.approx(float(local.step(feeds)[0]), rel=1e-6)
+    v = cl.fetch_resource_vars(["model/h0/attn/c_attn/w/vr"])
+    assert tuple(v["model/h0/attn/c_attn/w/vr"].shape) == (3 * cfg.n_embd,)
+    server.stop(0)
+
+
 def test_checkpoint_lazy_save_rotate_restore(tmp_path):
     impl, server, cl = _start(tmp_path)
     cfg = CONFIGS["tiny"]
