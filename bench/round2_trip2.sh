@@ -13,7 +13,8 @@ step() {
   echo "$name rc=$? $(( $(date +%s) - t0 ))s" | tee -a $out/summary.txt
 }
 export -f run2
-step pytest_multi_gpu  400 python -m pytest tests/test_multi_gpu.py -x -q
+step mc_worker         300 bash -c 'run2 29510 tests/mc_worker.py gpurun_out/r2t2/mc.json'
+step pytest_multi_gpu  500 python -m pytest tests/test_multi_gpu.py -x -q
 TEPDIST_TEST_EXPERIMENTAL=1 step tp_fused_plan 200 python -m pytest tests/test_multi_gpu.py -x -q -k tp_plan
 step bench_n2          200 bash -c 'run2 29511 bench.py --gpus 2 --steps 20 --warmup 5'
 # pipeline with the persistent receive ring + scheduler-driven release (only gloo-tested so far), then the tp plan after the

@@ -75,10 +75,13 @@ class CheckpointManager:
         if os.path.exists(prefix):
             shutil.rmtree(prefix)
         os.replace(tmp, prefix)     # atomic publish
+        if global_step in self.queue:          # re-saving a step (lazy save then explicit save, resume then save) must not
+            self.queue.remove(global_step)     # make rotation delete the directory that was just written
         self.queue.append(global_step)
         while len(self.queue) > self.max_to_keep:
             old = self.queue.pop(0)
-            shutil.rmtree(os.path.join(self.dir, f"step_{old}"), ignore_errors=True)
+            if old not in self.queue:
+                shutil.rmtree(os.path.join(self.dir, f"step_{old}"), ignore_errors=True)
         json.dump(self.queue, open(self.queue_file, "w"))
         self.lazy_request = None
         return prefix

@@ -39,15 +39,106 @@ def _sigs(lib):
         fn.argtypes = a
 
 
-class SymmetricBuffer:
-    """nbytes of device memory on every rank of `group`, mutually mapped."""
+_VMM_STATE: dict = {}
 
-    def __init__(self, nbytes: int, group=None):
+
+def _vmm_sigs(lib):
+    vp, i, ll, f = ctypes.c_void_p, ctypes.c_int, ctypes.c_longlong, ctypes.c_float
+    ull = ctypes.c_ulonglong
+    pi, pll, pull, pp = ctypes.POINTER(i), ctypes.POINTER(ll), ctypes.POINTER(ull), ctypes.POINTER(ctypes.c_void_p)
+    table = {
+        "tepd_vmm_query": [i, i, pi, pll], "tepd_vmm_create": [i, ll, pull, pi], "tepd_vmm_import_fd": [i, pull],
+        "tepd_vmm_map": [ull, i, ll, ll, pp], "tepd_vmm_unmap": [vp, ll], "tepd_vmm_release": [ull],
+        "tepd_mc_create": [i, ll, pull, pi], "tepd_mc_add_device": [ull, i], "tepd_mc_bind": [ull, ull, ll],
+        "tepd_mc_barrier": [vp, vp, vp, i, vp, vp],
+        "tepd_mc_all_reduce_bf16": [vp, vp, vp, vp, i, i, ll, i, vp, vp, vp, i, vp],
+        "tepd_mc_rs_adamw_ag": [vp, vp, vp, vp, vp, ll, ll, ll, f, f, f, f, vp, i, i, vp],
+        "tepd_mc_all_gather": [vp, vp, ll, ll, i, vp],
+        "tepd_mc_reduce_scatter_f32": [vp, vp, ll, ll, i, vp],
+    }
+    for k, a in table.items():
+        fn = getattr(lib, k)
+        fn.restype = ctypes.c_int
+        fn.argtypes = a
+
+
+def _exchange_fds(fds: List[int], group) -> dict:
+    """Every rank hands `fds` (POSIX handles of its physical allocations) to every other rank of `group` over abstract
+    AF_UNIX sockets with SCM_RIGHTS -- the way a file descriptor crosses a process boundary without ptrace rights.
+    Returns {rank: [fd, ...]} with the receiver-side descriptor numbers (own entry = the fds passed in)."""
+    import socket
+    import struct
+    import uuid
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    tok = [uuid.uuid4().hex if rank == 0 else None]
+    dist.broadcast_object_list(tok, src=dist.get_global_rank(group, 0) if group is not None else 0, group=group)
+    names = [f"\0tepd-{tok[0]}-{r}" for r in range(world)]
+    srv = socket.socket(socket.AF_UNIX, socket.SOCK_STREAM)
+    srv.bind(names[rank])
+    srv.listen(world)
+    dist.barrier(group)                       # everybody is listening
+    for p in range(world):
+        if p == rank:
+            continue
+        c = socket.socket(socket.AF_UNIX, socket.SOCK_STREAM)
+        c.connect(names[p])
+        socket.send_fds(c, [struct.pack("i", rank)], list(fds))
+        c.close()
+    got = {rank: list(fds)}
+    srv.settimeout(120)
+    for _ in range(world - 1):
+        conn, _a = srv.accept()
+        msg, rfds, _f, _ad = socket.recv_fds(conn, 16, 8)
+        got[struct.unpack("i", msg[:4])[0]] = list(rfds)
+        conn.close()
+    srv.close()
+    dist.barrier(group)
+    return got
+
+
+def symm_backend(group=None) -> str:
+    """'vmm' when every rank of the group can bind VMM allocations to an NVSwitch multicast object (NVLS), else 'ipc'
+    (cudaIpc peer mappings, no multicast).  TEPDIST_SYMM=ipc|vmm overrides the probe."""
+    import os
+    forced = os.environ.get("TEPDIST_SYMM")
+    if forced in ("ipc", "vmm"):
+        return forced
+    key = id(group) if group is not None else 0
+    if key not in _VMM_STATE:
+        lib = ops.lib()
+        _vmm_sigs(lib)
+        sup, gran = ctypes.c_int(0), ctypes.c_longlong(0)
+        rc = lib.tepd_vmm_query(torch.cuda.current_device(), dist.get_world_size(group), ctypes.byref(sup), ctypes.byref(gran))
+        mine = bool(rc == 0 and sup.value and gran.value > 0)
+        everyone: List[Optional[bool]] = [None] * dist.get_world_size(group)
+        dist.all_gather_object(everyone, mine, group=group)
+        _VMM_STATE[key] = "vmm" if all(everyone) else "ipc"
+    return _VMM_STATE[key]
+
+
+class SymmetricBuffer:
+    """nbytes of device memory on every rank of `group`, mutually mapped.
+
+    backend 'vmm' (default on NVSwitch boxes): cuMemCreate physical pages, POSIX-fd handles exchanged over unix sockets,
+    every peer's pages mapped into this process (`ptrs[r]`, unicast) AND all of them bound to one multicast object whose
+    mapping `mc_ptr` addresses the n replicas at once: `multimem.ld_reduce` on it returns the switch-reduced value,
+    `multimem.st` writes every replica (ops/csrc/vmm_sm100.cu).  backend 'ipc': cudaMalloc + cudaIpc handles, `mc_ptr` None."""
+
+    def __init__(self, nbytes: int, group=None, backend: Optional[str] = None):
         self.lib = ops.lib()
         _sigs(self.lib)
         self.group = group
         self.world = dist.get_world_size(group)
         self.rank = dist.get_rank(group)
+        self.backend = backend or symm_backend(group)
+        self.mc_ptr: Optional[int] = None
+        if self.backend == "vmm":
+            self._init_vmm(nbytes)
+        else:
+            self._init_ipc(nbytes)
+        self.ptr_array = (ctypes.c_void_p * self.world)(*self.ptrs)
+
+    def _init_ipc(self, nbytes: int) -> None:
         self.nbytes = (nbytes + 255) // 256 * 256
         p = ctypes.c_void_p()
         rc = self.lib.tepd_symm_alloc(self.nbytes, ctypes.byref(p))
@@ -60,7 +151,7 @@ class SymmetricBuffer:
         if rc:
             raise RuntimeError(f"cudaIpcGetMemHandle failed ({rc})")
         handles: List[Optional[bytes]] = [None] * self.world
-        dist.all_gather_object(handles, bytes(h.raw), group=group)
+        dist.all_gather_object(handles, bytes(h.raw), group=self.group)
         self.ptrs: List[int] = []
         for r, hb in enumerate(handles):
             if r == self.rank:
@@ -71,13 +162,113 @@ class SymmetricBuffer:
             if rc:
                 raise RuntimeError(f"cudaIpcOpenMemHandle(rank {r}) failed ({rc})")
             self.ptrs.append(q.value)
-        self.ptr_array = (ctypes.c_void_p * self.world)(*self.ptrs)
+
+    def _init_vmm(self, nbytes: int) -> None:
+        import os
+        lib = self.lib
+        _vmm_sigs(lib)
+        dev = torch.cuda.current_device()
+        sup, gran = ctypes.c_int(0), ctypes.c_longlong(0)
+        rc = lib.tepd_vmm_query(dev, self.world, ctypes.byref(sup), ctypes.byref(gran))
+        if rc or gran.value <= 0:
+            raise RuntimeError(f"VMM API unavailable ({rc})")
+        g = gran.value
+        self.nbytes = (max(nbytes, 1) + g - 1) // g * g
+        use_mc = bool(sup.value) and self.world > 1
+
+        def chk(rc, what):
+            if rc:
+                raise RuntimeError(f"{what} failed ({rc}) on rank {self.rank}")
+
+        mem, fd = ctypes.c_ulonglong(0), ctypes.c_int(-1)
+        chk(lib.tepd_vmm_create(dev, self.nbytes, ctypes.byref(mem), ctypes.byref(fd)), "cuMemCreate/export")
+        send = [fd.value]
+        mc = ctypes.c_ulonglong(0)
+        if use_mc and self.rank == 0:
+            mfd = ctypes.c_int(-1)
+            chk(lib.tepd_mc_create(self.world, self.nbytes, ctypes.byref(mc), ctypes.byref(mfd)), "cuMulticastCreate")
+            send.append(mfd.value)
+        got = _exchange_fds(send, self.group) if self.world > 1 else {self.rank: send}
+        self.ptrs = []
+        self._handles = []
+        for r in range(self.world):
+            h = mem
+            if r != self.rank:
+                h = ctypes.c_ulonglong(0)
+                chk(lib.tepd_vmm_import_fd(got[r][0], ctypes.byref(h)), f"import of rank {r}'s allocation")
+            q = ctypes.c_void_p()
+            chk(lib.tepd_vmm_map(h.value, dev, self.nbytes, g, ctypes.byref(q)), f"map of rank {r}'s allocation")
+            self.ptrs.append(q.value)
+            self._handles.append(h.value)
+        self.local_ptr = self.ptrs[self.rank]
+        if use_mc:
+            if self.rank != 0:
+                chk(lib.tepd_vmm_import_fd(got[0][1], ctypes.byref(mc)), "import of the multicast object")
+            chk(lib.tepd_mc_add_device(mc.value, dev), "cuMulticastAddDevice")
+            dist.barrier(self.group)               # every device is part of the object before anybody binds memory
+            chk(lib.tepd_mc_bind(mc.value, mem.value, self.nbytes), "cuMulticastBindMem")
+            q = ctypes.c_void_p()
+            chk(lib.tepd_vmm_map(mc.value, dev, self.nbytes, g, ctypes.byref(q)), "map of the multicast object")
+            self.mc_ptr = q.value
+            self._mc_handle = mc.value
+            dist.barrier(self.group)
+        for r, fds in got.items():
+            for f_ in fds:
+                os.close(f_)
+        self.tensor(torch.uint8).zero_()
+        torch.cuda.synchronize()
+        if self.world > 1:
+            dist.barrier(self.group)
 
     def tensor(self, dtype: torch.dtype, numel: Optional[int] = None, offset_bytes: int = 0) -> torch.Tensor:
         """Zero-copy torch view of the LOCAL buffer."""
         t = torch.as_tensor(_CudaArray(self.local_ptr + offset_bytes, self.nbytes - offset_bytes), device="cuda")
         t = t.view(dtype)
         return t if numel is None else t[:numel]
+
+
+class McContext:
+    """Flag state for the multimem kernels of ONE stream of launches: a symmetric flag word per CTA slot (signalled with a
+    single `multimem.red` per rank), a local arrival count per slot (nothing is ever reset, so captured launches replay
+    unchanged) and an error word that a timed-out spin raises instead of hanging the box."""
+
+    MAX_CTAS = 512
+
+    def __init__(self, group=None):
+        self.flags = SymmetricBuffer(self.MAX_CTAS * 4, group, backend="vmm")
+        if self.flags.mc_ptr is None:
+            raise RuntimeError("multicast is not available in this group")
+        self.lib = self.flags.lib
+        self.world, self.rank = self.flags.world, self.flags.rank
+        dev = torch.device("cuda", torch.cuda.current_device())
+        self.epochs = torch.zeros(self.MAX_CTAS, dtype=torch.int32, device=dev)
+        self.err = torch.zeros(1, dtype=torch.int32, device=dev)
+
+    def check(self) -> None:
+        if int(self.err.item()):
+            raise RuntimeError("a multimem barrier timed out: some rank never arrived")
+
+    def barrier(self, stream: Optional[int] = None) -> None:
+        s = torch.cuda.current_stream().cuda_stream if stream is None else stream
+        rc = self.lib.tepd_mc_barrier(self.flags.mc_ptr, self.flags.local_ptr, self.epochs.data_ptr(), self.world,
+                                      self.err.data_ptr(), s)
+        if rc:
+            raise RuntimeError(f"mc_barrier failed ({rc})")
+        ops._count()
+
+    def all_reduce_bf16_(self, buf: SymmetricBuffer, numel: int, N: int, bias: Optional[torch.Tensor] = None,
+                         residual: Optional[torch.Tensor] = None, offset_bytes: int = 0, ctas: int = 0) -> None:
+        """In place on the symmetric bf16 buffer: buf[:numel] <- sum over ranks (+ bias[col] + residual), on every rank.  One
+        kernel: barrier, `multimem.ld_reduce` of this rank's 1/n slice, epilogue, `multimem.st` to all, barrier."""
+        assert buf.mc_ptr is not None and numel % (8 * self.world) == 0
+        rc = self.lib.tepd_mc_all_reduce_bf16(buf.mc_ptr + offset_bytes, self.flags.mc_ptr, self.flags.local_ptr,
+                                              self.epochs.data_ptr(), self.world, self.rank, numel, N,
+                                              None if bias is None else bias.data_ptr(),
+                                              None if residual is None else residual.data_ptr(), self.err.data_ptr(), ctas,
+                                              torch.cuda.current_stream().cuda_stream)
+        if rc:
+            raise RuntimeError(f"mc_all_reduce_bf16 failed ({rc})")
+        ops._count()
 
 
 class SymmBarrier:

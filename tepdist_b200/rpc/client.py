@@ -49,9 +49,9 @@ class Client:
     def execute_plan(self, feeds: Optional[Dict[str, torch.Tensor]] = None, fetch_vars: Optional[List[str]] = None):
         """One training step.  With NUM_PARALLEL_RPC_STEPS > 0 returns a Future (bounded number of steps in flight)."""
         self._step += 1
+        req = {"handle": self.handle, "feeds": feeds, "fetch_vars": fetch_vars, "seq": self._step}
         if fetch_vars is None and self.fetch_every and self._step % self.fetch_every == 0:
-            fetch_vars = ["*"]
-        req = {"handle": self.handle, "feeds": feeds, "fetch_vars": fetch_vars if fetch_vars != ["*"] else None}
+            req["fetch_all"] = True          # periodic refresh of every variable (FETCH_RESOURCE_VAR_STEPS)
 
         def run():
             try:

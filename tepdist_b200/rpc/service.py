@@ -34,7 +34,10 @@ def pack(obj: Any) -> bytes:
 
 
 def unpack(b: bytes) -> Any:
-    return torch.load(io.BytesIO(b), weights_only=False)
+    """Decode a request / reply.  `weights_only=True`: the restricted unpickler accepts containers, scalars, strings, tensors,
+    dtypes and sizes only -- a request can carry data, never code (the reference's protobuf messages have the same property;
+    a full pickle load on an unauthenticated port would hand every client arbitrary code execution on all server ranks)."""
+    return torch.load(io.BytesIO(b), weights_only=True)
 
 
 class ExecutionPlanCache:
@@ -75,6 +78,8 @@ class ServiceImpl:
         self.warmed_up = False
         self.restore_request: Optional[int] = None
         self.step_log: List[float] = []
+        self.next_seq = 1                                  # ExecutePlan ordering when the client pipelines steps
+        self.seq_cv = threading.Condition(self.exec_lock)
         from .. import _C
         self.env = _C.ServiceEnv.instance()
         self.env.load()
@@ -140,7 +145,7 @@ class ServiceImpl:
         """Make fp32 master weights / moments whole on every rank (sharded-optimizer plans keep only the owned chunk fresh)."""
         tr = self.cache.get(msg["handle"])
         # whole variables on the master, whatever the plan did to them (ZeRO chunks, stored shards, pipeline stages)
-        self._full_state = tr.full_state_dict(moments=bool(msg.get("moments")), dst=0)
+        return tr.full_state_dict(moments=bool(msg.get("moments")), dst=0)
 
     def _do_restore(self, msg):
         self.restore_request = msg.get("global_step", -1)
@@ -150,8 +155,9 @@ class ServiceImpl:
     def BuildExecutionPlan(self, req: bytes, ctx) -> bytes:
         m = unpack(req)
         msg = {"cmd": "build", **m}
-        self._bcast(msg)
-        handle = self._do_build(msg)
+        with self.exec_lock:
+            self._bcast(msg)
+            handle = self._do_build(msg)
         tr = self.cache.get(handle)
         return pack({"handle": handle, "plan_info": {k: v for k, v in tr.plan_info.items() if k != "log"}})
 
@@ -166,21 +172,31 @@ class ServiceImpl:
         import time
         m = unpack(req)
         feeds = m.get("feeds") or {k: self.host_inputs[k] for k in m.get("input_names", self.host_inputs)}
-        with self.exec_lock:
-            t0 = time.time()
-            msg = {"cmd": "execute", "handle": m["handle"], "feeds": feeds}
-            self._bcast(msg)
-            loss, tr = self._do_execute(msg)
-            dt = (time.time() - t0) * 1e3
-        self.step_log.append(dt)
-        out = {"loss": loss, "duration_ms": dt}
-        if m.get("fetch_vars"):
-            with self.exec_lock:
-                msg = {"cmd": "sync_state", "handle": m["handle"], "moments": self._wants_slots(tr, m["fetch_vars"])}
+        seq = m.get("seq")
+        with self.seq_cv:                     # == exec_lock; every broadcast + command pair runs under it
+            if seq is not None:               # pipelined clients (NUM_PARALLEL_RPC_STEPS): steps run in the order they were issued
+                ok = self.seq_cv.wait_for(lambda: seq <= self.next_seq, timeout=600)
+                if not ok or seq < self.next_seq:
+                    raise RuntimeError(f"ExecutePlan seq {seq}: expected {self.next_seq}")
+            try:
+                t0 = time.time()
+                msg = {"cmd": "execute", "handle": m["handle"], "feeds": feeds}
                 self._bcast(msg)
-                self._do_sync_state(msg)
-            sd = self._full_state
-            out["vars"] = {k: sd[k].cpu() for k in m["fetch_vars"] if k in sd}
+                loss, tr = self._do_execute(msg)
+                dt = (time.time() - t0) * 1e3
+                self.step_log.append(dt)
+                out = {"loss": loss, "duration_ms": dt}
+                want = m.get("fetch_vars")
+                if want or m.get("fetch_all"):
+                    msg = {"cmd": "sync_state", "handle": m["handle"], "moments": self._wants_slots(tr, want or [])}
+                    self._bcast(msg)
+                    sd = self._do_sync_state(msg)
+                    names = want or [k for k in sd if not k.endswith(("/m", "/v"))]
+                    out["vars"] = {k: sd[k].cpu() for k in names if k in sd}
+            finally:
+                if seq is not None:
+                    self.next_seq = seq + 1
+                    self.seq_cv.notify_all()
         return pack(out)
 
     def FetchResourceVars(self, req: bytes, ctx) -> bytes:
@@ -189,8 +205,7 @@ class ServiceImpl:
         with self.exec_lock:
             msg = {"cmd": "sync_state", "handle": m["handle"], "moments": self._wants_slots(tr, m.get("names") or [])}
             self._bcast(msg)
-            self._do_sync_state(msg)
-        sd = self._full_state
+            sd = self._do_sync_state(msg)
         names = m.get("names") or [k for k in sd if not k.endswith(("/m", "/v"))]
         return pack({k: sd[k].cpu() for k in names if k in sd})
 
@@ -205,14 +220,17 @@ class ServiceImpl:
     def DoRemoteRestore(self, req: bytes, ctx) -> bytes:
         m = unpack(req)
         msg = {"cmd": "restore", **m}
-        self._bcast(msg)
-        return pack({"result": self._do_restore(msg)})
+        with self.exec_lock:
+            self._bcast(msg)
+            r = self._do_restore(msg)
+        return pack({"result": r})
 
     def GetServerInfo(self, req: bytes, ctx) -> bytes:
         return pack({"world": self.world, "config": self.env.dump(), "steps": len(self.step_log)})
 
     def Shutdown(self, req: bytes, ctx) -> bytes:
-        self._bcast({"cmd": "shutdown"})
+        with self.exec_lock:
+            self._bcast({"cmd": "shutdown"})
         threading.Timer(0.2, lambda: self._server.stop(0)).start()
         return pack({"ok": True})
 

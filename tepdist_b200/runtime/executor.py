@@ -647,17 +647,23 @@ class Executor:
         if not self.use_cuda_graph:
             return self._run(feeds)
         if self._graph is None:
-            # static input buffers, eager warm-up on a side stream, then capture
-            for k, t in feeds.items():
-                self._static_in[k] = t.to(self.device).clone()
-            s = torch.cuda.Stream()
-            s.wait_stream(torch.cuda.current_stream())
-            with torch.cuda.stream(s):
-                out = self._run(self._static_in)
-            torch.cuda.current_stream().wait_stream(s)
-            torch.cuda.synchronize()
-            if self.step_count < 2:
+            if not self._static_in:
+                # first call: static input buffers + an eager step on a side stream (it is both this call's step and the
+                # warm-up the capture needs: lazy allocations, symmetric buffers, kernel attribute setup)
+                for k, t in feeds.items():
+                    self._static_in[k] = t.to(self.device).clone()
+                s = torch.cuda.Stream()
+                s.wait_stream(torch.cuda.current_stream())
+                with torch.cuda.stream(s):
+                    out = self._run(self._static_in)
+                torch.cuda.current_stream().wait_stream(s)
+                torch.cuda.synchronize()
                 return out
+            # second call: capture, then replay once -- exactly ONE optimizer update per step() call (an eager run followed by
+            # capture + replay would apply the same batch twice with the same step index)
+            for k, t in feeds.items():
+                self._static_in[k].copy_(t, non_blocking=True)
+            torch.cuda.synchronize()
             self._graph = torch.cuda.CUDAGraph()
             with torch.cuda.graph(self._graph):
                 self._static_out = self._run(self._static_in)

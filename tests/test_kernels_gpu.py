@@ -49,5 +49,8 @@ def test_cuda_graph_step_matches_eager():
     lab = torch.roll(tok, -1, 1)
     la = [float(a.step({"tokens": tok, "labels": lab})[0]) for _ in range(6)]
     lb = [float(b.step({"tokens": tok, "labels": lab})[0]) for _ in range(6)]
-    # step 2 of the graph executor is the capture step (not executed), so its trajectory lags by one update
+    # one optimizer update per step() call on both paths (eager first call, capture + single replay on the second): the
+    # trajectories agree step by step up to the summation-order noise of bf16 kernels
     assert la[-1] < la[0] and lb[-1] < lb[0]
+    for x, y in zip(la, lb):
+        assert abs(x - y) < 2e-2 * abs(y), (la, lb)

@@ -100,6 +100,62 @@ def test_step_pipelining_env(tmp_path, monkeypatch):
     server.stop(0)
 
 
+def test_periodic_variable_fetch_and_step_order(tmp_path, monkeypatch):
+    """FETCH_RESOURCE_VAR_STEPS=2: every second ExecutePlan returns all (non-slot) variables and refreshes Client.variables;
+    pipelined steps (NUM_PARALLEL_RPC_STEPS) execute in issue order -- the server enforces the client's sequence numbers."""
+    monkeypatch.setenv("FETCH_RESOURCE_VAR_STEPS", "2")
+    monkeypatch.setenv("NUM_PARALLEL_RPC_STEPS", "3")
+    impl, server, cl = _start(tmp_path)
+    cfg = CONFIGS["tiny"]
+    cl.build_execution_plan(build_gpt2_graph(cfg))
+    tok = torch.randint(0, cfg.n_vocab, (cfg.batch, cfg.n_ctx), dtype=torch.int32)
+    feeds = {"tokens": tok, "labels": torch.roll(tok, -1, 1)}
+    r1 = cl.execute_plan(feeds).result()
+    assert "vars" not in r1 and not cl.variables
+    r2 = cl.execute_plan(feeds).result()
+    assert "model/ln_f/g" in r2["vars"] and not any(k.endswith(("/m", "/v")) for k in r2["vars"])
+    snap = cl.variables["model/ln_f/g"].clone()
+    futs = [cl.execute_plan(feeds) for _ in range(6)]
+    losses = [f.result()["loss"] for f in futs]
+    assert losses == sorted(losses, reverse=True), losses       # same batch every step: in-order execution is monotone
+    assert not torch.equal(cl.variables["model/ln_f/g"], snap)  # refreshed at steps 4, 6, 8
+    assert impl.next_seq == 9
+    server.stop(0)
+
+
+def test_requests_cannot_carry_code(tmp_path):
+    """Request bodies go through the restricted unpickler: a pickle that would run code on load is rejected by the server."""
+    import io
+    import pickle
+    import grpc
+    from tepdist_b200.rpc.service import SERVICE, unpack
+
+    class Evil:
+        def __reduce__(self):
+            return (os.system, ("echo pwned > %s" % (tmp_path / "pwned"),))
+
+    buf = io.BytesIO()
+    torch.save({"x": Evil()}, buf)
+    with pytest.raises(pickle.UnpicklingError):
+        unpack(buf.getvalue())
+    impl, server, cl = _start(tmp_path)
+    with pytest.raises(grpc.RpcError):
+        cl.channel.unary_unary(f"/{SERVICE}/FetchResourceVars")(buf.getvalue())
+    assert not (tmp_path / "pwned").exists()
+    server.stop(0)
+
+
+def test_resaving_a_step_keeps_its_directory(tmp_path):
+    from tepdist_b200.ckpt import CheckpointManager
+    from tepdist_b200.runtime.executor import Executor
+    ex = Executor(build_gpt2_graph(CONFIGS["tiny"]), torch.device("cpu"), use_cuda_graph=False)
+    cm = CheckpointManager(str(tmp_path), 0, 1, max_to_keep=1)
+    cm.save(ex, 5)
+    cm.save(ex, 5)
+    assert cm.queue == [5] and os.path.exists(os.path.join(cm.dir, "step_5", "manifest.json"))
+    assert cm.restore(ex) == 5
+
+
 def test_launcher_cluster_spec(tmp_path):
     from tepdist_b200.launch import entry_for
     spec = {"master": {"ip": "10.0.0.1", "port": 2222, "gpu_ids": [0, 1]}, "workers": [{"ip": "10.0.0.2", "port": 2223, "gpu_ids": [2, 3]}]}
