@@ -64,6 +64,7 @@ def main():
     ap.add_argument("--comm", default="fused", choices=["fused", "nccl"])
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--no-exposed", action="store_true", help="skip the exposed-communication measurement (N > 1)")
+    ap.add_argument("--no-tp", action="store_true", help="skip the tensor-parallel arm (N > 1)")
     args = ap.parse_args()
 
     if args.impl == "reference":
@@ -180,10 +181,41 @@ def main():
         barrier()
         ms_dry = g0.elapsed_time(g1)
 
-    t = torch.tensor([ms, ms_e2e, ms_dry], dtype=torch.float64, device=dev)
+    # ---------------- tensor-parallel arm (BASELINE.json config "GPT-2 345M auto-SPMD (tensor-parallel)"): the SAME global
+    # step (batch = per-GPU batch x N) under the planner's Megatron plan (weight matrices stored sharded over all N GPUs,
+    # `linear -> all_reduce -> + bias -> + residual` chains), once with the chains executed as GEMM -> NVLS all-reduce
+    # (multimem kernels over the multicast-bound symmetric buffers, comm = fused) and once with NCCL collectives.
+    tp_ms = {"fused": 0.0, "nccl": 0.0}
+    tp_info = {}
+    if world > 1 and not library and not args.no_tp:
+        from tepdist_b200.runtime import executor as ex_mod
+        for tag, fused, comm in (("fused", True, "fused"), ("nccl", False, "nccl")):
+            try:
+                ex_mod.TP_FUSED = fused
+                ttr = Trainer(graph, strategy="tp", use_cuda_graph=not args.no_graph, comm_mode=comm)
+                for i in range(W):
+                    ttr.step_async({"tokens": dev_tok[i % nbuf], "labels": dev_lab[i % nbuf]})
+                barrier()
+                h0, h1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                h0.record()
+                for i in range(K):
+                    tl = ttr.step_async({"tokens": dev_tok[i % nbuf], "labels": dev_lab[i % nbuf]})
+                h1.record()
+                barrier()
+                tp_ms[tag] = h0.elapsed_time(h1)
+                tp_info[tag + "_chains"] = len(getattr(ttr.exec, "tp_fuse", {}) or {})
+                tp_info[tag + "_loss"] = float(tl)
+                tp_info["parallelism"] = ttr.plan_info.get("parallelism")
+                del ttr
+            except Exception as e:  # noqa: BLE001  (the headline number must survive a failure of the extra arm)
+                tp_info[tag + "_error"] = f"{type(e).__name__}: {e}"[:300]
+            finally:
+                ex_mod.TP_FUSED = False
+
+    t = torch.tensor([ms, ms_e2e, ms_dry, tp_ms["fused"], tp_ms["nccl"]], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms, ms_e2e, ms_dry = t.tolist()
+    ms, ms_e2e, ms_dry, tp_fused_ms, tp_nccl_ms = t.tolist()
     if rank == 0:
         tokens = B * S * world * K
         value = tokens / (ms / 1e3)
@@ -215,6 +247,18 @@ def main():
             "final_loss": final_loss,
             "clocks": summarize_clocks(samples),
         }
+        if world > 1 and not library and not args.no_tp:
+            tp = dict(tp_info)
+            tp["global_batch"] = B * world
+            for tag, v in (("fused", tp_fused_ms), ("nccl", tp_nccl_ms)):
+                if v > 0:
+                    tp[tag + "_ms_per_step"] = v / K
+                    tp[tag + "_tokens_per_s"] = tokens / (v / 1e3)
+            if tp_fused_ms > 0 and tp_nccl_ms > 0:
+                tp["fused_over_nccl"] = tp_nccl_ms / tp_fused_ms
+            tp["note"] = ("same global batch as the data-parallel headline; fused = GEMM -> multimem (NVLS) all-reduce with bias + "
+                          "residual in the reduction kernel, nccl = same plan with NCCL all-reduce + separate bias / residual adds")
+            out["tp"] = tp
         print(json.dumps(out), flush=True)
     if world > 1:
         dist.barrier()

@@ -177,6 +177,7 @@ PYBIND11_MODULE(_C, m) {
       .def(py::init<>())
       .def_readwrite("num", &SpmdOptions::num)
       .def_readwrite("var_mem_limit", &SpmdOptions::var_mem_limit)
+      .def_readwrite("mem_split_min_rank", &SpmdOptions::mem_split_min_rank)
       .def_readwrite("cost_factor", &SpmdOptions::cost_factor)
       .def_readwrite("opt_level", &SpmdOptions::opt_level)
       .def_readwrite("ignore_annotation", &SpmdOptions::ignore_annotation)

@@ -53,7 +53,7 @@ void BuildProblem(Problem& p, SpmdStats* stats) {
     if (n.op == "parameter") {
       double b = VarStateBytes(g, n, adam);
       var_bytes += b;
-      vars.push_back({b, n.id});
+      if ((int)n.outputs[0].dims.size() >= opt.mem_split_min_rank) vars.push_back({b, n.id});
     }
   std::set<int> must_split;
   std::sort(vars.rbegin(), vars.rend());

@@ -22,6 +22,8 @@ namespace tepdist {
 struct SpmdOptions {
   int num = 2;                       // devices at this mesh level
   double var_mem_limit = 150e9;      // VAR_MEM_LIMIT (bytes per device for variables + slots + grads)
+  int mem_split_min_rank = 1;        // memory plan: only variables of at least this rank may be FORCED to be stored sharded
+                                     // (2 = matrices only: Megatron-style tensor parallelism keeps biases / LayerNorm vectors whole)
   double cost_factor = 1.0;          // COST_FACTOR (all-to-all weight)
   int opt_level = 2;                 // OPT_LEVEL: >=3 one whole-graph problem, <3 sub-graph DP
   bool ignore_annotation = true;     // IGNORE_ANNOTATION

@@ -28,7 +28,8 @@ def plan_spmd(graph: Graph, num: int, strategy: str = "auto", options: Optional[
     if strategy in ("dp", "tp"):
         o.ignore_annotation = False
     if strategy == "tp":
-        o.var_mem_limit = 1.0  # force every weight to be stored sharded -> tensor parallel
+        o.var_mem_limit = 1.0  # force every weight MATRIX to be stored sharded -> tensor parallel (vectors stay whole)
+        o.mem_split_min_rank = 2
     from .. import config
     o.hw = config.hw_profile()
     config.check_num_gradients(sum(1 for n in graph.nodes if n.op.startswith("apply_")))
@@ -93,6 +94,7 @@ def plan_spmd_mesh(graph: Graph, nums, kinds):
                 setattr(o, k, v)
         if kind == "tp":
             o.var_mem_limit = 1.0
+            o.mem_split_min_rank = 2
         plan = _C.plan_spmd_level(cg, o)
         infeasible += plan.stats.infeasible_subgraphs
         cg, _ = _C.spmd_transform(cg, plan, lvl, int(num))

@@ -460,6 +460,35 @@ class GemmAllReduce:
         return out.tensor(torch.bfloat16, self.M * self.N).view(self.M, self.N)
 
 
+class GemmAllReduceMC:
+    """Row-parallel linear + ALL-reduce over NVLS: the tcgen05 GEMM writes its bf16 partial [M, N] straight into a
+    symmetric buffer (no staging copy), then ONE multimem kernel reduces it inside the NVSwitch -- every rank pulls its 1/n
+    slice with `multimem.ld_reduce` (fp32 accumulation in the switch), adds bias + residual and publishes the finished
+    rows to all ranks with `multimem.st`; the two cross-rank barriers live inside that kernel (one `multimem.red` per CTA).
+    Per element the owner receives 1x (not (n-1)x) and sends 1x (not (n-1)x): the NVLink bytes of a tensor-parallel
+    all-reduce no longer grow with n.  Same call interface as GemmAllReduce (the unicast slot version)."""
+
+    def __init__(self, M: int, N: int, group=None, ctx: Optional["McContext"] = None, ctas: int = 0):
+        self.M, self.N, self.group = M, N, group
+        self.world = dist.get_world_size(group)
+        self.rank = dist.get_rank(group)
+        assert (M * N) % (8 * self.world) == 0
+        self.ctx = ctx or McContext(group)
+        self.ctas = ctas
+
+    def new_output(self) -> SymmetricBuffer:
+        return SymmetricBuffer(self.M * self.N * 2, self.group, backend="vmm")
+
+    def __call__(self, x: torch.Tensor, w: torch.Tensor, out: SymmetricBuffer, bias: Optional[torch.Tensor] = None,
+                 residual: Optional[torch.Tensor] = None, b_mn: bool = False, block_n: int = 0) -> torch.Tensor:
+        y = out.tensor(torch.bfloat16, self.M * self.N).view(self.M, self.N)
+        ops.gemm(x, w, b_mn=b_mn, out=y)
+        if residual is not None:
+            assert residual.is_contiguous() and residual.dtype == torch.bfloat16
+        self.ctx.all_reduce_bf16_(out, self.M * self.N, self.N, bias=bias, residual=residual, ctas=self.ctas)
+        return y
+
+
 class AllGatherGemm:
     """Column-parallel linear fused with the all-gather of its row-sharded input.  A small copy kernel on a side stream
     pulls the peers' shards into a local staging buffer chunk by chunk (p2p_gather_chunks) while the persistent GEMM

@@ -1091,16 +1091,22 @@ class Executor:
         if TP_FUSED_IMPL is not None:
             GemmAllReduce, SymmBarrier = TP_FUSED_IMPL, (lambda pg: None)
         else:
-            from ..parallel.symm import GemmAllReduce, SymmBarrier
+            from ..parallel.symm import GemmAllReduce, GemmAllReduceMC, McContext, SymmBarrier, symm_backend
         self._tp_ops: Dict[Tuple[int, int, int], Any] = {}
         bar: Dict[int, Any] = {}
         for lid, info in self.tp_fuse.items():
             key = (info["level"], info["M"], info["N"])
             if key not in self._tp_ops:
                 pg = mesh.group(info["level"])
+                # NVLS (multicast) version when the group's symmetric memory is multicast-bound; unicast slots otherwise
+                use_mc = (TP_FUSED_IMPL is None and os.environ.get("TEPDIST_TP_MC", "1") == "1" and symm_backend(pg) == "vmm"
+                          and (info["M"] * info["N"]) % (8 * info["num"]) == 0)
                 if info["level"] not in bar:
-                    bar[info["level"]] = SymmBarrier(pg)
-                self._tp_ops[key] = GemmAllReduce(info["M"], info["N"], pg, bar[info["level"]])
+                    bar[info["level"]] = McContext(pg) if use_mc else SymmBarrier(pg)
+                if use_mc:
+                    self._tp_ops[key] = GemmAllReduceMC(info["M"], info["N"], pg, bar[info["level"]])
+                else:
+                    self._tp_ops[key] = GemmAllReduce(info["M"], info["N"], pg, bar[info["level"]])
             info["op"] = self._tp_ops[key]
             info["out"] = info["op"].new_output()        # symmetric [M, N] bf16, written by every rank
             # each chain node aliases its immediate predecessor (lin -> ar -> +bias -> +res): that is the dataflow the
@@ -1303,7 +1309,15 @@ class Executor:
             T = int(a.get("global_tokens", l2.shape[0]))  # batch-sharded: partial sum of the GLOBAL mean
             total, _rows = ops.xent_fwd_bwd(l2, labels.reshape(-1), a.get("vocab", Vp), 1.0 / T)
             return [total.reshape(()), l2.view(logits.shape)]
-        return self._exec_generic(n, ins)
+        outs = self._exec_generic(n, ins)
+        # mixed-precision operands (bf16 activation + fp32 bias / statistic) promote in torch; the plan's declared element type
+        # is what every consumer -- and every hand-written kernel behind it -- expects
+        for i, t in enumerate(outs):
+            if i < len(n.outputs) and torch.is_tensor(t) and t.is_floating_point():
+                want = torch_dtype(n.outputs[i].dtype, dev)
+                if want.is_floating_point and t.dtype != want:
+                    outs[i] = t.to(want)
+        return outs
 
     def _exec_generic(self, n: Node, ins: List[torch.Tensor]) -> List[torch.Tensor]:
         """HLO-like ops: plain torch math (not on the GPT-2 hot path; conv/bn go through cuDNN exactly as the

@@ -42,11 +42,13 @@ def main():
 
     # ---- unicast peer mapping through the VMM handles: write own rank id, read the neighbour's
     probe = symm.SymmetricBuffer(4096)
-    probe.tensor(torch.int32)[:16] = rank + 1
+    probe.tensor(torch.float32)[:1024] = float(rank + 1)
     torch.cuda.synchronize(); dist.barrier()
-    peer = (rank + 1) % n
-    pv = torch.as_tensor(symm._CudaArray(probe.ptrs[peer], 64), device="cuda").view(torch.int32)
-    res["peer_read_ok"] = bool((pv == peer + 1).all().item())
+    acc = torch.zeros(1024, device=dev)
+    symm._sigs(probe.lib)
+    rc = probe.lib.tepd_p2p_reduce_scatter(probe.ptr_array, acc.data_ptr(), n, 0, 1024, 4, torch.cuda.current_stream().cuda_stream)
+    torch.cuda.synchronize()
+    res["peer_read_ok"] = bool(rc == 0 and (acc == n * (n + 1) / 2).all().item())
     say("peer read", res["peer_read_ok"])
 
     # ---- all-reduce numerics (+ bias + residual epilogue)
