@@ -118,10 +118,16 @@ def main():
         local_rank = trainer.ctx["local_rank"]
     assert world == args.gpus, f"--gpus {args.gpus} but WORLD_SIZE={world} (launch with torch.distributed.run)"
     B, S = args.batch, cfg.n_ctx
-    gen = torch.Generator().manual_seed(1234 + rank)
+    is_pp = (not library) and args.strategy.startswith("pp")
+    if is_pp:
+        # pipeline plans: stage 0 consumes the tokens, the last stage the labels, each sliced per micro-batch -- every rank is
+        # fed the GLOBAL batch (the same on all ranks) and the stage workers take what their stage needs
+        args.no_exposed = args.no_tp = True
+    gen = torch.Generator().manual_seed(1234 + (0 if is_pp else rank))
     # synthetic fake_input: random tokens, labels = tokens shifted by one (reference: examples/GPT2/inputs.py:42-55)
     nbuf = 4
-    host_tok = [torch.randint(0, cfg.n_vocab, (B, S), generator=gen, dtype=torch.int32).pin_memory() for _ in range(nbuf)]
+    rows = B * world if is_pp else B
+    host_tok = [torch.randint(0, cfg.n_vocab, (rows, S), generator=gen, dtype=torch.int32).pin_memory() for _ in range(nbuf)]
     host_lab = [torch.roll(t, -1, 1).pin_memory() for t in host_tok]
     dev_tok = [t.to(dev) for t in host_tok]
     dev_lab = [t.to(dev) for t in host_lab]
@@ -237,8 +243,8 @@ def main():
                        "optimizer": "AdamW (fp32 master + moments)", "parallelism": parallelism if library else trainer.plan_info.get("parallelism", f"dp{world}"),
                        "cuda_graph": (lt.use_graph if library else not args.no_graph), "comm": "nccl-per-tensor" if library else args.comm,
                        "l2": "working set per step >> 126 MB L2 (0.7 GB bf16 weights + 5.7 GB fp32 optimizer state touched every step)"},
-            "e2e": {"value": e2e, "unit": "tokens/s", "ms_per_step": ms_e2e / K, "h2d_bytes_per_step": 2 * B * S * 4 * world,
-                    "d2h_bytes_per_step": 4 * world},
+            "e2e": {"value": e2e, "unit": "tokens/s", "ms_per_step": ms_e2e / K,
+                    "h2d_bytes_per_step": 2 * rows * S * 4 * world, "d2h_bytes_per_step": 4 * world},
             "gpu_launches": launches,
             "exposed_comm_ms_per_step": ((ms - ms_dry) / K) if ms_dry > 0 else (0.0 if world == 1 else None),
             "compute_only_ms_per_step": (ms_dry / K) if ms_dry > 0 else None,
@@ -247,6 +253,12 @@ def main():
             "final_loss": final_loss,
             "clocks": summarize_clocks(samples),
         }
+        if is_pp:
+            pi = trainer.plan_info
+            out["pipeline"] = {"stages": pi.get("stages"), "micro_batches": pi.get("micro"), "spmd": pi.get("spmd"),
+                               "stage_cut": pi.get("stage_method"), "cut_bytes": pi.get("cut_bytes"),
+                               "scheduler_bubble_estimate": pi.get("bubble_est"), "scheduler_makespan_estimate_s": pi.get("makespan_est"),
+                               "p2p": "NCCL isend/irecv on side streams", "cuda_graph": False}
         if world > 1 and not library and not args.no_tp:
             tp = dict(tp_info)
             tp["global_batch"] = B * world

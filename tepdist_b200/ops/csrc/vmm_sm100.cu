@@ -357,49 +357,74 @@ __device__ __forceinline__ void adamw_one(float& p, float g, float& m, float& v,
 // buffer (fp32, or bf16 when GRAD_BF16); param_mc: multicast view of the symmetric bf16 parameter buffer.  No barrier
 // inside: the caller brackets a group of bucket launches with mc_barrier (gradients complete / parameters delivered).
 template <bool GRAD_BF16>
-__global__ void __launch_bounds__(256) mc_rs_adamw_ag_kernel(const void* __restrict__ grad_mc, bf16* __restrict__ param_mc,
+__device__ __forceinline__ void mc_load_grad8(const void* grad_mc, long long e, float (&g)[8]) {
+  if constexpr (GRAD_BF16) {
+    const uint4 u = mm_ld_reduce_bf16x8(reinterpret_cast<const bf16*>(grad_mc) + e);
+    const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
+#pragma unroll
+    for (int q = 0; q < 4; ++q) { const float2 t = __bfloat1622float2(h[q]); g[2 * q] = t.x; g[2 * q + 1] = t.y; }
+  } else {
+    const float4 a = mm_ld_reduce_f32x4(reinterpret_cast<const float*>(grad_mc) + e);
+    const float4 b = mm_ld_reduce_f32x4(reinterpret_cast<const float*>(grad_mc) + e + 4);
+    g[0] = a.x; g[1] = a.y; g[2] = a.z; g[3] = a.w; g[4] = b.x; g[5] = b.y; g[6] = b.z; g[7] = b.w;
+  }
+}
+
+__device__ __forceinline__ void adamw_update8(float (&g)[8], bf16* __restrict__ param_mc, float* __restrict__ master,
+                                              float* __restrict__ mom, float* __restrict__ var, long long e, long long n_decay,
+                                              float lr, float b1, float b2, float eps, float wd, float bc1, float bc2, float gscale) {
+  float p[8], m[8], v[8];
+#pragma unroll
+  for (int h = 0; h < 2; ++h) {
+    const float4 pp = *reinterpret_cast<const float4*>(master + e + 4 * h);
+    const float4 mm = *reinterpret_cast<const float4*>(mom + e + 4 * h);
+    const float4 vv = *reinterpret_cast<const float4*>(var + e + 4 * h);
+    p[4 * h] = pp.x; p[4 * h + 1] = pp.y; p[4 * h + 2] = pp.z; p[4 * h + 3] = pp.w;
+    m[4 * h] = mm.x; m[4 * h + 1] = mm.y; m[4 * h + 2] = mm.z; m[4 * h + 3] = mm.w;
+    v[4 * h] = vv.x; v[4 * h + 1] = vv.y; v[4 * h + 2] = vv.z; v[4 * h + 3] = vv.w;
+  }
+#pragma unroll
+  for (int j = 0; j < 8; ++j) adamw_one(p[j], g[j] * gscale, m[j], v[j], lr, b1, b2, eps, (e + j < n_decay) ? wd : 0.f, bc1, bc2);
+#pragma unroll
+  for (int h = 0; h < 2; ++h) {
+    *reinterpret_cast<float4*>(master + e + 4 * h) = make_float4(p[4 * h], p[4 * h + 1], p[4 * h + 2], p[4 * h + 3]);
+    *reinterpret_cast<float4*>(mom + e + 4 * h) = make_float4(m[4 * h], m[4 * h + 1], m[4 * h + 2], m[4 * h + 3]);
+    *reinterpret_cast<float4*>(var + e + 4 * h) = make_float4(v[4 * h], v[4 * h + 1], v[4 * h + 2], v[4 * h + 3]);
+  }
+  uint4 u;
+  __nv_bfloat162* h2 = reinterpret_cast<__nv_bfloat162*>(&u);
+#pragma unroll
+  for (int q = 0; q < 4; ++q) h2[q] = __floats2bfloat162_rn(p[2 * q], p[2 * q + 1]);
+  mm_st_b128(param_mc + e, u);     // all-gather: one store, the switch replicates it to every rank
+}
+
+// Flat element range [begin, end) is owned by this rank (8-aligned).  grad_mc: multicast view of the symmetric gradient
+// buffer (fp32, or bf16 when GRAD_BF16); param_mc: multicast view of the symmetric bf16 parameter buffer.  No barrier
+// inside: the caller brackets a group of bucket launches with mc_barrier (gradients complete / parameters delivered).
+// A switch reduction has several microseconds of latency: every thread keeps UNROLL independent ones in flight.
+template <bool GRAD_BF16>
+__global__ void __launch_bounds__(256, 2) mc_rs_adamw_ag_kernel(const void* __restrict__ grad_mc, bf16* __restrict__ param_mc,
                                                              float* __restrict__ master, float* __restrict__ mom,
                                                              float* __restrict__ var, long long begin, long long end,
                                                              long long n_decay, float b1, float b2, float eps, float wd,
                                                              const float* __restrict__ hyper) {
+  constexpr int UNROLL = 4;
   const float lr = hyper[0], bc1 = hyper[1], bc2 = hyper[2], gscale = hyper[3];
   const long long nvec = (end - begin) >> 3;
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < nvec; i += (long long)gridDim.x * blockDim.x) {
-    const long long e = begin + (i << 3);
+  const long long step = (long long)gridDim.x * blockDim.x;
+  long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  for (; i + (UNROLL - 1) * step < nvec; i += UNROLL * step) {
+    float g[UNROLL][8];
+#pragma unroll
+    for (int u = 0; u < UNROLL; ++u) mc_load_grad8<GRAD_BF16>(grad_mc, begin + ((i + u * step) << 3), g[u]);
+#pragma unroll
+    for (int u = 0; u < UNROLL; ++u)
+      adamw_update8(g[u], param_mc, master, mom, var, begin + ((i + u * step) << 3), n_decay, lr, b1, b2, eps, wd, bc1, bc2, gscale);
+  }
+  for (; i < nvec; i += step) {
     float g[8];
-    if constexpr (GRAD_BF16) {
-      const uint4 u = mm_ld_reduce_bf16x8(reinterpret_cast<const bf16*>(grad_mc) + e);
-      const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
-#pragma unroll
-      for (int q = 0; q < 4; ++q) { const float2 t = __bfloat1622float2(h[q]); g[2 * q] = t.x; g[2 * q + 1] = t.y; }
-    } else {
-      const float4 a = mm_ld_reduce_f32x4(reinterpret_cast<const float*>(grad_mc) + e);
-      const float4 b = mm_ld_reduce_f32x4(reinterpret_cast<const float*>(grad_mc) + e + 4);
-      g[0] = a.x; g[1] = a.y; g[2] = a.z; g[3] = a.w; g[4] = b.x; g[5] = b.y; g[6] = b.z; g[7] = b.w;
-    }
-    float p[8], m[8], v[8];
-#pragma unroll
-    for (int h = 0; h < 2; ++h) {
-      const float4 pp = *reinterpret_cast<const float4*>(master + e + 4 * h);
-      const float4 mm = *reinterpret_cast<const float4*>(mom + e + 4 * h);
-      const float4 vv = *reinterpret_cast<const float4*>(var + e + 4 * h);
-      p[4 * h] = pp.x; p[4 * h + 1] = pp.y; p[4 * h + 2] = pp.z; p[4 * h + 3] = pp.w;
-      m[4 * h] = mm.x; m[4 * h + 1] = mm.y; m[4 * h + 2] = mm.z; m[4 * h + 3] = mm.w;
-      v[4 * h] = vv.x; v[4 * h + 1] = vv.y; v[4 * h + 2] = vv.z; v[4 * h + 3] = vv.w;
-    }
-#pragma unroll
-    for (int j = 0; j < 8; ++j) adamw_one(p[j], g[j] * gscale, m[j], v[j], lr, b1, b2, eps, (e + j < n_decay) ? wd : 0.f, bc1, bc2);
-#pragma unroll
-    for (int h = 0; h < 2; ++h) {
-      *reinterpret_cast<float4*>(master + e + 4 * h) = make_float4(p[4 * h], p[4 * h + 1], p[4 * h + 2], p[4 * h + 3]);
-      *reinterpret_cast<float4*>(mom + e + 4 * h) = make_float4(m[4 * h], m[4 * h + 1], m[4 * h + 2], m[4 * h + 3]);
-      *reinterpret_cast<float4*>(var + e + 4 * h) = make_float4(v[4 * h], v[4 * h + 1], v[4 * h + 2], v[4 * h + 3]);
-    }
-    uint4 u;
-    __nv_bfloat162* h2 = reinterpret_cast<__nv_bfloat162*>(&u);
-#pragma unroll
-    for (int q = 0; q < 4; ++q) h2[q] = __floats2bfloat162_rn(p[2 * q], p[2 * q + 1]);
-    mm_st_b128(param_mc + e, u);     // all-gather: one store, the switch replicates it to every rank
+    mc_load_grad8<GRAD_BF16>(grad_mc, begin + (i << 3), g);
+    adamw_update8(g, param_mc, master, mom, var, begin + (i << 3), n_decay, lr, b1, b2, eps, wd, bc1, bc2, gscale);
   }
 }
 

@@ -287,22 +287,46 @@ class SymmBarrier:
 
 
 class FusedShardedOptimizer:
-    """reduce-scatter(grad) + AdamW(owned shard) + bf16 all-gather(param) as one peer-memory kernel per bucket."""
+    """reduce-scatter(grad) + AdamW(owned shard) + bf16 all-gather(param) as one kernel per bucket.
+
+    Multicast-bound buffers (backend 'vmm'): the NVLS kernel -- the gradient chunk arrives already summed by the switch
+    (`multimem.ld_reduce`, one load per 16 bytes instead of n-1 peer loads) and the updated bf16 shard leaves the GPU once
+    (`multimem.st`, replicated by the switch instead of n-1 peer stores); barriers are one `multimem.red` per rank with a
+    bounded spin.  Otherwise (IPC mappings, or TEPDIST_DP_MC=0): unicast P2P loads / stores."""
 
     def __init__(self, grad_buf: SymmetricBuffer, param_buf: SymmetricBuffer, group=None):
+        import os
         self.g, self.p = grad_buf, param_buf
-        self._barrier = SymmBarrier(group)
         self.world, self.rank = grad_buf.world, grad_buf.rank
+        self.mc: Optional[McContext] = None
+        if (grad_buf.mc_ptr is not None and param_buf.mc_ptr is not None and os.environ.get("TEPDIST_DP_MC", "1") == "1"):
+            self.mc = McContext(group)
+            self._barrier = None
+        else:
+            self._barrier = SymmBarrier(group)
+        self.mc_ctas = int(os.environ.get("TEPDIST_MC_CTAS", "0"))
         self.dry = False     # timing-only: same kernel on local memory alone (exposed-communication measurement)
 
     def barrier(self) -> None:
-        if not self.dry:
+        if self.dry:
+            return
+        if self.mc is not None:
+            self.mc.barrier()
+        else:
             self._barrier()
 
     def step(self, master, m, v, begin: int, end: int, n_decay: int, hyper, beta1, beta2, eps, wd, ctas: int = 0,
              local_grad: bool = False) -> None:
         """local_grad: the gradient of [begin, end) is already complete on every rank (replicated computation): only the
         update is sharded -- the owner reads its local gradient and still stores the new bf16 values to every peer."""
+        if self.mc is not None and not self.dry and not local_grad and begin % 8 == 0 and end % 8 == 0:
+            rc = self.g.lib.tepd_mc_rs_adamw_ag(self.g.mc_ptr, self.p.mc_ptr, master.data_ptr(), m.data_ptr(), v.data_ptr(),
+                                                begin, end, n_decay, beta1, beta2, eps, wd, hyper.data_ptr(), 0,
+                                                self.mc_ctas or ctas, torch.cuda.current_stream().cuda_stream)
+            if rc:
+                raise RuntimeError(f"mc_rs_adamw_ag failed ({rc})")
+            ops._count()
+            return
         gp, pp, n = self.g.ptr_array, self.p.ptr_array, self.world
         n_grad = n
         if local_grad:

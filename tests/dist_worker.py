@@ -9,6 +9,13 @@ import torch.distributed as dist
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 
 
+def _dev():
+    """CPU (gloo) by default; TEPDIST_TEST_DEVICE=cuda runs the same cases on GPUs over NCCL (tests/test_plans_multi_gpu.py)."""
+    if os.environ.get("TEPDIST_TEST_DEVICE") == "cuda":
+        return torch.device("cuda", int(os.environ.get("LOCAL_RANK", "0")))
+    return torch.device("cpu")
+
+
 def case_gpt2(strategy, feed_shards=False, batch=4):
     from tepdist_b200.api import Trainer
     from tepdist_b200.models.gpt2 import CONFIGS, build_gpt2_graph
@@ -16,7 +23,7 @@ def case_gpt2(strategy, feed_shards=False, batch=4):
     if strategy.startswith("pp") and int(os.environ.get("WORLD_SIZE", "1")) == 1:
         strategy = "auto"   # single-process oracle
     g = build_gpt2_graph(cfg, batch=batch)
-    tr = Trainer(g, strategy=strategy, device=torch.device("cpu"), use_cuda_graph=False)
+    tr = Trainer(g, strategy=strategy, device=_dev(), use_cuda_graph=False)
     torch.manual_seed(0)
     tok = torch.randint(0, cfg.n_vocab, (batch, cfg.n_ctx), dtype=torch.int32)
     lab = torch.roll(tok, -1, 1)
@@ -39,7 +46,7 @@ def case_ckpt(strategy):
     from tepdist_b200.models.gpt2 import CONFIGS, build_gpt2_graph
     cfg = CONFIGS["tiny"]
     g = build_gpt2_graph(cfg, batch=4, optimizer=os.environ.get("TEPDIST_TEST_OPT", "adamw"))
-    tr = Trainer(g, strategy=strategy, device=torch.device("cpu"), use_cuda_graph=False)
+    tr = Trainer(g, strategy=strategy, device=_dev(), use_cuda_graph=False)
     torch.manual_seed(0)
     tok = torch.randint(0, cfg.n_vocab, (4, cfg.n_ctx), dtype=torch.int32)
     feeds = {"tokens": tok, "labels": torch.roll(tok, -1, 1)}
@@ -55,7 +62,7 @@ def case_resume(strategy):
     from tepdist_b200.models.gpt2 import CONFIGS, build_gpt2_graph
     cfg = CONFIGS["tiny"]
     tr = Trainer(build_gpt2_graph(cfg, batch=4, optimizer=os.environ.get("TEPDIST_TEST_OPT", "adamw")), strategy=strategy,
-                 device=torch.device("cpu"), use_cuda_graph=False, seed=123)
+                 device=_dev(), use_cuda_graph=False, seed=123)
     step = tr.restore(os.environ["TEPDIST_TEST_CKPT"])
     torch.manual_seed(0)
     tok = torch.randint(0, cfg.n_vocab, (4, cfg.n_ctx), dtype=torch.int32)
@@ -68,7 +75,7 @@ def case_state(strategy):
     from tepdist_b200.api import Trainer
     from tepdist_b200.models.gpt2 import CONFIGS, build_gpt2_graph
     cfg = CONFIGS["tiny"]
-    tr = Trainer(build_gpt2_graph(cfg, batch=4), strategy=strategy, device=torch.device("cpu"), use_cuda_graph=False)
+    tr = Trainer(build_gpt2_graph(cfg, batch=4), strategy=strategy, device=_dev(), use_cuda_graph=False)
     torch.manual_seed(0)
     tok = torch.randint(0, cfg.n_vocab, (4, cfg.n_ctx), dtype=torch.int32)
     feeds = {"tokens": tok, "labels": torch.roll(tok, -1, 1)}
@@ -100,7 +107,7 @@ def case_clip(strategy):
         g.meta["optimizer"].update(lr=0.5)
         if mode != "none":
             g.meta["optimizer"].update(clip_norm=mode, clip_norm_value=0.05)
-        tr = Trainer(g, strategy=strategy, device=torch.device("cpu"), use_cuda_graph=False)
+        tr = Trainer(g, strategy=strategy, device=_dev(), use_cuda_graph=False)
         torch.manual_seed(0)
         tok = torch.randint(0, cfg.n_vocab, (4, cfg.n_ctx), dtype=torch.int32)
         out[mode] = [tr.step({"tokens": tok, "labels": torch.roll(tok, -1, 1)}) for _ in range(4)]
@@ -119,7 +126,7 @@ def case_sched(strategy):
     for opt, lr in (("adamw", 0.02), ("sgd", 0.5)):
         g = build_gpt2_graph(cfg, batch=4, optimizer=opt, schedule={"kind": "warmup_cosine", "warmup_steps": 2, "total_steps": 5, "end_ratio": 0.1})
         g.meta["optimizer"]["lr"] = lr
-        tr = Trainer(g, strategy=strategy, device=torch.device("cpu"), use_cuda_graph=False)
+        tr = Trainer(g, strategy=strategy, device=_dev(), use_cuda_graph=False)
         torch.manual_seed(0)
         tok = torch.randint(0, cfg.n_vocab, (4, cfg.n_ctx), dtype=torch.int32)
         out[opt] = [tr.step({"tokens": tok, "labels": torch.roll(tok, -1, 1)}) for _ in range(5)]
@@ -133,7 +140,7 @@ def case_fullstate(strategy):
     cfg = CONFIGS["tiny"]
     if strategy.startswith(("pp", "dp2")) and int(os.environ.get("WORLD_SIZE", "1")) == 1:
         strategy = "auto"
-    tr = Trainer(build_gpt2_graph(cfg, batch=4), strategy=strategy, device=torch.device("cpu"), use_cuda_graph=False)
+    tr = Trainer(build_gpt2_graph(cfg, batch=4), strategy=strategy, device=_dev(), use_cuda_graph=False)
     torch.manual_seed(0)
     tok = torch.randint(0, cfg.n_vocab, (4, cfg.n_ctx), dtype=torch.int32)
     feeds = {"tokens": tok, "labels": torch.roll(tok, -1, 1)}
@@ -188,7 +195,7 @@ def case_manualdp(strategy):
     world, rank = ctx["world"], ctx["rank"]
     cfg = CONFIGS["tiny"]
     per = 4 // world
-    ex = Executor(build_gpt2_graph(cfg, batch=per), torch.device("cpu"), seed=0, use_cuda_graph=False,
+    ex = Executor(build_gpt2_graph(cfg, batch=per), _dev(), seed=0, use_cuda_graph=False,
                   grad_sync=make_nccl_grad_sync(bucket_elems=10000) if world > 1 else None)
     torch.manual_seed(0)
     tok = torch.randint(0, cfg.n_vocab, (4, cfg.n_ctx), dtype=torch.int32)
@@ -209,7 +216,7 @@ def case_opts(strategy):
     out = {}
     for case in ("momentum", "lamb", "adafactor", "adafactor_relative_step", "sm3", "sm3_momentum"):
         hp = CASES[case][0]
-        tr = Trainer(build_mlp(case.split("_")[0], **hp), strategy=strategy, device=torch.device("cpu"), use_cuda_graph=False, seed=5)
+        tr = Trainer(build_mlp(case.split("_")[0], **hp), strategy=strategy, device=_dev(), use_cuda_graph=False, seed=5)
         torch.manual_seed(1)
         losses = [tr.step({"x": torch.randn(8, 16), "t": torch.randn(8, 4)}) for _ in range(6)]
         g = getattr(tr.exec, "g", None)
@@ -231,7 +238,7 @@ def case_optsgpt(strategy):
     cfg = CONFIGS["tiny"]
     out = {}
     for kind in ("lamb", "adafactor", "sm3"):
-        tr = Trainer(build_gpt2_graph(cfg, batch=4, optimizer=kind), strategy=strategy, device=torch.device("cpu"), use_cuda_graph=False)
+        tr = Trainer(build_gpt2_graph(cfg, batch=4, optimizer=kind), strategy=strategy, device=_dev(), use_cuda_graph=False)
         torch.manual_seed(0)
         tok = torch.randint(0, cfg.n_vocab, (4, cfg.n_ctx), dtype=torch.int32)
         losses = [tr.step({"tokens": tok, "labels": torch.roll(tok, -1, 1)}) for _ in range(4)]
@@ -246,7 +253,7 @@ def case_conv(strategy):
     from tepdist_b200.api import Trainer
     from tepdist_b200.models.smoke import build_conv_graph
     g = build_conv_graph(batch=8)
-    tr = Trainer(g, strategy=strategy, device=torch.device("cpu"), use_cuda_graph=False)
+    tr = Trainer(g, strategy=strategy, device=_dev(), use_cuda_graph=False)
     torch.manual_seed(0)
     feeds = {"x": torch.randn(8, 3, 16, 16), "t": torch.randn(8, 10)}
     losses = [tr.step(feeds) for _ in range(4)]
@@ -260,7 +267,7 @@ def case_mlp(strategy):
     from tepdist_b200.api import Trainer
     from tepdist_b200.models.smoke import build_mlp_graph
     g = build_mlp_graph(batch=8)
-    tr = Trainer(g, strategy=strategy, device=torch.device("cpu"), use_cuda_graph=False)
+    tr = Trainer(g, strategy=strategy, device=_dev(), use_cuda_graph=False)
     torch.manual_seed(0)
     x, t = torch.randn(8, 16), torch.rand(8, 4)
     losses = [tr.step({"x": x, "t": t}) for _ in range(5)]
@@ -274,7 +281,7 @@ def case_moe(strategy):
     g = build_moe_ffn_graph(groups=4, tokens_per_group=32, model=32, hidden=64, experts=4, capacity=16)
     if strategy == "ep":
         strategy = "tp"     # var_mem_limit=1 => weights must be stored sharded; expert dim is the cheapest split
-    tr = Trainer(g, strategy=strategy, device=torch.device("cpu"), use_cuda_graph=False)
+    tr = Trainer(g, strategy=strategy, device=_dev(), use_cuda_graph=False)
     torch.manual_seed(0)
     x, t = torch.randn(4, 32, 32), torch.randn(4, 32, 32)
     losses = [tr.step({"x": x, "t": t}) for _ in range(4)]

@@ -56,8 +56,8 @@ def main():
     M, N = 4096, 1024
     buf = symm.SymmetricBuffer(M * N * 2)
     x = (torch.randn(M, N, device=dev) * 0.5).to(torch.bfloat16)
-    bias = torch.randn(N, device=dev)
     torch.manual_seed(99)
+    bias = torch.randn(N, device=dev)                             # replicated
     resid = torch.randn(M, N, device=dev).to(torch.bfloat16)      # replicated
     ref = x.float().clone()
     dist.all_reduce(ref)

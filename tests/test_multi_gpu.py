@@ -48,8 +48,7 @@ def test_fused_moe_expert_parallel_fp8(tmp_path):
     assert r["relerr"] < 6e-2, r          # e4m3 activations x e4m3 weights
 
 
-@pytest.mark.skipif(torch.cuda.device_count() < 2 or os.environ.get("TEPDIST_TEST_EXPERIMENTAL") != "1",
-                    reason="needs 2 GPUs; opt-in (TEPDIST_TEST_EXPERIMENTAL=1) until the fused TP path is validated on hardware")
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
 def test_tp_plan_fused_all_reduce_matches_nccl(tmp_path):
     out = str(tmp_path / "tpplan.json")
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",

@@ -1,0 +1,62 @@
+"""Plans x GPUs: the same worker cases as the gloo tests (tests/dist_worker.py), on real GPUs over NCCL, against one GPU.
+
+Covers what only ran on CPU before: tensor-parallel, pipeline (1F1B over NCCL p2p), pipeline x SPMD, a two-dimensional SPMD
+mesh and expert parallelism (all-to-all) -- each must reproduce the single-GPU loss trajectory of the same model
+(reference: xla/tests/dapple_*_test.cc run their collectives on real devices)."""
+import json
+import os
+import socket
+import subprocess
+import sys
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _run(case, world, tmp_path):
+    out = str(tmp_path / f"out{world}.json")
+    env = dict(os.environ, TEPDIST_TEST_DEVICE="cuda", OMP_NUM_THREADS="2")
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}", "--master-addr", "127.0.0.1",
+           "--master-port", str(_free_port()), os.path.join(HERE, "dist_worker.py"), case, out]
+    if world == 1:
+        cmd = [sys.executable, os.path.join(HERE, "dist_worker.py"), case, out]
+    pr = subprocess.run(cmd, capture_output=True, text=True, timeout=900, env=env)
+    assert pr.returncode == 0, (pr.stdout[-1500:], pr.stderr[-3000:])
+    return json.load(open(out))
+
+
+def _close(got, ref, tol=3e-2):
+    for a, b in zip(got["losses"], ref["losses"]):
+        assert abs(a - b) <= tol * max(1.0, abs(b)), (got, ref)
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
+def test_plans_on_two_gpus_match_one_gpu(tmp_path):
+    cases = ["gpt2:auto", "gpt2:tp", "gpt2:pp2m2", "moe:ep", "mlp:dp"]
+    ref = _run("gpt2:auto+moe:auto+mlp:auto", 1, tmp_path)
+    got = _run("+".join(cases), 2, tmp_path)
+    for c in cases:
+        _close(got[c], ref[c.split(":")[0] + ":auto"])
+    assert got["gpt2:tp"]["parallelism"].startswith("tp"), got["gpt2:tp"]
+    assert got["gpt2:pp2m2"]["parallelism"].startswith("pp2"), got["gpt2:pp2m2"]
+    assert got["moe:ep"]["collectives"].get("all_to_all", 0) >= 2, got["moe:ep"]
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 4, reason="needs 4 GPUs")
+def test_pipeline_x_spmd_and_2d_mesh_on_four_gpus_match_one_gpu(tmp_path):
+    ref = _run("gpt2:auto", 1, tmp_path)
+    got = _run("gpt2:pp2m2+gpt2:dp2tp2", 4, tmp_path)
+    assert got["gpt2:pp2m2"]["parallelism"] == "pp2xspmd2/micro2", got["gpt2:pp2m2"]
+    _close(got["gpt2:pp2m2"], ref)
+    _close(got["gpt2:dp2tp2"], ref)
