@@ -205,6 +205,8 @@ PYBIND11_MODULE(_C, m) {
   m.def("plan_spmd_level", [](Graph& g, const SpmdOptions& o) { return PlanSpmdLevel(&g, o); });
   m.def("plan_spmd_by_rules", [](Graph& g, const SpmdOptions& o) { return PlanSpmdByRules(&g, o); });
   m.def("dump_strategies", &DumpStrategies);
+  m.def("verify_infer", [](const Graph& g, int num) { return VerifyInfer(g, num); });
+  m.def("unknown_ops", [](bool clear) { return UnknownOps(clear); }, py::arg("clear") = true);
 
   py::class_<PBQP>(m, "PBQP")
       .def(py::init<>())

@@ -395,15 +395,89 @@ void Sm3Rule(Ctx& c) {
   c.add_glue();
 }
 
+// ---- ops a traced torch / HLO-like graph brings along (reference: P/utils.cc:598-612 reverse, :734-917 pad / reduce-window /
+// select-and-scatter / sort / scatter, :1955-1981 iota) -----------------------------------------------------------------------
+void AxesUntouchedRule(Ctx& c, const std::vector<int64_t>& touched) {
+  // every operand and output has the input's rank; dims the op does NOT act along can be split on all of them at once
+  const TensorType& x = c.nin() ? c.in(0) : c.o();
+  for (int d = 0; d < x.rank(); ++d) {
+    if (std::find(touched.begin(), touched.end(), (int64_t)d) != touched.end()) continue;
+    bool ok = c.divisible(c.o(), d);
+    for (int i = 0; i < c.nin(); ++i) ok &= c.in(i).rank() == x.rank() && c.divisible(c.in(i), d);
+    if (ok) c.add(std::vector<DS>(c.nin(), c.S(d)), std::vector<DS>(c.n.outputs.size(), c.S(d)), "dim" + std::to_string(d));
+  }
+  c.add_glue();
+}
+void ReverseRule(Ctx& c) { AxesUntouchedRule(c, c.n.attr_v("dims")); }          // a reversed dim would need a shard permutation
+void SortRule(Ctx& c) { AxesUntouchedRule(c, {c.n.attr_i("axis", -1) < 0 ? c.in(0).rank() + c.n.attr_i("axis", -1) : c.n.attr_i("axis")}); }
+void WindowRule(Ctx& c) {
+  // reduce_window (x) / select_and_scatter (x, source): a dim is local iff its window is 1 wide, stride 1 and unpadded
+  const TensorType& x = c.in(0);
+  auto win = c.n.attr_v("window"), str = c.n.attr_v("strides"), pad = c.n.attr_v("padding");
+  std::vector<int64_t> touched;
+  for (int d = 0; d < x.rank(); ++d) {
+    const int64_t w = d < (int)win.size() ? win[d] : 1, s_ = d < (int)str.size() ? str[d] : 1;
+    const int64_t p0 = 2 * d < (int)pad.size() ? pad[2 * d] : 0, p1 = 2 * d + 1 < (int)pad.size() ? pad[2 * d + 1] : 0;
+    if (w != 1 || s_ != 1 || p0 != 0 || p1 != 0) touched.push_back(d);
+  }
+  AxesUntouchedRule(c, touched);
+}
+void PadRule(Ctx& c) {
+  // general pad (low / high / interior per dim): dims that are not padded keep their split
+  const TensorType& x = c.in(0);
+  auto lo = c.n.attr_v("low"), hi = c.n.attr_v("high"), in_ = c.n.attr_v("interior");
+  for (int d = 0; d < x.rank(); ++d) {
+    const bool padded = (d < (int)lo.size() && lo[d]) || (d < (int)hi.size() && hi[d]) || (d < (int)in_.size() && in_[d]);
+    if (padded || !c.divisible(x, d) || !c.divisible(c.o(), d)) continue;
+    std::vector<DS> ins(c.nin(), c.G());    // (operand 1, when present, is the scalar padding value)
+    ins[0] = c.S(d);
+    c.add(ins, {c.S(d)}, "dim" + std::to_string(d));
+  }
+  c.add_glue();
+}
+void IotaRule(Ctx& c) {
+  // source: shards along a non-iota dim are identical copies; the iota dim itself would need a per-shard offset
+  const TensorType& o = c.o();
+  const int64_t id = c.n.attr_i("dim", 0);
+  for (int d = 0; d < o.rank(); ++d)
+    if (d != id && c.divisible(o, d)) c.add({}, {c.S(d)}, "dim" + std::to_string(d));
+  c.add_glue();
+}
+void SelectRule(Ctx& c) { Elementwise(c, false); }   // select(pred, a, b) / clamp(lo, x, hi): broadcast-aware elementwise
+void ScatterRule(Ctx& c) {
+  // scatter(operand, indices, updates) along `axis`: every other dim of operand / updates (and of equally shaped indices) is local
+  const TensorType& x = c.in(0);
+  int64_t ax = c.n.attr_i("axis", 0);
+  if (ax < 0) ax += x.rank();
+  for (int d = 0; d < x.rank(); ++d) {
+    if (d == ax || !c.divisible(x, d) || !c.divisible(c.o(), d)) continue;
+    std::vector<DS> ins = {c.S(d)};
+    bool ok = true;
+    for (int i = 1; i < c.nin(); ++i) {
+      if (c.in(i).rank() == x.rank() && c.divisible(c.in(i), d)) ins.push_back(c.S(d));
+      else ok = false;
+    }
+    if (ok) c.add(ins, {c.S(d)}, "dim" + std::to_string(d));
+  }
+  c.add_glue();
+}
+
+std::set<std::string>& UnknownOpsSeen() {
+  static std::set<std::string> s;
+  return s;
+}
+
 }  // namespace
 
 std::vector<Candidate> EnumerateCandidates(const Graph& g, const Node& n, int num, const RuleOptions& opt) {
   Ctx c{g, n, num, {}};
   const std::string& op = n.op;
   static const std::set<std::string> unary_linear = {"neg", "scale", "cast"};
-  static const std::set<std::string> unary = {"gelu", "relu", "tanh", "exp", "log"};
+  static const std::set<std::string> unary = {"gelu", "relu", "tanh", "exp", "log", "sqrt", "rsqrt", "sigmoid", "abs", "sign", "erf",
+                                               "logical_not", "floor", "ceil", "silu"};
   static const std::set<std::string> binary_linear = {"add", "sub"};
-  static const std::set<std::string> binary = {"mul", "div", "relu_bwd", "tanh_bwd", "gelu_bwd"};
+  static const std::set<std::string> binary = {"mul", "div", "relu_bwd", "tanh_bwd", "gelu_bwd", "maximum", "minimum", "pow", "compare",
+                                                "logical_and", "logical_or", "sigmoid_bwd", "silu_bwd"};
   if (IsSource(op)) SourceRule(c);
   else if (unary_linear.count(op) || binary_linear.count(op)) Elementwise(c, true);
   else if (unary.count(op) || binary.count(op)) Elementwise(c, false);
@@ -444,7 +518,17 @@ std::vector<Candidate> EnumerateCandidates(const Graph& g, const Node& n, int nu
     if (ok) c.add(std::vector<DS>(c.nin(), c.S(0)), {c.S(0)}, "group");
     c.add_glue();
   }
-  else c.add_glue();  // unknown op: replicated only (safe)
+  else if (op == "reverse") ReverseRule(c);
+  else if (op == "sort") SortRule(c);
+  else if (op == "reduce_window" || op == "select_and_scatter") WindowRule(c);
+  else if (op == "pad") PadRule(c);
+  else if (op == "iota") IotaRule(c);
+  else if (op == "select" || op == "clamp") SelectRule(c);
+  else if (op == "scatter") ScatterRule(c);
+  else {
+    UnknownOpsSeen().insert(op);   // replicated only (safe) -- but never silently: the planner reports these (SpmdStats.unknown_ops)
+    c.add_glue();
+  }
   return std::move(c.out);
 }
 
@@ -544,6 +628,62 @@ bool InferGraph(const Graph& g, int num, std::map<ValueRef, DimStrategy>* assign
       if (!visit(*it)) return false;
   }
   return true;
+}
+
+std::vector<std::string> UnknownOps(bool clear) {
+  std::vector<std::string> r(UnknownOpsSeen().begin(), UnknownOpsSeen().end());
+  if (clear) UnknownOpsSeen().clear();
+  return r;
+}
+
+// Round-trip check of the rule table on a whole graph (reference VerifyInfer, P/utils.cc:1781-1848): for every node and every
+// candidate, (1) every split divides its dimension, (2) re-deriving the candidate from any single operand layout (ForwardInfer)
+// or output layout (BackInfer) finds it again, (3) the shard shapes are what the op would produce from its shard operands for
+// the shape-preserving op families (elementwise: output shard dims == broadcast of operand shard dims).  Returns violations.
+std::vector<std::string> VerifyInfer(const Graph& g, int num) {
+  std::vector<std::string> bad;
+  RuleOptions opt;
+  opt.allow_glue_compute_intensive = true;
+  auto same = [](const Candidate& a, const Candidate& b) { return a.ins == b.ins && a.outs == b.outs; };
+  for (const auto& n : g.nodes) {
+    auto cands = EnumerateCandidates(g, n, num, opt);
+    if (cands.empty()) bad.push_back(n.op + " '" + n.name + "': no candidate at all");
+    for (const auto& c : cands) {
+      if (c.ins.size() != n.inputs.size() || c.outs.size() != n.outputs.size()) {
+        bad.push_back(n.op + " '" + n.name + "' [" + c.tag + "]: arity mismatch");
+        continue;
+      }
+      for (size_t i = 0; i < c.ins.size(); ++i) {
+        if (c.ins[i].is_split() && !c.ins[i].Valid(g.type(n.inputs[i])))
+          bad.push_back(n.op + " '" + n.name + "' [" + c.tag + "]: operand " + std::to_string(i) + " split does not divide");
+        bool found = false;
+        for (const auto& f : ForwardInfer(g, n, num, (int)i, c.ins[i])) found |= same(f, c);
+        if (!found) bad.push_back(n.op + " '" + n.name + "' [" + c.tag + "]: forward round trip from operand " + std::to_string(i) + " lost it");
+      }
+      for (size_t j = 0; j < c.outs.size(); ++j) {
+        if (c.outs[j].is_split() && !c.outs[j].Valid(n.outputs[j]))
+          bad.push_back(n.op + " '" + n.name + "' [" + c.tag + "]: output " + std::to_string(j) + " split does not divide");
+        bool found = false;
+        for (const auto& f : BackInfer(g, n, num, (int)j, c.outs[j])) found |= same(f, c);
+        if (!found) bad.push_back(n.op + " '" + n.name + "' [" + c.tag + "]: backward round trip from output " + std::to_string(j) + " lost it");
+      }
+      // shape algebra for elementwise families: out shard dim == max over operand shard dims (right-aligned broadcasting)
+      static const std::set<std::string> ew = {"add", "sub", "mul", "div", "neg", "scale", "cast", "gelu", "relu", "tanh", "exp", "log",
+                                               "maximum", "minimum", "select", "clamp", "sqrt", "rsqrt", "sigmoid", "abs"};
+      if (ew.count(n.op) && !c.outs.empty() && !c.outs[0].partial) {
+        TensorType so = ShardType(n.outputs[0], c.outs[0]);
+        for (size_t i = 0; i < c.ins.size(); ++i) {
+          if (c.ins[i].partial) continue;
+          TensorType si = ShardType(g.type(n.inputs[i]), c.ins[i]);
+          const int off = so.rank() - si.rank();
+          for (int d = 0; d < si.rank(); ++d)
+            if (si.dims[d] != 1 && si.dims[d] != so.dims[d + off])
+              bad.push_back(n.op + " '" + n.name + "' [" + c.tag + "]: shard shapes of operand " + std::to_string(i) + " and output disagree");
+        }
+      }
+    }
+  }
+  return bad;
 }
 
 }  // namespace tepdist

@@ -40,4 +40,10 @@ TensorType ShardType(const TensorType& t, const DimStrategy& s);
 // backward sweeps; returns false on conflict.  `assign` maps value -> strategy (absent = undecided).
 bool InferGraph(const Graph& g, int num, std::map<ValueRef, DimStrategy>* assign, std::string* conflict = nullptr);
 
+// Ops that hit the "replicate everything" fallback since the last call (the planner surfaces them as a warning).
+std::vector<std::string> UnknownOps(bool clear = true);
+
+// Round-trip / shape-algebra check of the rule table over every node of `g` (reference VerifyInfer); returns the violations.
+std::vector<std::string> VerifyInfer(const Graph& g, int num);
+
 }  // namespace tepdist

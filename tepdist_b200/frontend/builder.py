@@ -139,6 +139,40 @@ class GraphBuilder:
     def scale(self, x, alpha: float, name="scale"): return self._ew("scale", [x], name, {"alpha": alpha})
     def cast(self, x, dtype: str, name="cast"): return self._ew("cast", [x], name, {"dtype": dtype}, dtype)
 
+    # ---- further elementwise / structural ops (traced torch graphs bring them along; rules: csrc/rules.cc)
+    def sqrt(self, x, name="sqrt"): return self._ew("sqrt", [x], name)
+    def rsqrt(self, x, name="rsqrt"): return self._ew("rsqrt", [x], name)
+    def sigmoid(self, x, name="sigmoid"): return self._ew("sigmoid", [x], name)
+    def abs(self, x, name="abs"): return self._ew("abs", [x], name)
+    def maximum(self, x, y, name="maximum"): return self._ew("maximum", [x, y], name)
+    def minimum(self, x, y, name="minimum"): return self._ew("minimum", [x, y], name)
+    def compare(self, x, y, direction: str = "gt", name="compare"): return self._ew("compare", [x, y], name, {"direction": direction}, "bool")
+
+    def select(self, pred: Value, a: Value, b_: Value, name="select") -> Value:
+        shape = max((self.t(v).shape for v in (pred, a, b_)), key=numel)
+        return self._n("select", [pred, a, b_], [TensorType(shape, self.t(a).dtype)], {}, name).out()
+
+    def reverse(self, x: Value, dims: Sequence[int], name="reverse") -> Value:
+        return self._n("reverse", [x], [self.t(x)], {"dims": [d % len(self.t(x).shape) for d in dims]}, name).out()
+
+    def sort(self, x: Value, axis: int = -1, descending: bool = False, name="sort") -> Value:
+        return self._n("sort", [x], [self.t(x)], {"axis": axis % len(self.t(x).shape), "descending": descending}, name).out()
+
+    def iota(self, shape: Sequence[int], dim: int, dtype: str = "i32", name="iota") -> Value:
+        return self._n("iota", [], [TensorType(tuple(shape), dtype)], {"dim": dim}, name).out()
+
+    def pad(self, x: Value, low: Sequence[int], high: Sequence[int], value: float = 0.0, name="pad") -> Value:
+        s = self.t(x).shape
+        out = tuple(d + lo + hi for d, lo, hi in zip(s, low, high))
+        return self._n("pad", [x], [TensorType(out, self.t(x).dtype)], {"low": list(low), "high": list(high), "value": value}, name).out()
+
+    def reduce_window(self, x: Value, window: Sequence[int], strides: Sequence[int], kind: str = "max", name="reduce_window") -> Value:
+        """Unpadded window reduction over an N-d tensor (window / stride 1 on the dims it does not act along)."""
+        s = self.t(x).shape
+        out = tuple((d - w) // st + 1 for d, w, st in zip(s, window, strides))
+        return self._n("reduce_window", [x], [TensorType(out, self.t(x).dtype)],
+                       {"window": list(window), "strides": list(strides), "padding": [0] * (2 * len(s)), "kind": kind}, name).out()
+
     def softmax(self, x: Value, axis: int = -1, name="softmax") -> Value:
         return self._n("softmax", [x], [self.t(x)], {"axis": axis % len(self.t(x).shape)}, name).out()
 
@@ -430,7 +464,39 @@ def backward(b: GraphBuilder, loss: Value) -> Dict[int, Value]:
         elif n.op == "moe_dispatch_mask":
             gts = n.inputs[0]
             push(gts, B("moe_dispatch_mask_bwd", [dy, gts], [T(gts)], dict(n.attrs), grp).out())
-        elif n.op in ("one_hot", "reduce_max"):
+        elif n.op == "sqrt":       # d sqrt(x) = dy / (2 y)
+            half = B("scale", [dy], [T(dy)], {"alpha": 0.5}, grp).out()
+            push(n.inputs[0], B("div", [half, Value(n.id, 0)], [T(dy)], {}, grp).out())
+        elif n.op == "rsqrt":      # d x^-1/2 = -1/2 y^3 dy
+            y2 = B("mul", [Value(n.id, 0), Value(n.id, 0)], [T(dy)], {}, grp).out()
+            y3 = B("mul", [y2, Value(n.id, 0)], [T(dy)], {}, grp).out()
+            push(n.inputs[0], B("scale", [B("mul", [dy, y3], [T(dy)], {}, grp).out()], [T(dy)], {"alpha": -0.5}, grp).out())
+        elif n.op == "sigmoid":
+            push(n.inputs[0], B("sigmoid_bwd", [dy, Value(n.id, 0)], [T(dy)], {}, grp).out())
+        elif n.op == "abs":
+            push(n.inputs[0], B("mul", [dy, B("sign", [n.inputs[0]], [T(dy)], {}, grp).out()], [T(dy)], {}, grp).out())
+        elif n.op in ("maximum", "minimum"):
+            x, y = n.inputs
+            take_x = B("compare", [x, y], [TensorType(T(dy).shape, "bool")], {"direction": "ge" if n.op == "maximum" else "le"}, grp).out()
+            zero = B("constant", [], [TensorType((), T(dy).dtype)], {"value": 0.0}, grp).out()
+            push(x, _unbroadcast(b, B("select", [take_x, dy, zero], [T(dy)], {}, grp).out(), T(x).shape, grp))
+            push(y, _unbroadcast(b, B("select", [take_x, zero, dy], [T(dy)], {}, grp).out(), T(y).shape, grp))
+        elif n.op == "select":
+            pred, x, y = n.inputs
+            zero = B("constant", [], [TensorType((), T(dy).dtype)], {"value": 0.0}, grp).out()
+            push(x, _unbroadcast(b, B("select", [pred, dy, zero], [T(dy)], {}, grp).out(), T(x).shape, grp))
+            push(y, _unbroadcast(b, B("select", [pred, zero, dy], [T(dy)], {}, grp).out(), T(y).shape, grp))
+        elif n.op == "reverse":
+            push(n.inputs[0], B("reverse", [dy], [T(dy)], {"dims": n.attrs["dims"]}, grp).out())
+        elif n.op == "pad":
+            x = n.inputs[0]
+            lo = n.attrs["low"]
+            lim = [l + d for l, d in zip(lo, T(x).shape)]
+            push(x, B("slice", [dy], [TensorType(T(x).shape, T(dy).dtype)], {"starts": list(lo), "limits": lim}, grp).out())
+        elif n.op == "reduce_window":
+            x = n.inputs[0]
+            push(x, B("select_and_scatter", [x, dy], [T(x)], dict(n.attrs), grp).out())
+        elif n.op in ("one_hot", "reduce_max", "compare", "iota", "sort", "sign"):
             pass
         else:
             raise NotImplementedError(f"no vjp for op '{n.op}'")

@@ -32,7 +32,11 @@ constexpr int B_BYTES = (BN / 2) * BK * 2;  // 16 KB (this CTA's half of B)
 constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
 constexpr int STAGES = 6;
 constexpr int TMEM_COLS = 2 * BN;           // double-buffered accumulator
-constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 + 256;
+// TMA-store epilogue: every epilogue warp owns two 4 KB staging buffers (32 rows x 128 B, SWIZZLE_128B) that it fills with
+// conflict-free 16-byte shared stores and hands to the TMA unit (cp.async.bulk.tensor ... global.shared::cta); the global
+// writes are then full 128-byte lines issued by the copy engine instead of 32-way scattered 16-byte stores from the LSU.
+constexpr int OUT_STAGE_BYTES = 4 * 2 * 4096;
+constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + OUT_STAGE_BYTES + 1024 + 256;
 
 struct Gemm2Params {
   int M, N, K;
@@ -160,12 +164,16 @@ __device__ __forceinline__ float gelu_grad_f(float x) {
 // F32 = fp32 plain-store epilogue (weight gradients) instead of the bf16 epilogues; SK = stream-K schedule.  Both are
 // compile-time: carrying the stream-K / fp32 branches in the bf16 tile-parallel kernel cost 5 % of the GPT-2 step
 // (154 vs 93 registers, trip 24 / 25 A/B), so every combination that is used gets its own lean instantiation.
-template <bool A_MN, bool B_MN, bool F32, bool SK>
+// TS = TMA-store epilogue (tile-parallel schedule only; tmap_d / tmap_d2 describe D / D2 with a [32 rows x 128 B] box).
+template <bool A_MN, bool B_MN, bool F32, bool SK, bool TS>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1)
-gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b, const Gemm2Params p) {
+gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b, const Gemm2Params p,
+                  const __grid_constant__ CUtensorMap tmap_d, const __grid_constant__ CUtensorMap tmap_d2) {
+  static_assert(!(TS && SK), "the TMA-store epilogue is only wired for the tile-parallel schedule");
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);
+  uint8_t* out_stage = smem + STAGES * STAGE_BYTES;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES + OUT_STAGE_BYTES);
   uint64_t* empty_bar = full_bar + STAGES;
   uint64_t* tmem_full = empty_bar + STAGES;
   uint64_t* tmem_empty = tmem_full + 2;
@@ -178,6 +186,7 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmap_a);
     tma_prefetch_desc(&tmap_b);
+    if constexpr (TS) tma_prefetch_desc(&tmap_d);
     for (int s = 0; s < STAGES; ++s) {
       mbar_init(&full_bar[s], 1);    // leader's copy is the live one: one arrive.expect_tx + 2 CTAs' TMA bytes
       mbar_init(&empty_bar[s], 1);   // one multicast commit per phase
@@ -311,6 +320,125 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
       const int row = m_pair * 2 * BM + cta * BM + quarter * 32 + lane;
       const bool row_ok = row < p.M;
       const uint32_t t_row = tmem_base + (uint32_t(quarter * 32) << 16) + acc * BN;
+      if constexpr (TS) {
+        uint8_t* my_stage = out_stage + quarter * 8192;           // two 4 KB buffers of this warp
+        const int row_base = m_pair * 2 * BM + cta * BM + quarter * 32;
+        const bool dual = !F32 && p.act == 1 && p.D2 != nullptr;
+        const uint32_t sw = (uint32_t)(lane & 7);                 // SWIZZLE_128B: 16-byte chunk index ^= row & 7
+#pragma unroll 1
+        for (int c = 0; c < BN / 32; ++c) {
+          uint32_t r[32];
+          tmem_ld_32x32(t_row + c * 32, r);
+          tmem_ld_wait();
+          const int col0 = n_blk * BN + c * 32;
+          if (col0 >= p.N) break;                                 // (warp-uniform) whole chunk beyond the matrix
+          float v[32];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]) * p.alpha;
+          if constexpr (F32) {
+            // fp32 output (weight gradients): one chunk = 32 floats = one 128-byte row segment; buffers alternate per chunk
+            uint8_t* buf = my_stage + (c & 1) * 4096;
+            if (lane == 0) tma_store_wait_read<1>();
+            __syncwarp();
+            uint4* rowp = reinterpret_cast<uint4*>(buf + lane * 128);
+#pragma unroll
+            for (int q = 0; q < 8; ++q)
+              rowp[q ^ sw] = make_uint4(__float_as_uint(v[q * 4]), __float_as_uint(v[q * 4 + 1]), __float_as_uint(v[q * 4 + 2]),
+                                        __float_as_uint(v[q * 4 + 3]));
+            fence_proxy_async();
+            __syncwarp();
+            if (lane == 0) {
+              tma_store_3d(&tmap_d, buf, col0, row_base, 0);
+              tma_store_commit();
+            }
+            continue;
+          }
+          if (p.bias != nullptr) {
+            if (p.bias_bf16) {
+              const __nv_bfloat16* bp = reinterpret_cast<const __nv_bfloat16*>(p.bias) + col0;
+#pragma unroll
+              for (int j = 0; j < 32; ++j) if (col0 + j < p.N) v[j] += __bfloat162float(bp[j]);
+            } else {
+              const float* bp = reinterpret_cast<const float*>(p.bias) + col0;
+#pragma unroll
+              for (int j = 0; j < 32; ++j) if (col0 + j < p.N) v[j] += __ldg(bp + j);
+            }
+          }
+          const int half = c & 1, slab = c >> 1;                  // a 64-column slab = two chunks = one 128-byte bf16 row
+          if (half == 0) {                                        // about to overwrite a staging buffer: its last TMA store
+            if (lane == 0) {                                      // must have finished READING it
+              if (dual) tma_store_wait_read<0>(); else tma_store_wait_read<1>();
+            }
+            __syncwarp();
+          }
+          uint8_t* buf_main = my_stage + (dual ? 4096 : (slab & 1) * 4096);
+          auto stage_row = [&](uint8_t* buf) {
+            uint4* rowp = reinterpret_cast<uint4*>(buf + lane * 128);
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              uint4 u;
+              u.x = pack_bf16x2(v[q * 8 + 0], v[q * 8 + 1]);
+              u.y = pack_bf16x2(v[q * 8 + 2], v[q * 8 + 3]);
+              u.z = pack_bf16x2(v[q * 8 + 4], v[q * 8 + 5]);
+              u.w = pack_bf16x2(v[q * 8 + 6], v[q * 8 + 7]);
+              rowp[(uint32_t)(half * 4 + q) ^ sw] = u;
+            }
+          };
+          const long long off = (long long)row * p.ldd + col0;
+          if (p.act == 1) {
+            if (dual) stage_row(my_stage);                        // pre-activation (saved for backward) -> D
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = gelu_f(v[j]);
+          } else if (p.act == 2) {
+            if (row_ok) {
+              const uint4* ap = reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(p.aux) + off);
+#pragma unroll
+              for (int q = 0; q < 4; ++q)
+                if (col0 + q * 8 < p.N) {
+                  uint4 u = __ldg(ap + q);
+                  const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
+#pragma unroll
+                  for (int e = 0; e < 4; ++e) {
+                    float2 f = __bfloat1622float2(h[e]);
+                    v[q * 8 + e * 2] *= gelu_grad_f(f.x);
+                    v[q * 8 + e * 2 + 1] *= gelu_grad_f(f.y);
+                  }
+                }
+            }
+          }
+          if (p.residual != nullptr && row_ok) {
+            const uint4* rp = reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(p.residual) +
+                                                             (long long)row * p.ld_res + col0);
+#pragma unroll
+            for (int q = 0; q < 4; ++q)
+              if (col0 + q * 8 < p.N) {
+                uint4 u = __ldg(rp + q);
+                const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                  float2 f = __bfloat1622float2(h[e]);
+                  v[q * 8 + e * 2] += f.x;
+                  v[q * 8 + e * 2 + 1] += f.y;
+                }
+              }
+          }
+          stage_row(buf_main);
+          if (half == 1 || col0 + 32 >= p.N) {                    // slab complete (or the matrix ends inside it)
+            fence_proxy_async();
+            __syncwarp();
+            if (lane == 0) {
+              const int scol = n_blk * BN + slab * 64;
+              if (dual) {
+                tma_store_3d(&tmap_d, my_stage, scol, row_base, 0);
+                tma_store_3d(&tmap_d2, buf_main, scol, row_base, 0);
+              } else {
+                tma_store_3d(p.act == 1 && p.D2 != nullptr ? &tmap_d2 : &tmap_d, buf_main, scol, row_base, 0);
+              }
+              tma_store_commit();
+            }
+          }
+        }
+      } else {
 #pragma unroll 1
       for (int c = 0; c < BN / 32; ++c) {
         uint32_t r[32];
@@ -409,6 +537,7 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
           store(p.D2 != nullptr && p.act == 1 ? p.D2 : p.D);
         }
       }
+      }   // !TS
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive_cluster(mapa_rank(smem_u32(&tmem_empty[acc]), 0));   // always the leader's barrier
@@ -425,6 +554,9 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
       }
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
+    if constexpr (TS) {
+      if (lane == 0) tma_store_wait<0>();      // every bulk store of this warp has been written out
+    }
   }
 
   tc_fence_before();
@@ -439,6 +571,17 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
 
 extern "C" int tepd_make_tmap_bf16_3d(CUtensorMap* out, const void* ptr, long long inner, long long rows, long long batch,
                                       long long ld_elems, long long batch_stride_elems, int box_inner, int box_rows);
+extern "C" int tepd_make_tmap_3d(CUtensorMap* out, const void* ptr, int dtype, long long inner, long long rows, long long batch,
+                                 long long ld_elems, long long batch_stride_elems, int box_inner, int box_rows, int swizzle128);
+
+static bool gemm2_tma_store_enabled() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("TEPDIST_GEMM2_TMA_STORE");
+    v = (e && e[0] == '0') ? 0 : 1;
+  }
+  return v == 1;
+}
 
 // D[M,N] = epilogue(alpha * A @ B): A = [M,K] (a_mn=0) or [K,M] (a_mn=1); B = [N,K] (b_mn=0) or [K,N] (b_mn=1); bf16 in;
 // bf16 out with epilogues, or fp32 plain stores (out_fp32).  stream_k != 0 selects the stream-K schedule.
@@ -490,22 +633,36 @@ extern "C" int tepd_gemm2_bf16(const void* A, const void* B, void* D, void* D2, 
     clusters = (int)((iters + per - 1) / per);
   }
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
-#define LAUNCH2(AM, BMN, F, SKK)                                                                                                \
+  const bool sk = p.stream_k > 0;
+  // TMA-store epilogue: output row pitch must be a multiple of 16 bytes and the base 16-byte aligned (always true for the
+  // contiguous activations / flat gradient slots this is called with); stream-K keeps the register epilogue
+  const long long esz = out_fp32 ? 4 : 2;
+  const bool ts = !sk && gemm2_tma_store_enabled() && ((ldd * esz) % 16 == 0) && (((uintptr_t)D & 15) == 0) &&
+                  (D2 == nullptr || ((uintptr_t)D2 & 15) == 0);
+  CUtensorMap td = ta, td2 = ta;
+  if (ts) {
+    rc = tepd_make_tmap_3d(&td, D, out_fp32 ? 1 : 0, N, M, 1, ldd, 0, out_fp32 ? 32 : 64, 32, 1);
+    if (rc) return 300 + rc;
+    if (D2 != nullptr) {
+      rc = tepd_make_tmap_3d(&td2, D2, 0, N, M, 1, ldd, 0, 64, 32, 1);
+      if (rc) return 400 + rc;
+    }
+  }
+#define LAUNCH2(AM, BMN, F, SKK, TSS)                                                                                           \
   {                                                                                                                             \
     static bool cfg = false;                                                                                                    \
-    auto kern = gemm2_bf16_kernel<AM, BMN, F, SKK>;                                                                                     \
+    auto kern = gemm2_bf16_kernel<AM, BMN, F, SKK, TSS>;                                                                        \
     if (!cfg) {                                                                                                                 \
       if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES) != cudaSuccess) return -6;        \
       cfg = true;                                                                                                               \
     }                                                                                                                           \
-    cudaError_t le = tepd::launch(kern, dim3(2 * clusters), dim3(THREADS), SMEM_BYTES, s, ta, tb, p);                           \
+    cudaError_t le = tepd::launch(kern, dim3(2 * clusters), dim3(THREADS), SMEM_BYTES, s, ta, tb, p, td, td2);                  \
     if (le != cudaSuccess) return (int)le;                                                                                      \
   }
-  const bool sk = p.stream_k > 0;
 #define PICK2(AM, BMN)                                                                   \
   {                                                                                      \
-    if (out_fp32) { if (sk) LAUNCH2(AM, BMN, true, true) else LAUNCH2(AM, BMN, true, false) }   \
-    else          { if (sk) LAUNCH2(AM, BMN, false, true) else LAUNCH2(AM, BMN, false, false) } \
+    if (out_fp32) { if (sk) LAUNCH2(AM, BMN, true, true, false) else if (ts) LAUNCH2(AM, BMN, true, false, true) else LAUNCH2(AM, BMN, true, false, false) }   \
+    else          { if (sk) LAUNCH2(AM, BMN, false, true, false) else if (ts) LAUNCH2(AM, BMN, false, false, true) else LAUNCH2(AM, BMN, false, false, false) } \
   }
   if (a_mn) PICK2(true, true)
   else if (b_mn) PICK2(false, true)

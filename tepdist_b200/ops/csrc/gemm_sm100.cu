@@ -559,6 +559,24 @@ extern "C" int tepd_make_tmap_bf16_3d(CUtensorMap* out, const void* ptr, long lo
   return r == CUDA_SUCCESS ? 0 : (int)r;
 }
 
+// Generic 3-D tensor map (any element type / box / swizzle): used for the TMA-store epilogues.
+//   dtype: 0 = bf16, 1 = fp32;  swizzle128: 1 = SWIZZLE_128B (box_inner * elem size must be 128 B), 0 = none
+extern "C" int tepd_make_tmap_3d(CUtensorMap* out, const void* ptr, int dtype, long long inner, long long rows, long long batch,
+                                 long long ld_elems, long long batch_stride_elems, int box_inner, int box_rows, int swizzle128) {
+  EncodeTiledFn fn = get_encode_fn();
+  if (!fn) return -1;
+  const cuuint64_t es = dtype == 1 ? 4 : 2;
+  cuuint64_t dims[3] = {(cuuint64_t)inner, (cuuint64_t)rows, (cuuint64_t)batch};
+  cuuint64_t strides[2] = {(cuuint64_t)ld_elems * es, (cuuint64_t)(batch > 1 ? batch_stride_elems : rows * ld_elems) * es};
+  cuuint32_t box[3] = {(cuuint32_t)box_inner, (cuuint32_t)box_rows, 1};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = fn(out, dtype == 1 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(ptr),
+                  dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                  swizzle128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? 0 : (int)r;
+}
+
 template <int BLOCK_N, bool A_MN, bool B_MN>
 static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, int num_sms,
                        cudaStream_t stream) {

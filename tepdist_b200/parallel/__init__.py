@@ -38,7 +38,13 @@ def plan_spmd(graph: Graph, num: int, strategy: str = "auto", options: Optional[
             setattr(o, k, v)
     # "dp" / "rule": annotation-driven rule mode (reference FastSpmdStrategy, RULE_MODE=true): the batch split on the
     # sample inputs is propagated through the graph, variables stay replicated, gradients come out partial.
+    _C.unknown_ops(True)
     plan = _C.plan_spmd_by_rules(cg, o) if strategy in ("rule", "dp") else _C.plan_spmd_level(cg, o)
+    unknown = list(_C.unknown_ops(True))
+    if unknown:
+        import warnings
+        warnings.warn(f"SPMD planner: no sharding rule for op(s) {sorted(unknown)}: they (and what only they connect) stay replicated; "
+                      "add a rule to csrc/rules.cc to let the planner shard through them")
     if getattr(plan.stats, "ignored_annotations", 0):
         import warnings
         warnings.warn(f"SPMD planner: {plan.stats.ignored_annotations} sharding annotation(s) cannot be honoured by any strategy of "
@@ -68,7 +74,7 @@ def plan_spmd(graph: Graph, num: int, strategy: str = "auto", options: Optional[
     info = {"comm_info": st.comm_info(), "comm_bytes": plan.stats.comm_bytes, "solve_seconds": plan.stats.solve_seconds,
             "subgraphs": plan.stats.num_subgraphs, "distinct_subgraphs": plan.stats.distinct_subgraphs,
             "collectives": dict(plan.stats.collectives), "dot_strategies": tags, "grad_buckets": buckets, "infeasible_subgraphs": plan.stats.infeasible_subgraphs,
-            "strategies_txt": _C.dump_strategies(cg, plan)}
+            "strategies_txt": _C.dump_strategies(cg, plan), "unknown_ops": sorted(unknown)}
     return out, info
 
 

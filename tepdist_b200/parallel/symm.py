@@ -292,14 +292,17 @@ class FusedShardedOptimizer:
     Multicast-bound buffers (backend 'vmm'): the NVLS kernel -- the gradient chunk arrives already summed by the switch
     (`multimem.ld_reduce`, one load per 16 bytes instead of n-1 peer loads) and the updated bf16 shard leaves the GPU once
     (`multimem.st`, replicated by the switch instead of n-1 peer stores); barriers are one `multimem.red` per rank with a
-    bounded spin.  Otherwise (IPC mappings, or TEPDIST_DP_MC=0): unicast P2P loads / stores."""
+    bounded spin.  Opt-in (TEPDIST_DP_MC=1): measured on 4 x B200 the fp32 switch reduction is SLOWER than unicast peer loads for
+    this kernel (8M parameters: 122 us vs 74 us; GPT-2 345M dp4 step 20.1 vs 17.5 ms) -- a reduce-scatter through the switch
+    still costs every GPU its full gradient buffer in egress, so NVLS only pays for the all-gather half; with a bf16 gradient
+    wire it is 55 us.  Default: unicast P2P loads / stores (IPC or VMM mappings alike)."""
 
     def __init__(self, grad_buf: SymmetricBuffer, param_buf: SymmetricBuffer, group=None):
         import os
         self.g, self.p = grad_buf, param_buf
         self.world, self.rank = grad_buf.world, grad_buf.rank
         self.mc: Optional[McContext] = None
-        if (grad_buf.mc_ptr is not None and param_buf.mc_ptr is not None and os.environ.get("TEPDIST_DP_MC", "1") == "1"):
+        if (grad_buf.mc_ptr is not None and param_buf.mc_ptr is not None and os.environ.get("TEPDIST_DP_MC", "0") == "1"):
             self.mc = McContext(group)
             self._barrier = None
         else:

@@ -1194,6 +1194,10 @@ class Executor:
             t = feeds[n.name]
             if t.device != dev:
                 t = t.to(dev, non_blocking=True)
+            if t.is_floating_point():          # a float batch fed in another precision than the plan declares (fp32 loader, bf16 model)
+                wdt = torch_dtype(n.outputs[0].dtype, dev)
+                if wdt.is_floating_point and t.dtype != wdt:
+                    t = t.to(wdt)
             want = tuple(n.outputs[0].shape)
             if tuple(t.shape) != want:
                 full = tuple(a.get("full_shape", want))
@@ -1337,6 +1341,51 @@ class Executor:
         if op == "relu_bwd": return [ins[0] * (ins[1] > 0).to(ins[0].dtype)]
         if op == "tanh_bwd": return [ins[0] * (1 - ins[1] * ins[1])]
         if op == "scale": return [x * a["alpha"]]
+        if op == "sqrt": return [x.sqrt()]
+        if op == "rsqrt": return [x.rsqrt()]
+        if op == "sigmoid": return [x.sigmoid()]
+        if op == "sigmoid_bwd": return [ins[0] * ins[1] * (1 - ins[1])]
+        if op == "abs": return [x.abs()]
+        if op == "sign": return [x.sign()]
+        if op == "maximum": return [torch.maximum(ins[0], ins[1])]
+        if op == "minimum": return [torch.minimum(ins[0], ins[1])]
+        if op == "compare":
+            fn = {"gt": torch.gt, "ge": torch.ge, "lt": torch.lt, "le": torch.le, "eq": torch.eq, "ne": torch.ne}[a.get("direction", "gt")]
+            return [fn(ins[0], ins[1])]
+        if op == "select": return [torch.where(ins[0].bool(), ins[1], ins[2])]
+        if op == "clamp": return [torch.minimum(torch.maximum(ins[1], ins[0]), ins[2])]
+        if op == "reverse": return [torch.flip(x, list(a["dims"]))]
+        if op == "sort": return [torch.sort(x, dim=int(a["axis"]), descending=bool(a.get("descending", False))).values]
+        if op == "iota":
+            shp = tuple(n.outputs[0].shape)
+            d = int(a.get("dim", 0))
+            view = [1] * len(shp)
+            view[d] = shp[d]
+            r = torch.arange(shp[d], device=self.device, dtype=torch_dtype(n.outputs[0].dtype, self.device))
+            return [r.view(view).expand(shp).contiguous()]
+        if op == "pad":
+            lo, hi = list(a["low"]), list(a["high"])
+            spec = []
+            for l, h in zip(reversed(lo), reversed(hi)):
+                spec += [int(l), int(h)]
+            return [F.pad(x, spec, value=float(a.get("value", 0.0)))]
+        if op in ("reduce_window", "select_and_scatter"):
+            # window reduction over the dims with window > 1 (max or sum); backward re-runs it under autograd on the saved input
+            def fwd(t):
+                y = t
+                for d, (w, st) in enumerate(zip(a["window"], a["strides"])):
+                    if w == 1 and st == 1:
+                        continue
+                    u = y.unfold(d, int(w), int(st))
+                    y = u.amax(-1) if a.get("kind", "max") == "max" else u.sum(-1)
+                return y
+            if op == "reduce_window":
+                return [fwd(x.float()).to(x.dtype)]
+            xin = ins[0].detach().float().requires_grad_(True)
+            with torch.enable_grad():
+                y = fwd(xin)
+            (gx,) = torch.autograd.grad(y, xin, ins[1].float().reshape(y.shape))
+            return [gx.to(ins[0].dtype)]
         if op == "cast": return [x.to(torch_dtype(a["dtype"], self.device))]
         if op == "softmax": return [torch.softmax(x.float(), a["axis"]).to(x.dtype)]
         if op == "softmax_bwd":

@@ -539,3 +539,111 @@ def test_no_sub_graph_is_left_without_a_consistent_assignment():
         kw = {} if lim is None else {"var_mem_limit": lim}
         _, plan = _plan(g, num, **kw)
         assert plan.stats.infeasible_subgraphs == 0, (name, num, lim, plan.stats.num_subgraphs)
+
+
+# ------------------------------------------------------------------------------------------------ rule-table breadth + VerifyInfer
+def _aux_ops_graph():
+    """One graph through the op families added for traced torch graphs: pad / reverse / reduce-window / sort / iota / select /
+    maximum / sqrt / sigmoid, ending in a trainable linear (so the backward exists: slice, reverse, select-and-scatter ...)."""
+    from tepdist_b200.frontend.builder import GraphBuilder, build_training_step
+    b = GraphBuilder("aux_ops", compute_dtype="f32")
+    x = b.input("x", (8, 16, 32), "f32")
+    w = b.parameter("w", (32, 32), {"kind": "normal", "mean": 0.0, "std": 0.1}, compute_dtype="f32")
+    h = b.linear(x, w, name="lin")                                   # [8, 16, 32]
+    h = b.pad(h, (0, 2, 0), (0, 2, 0), name="pad_seq")                # [8, 20, 32]
+    h = b.reverse(h, [1], name="flip_seq")
+    h = b.reduce_window(h, (1, 2, 1), (1, 2, 1), kind="max", name="pool_seq")   # [8, 10, 32]
+    h = b.maximum(h, b.scale(h, 0.1), name="leaky")
+    h = b.sigmoid(h)
+    pos = b.cast(b.iota((8, 10, 32), 1, "i32"), "f32")
+    h = b.select(b.compare(pos, b.constant(4.5, (), "f32"), "lt"), h, b.sqrt(b.abs(h)), name="sel")
+    s = b.sort(h, axis=2, name="sorted")
+    d = b.sub(h, b.scale(s, 0.0))
+    loss = b.reduce_mean(b.mul(d, d), [0, 1, 2], name="loss")
+    return build_training_step(b, loss, "sgd", lr=0.1)
+
+
+def test_new_rules_keep_the_batch_split_through_pad_reverse_window_sort_select():
+    from tepdist_b200 import _C
+    from tepdist_b200.parallel import plan_spmd
+    from tepdist_b200.planner import to_native
+    g = _aux_ops_graph()
+    assert _C.verify_infer(to_native(g), 2) == []
+    import warnings
+    with warnings.catch_warnings():
+        warnings.simplefilter("error")            # an unknown-op warning would fail the test
+        g2, info = plan_spmd(g, 2, "dp")
+    assert info["unknown_ops"] == []
+    by_name = {n.name: n for n in g2.nodes}
+    for nm in ("pad_seq", "flip_seq", "pool_seq", "leaky", "sel", "sorted"):
+        assert tuple(by_name[nm].outputs[0].shape)[0] == 4, (nm, by_name[nm].outputs[0].shape)   # batch 8 split over 2 devices
+    # golden: the only communication of the data-parallel plan is the gradient reduction of `w` (+ the loss)
+    assert set(info["collectives"]) <= {"all_reduce", "reduce_scatter", "all_gather"}, info["collectives"]
+
+
+def test_split_never_lands_on_a_dim_the_op_acts_along():
+    from tepdist_b200 import _C
+    from tepdist_b200.frontend.builder import GraphBuilder
+    from tepdist_b200.planner import to_native
+    b = GraphBuilder("t", compute_dtype="f32")
+    x = b.input("x", (4, 8, 6), "f32")
+    ops_ = {"pad": b.pad(x, (0, 1, 0), (0, 1, 0)), "reverse": b.reverse(x, [2]), "sort": b.sort(x, axis=1),
+            "reduce_window": b.reduce_window(x, (1, 2, 1), (1, 2, 1)), "iota": b.iota((4, 8, 6), 0)}
+    g = b.g
+    cg = to_native(g)
+    banned = {"pad": 1, "reverse": 2, "sort": 1, "reduce_window": 1, "iota": 0}
+    for name, v in ops_.items():
+        cands = _C.enumerate_candidates(cg, v.node, 2)
+        dims = {c.outs[0].dim for c in cands if c.outs[0].dim >= 0}
+        assert banned[name] not in dims and dims, (name, dims)
+
+
+def test_unknown_op_is_reported_not_silently_replicated():
+    import warnings
+    from tepdist_b200.frontend.builder import GraphBuilder, build_training_step
+    from tepdist_b200.parallel import plan_spmd
+    b = GraphBuilder("u", compute_dtype="f32")
+    x = b.input("x", (8, 16), "f32")
+    w = b.parameter("w", (16, 16), {"kind": "normal", "mean": 0.0, "std": 0.1}, compute_dtype="f32")
+    h = b.linear(x, w)
+    h = b._ew("my_custom_op", [h], "custom")       # no rule, no vjp needed below it
+    g = b.g
+    g.outputs.append(h)
+    with warnings.catch_warnings(record=True) as rec:
+        warnings.simplefilter("always")
+        _, info = plan_spmd(g, 2, "auto")
+    assert info["unknown_ops"] == ["my_custom_op"]
+    assert any("my_custom_op" in str(r.message) for r in rec)
+
+
+def test_verify_infer_is_clean_on_every_model_family():
+    from tepdist_b200 import _C
+    from tepdist_b200.models.gpt2 import CONFIGS, build_gpt2_graph
+    from tepdist_b200.models.gpt_moe import build_moe_ffn_graph
+    from tepdist_b200.models.wide_resnet import WideResNetConfig, build_wide_resnet_graph
+    from tepdist_b200.planner import to_native
+    graphs = [build_gpt2_graph(CONFIGS["tiny"], batch=4), build_moe_ffn_graph(groups=4, tokens_per_group=32, model=32, hidden=64, experts=4, capacity=16)]
+    graphs.append(build_wide_resnet_graph(WideResNetConfig(model_type=0, batch=4, image=32, classes=10)))
+    for g in graphs:
+        for num in (2, 4):
+            assert _C.verify_infer(to_native(g), num) == [], g.name
+
+
+def test_aux_op_family_executes_and_trains():
+    """The executor runs every op of the new family (forward and the vjps the builder emits) and SGD reduces the loss; the
+    value of the first loss matches the same computation written in torch."""
+    import torch
+    from tepdist_b200.runtime.executor import Executor
+    g = _aux_ops_graph()
+    ex = Executor(g, torch.device("cpu"), seed=0, use_cuda_graph=False)
+    torch.manual_seed(0)
+    x = torch.randn(8, 16, 32)
+    w = ex.store.state_dict()["w"].float().clone()
+    losses = [float(ex.step({"x": x})[0]) for _ in range(4)]
+    assert all(l == l for l in losses) and losses[-1] < losses[0], losses
+    h = torch.nn.functional.pad(x @ w.t(), (0, 0, 2, 2)).flip(1)
+    h = h.unfold(1, 2, 2).amax(-1)
+    h = torch.maximum(h, 0.1 * h).sigmoid()
+    pos = torch.arange(10).view(1, 10, 1).expand(8, 10, 32).float()
+    h = torch.where(pos < 4.5, h, h.abs().sqrt())
+    assert abs(float((h * h).mean()) - losses[0]) < 1e-4 * max(1.0, losses[0]), (float((h * h).mean()), losses[0])
