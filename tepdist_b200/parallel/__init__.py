@@ -213,7 +213,7 @@ class PipelineRunner:
         return [t.reshape(())]
 
 
-def build_pipeline(graph: Graph, trainer, stages: int, micro: int, comm_mode: str, seed: int):
+def build_pipeline(graph: Graph, trainer, stages: int, micro: int, comm_mode: str, seed: int, use_cuda_graph: bool = False):
     from ..runtime.pipeline import StageWorker
     from .collectives import CollectiveRunner
     from .mesh import DeviceMesh
@@ -252,7 +252,7 @@ def build_pipeline(graph: Graph, trainer, stages: int, micro: int, comm_mode: st
     base = mesh.base[stage_level]
     worker = StageWorker(g2, stage, S, M, 0 if M > 1 else -1, trainer.device, rank - base if stage > 0 else None,
                          rank + base if stage < S - 1 else None, seed=seed, collective=CollectiveRunner(mesh), coords=coords,
-                         comm_mode=comm_mode)
+                         comm_mode=comm_mode, use_cuda_graph=use_cuda_graph)
     worker.plan_transfers()
     tasks = d["tasks"][str(stage * n)]
     return PipelineRunner(worker, tasks, trainer.device)
@@ -278,7 +278,9 @@ def plan_and_build(graph: Graph, trainer, strategy: str, comm_mode: str, use_cud
         S_, _, M_ = body.partition("m")
         stages = int(S_)
         micro = int(M_) if M_ else max(2, 2 * stages)
-        return build_pipeline(graph, trainer, stages, micro, comm_mode, seed)
+        import os
+        return build_pipeline(graph, trainer, stages, micro, comm_mode, seed,
+                              use_cuda_graph=use_cuda_graph and os.environ.get("TEPDIST_PP_GRAPH", "1") == "1")
     from .collectives import CollectiveRunner
     from .mesh import DeviceMesh
     world, rank = trainer.world, trainer.rank

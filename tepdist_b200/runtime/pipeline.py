@@ -64,8 +64,25 @@ class StageWorker:
 
     def __init__(self, graph: Graph, stage: int, num_stages: int, num_micro: int, micro_level: int, device: torch.device,
                  peer_prev: Optional[int], peer_next: Optional[int], seed: int = 0, collective: Any = None,
-                 coords: Optional[Dict[int, int]] = None, comm_mode: str = "nccl"):
+                 coords: Optional[Dict[int, int]] = None, comm_mode: str = "nccl", use_cuda_graph: bool = False):
         self.stage, self.S, self.M, self.micro_level = stage, num_stages, num_micro, micro_level
+        # CUDA graphs of the stage bodies (reference: each stage is ONE compiled executable per direction, virtual_client.cc:
+        # 1662-1807; here the interpreter would otherwise pay ~30 us of Python per kernel, 7000+ kernels per step): the forward
+        # and the backward body of a micro-batch are captured once per in-flight SLOT (activations of slot k live in graph k's
+        # private pool; receive buffers, input staging and outputs have fixed addresses per slot) and replayed afterwards
+        import os
+        # TEPDIST_PP_GRAPH_EMULATE=1 (CPU tests): same slot / staging / fixed-address bookkeeping, but a "replay" re-executes the
+        # body eagerly and copies its results into the tensors recorded at "capture" -- a slot reused while its previous owner is
+        # still live, a stale staging buffer or a mis-wired receive slot then shows up as a wrong loss without any GPU
+        self.graph_emulate = os.environ.get("TEPDIST_PP_GRAPH_EMULATE") == "1"
+        self.use_graph = (bool(use_cuda_graph) and device.type == "cuda") or self.graph_emulate
+        self.graphs: Dict[Tuple[bool, int], Any] = {}
+        self.graph_env: Dict[Tuple[bool, int], Dict[Tuple[int, int], torch.Tensor]] = {}
+        self._static_feeds: Dict[int, Dict[str, torch.Tensor]] = {}
+        self.slot_of: Dict[int, int] = {}
+        self.num_slots = 0
+        self.steps_run = 0
+        self.graph_stats = {"captured": 0, "replayed": 0}
         self.peer_prev, self.peer_next = peer_prev, peer_next
         g, self.summed = elide_shared_level_collectives(graph, [micro_level] if num_micro > 1 else [])
         # this stage's slice of the program: sources it owns + its compute nodes
@@ -166,7 +183,7 @@ class StageWorker:
     def _micro_env(self, m: int) -> Dict[Tuple[int, int], torch.Tensor]:
         return self.env.setdefault(m, {})
 
-    def _run_nodes(self, nodes: List[Node], m: int, feeds: Dict[str, torch.Tensor]) -> None:
+    def _run_nodes(self, nodes: List[Node], m: int, feeds: Dict[str, torch.Tensor], accumulate: bool = True) -> None:
         ex = self.exec
         ex.coords[self.micro_level] = m
         ex._tag = m
@@ -193,11 +210,114 @@ class StageWorker:
                     gv = ex.store.grad_view(pid)
                     if t.data_ptr() != gv.data_ptr():
                         gv.add_(t.reshape(gv.shape).to(gv.dtype))
-                if (n.id, i) in self.acc_keys:   # gradients outside the flat buffer: accumulate over micro-batches (GA)
-                    if (n.id, i) in self.acc_env:
-                        self.acc_env[(n.id, i)] = self.acc_env[(n.id, i)] + t
-                    else:
-                        self.acc_env[(n.id, i)] = t.clone()
+                if accumulate and (n.id, i) in self.acc_keys:
+                    self._accumulate_extra((n.id, i), t)
+
+    def _accumulate_extra(self, key: Tuple[int, int], t: torch.Tensor) -> None:
+        """Gradients outside the flat buffer: accumulate over micro-batches (GA)."""
+        if key in self.acc_env:
+            self.acc_env[key] = self.acc_env[key] + t
+        else:
+            self.acc_env[key] = t.clone()
+
+    # ------------------------------------------------------------------ CUDA graphs of the stage bodies
+    def plan_slots(self, task_list: List[Dict[str, Any]]) -> None:
+        """Static slot of every micro-batch: taken at the first task that touches it (a hoisted forward Recv or the forward
+        Compute), returned where the scheduler's GC plan releases the micro-batch.  The number of slots is what the schedule
+        keeps in flight on this stage (1F1B: at most stages - stage; GROUP_SCHED_COUNT groups: more)."""
+        free: List[int] = []
+        slot_of: Dict[int, int] = {}
+        n = 0
+        for t in task_list:
+            m = t["micro"]
+            if m is not None and m >= 0 and m not in slot_of and t["type"] in ("Recv", "Compute", "Input") and not t["backward"]:
+                if free:
+                    free.sort()
+                    slot_of[m] = free.pop(0)
+                else:
+                    slot_of[m] = n
+                    n += 1
+            for dead in t.get("release", ()):
+                if dead in slot_of:
+                    free.append(slot_of[dead])
+        self.slot_of, self.num_slots = slot_of, n
+
+    def _stage_feeds(self, slot: int, m: int, feeds: Dict[str, torch.Tensor]) -> Dict[str, torch.Tensor]:
+        """Per-slot staging of the fed inputs this stage consumes: micro-batch m's shard is copied into a fixed buffer (the
+        captured body reads that address)."""
+        ex = self.exec
+        ex.coords[self.micro_level] = m
+        out = self._static_feeds.setdefault(slot, {})
+        dev = ex.device
+        for n in self.sub.nodes:
+            if n.op != "input" or n.name not in feeds:
+                continue
+            t = feeds[n.name]
+            if t.device != dev:
+                t = t.to(dev, non_blocking=True)
+            want = tuple(n.outputs[0].shape)
+            if tuple(t.shape) != want:
+                t = shard_of(t, n.attrs, ex.coords)
+            if tuple(t.shape) != want:
+                raise ValueError(f"pipeline stage {self.stage}: input '{n.name}' fed with shape {tuple(feeds[n.name].shape)}; with CUDA "
+                                 f"graphs the GLOBAL batch {tuple(n.attrs.get('full_shape', want))} must be fed on every rank")
+            if n.name not in out:
+                out[n.name] = t.contiguous().clone()
+            else:
+                out[n.name].copy_(t, non_blocking=True)
+        return out
+
+    def _run_phase(self, bwd: bool, m: int, feeds: Dict[str, torch.Tensor]) -> None:
+        nodes = self.bwd_nodes if bwd else self.fwd_nodes
+        if not self.use_graph or self.steps_run < 1 or m not in self.slot_of:
+            self._run_nodes(nodes, m, feeds)          # eager (first step = warm-up: lazy allocations, kernel attributes)
+            return
+        slot = self.slot_of[m]
+        key = (bwd, slot)
+        sfeeds = self._stage_feeds(slot, m, feeds)
+        env = self._micro_env(m)
+        if key not in self.graphs:
+            before = set(env)
+            if self.graph_emulate:
+                self._run_nodes(nodes, m, sfeeds, accumulate=False)
+                self.graphs[key] = "emulated"
+            else:
+                cur = torch.cuda.current_stream()
+                side = getattr(self, "_cap_stream", None)
+                if side is None:
+                    side = self._cap_stream = torch.cuda.Stream()
+                side.wait_stream(cur)
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.stream(side):
+                    # thread-local capture mode: NCCL's watchdog thread and in-flight p2p of other streams stay legal; no device-
+                    # wide synchronisation here (a peer may be waiting for data this rank has already queued)
+                    g.capture_begin(capture_error_mode="thread_local")
+                    try:
+                        self._run_nodes(nodes, m, sfeeds, accumulate=False)
+                    finally:
+                        g.capture_end()
+                cur.wait_stream(side)
+                self.graphs[key] = g
+                g.replay()                            # capture records, it does not execute
+            self.graph_env[key] = {k: v for k, v in env.items() if k not in before}
+            self.graph_stats["captured"] += 1
+        elif self.graph_emulate:
+            scratch = dict(env)
+            self.env[m] = scratch
+            self._run_nodes(nodes, m, sfeeds, accumulate=False)
+            self.env[m] = env
+            for k, v in self.graph_env[key].items():
+                if scratch[k].data_ptr() != v.data_ptr():
+                    v.copy_(scratch[k])
+            env.update(self.graph_env[key])
+            self.graph_stats["replayed"] += 1
+        else:
+            env.update(self.graph_env[key])
+            self.graphs[key].replay()
+            self.graph_stats["replayed"] += 1
+        for k in self.acc_keys:
+            if k in self.graph_env[key]:
+                self._accumulate_extra(k, self.graph_env[key][k])
 
     def begin_step(self) -> None:
         self.exec.step_count += 1
@@ -210,10 +330,10 @@ class StageWorker:
         self.loss_acc = None
 
     def forward(self, m: int, feeds: Dict[str, torch.Tensor]) -> None:
-        self._run_nodes(self.fwd_nodes, m, feeds)
+        self._run_phase(False, m, feeds)
 
     def backward(self, m: int, feeds: Dict[str, torch.Tensor]) -> None:
-        self._run_nodes(self.bwd_nodes, m, feeds)
+        self._run_phase(True, m, feeds)
         env = self._micro_env(m)
         for v in self.sub.outputs:   # fetches (loss) are summed over micro-batches
             if v.key() in env:
@@ -268,6 +388,8 @@ class StageWorker:
         if ent is not None:
             buf, owner = ent
             if owner != m and (owner in self.env or owner in self._threaded):
+                if self.use_graph:
+                    raise RuntimeError(f"stage {self.stage}: receive slot {slot} of micro-batch {m} is still owned by {owner}")
                 self.ring_stats["miss"] += 1
                 return fresh()
             for w, t in self.pending_send:          # a pass-through send may still be reading the slot
@@ -285,6 +407,8 @@ class StageWorker:
         peer = self.peer_next if backward else self.peer_prev
         env = self._micro_env(m)
         works = []
+        if self.use_graph and m in self.slot_of:
+            slot = self.slot_of[m]       # the receive ring is indexed by the graph slot: captured bodies read fixed addresses
         for key in self._values_for(boundary, backward):
             buf = self._recv_buffer(m, backward, key, slot)
             works.append(dist.irecv(buf, peer))
@@ -298,6 +422,9 @@ class StageWorker:
 
 def run_pipeline_step(worker: StageWorker, task_list: List[Dict[str, Any]], feeds: Dict[str, torch.Tensor]) -> Optional[float]:
     """Execute one training step by walking this device's ordered task list."""
+    if worker.use_graph and getattr(worker, "_slots_for", None) is not task_list:
+        worker.plan_slots(task_list)
+        worker._slots_for = task_list
     worker.begin_step()
     worker._threaded = {}
     pending_recv: Dict[Tuple[int, bool], List[Any]] = {}
@@ -326,4 +453,5 @@ def run_pipeline_step(worker: StageWorker, task_list: List[Dict[str, Any]], feed
             worker.release(dead)
     for w, _ in pending_send:
         w.wait()
+    worker.steps_run += 1
     return None if worker.loss_acc is None else float(worker.loss_acc)

@@ -37,6 +37,9 @@ def case_gpt2(strategy, feed_shards=False, batch=4):
         stats = [None] * tr.world
         dist.all_gather_object(stats, dict(worker.ring_stats, stage=worker.stage, sync_recvs=worker.sync_recvs))
         res["ring"] = stats
+        gst = [None] * tr.world
+        dist.all_gather_object(gst, dict(worker.graph_stats, slots=worker.num_slots, stage=worker.stage))
+        res["graphs"] = gst
     return res
 
 

@@ -379,3 +379,15 @@ def test_executor_side_of_fused_tp_all_reduce_with_emulated_kernel(tmp_path):
     assert got["parallelism"].startswith("tp") and got["fused_calls"] > 0, got
     for a, b in zip(got["losses"], ref["losses"]):
         assert abs(a - b) <= 2e-4 * max(1.0, abs(b)), (got, ref)
+
+
+def test_pipeline_stage_graph_bookkeeping_emulated(tmp_path):
+    """The CUDA-graph mode of the pipeline stage workers (per-slot capture of the forward / backward bodies, receive ring and
+    input staging indexed by the slot, fixed output addresses) with the graphs EMULATED on CPU: 4 micro-batches over 2 in-flight
+    slots per stage, so every slot is reused -- the losses must still equal the single-process run."""
+    ref = _single("gpt2:auto")
+    got = _run("gpt2:pp2m4", 2, tmp_path, extra_env={"TEPDIST_PP_GRAPH_EMULATE": "1"})
+    assert got["parallelism"].startswith("pp2"), got
+    for a, b in zip(got["losses"], ref["losses"]):
+        assert abs(a - b) <= 2e-4 * max(1.0, abs(b)), (got, ref)
+    assert got["graphs"] and all(s["captured"] >= 2 and s["replayed"] >= 4 and s["slots"] <= 3 for s in got["graphs"]), got["graphs"]
