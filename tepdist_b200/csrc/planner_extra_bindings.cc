@@ -4,6 +4,7 @@
 #include "auto_parallel.h"
 #include "ilp.h"
 #include "stage_planner.h"
+#include "runtime/task_graph.h"
 
 namespace py = pybind11;
 using namespace tepdist;
@@ -85,6 +86,12 @@ void BindPlannerExtra(py::module_& m) {
       .def_readonly("from_stage", &StageTransfer::from_stage).def_readonly("to_stage", &StageTransfer::to_stage)
       .def_readonly("backward", &StageTransfer::backward).def_readonly("bytes", &StageTransfer::bytes);
   m.def("stage_decompose", [](const Graph& g, int stages, Decomposition& d) { return StageDecompose(g, stages, &d); });
+  m.def("compile_task_dag", [](const Graph& g, const Decomposition& d, const std::vector<StageTransfer>& x, int micro, int spmd,
+                               const HwProfile& hw) {
+    PipelineSpec sp;
+    TaskDAG dag = CompileTaskDAG(g, d, x, micro, spmd, hw, &sp);
+    return py::make_tuple(dag, sp);
+  });
 
   py::class_<EvalInput>(m, "EvalInput")
       .def(py::init<>())

@@ -82,6 +82,14 @@ struct Schedule {
 };
 Schedule ScheduleTasks(TaskDAG* dag, const PipelineSpec& spec, const ScheduleOptions& opt);
 
+// D3 proper: the same DAG compiled from the DefContext tree of a decomposed plan (compile_task_dag.cc); fills `spec_out` with
+// the costs it derived so the scheduler prices the same numbers.  (Declared here, defined next to the planner types.)
+struct Decomposition;
+struct StageTransfer;
+class Graph;
+TaskDAG CompileTaskDAG(const Graph& g, const Decomposition& d, const std::vector<StageTransfer>& xfers, int num_micro, int spmd,
+                       const HwProfile& hw, PipelineSpec* spec_out);
+
 // D6 OutputBuffersLifeTimeTracker: ref-count every task output along a linear execution order; returns for each
 // position the outputs that become dead right after it.
 std::vector<std::vector<int>> ComputeReleasePlan(const TaskDAG& dag, const std::vector<int>& order);

@@ -36,7 +36,7 @@ void BindRuntime(py::module_& m) {
       .def_readonly("cost", &TaskNode::cost).def_readonly("out_bytes", &TaskNode::out_bytes)
       .def_readonly("parents", &TaskNode::parents).def_readonly("children", &TaskNode::children)
       .def_readonly("mem_to_release", &TaskNode::mem_to_release).def_readonly("buffer_id", &TaskNode::buffer_id)
-      .def_readonly("buffer_reused", &TaskNode::buffer_reused);
+      .def_readonly("buffer_reused", &TaskNode::buffer_reused).def_readonly("def_ctx", &TaskNode::def_ctx);
   py::class_<TaskDAG>(m, "TaskDAG")
       .def(py::init<>())
       .def_readonly("nodes", &TaskDAG::nodes).def_readonly("source", &TaskDAG::source).def_readonly("sink", &TaskDAG::sink)

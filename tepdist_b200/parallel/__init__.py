@@ -164,19 +164,15 @@ def plan_pipeline(graph: Graph, world: int, stages: int, micro: int, options: Op
     pr = plan.proposal
     out = from_native(plan.graph)
     merge_client_attrs(out, graph)
-    # task graph + 1F1B schedule (C++ runtime core)
+    # task graph + 1F1B schedule (C++ runtime core): the plan is decomposed into its DefContext tree (SyncFreeDecompose: CG /
+    # GAINIT / GA / AG; StageDecompose: CG_SLICE_<s>_{F,B}, AG_SLICE_<s> + the neighbour-only transfer list) and the TaskDAG is
+    # COMPILED from that tree -- task costs are the contexts' FLOPs, Send / Recv bytes the transfer list (CompileTaskDAG)
     hw = config.hw_profile()
-    sp = _C.PipelineSpec()
     if config.pp_bandwidth() is not None:
-        sp.p2p_bw = config.pp_bandwidth()
-    sp.num_stages, sp.num_micro, sp.spmd = pr.stages, pr.micro, pr.spmd
-    fl = list(plan.stage_plan.stage_flops) or [sum(plan.graph.node_flops(i) for i in range(plan.graph.num_nodes()))]
-    sp.fwd_seconds = [f / 3.0 / hw.flops for f in fl]
-    sp.bwd_seconds = [f * 2.0 / 3.0 / hw.flops for f in fl]
-    sp.ag_seconds = [1e-4] * pr.stages
-    sp.act_bytes = [1.0] * pr.stages
-    sp.boundary_bytes = [plan.stage_plan.cut_bytes / max(1, pr.stages - 1) / 2.0] * max(0, pr.stages - 1)
-    dag = _C.build_pipeline_task_dag(sp)
+        hw.link_bw = config.pp_bandwidth()
+    dec = _C.sync_free_decompose(plan.graph, 0 if pr.micro > 1 else -1)
+    xfers = _C.stage_decompose(plan.graph, pr.stages, dec)
+    dag, sp = _C.compile_task_dag(plan.graph, dec, xfers, pr.micro, pr.spmd, hw)
     so = _C.ScheduleOptions()
     for k, v in config.schedule_overrides().items():
         setattr(so, k, v)
@@ -191,6 +187,8 @@ def plan_pipeline(graph: Graph, world: int, stages: int, micro: int, options: Op
                          "buffer_reused": dag.nodes[t].buffer_reused, "release": released_micros(t)} for t in lst]
              for dev, lst in sch.device_tasks.items()}
     info = {"stages": pr.stages, "micro": pr.micro, "spmd": pr.spmd, "log": plan.log, "eval": repr(plan.eval),
+            "def_contexts": [c.name for c in dec.ctx], "stage_fwd_seconds": list(sp.fwd_seconds), "stage_bwd_seconds": list(sp.bwd_seconds),
+            "boundary_bytes": list(sp.boundary_bytes),
             "makespan_est": sch.makespan, "bubble_est": sch.bubble_ratio, "cut_bytes": plan.stage_plan.cut_bytes,
             "stage_method": plan.stage_plan.method, "candidates": list(plan.candidates)}
     return out, info, tasks
@@ -249,7 +247,7 @@ def build_pipeline(graph: Graph, trainer, stages: int, micro: int, comm_mode: st
     for l, sh in enumerate(shared):
         if sh:
             coords[l] = 0
-    base = mesh.base[stage_level]
+    base = mesh.stride(stage_level)
     worker = StageWorker(g2, stage, S, M, 0 if M > 1 else -1, trainer.device, rank - base if stage > 0 else None,
                          rank + base if stage < S - 1 else None, seed=seed, collective=CollectiveRunner(mesh), coords=coords,
                          comm_mode=comm_mode, use_cuda_graph=use_cuda_graph)

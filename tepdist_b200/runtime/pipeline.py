@@ -85,8 +85,16 @@ class StageWorker:
         self.graph_stats = {"captured": 0, "replayed": 0}
         self.peer_prev, self.peer_next = peer_prev, peer_next
         g, self.summed = elide_shared_level_collectives(graph, [micro_level] if num_micro > 1 else [])
-        # this stage's slice of the program: sources it owns + its compute nodes
+        # this stage's slice of the program: sources it owns + its compute nodes.  WHICH nodes run per micro-batch forward /
+        # per micro-batch backward / once per step, and WHICH values cross which stage boundary, is not derived here: it is the
+        # DefContext tree of the C++ core (SyncFreeDecompose + StageDecompose, csrc/auto_parallel.cc) for exactly this graph
         self.full = g
+        from .. import _C
+        from ..planner import to_native
+        cg = to_native(g)
+        self.decomposition = _C.sync_free_decompose(cg, micro_level if num_micro > 1 else -1)
+        self.transfers = _C.stage_decompose(cg, num_stages, self.decomposition)
+        ctx = {(c.kind, c.stage): c for c in self.decomposition.ctx}
         mine = [n for n in g.nodes if n.stage == stage]
         self.sub, self.idmap = self._extract(g, mine)
         self.exec = Executor(self.sub, device, seed=seed, collective=collective, coords=dict(coords or {}), comm_mode=comm_mode)
@@ -97,8 +105,17 @@ class StageWorker:
         self.exec.pipeline_norm_divisor = spmd   # global-norm clipping: stage sums are added up over the whole job
         self.exec._plan_store_init()
         ex = self.exec
-        self.fwd_nodes = [n for n in self.sub.nodes if not n.backward and n.op not in ("state", "boundary") and n.id not in ex.post_apply]
-        self.bwd_nodes = [n for n in self.sub.nodes if n.backward and n.id not in ex.post_apply and not n.op.startswith("apply_")]
+        if num_stages > 1:
+            fwd_ids = {self.idmap[i] for i in ctx[("stage_fwd", stage)].nodes if i in self.idmap}
+            bwd_ids = {self.idmap[i] for i in ctx[("stage_bwd", stage)].nodes if i in self.idmap}
+        else:   # one stage: the CG context is the whole per-micro-batch program
+            cgc = next(c for c in self.decomposition.ctx if c.kind == "cg")
+            fwd_ids = {self.idmap[i] for i in cgc.nodes if i in self.idmap and not g.nodes[i].backward}
+            bwd_ids = {self.idmap[i] for i in cgc.nodes if i in self.idmap and g.nodes[i].backward}
+        # the forward list additionally materialises the sources this stage owns (variables / constants live in ENTRY)
+        self.fwd_nodes = [n for n in self.sub.nodes if (n.id in fwd_ids or (n.op in ("parameter", "constant") and not n.backward))
+                          and n.id not in ex.post_apply]
+        self.bwd_nodes = [n for n in self.sub.nodes if n.id in bwd_ids and n.id not in ex.post_apply]
         self.env: Dict[int, Dict[Tuple[int, int], torch.Tensor]] = {}
         # persistent receive buffers: (backward, value key, slot) -> (buffer, micro-batch that owns it this step)
         self._ring: Dict[Tuple[bool, Tuple[int, int], int], Tuple[torch.Tensor, Optional[int]]] = {}
@@ -156,27 +173,16 @@ class StageWorker:
 
     # ------------------------------------------------------------------ transfer plan (neighbour-only, B4)
     def plan_transfers(self) -> None:
-        """For every boundary (s, s+1) and direction, the ordered list of full-graph values that cross it (values
-        consumed k stages away hop through each intermediate stage).  Every rank derives the same lists."""
-        g = self.full
+        """For every boundary (s, s+1) and direction, the ordered list of full-graph values that cross it -- the StageTransfer
+        list of the C++ StageDecompose pass (values consumed k stages away hop through each intermediate stage).  Every rank
+        decomposes the same graph, hence derives the same lists in the same order."""
         fwd: Dict[int, List[Tuple[int, int]]] = {b: [] for b in range(self.S - 1)}   # boundary b: stage b -> b+1
         bwd: Dict[int, List[Tuple[int, int]]] = {b: [] for b in range(self.S - 1)}   # boundary b: stage b+1 -> b
-        seen = set()
-        for n in g.nodes:
-            if n.op in ("parameter", "state"):
-                continue
-            for v in n.inputs:
-                p = g.nodes[v.node]
-                if p.op in ("parameter", "state", "constant") or p.stage < 0 or n.stage < 0 or p.stage == n.stage:
-                    continue
-                a, b = p.stage, n.stage
-                step = 1 if b > a else -1
-                for s in range(a, b, step):
-                    key = (v.node, v.idx, s, s + step)
-                    if key in seen:
-                        continue
-                    seen.add(key)
-                    (fwd[s] if step > 0 else bwd[s + step]).append(v.key())
+        for t in self.transfers:
+            if t.backward:
+                bwd[t.to_stage].append(tuple(t.value))
+            else:
+                fwd[t.from_stage].append(tuple(t.value))
         self.xfer_fwd, self.xfer_bwd = fwd, bwd
 
     # ------------------------------------------------------------------ phases

@@ -390,12 +390,13 @@ def test_gpt2_1p5b_plans_quickly_in_every_mode():
     assert time.time() - t0 < 60.0
 
 
-def test_cxx_stage_decomposition_and_runtime_transfer_planning_agree():
-    """The pipeline runtime derives the values crossing each stage boundary itself (runtime/pipeline.py::plan_transfers); the
-    C++ StageDecompose pass computes the same thing but is not on the execution path.  They must agree -- per boundary, per
-    direction, multi-hop threading included -- on 2-stage, 4-stage and hybrid (pipeline x SPMD) plans.  Also pins that
-    planner.to_native keeps the pipeline stage of every node (it used to drop them, which made this comparison see 0 transfers)."""
-    import types
+def test_stage_workers_execute_the_cxx_decomposition():
+    """B3 / B4 / C2: the pipeline runtime does not derive stage phases or transfers on its own -- StageWorker takes the per-
+    micro-batch forward / backward node lists from the DefContext tree (SyncFreeDecompose + StageDecompose) and the values that
+    cross each boundary from the StageTransfer list.  Checked here on 2-stage, 4-stage and hybrid (pipeline x SPMD) plans:
+    the consumed lists are exactly the C++ result, transfers are neighbour-only with multi-hop threading, the contexts cover
+    every non-source node exactly once, and planner.to_native keeps the pipeline stage of every node."""
+    import torch
     from tepdist_b200.models.gpt2 import CONFIGS, build_gpt2_graph
     from tepdist_b200.parallel import plan_pipeline
     from tepdist_b200.planner import from_native, to_native
@@ -403,46 +404,27 @@ def test_cxx_stage_decomposition_and_runtime_transfer_planning_agree():
     g = build_gpt2_graph(CONFIGS["tiny"], batch=4)
     for (world, S, M) in [(2, 2, 2), (4, 4, 4), (4, 2, 2)]:
         g2, info, _ = plan_pipeline(g, world, S, M)
-        cg = to_native(g2)
-        assert [cg.node_stage(i) for i in range(cg.num_nodes())] == [n.stage for n in g2.nodes]
-        assert [n.stage for n in from_native(cg).nodes] == [n.stage for n in g2.nodes]
-        stub = types.SimpleNamespace(full=g2, S=info["stages"])
-        StageWorker.plan_transfers(stub)
-        py = {(v, b, b + 1) for b, vals in stub.xfer_fwd.items() for v in vals} | \
-             {(v, b + 1, b) for b, vals in stub.xfer_bwd.items() for v in vals}
-        d = _C.sync_free_decompose(cg, 0 if info["micro"] > 1 else -1)
-        cc = {(tuple(t.value), t.from_stage, t.to_stage) for t in _C.stage_decompose(cg, info["stages"], d)}
-        assert len(py) >= 2 * (info["stages"] - 1), (world, S, M, py)       # at least activation + gradient per boundary
-        assert py == cc, ((world, S, M), sorted(py - cc)[:4], sorted(cc - py)[:4])
-        for t in _C.stage_decompose(cg, info["stages"], _C.sync_free_decompose(cg, 0 if info["micro"] > 1 else -1)):
-            assert abs(t.to_stage - t.from_stage) == 1 and t.backward == (t.to_stage < t.from_stage) and t.bytes > 0
-
-
-def test_cxx_def_contexts_match_the_phases_the_stage_workers_execute():
-    """B3 / C2 cross-check.  The stage workers split their slice of the program into a per-micro-batch forward list, a per-micro-
-    batch backward list and a once-per-step optimizer phase themselves (runtime/pipeline.py); the C++ SyncFreeDecompose +
-    StageDecompose passes build the DefContext tree CG_SLICE_<s>_F / _B / AG_SLICE_<s> for the same purpose but are not on the
-    execution path.  Node for node they must describe the same phases (the runtime additionally lists the source nodes --
-    variables, constants -- in its forward list; C++ keeps those in ENTRY)."""
-    import torch
-    from tepdist_b200.models.gpt2 import CONFIGS, build_gpt2_graph
-    from tepdist_b200.parallel import plan_pipeline
-    from tepdist_b200.runtime.pipeline import StageWorker
-    g = build_gpt2_graph(CONFIGS["tiny"], batch=4)
-    for (world, S, M) in [(2, 2, 2), (4, 4, 4)]:
-        g2, info, _ = plan_pipeline(g, world, S, M)
-        assert info["spmd"] == 1
+        cg2 = to_native(g2)
+        assert [cg2.node_stage(i) for i in range(cg2.num_nodes())] == [n.stage for n in g2.nodes]
+        assert [n.stage for n in from_native(cg2).nodes] == [n.stage for n in g2.nodes]
+        assert "CG_SLICE_0_F" in info["def_contexts"] and f"AG_SLICE_{S - 1}" in info["def_contexts"]
         ml = 0 if info["micro"] > 1 else -1
         workers = [StageWorker(g2, s, S, M, ml, torch.device("cpu"), None, None) for s in range(S)]
         full = workers[0].full                       # (micro-level collectives elided: ids differ from g2)
         cg = to_native(full)
         d = _C.sync_free_decompose(cg, ml)
-        _C.stage_decompose(cg, S, d)
+        xf = _C.stage_decompose(cg, S, d)
+        assert len(xf) >= 2 * (S - 1)                # at least activation + gradient per boundary
+        for t in xf:
+            assert abs(t.to_stage - t.from_stage) == 1 and t.backward == (t.to_stage < t.from_stage) and t.bytes > 0
         cxx = {(c.kind, c.stage): set(c.nodes) for c in d.ctx if c.stage >= 0}
         assert set(cxx) == {(k, s) for k in ("stage_fwd", "stage_bwd", "stage_ag") for s in range(S)}
-        sources = ("parameter", "state", "constant")     # (the samples -- `input` nodes -- are per-micro-batch on both sides)
+        sources = ("parameter", "state", "constant")
         covered = set()
         for s, w in enumerate(workers):
+            w.plan_transfers()
+            assert {(v, b, b + 1) for b, vals in w.xfer_fwd.items() for v in vals} | \
+                   {(v, b + 1, b) for b, vals in w.xfer_bwd.items() for v in vals} == {(tuple(t.value), t.from_stage, t.to_stage) for t in xf}
             inv = {v: k for k, v in w.idmap.items()}
             fwd = {inv[n.id] for n in w.fwd_nodes if n.id in inv and n.op not in sources}
             bwd = {inv[n.id] for n in w.bwd_nodes if n.id in inv}
@@ -452,12 +434,40 @@ def test_cxx_def_contexts_match_the_phases_the_stage_workers_execute():
                 assert mine == theirs, ((world, S, M), s, kind, [full.nodes[i].name for i in sorted(mine ^ theirs)][:6])
                 assert mine and not (mine & covered)
                 covered |= mine
-        # together the contexts cover every non-source node exactly once
         rest = {n.id for n in full.nodes if n.op not in sources}
         # (the only source inside a phase is the backward pass's seed constant dloss = 1)
         assert covered >= rest and all(full.nodes[i].op == "constant" and full.nodes[i].backward for i in covered - rest)
         per_micro = {c.name: c.per_micro_batch for c in d.ctx}
         assert per_micro["CG"] and not per_micro["AG"]
+
+
+def test_task_dag_is_compiled_from_the_def_context_tree():
+    """D3: the scheduler's TaskDAG comes from CompileTaskDAG(DefContext tree, StageTransfer list): compute tasks carry the
+    context they execute, their costs are the contexts' FLOPs over the device rate, Send / Recv costs the transfer bytes."""
+    from tepdist_b200 import config
+    from tepdist_b200.models.gpt2 import CONFIGS, build_gpt2_graph
+    from tepdist_b200.planner import to_native
+    g = build_gpt2_graph(CONFIGS["tiny"], batch=8)
+    ap = _C.AutoParallelOptions()
+    ap.num_devices, ap.mode, ap.num_stages, ap.num_micro_batches = 4, "config", 2, 4
+    plan = _C.auto_parallel(to_native(g), ap)
+    d = _C.sync_free_decompose(plan.graph, 0)
+    xf = _C.stage_decompose(plan.graph, 2, d)
+    hw = config.hw_profile()
+    dag, sp = _C.compile_task_dag(plan.graph, d, xf, 4, 2, hw)
+    names = [c.name for c in d.ctx]
+    comp = [t for t in dag.nodes if t.type == _C.TaskType.Compute]
+    assert len(comp) == 2 * 4 * 2                                  # stages x micro-batches x {fwd, bwd}
+    for t in comp:
+        c = d.ctx[t.def_ctx]
+        assert c.name == f"CG_SLICE_{t.stage}_{'B' if t.backward else 'F'}" and names[t.def_ctx] == c.name
+        assert abs(t.cost - max(c.gflops * 1e9 / hw.flops, 1e-7)) < 1e-12
+    assert all(d.ctx[t.def_ctx].name == f"AG_SLICE_{t.stage}" for t in dag.nodes if t.type == _C.TaskType.AG)
+    fwd_bytes = sum(t.bytes for t in xf if not t.backward)
+    assert abs(sum(sp.boundary_bytes) - fwd_bytes) < 1e-6 and fwd_bytes > 0
+    assert list(sp.bwd_seconds)[0] > list(sp.fwd_seconds)[0] > 0   # backward of a stage costs more than its forward
+    sch = _C.schedule_tasks(dag, sp, _C.ScheduleOptions())
+    assert 0 < sch.bubble_ratio < 1.0 and not sch.oom              # (tiny model: p2p latency dominates the 0.1 us tasks)
 
 
 def _mixed_precision_mlp(batch=8, d_in=16, d_h=32, d_out=4):
