@@ -218,6 +218,25 @@ def main():
             finally:
                 ex_mod.TP_FUSED = False
 
+    # ---------------- pipeline: measured bubble per stage (2 extra steps with CUDA events around every stage body)
+    pp_meas = None
+    if is_pp:
+        w = trainer.exec.worker
+        w.timing = True
+        bub = []
+        for i in range(2):
+            trainer.step_async({"tokens": dev_tok[i % nbuf], "labels": dev_lab[i % nbuf]})
+            bub.append(w.last_timing["bubble"])
+        w.timing = False
+        tb = torch.tensor([sum(bub) / len(bub), float(w.stage)], dtype=torch.float64, device=dev)
+        allb = [torch.zeros_like(tb) for _ in range(world)]
+        dist.all_gather(allb, tb)
+        per_stage = {}
+        for x in allb:
+            per_stage.setdefault(int(x[1].item()), []).append(float(x[0].item()))
+        pp_meas = {"bubble_per_stage": {str(k): round(sum(v) / len(v), 4) for k, v in sorted(per_stage.items())},
+                   "cuda_graph": bool(w.use_graph), "graphs_captured": w.graph_stats["captured"], "slots": w.num_slots}
+
     t = torch.tensor([ms, ms_e2e, ms_dry, tp_ms["fused"], tp_ms["nccl"]], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -258,7 +277,9 @@ def main():
             out["pipeline"] = {"stages": pi.get("stages"), "micro_batches": pi.get("micro"), "spmd": pi.get("spmd"),
                                "stage_cut": pi.get("stage_method"), "cut_bytes": pi.get("cut_bytes"),
                                "scheduler_bubble_estimate": pi.get("bubble_est"), "scheduler_makespan_estimate_s": pi.get("makespan_est"),
-                               "p2p": "NCCL isend/irecv on side streams", "cuda_graph": False}
+                               "p2p": "NCCL isend/irecv on side streams", **(pp_meas or {})}
+            out["pipeline"]["measured_bubble_mean"] = (sum(out["pipeline"]["bubble_per_stage"].values()) /
+                                                        max(1, len(out["pipeline"]["bubble_per_stage"]))) if pp_meas else None
         if world > 1 and not library and not args.no_tp:
             tp = dict(tp_info)
             tp["global_batch"] = B * world

@@ -22,7 +22,7 @@ mkdir -p gpurun_out
 rc_all=0
 for c in $checks; do
   log="gpurun_out/sanitize_${tool}_${c}.log"
-  timeout 600 compute-sanitizer --tool "$tool" --error-exitcode 77 --print-limit 20 \
+  timeout 600 compute-sanitizer --tool "$tool" --report-api-errors no --error-exitcode 77 --print-limit 20 \
       python tests/kernel_checks.py --one "$c" > "$log" 2>&1
   rc=$?
   echo "$tool $c rc=$rc $(grep -c 'ERROR SUMMARY\|========= Error\|Race reported\|Invalid' "$log") flagged-lines"

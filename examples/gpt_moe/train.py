@@ -32,12 +32,24 @@ def main():
     tok = torch.randint(0, cfg.vocab, (cfg.batch, cfg.seq), generator=gen, dtype=torch.int32)
     feeds = {"tokens": tok, "labels": torch.roll(tok, -1, 1)}
     t0 = time.time()
+    t_steady = None
     for i in range(a.steps):
+        if i == 3:      # steps 0-2: planning artefacts, lazy allocations, kernel attribute setup
+            if torch.cuda.is_available():
+                torch.cuda.synchronize()
+            t_steady = time.time()
         loss = tr.step(feeds)
         if tr.rank == 0:
             print(f"step {i} loss {loss:.4f}")
+    if torch.cuda.is_available():
+        torch.cuda.synchronize()
     if tr.rank == 0:
-        print(f"{a.steps} steps in {time.time() - t0:.2f}s; plan: {tr.plan_info.get('parallelism', 'single')}")
+        msg = f"{a.steps} steps in {time.time() - t0:.2f}s; plan: {tr.plan_info.get('parallelism', 'single')}"
+        if t_steady is not None and a.steps > 3:
+            dt = (time.time() - t_steady) / (a.steps - 3)
+            msg += f"; steady state {dt * 1e3:.1f} ms/step = {cfg.batch * cfg.seq / dt:.0f} tokens/s (global batch {cfg.batch} x {cfg.seq})"
+        msg += f"; collectives: {tr.plan_info.get('collectives')}"
+        print(msg)
     os._exit(0)
 
 

@@ -432,6 +432,11 @@ def run_pipeline_step(worker: StageWorker, task_list: List[Dict[str, Any]], feed
         worker.plan_slots(task_list)
         worker._slots_for = task_list
     worker.begin_step()
+    timing = getattr(worker, "timing", False) and worker.exec.device.type == "cuda"
+    spans: List[Tuple[Any, Any]] = []
+    if timing:
+        t_begin = torch.cuda.Event(enable_timing=True)
+        t_begin.record()
     worker._threaded = {}
     pending_recv: Dict[Tuple[int, bool], List[Any]] = {}
     pending_send = worker.pending_send = []
@@ -447,7 +452,13 @@ def run_pipeline_step(worker: StageWorker, task_list: List[Dict[str, Any]], feed
             for w in pending_recv.pop((m, bwd), []):
                 w.wait()
         elif kind == "Compute":
+            if timing:
+                a, b_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                a.record()
             (worker.backward if bwd else worker.forward)(m, feeds)
+            if timing:
+                b_.record()
+                spans.append((a, b_))
         elif kind == "Send":
             pending_send += worker.send(m, bwd)   # (work, payload) pairs: payloads stay referenced until waited
         elif kind == "AG":
@@ -460,4 +471,12 @@ def run_pipeline_step(worker: StageWorker, task_list: List[Dict[str, Any]], feed
     for w, _ in pending_send:
         w.wait()
     worker.steps_run += 1
+    if timing:
+        # measured bubble of THIS stage: share of the step (first task .. last send completed) in which no stage body ran
+        t_end = torch.cuda.Event(enable_timing=True)
+        t_end.record()
+        torch.cuda.synchronize()
+        busy = sum(a.elapsed_time(b_) for a, b_ in spans)
+        total = t_begin.elapsed_time(t_end)
+        worker.last_timing = {"busy_ms": busy, "step_ms": total, "bubble": 1.0 - busy / total if total > 0 else 0.0}
     return None if worker.loss_acc is None else float(worker.loss_acc)
