@@ -8,6 +8,7 @@ as ``gpu_launches``).
 from __future__ import annotations
 
 import ctypes
+import math
 import os
 from typing import Optional
 
@@ -273,6 +274,57 @@ def gemm2(a: torch.Tensor, b: torch.Tensor, *, a_mn: bool = False, b_mn: bool = 
     _check(rc, "gemm2_bf16")
     _count()
     return out
+
+
+def einsum(eq: str, a: torch.Tensor, b: torch.Tensor, _force: bool = False) -> torch.Tensor:
+    """Two-operand einsum as ONE batched tcgen05 GEMM (the expert FFNs / dispatch / combine of GPT-MoE and their gradients are
+    einsums with a leading expert or group dim; the reference hands them to cuBLAS batched GEMMs).
+
+    Indices are classified batch (in a, b, out) / M (a, out) / N (b, out) / K (a, b): each operand is brought to
+    [batch, rows, cols] with its groups kept in memory order when they already are (either major is fine: the kernel reads
+    K-major and MN-major operands alike through TMA), copied once otherwise; the [batch, M, N] result is viewed / permuted
+    to the requested output order.  Falls back to torch.einsum for index patterns or shapes outside the kernel's alignment
+    rules (dims % 8, bf16)."""
+    lhs, out_idx = eq.replace(" ", "").split("->")
+    ia, ib = lhs.split(",")
+    ok = (((a.is_cuda and a.dtype == torch.bfloat16 and b.dtype == torch.bfloat16) or _force) and len(set(ia)) == len(ia)
+          and len(set(ib)) == len(ib) and len(set(out_idx)) == len(out_idx))
+    if ok:
+        batch = [c for c in out_idx if c in ia and c in ib]
+        m_idx = [c for c in ia if c in out_idx and c not in ib]
+        n_idx = [c for c in ib if c in out_idx and c not in ia]
+        k_idx = [c for c in ia if c in ib and c not in out_idx]
+        ok = (len(batch) + len(m_idx) + len(k_idx) == len(ia) and len(batch) + len(n_idx) + len(k_idx) == len(ib)
+              and bool(m_idx) and bool(n_idx) and bool(k_idx))
+    if not ok:
+        return torch.einsum(eq, a, b)
+    size = {c: d for c, d in zip(ia, a.shape)}
+    size.update({c: d for c, d in zip(ib, b.shape)})
+    prod = lambda idx: int(math.prod(size[c] for c in idx)) if idx else 1
+    B_, M, N, K = prod(batch), prod(m_idx), prod(n_idx), prod(k_idx)
+    if M % 8 or N % 8 or K % 8:
+        return torch.einsum(eq, a, b)
+
+    def arrange(t: torch.Tensor, idx: str, rows, cols):
+        """-> (tensor [B, R, C] contiguous, transposed?) choosing rows-major or cols-major storage, whichever needs no copy."""
+        for first, second, tr in ((rows, cols, False), (cols, rows, True)):
+            want = "".join(batch + first + second)
+            if want == idx and t.is_contiguous():
+                return t.reshape(B_, prod(first), prod(second)), tr
+        perm = [idx.index(c) for c in batch + rows + cols]
+        return t.permute(perm).contiguous().reshape(B_, prod(rows), prod(cols)), False
+
+    a3, a_tr = arrange(a, ia, m_idx, k_idx)        # [B, M, K] or (a_tr) [B, K, M]
+    b3, b_tr = arrange(b, ib, k_idx, n_idx)        # [B, K, N] or (b_tr) [B, N, K]
+    if B_ == 1:
+        d = gemm(a3[0], b3[0], a_mn=a_tr, b_mn=not b_tr).unsqueeze(0)
+    else:
+        d = gemm(a3, b3, a_mn=a_tr, b_mn=not b_tr)
+    d = d.reshape([size[c] for c in batch + m_idx + n_idx])
+    cur = "".join(batch + m_idx + n_idx)
+    if cur != out_idx:
+        d = d.permute([cur.index(c) for c in out_idx]).contiguous()
+    return d
 
 
 # --------------------------------------------------------------------------------------------- convolution

@@ -574,6 +574,33 @@ def check_attn_perf():
     return out
 
 
+def check_einsum():
+    """ops.einsum (one batched tcgen05 GEMM per einsum) on the GPT-MoE patterns: forward and gradient equations, both operand
+    majors, with and without the layout copies; vs torch.einsum in fp32.  Then throughput of the expert FC vs torch.einsum."""
+    from tepdist_b200 import ops
+    out = {}
+    torch.manual_seed(3)
+    G, S, E, C, M, H = 4, 256, 8, 32, 128, 256
+    t = {k: (torch.randn(*shape, device="cuda") * 0.5).to(torch.bfloat16) for k, shape in {
+        "GSEC": (G, S, E, C), "GSM": (G, S, M), "EGCM": (E, G, C, M), "EMH": (E, M, H), "EGCH": (E, G, C, H), "EHM": (E, H, M)}.items()}
+    for eq in ["GSEC,GSM->EGCM", "EGCM,EMH->EGCH", "EGCH,EHM->EGCM", "GSEC,EGCM->GSM", "EGCM,GSM->GSEC", "EGCH,EMH->EGCM",
+               "EGCM,EGCH->EMH", "EGCM,EHM->EGCH", "EGCH,EGCM->EHM"]:
+        ia, ib = eq.split("->")[0].split(",")
+        n0 = ops.launch_count()
+        got = ops.einsum(eq, t[ia], t[ib])
+        assert ops.launch_count() > n0, eq           # the tcgen05 GEMM ran, not the torch fallback
+        ref = torch.einsum(eq, t[ia].float(), t[ib].float())
+        out[eq] = _rel_err(got, ref)
+        assert out[eq] < 1e-2, (eq, out[eq])
+    # GPT-MoE expert FC1 at the reference shape per GPU under EP-8: 1 local expert x (8 groups x 256 slots) x 768 -> 6144
+    x = torch.randn(1, 8, 256, 768, device="cuda", dtype=torch.bfloat16)
+    w = torch.randn(1, 768, 6144, device="cuda", dtype=torch.bfloat16)
+    fl = 2.0 * 2048 * 768 * 6144
+    out["fc1_tflops"] = fl / _time_ms(lambda: ops.einsum("EGCM,EMH->EGCH", x, w)) / 1e9
+    out["fc1_torch_tflops"] = fl / _time_ms(lambda: torch.einsum("EGCM,EMH->EGCH", x, w)) / 1e9
+    return out
+
+
 CHECKS = {
     "gemm_layouts": check_gemm_layouts,
     "gemm_epilogues": check_gemm_epilogues,
@@ -584,6 +611,7 @@ CHECKS = {
     "attn_bwd": check_attn_bwd,
     "gemm_perf": check_gemm_perf,
     "conv": check_conv,
+    "einsum": check_einsum,
     "attn_d48": check_attn_d48,
     "attn_poly": check_attn_poly,
     "attn_fwd2": check_attn_fwd2,

@@ -393,3 +393,27 @@ def test_variable_store_fills_only_its_shard_bit_identically(monkeypatch):
                 oracle = shard_of(init_mod.init_tensor(n.attrs.get("init", {"kind": "constant", "value": 0.0}), full, 5, n.name),
                                   n.attrs, coords)
                 assert torch.equal(st.master_view(n.id), oracle.reshape(st.shape[n.id])), (n.name, coords)
+
+
+def test_einsum_lowering_to_batched_gemm_matches_torch_einsum():
+    """ops.einsum brings any batch / M / N / K index pattern to ONE [batch, M, K] x [batch, K, N] GEMM call (either operand
+    major, copies only when the memory order forces one): every GPT-MoE einsum (dispatch, expert FCs, combine) and the
+    gradient einsums the autodiff derives from them must equal torch.einsum.  (CPU: the GEMM is its fp32 reference path.)"""
+    import torch
+    from tepdist_b200 import ops
+    torch.manual_seed(0)
+    G, S, E, C, M, H = 2, 16, 4, 8, 24, 32
+    t = {"GSEC": torch.randn(G, S, E, C), "GSM": torch.randn(G, S, M), "EGCM": torch.randn(E, G, C, M), "EMH": torch.randn(E, M, H),
+         "EGCH": torch.randn(E, G, C, H), "EHM": torch.randn(E, H, M)}
+    eqs = ["GSEC,GSM->EGCM", "EGCM,EMH->EGCH", "EGCH,EHM->EGCM", "GSEC,EGCM->GSM",           # forward
+           "EGCM,GSM->GSEC", "GSEC,EGCM->GSM", "EGCH,EMH->EGCM", "EGCM,EGCH->EMH",           # vjps w.r.t. each operand
+           "EGCM,EHM->EGCH", "EGCH,EGCM->EHM", "GSM,EGCM->GSEC", "GSEC,GSM->EGCM"]
+    for eq in eqs:
+        ia, ib = eq.split("->")[0].split(",")
+        got = ops.einsum(eq, t[ia], t[ib], _force=True)
+        ref = torch.einsum(eq, t[ia], t[ib])
+        # (the GEMM entry point rounds its result to bf16 like the kernel does: compare in relative Frobenius norm)
+        assert got.shape == ref.shape and float((got.float() - ref).norm() / ref.norm()) < 1e-2, eq
+    # patterns the lowering does not cover fall back to torch.einsum
+    x = torch.randn(4, 8)
+    assert torch.allclose(ops.einsum("ab,ab->a", x, x, _force=True), (x * x).sum(1), atol=1e-5)
