@@ -62,6 +62,9 @@ def spmd_overrides() -> Dict[str, Any]:
     _take(o, "aux_affinity", "AUX_AFFINITY", "bool")
     _take(o, "forward_sub_graph_num", "FORWARD_SUB_GRAPH_NUM", "int")
     _take(o, "ilp_time_limit_s", "ILP_TIME_LIMIT", "float", 60.0)
+    import os
+    if os.environ.get("TEPDIST_COLL_LATENCY_BYTES") is not None:   # per-collective latency term of the SPMD cost (bytes of wire
+        o["collective_latency_bytes"] = float(os.environ["TEPDIST_COLL_LATENCY_BYTES"])   # time; 0 = byte counts only)
     return o
 
 

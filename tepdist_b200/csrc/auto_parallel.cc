@@ -239,7 +239,7 @@ EvalResult Evaluate(const EvalInput& in, const HwProfile& hw) {
   for (int s = 0; s < S; ++s) {
     double fl = s < (int)in.stage_flops.size() ? in.stage_flops[s] : 0.0;
     total_flops += fl;
-    const double t = fl / n / M / hw.flops;
+    const double t = fl / n / M / hw.flops * hw.ComputeSlowdown(in.rows_per_micro);
     f[s] = t / 3.0;
     b[s] = t * 2.0 / 3.0;
   }
@@ -253,7 +253,7 @@ EvalResult Evaluate(const EvalInput& in, const HwProfile& hw) {
     steady = std::max(steady, f[s] + b[s] + comm_mb / S);
   }
   r.total_duration = fill + drain + (M - 1) * steady + comm_mb / S;
-  r.compute_time = total_flops / (S * n) / hw.flops;
+  r.compute_time = total_flops / (S * n) / hw.flops * hw.ComputeSlowdown(in.rows_per_micro);
   r.comm_time = comm_mb * M / S;
   r.p2p_time = S > 1 ? 2.0 * (S - 1) * xfer : 0.0;
   r.gpu_efficiency = r.compute_time / r.total_duration;
@@ -397,9 +397,21 @@ ParallelPlan AutoParallelRun(const Graph& g, const AutoParallelOptions& opt) {
     }
     // gradient collectives overlap with backward on B200 (side stream); activation collectives are exposed
     ei.spmd_comm_bytes = spmd_comm * p.micro;
-    ei.exposed_comm_fraction = opt.hw.name == "reference_v100" ? 1.0 : 0.35;
+    ei.exposed_comm_fraction = opt.exposed_comm_fraction >= 0 ? opt.exposed_comm_fraction : opt.hw.ExposedCommFraction(p.spmd);
     ei.var_bytes = VarBytes(g);
     ei.act_bytes = ActBytes(g);
+    {   // rows one device works on per micro-batch: the sample inputs' leading extent (tokens = every element of an integer
+        // input; feature tensors: everything but the innermost dim), split over the SPMD group and the micro-batches
+      double rows = 0;
+      for (auto& n : g.nodes)
+        if (n.op == "input" && !n.outputs.empty()) {
+          const TensorType& t = n.outputs[0];
+          double r = (double)t.numel();
+          if (t.dtype != "i32" && t.dtype != "i64" && t.rank() > 1) r /= (double)t.dims.back();
+          rows = std::max(rows, r);
+        }
+      ei.rows_per_micro = rows / std::max(1, p.spmd) / std::max(1, p.micro);
+    }
     cand.eval = Evaluate(ei, opt.hw);
     cand.graph = std::move(cur);
     log << "[candidate] " << p.str() << " -> " << cand.eval.str() << "\n";

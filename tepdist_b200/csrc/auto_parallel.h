@@ -81,6 +81,7 @@ struct EvalInput {
   double cut_bytes = 0;                // per micro-batch across all boundaries
   double var_bytes = 0;                // variables + slots + grads, whole model
   double act_bytes = 0;                // activations stashed per micro-batch, whole model
+  double rows_per_micro = 0;           // GEMM rows (tokens / pixels) one device processes per micro-batch; 0 = unknown
 };
 EvalResult Evaluate(const EvalInput& in, const HwProfile& hw);
 
@@ -99,6 +100,7 @@ struct AutoParallelOptions {
   double unbalanced_ratio = 0.08;
   bool allow_pipeline = true;
   bool spmd_rule_mode = false;   // SPMD level by annotation propagation (batch split) instead of the cost-based planner
+  double exposed_comm_fraction = -1;   // evaluator: < 0 = the hardware profile's calibrated value for the SPMD group size
   HwProfile hw;
 };
 struct ParallelPlan {

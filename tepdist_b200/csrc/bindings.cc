@@ -171,6 +171,9 @@ PYBIND11_MODULE(_C, m) {
       .def_readwrite("link_bw", &HwProfile::link_bw)
       .def_readwrite("inter_node_bw", &HwProfile::inter_node_bw)
       .def_readwrite("coll_latency", &HwProfile::coll_latency)
+      .def_readwrite("small_batch_half_rows", &HwProfile::small_batch_half_rows)
+      .def("exposed_comm_fraction", &HwProfile::ExposedCommFraction)
+      .def("compute_slowdown", &HwProfile::ComputeSlowdown)
       .def_readwrite("mem_bytes", &HwProfile::mem_bytes);
 
   py::class_<SpmdOptions>(m, "SpmdOptions")
@@ -178,6 +181,7 @@ PYBIND11_MODULE(_C, m) {
       .def_readwrite("num", &SpmdOptions::num)
       .def_readwrite("var_mem_limit", &SpmdOptions::var_mem_limit)
       .def_readwrite("mem_split_min_rank", &SpmdOptions::mem_split_min_rank)
+      .def_readwrite("collective_latency_bytes", &SpmdOptions::collective_latency_bytes)
       .def_readwrite("cost_factor", &SpmdOptions::cost_factor)
       .def_readwrite("opt_level", &SpmdOptions::opt_level)
       .def_readwrite("ignore_annotation", &SpmdOptions::ignore_annotation)

@@ -19,6 +19,21 @@ struct HwProfile {
   double inter_node_bw = 5.0e10; // B/s (unused on one box)
   double coll_latency = 8e-6;    // s per collective launch/sync
   double mem_bytes = 180e9 * 0.9;
+  // Share of the SPMD collectives' wire time that is NOT hidden under compute, by group size: measured on this pool's B200s with
+  // bench.py's dry-comm subtraction (GPT-2 345M, batch 4 x 1024 per GPU, fused bucketed reduce-scatter + AdamW + all-gather on a
+  // side stream; profiles/README.md): exposed 0.45 / 1.44 / 2.22 ms of 1.38 / 2.07 / 2.42 ms of wire time at n = 2 / 4 / 8.
+  double ExposedCommFraction(int n) const {
+    if (name == "reference_v100") return 1.0;          // the reference issues every collective in-stream
+    if (n <= 2) return 0.33;
+    if (n <= 4) return 0.70;
+    return 0.90;
+  }
+  // Tensor-core work on few rows runs far below the sustained rate (tile-count quantisation on 148 SMs, per-kernel prologue /
+  // epilogue of ~10 us against ~4 us of MMAs): time = flops / rate * (1 + half_rows / rows).  half_rows = 4096 fits the two
+  // measurements we have for GPT-2 345M layers: 4096 rows per step at ~50 % of the sustained rate (17 ms data parallel) and
+  // 1024 rows per micro-batch 2.5x slower per row (42 ms, 2-stage pipeline x 8 micro-batches; profiles/README.md).
+  double small_batch_half_rows = 4096;
+  double ComputeSlowdown(double rows) const { return (rows > 0 && name != "reference_v100") ? 1.0 + small_batch_half_rows / rows : 1.0; }
   static HwProfile B200() { return HwProfile(); }
   static HwProfile ReferenceV100() {
     HwProfile h;

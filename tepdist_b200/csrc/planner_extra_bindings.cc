@@ -99,7 +99,8 @@ void BindPlannerExtra(py::module_& m) {
       .def_readwrite("spmd", &EvalInput::spmd).def_readwrite("spmd_comm_bytes", &EvalInput::spmd_comm_bytes)
       .def_readwrite("exposed_comm_fraction", &EvalInput::exposed_comm_fraction)
       .def_readwrite("stage_flops", &EvalInput::stage_flops).def_readwrite("cut_bytes", &EvalInput::cut_bytes)
-      .def_readwrite("var_bytes", &EvalInput::var_bytes).def_readwrite("act_bytes", &EvalInput::act_bytes);
+      .def_readwrite("var_bytes", &EvalInput::var_bytes).def_readwrite("act_bytes", &EvalInput::act_bytes)
+      .def_readwrite("rows_per_micro", &EvalInput::rows_per_micro);
   py::class_<EvalResult>(m, "EvalResult")
       .def_readonly("feasible", &EvalResult::feasible).def_readonly("total_duration", &EvalResult::total_duration)
       .def_readonly("compute_time", &EvalResult::compute_time).def_readonly("comm_time", &EvalResult::comm_time)
@@ -121,6 +122,7 @@ void BindPlannerExtra(py::module_& m) {
       .def_readwrite("unbalanced_ratio", &AutoParallelOptions::unbalanced_ratio)
       .def_readwrite("allow_pipeline", &AutoParallelOptions::allow_pipeline)
       .def_readwrite("spmd_rule_mode", &AutoParallelOptions::spmd_rule_mode)
+      .def_readwrite("exposed_comm_fraction", &AutoParallelOptions::exposed_comm_fraction)
       .def_readwrite("hw", &AutoParallelOptions::hw);
   py::class_<ParallelPlan>(m, "ParallelPlan")
       .def_readonly("proposal", &ParallelPlan::proposal).def_readonly("graph", &ParallelPlan::graph)

@@ -149,7 +149,22 @@ double EdgeCost(const Problem& p, const Edge& e, const Candidate& cp, const Cand
   if (e.operand >= 2 && from.is_split() && !(from == to) && p.g.nodes[e.prod].op == "state" &&
       p.g.nodes[e.cons].op.rfind("apply_", 0) == 0)
     return kInfCost;
-  return ReshardCost(from, to, e.bytes, p.opt.num, p.opt.cost_factor);
+  double cost = ReshardCost(from, to, e.bytes, p.opt.num, p.opt.cost_factor);
+  if (cost > 0 && cost < kInfCost) {
+    // a collective is not free below its byte count: launch + cross-GPU synchronisation (~8 us on NVSwitch = ~6 MB of wire
+    // time).  Without this term dozens of tiny LayerNorm-statistics / loss all-reduces look free next to one large one.
+    const Reshard kind = ClassifyReshard(from, to);
+    const bool launches = kind == Reshard::kAllReduce || kind == Reshard::kAllGather || kind == Reshard::kReduceScatter ||
+                          kind == Reshard::kAllToAll;
+    const std::string& po = p.g.nodes[e.prod].op;
+    const std::string& co = p.g.nodes[e.cons].op;
+    const bool bucketed = po == "parameter" || po == "state" || po.rfind("apply_", 0) == 0 || co.rfind("apply_", 0) == 0;
+    if (launches && !bucketed) {
+      const double lat = p.opt.collective_latency_bytes >= 0 ? p.opt.collective_latency_bytes : p.opt.hw.coll_latency * p.opt.hw.link_bw;
+      cost += lat;
+    }
+  }
+  return cost;
 }
 
 // Solve the sub-problem over `members`; `fixed` pins nodes (members or foreign endpoints) to one strategy of

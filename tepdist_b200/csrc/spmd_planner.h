@@ -33,6 +33,10 @@ struct SpmdOptions {
   double replicate_penalty = 1e-3;   // per byte of activation computed redundantly (keeps free splits split)
   double memory_weight = 0.0;        // per byte of variable state stored per device (0: memory only via VAR_MEM_LIMIT)
   double shard_storage_penalty = 1e-6;  // tie-break: keep variables stored whole unless sharding saves traffic
+  double collective_latency_bytes = -1; // per-collective launch + sync latency, in bytes of wire time, added to every edge whose
+                                        // re-layout launches a collective in the activation path (< 0: hw.coll_latency *
+                                        // hw.link_bw; 0 disables).  Gradient / parameter collectives are bucketed by the
+                                        // runtime (a handful of launches per step whatever the number of variables) and pay none.
   HwProfile hw;
 };
 

@@ -90,7 +90,9 @@ def test_long_context_plan_batch1_head_seq_all_to_all(tmp_path):
     token-wise over the sequence, resharding between the two with all-to-all (the Ulysses / Megatron-SP pattern emerges
     from the generic split->split' reshard; reference: 'token parallel' README.md:22)."""
     ref = _single("gpt2b1:auto")
-    got = _run("gpt2b1:auto", 2, tmp_path)
+    # (toy sizes: the per-collective latency term would outweigh every byte count of a 128-token sequence; the structural
+    # property -- heads <-> sequence resharding by all-to-all -- is a byte-cost decision, so price bytes only here)
+    got = _run("gpt2b1:auto", 2, tmp_path, extra_env={"TEPDIST_COLL_LATENCY_BYTES": "0"})
     assert got["collectives"].get("all_to_all", 0) >= 2, got
     for a, b in zip(got["losses"], ref["losses"]):
         assert abs(a - b) <= 2e-4 * max(1.0, abs(b)), (got, ref)
