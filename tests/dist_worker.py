@@ -217,6 +217,9 @@ def case_opts(strategy):
     from tepdist_b200.api import Trainer
     from test_optimizers_cpu import CASES, build_mlp
     out = {}
+    # (a toy MLP: price bytes only so the planner still splits it Megatron-style -- with the per-collective latency term it is,
+    # correctly, data parallel, and no update would act on a stored shard)
+    os.environ["TEPDIST_COLL_LATENCY_BYTES"] = "0"
     for case in ("momentum", "lamb", "adafactor", "adafactor_relative_step", "sm3", "sm3_momentum"):
         hp = CASES[case][0]
         tr = Trainer(build_mlp(case.split("_")[0], **hp), strategy=strategy, device=_dev(), use_cuda_graph=False, seed=5)
@@ -230,6 +233,7 @@ def case_opts(strategy):
                     src = g.nodes[n.inputs[0].node]
                     sharded += int(src.op == "dynamic_slice" or "shard_dims" in src.attrs)
         out[case] = {"losses": losses, "sharded_updates": sharded}
+    del os.environ["TEPDIST_COLL_LATENCY_BYTES"]
     return {"losses": [], "parallelism": strategy, "collectives": None, "opts": out}
 
 
