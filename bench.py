@@ -65,6 +65,8 @@ def main():
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--no-exposed", action="store_true", help="skip the exposed-communication measurement (N > 1)")
     ap.add_argument("--no-tp", action="store_true", help="skip the tensor-parallel arm (N > 1)")
+    ap.add_argument("--no-library-arm", action="store_true",
+                    help="skip the same-box library comparator (cuBLAS / SDPA / per-tensor NCCL step, bench/torch_baseline.py)")
     args = ap.parse_args()
 
     if args.impl == "reference":
@@ -237,10 +239,37 @@ def main():
         pp_meas = {"bubble_per_stage": {str(k): round(sum(v) / len(v), 4) for k, v in sorted(per_stage.items())},
                    "cuda_graph": bool(w.use_graph), "graphs_captured": w.graph_stats["captured"], "slots": w.num_slots}
 
-    t = torch.tensor([ms, ms_e2e, ms_dry, tp_ms["fused"], tp_ms["nccl"]], dtype=torch.float64, device=dev)
+    # ---------------- same-box comparator: the library step (cuBLAS GEMMs, SDPA attention, torch fused AdamW, one in-stream
+    # ncclAllReduce per gradient tensor, whole step in a CUDA graph; none of this repository's kernels) timed in THIS process on
+    # THIS box, so the ratio does not depend on box-to-box variance (the reference itself cannot be installed: DESIGN.md)
+    ms_lib = 0.0
+    lib_err = None
+    if not library and not is_pp and not args.no_library_arm and cfg.name == "gpt2-345M":
+        try:
+            import importlib.util
+            spec = importlib.util.spec_from_file_location(
+                "torch_baseline", os.path.join(os.path.dirname(os.path.abspath(__file__)), "bench", "torch_baseline.py"))
+            mod = importlib.util.module_from_spec(spec)
+            spec.loader.exec_module(mod)
+            lt = mod.LibraryTrainer(cfg, dev, world, use_graph=not args.no_graph)
+            for i in range(W):
+                lt.step(dev_tok[i % nbuf], dev_lab[i % nbuf])
+            barrier()
+            l0, l1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            l0.record()
+            for i in range(K):
+                lt.step(dev_tok[i % nbuf], dev_lab[i % nbuf])
+            l1.record()
+            barrier()
+            ms_lib = l0.elapsed_time(l1)
+            del lt
+        except Exception as e:  # noqa: BLE001
+            lib_err = f"{type(e).__name__}: {e}"[:300]
+
+    t = torch.tensor([ms, ms_e2e, ms_dry, tp_ms["fused"], tp_ms["nccl"], ms_lib], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms, ms_e2e, ms_dry, tp_fused_ms, tp_nccl_ms = t.tolist()
+    ms, ms_e2e, ms_dry, tp_fused_ms, tp_nccl_ms, ms_lib = t.tolist()
     if rank == 0:
         tokens = B * S * world * K
         value = tokens / (ms / 1e3)
@@ -272,6 +301,11 @@ def main():
             "final_loss": final_loss,
             "clocks": summarize_clocks(samples),
         }
+        if ms_lib > 0:
+            out["library_arm"] = {"ms_per_step": ms_lib / K, "tokens_per_s": tokens / (ms_lib / 1e3), "ours_over_library": ms_lib / ms,
+                                  "what": "same box, same process: torch cuBLAS / SDPA / fused AdamW + per-tensor in-stream NCCL all-reduce, CUDA graph"}
+        elif lib_err:
+            out["library_arm"] = {"error": lib_err}
         if is_pp:
             pi = trainer.plan_info
             out["pipeline"] = {"stages": pi.get("stages"), "micro_batches": pi.get("micro"), "spmd": pi.get("spmd"),

@@ -17,6 +17,9 @@
 #include "sm100_ptx.cuh"
 #include "launch.cuh"
 #include <stdio.h>
+#include <map>
+#include <mutex>
+#include <utility>
 
 using namespace sm100;
 
@@ -617,19 +620,32 @@ extern "C" int tepd_gemm2_bf16(const void* A, const void* B, void* D, void* D2, 
     long long per = (iters + pairs - 1) / pairs;
     if (per < 4) per = 4;
     constexpr int kSlots = 160;
-    static float* ws[16] = {nullptr};
-    static unsigned* flags[16] = {nullptr};
+    // one workspace + flag array per (device, stream): two stream-K GEMMs on different streams (communication overlap runs
+    // GEMMs on side streams) must not share partial tiles or flags.  First use of a stream allocates (outside CUDA-graph
+    // capture: the executor warms every stream up eagerly).
+    struct SkWs { float* ws; unsigned* flags; };
+    static std::map<std::pair<int, cudaStream_t>, SkWs> pool;
+    static std::mutex pool_mu;
     int dev = 0;
     cudaGetDevice(&dev);
-    if (num_sms > kSlots || dev >= 16) return -6;
-    if (ws[dev] == nullptr) {   // first use must happen outside CUDA-graph capture (the executor warms up eagerly)
-      const size_t bytes = (size_t)kSlots * BM * BN * sizeof(float);
-      if (cudaMalloc(&ws[dev], bytes) != cudaSuccess) return -7;
-      if (cudaMalloc(&flags[dev], kSlots * sizeof(unsigned)) != cudaSuccess) return -7;
-      cudaMemset(flags[dev], 0, kSlots * sizeof(unsigned));
-      cudaDeviceSynchronize();
+    if (num_sms > kSlots) return -6;
+    SkWs w;
+    {
+      std::lock_guard<std::mutex> lk(pool_mu);
+      auto key = std::make_pair(dev, reinterpret_cast<cudaStream_t>(stream));
+      auto it = pool.find(key);
+      if (it == pool.end()) {
+        const size_t bytes = (size_t)kSlots * BM * BN * sizeof(float);
+        SkWs nw{nullptr, nullptr};
+        if (cudaMalloc(&nw.ws, bytes) != cudaSuccess) return -7;
+        if (cudaMalloc(&nw.flags, kSlots * sizeof(unsigned)) != cudaSuccess) return -7;
+        cudaMemset(nw.flags, 0, kSlots * sizeof(unsigned));
+        cudaDeviceSynchronize();
+        it = pool.emplace(key, nw).first;
+      }
+      w = it->second;
     }
-    p.stream_k = (int)per; p.sk_ws = ws[dev]; p.sk_flag = flags[dev];
+    p.stream_k = (int)per; p.sk_ws = w.ws; p.sk_flag = w.flags;
     clusters = (int)((iters + per - 1) / per);
   }
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);

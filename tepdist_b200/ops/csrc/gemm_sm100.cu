@@ -12,6 +12,9 @@
 #include "sm100_ptx.cuh"
 #include "launch.cuh"
 #include <stdio.h>
+#include <map>
+#include <mutex>
+#include <utility>
 
 using namespace sm100;
 
@@ -627,20 +630,31 @@ extern "C" int tepd_gemm_bf16(const void* A, const void* B, void* D, const void*
       // allocated once; flags are reset by their consumer.  GEMMs of one device must not run concurrently on two
       // streams in this mode.
       constexpr int kSlots = 160;
-      static float* ws[16] = {nullptr};
-      static unsigned* cnt[16] = {nullptr};
+      // one workspace + flag array per (device, stream): see gemm2_sm100.cu
+      struct SkWs { float* ws; unsigned* cnt; };
+      static std::map<std::pair<int, void*>, SkWs> pool;
+      static std::mutex pool_mu;
       int dev = 0;
       cudaGetDevice(&dev);
-      if (num_sms + 1 > kSlots || dev >= 16) return -6;
-      if (ws[dev] == nullptr) {
-        const size_t bytes = (size_t)kSlots * BLOCK_M * 256 * sizeof(float);
-        if (cudaMalloc(&ws[dev], bytes) != cudaSuccess) return -7;
-        if (cudaMalloc(&cnt[dev], kSlots * sizeof(unsigned)) != cudaSuccess) return -7;
-        cudaMemset(ws[dev], 0, bytes);
-        cudaMemset(cnt[dev], 0, kSlots * sizeof(unsigned));
-        cudaDeviceSynchronize();
+      if (num_sms + 1 > kSlots) return -6;
+      SkWs w;
+      {
+        std::lock_guard<std::mutex> lk(pool_mu);
+        auto key = std::make_pair(dev, stream);
+        auto it = pool.find(key);
+        if (it == pool.end()) {
+          const size_t bytes = (size_t)kSlots * BLOCK_M * 256 * sizeof(float);
+          SkWs nw{nullptr, nullptr};
+          if (cudaMalloc(&nw.ws, bytes) != cudaSuccess) return -7;
+          if (cudaMalloc(&nw.cnt, kSlots * sizeof(unsigned)) != cudaSuccess) return -7;
+          cudaMemset(nw.ws, 0, bytes);
+          cudaMemset(nw.cnt, 0, kSlots * sizeof(unsigned));
+          cudaDeviceSynchronize();
+          it = pool.emplace(key, nw).first;
+        }
+        w = it->second;
       }
-      p.sk_ws = ws[dev]; p.sk_cnt = cnt[dev];
+      p.sk_ws = w.ws; p.sk_cnt = w.cnt;
     }
   }
   if (split_k < 1) split_k = 1;

@@ -297,12 +297,14 @@ class FusedShardedOptimizer:
     still costs every GPU its full gradient buffer in egress, so NVLS only pays for the all-gather half; with a bf16 gradient
     wire it is 55 us.  Default: unicast P2P loads / stores (IPC or VMM mappings alike)."""
 
-    def __init__(self, grad_buf: SymmetricBuffer, param_buf: SymmetricBuffer, group=None):
+    def __init__(self, grad_buf: SymmetricBuffer, param_buf: SymmetricBuffer, group=None, grad16_buf: Optional[SymmetricBuffer] = None):
         import os
         self.g, self.p = grad_buf, param_buf
+        self.g16 = grad16_buf          # bf16 staging copy of the gradients (bf16 wire; implies the NVLS kernel)
         self.world, self.rank = grad_buf.world, grad_buf.rank
         self.mc: Optional[McContext] = None
-        if (grad_buf.mc_ptr is not None and param_buf.mc_ptr is not None and os.environ.get("TEPDIST_DP_MC", "0") == "1"):
+        if (grad_buf.mc_ptr is not None and param_buf.mc_ptr is not None
+                and (os.environ.get("TEPDIST_DP_MC", "0") == "1" or grad16_buf is not None)):
             self.mc = McContext(group)
             self._barrier = None
         else:
@@ -323,9 +325,11 @@ class FusedShardedOptimizer:
         """local_grad: the gradient of [begin, end) is already complete on every rank (replicated computation): only the
         update is sharded -- the owner reads its local gradient and still stores the new bf16 values to every peer."""
         if self.mc is not None and not self.dry and not local_grad and begin % 8 == 0 and end % 8 == 0:
-            rc = self.g.lib.tepd_mc_rs_adamw_ag(self.g.mc_ptr, self.p.mc_ptr, master.data_ptr(), m.data_ptr(), v.data_ptr(),
-                                                begin, end, n_decay, beta1, beta2, eps, wd, hyper.data_ptr(), 0,
-                                                self.mc_ctas or ctas, torch.cuda.current_stream().cuda_stream)
+            src = self.g16 if self.g16 is not None else self.g
+            rc = self.g.lib.tepd_mc_rs_adamw_ag(src.mc_ptr, self.p.mc_ptr, master.data_ptr(), m.data_ptr(), v.data_ptr(),
+                                                begin, end, n_decay, beta1, beta2, eps, wd, hyper.data_ptr(),
+                                                int(self.g16 is not None), self.mc_ctas or ctas,
+                                                torch.cuda.current_stream().cuda_stream)
             if rc:
                 raise RuntimeError(f"mc_rs_adamw_ag failed ({rc})")
             ops._count()

@@ -131,6 +131,11 @@ class VariableStore:
         c.copy_(self.compute)
         self.grad, self.compute = g, c
         self.symm_grad, self.symm_param = gb, pb
+        # bf16 gradient wire (TEPDIST_GRAD_WIRE=bf16, the reference's FP16_COMM idea on the NVLS path): a bf16 staging copy of the
+        # gradient buffer that the switch reduces with fp32 accumulation; half the NVLink bytes of the fp32 wire
+        self.symm_grad16 = None
+        if os.environ.get("TEPDIST_GRAD_WIRE", "f32") == "bf16" and gb.mc_ptr is not None:
+            self.symm_grad16 = SymmetricBuffer(self.total * 2, group)
 
     def _flat_slot(self, n) -> bool:
         """First / second moment slots with their variable's shape live in the flat m / v buffers."""
@@ -518,7 +523,7 @@ class Executor:
             pg = self.collective.mesh.group(fz["level"])
             try:
                 st.make_symmetric(pg)
-                self.flat_zero["fused"] = FusedShardedOptimizer(st.symm_grad, st.symm_param, pg)
+                self.flat_zero["fused"] = FusedShardedOptimizer(st.symm_grad, st.symm_param, pg, grad16_buf=st.symm_grad16)
                 self.flat_zero["fused"].dry = self.dry_comm
             except RuntimeError as e:   # e.g. CUDA IPC unavailable in this container: keep the NCCL path, loudly
                 import warnings
@@ -544,6 +549,8 @@ class Executor:
             chunk = (e0 - s0) // n
             last = len(pending) == len(fz["buckets"]) - 1
             with torch.cuda.stream(cs):
+                if fo.g16 is not None and not fo.dry:      # bf16 wire: stage this bucket's gradients (all of it: peers reduce their chunks of it)
+                    ops.cast_f32_bf16(st.grad[s0:e0], fo.g16.tensor(torch.bfloat16, st.total)[s0:e0])
                 fo.barrier()
                 fo.step(st.master, st.m, st.v, s0 + r * chunk, s0 + (r + 1) * chunk, st.n_decay, self.hyper,
                         o.get("beta1", 0.9), o.get("beta2", 0.999), o.get("eps", 1e-8), o.get("weight_decay", 0.0),
