@@ -1462,7 +1462,8 @@ class Executor:
         if op == "einsum":
             # own batched tcgen05 GEMM for bf16 operands on the GPU (expert FFNs, dispatch / combine and their gradients);
             # torch.einsum for the CPU oracle and for patterns outside the kernel's alignment rules
-            if ins[0].is_cuda and ins[0].dtype == torch.bfloat16 and ins[1].dtype == torch.bfloat16:
+            if (ins[0].is_cuda and ins[0].dtype == torch.bfloat16 and ins[1].dtype == torch.bfloat16
+                    and os.environ.get("TEPDIST_EINSUM", "own") != "torch"):
                 return [ops.einsum(a["eq"], ins[0], ins[1])]
             return [torch.einsum(a["eq"], ins[0], ins[1])]
         # convolutions: own path = NHWC im2col / col2im kernels + tcgen05 GEMMs (ops/csrc/conv_sm100.cu); cuDNN through torch
