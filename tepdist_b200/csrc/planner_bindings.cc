@@ -24,6 +24,7 @@ void BindPlanner(py::module_& m) {
     Graph out = SpmdTransform(g, plan, level, num, &st);
     return py::make_tuple(out, st);
   });
+  m.def("plan_flat_buckets", &PlanFlatBuckets);
   m.def("combine_gradient_collectives", [](Graph& g, int64_t bucket_bytes, int max_per_bucket) {
     return CombineGradientCollectives(&g, bucket_bytes, max_per_bucket);
   }, py::arg("graph"), py::arg("bucket_bytes"), py::arg("max_per_bucket") = 1 << 30);

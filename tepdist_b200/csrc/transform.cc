@@ -261,6 +261,18 @@ int CombineGradientCollectives(Graph* g, int64_t bucket_bytes, int max_per_bucke
   return any ? bucket + 1 : 0;
 }
 
+std::vector<int64_t> PlanFlatBuckets(const std::vector<int64_t>& offsets, int64_t end, int64_t gran, int64_t first, int64_t cap) {
+  std::vector<int64_t> bounds = {0};
+  for (size_t i = 1; i < offsets.size(); ++i) {
+    const int64_t off = offsets[i];
+    const int shift = (int)std::min<size_t>(bounds.size() - 1, 16);
+    const int64_t want = std::min(cap, first << shift);
+    if (off - bounds.back() >= want && gran > 0 && off % gran == 0) bounds.push_back(off);
+  }
+  bounds.push_back(end);
+  return bounds;
+}
+
 int LivenessOptimize(Graph* g, int64_t min_bytes) {
   // B6 (reference hlo_liveness_optimizer.cc:26-54): a converted copy of a variable that has several users -- typically one
   // in the forward and one in the backward pass -- stays alive from its first to its last user, i.e. for most of the step.

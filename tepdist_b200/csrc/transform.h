@@ -36,6 +36,15 @@ int CombineGradientCollectives(Graph* g, int64_t bucket_bytes, int max_per_bucke
 
 // B6: give every user of cast(parameter) its own cast so the casted copy is not live across the step.
 // B6: per-user copies of convert(parameter) results of at least `min_bytes` (see transform.cc).  Renumbers nodes.
+// B7, storage-order variant -- the one the runtime executes: bucket boundaries over the FLAT gradient buffer (variables in
+// storage order = layer order; `offsets` are the element offsets of the regular variables, ascending, all < end).  Sizes are
+// graded: the first bucket is `first` elements and every following one doubles up to `cap`, because the variables at the
+// front of the buffer belong to the first layers, whose gradients the backward pass produces LAST -- whatever is still in flight
+// when backward ends is exposed, so the buckets that become ready last are the small ones.  A boundary is only placed at a
+// variable start that is a multiple of `gran` (= group size x alignment: every rank's chunk of a bucket stays aligned).
+// Returns the boundaries [0, b1, ..., end].
+std::vector<int64_t> PlanFlatBuckets(const std::vector<int64_t>& offsets, int64_t end, int64_t gran, int64_t first, int64_t cap);
+
 int LivenessOptimize(Graph* g, int64_t min_bytes = 1 << 20);
 
 }  // namespace tepdist

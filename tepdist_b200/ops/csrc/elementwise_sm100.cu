@@ -5,6 +5,7 @@
 #include <cuda_bf16.h>
 #include <stdint.h>
 #include "launch.cuh"
+#include <cooperative_groups.h>
 
 namespace {
 
@@ -114,7 +115,7 @@ __global__ void __launch_bounds__(256) layernorm_fwd_kernel(const bf16* __restri
 // approach HBM bandwidth), reduced across the 8 warps at the end and added (fp32 red) to the gradient buffers.
 // Optional dres: fused residual-stream gradient add (dx_total = dx + dres).
 template <int MAXV>
-__global__ void __launch_bounds__(256, (MAXV <= 4) ? 3 : 1) layernorm_bwd_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ x,
+__global__ void __cluster_dims__(4, 1, 1) __launch_bounds__(256, (MAXV <= 4) ? 3 : 1) layernorm_bwd_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ x,
                                                            const float* __restrict__ gamma,
                                                            const float* __restrict__ mean_in,
                                                            const float* __restrict__ rstd_in, bf16* __restrict__ dx,
@@ -193,13 +194,34 @@ __global__ void __launch_bounds__(256, (MAXV <= 4) ? 3 : 1) layernorm_bwd_kernel
     }
   }
   __syncthreads();
+  // CTA-level sums of the 8 per-warp rows, written back into warp 0's rows (column c is touched by one thread only)
   for (int c = threadIdx.x; c < C; c += 256) {
     float sg = 0.f, sb = 0.f;
 #pragma unroll
     for (int w = 0; w < 8; ++w) { sg += red[(size_t)w * C + c]; sb += red[(size_t)(8 + w) * C + c]; }
+    red[c] = sg;
+    red[(size_t)8 * C + c] = sb;
+  }
+  // cluster-level reduction through distributed shared memory before the global atomics: the 2 * C gradient words live in
+  // 2 * C / 32 cache lines, and with one atomic per column per CTA (444 CTAs) every one of those lines took ~14 K serialized
+  // L2 atomics -- the kernel ran at 12 % of DRAM bandwidth.  CTA r of a 4-CTA cluster sums a quarter of the columns over
+  // the 4 CTAs' rows and issues the atomics for them: 4x fewer atomics, same arithmetic.
+  namespace cg = cooperative_groups;
+  cg::cluster_group cluster = cg::this_cluster();
+  cluster.sync();
+  const unsigned nb = cluster.num_blocks(), r = cluster.block_rank();
+  const int c0 = (int)((long long)C * r / nb), c1 = (int)((long long)C * (r + 1) / nb);
+  for (int c = c0 + threadIdx.x; c < c1; c += 256) {
+    float sg = 0.f, sb = 0.f;
+    for (unsigned k = 0; k < nb; ++k) {
+      const float* rem = cluster.map_shared_rank(red, k);
+      sg += rem[c];
+      sb += rem[(size_t)8 * C + c];
+    }
     atomicAdd(dgamma + c, sg);
     atomicAdd(dbeta + c, sb);
   }
+  cluster.sync();   // peers may still be reading this CTA's rows
 }
 
 // ------------------------------------------------------------------ GELU (tanh form, GPT-2)
@@ -595,6 +617,7 @@ extern "C" int tepd_layernorm_bwd(const void* dy, const void* x, const void* gam
   if (C % 8 || C > 2048) return -2;
   int grid = 148 * 3;
   if (grid > (rows + 7) / 8) grid = (rows + 7) / 8;
+  grid = (grid + 3) / 4 * 4;          // whole 4-CTA clusters (a CTA without rows still takes part in the cluster reduction)
   size_t smem = (size_t)16 * C * sizeof(float);
 #define LN_BWD(MV)                                                                                          \
   {                                                                                                         \

@@ -25,8 +25,10 @@ from ..ir import COLLECTIVE_OPS, SOURCE_OPS, Graph, Node, TensorType, Value
 from ..utils.init import init_tensor
 
 # tensor-parallel plans: run `linear -> all_reduce [-> + bias] [-> + residual]` as GEMM -> all-reduce over peer memory
-# (parallel/symm.py GemmAllReduce) instead of cuBLAS-free GEMM + NCCL.  Opt-in until validated on multi-GPU hardware.
-TP_FUSED = os.environ.get("TEPDIST_TP_FUSED", "0") == "1"
+# (parallel/symm.py GemmAllReduceMC: GEMM into a multicast-bound buffer + ONE multimem reduction kernel with bias / residual
+# fused) instead of GEMM + NCCL + separate adds.  Default in comm = "fused" mode (validated on 2 / 4 / 8 B200: 1.10x / 1.25x /
+# 1.51x the NCCL arm of the same plan, profiles/round2); TEPDIST_TP_FUSED=0 or comm = "nccl" selects the library collectives.
+TP_FUSED = os.environ.get("TEPDIST_TP_FUSED", "1") == "1"
 # test hook: a factory (M, N, group, barrier) -> object with new_output() / __call__(x, w, out, bias, residual, b_mn) that
 # stands in for parallel.symm.GemmAllReduce, so the executor-side chain fusion can be exercised on CPU (gloo) where the
 # peer-memory kernels cannot run
@@ -474,12 +476,9 @@ class Executor:
         # are produced LAST by the backward pass -- whatever is still in flight when backward ends is exposed, so the
         # buckets that become ready last are small (4M elements, doubling up to bucket_elems)
         first = int(self.opt.get("first_bucket_elems", os.environ.get("TEPDIST_FIRST_BUCKET", 4 * 1024 * 1024)))
-        bounds = [0]
-        for off, p in offs[1:]:
-            want = min(bucket_elems, first << min(len(bounds) - 1, 16))
-            if off - bounds[-1] >= want and off % gran == 0:
-                bounds.append(off)
-        bounds.append(end)
+        from .. import _C
+        # (the bucket policy lives in the C++ core next to the gradient-collective combiner: csrc/transform.cc PlanFlatBuckets)
+        bounds = list(_C.plan_flat_buckets([int(off) for off, _ in offs], int(end), int(gran), int(first), int(bucket_elems)))
         buckets = [(bounds[i], bounds[i + 1]) for i in range(len(bounds) - 1)]
         binding = {k: v for k, v in fz["binding"].items()}
         regular_apply = set(fz["regular_apply"])
@@ -1101,8 +1100,17 @@ class Executor:
             from ..parallel.symm import GemmAllReduce, GemmAllReduceMC, McContext, SymmBarrier, symm_backend
         self._tp_ops: Dict[Tuple[int, int, int], Any] = {}
         bar: Dict[int, Any] = {}
-        for lid, info in self.tp_fuse.items():
+        for lid, info in list(self.tp_fuse.items()):
             key = (info["level"], info["M"], info["N"])
+            if TP_FUSED_IMPL is None and key not in self._tp_ops:
+                # without a multicast-bound group (no NVSwitch multicast / IPC fallback) the chain stays on NCCL: the unicast slot
+                # variant (GemmAllReduce) is kept for experiments only (TEPDIST_TP_UNICAST=1), it has not beaten NCCL + cuBLAS
+                pg0 = mesh.group(info["level"])
+                mc_ok = (os.environ.get("TEPDIST_TP_MC", "1") == "1" and symm_backend(pg0) == "vmm"
+                         and (info["M"] * info["N"]) % (8 * info["num"]) == 0)
+                if not mc_ok and os.environ.get("TEPDIST_TP_UNICAST", "0") != "1":
+                    del self.tp_fuse[lid]
+                    continue
             if key not in self._tp_ops:
                 pg = mesh.group(info["level"])
                 # NVLS (multicast) version when the group's symmetric memory is multicast-bound; unicast slots otherwise
