@@ -620,30 +620,37 @@ extern "C" int tepd_gemm2_bf16(const void* A, const void* B, void* D, void* D2, 
     long long per = (iters + pairs - 1) / pairs;
     if (per < 4) per = 4;
     constexpr int kSlots = 160;
-    // one workspace + flag array per (device, stream): two stream-K GEMMs on different streams (communication overlap runs
-    // GEMMs on side streams) must not share partial tiles or flags.  First use of a stream allocates (outside CUDA-graph
-    // capture: the executor warms every stream up eagerly).
+    // Workspaces + flag arrays: a pool of kPool per device, ALL allocated at the first stream-K call of the device (the
+    // executor's eager warm-up step, i.e. outside CUDA-graph capture); every stream is bound to one of them in order of first
+    // appearance (binding allocates nothing, so it may happen during capture -- the capture stream differs from the warm-up
+    // stream).  Two stream-K GEMMs running concurrently on different streams (communication overlap uses side streams) thus
+    // never share partial tiles or flags, for up to kPool concurrently active streams per device.
+    constexpr int kPool = 4;
     struct SkWs { float* ws; unsigned* flags; };
-    static std::map<std::pair<int, cudaStream_t>, SkWs> pool;
+    struct DevPool { bool ready = false; SkWs w[kPool]; std::map<cudaStream_t, int> bound; int next = 0; };
+    static DevPool pools[16];
     static std::mutex pool_mu;
     int dev = 0;
     cudaGetDevice(&dev);
-    if (num_sms > kSlots) return -6;
+    if (num_sms > kSlots || dev >= 16) return -6;
     SkWs w;
     {
       std::lock_guard<std::mutex> lk(pool_mu);
-      auto key = std::make_pair(dev, reinterpret_cast<cudaStream_t>(stream));
-      auto it = pool.find(key);
-      if (it == pool.end()) {
+      DevPool& dp = pools[dev];
+      if (!dp.ready) {
         const size_t bytes = (size_t)kSlots * BM * BN * sizeof(float);
-        SkWs nw{nullptr, nullptr};
-        if (cudaMalloc(&nw.ws, bytes) != cudaSuccess) return -7;
-        if (cudaMalloc(&nw.flags, kSlots * sizeof(unsigned)) != cudaSuccess) return -7;
-        cudaMemset(nw.flags, 0, kSlots * sizeof(unsigned));
+        for (int i = 0; i < kPool; ++i) {
+          if (cudaMalloc(&dp.w[i].ws, bytes) != cudaSuccess) return -7;
+          if (cudaMalloc(&dp.w[i].flags, kSlots * sizeof(unsigned)) != cudaSuccess) return -7;
+          cudaMemset(dp.w[i].flags, 0, kSlots * sizeof(unsigned));
+        }
         cudaDeviceSynchronize();
-        it = pool.emplace(key, nw).first;
+        dp.ready = true;
       }
-      w = it->second;
+      cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+      auto it = dp.bound.find(st);
+      if (it == dp.bound.end()) it = dp.bound.emplace(st, dp.next++ % kPool).first;
+      w = dp.w[it->second];
     }
     p.stream_k = (int)per; p.sk_ws = w.ws; p.sk_flag = w.flags;
     clusters = (int)((iters + per - 1) / per);

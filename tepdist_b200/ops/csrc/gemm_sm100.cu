@@ -630,29 +630,34 @@ extern "C" int tepd_gemm_bf16(const void* A, const void* B, void* D, const void*
       // allocated once; flags are reset by their consumer.  GEMMs of one device must not run concurrently on two
       // streams in this mode.
       constexpr int kSlots = 160;
-      // one workspace + flag array per (device, stream): see gemm2_sm100.cu
+      // pool of workspaces per device, all allocated at the first call (outside capture); streams are bound to one of them
+      // in order of first appearance: see gemm2_sm100.cu
+      constexpr int kPool = 4;
       struct SkWs { float* ws; unsigned* cnt; };
-      static std::map<std::pair<int, void*>, SkWs> pool;
+      struct DevPool { bool ready = false; SkWs w[kPool]; std::map<void*, int> bound; int next = 0; };
+      static DevPool pools[16];
       static std::mutex pool_mu;
       int dev = 0;
       cudaGetDevice(&dev);
-      if (num_sms + 1 > kSlots) return -6;
+      if (num_sms + 1 > kSlots || dev >= 16) return -6;
       SkWs w;
       {
         std::lock_guard<std::mutex> lk(pool_mu);
-        auto key = std::make_pair(dev, stream);
-        auto it = pool.find(key);
-        if (it == pool.end()) {
+        DevPool& dp = pools[dev];
+        if (!dp.ready) {
           const size_t bytes = (size_t)kSlots * BLOCK_M * 256 * sizeof(float);
-          SkWs nw{nullptr, nullptr};
-          if (cudaMalloc(&nw.ws, bytes) != cudaSuccess) return -7;
-          if (cudaMalloc(&nw.cnt, kSlots * sizeof(unsigned)) != cudaSuccess) return -7;
-          cudaMemset(nw.ws, 0, bytes);
-          cudaMemset(nw.cnt, 0, kSlots * sizeof(unsigned));
+          for (int i = 0; i < kPool; ++i) {
+            if (cudaMalloc(&dp.w[i].ws, bytes) != cudaSuccess) return -7;
+            if (cudaMalloc(&dp.w[i].cnt, kSlots * sizeof(unsigned)) != cudaSuccess) return -7;
+            cudaMemset(dp.w[i].ws, 0, bytes);
+            cudaMemset(dp.w[i].cnt, 0, kSlots * sizeof(unsigned));
+          }
           cudaDeviceSynchronize();
-          it = pool.emplace(key, nw).first;
+          dp.ready = true;
         }
-        w = it->second;
+        auto it = dp.bound.find(stream);
+        if (it == dp.bound.end()) it = dp.bound.emplace(stream, dp.next++ % kPool).first;
+        w = dp.w[it->second];
       }
       p.sk_ws = w.ws; p.sk_cnt = w.cnt;
     }
