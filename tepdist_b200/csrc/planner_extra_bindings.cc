@@ -56,7 +56,24 @@ void BindPlannerExtra(py::module_& m) {
   py::class_<StagePlanResult>(m, "StagePlanResult")
       .def_readonly("sketch_stage", &StagePlanResult::sketch_stage).def_readonly("cut_bytes", &StagePlanResult::cut_bytes)
       .def_readonly("stage_flops", &StagePlanResult::stage_flops).def_readonly("method", &StagePlanResult::method)
-      .def_readonly("optimal", &StagePlanResult::optimal).def_readonly("seconds", &StagePlanResult::seconds);
+      .def_readonly("optimal", &StagePlanResult::optimal).def_readonly("seconds", &StagePlanResult::seconds)
+      .def_readonly("backward_stage", &StagePlanResult::backward_stage).def_readonly("backward_method", &StagePlanResult::backward_method)
+      .def_readonly("backward_moved", &StagePlanResult::backward_moved);
+  py::class_<BackwardPlanResult>(m, "BackwardPlanResult")
+      .def_readonly("sketch_stage", &BackwardPlanResult::sketch_stage).def_readonly("objective", &BackwardPlanResult::objective)
+      .def_readonly("moved", &BackwardPlanResult::moved).def_readonly("stage_flops", &BackwardPlanResult::stage_flops)
+      .def_readonly("method", &BackwardPlanResult::method);
+  m.def("plan_backward_on_sketch", &PlanBackwardOnSketch);
+  m.def("make_sketch", [](const std::vector<double>& fwd, const std::vector<double>& bwd, const std::vector<std::tuple<int, int, double>>& edges) {
+    GraphSketch sk;
+    for (size_t i = 0; i < fwd.size(); ++i) {
+      SketchNode nd;
+      nd.id = (int)i; nd.fwd_flops = fwd[i]; nd.bwd_flops = bwd[i]; nd.name = "n" + std::to_string(i);
+      sk.nodes.push_back(nd);
+    }
+    for (auto& e : edges) sk.edges.push_back({std::get<0>(e), std::get<1>(e), std::get<2>(e)});
+    return sk;
+  });
   m.def("plan_stages_on_sketch", &PlanStagesOnSketch);
   m.def("plan_stages", [](Graph& g, const StagePlanOptions& o) { return PlanStages(&g, o); });
 

@@ -226,6 +226,82 @@ StagePlanResult PlanStagesOnSketch(const GraphSketch& sk, const StagePlanOptions
   return r;
 }
 
+BackwardPlanResult PlanBackwardOnSketch(const GraphSketch& sk, const std::vector<int>& sf, const std::vector<double>& act,
+                                        const StagePlanOptions& opt) {
+  BackwardPlanResult r;
+  const int n = (int)sk.nodes.size(), S = opt.num_stages;
+  r.sketch_stage = sf;
+  r.method = "mirror";
+  auto finish = [&]() {
+    r.stage_flops.assign(std::max(1, S), 0.0);
+    r.objective = 0;
+    r.moved = 0;
+    for (int i = 0; i < n; ++i) {
+      r.stage_flops[sf[i]] += sk.nodes[i].fwd_flops;
+      r.stage_flops[r.sketch_stage[i]] += sk.nodes[i].bwd_flops;
+      r.objective += (i < (int)act.size() ? act[i] : 0.0) * std::abs(r.sketch_stage[i] - sf[i]);
+      r.moved += r.sketch_stage[i] != sf[i];
+    }
+    for (auto& e : sk.edges) r.objective += 0.5 * e.bytes * std::abs(r.sketch_stage[e.dst] - r.sketch_stage[e.src]);
+    return r;
+  };
+  if (S <= 1 || n == 0 || n * (S - 1) > 120) return finish();   // (large sketches: mirror; the ILP is for the coarse sketch)
+  double total = 0, fmax = 0;
+  for (auto& x : sk.nodes) { total += x.fwd_flops + x.bwd_flops; fmax = std::max(fmax, x.fwd_flops + x.bwd_flops); }
+  // budget: what the forward plan already needed (the mirror placement is feasible by construction), never below the nominal one
+  std::vector<double> mirror(S, 0.0);
+  for (int i = 0; i < n; ++i) mirror[sf[i]] += sk.nodes[i].fwd_flops + sk.nodes[i].bwd_flops;
+  const double nominal = std::max(total / S * (1.0 + opt.unbalanced_ratio), fmax);
+  const double worst_mirror = *std::max_element(mirror.begin(), mirror.end());
+  const double cap = std::max(nominal, 0.0) < worst_mirror ? nominal : worst_mirror;   // try to do at least as well as the nominal budget
+  IlpModel m;
+  auto Z = [&](int i, int k) { return i * (S - 1) + k; };
+  for (int i = 0; i < n; ++i)
+    for (int k = 0; k < S - 1; ++k) m.AddVar(0, 1, 0.0, true);
+  for (int i = 0; i < n; ++i)
+    for (int k = 0; k + 1 < S - 1; ++k) m.AddRow({Z(i, k), Z(i, k + 1)}, {1, -1}, -IlpModel::kInf, 0);   // z monotone in k
+  double constant = 0;
+  for (auto& e : sk.edges)
+    for (int k = 0; k < S - 1; ++k) {
+      m.AddRow({Z(e.dst, k), Z(e.src, k)}, {1, -1}, -IlpModel::kInf, 0);   // sb(dst) >= sb(src)
+      m.obj[Z(e.src, k)] += 0.5 * e.bytes;     // (sketch edge bytes count both directions; the backward half is priced here)
+      m.obj[Z(e.dst, k)] -= 0.5 * e.bytes;
+    }
+  for (int i = 0; i < n; ++i)
+    for (int k = 0; k < S - 1; ++k) {
+      const double a = i < (int)act.size() ? act[i] : 0.0;
+      if (sf[i] <= k) { m.obj[Z(i, k)] -= a; constant += a; }   // zf = 1: |z - 1| = 1 - z
+      else m.obj[Z(i, k)] += a;                                  // zf = 0: |z - 0| = z
+    }
+  std::vector<double> fwd_on(S, 0.0);
+  for (int i = 0; i < n; ++i) fwd_on[sf[i]] += sk.nodes[i].fwd_flops;
+  double bwd_total = 0;
+  for (auto& x : sk.nodes) bwd_total += x.bwd_flops;
+  for (int k = 0; k < S; ++k) {   // device k: fwd_on[k] + sum_i bwd(i) * [sb(i) == k] <= cap, [sb == k] = z[k] - z[k-1]
+    std::vector<int> idx;
+    std::vector<double> val;
+    for (int i = 0; i < n; ++i) {
+      if (k < S - 1) { idx.push_back(Z(i, k)); val.push_back(sk.nodes[i].bwd_flops); }
+      if (k > 0) { idx.push_back(Z(i, k - 1)); val.push_back(-sk.nodes[i].bwd_flops); }
+    }
+    m.AddRow(idx, val, -IlpModel::kInf, (k == S - 1 ? cap - fwd_on[k] - bwd_total : cap - fwd_on[k]));
+  }
+  IlpResult ir = SolveIlp(m, opt.ilp_time_limit_s);
+  if (ir.status == IlpResult::kOptimal || ir.status == IlpResult::kFeasible) {
+    for (int i = 0; i < n; ++i) {
+      int st = S - 1;
+      for (int k = 0; k < S - 1; ++k)
+        if (ir.x[Z(i, k)] > 0.5) { st = k; break; }
+      r.sketch_stage[i] = st;
+    }
+    r.method = ir.status == IlpResult::kOptimal ? "ilp" : "ilp-timeout";
+  } else if (cap < worst_mirror) {
+    r.method = "mirror";    // the nominal budget is infeasible for the backward groups at this granularity: keep the mirror
+  }
+  (void)constant;
+  return finish();
+}
+
 StagePlanResult PlanStages(Graph* gp, const StagePlanOptions& opt) {
   Graph& g = *gp;
   GraphSketch sk = BuildSketch(g, /*fine_grained=*/false);
@@ -240,7 +316,31 @@ StagePlanResult PlanStages(Graph* gp, const StagePlanOptions& opt) {
       // producer's group id but may sit on the consumer's stage)
       if (n.group >= 0 && !IsCollective(n.op) && !group_stage.count(n.group)) group_stage[n.group] = n.stage;
     }
-  // backward ops: mirror stage of their forward group (logical 2S-1-s, same physical device s)
+  // backward ops: their op group is placed as a unit by the backward ILP (mirror stage of the forward group -- logical
+  // 2S-1-s, same physical device s -- unless moving the group pays for shipping its activation stash)
+  {
+    std::vector<double> act(sk.nodes.size(), 0.0);
+    for (auto& n : g.nodes) {
+      const int k = sk.node_of[n.id];
+      if (k < 0) continue;
+      for (int o = 0; o < (int)n.outputs.size(); ++o) {
+        bool saved = false;
+        for (auto& u : g.users(ValueRef{n.id, o})) saved |= g.nodes[u.node].backward;
+        if (saved) act[k] += (double)n.outputs[o].bytes();
+      }
+    }
+    BackwardPlanResult bp = PlanBackwardOnSketch(sk, r.sketch_stage, act, opt);
+    r.backward_stage = bp.sketch_stage;
+    r.backward_method = bp.method;
+    r.backward_moved = bp.moved;
+    if (bp.moved > 0) {
+      r.stage_flops = bp.stage_flops;
+      std::map<int, int> group_sk;
+      for (auto& n : g.nodes)
+        if (sk.node_of[n.id] >= 0 && n.group >= 0 && !IsCollective(n.op) && !group_sk.count(n.group)) group_sk[n.group] = sk.node_of[n.id];
+      for (auto& kv : group_sk) group_stage[kv.first] = bp.sketch_stage[kv.second];
+    }
+  }
   for (auto& n : g.nodes)
     if (n.stage < 0 && n.backward) {
       auto it = group_stage.find(n.group);

@@ -49,8 +49,32 @@ struct StagePlanResult {
   std::string method;               // "dp-chain" | "ilp"
   bool optimal = true;
   double seconds = 0;
+  std::vector<int> backward_stage;  // per sketch node: device of its backward op group (BackwardPlan)
+  std::string backward_method;      // "mirror" | "ilp" | "ilp-timeout"
+  int backward_moved = 0;
 };
 StagePlanResult PlanStagesOnSketch(const GraphSketch& sk, const StagePlanOptions& opt);
+
+// Backward stage plan (reference GraphSketch::BackwardPlan, hlo_graph_sketch.cc:2169-2427, with the op-group bookkeeping of
+// BuildOpGroupInfo :1339-1585 and the mirror-stage |d| linearisation :311-476).  Every forward sketch node i owns one op GROUP
+// of backward instructions (its gradient ops) with `bwd_flops` and a stash of `act_bytes` activations that live on the
+// forward stage sf(i).  The group is placed as ONE unit (op-group constraint) on device sb(i):
+//   minimise   sum_edges bytes(e) * (sb(src) - sb(dst))         gradient traffic, neighbour hops (flows run dst -> src)
+//            + sum_i act_bytes(i) * |sb(i) - sf(i)|              moving a group off its mirror stage ships its stash
+//   s.t.       sb(src) <= sb(dst) for every forward edge src -> dst      (gradients flow from later to earlier stages)
+//              sum_{sf(i) = k} fwd(i) + sum_{sb(i) = k} bwd(i) <= budget  (per device, forward work fixed by the forward plan)
+// With cumulative binaries z[i][k] = [sb(i) <= k] both absolute values are linear (sf is a constant).  Mirroring (sb = sf) is
+// always feasible when the forward plan respected the same budget on fwd + bwd, and is what the ILP returns unless moving a
+// group pays -- e.g. a backward-heavy group with a small stash next to an underloaded stage.
+struct BackwardPlanResult {
+  std::vector<int> sketch_stage;    // sb per sketch node
+  double objective = 0;             // bytes
+  int moved = 0;                    // groups placed off their mirror stage
+  std::vector<double> stage_flops;  // fwd + bwd per device after the backward placement
+  std::string method;               // "mirror" | "ilp" | "ilp-timeout"
+};
+BackwardPlanResult PlanBackwardOnSketch(const GraphSketch& sk, const std::vector<int>& fwd_stage, const std::vector<double>& act_bytes,
+                                        const StagePlanOptions& opt);
 
 // Full stage planning: sketch -> plan -> write Node::stage for every node of `g` (forward ops by plan, backward ops
 // by op_group mirror, variables/slots/apply by their consumers); returns the plan.
