@@ -159,7 +159,8 @@ PYBIND11_MODULE(_C, m) {
   });
   m.def("reshard_kind", [](const DimStrategy& a, const DimStrategy& b) { return std::string(ReshardName(ClassifyReshard(a, b))); });
   m.def("reshard_cost", &ReshardCost, py::arg("from_"), py::arg("to"), py::arg("bytes"), py::arg("n"), py::arg("cost_factor") = 1.0);
-  m.def("find_critical_nodes", &FindCriticalNodes);
+  m.def("find_critical_nodes", &FindCriticalNodes, py::arg("graph"), py::arg("min_segment_flops_frac") = 0.0);
+  m.def("find_critical_nodes_by_main_path", &FindCriticalNodesByMainPath);
 
   py::class_<HwProfile>(m, "HwProfile")
       .def(py::init<>())
@@ -182,6 +183,7 @@ PYBIND11_MODULE(_C, m) {
       .def_readwrite("var_mem_limit", &SpmdOptions::var_mem_limit)
       .def_readwrite("mem_split_min_rank", &SpmdOptions::mem_split_min_rank)
       .def_readwrite("collective_latency_bytes", &SpmdOptions::collective_latency_bytes)
+      .def_readwrite("min_segment_flops_frac", &SpmdOptions::min_segment_flops_frac)
       .def_readwrite("cost_factor", &SpmdOptions::cost_factor)
       .def_readwrite("opt_level", &SpmdOptions::opt_level)
       .def_readwrite("ignore_annotation", &SpmdOptions::ignore_annotation)

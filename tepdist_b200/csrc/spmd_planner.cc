@@ -281,7 +281,7 @@ std::string SegmentSignature(const Problem& p, const std::vector<int>& members, 
 
 }  // namespace
 
-std::vector<int> FindCriticalNodes(const Graph& g) {
+std::vector<int> FindCriticalNodes(const Graph& g, double min_segment_flops_frac) {
   std::vector<int> seps;
   std::map<ValueRef, int> live;  // value -> remaining forward uses
   auto fwd_uses = [&](ValueRef v) {
@@ -307,7 +307,82 @@ std::vector<int> FindCriticalNodes(const Graph& g) {
         n.outputs[0].bytes() >= 1024)
       seps.push_back(n.id);
   }
+  if (min_segment_flops_frac > 0 && !seps.empty()) {
+    // tiny-node clustering: a separator whose sub-graph (the forward nodes since the previous kept separator) carries less than
+    // the given share of the forward FLOPs is dropped, merging that sub-graph into the next one
+    double total = 0;
+    for (auto& n : g.nodes)
+      if (IsFwdCompute(n)) total += NodeFlops(g, n);
+    std::vector<int> kept;
+    double acc = 0;
+    size_t si = 0;
+    for (auto& n : g.nodes) {
+      if (!IsFwdCompute(n)) continue;
+      acc += NodeFlops(g, n);
+      if (si < seps.size() && n.id == seps[si]) {
+        if (acc >= min_segment_flops_frac * total) { kept.push_back(n.id); acc = 0; }
+        ++si;
+      }
+    }
+    seps.swap(kept);
+  }
   return seps;
+}
+
+std::vector<int> FindCriticalNodesByMainPath(const Graph& g) {
+  // forward compute nodes in topological (id) order
+  std::vector<int> order;
+  for (auto& n : g.nodes)
+    if (IsFwdCompute(n)) order.push_back(n.id);
+  if (order.empty()) return {};
+  std::map<int, int> pos;
+  for (int i = 0; i < (int)order.size(); ++i) pos[order[i]] = i;
+  const int L = (int)order.size();
+  // max-FLOPs path ending at the last forward node: best[i] = heaviest path weight ending at i, pred[i]
+  std::vector<double> best(L, 0.0);
+  std::vector<int> pred(L, -1);
+  for (int i = 0; i < L; ++i) {
+    const Node& n = g.nodes[order[i]];
+    double b = 0;
+    int p = -1;
+    for (auto& v : n.inputs) {
+      auto it = pos.find(v.node);
+      if (it != pos.end() && best[it->second] >= b) { b = best[it->second]; p = it->second; }
+    }
+    best[i] = b + NodeFlops(g, n) + 1e-3;   // (+epsilon: zero-FLOP nodes still extend a path)
+    pred[i] = p;
+  }
+  std::vector<char> on_path(L, 0);
+  for (int i = L - 1; i >= 0; i = pred[i]) {
+    on_path[i] = 1;
+    if (pred[i] < 0) break;
+  }
+  // bypass count per position: forward edges (u -> v) with pos(u) < c < pos(v); plus values of u still needed after c
+  std::vector<int> bypass(L + 1, 0);
+  for (int i = 0; i < L; ++i) {
+    const Node& n = g.nodes[order[i]];
+    for (auto& v : n.inputs) {
+      auto it = pos.find(v.node);
+      if (it == pos.end()) continue;
+      const int a = it->second;
+      if (i - a >= 2) { bypass[a + 1] += 1; bypass[i] -= 1; }   // positions a+1 .. i-1 are bypassed
+    }
+  }
+  std::vector<int> out;
+  int run = 0;
+  for (int c = 0; c < L; ++c) {
+    run += bypass[c];
+    if (c == L - 1 || !on_path[c] || run != 0) continue;
+    const Node& n = g.nodes[order[c]];
+    // FreedomDegree == 0 also requires that only output 0 of the node is consumed downstream in the forward pass
+    bool single = n.outputs[0].bytes() >= 1024;
+    bool has_use = false;
+    for (int o = 0; o < (int)n.outputs.size(); ++o)
+      for (auto& u : g.users(ValueRef{n.id, o}))
+        if (IsFwdCompute(g.nodes[u.node])) { has_use = true; if (o != 0) single = false; }
+    if (single && has_use) out.push_back(n.id);
+  }
+  return out;
 }
 
 SpmdPlan PlanSpmdLevel(Graph* gp, const SpmdOptions& opt) {
@@ -320,7 +395,7 @@ SpmdPlan PlanSpmdLevel(Graph* gp, const SpmdOptions& opt) {
   std::vector<int> chosen(N, 0);
 
   std::vector<int> seps;
-  if (opt.opt_level < 3) seps = FindCriticalNodes(g);
+  if (opt.opt_level < 3) seps = FindCriticalNodes(g, opt.min_segment_flops_frac);
   if (opt.forward_sub_graph_num > 0 && (int)seps.size() > opt.forward_sub_graph_num - 1) {
     std::vector<int> pick;
     const int want = opt.forward_sub_graph_num - 1;

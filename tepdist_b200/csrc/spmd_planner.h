@@ -29,6 +29,7 @@ struct SpmdOptions {
   bool ignore_annotation = true;     // IGNORE_ANNOTATION
   bool aux_affinity = false;         // AUX_AFFINITY (variable <-> optimizer slots share a layout)
   int forward_sub_graph_num = 0;     // FORWARD_SUB_GRAPH_NUM: 0 = cut at every separator
+  double min_segment_flops_frac = 0; // tiny-node clustering: separators cutting off less than this share of the forward FLOPs are dropped
   double ilp_time_limit_s = 20.0;    // ILP_TIME_LIMIT
   double replicate_penalty = 1e-3;   // per byte of activation computed redundantly (keeps free splits split)
   double memory_weight = 0.0;        // per byte of variable state stored per device (0: memory only via VAR_MEM_LIMIT)
@@ -62,7 +63,17 @@ struct SpmdPlan {
 
 // Forward separators: forward values through which ALL forward dataflow passes (the reference's critical nodes,
 // GraphSketch::FindCriticalInsts — FreedomDegree()==0 on the heavy path).
-std::vector<int> FindCriticalNodes(const Graph& g);
+// Critical nodes = separators of the forward dataflow (reference GraphSketch, hlo_graph_sketch.cc:1288-1336: the nodes of the
+// max-FLOPs main path whose FreedomDegree is 0).  Computed by a liveness scan: after a critical node executes, its output is
+// the ONLY live forward value, i.e. no value bypasses it -- which is the FreedomDegree == 0 condition and puts the node on every
+// source-to-loss path, the heaviest one included.  `min_segment_flops_frac` > 0 additionally drops separators that would cut off
+// a sub-graph with less than that share of the forward FLOPs (the reference's tiny-node clustering): their nodes are merged
+// into the following sub-graph.
+std::vector<int> FindCriticalNodes(const Graph& g, double min_segment_flops_frac = 0.0);
+// The same set from the DEFINITION (independent implementation used to verify the scan): the forward nodes that lie on the
+// max-FLOPs source-to-loss path and have no bypassing forward edge (every forward edge (u, v) with topological position
+// pos(u) < pos(c) < pos(v) is absent).
+std::vector<int> FindCriticalNodesByMainPath(const Graph& g);
 
 // Plans one level and appends the chosen DimStrategy to every value's DistSpec (levels.push_back).
 SpmdPlan PlanSpmdLevel(Graph* g, const SpmdOptions& opt);

@@ -738,3 +738,29 @@ def test_backward_stage_plan_places_op_groups_by_ilp():
     so.num_stages = 2
     res = _C.plan_stages(cg, so)
     assert res.backward_method == "ilp" and res.backward_moved == 0 and list(res.backward_stage) == list(res.sketch_stage)
+
+
+def test_critical_nodes_scan_equals_the_main_path_definition_and_clusters_tiny_segments():
+    """A5: the separators found by the liveness scan are exactly the nodes of the max-FLOPs main path with no bypassing
+    forward edge (FreedomDegree == 0) -- two independent implementations, compared on every model family; tiny-node clustering
+    drops separators that cut off less than the requested share of the forward FLOPs."""
+    from tepdist_b200.models.gpt2 import CONFIGS, build_gpt2_graph
+    from tepdist_b200.models.gpt_moe import MoEConfig, build_gpt_moe_graph
+    from tepdist_b200.models.wide_resnet import WideResNetConfig, build_wide_resnet_graph
+    from tepdist_b200.planner import to_native
+    graphs = [build_gpt2_graph(CONFIGS["tiny"], batch=4),
+              build_gpt_moe_graph(MoEConfig(n_layer=2, hidden=128, ffn=256, n_head=2, experts=4, capacity=64, groups=4, seq=128, batch=4, vocab=1000)),
+              build_wide_resnet_graph(WideResNetConfig(model_type=0, batch=4, image=32, classes=10))]
+    for g in graphs:
+        cg = to_native(g)
+        scan = list(_C.find_critical_nodes(cg))
+        assert scan == list(_C.find_critical_nodes_by_main_path(cg)), g.name
+        assert len(scan) >= 3, (g.name, scan)
+        coarse = list(_C.find_critical_nodes(cg, 0.2))
+        assert set(coarse) <= set(scan) and len(coarse) < len(scan) and len(coarse) <= 5, (g.name, len(scan), len(coarse))
+    # the clustered separators still give a valid (and identical-cost) plan
+    from tepdist_b200.parallel import plan_spmd
+    g = graphs[0]
+    _, a = plan_spmd(g, 2, "auto")
+    _, b_ = plan_spmd(g, 2, "auto", options={"min_segment_flops_frac": 0.2})
+    assert b_["subgraphs"] < a["subgraphs"] and abs(a["comm_bytes"] - b_["comm_bytes"]) <= 1e-6 * max(1.0, a["comm_bytes"])
