@@ -22,12 +22,13 @@ def main():
                     help='reference: "optimizer" in examples/gpt_moe/pretrain_moe.json')
     ap.add_argument("--clip-norm", default=None, choices=["global", "local"], help='gradient clipping (reference gpt_moe config: "clip_norm")')
     ap.add_argument("--clip-norm-value", type=float, default=1.0)
+    ap.add_argument("--no-graph", action="store_true", help="run the step eagerly (default: whole step replayed from a CUDA graph)")
     a = ap.parse_args()
     clip = {"clip_norm": a.clip_norm, "clip_norm_value": a.clip_norm_value} if a.clip_norm else {}
     cfg = MoEConfig(batch=a.batch)
     if a.tiny:
         cfg = MoEConfig(n_layer=2, hidden=128, ffn=256, n_head=2, experts=4, capacity=64, groups=4, seq=128, batch=a.batch, vocab=1000)
-    tr = Trainer(build_gpt_moe_graph(cfg, optimizer=a.optimizer, **clip), strategy=a.strategy, use_cuda_graph=False)
+    tr = Trainer(build_gpt_moe_graph(cfg, optimizer=a.optimizer, **clip), strategy=a.strategy, use_cuda_graph=not a.no_graph)
     gen = torch.Generator().manual_seed(0)
     tok = torch.randint(0, cfg.vocab, (cfg.batch, cfg.seq), generator=gen, dtype=torch.int32)
     feeds = {"tokens": tok, "labels": torch.roll(tok, -1, 1)}

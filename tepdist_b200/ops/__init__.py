@@ -94,6 +94,9 @@ class _Sig:
     tepd_sgd = [_vp, _vp, _vp, _ll, _f, _f, _vp]
     tepd_axpy_f32 = [_vp, _vp, _ll, _f, _vp]
     tepd_cast_f32_bf16 = [_vp, _vp, _ll, _vp]
+    tepd_moe_gather_scale = [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp]
+    tepd_moe_combine_sum = [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp]
+    tepd_moe_route_dots = [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp]
     tepd_attn_fwd = [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _f, _i, _ll, _ll, _ll, _vp]
     tepd_attn_bwd = [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _f, _i,
                      _ll, _ll, _ll, _ll, _ll, _ll, _vp]
@@ -325,6 +328,57 @@ def einsum(eq: str, a: torch.Tensor, b: torch.Tensor, _force: bool = False) -> t
     if cur != out_idx:
         d = d.permute([cur.index(c) for c in out_idx]).contiguous()
     return d
+
+
+# --------------------------------------------------------------------------------------------- MoE route-table kernels
+def moe_gather_scale(src: torch.Tensor, slot_src: torch.Tensor, w: torch.Tensor, E: int, C: int) -> torch.Tensor:
+    """out[e, g, c, :] = w[g, e, c] * src[g, slot_src[g, e, c], :] (zero where slot_src < 0).  src [G, S, M]; slot_src int32 [G, E, C]."""
+    G, S, M = src.shape
+    if not src.is_cuda or src.dtype != torch.bfloat16 or M % 8:
+        valid = slot_src >= 0
+        idx = slot_src.clamp(min=0).long().reshape(G, E * C)
+        rows = torch.gather(src.float(), 1, idx.unsqueeze(-1).expand(G, E * C, M)).reshape(G, E, C, M)
+        out = rows * (w.float() * valid).unsqueeze(-1)
+        return out.permute(1, 0, 2, 3).contiguous().to(src.dtype)
+    out = torch.empty(E, G, C, M, dtype=src.dtype, device=src.device)
+    _check(lib().tepd_moe_gather_scale(src.contiguous().data_ptr(), slot_src.contiguous().data_ptr(), w.contiguous().data_ptr(),
+                                       out.data_ptr(), G, S, E, C, M, _stream()), "moe_gather_scale")
+    _count()
+    return out
+
+
+def moe_combine_sum(y: torch.Tensor, re: torch.Tensor, rc: torch.Tensor, gw: torch.Tensor, S: int) -> torch.Tensor:
+    """out[g, s, :] = sum_k gw[g, s, k] * y[re[g, s, k], g, rc[g, s, k], :] (routes with re < 0 dropped).  y [E, G, C, M]."""
+    E, G, C, M = y.shape
+    K = re.shape[-1]
+    if not y.is_cuda or y.dtype != torch.bfloat16 or M % 8:
+        yg = y.float().permute(1, 0, 2, 3).reshape(G, E * C, M)
+        flat = (re.clamp(min=0).long() * C + rc.clamp(min=0).long()).reshape(G, S * K)
+        rows = torch.gather(yg, 1, flat.unsqueeze(-1).expand(G, S * K, M)).reshape(G, S, K, M)
+        out = (rows * (gw.float() * (re >= 0)).unsqueeze(-1)).sum(2)
+        return out.to(y.dtype)
+    out = torch.empty(G, S, M, dtype=y.dtype, device=y.device)
+    _check(lib().tepd_moe_combine_sum(y.contiguous().data_ptr(), re.contiguous().data_ptr(), rc.contiguous().data_ptr(),
+                                      gw.contiguous().data_ptr(), out.data_ptr(), G, S, E, C, M, K, _stream()), "moe_combine_sum")
+    _count()
+    return out
+
+
+def moe_route_dots(a: torch.Tensor, b: torch.Tensor, re: torch.Tensor, rc: torch.Tensor) -> torch.Tensor:
+    """dots[g, s, k] = < a[g, s, :], b[re[g, s, k], g, rc[g, s, k], :] > (0 for dropped routes), fp32.  a [G, S, M]; b [E, G, C, M]."""
+    G, S, M = a.shape
+    E, _, C, _ = b.shape
+    K = re.shape[-1]
+    if not a.is_cuda or a.dtype != torch.bfloat16 or M % 8:
+        bg = b.float().permute(1, 0, 2, 3).reshape(G, E * C, M)
+        flat = (re.clamp(min=0).long() * C + rc.clamp(min=0).long()).reshape(G, S * K)
+        rows = torch.gather(bg, 1, flat.unsqueeze(-1).expand(G, S * K, M)).reshape(G, S, K, M)
+        return ((rows * a.float().unsqueeze(2)).sum(-1) * (re >= 0)).float()
+    dots = torch.empty(G, S, K, dtype=torch.float32, device=a.device)
+    _check(lib().tepd_moe_route_dots(a.contiguous().data_ptr(), b.contiguous().data_ptr(), re.contiguous().data_ptr(),
+                                     rc.contiguous().data_ptr(), dots.data_ptr(), G, S, E, C, M, K, _stream()), "moe_route_dots")
+    _count()
+    return dots
 
 
 # --------------------------------------------------------------------------------------------- convolution

@@ -33,6 +33,9 @@ TP_FUSED = os.environ.get("TEPDIST_TP_FUSED", "1") == "1"
 # stands in for parallel.symm.GemmAllReduce, so the executor-side chain fusion can be exercised on CPU (gloo) where the
 # peer-memory kernels cannot run
 TP_FUSED_IMPL = None
+# GPT-MoE: dispatch / combine einsums whose mask comes from moe_dispatch_mask run as route-table row gathers (ops.moe_*), not as
+# dense [G,S,E*C] x [G,S,M] GEMMs; TEPDIST_MOE_SPARSE=0 keeps the dense einsums (the comparator)
+MOE_SPARSE = os.environ.get("TEPDIST_MOE_SPARSE", "1") == "1"
 # weight gradients with a single producer are written with plain stores instead of fp32 atomics into a zero-filled slot
 WGRAD_PLAIN_STORE = os.environ.get("TEPDIST_WGRAD_STORE", "1") == "1"
 
@@ -374,6 +377,8 @@ class Executor:
         self.grad_accumulate = False   # True when gradients add up over micro-batches (pipeline stage workers)
         self._plan_store_init()
         self.tp_fuse: Dict[int, Dict[str, Any]] = {}
+        self._moe_routes: Dict[Tuple[Any, int], Dict[str, Any]] = {}
+        self._moe_einsum: Dict[int, Tuple[str, int]] = self._find_moe_einsums(self.g) if MOE_SPARSE else {}
         if TP_FUSED and self.collective is not None and ((self.comm_mode == "fused" and self.device.type == "cuda") or TP_FUSED_IMPL):
             self._plan_tp_fusion()
 
@@ -1043,6 +1048,33 @@ class Executor:
             ops.sgd_step(st.master, st.grad, st.compute, self._lr(1e-2))
 
     @staticmethod
+    def _find_moe_einsums(g: Graph) -> Dict[int, Tuple[str, int]]:
+        """einsum node id -> (kind, id of the moe_dispatch_mask node whose route tables it can use).  Matches the GShard
+        formulation of models/gpt_moe.py: dispatch "GSEC,GSM->EGCM" / combine "GSEC,EGCM->GSM" with the mask as operand 0
+        (which also covers the two gradient einsums that take the mask), and the two d-mask einsums "EGCM,GSM->GSEC" /
+        "GSM,EGCM->GSEC", tied to their forward einsum through the op group."""
+        found: Dict[int, Tuple[str, int]] = {}
+        by_group: Dict[Tuple[int, str], int] = {}
+        for n in g.nodes:
+            if n.op != "einsum" or len(n.inputs) != 2:
+                continue
+            eq = str(n.attrs.get("eq", "")).replace(" ", "")
+            src = g.nodes[n.inputs[0].node]
+            if src.op == "moe_dispatch_mask" and eq in ("GSEC,GSM->EGCM", "GSEC,EGCM->GSM"):
+                found[n.id] = ("gather" if eq.endswith("EGCM") else "combine", src.id)
+                if not n.backward:
+                    by_group[(n.group, eq)] = src.id
+        for n in g.nodes:
+            if n.op != "einsum" or not n.backward or n.id in found:
+                continue
+            eq = str(n.attrs.get("eq", "")).replace(" ", "")
+            if eq == "EGCM,GSM->GSEC" and (n.group, "GSEC,GSM->EGCM") in by_group:
+                found[n.id] = ("dots_eg_first", by_group[(n.group, "GSEC,GSM->EGCM")])
+            elif eq == "GSM,EGCM->GSEC" and (n.group, "GSEC,EGCM->GSM") in by_group:
+                found[n.id] = ("dots", by_group[(n.group, "GSEC,EGCM->GSM")])
+        return found
+
+    @staticmethod
     def find_tp_chains(g: Graph, skip: Optional[set] = None) -> Dict[int, Dict[str, Any]]:
         """LIN (linear / linear_dgrad, no fused epilogue) -> all_reduce(sum) [-> add(bias [N])] [-> add(residual)] chains in
         which every link has exactly one user: {LIN id: {ar, M, N, level, num, bias key, res key, chain node ids}}."""
@@ -1444,16 +1476,39 @@ class Executor:
             remaining = gates.clone()
             offset = torch.zeros(Gn, 1, E, device=gates.device)
             sel = torch.zeros(Gn, Sn, E, C, device=gates.device)   # 0/1 slot assignment
+            r_e, r_c, r_w = [], [], []
             for _ in range(k):
                 idx = remaining.argmax(-1)
                 mask = F.one_hot(idx, E).float()
                 pos = (mask.cumsum(1) - 1 + offset) * mask
                 keep = (pos < C).float() * mask
                 sel = sel + keep.unsqueeze(-1) * F.one_hot(pos.long().clamp(max=C - 1), C).float()
+                if op == "moe_dispatch_mask" and MOE_SPARSE:
+                    kept = keep.sum(-1) > 0                                   # [G, S]: this choice got a slot
+                    r_e.append(torch.where(kept, idx, torch.full_like(idx, -1)).int())
+                    r_c.append((pos * mask).sum(-1).long().clamp(max=C - 1).int())
+                    r_w.append(gates.gather(-1, idx.unsqueeze(-1)).squeeze(-1) * kept)
                 offset = offset + mask.sum(1, keepdim=True)
                 remaining = remaining.masked_fill(mask.bool(), float("-inf"))
             if op == "moe_dispatch_mask":
-                return [(gates.unsqueeze(-1) * sel).to(torch_dtype(n.outputs[0].dtype, self.device))]
+                out = (gates.unsqueeze(-1) * sel).to(torch_dtype(n.outputs[0].dtype, self.device))
+                if MOE_SPARSE:
+                    # route tables of this mask (token -> its <= k slots; slot -> its one token), kept for the dispatch /
+                    # combine einsums that consume the mask and for the gradient einsums that produce d mask
+                    re_, rc_, gw_ = torch.stack(r_e, -1).contiguous(), torch.stack(r_c, -1).contiguous(), torch.stack(r_w, -1).contiguous()
+                    slot_src = torch.full((Gn, E * C), -1, dtype=torch.int32, device=gates.device)
+                    slot_w = torch.zeros(Gn, E * C, dtype=torch.float32, device=gates.device)
+                    s_idx = torch.arange(Sn, device=gates.device, dtype=torch.int32).view(1, Sn, 1).expand(Gn, Sn, k)
+                    flat = (re_.clamp(min=0).long() * C + rc_.long())
+                    flat = torch.where(re_ >= 0, flat, torch.full_like(flat, E * C))          # dropped routes -> a dummy column
+                    pad_src = torch.cat([slot_src, slot_src.new_full((Gn, 1), -1)], 1)
+                    pad_w = torch.cat([slot_w, slot_w.new_zeros(Gn, 1)], 1)
+                    pad_src.scatter_(1, flat.reshape(Gn, -1), s_idx.reshape(Gn, -1))
+                    pad_w.scatter_(1, flat.reshape(Gn, -1), gw_.reshape(Gn, -1).float())
+                    self._moe_routes[(self._tag, n.id)] = {"re": re_, "rc": rc_, "gw": gw_.float().contiguous(), "E": E, "C": C,
+                                                           "slot_src": pad_src[:, :E * C].reshape(Gn, E, C).contiguous(),
+                                                           "slot_w": pad_w[:, :E * C].reshape(Gn, E, C).contiguous()}
+                return [out]
             return [(ins[0].float() * sel).sum(-1).to(ins[1].dtype)]
         if op == "one_hot":
             return [F.one_hot(x.long(), a["depth"]).to(torch_dtype(n.outputs[0].dtype, self.device))]
@@ -1467,6 +1522,23 @@ class Executor:
             if ta: A = A.transpose(-1, -2)
             if tb: B = B.transpose(-1, -2)
             return [torch.matmul(A, B)]
+        if op == "einsum" and n.id in self._moe_einsum:
+            kind, mask_id = self._moe_einsum[n.id]
+            rt = self._moe_routes.get((self._tag, mask_id))
+            if rt is not None:
+                if kind == "gather":         # "GSEC,GSM->EGCM": dispatch / d(expert output) of the combine
+                    return [ops.moe_gather_scale(ins[1].contiguous(), rt["slot_src"], rt["slot_w"], rt["E"], rt["C"])]
+                if kind == "combine":        # "GSEC,EGCM->GSM": combine / d(tokens) of the dispatch
+                    return [ops.moe_combine_sum(ins[1].contiguous(), rt["re"], rt["rc"], rt["gw"], ins[0].shape[1])]
+                # d mask: "EGCM,GSM->GSEC" (dots of d dispatched rows with tokens) / "GSM,EGCM->GSEC" (d out with expert outputs)
+                a_, b_ = (ins[1], ins[0]) if kind == "dots_eg_first" else (ins[0], ins[1])
+                dots = ops.moe_route_dots(a_.contiguous(), b_.contiguous(), rt["re"], rt["rc"])
+                Gn, Sn, K_ = dots.shape
+                dense = torch.zeros(Gn, Sn, rt["E"] * rt["C"] + 1, dtype=torch.float32, device=dots.device)
+                flat = rt["re"].clamp(min=0).long() * rt["C"] + rt["rc"].long()
+                flat = torch.where(rt["re"] >= 0, flat, torch.full_like(flat, rt["E"] * rt["C"]))
+                dense.scatter_(2, flat, dots)
+                return [dense[:, :, :rt["E"] * rt["C"]].reshape(Gn, Sn, rt["E"], rt["C"]).to(torch_dtype(n.outputs[0].dtype, self.device))]
         if op == "einsum":
             # own batched tcgen05 GEMM for bf16 operands on the GPU (expert FFNs, dispatch / combine and their gradients);
             # torch.einsum for the CPU oracle and for patterns outside the kernel's alignment rules

@@ -601,6 +601,39 @@ def check_einsum():
     return out
 
 
+def check_moe_routes():
+    """Route-table dispatch / combine kernels (ops.moe_gather_scale / moe_combine_sum / moe_route_dots) vs their plain torch
+    reference (the CPU branch of the same functions, fp32), with dropped routes; then time vs the dense einsum they replace."""
+    from tepdist_b200 import ops
+    out = {}
+    torch.manual_seed(11)
+    G, S, E, C, M, K = 2, 512, 8, 64, 768, 2
+    x = torch.randn(G, S, M, device="cuda").to(torch.bfloat16)
+    y = torch.randn(E, G, C, M, device="cuda").to(torch.bfloat16)
+    re = torch.randint(-1, E, (G, S, K), device="cuda", dtype=torch.int32)
+    rc = torch.randint(0, C, (G, S, K), device="cuda", dtype=torch.int32)
+    gw = torch.rand(G, S, K, device="cuda") * (re >= 0)
+    slot_src = torch.randint(-1, S, (G, E, C), device="cuda", dtype=torch.int32)
+    slot_w = torch.rand(G, E, C, device="cuda")
+    cpu = lambda t: t.cpu().float() if t.is_floating_point() else t.cpu()
+    n0 = ops.launch_count()
+    out["gather"] = _rel_err(ops.moe_gather_scale(x, slot_src, slot_w, E, C), ops.moe_gather_scale(cpu(x), cpu(slot_src), cpu(slot_w), E, C).cuda())
+    out["combine"] = _rel_err(ops.moe_combine_sum(y, re, rc, gw, S), ops.moe_combine_sum(cpu(y), cpu(re), cpu(rc), cpu(gw), S).cuda())
+    out["dots"] = _rel_err(ops.moe_route_dots(x, y, re, rc), ops.moe_route_dots(cpu(x), cpu(y), cpu(re), cpu(rc)).cuda())
+    assert ops.launch_count() - n0 == 3
+    for k in ("gather", "combine", "dots"):
+        assert out[k] < 1e-2, out
+    # reference shape per GPU under EP-8 (1 group of 8192 tokens, 8 experts x 256 slots, model 768)
+    G, S, E, C, M = 1, 8192, 8, 256, 768
+    x = torch.randn(G, S, M, device="cuda").to(torch.bfloat16)
+    mask = torch.zeros(G, S, E, C, device="cuda", dtype=torch.bfloat16)
+    slot_src = torch.randint(0, S, (G, E, C), device="cuda", dtype=torch.int32)
+    slot_w = torch.rand(G, E, C, device="cuda")
+    out["gather_us"] = 1e3 * _time_ms(lambda: ops.moe_gather_scale(x, slot_src, slot_w, E, C))
+    out["dense_dispatch_einsum_us"] = 1e3 * _time_ms(lambda: ops.einsum("GSEC,GSM->EGCM", mask, x))
+    return out
+
+
 CHECKS = {
     "gemm_layouts": check_gemm_layouts,
     "gemm_epilogues": check_gemm_epilogues,
@@ -612,6 +645,7 @@ CHECKS = {
     "gemm_perf": check_gemm_perf,
     "conv": check_conv,
     "einsum": check_einsum,
+    "moe_routes": check_moe_routes,
     "attn_d48": check_attn_d48,
     "attn_poly": check_attn_poly,
     "attn_fwd2": check_attn_fwd2,

@@ -417,3 +417,41 @@ def test_einsum_lowering_to_batched_gemm_matches_torch_einsum():
     # patterns the lowering does not cover fall back to torch.einsum
     x = torch.randn(4, 8)
     assert torch.allclose(ops.einsum("ab,ab->a", x, x, _force=True), (x * x).sum(1), atol=1e-5)
+
+
+def test_moe_route_table_path_equals_the_dense_einsums():
+    """GPT-MoE's dispatch / combine einsums (and the four gradient einsums around them) run as route-table row gathers when their
+    mask comes from moe_dispatch_mask.  Same losses and same updated weights as the dense-einsum execution, step by step, on
+    the MoE FFN graph and on a tiny GPT-MoE -- forward, backward and token dropping (capacity smaller than the demand) included."""
+    import torch
+    from tepdist_b200.models.gpt_moe import MoEConfig, build_gpt_moe_graph, build_moe_ffn_graph
+    from tepdist_b200.runtime import executor as ex_mod
+    from tepdist_b200.runtime.executor import Executor
+
+    def run(g, feeds, sparse):
+        ex_mod.MOE_SPARSE = sparse
+        try:
+            ex = Executor(g, torch.device("cpu"), seed=0, use_cuda_graph=False)
+            n_sparse = len(ex._moe_einsum)
+            losses = [float(ex.step(feeds)[0]) for _ in range(3)]
+            return losses, ex.store.state_dict(), n_sparse
+        finally:
+            ex_mod.MOE_SPARSE = True
+
+    torch.manual_seed(0)
+    g = build_moe_ffn_graph(groups=4, tokens_per_group=32, model=32, hidden=64, experts=4, capacity=8)     # capacity 8 < 32 * 2 / 4: drops
+    feeds = {"x": torch.randn(4, 32, 32), "t": torch.randn(4, 32, 32)}
+    ld, sd, nd = run(g, feeds, False)
+    ls, ss, ns = run(g, feeds, True)
+    assert nd == 0 and ns == 5, (nd, ns)          # dispatch, combine + their gradient einsums (x is an input here: no d x)
+    for a, b in zip(ls, ld):
+        assert abs(a - b) <= 1e-5 * max(1.0, abs(b)), (ls, ld)
+    for k in sd:
+        assert torch.allclose(ss[k].float(), sd[k].float(), atol=1e-5, rtol=1e-4), k
+    cfg = MoEConfig(n_layer=2, hidden=64, ffn=128, n_head=2, experts=4, capacity=16, groups=2, seq=64, batch=2, vocab=500)
+    g2 = build_gpt_moe_graph(cfg)
+    tok = torch.randint(0, cfg.vocab, (cfg.batch, cfg.seq), dtype=torch.int32)
+    f2 = {"tokens": tok, "labels": torch.roll(tok, -1, 1)}
+    ld, _, _ = run(g2, f2, False)
+    ls, _, ns = run(g2, f2, True)
+    assert ns == 6 and all(abs(a - b) <= 1e-5 * max(1.0, abs(b)) for a, b in zip(ls, ld)), (ls, ld)
