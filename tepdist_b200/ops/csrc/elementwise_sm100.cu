@@ -5,7 +5,6 @@
 #include <cuda_bf16.h>
 #include <stdint.h>
 #include "launch.cuh"
-#include <cooperative_groups.h>
 
 namespace {
 
@@ -114,22 +113,24 @@ __global__ void __launch_bounds__(256) layernorm_fwd_kernel(const bf16* __restri
 // rows (no atomics inside the CTA, no 64-register accumulator arrays => 3 CTAs/SM keep enough loads in flight to
 // approach HBM bandwidth), reduced across the 8 warps at the end and added (fp32 red) to the gradient buffers.
 // Optional dres: fused residual-stream gradient add (dx_total = dx + dres).
-template <int MAXV>
-__global__ void __cluster_dims__(4, 1, 1) __launch_bounds__(256, (MAXV <= 4) ? 3 : 1) layernorm_bwd_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ x,
+// WARPS = 8: 256-thread CTAs, 3 per SM (64 KB of accumulator rows each); WARPS = 16: one 512-thread CTA per SM (128 KB) --
+// a third of the CTAs, hence a third of the global atomics on the 2 * C gradient words (TEPDIST_LN_BWD_WARPS selects).
+template <int MAXV, int WARPS>
+__global__ void __launch_bounds__(32 * WARPS, (MAXV <= 4 && WARPS == 8) ? 3 : 1) layernorm_bwd_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ x,
                                                            const float* __restrict__ gamma,
                                                            const float* __restrict__ mean_in,
                                                            const float* __restrict__ rstd_in, bf16* __restrict__ dx,
                                                            float* __restrict__ dgamma, float* __restrict__ dbeta,
                                                            const bf16* __restrict__ dres, int rows, int C) {
-  extern __shared__ float red[];  // [2][8][C]: dgamma rows then dbeta rows, one per warp
+  extern __shared__ float red[];  // [2][WARPS][C]: dgamma rows then dbeta rows, one per warp
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int nvec = C >> 3;
   float* my_dg = red + (size_t)warp * C;
-  float* my_db = red + (size_t)(8 + warp) * C;
+  float* my_db = red + (size_t)(WARPS + warp) * C;
   for (int c = lane; c < C; c += 32) { my_dg[c] = 0.f; my_db[c] = 0.f; }
   __syncwarp();
   pdl_wait();
-  for (int row = blockIdx.x * 8 + warp; row < rows; row += gridDim.x * 8) {
+  for (int row = blockIdx.x * WARPS + warp; row < rows; row += gridDim.x * WARPS) {
     const uint4* xr = reinterpret_cast<const uint4*>(x + (size_t)row * C);
     const uint4* dyr = reinterpret_cast<const uint4*>(dy + (size_t)row * C);
     const float mean = mean_in[row], rstd = rstd_in[row];
@@ -194,34 +195,13 @@ __global__ void __cluster_dims__(4, 1, 1) __launch_bounds__(256, (MAXV <= 4) ? 3
     }
   }
   __syncthreads();
-  // CTA-level sums of the 8 per-warp rows, written back into warp 0's rows (column c is touched by one thread only)
-  for (int c = threadIdx.x; c < C; c += 256) {
+  for (int c = threadIdx.x; c < C; c += 32 * WARPS) {
     float sg = 0.f, sb = 0.f;
 #pragma unroll
-    for (int w = 0; w < 8; ++w) { sg += red[(size_t)w * C + c]; sb += red[(size_t)(8 + w) * C + c]; }
-    red[c] = sg;
-    red[(size_t)8 * C + c] = sb;
-  }
-  // cluster-level reduction through distributed shared memory before the global atomics: the 2 * C gradient words live in
-  // 2 * C / 32 cache lines, and with one atomic per column per CTA (444 CTAs) every one of those lines took ~14 K serialized
-  // L2 atomics -- the kernel ran at 12 % of DRAM bandwidth.  CTA r of a 4-CTA cluster sums a quarter of the columns over
-  // the 4 CTAs' rows and issues the atomics for them: 4x fewer atomics, same arithmetic.
-  namespace cg = cooperative_groups;
-  cg::cluster_group cluster = cg::this_cluster();
-  cluster.sync();
-  const unsigned nb = cluster.num_blocks(), r = cluster.block_rank();
-  const int c0 = (int)((long long)C * r / nb), c1 = (int)((long long)C * (r + 1) / nb);
-  for (int c = c0 + threadIdx.x; c < c1; c += 256) {
-    float sg = 0.f, sb = 0.f;
-    for (unsigned k = 0; k < nb; ++k) {
-      const float* rem = cluster.map_shared_rank(red, k);
-      sg += rem[c];
-      sb += rem[(size_t)8 * C + c];
-    }
+    for (int w = 0; w < WARPS; ++w) { sg += red[(size_t)w * C + c]; sb += red[(size_t)(WARPS + w) * C + c]; }
     atomicAdd(dgamma + c, sg);
     atomicAdd(dbeta + c, sb);
   }
-  cluster.sync();   // peers may still be reading this CTA's rows
 }
 
 // ------------------------------------------------------------------ GELU (tanh form, GPT-2)
@@ -616,16 +596,22 @@ extern "C" int tepd_layernorm_bwd(const void* dy, const void* x, const void* gam
                                   void* dx, void* dgamma, void* dbeta, const void* dres, int rows, int C, void* stream) {
   if (C % 8 || C > 2048) return -2;
   int grid = 148 * 3;
-  if (grid > (rows + 7) / 8) grid = (rows + 7) / 8;
-  grid = (grid + 3) / 4 * 4;          // whole 4-CTA clusters (a CTA without rows still takes part in the cluster reduction)
-  size_t smem = (size_t)16 * C * sizeof(float);
-#define LN_BWD(MV)                                                                                          \
+  static int warps = 0;
+  if (warps == 0) {
+    const char* e = getenv("TEPDIST_LN_BWD_WARPS");
+    warps = (e && atoi(e) == 16) ? 16 : 8;
+  }
+  if (warps == 16 && C > 1024) warps = 8;      // (2 * 16 * C floats must fit one CTA's shared memory)
+  if (warps == 16) grid = 148;
+  if (grid > (rows + warps - 1) / warps) grid = (rows + warps - 1) / warps;
+  size_t smem = (size_t)2 * warps * C * sizeof(float);
+#define LN_BWD(MV, W)                                                                                       \
   {                                                                                                         \
     static bool cfg = false;                                                                                \
-    if (!cfg) { cudaFuncSetAttribute(layernorm_bwd_kernel<MV>, cudaFuncAttributeMaxDynamicSharedMemorySize, 16 * 2048 * 4); cfg = true; } \
-    return (int)tepd::launch(layernorm_bwd_kernel<MV>, dim3(grid), dim3(256), smem, CS(stream), (const bf16*)dy, (const bf16*)x, (const float*)gamma, (const float*)mean, (const float*)rstd, (bf16*)dx, (float*)dgamma, (float*)dbeta, (const bf16*)dres, rows, C); \
+    if (!cfg) { cudaFuncSetAttribute(layernorm_bwd_kernel<MV, W>, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * W * 2048 * 4 > 200 * 1024 ? 200 * 1024 : 2 * W * 2048 * 4); cfg = true; } \
+    return (int)tepd::launch(layernorm_bwd_kernel<MV, W>, dim3(grid), dim3(32 * W), smem, CS(stream), (const bf16*)dy, (const bf16*)x, (const float*)gamma, (const float*)mean, (const float*)rstd, (bf16*)dx, (float*)dgamma, (float*)dbeta, (const bf16*)dres, rows, C); \
   }
-  if (C <= 1024) LN_BWD(4) else LN_BWD(8)
+  if (C <= 1024) { if (warps == 16) LN_BWD(4, 16) else LN_BWD(4, 8) } else LN_BWD(8, 8)
 #undef LN_BWD
 }
 
