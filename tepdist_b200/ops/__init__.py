@@ -85,6 +85,9 @@ class _Sig:
     tepd_colsum = [_vp, _vp, _i, _i, _vp]
     tepd_bn_fwd_nhwc = [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _f, _i, _vp]
     tepd_bn_bwd_nhwc = [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _vp]
+    tepd_bn_reduce_nhwc = [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _vp]
+    tepd_bn_fwd_apply_nhwc = [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _f, _i, _f, _vp]
+    tepd_bn_bwd_apply_nhwc = [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _f, _vp]
     tepd_im2col_nhwc = [_vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _vp]
     tepd_col2im_nhwc = [_vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _vp]
     tepd_embedding_fwd = [_vp, _vp, _vp, _vp, _i, _i, _i, _vp]
@@ -489,6 +492,44 @@ def batchnorm_bwd(dy: torch.Tensor, x: torch.Tensor, gamma: torch.Tensor, mean: 
                                   ws.data_ptr(), N * H * W, C, _stream()), "bn_bwd")
     _count(2)
     return dx.permute(0, 3, 1, 2), ws[1], ws[0]
+
+
+def batchnorm_fwd_synced(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, eps: float, allsum, num_shards: int,
+                         relu: bool = False):
+    """Synchronised training-mode BatchNorm, native split phases: local per-channel sums (bn_reduce2), `allsum(ws)` completes them
+    over the devices that split the batch (one all-reduce of 2 x C floats), apply with the GLOBAL count.  -> (y, mean, rstd)."""
+    N, C, H, W = x.shape
+    xn = _nhwc(x)
+    rows = N * H * W
+    y = torch.empty_like(xn)
+    ws = torch.zeros(2, C, dtype=torch.float32, device=x.device)
+    mean = torch.empty(C, dtype=torch.float32, device=x.device)
+    rstd = torch.empty(C, dtype=torch.float32, device=x.device)
+    _check(lib().tepd_bn_reduce_nhwc(xn.data_ptr(), None, None, None, ws.data_ptr(), rows, C, 0, _stream()), "bn_reduce")
+    allsum(ws)
+    _check(lib().tepd_bn_fwd_apply_nhwc(xn.data_ptr(), ws.data_ptr(), gamma.data_ptr(), beta.data_ptr(), y.data_ptr(), mean.data_ptr(),
+                                        rstd.data_ptr(), rows, C, float(eps), int(relu), float(rows * num_shards), _stream()), "bn_fwd_apply")
+    _count(2)
+    return y.permute(0, 3, 1, 2), mean, rstd
+
+
+def batchnorm_bwd_synced(dy: torch.Tensor, x: torch.Tensor, gamma: torch.Tensor, mean: torch.Tensor, rstd: torch.Tensor, allsum,
+                         num_shards: int):
+    """-> (dx, dgamma_local, dbeta_local): dgamma / dbeta stay this shard's partial sums (the plan reduces them with the other
+    gradients); dx uses the batch-global sums."""
+    N, C, H, W = x.shape
+    xn, dyn = _nhwc(x), _nhwc(dy)
+    rows = N * H * W
+    dx = torch.empty_like(xn)
+    ws = torch.zeros(2, C, dtype=torch.float32, device=x.device)
+    _check(lib().tepd_bn_reduce_nhwc(dyn.data_ptr(), xn.data_ptr(), mean.data_ptr(), rstd.data_ptr(), ws.data_ptr(), rows, C, 1, _stream()),
+           "bn_reduce")
+    local = ws.clone()
+    allsum(ws)
+    _check(lib().tepd_bn_bwd_apply_nhwc(dyn.data_ptr(), xn.data_ptr(), gamma.data_ptr(), mean.data_ptr(), rstd.data_ptr(), ws.data_ptr(),
+                                        dx.data_ptr(), rows, C, float(rows * num_shards), _stream()), "bn_bwd_apply")
+    _count(2)
+    return dx.permute(0, 3, 1, 2), local[1], local[0]
 
 
 # --------------------------------------------------------------------------------------------- LayerNorm

@@ -296,10 +296,10 @@ __global__ void __launch_bounds__(256) bn_fwd_apply_kernel(const bf16* __restric
                                                           const float* __restrict__ sumsq, const float* __restrict__ gamma,
                                                           const float* __restrict__ beta, bf16* __restrict__ y,
                                                           float* __restrict__ mean_out, float* __restrict__ rstd_out, int rows,
-                                                          int C, float eps, int relu) {
+                                                          int C, float eps, int relu, float count) {
   pdl_wait();
   const int cv = C >> 3;
-  const float inv = 1.f / rows;
+  const float inv = 1.f / count;     // count = rows of the GLOBAL batch (rows of every shard when the batch is split)
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < (size_t)rows * cv; i += (size_t)gridDim.x * blockDim.x) {
     const int c0 = (int)(i % cv) * 8;
     float f[8], o[8];
@@ -320,10 +320,11 @@ __global__ void __launch_bounds__(256) bn_fwd_apply_kernel(const bf16* __restric
 __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ x,
                                                           const float* __restrict__ gamma, const float* __restrict__ mean,
                                                           const float* __restrict__ rstd, const float* __restrict__ sum_dy,
-                                                          const float* __restrict__ sum_dyxh, bf16* __restrict__ dx, int rows, int C) {
+                                                          const float* __restrict__ sum_dyxh, bf16* __restrict__ dx, int rows, int C,
+                                                          float count) {
   pdl_wait();
   const int cv = C >> 3;
-  const float inv = 1.f / rows;
+  const float inv = 1.f / count;
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < (size_t)rows * cv; i += (size_t)gridDim.x * blockDim.x) {
     const int c0 = (int)(i % cv) * 8;
     float d[8], f[8], o[8];
@@ -599,7 +600,7 @@ extern "C" int tepd_layernorm_bwd(const void* dy, const void* x, const void* gam
   static int warps = 0;
   if (warps == 0) {
     const char* e = getenv("TEPDIST_LN_BWD_WARPS");
-    warps = (e && atoi(e) == 16) ? 16 : 8;
+    warps = (e && atoi(e) == 8) ? 8 : 16;      // measured in situ (GPT-2 345M, 49 launches): 15.6 us (16 warps, 148 CTAs) vs 17.2 us (8 warps, 444 CTAs)
   }
   if (warps == 16 && C > 1024) warps = 8;      // (2 * 16 * C floats must fit one CTA's shared memory)
   if (warps == 16) grid = 148;
@@ -687,7 +688,7 @@ extern "C" int tepd_bn_fwd_nhwc(const void* x, const void* gamma, const void* be
   if (e != cudaSuccess) return (int)e;
   return (int)tepd::launch(bn_fwd_apply_kernel, dim3(grid_for((size_t)rows * C / 8, 256)), dim3(256), 0, CS(stream), (const bf16*)x,
                            (const float*)w, (const float*)(w + C), (const float*)gamma, (const float*)beta, (bf16*)y, (float*)mean,
-                           (float*)rstd, rows, C, eps, relu);
+                           (float*)rstd, rows, C, eps, relu, (float)rows);
 }
 extern "C" int tepd_bn_bwd_nhwc(const void* dy, const void* x, const void* gamma, const void* mean, const void* rstd, void* dx,
                                 void* ws, int rows, int C, void* stream) {
@@ -700,5 +701,34 @@ extern "C" int tepd_bn_bwd_nhwc(const void* dy, const void* x, const void* gamma
   if (e != cudaSuccess) return (int)e;
   return (int)tepd::launch(bn_bwd_apply_kernel, dim3(grid_for((size_t)rows * C / 8, 256)), dim3(256), 0, CS(stream), (const bf16*)dy,
                            (const bf16*)x, (const float*)gamma, (const float*)mean, (const float*)rstd, (const float*)w,
-                           (const float*)(w + C), (bf16*)dx, rows, C);
+                           (const float*)(w + C), (bf16*)dx, rows, C, (float)rows);
+}
+// Split-phase BatchNorm for a batch that is split over devices (synchronised BatchNorm): the per-channel sums of the local
+// shard are produced by `tepd_bn_reduce_nhwc`, completed across the devices by an all-reduce of the 2 x C words, and consumed
+// by the apply halves with the GLOBAL row count.  mode 0: ws = [sum(x), sum(x^2)]; mode 1: ws = [sum(dy), sum(dy * xhat)].
+extern "C" int tepd_bn_reduce_nhwc(const void* a, const void* x, const void* mean, const void* rstd, void* ws, int rows, int C, int mode,
+                                   void* stream) {
+  if (C % 8) return -2;
+  const int rpb = 128;
+  dim3 grid((C + 255) / 256, (rows + rpb - 1) / rpb);
+  float* w = (float*)ws;
+  if (mode == 0)
+    return (int)tepd::launch(bn_reduce2_kernel<0>, grid, dim3(256), 0, CS(stream), (const bf16*)a, (const bf16*)nullptr,
+                             (const float*)nullptr, (const float*)nullptr, w, w + C, rows, C, rpb);
+  return (int)tepd::launch(bn_reduce2_kernel<1>, grid, dim3(256), 0, CS(stream), (const bf16*)a, (const bf16*)x, (const float*)mean,
+                           (const float*)rstd, w, w + C, rows, C, rpb);
+}
+extern "C" int tepd_bn_fwd_apply_nhwc(const void* x, const void* ws, const void* gamma, const void* beta, void* y, void* mean, void* rstd,
+                                      int rows, int C, float eps, int relu, float count, void* stream) {
+  if (C % 8) return -2;
+  const float* w = (const float*)ws;
+  return (int)tepd::launch(bn_fwd_apply_kernel, dim3(grid_for((size_t)rows * C / 8, 256)), dim3(256), 0, CS(stream), (const bf16*)x, w,
+                           w + C, (const float*)gamma, (const float*)beta, (bf16*)y, (float*)mean, (float*)rstd, rows, C, eps, relu, count);
+}
+extern "C" int tepd_bn_bwd_apply_nhwc(const void* dy, const void* x, const void* gamma, const void* mean, const void* rstd, const void* ws,
+                                      void* dx, int rows, int C, float count, void* stream) {
+  if (C % 8) return -2;
+  const float* w = (const float*)ws;
+  return (int)tepd::launch(bn_bwd_apply_kernel, dim3(grid_for((size_t)rows * C / 8, 256)), dim3(256), 0, CS(stream), (const bf16*)dy,
+                           (const bf16*)x, (const float*)gamma, (const float*)mean, (const float*)rstd, w, w + C, (bf16*)dx, rows, C, count);
 }

@@ -1013,6 +1013,23 @@ class Executor:
             xx, gm, bt = ins
         else:
             dy, xx, gm = ins
+        if ops.bn_native_ok(xx) and os.environ.get("TEPDIST_BN_SYNC", "native") == "native":
+            # native split phases: local sums kernel -> all-reduce of 2 x C floats -> apply kernel with the global count
+            shards = 1
+            for _, num in levels:
+                shards *= num
+            key = (self._tag, n.inputs[0 if n.op == "batchnorm" else 1].key())
+            if n.op == "batchnorm":
+                y, mean, rstd = ops.batchnorm_fwd_synced(xx, gm.float(), bt.float(), a["eps"], allsum, shards, relu=bool(a.get("relu")))
+                self.bn_sync_stats[key] = (mean, rstd)
+                return [y]
+            st_ = self.bn_sync_stats.pop(key, None)
+            if st_ is not None:
+                mean, rstd = st_
+                dx, dgl, dbl = ops.batchnorm_bwd_synced(dy, xx, gm.float(), mean, rstd, allsum, shards)
+                dg = self._grad_out(n, 1, n.outputs[1].shape); dg.add_(dgl)
+                db = self._grad_out(n, 2, n.outputs[2].shape); db.add_(dbl)
+                return [dx, dg, db]
         xf = xx.float()
         cnt = float(xf.numel() // xf.shape[1])
         for _, num in levels:

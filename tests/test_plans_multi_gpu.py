@@ -43,8 +43,8 @@ def _close(got, ref, tol=3e-2):
 
 @pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
 def test_plans_on_two_gpus_match_one_gpu(tmp_path):
-    cases = ["gpt2:auto", "gpt2:tp", "gpt2:pp2m2", "moe:ep", "mlp:dp"]
-    ref = _run("gpt2:auto+moe:auto+mlp:auto", 1, tmp_path)
+    cases = ["gpt2:auto", "gpt2:tp", "gpt2:pp2m2", "moe:ep", "mlp:dp", "conv:dp"]     # conv:dp = synchronised BatchNorm, native split phases
+    ref = _run("gpt2:auto+moe:auto+mlp:auto+conv:auto", 1, tmp_path)
     got = _run("+".join(cases), 2, tmp_path)
     for c in cases:
         _close(got[c], ref[c.split(":")[0] + ":auto"])
