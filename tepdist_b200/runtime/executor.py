@@ -1543,6 +1543,22 @@ class Executor:
             kind, mask_id = self._moe_einsum[n.id]
             rt = self._moe_routes.get((self._tag, mask_id))
             if rt is not None:
+                # the route tables describe the mask AS THIS RANK HOLDS IT ([G_local, S, E, C]); an einsum the planner sharded
+                # differently (e.g. a gradient einsum split over E instead of G) sees other local extents: keep it dense
+                Gr, Sr, Kr = rt["re"].shape
+                Er, Cr = rt["E"], rt["C"]
+                tok = ins[0] if kind == "dots" else ins[1]        # the [G, S, M] operand (gather / dots_eg_first) ...
+                exp = ins[1] if kind in ("dots", "combine") else ins[0]   # ... and the [E, G, C, M] one
+                ok = True
+                if kind in ("gather", "dots", "dots_eg_first"):
+                    ok &= tok.dim() == 3 and tuple(tok.shape[:2]) == (Gr, Sr)
+                if kind in ("combine", "dots", "dots_eg_first"):
+                    ok &= exp.dim() == 4 and tuple(exp.shape[:3]) == (Er, Gr, Cr)
+                if kind in ("gather", "combine"):
+                    ok &= tuple(ins[0].shape) == (Gr, Sr, Er, Cr)
+                if not ok:
+                    rt = None
+            if rt is not None:
                 if kind == "gather":         # "GSEC,GSM->EGCM": dispatch / d(expert output) of the combine
                     return [ops.moe_gather_scale(ins[1].contiguous(), rt["slot_src"], rt["slot_w"], rt["E"], rt["C"])]
                 if kind == "combine":        # "GSEC,EGCM->GSM": combine / d(tokens) of the dispatch

@@ -32,6 +32,8 @@ def _c_decls():
                     kinds.append("i")
                 elif base == "float":
                     kinds.append("f")
+                elif base == "unsigned long long":
+                    kinds.append("ull")
                 else:
                     kinds.append("?" + base)
             assert name not in decls, f"{name} declared twice"
@@ -48,8 +50,11 @@ def _kind(t):
         return "ll"
     if t is ctypes.c_float:
         return "f"
+    if t in (ctypes.c_ulonglong, ctypes.c_ulong) and ctypes.sizeof(t) == 8:
+        return "ull"
     if isinstance(t, type) and issubclass(t, ctypes._Pointer):
-        return "pp"
+        # POINTER(c_void_p) = an array of pointers / an out-pointer to a pointer ("pp"); POINTER(<scalar>) = a plain out-parameter
+        return "pp" if t._type_ is ctypes.c_void_p else "p"
     return "?" + repr(t)
 
 
@@ -74,6 +79,7 @@ def _python_tables():
     tables = {n: getattr(ops._Sig, n) for n in dir(ops._Sig) if n.startswith("tepd_")}
     lib = _FakeLib()
     symm._sigs(lib)
+    symm._vmm_sigs(lib)
     symm._peer_sig(lib)
     moe._sig(lib)
     for name, fn in lib.fns.items():
@@ -104,6 +110,6 @@ def test_every_ctypes_table_matches_its_extern_c_declaration():
 def test_every_kernel_entry_point_used_from_python_has_a_table():
     """Entry points without an argtypes table would be called with ctypes' default int conversion (truncates 64-bit pointers)."""
     decls, tables = _c_decls(), _python_tables()
-    internal = {"tepd_make_tmap_bf16_3d", "tepd_make_tmap_bshd"}       # called from C++ only
+    internal = {"tepd_make_tmap_bf16_3d", "tepd_make_tmap_bshd", "tepd_make_tmap_3d"}       # called from C++ only
     missing = sorted(set(decls) - set(tables) - internal)
     assert not missing, missing
