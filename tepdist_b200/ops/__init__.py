@@ -97,6 +97,7 @@ class _Sig:
     tepd_sgd = [_vp, _vp, _vp, _ll, _f, _f, _vp]
     tepd_axpy_f32 = [_vp, _vp, _ll, _f, _vp]
     tepd_cast_f32_bf16 = [_vp, _vp, _ll, _vp]
+    tepd_ew_bf16 = [_vp, _vp, _vp, _ll, _i, _vp]
     tepd_moe_gather_scale = [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp]
     tepd_moe_combine_sum = [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp]
     tepd_moe_route_dots = [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp]
@@ -331,6 +332,31 @@ def einsum(eq: str, a: torch.Tensor, b: torch.Tensor, _force: bool = False) -> t
     if cur != out_idx:
         d = d.permute([cur.index(c) for c in out_idx]).contiguous()
     return d
+
+
+def _dense_same_layout(*ts: torch.Tensor) -> bool:
+    """All tensors bf16 on the GPU, same shape and strides, dense in memory (any of contiguous / channels_last): an elementwise
+    kernel may then walk the raw storage linearly."""
+    t0 = ts[0]
+    if not (t0.is_cuda and t0.dtype == torch.bfloat16 and t0.numel() % 8 == 0 and t0.numel() > 0):
+        return False
+    if not (t0.is_contiguous() or (t0.dim() == 4 and t0.is_contiguous(memory_format=torch.channels_last))):
+        return False
+    return all(t.dtype == t0.dtype and t.shape == t0.shape and t.stride() == t0.stride() and t.is_cuda for t in ts[1:])
+
+
+def ew_native(mode: str, a: torch.Tensor, b: Optional[torch.Tensor] = None) -> Optional[torch.Tensor]:
+    """relu(a) | relu_bwd: a * (b > 0) | add: a + b with the own vectorised kernel; None when the operands do not qualify
+    (the caller then uses the torch op)."""
+    ts = (a,) if b is None else (a, b)
+    if not _dense_same_layout(*ts):
+        return None
+    out = torch.empty_like(a)
+    rc = lib().tepd_ew_bf16(a.data_ptr(), a.data_ptr() if b is None else b.data_ptr(), out.data_ptr(), a.numel(),
+                            {"relu": 0, "relu_bwd": 1, "add": 2}[mode], _stream())
+    _check(rc, "ew_bf16")
+    _count()
+    return out
 
 
 # --------------------------------------------------------------------------------------------- MoE route-table kernels

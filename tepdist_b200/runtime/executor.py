@@ -1393,6 +1393,10 @@ class Executor:
         op, a = n.op, n.attrs
         F = torch.nn.functional
         x = ins[0] if ins else None
+        if op in ("add", "relu", "relu_bwd") and x.is_cuda:      # own vectorised kernels for the conv-net elementwise ops
+            y = ops.ew_native(op, ins[0], ins[1] if len(ins) > 1 else None)
+            if y is not None:
+                return [y]
         if op == "add": return [ins[0] + ins[1]]
         if op == "sub": return [ins[0] - ins[1]]
         if op == "mul": return [ins[0] * ins[1]]

@@ -601,6 +601,26 @@ def check_einsum():
     return out
 
 
+def check_ew():
+    """Own elementwise kernels of the conv path (ReLU, ReLU backward, residual add) on contiguous and channels_last tensors."""
+    from tepdist_b200 import ops
+    out = {}
+    torch.manual_seed(5)
+    for tag, mk in (("nchw", lambda t: t), ("nhwc", lambda t: t.contiguous(memory_format=torch.channels_last))):
+        a = mk(torch.randn(4, 64, 14, 14, device="cuda").to(torch.bfloat16))
+        b = mk(torch.randn(4, 64, 14, 14, device="cuda").to(torch.bfloat16))
+        n0 = ops.launch_count()
+        r = ops.ew_native("relu", a)
+        rb = ops.ew_native("relu_bwd", a, r)
+        ad = ops.ew_native("add", a, b)
+        assert ops.launch_count() - n0 == 3 and r.stride() == a.stride()
+        assert torch.equal(r, a.relu()) and torch.equal(rb, a * (r > 0).to(a.dtype))
+        out["add_" + tag] = _rel_err(ad, a.float() + b.float())
+        assert out["add_" + tag] < 1e-2
+    assert ops.ew_native("add", a, b[:, :32]) is None        # shapes differ: caller falls back to the torch op
+    return out
+
+
 def check_moe_routes():
     """Route-table dispatch / combine kernels (ops.moe_gather_scale / moe_combine_sum / moe_route_dots) vs their plain torch
     reference (the CPU branch of the same functions, fp32), with dropped routes; then time vs the dense einsum they replace."""
@@ -646,6 +666,7 @@ CHECKS = {
     "conv": check_conv,
     "einsum": check_einsum,
     "moe_routes": check_moe_routes,
+    "ew": check_ew,
     "attn_d48": check_attn_d48,
     "attn_poly": check_attn_poly,
     "attn_fwd2": check_attn_fwd2,
