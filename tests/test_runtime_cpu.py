@@ -455,3 +455,52 @@ def test_moe_route_table_path_equals_the_dense_einsums():
     ld, _, _ = run(g2, f2, False)
     ls, _, ns = run(g2, f2, True)
     assert ns == 6 and all(abs(a - b) <= 1e-5 * max(1.0, abs(b)) for a, b in zip(ls, ld)), (ls, ld)
+
+
+def test_flat_bucket_policy_is_graded_aligned_and_covers_the_buffer():
+    """B7 (storage-order variant, executed by the runtime): bucket boundaries over the flat gradient buffer start small and double
+    up to the cap, only ever fall on variable starts that are multiples of the chunk granularity, and tile [0, end) exactly."""
+    offs, o = [], 0
+    sizes = [1 << 20] * 12 + [3 << 20] * 30 + [50 << 20, 1 << 18, 1 << 18]
+    for sz in sizes:
+        offs.append(o)
+        o += sz
+    end = o
+    gran = 8 * 128
+    b = list(_C.plan_flat_buckets(offs, end, gran, 4 << 20, 48 << 20))
+    assert b[0] == 0 and b[-1] == end and b == sorted(set(b))
+    assert all(x in offs and x % gran == 0 for x in b[1:-1])
+    widths = [b[i + 1] - b[i] for i in range(len(b) - 1)]
+    assert widths[0] >= 4 << 20 and widths[0] < widths[2]             # graded: the first buckets are the small ones
+    assert all(w >= min(48 << 20, (4 << 20) << min(i, 16)) or i == len(widths) - 1 for i, w in enumerate(widths))
+    # the same policy the executor used to compute in Python
+    ref = [0]
+    for off in offs[1:]:
+        want = min(48 << 20, (4 << 20) << min(len(ref) - 1, 16))
+        if off - ref[-1] >= want and off % gran == 0:
+            ref.append(off)
+    ref.append(end)
+    assert b == ref
+
+
+def test_pipeline_slot_assignment_follows_the_release_plan():
+    """CUDA-graph stage bodies: slots are taken at a micro-batch's first task (a hoisted forward Recv counts) and returned where the
+    scheduler releases the micro-batch -- never more slots than micro-batches in flight, never a slot shared by two live ones."""
+    import types
+    from tepdist_b200.models.gpt2 import CONFIGS, build_gpt2_graph
+    from tepdist_b200.parallel import plan_pipeline
+    from tepdist_b200.runtime.pipeline import StageWorker
+    g = build_gpt2_graph(CONFIGS["tiny"], batch=8)
+    _, info, tasks = plan_pipeline(g, 4, 4, 8)
+    for dev, lst in tasks.items():
+        w = types.SimpleNamespace()
+        StageWorker.plan_slots(w, lst)
+        assert set(w.slot_of) == set(range(8)) and 1 <= w.num_slots <= 4 + 1, (dev, w.slot_of)
+        live = {}
+        for t in lst:
+            m = t["micro"]
+            if m is not None and m >= 0 and not t["backward"] and t["type"] in ("Recv", "Compute", "Input") and m not in live.values():
+                assert w.slot_of[m] not in live, (dev, m, live)
+                live[w.slot_of[m]] = m
+            for dead in t.get("release", ()):
+                live.pop(w.slot_of[dead], None)
