@@ -67,3 +67,20 @@ elif which == "conv":
         y = ops.conv2d_fwd(x, w, 1, 1)
         ops.conv2d_dgrad(y, w, x.shape, 1, 1)
     torch.cuda.synchronize()
+if which == "moe":                # GPT-MoE per-GPU shapes under EP-8: route-table gather / combine / dots + the expert FC einsums
+    G, S, E, C, M, H = 1, 8192, 8, 256, 768, 6144
+    x = torch.randn(G, S, M, device="cuda", dtype=torch.bfloat16)
+    y = torch.randn(E, G, C, M, device="cuda", dtype=torch.bfloat16)
+    slot_src = torch.randint(0, S, (G, E, C), device="cuda", dtype=torch.int32)
+    slot_w = torch.rand(G, E, C, device="cuda")
+    re = torch.randint(0, E, (G, S, 2), device="cuda", dtype=torch.int32)
+    rc = torch.randint(0, C, (G, S, 2), device="cuda", dtype=torch.int32)
+    gw = torch.rand(G, S, 2, device="cuda")
+    xe = torch.randn(1, 8, 256, M, device="cuda", dtype=torch.bfloat16)
+    wi = torch.randn(1, M, H, device="cuda", dtype=torch.bfloat16)
+    for _ in range(4):
+        ops.moe_gather_scale(x, slot_src, slot_w, E, C)
+        ops.moe_combine_sum(y, re, rc, gw, S)
+        ops.moe_route_dots(x, y, re, rc)
+        ops.einsum("EGCM,EMH->EGCH", xe, wi)
+    torch.cuda.synchronize()

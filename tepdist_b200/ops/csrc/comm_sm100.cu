@@ -49,7 +49,9 @@ __global__ void symm_barrier_kernel(PeerPtrs flags, int n, int rank, uint32_t* l
     __threadfence_system();
     st_release_sys(reinterpret_cast<uint32_t*>(flags.p[t]) + rank, epoch);
     const uint32_t* mine = reinterpret_cast<const uint32_t*>(flags.p[rank]) + t;
+    const long long t0 = clock64();
     while ((int32_t)(ld_acquire_sys(mine) - epoch) < 0) {
+      if (clock64() - t0 > 20000000000LL) __trap();   // ~10 s of SM clocks: a peer that never arrives fails the launch loudly
     }
   }
   __syncthreads();
