@@ -8,8 +8,9 @@ step() {
   timeout "$t" "$@" > "$out/$name.log" 2>&1
   echo "$name rc=$? $(( $(date +%s) - t0 ))s" | tee -a $out/summary.txt
 }
-step pytest_gpu 600 python -m pytest tests -m gpu -x -q
+
 step smoke      120 python -c "import __graft_entry__ as g; g.smoke()"
 step bench_n1   200 python bench.py --steps 20 --warmup 5
+step pytest_gpu 300 python -m pytest tests -m gpu -x -q
 cat $out/summary.txt
 tail -n 1 $out/bench_n1.log | cut -c1-300

@@ -64,6 +64,9 @@ SyncFreeResult SyncFreeAnalysis(const Graph& g, int num_micro) {
           if (s.is_split() || s.partial) clean = false;
       }
     }
+    // a sequence split that runs through attention is NOT sync-free: the "seq" candidate communicates inside the node (K / V ring)
+    for (auto& n : c.nodes)
+      if ((n.op == "attention" || n.op == "attention_bwd") && plan.choice[n.id].tag == "seq") clean = false;
     if (!clean) continue;
     if (split > best.num_split_values) {
       best.ok = true;

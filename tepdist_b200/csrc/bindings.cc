@@ -131,6 +131,8 @@ PYBIND11_MODULE(_C, m) {
         for (auto& kv : g.nodes[i].attrs) d[py::str(kv.first)] = FromAttr(kv.second);
         return d;
       })
+      .def("set_node_attr", [](Graph& g, int i, const std::string& k, py::object v) { g.nodes[i].attrs[k] = ToAttr(v); })
+      .def("erase_node_attr", [](Graph& g, int i, const std::string& k) { g.nodes[i].attrs.erase(k); })
       .def("node_dist", [](const Graph& g, int i) { return g.nodes[i].dist; })
       .def("outputs", [](const Graph& g) {
         std::vector<std::pair<int, int>> r;
@@ -182,6 +184,7 @@ PYBIND11_MODULE(_C, m) {
       .def_readwrite("num", &SpmdOptions::num)
       .def_readwrite("var_mem_limit", &SpmdOptions::var_mem_limit)
       .def_readwrite("mem_split_min_rank", &SpmdOptions::mem_split_min_rank)
+      .def_readwrite("context_parallel", &SpmdOptions::context_parallel)
       .def_readwrite("collective_latency_bytes", &SpmdOptions::collective_latency_bytes)
       .def_readwrite("min_segment_flops_frac", &SpmdOptions::min_segment_flops_frac)
       .def_readwrite("cost_factor", &SpmdOptions::cost_factor)

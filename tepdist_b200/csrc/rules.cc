@@ -190,26 +190,38 @@ void LayerNormBwdRule(Ctx& c) {
     if (c.divisible(x, d)) c.add({c.S(d), c.S(d), c.G()}, {c.S(d), c.P(), c.P()}, "dim" + std::to_string(d));
   c.add_glue();
 }
-void AttentionRule(Ctx& c) {
+// Context parallelism ("seq" candidates): the sequence stays split through attention; every rank keeps its query block and the
+// K / V blocks travel around a ring (causal: blocks from later ranks are skipped, the diagonal block is masked), partial outputs
+// merge by log-sum-exp.  The reference has no such op (long context = token split + what XLA SPMD makes of the dots);
+// priced as the K / V all-gather it replaces (forward) plus the dK / dV reduce-scatter (backward).
+double RingBytes(const TensorType& qkv, int num) { return (double)qkv.bytes() * (2.0 / 3.0) * (num - 1) / num; }
+void AttentionRule(Ctx& c, const RuleOptions& opt) {
   // qkv [B,S,H*3*D] (heads-major, so a plain last-dim split is a split over heads) -> o [B,S,H*D], lse [B,H,S]
   const int64_t H = c.n.attr_i("heads");
-  if (c.divisible(c.in(0), 0)) c.add({c.S(0)}, {c.S(0), c.S(0)}, "batch");
-  if (H % c.num == 0) c.add({c.S(2)}, {c.S(2), c.S(1)}, "heads");
-  c.add_glue();
+  const bool cp = opt.context_parallel && c.divisible(c.in(0), 1);   // "cp": the sequence split is the only way through attention
+  if (c.divisible(c.in(0), 0) && !cp) c.add({c.S(0)}, {c.S(0), c.S(0)}, "batch");
+  if (H % c.num == 0 && !cp) c.add({c.S(2)}, {c.S(2), c.S(1)}, "heads");
+  if (c.divisible(c.in(0), 1)) c.add({c.S(1)}, {c.S(1), c.S(2)}, "seq", RingBytes(c.in(0), c.num));
+  if (!cp) c.add_glue();   // (replicated attention = n x the S^2 FLOPs per rank: never what "cp" asks for)
 }
-void AttentionBwdRule(Ctx& c) {
+void AttentionBwdRule(Ctx& c, const RuleOptions& opt) {
   const int64_t H = c.n.attr_i("heads");  // (do, qkv, o, lse) -> dqkv
-  if (c.divisible(c.in(1), 0)) c.add({c.S(0), c.S(0), c.S(0), c.S(0)}, {c.S(0)}, "batch");
-  if (H % c.num == 0) c.add({c.S(2), c.S(2), c.S(2), c.S(1)}, {c.S(2)}, "heads");
-  c.add_glue();
+  const bool cp = opt.context_parallel && c.divisible(c.in(1), 1);
+  if (c.divisible(c.in(1), 0) && !cp) c.add({c.S(0), c.S(0), c.S(0), c.S(0)}, {c.S(0)}, "batch");
+  if (H % c.num == 0 && !cp) c.add({c.S(2), c.S(2), c.S(2), c.S(1)}, {c.S(2)}, "heads");
+  if (c.divisible(c.in(1), 1)) c.add({c.S(1), c.S(1), c.S(1), c.S(2)}, {c.S(1)}, "seq", 2.0 * RingBytes(c.in(1), c.num));
+  if (!cp) c.add_glue();
 }
 void EmbeddingRule(Ctx& c) {  // tokens[B,S], wte[V,C], wpe[S,C] -> [B,S,C]
   if (c.divisible(c.in(0), 0)) c.add({c.S(0), c.G(), c.G()}, {c.S(0)}, "batch");
+  // sequence split: rank r embeds positions [r S/n, (r+1) S/n) -- exactly the rows of a position table stored split on dim 0
+  if (c.divisible(c.in(0), 1) && c.in(2).dims[0] == c.in(0).dims[1]) c.add({c.S(1), c.G(), c.S(0)}, {c.S(1)}, "seq");
   c.add({c.G(), c.S(1), c.S(1)}, {c.S(2)}, "hidden");
   c.add_glue();
 }
 void EmbeddingBwdRule(Ctx& c) {  // tokens, dy[B,S,C] -> dwte[V,C], dwpe[S,C]
   if (c.divisible(c.in(0), 0)) c.add({c.S(0), c.S(0)}, {c.P(), c.P()}, "batch");
+  if (c.divisible(c.in(0), 1) && c.o(1).dims[0] == c.in(0).dims[1]) c.add({c.S(1), c.S(1)}, {c.P(), c.S(0)}, "seq");
   c.add({c.G(), c.S(2)}, {c.S(1), c.S(1)}, "hidden");
   c.add_glue();
 }
@@ -489,8 +501,8 @@ std::vector<Candidate> EnumerateCandidates(const Graph& g, const Node& n, int nu
   else if (op == "conv2d" || op == "conv2d_dgrad" || op == "conv2d_wgrad") ConvRule(c, opt);
   else if (op == "layernorm") LayerNormRule(c);
   else if (op == "layernorm_bwd") LayerNormBwdRule(c);
-  else if (op == "attention") AttentionRule(c);
-  else if (op == "attention_bwd") AttentionBwdRule(c);
+  else if (op == "attention") AttentionRule(c, opt);
+  else if (op == "attention_bwd") AttentionBwdRule(c, opt);
   else if (op == "embedding") EmbeddingRule(c);
   else if (op == "embedding_bwd") EmbeddingBwdRule(c);
   else if (op == "softmax_xent") XentRule(c);

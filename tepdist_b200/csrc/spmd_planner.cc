@@ -78,6 +78,7 @@ void BuildProblem(Problem& p, SpmdStats* stats) {
   for (auto& n : g.nodes) {
     RuleOptions ro;
     ro.save_variable_mem = IsComputeIntensive(n.op) && mem_save_groups.count(n.group) > 0;
+    ro.context_parallel = opt.context_parallel;
     if (ro.save_variable_mem) p.forced.insert(n.id);   // (candidates restricted to the ones that keep the weight split)
     auto c = EnumerateCandidates(g, n, opt.num, ro);
     // user annotations (xla_sharding.split / replicate equivalents)
@@ -105,6 +106,12 @@ void BuildProblem(Problem& p, SpmdStats* stats) {
     nc.resize(c.size());
     for (size_t i = 0; i < c.size(); ++i) {
       double cost = c[i].node_cost;
+      if (c[i].tag == "seq" && (n.op == "attention" || n.op == "attention_bwd")) {
+        // the ring posts one exchange per hop (forward: K / V; backward: K / V and the dK / dV accumulator): same per-launch
+        // price as every other collective, or the ring would look free next to the gathers it competes with
+        const double lat = opt.collective_latency_bytes >= 0 ? opt.collective_latency_bytes : opt.hw.coll_latency * opt.hw.link_bw;
+        cost += lat * (n.op == "attention" ? opt.num - 1 : 2 * opt.num - 1);
+      }
       bool all_glue = true;
       for (auto& s : c[i].outs) all_glue &= s.is_glue();
       if (IsVariable(n.op)) {
@@ -115,6 +122,11 @@ void BuildProblem(Problem& p, SpmdStats* stats) {
         double b = 0;
         for (auto& t : n.outputs) b += (double)t.bytes();
         cost += opt.replicate_penalty * b * (1.0 - 1.0 / opt.num);
+        // attention is the one op here whose work grows with the SQUARE of a dim while its bytes grow linearly: running it
+        // replicated repeats (n-1)/n of those FLOPs on every rank -- priced as the bytes the links move in that time, so that
+        // past a few hundred tokens the K / V ring ("seq") beats gathering the sequence
+        if (n.op == "attention" || n.op == "attention_bwd")
+          cost += NodeFlops(g, n) * (1.0 - 1.0 / opt.num) * opt.hw.link_bw / opt.hw.flops;
       }
       for (int o = 0; o < (int)n.outputs.size(); ++o)
         if (fetch.count(ValueRef{n.id, o}))

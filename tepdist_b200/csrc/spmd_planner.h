@@ -22,6 +22,7 @@ namespace tepdist {
 struct SpmdOptions {
   int num = 2;                       // devices at this mesh level
   double var_mem_limit = 150e9;      // VAR_MEM_LIMIT (bytes per device for variables + slots + grads)
+  bool context_parallel = false;     // attention never reshards to heads: the sequence split stays, K / V ride a ring ("cp" strategy)
   int mem_split_min_rank = 1;        // memory plan: only variables of at least this rank may be FORCED to be stored sharded
                                      // (2 = matrices only: Megatron-style tensor parallelism keeps biases / LayerNorm vectors whole)
   double cost_factor = 1.0;          // COST_FACTOR (all-to-all weight)

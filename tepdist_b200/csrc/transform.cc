@@ -100,6 +100,13 @@ struct Rewriter {
     }
     if (op == "attention" || op == "attention_bwd") {
       if (c.tag == "heads") a["heads"] = (int64_t)(n.attr_i("heads") / num);
+      if (c.tag == "seq") {   // context parallel: the runtime runs the K / V ring over the ranks of this level
+        std::vector<int64_t> lv = n.attr_v("cp_levels"), nm = n.attr_v("cp_nums");
+        lv.push_back((int64_t)level);
+        nm.push_back((int64_t)num);
+        a["cp_levels"] = lv;
+        a["cp_nums"] = nm;
+      }
     }
     if (op == "softmax_xent") {
       const TensorType& l = g.type(n.inputs[0]);

@@ -86,9 +86,15 @@ def attention_bwd(do: torch.Tensor, q, k, v, o, lse, scale: float | None = None,
         dq.copy_(gq[:, :S, :, :D]); dk.copy_(gk[:, :S, :, :D]); dv.copy_(gv[:, :S, :, :D])
         return dq, dk, dv
     if not q.is_cuda or D != _HD or S % 128:
-        _, _, p = _ref_fwd(q, k, v, scale, causal)
         dof = do.float().permute(0, 2, 1, 3)
         qf, kf, vf = (t.float().permute(0, 2, 1, 3) for t in (q, k, v))
+        # probabilities from the GIVEN log-sum-exp (like the kernels): a block of a longer key sequence (ring attention) passes
+        # the log-sum-exp over ALL keys, and its probabilities must not be re-normalised over the block
+        sc = torch.matmul(qf, kf.transpose(-1, -2)) * scale
+        if causal:
+            mask = torch.ones(S, S, dtype=torch.bool, device=q.device).tril()
+            sc = sc.masked_fill(~mask, float("-inf"))
+        p = torch.exp(sc - lse.float().unsqueeze(-1))
         dvf = torch.matmul(p.transpose(-1, -2), dof)
         dp = torch.matmul(dof, vf.transpose(-1, -2))
         delta = (dof * o.float().permute(0, 2, 1, 3)).sum(-1, keepdim=True)
@@ -109,3 +115,57 @@ def attention_bwd(do: torch.Tensor, q, k, v, o, lse, scale: float | None = None,
                                dq.stride(0), dq.stride(1), dq.stride(2), _stream()), "attn_bwd")
     _count(3)
     return dq, dk, dv
+
+
+# --------------------------------------------------------------------------------------------- ring (context-parallel) helpers
+def _native_ring(*ts: torch.Tensor) -> bool:
+    return all(t.is_cuda and t.is_contiguous() for t in ts) and ts[0].shape[-1] % 8 == 0
+
+
+def attn_merge_(o_acc: torch.Tensor, lse_acc: torch.Tensor, lse_out: torch.Tensor, o_j: torch.Tensor, lse_j: torch.Tensor,
+                first: bool) -> torch.Tensor:
+    """Log-sum-exp merge of one block's partial attention (o_j [B,L,H,D], lse_j [B,H,L]) into the running fp32 pair
+    (o_acc in place; the merged log-sum-exp goes to `lse_out`, which is returned).  One kernel (elementwise_sm100.cu
+    attn_merge_kernel); plain torch math on CPU."""
+    B, L, H, D = o_j.shape
+    if o_j.dtype == torch.bfloat16 and _native_ring(o_j, o_acc, lse_acc, lse_out, lse_j):
+        from . import lib, _check, _count, _stream
+        _check(lib().tepd_attn_merge(o_acc.data_ptr(), lse_acc.data_ptr(), lse_out.data_ptr(), o_j.data_ptr(), lse_j.data_ptr(),
+                                     B, L, H, D, int(first), _stream()), "attn_merge")
+        _count()
+        return lse_out
+    if first:
+        o_acc.copy_(o_j)
+        lse_out.copy_(lse_j)
+        return lse_out
+    new = torch.logaddexp(lse_acc, lse_j)
+    wa = torch.exp(lse_acc - new).permute(0, 2, 1).unsqueeze(-1)     # [B,L,H,1]
+    wj = torch.exp(lse_j - new).permute(0, 2, 1).unsqueeze(-1)
+    o_acc.mul_(wa).add_(o_j.float() * wj)
+    lse_out.copy_(new)
+    return lse_out
+
+
+def attn_ring_accum_(dq_acc: torch.Tensor, kv_acc: torch.Tensor, part: torch.Tensor) -> None:
+    """dq_acc [B,L,H,D] += part[..,0,:]; kv_acc [B,L,H,2,D] += part[..,1:,:] (part [B,L,H,3,D]: one block's dq / dk / dv)."""
+    if part.dtype == torch.bfloat16 and _native_ring(part, dq_acc, kv_acc):
+        from . import lib, _check, _count, _stream
+        _check(lib().tepd_attn_ring_accum(dq_acc.data_ptr(), kv_acc.data_ptr(), part.data_ptr(), dq_acc.numel() // dq_acc.shape[-1],
+                                          dq_acc.shape[-1], 0, _stream()), "attn_ring_accum")
+        _count()
+        return
+    dq_acc += part[:, :, :, 0]
+    kv_acc += part[:, :, :, 1:]
+
+
+def attn_ring_pack(dq_acc: torch.Tensor, kv_acc: torch.Tensor, out: torch.Tensor) -> torch.Tensor:
+    """out [B,L,H,3,D] (compute dtype) <- the fp32 accumulators at the end of the ring."""
+    if out.dtype == torch.bfloat16 and _native_ring(out, dq_acc, kv_acc):
+        from . import lib, _check, _count, _stream
+        _check(lib().tepd_attn_ring_accum(dq_acc.data_ptr(), kv_acc.data_ptr(), out.data_ptr(), dq_acc.numel() // dq_acc.shape[-1],
+                                          dq_acc.shape[-1], 1, _stream()), "attn_ring_pack")
+        _count()
+        return out
+    out[:, :, :, 0].copy_(dq_acc)
+    out[:, :, :, 1:].copy_(kv_acc)
+    return out

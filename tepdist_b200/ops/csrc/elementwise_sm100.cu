@@ -588,6 +588,67 @@ __global__ void __launch_bounds__(256) cast_f32_bf16_vec_kernel(const float4* __
   }
 }
 
+// ---- ring (context-parallel) attention helpers.  Layouts: o / dq [B,L,H,D], lse [B,H,L], qkv-like [B,L,H,3,D], kv-like [B,L,H,2,D];
+// D % 8 == 0; one thread per 8 consecutive d.
+// merge: (o_acc, lse_in) <- log-sum-exp merge with one block's (o_j, lse_j); lse written to lse_out (ping-pong: every thread of a
+// row reads lse_in).  first != 0: plain initialisation.
+__global__ void __launch_bounds__(256) attn_merge_kernel(float* __restrict__ o_acc, const float* __restrict__ lse_in,
+                                                         float* __restrict__ lse_out, const bf16* __restrict__ o_j,
+                                                         const float* __restrict__ lse_j, int B, int L, int H, int D, int first) {
+  const int dv = D / 8;
+  const size_t nvec = (size_t)B * L * H * dv;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < nvec; i += (size_t)gridDim.x * blockDim.x) {
+    const size_t row = i / dv;                     // (b, l, h)
+    const int h = (int)(row % H), l = (int)((row / H) % L), b = (int)(row / ((size_t)H * L));
+    const size_t li = ((size_t)b * H + h) * L + l;
+    float x[8];
+    unpack8(__ldg(reinterpret_cast<const uint4*>(o_j) + i), x);
+    float4* oa = reinterpret_cast<float4*>(o_acc) + 2 * i;
+    const float lj = __ldg(lse_j + li);
+    if (first) {
+      oa[0] = make_float4(x[0], x[1], x[2], x[3]);
+      oa[1] = make_float4(x[4], x[5], x[6], x[7]);
+      if (i % dv == 0) lse_out[li] = lj;
+      continue;
+    }
+    const float la = __ldg(lse_in + li);
+    const float mx = fmaxf(la, lj);
+    const float nw = mx + __logf(__expf(la - mx) + __expf(lj - mx));
+    const float wa = __expf(la - nw), wj = __expf(lj - nw);
+    float4 a0 = oa[0], a1 = oa[1];
+    a0.x = a0.x * wa + x[0] * wj; a0.y = a0.y * wa + x[1] * wj; a0.z = a0.z * wa + x[2] * wj; a0.w = a0.w * wa + x[3] * wj;
+    a1.x = a1.x * wa + x[4] * wj; a1.y = a1.y * wa + x[5] * wj; a1.z = a1.z * wa + x[6] * wj; a1.w = a1.w * wa + x[7] * wj;
+    oa[0] = a0; oa[1] = a1;
+    if (i % dv == 0) lse_out[li] = nw;
+  }
+}
+// accum: dq_acc [B,L,H,D] += part[..,0,:];  kv_acc [B,L,H,2,D] += part[..,1:3,:]   (part = one block's bf16 dq / dk / dv)
+// pack (PACK = 1): the inverse at the end of the ring: part[..,0,:] = bf16(dq_acc), part[..,1:3,:] = bf16(kv_acc)
+template <int PACK>
+__global__ void __launch_bounds__(256) attn_ring_accum_kernel(float* __restrict__ dq_acc, float* __restrict__ kv_acc, bf16* __restrict__ part,
+                                                              size_t rows, int D) {
+  const int dv = D / 8;
+  const size_t nvec = rows * 3 * dv;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < nvec; i += (size_t)gridDim.x * blockDim.x) {
+    const int c = (int)(i % dv), slot = (int)((i / dv) % 3);
+    const size_t row = i / ((size_t)3 * dv);
+    float* dst = slot == 0 ? dq_acc + (row * D + (size_t)c * 8) : kv_acc + ((row * 2 + (slot - 1)) * D + (size_t)c * 8);
+    float4* d4 = reinterpret_cast<float4*>(dst);
+    if (PACK) {
+      const float4 a0 = d4[0], a1 = d4[1];
+      float o[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+      reinterpret_cast<uint4*>(part)[i] = pack8(o);
+    } else {
+      float x[8];
+      unpack8(__ldg(reinterpret_cast<const uint4*>(part) + i), x);
+      float4 a0 = d4[0], a1 = d4[1];
+      a0.x += x[0]; a0.y += x[1]; a0.z += x[2]; a0.w += x[3];
+      a1.x += x[4]; a1.y += x[5]; a1.z += x[6]; a1.w += x[7];
+      d4[0] = a0; d4[1] = a1;
+    }
+  }
+}
+
 inline int grid_for(size_t work, int threads) {
   size_t b = (work + threads - 1) / threads;
   size_t cap = 148 * 8;
@@ -689,6 +750,20 @@ extern "C" int tepd_ew_bf16(const void* a, const void* b, void* out, long long n
   if (mode == 0) return (int)tepd::launch(ew_bf16_kernel<0>, grid, dim3(256), 0, CS(stream), (const uint4*)a, (const uint4*)b, (uint4*)out, nvec);
   if (mode == 1) return (int)tepd::launch(ew_bf16_kernel<1>, grid, dim3(256), 0, CS(stream), (const uint4*)a, (const uint4*)b, (uint4*)out, nvec);
   return (int)tepd::launch(ew_bf16_kernel<2>, grid, dim3(256), 0, CS(stream), (const uint4*)a, (const uint4*)b, (uint4*)out, nvec);
+}
+extern "C" int tepd_attn_merge(void* o_acc, const void* lse_in, void* lse_out, const void* o_j, const void* lse_j, int B, int L, int H,
+                               int D, int first, void* stream) {
+  if (D % 8 || ((reinterpret_cast<uintptr_t>(o_acc) | reinterpret_cast<uintptr_t>(o_j)) & 15)) return -2;
+  attn_merge_kernel<<<grid_for((size_t)B * L * H * (D / 8), 256), 256, 0, CS(stream)>>>((float*)o_acc, (const float*)lse_in, (float*)lse_out,
+                                                                                      (const bf16*)o_j, (const float*)lse_j, B, L, H, D, first);
+  return (int)cudaGetLastError();
+}
+extern "C" int tepd_attn_ring_accum(void* dq_acc, void* kv_acc, void* part, long long rows, int D, int pack, void* stream) {
+  if (D % 8 || ((reinterpret_cast<uintptr_t>(dq_acc) | reinterpret_cast<uintptr_t>(kv_acc) | reinterpret_cast<uintptr_t>(part)) & 15)) return -2;
+  const int grid = grid_for((size_t)rows * 3 * (D / 8), 256);
+  if (pack) attn_ring_accum_kernel<1><<<grid, 256, 0, CS(stream)>>>((float*)dq_acc, (float*)kv_acc, (bf16*)part, (size_t)rows, D);
+  else attn_ring_accum_kernel<0><<<grid, 256, 0, CS(stream)>>>((float*)dq_acc, (float*)kv_acc, (bf16*)part, (size_t)rows, D);
+  return (int)cudaGetLastError();
 }
 extern "C" int tepd_cast_f32_bf16(const void* in, void* out, long long n, void* stream) {
   if (n % 8 == 0 && (reinterpret_cast<uintptr_t>(in) & 31) == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0)

@@ -17,16 +17,20 @@ def plan_spmd(graph: Graph, num: int, strategy: str = "auto", options: Optional[
     from ..planner import from_native, merge_client_attrs, to_native
     options = dict(options or {})
     g = graph
-    if strategy in ("dp", "tp"):
+    if strategy in ("dp", "tp", "cp"):
         g = Graph.from_dict(graph.to_dict())
         for n in g.nodes:
             if n.op == "input":
-                n.attrs["sharding"] = {"0": {"dim": 0 if strategy == "dp" else -1, "num": num}}
+                # "cp" (context parallel): every [batch, sequence, ...] sample input is cut along the SEQUENCE
+                dim = {"dp": 0, "tp": -1}.get(strategy, 1 if len(n.outputs[0].shape) >= 2 else -1)
+                n.attrs["sharding"] = {"0": {"dim": dim, "num": num}}
     cg = to_native(g)
     o = _C.SpmdOptions()
     o.num = num
-    if strategy in ("dp", "tp"):
+    if strategy in ("dp", "tp", "cp"):
         o.ignore_annotation = False
+    if strategy == "cp":
+        o.context_parallel = True
     if strategy == "tp":
         o.var_mem_limit = 1.0  # force every weight MATRIX to be stored sharded -> tensor parallel (vectors stay whole)
         o.mem_split_min_rank = 2
@@ -71,7 +75,8 @@ def plan_spmd(graph: Graph, num: int, strategy: str = "auto", options: Optional[
         if cg.node_op(i) == "einsum" and c.tag == "batch" and w_split:
             kind = "ep"   # a batch (expert) dim of the weight is split: expert parallel
         tags[kind] = tags.get(kind, 0) + 1
-    info = {"comm_info": st.comm_info(), "comm_bytes": plan.stats.comm_bytes, "solve_seconds": plan.stats.solve_seconds,
+    ring = sum(1 for i in range(cg.num_nodes()) if cg.node_op(i) == "attention" and plan.choice[i].tag == "seq")
+    info = {"context_parallel": ring, "comm_info": st.comm_info(), "comm_bytes": plan.stats.comm_bytes, "solve_seconds": plan.stats.solve_seconds,
             "subgraphs": plan.stats.num_subgraphs, "distinct_subgraphs": plan.stats.distinct_subgraphs,
             "collectives": dict(plan.stats.collectives), "dot_strategies": tags, "grad_buckets": buckets, "infeasible_subgraphs": plan.stats.infeasible_subgraphs,
             "strategies_txt": _C.dump_strategies(cg, plan), "unknown_ops": sorted(unknown)}
@@ -101,7 +106,17 @@ def plan_spmd_mesh(graph: Graph, nums, kinds):
         if kind == "tp":
             o.var_mem_limit = 1.0
             o.mem_split_min_rank = 2
+        if kind == "cp":    # sequence split seeded on the sample inputs of THIS level, attention keeps it (K / V ring)
+            o.context_parallel = True
+            o.ignore_annotation = False
+            for i in range(cg.num_nodes()):
+                if cg.node_op(i) == "input":
+                    cg.set_node_attr(i, "shard_dim", 1 if len(cg.node_outputs(i)[0][0]) >= 2 else -1)
         plan = _C.plan_spmd_level(cg, o)
+        if kind == "cp":
+            for i in range(cg.num_nodes()):
+                if cg.node_op(i) == "input":
+                    cg.erase_node_attr(i, "shard_dim")
         infeasible += plan.stats.infeasible_subgraphs
         cg, _ = _C.spmd_transform(cg, plan, lvl, int(num))
         for k, v in dict(plan.stats.collectives).items():
@@ -121,7 +136,7 @@ def plan_spmd_mesh(graph: Graph, nums, kinds):
 def _parse_mesh_strategy(strategy: str):
     """"dp4tp2" / "tp2dp4" / "dp2tp2dp2" -> ([4, 2], ["dp", "tp"]) ; None when `strategy` is not a mesh spec."""
     import re
-    parts = re.findall(r"(dp|tp|auto)(\d+)", strategy)
+    parts = re.findall(r"(dp|tp|cp|auto)(\d+)", strategy)
     if len(parts) < 2 or "".join(k + n for k, n in parts) != strategy:
         return None
     # tensor-parallel levels are planned first: the data-parallel level (with its ZeRO-style optimizer sharding) then acts
@@ -131,6 +146,8 @@ def _parse_mesh_strategy(strategy: str):
 
 
 def classify_parallelism(info: Dict[str, Any], num: int) -> str:
+    if info.get("context_parallel"):
+        return f"cp{num}"      # the sequence split runs through attention (K / V ring); everything else is token-wise
     t = info.get("dot_strategies", {})
     if not t:
         return f"replicated{num}"

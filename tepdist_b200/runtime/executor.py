@@ -246,6 +246,9 @@ class Executor:
         self.step_count = 0
         self._tag = 0   # micro-batch tag for per-micro-batch side tables (pipeline interleaves micro-batches)
         self.use_cuda_graph = use_cuda_graph and self.device.type == "cuda"
+        if self.use_cuda_graph and any(n.attrs.get("cp_levels") for n in graph.nodes) and os.environ.get("TEPDIST_CP_GRAPH") != "1":
+            self.use_cuda_graph = False    # ring attention posts point-to-point batches per block: run the step eagerly
+        self._rings: Dict[Tuple[int, ...], Any] = {}
         self._graph: Optional[torch.cuda.CUDAGraph] = None
         self._static_in: Dict[str, torch.Tensor] = {}
         self._static_out: List[torch.Tensor] = []
@@ -982,6 +985,21 @@ class Executor:
             comp.copy_(master.to(comp.dtype))
         env[(n.id, 0)] = comp if comp.is_contiguous() else comp.contiguous()
 
+    def _ring(self, n: Node):
+        """The K / V ring of a context-parallel attention node (transform.cc stamps `cp_levels` on "seq" candidates), or None."""
+        lv = [int(l) for l, num in zip(n.attrs.get("cp_levels", []), n.attrs.get("cp_nums", [])) if int(num) > 1]
+        if not lv or self.collective is None or self.collective.mesh.world == 1:
+            return None
+        if len(lv) > 1:
+            raise NotImplementedError("context parallelism over more than one mesh level (split the sequence on ONE level)")
+        key = tuple(lv)
+        if key not in self._rings:
+            from ..parallel.ring_attention import RingAttention
+            mesh = self.collective.mesh
+            self._rings[key] = RingAttention(mesh.group(lv[0]), mesh.group_ranks(lv[0]), mesh.index_in_group(lv[0]),
+                                             dry=self.collective.dry)
+        return self._rings[key]
+
     def _bn_sync_levels(self, n: Node) -> List[Tuple[int, int]]:
         """(level, num) pairs over which a batch-split BatchNorm has to complete its statistics: the levels the transform
         recorded, minus time-multiplexed ones (micro-batches of a pipeline normalise on their own, as in the reference)."""
@@ -1358,6 +1376,10 @@ class Executor:
             H = a["heads"]
             D = C3 // 3 // H
             q5 = qkv.view(B, S, H, 3, D)  # heads-major: a last-dim split is a split over heads
+            ring = self._ring(n)
+            if ring is not None:    # context parallel: S is this rank's block of the sequence, K / V blocks ride the ring
+                o, lse = ring.forward(q5[:, :, :, 0], q5[:, :, :, 1], q5[:, :, :, 2], causal=a.get("causal", True))
+                return [o.reshape(B, S, H * D), lse]
             o, lse = ops.attention_fwd(q5[:, :, :, 0], q5[:, :, :, 1], q5[:, :, :, 2], causal=a.get("causal", True))
             return [o.view(B, S, H * D), lse]
         if op == "attention_bwd":
@@ -1367,6 +1389,11 @@ class Executor:
             D = C3 // 3 // H
             q5 = qkv.view(B, S, H, 3, D)
             dqkv = torch.empty(B, S, H, 3, D, dtype=qkv.dtype, device=dev)
+            ring = self._ring(n)
+            if ring is not None:
+                ring.backward(do.reshape(B, S, H, D), q5[:, :, :, 0], q5[:, :, :, 1], q5[:, :, :, 2], o.reshape(B, S, H, D), lse,
+                              causal=a.get("causal", True), dqkv_out=dqkv)
+                return [dqkv.view(B, S, C3)]
             ops.attention_bwd(do.reshape(B, S, H, D), q5[:, :, :, 0], q5[:, :, :, 1], q5[:, :, :, 2], o.reshape(B, S, H, D),
                               lse, causal=a.get("causal", True), dqkv_out=dqkv)
             return [dqkv.view(B, S, C3)]

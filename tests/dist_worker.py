@@ -20,8 +20,11 @@ def case_gpt2(strategy, feed_shards=False, batch=4):
     from tepdist_b200.api import Trainer
     from tepdist_b200.models.gpt2 import CONFIGS, build_gpt2_graph
     cfg = CONFIGS["tiny"]
-    if strategy.startswith("pp") and int(os.environ.get("WORLD_SIZE", "1")) == 1:
+    if strategy.startswith(("pp", "cp", "dp2cp")) and int(os.environ.get("WORLD_SIZE", "1")) == 1:
         strategy = "auto"   # single-process oracle
+    if os.environ.get("TEPDIST_TEST_NCTX"):     # (GPU runs of the ring: blocks of 128 tokens go through the tcgen05 kernels)
+        import dataclasses
+        cfg = dataclasses.replace(cfg, n_ctx=int(os.environ["TEPDIST_TEST_NCTX"]))
     g = build_gpt2_graph(cfg, batch=batch)
     tr = Trainer(g, strategy=strategy, device=_dev(), use_cuda_graph=False)
     torch.manual_seed(0)

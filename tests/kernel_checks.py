@@ -654,7 +654,84 @@ def check_moe_routes():
     return out
 
 
+def check_ring_blocks(device="cuda"):
+    """Context-parallel attention on ONE device: every virtual rank's ring schedule (parallel/ring_attention.py) run serially
+    with the same block kernels and helper kernels -- causal diagonal block, unmasked off-diagonal blocks through the shared-stride
+    work buffer, log-sum-exp merge kernel, backward blocks fed the GLOBAL log-sum-exp / output, fp32 dq / dK / dV accumulation and
+    pack kernels -- against full-sequence attention (fp32 torch reference)."""
+    from tepdist_b200 import ops
+    from tepdist_b200.ops.attention import _ref_fwd, attn_merge_, attn_ring_accum_, attn_ring_pack
+    out = {}
+    torch.manual_seed(3)
+    dt = torch.bfloat16 if device == "cuda" else torch.float32
+    for (B, S, H, n, causal) in [(2, 512, 3, 4, True), (1, 256, 2, 2, False)]:
+        D, L = 64, S // n
+        qkv = torch.randn(B, S, H, 3, D, device=device).to(dt)
+        do = torch.randn(B, S, H, D, device=device).to(dt)
+        q, k, v = qkv[:, :, :, 0], qkv[:, :, :, 1], qkv[:, :, :, 2]
+        o_ref, lse_ref, _ = _ref_fwd(q.float(), k.float(), v.float(), 1.0 / 8.0, causal)
+        g_ref = torch.empty(B, S, H, 3, D, device=device)
+        ops.attention_bwd(do.float().cpu(), q.float().cpu(), k.float().cpu(), v.float().cpu(), o_ref.cpu(), lse_ref.cpu(), causal=causal,
+                          dqkv_out=(g_cpu := torch.empty(B, S, H, 3, D)))
+        g_ref.copy_(g_cpu)
+        o_all = torch.empty(B, S, H, D, device=device, dtype=dt)
+        lse_all = torch.empty(B, H, S, device=device)
+        blk = lambda t, r: t[:, r * L:(r + 1) * L]
+        dq_acc = torch.zeros(n, B, L, H, D, device=device)
+        kv_acc = torch.zeros(n, B, L, H, 2, D, device=device)
+        n0 = ops.launch_count()
+        for r in range(n):                              # forward of virtual rank r
+            o_acc = torch.empty(B, L, H, D, device=device)
+            la, lb = torch.empty(B, H, L, device=device), torch.empty(B, H, L, device=device)
+            work = torch.empty(B, L, H, 3, D, device=device, dtype=dt)
+            work[:, :, :, 0].copy_(blk(q, r))
+            first = True
+            for t in range(n):
+                j = (r - t) % n
+                if causal and j > r:
+                    continue
+                if t == 0:
+                    o_j, lse_j = ops.attention_fwd(blk(q, r), blk(k, r), blk(v, r), causal=causal)
+                else:
+                    work[:, :, :, 1:].copy_(torch.stack((blk(k, j), blk(v, j)), 3))
+                    o_j, lse_j = ops.attention_fwd(work[:, :, :, 0], work[:, :, :, 1], work[:, :, :, 2], causal=False)
+                attn_merge_(o_acc, la, lb, o_j.contiguous(), lse_j.contiguous(), first)
+                la, lb, first = lb, la, False
+            blk(o_all, r).copy_(o_acc)
+            lse_all[:, :, r * L:(r + 1) * L].copy_(la)
+        for r in range(n):                              # backward of virtual rank r: contributions to dq_r and to dK / dV of block j
+            work = torch.empty(B, L, H, 3, D, device=device, dtype=dt)
+            work[:, :, :, 0].copy_(blk(q, r))
+            part = torch.empty(B, L, H, 3, D, device=device, dtype=dt)
+            o_r, lse_r, do_r = blk(o_all, r).contiguous(), lse_all[:, :, r * L:(r + 1) * L].contiguous(), blk(do, r).contiguous()
+            for t in range(n):
+                j = (r - t) % n
+                if causal and j > r:
+                    continue
+                if t == 0:
+                    ops.attention_bwd(do_r, blk(q, r), blk(k, r), blk(v, r), o_r, lse_r, causal=causal, dqkv_out=part)
+                else:
+                    work[:, :, :, 1:].copy_(torch.stack((blk(k, j), blk(v, j)), 3))
+                    ops.attention_bwd(do_r, work[:, :, :, 0], work[:, :, :, 1], work[:, :, :, 2], o_r, lse_r, causal=False, dqkv_out=part)
+                attn_ring_accum_(dq_acc[r], kv_acc[j], part)
+        g = torch.empty(B, S, H, 3, D, device=device, dtype=dt)
+        for r in range(n):
+            blk(g, r).copy_(attn_ring_pack(dq_acc[r], kv_acc[r], torch.empty(B, L, H, 3, D, device=device, dtype=dt)))
+        if device == "cuda":
+            assert ops.launch_count() > n0
+        tag = f"S{S}n{n}c{int(causal)}"
+        out["o_" + tag] = _rel_err(o_all, o_ref)
+        out["lse_" + tag] = _rel_err(lse_all, lse_ref)
+        for i, nm in enumerate(("dq", "dk", "dv")):
+            out[f"{nm}_{tag}"] = _rel_err(g[:, :, :, i], g_ref[:, :, :, i])
+        tol = 3e-2 if device == "cuda" else 1e-5
+        for key, e in out.items():
+            assert e < tol, (key, e, out)
+    return out
+
+
 CHECKS = {
+    "ring_blocks": check_ring_blocks,
     "gemm_layouts": check_gemm_layouts,
     "gemm_epilogues": check_gemm_epilogues,
     "layernorm": check_layernorm,

@@ -50,7 +50,7 @@ def _batch(cases, world, tmp_path):
 
 # cases of the feature tests below that share one job per world size
 _SHARED = {2: ["fullstate:auto", "fullstate:pp2m2", "conv:dp", "opts:auto", "sched:auto", "sched:pp2m2"],
-           4: ["fullstate:dp2tp2", "clip:dp2tp2", "clip:pp2m2", "conv:dp2tp2", "optsgpt:dp2tp2"]}
+           4: ["fullstate:dp2tp2", "clip:dp2tp2", "clip:pp2m2", "conv:dp2tp2", "optsgpt:dp2tp2", "gpt2:dp2cp2"]}
 
 
 def _get(case, world, tmp_path):
@@ -65,7 +65,7 @@ def _single(case):
             "gpt2b1": lambda st: dist_worker.case_gpt2(st, False, 1), "moe": dist_worker.case_moe}[name]("auto")
 
 
-_WORLD2_CASES = ["mlp:auto", "mlp:dp", "gpt2:auto", "gpt2s:auto", "gpt2:explore", "gpt2:tp", "gpt2:pp2m2", "moe:ep"]
+_WORLD2_CASES = ["mlp:auto", "mlp:dp", "gpt2:auto", "gpt2s:auto", "gpt2:explore", "gpt2:tp", "gpt2:pp2m2", "moe:ep", "gpt2:cp"]
 
 
 @pytest.mark.parametrize("case", _WORLD2_CASES)
@@ -81,8 +81,20 @@ def test_spmd_world2_matches_single_process(case, tmp_path):
         assert got["parallelism"].startswith("pp2"), got
     if case == "gpt2:tp":
         assert got["parallelism"].startswith("tp"), got
+    if case == "gpt2:cp":     # context parallel: sequence split through attention, K / V ring (parallel/ring_attention.py)
+        assert got["parallelism"] == "cp2", got
     if case in ("mlp:dp", "gpt2:auto", "gpt2:explore"):  # (mlp:auto legitimately prefers a 128-byte activation all-reduce over gradient sync)
         assert got["parallelism"].startswith("dp"), got
+
+
+def test_context_parallel_on_a_2d_mesh_matches_single_process(tmp_path):
+    """dp2cp2 on 4 ranks: the batch is split over one mesh level, the sequence over the other; each pair of ranks that shares a
+    batch shard forms its own K / V ring (the ring's process group is the cp level's group, not the world)."""
+    ref = _single("gpt2:auto")
+    got = _get("gpt2:dp2cp2", 4, tmp_path)
+    assert got["parallelism"] == "dp2xcp2", got
+    for a, b in zip(got["losses"], ref["losses"]):
+        assert abs(a - b) <= 2e-4 * max(1.0, abs(b)), (got, ref)
 
 
 def test_long_context_plan_batch1_head_seq_all_to_all(tmp_path):

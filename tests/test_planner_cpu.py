@@ -764,3 +764,39 @@ def test_critical_nodes_scan_equals_the_main_path_definition_and_clusters_tiny_s
     _, a = plan_spmd(g, 2, "auto")
     _, b_ = plan_spmd(g, 2, "auto", options={"min_segment_flops_frac": 0.2})
     assert b_["subgraphs"] < a["subgraphs"] and abs(a["comm_bytes"] - b_["comm_bytes"]) <= 1e-6 * max(1.0, a["comm_bytes"])
+
+
+def test_context_parallel_plan_keeps_the_sequence_split_through_attention():
+    """`cp`: the sample inputs are seeded with a sequence split, attention offers only its "seq" candidate (queries stay,
+    K / V ride a ring: priced as the K / V all-gather it replaces, twice that backward), the transform stamps the ring's
+    mesh level on the node, the position table is stored split on its rows.  Without `cp` the ring candidate is still on the
+    menu -- it is what lets a model whose head count does not divide the device count (GPT-2 1.5B: 25 heads) shard attention
+    when there is no batch to split."""
+    import dataclasses
+    from tepdist_b200.parallel import plan_spmd
+    cfg = CONFIGS["tiny"]
+    g = build_gpt2_graph(cfg, batch=2)
+    out, info = plan_spmd(g, 2, "cp")
+    assert info["context_parallel"] == cfg.n_layer
+    att = [n for n in out.nodes if n.op in ("attention", "attention_bwd")]
+    assert len(att) == 2 * cfg.n_layer
+    for n in att:
+        assert n.attrs["cp_levels"] == [0] and n.attrs["cp_nums"] == [2], n.attrs
+        assert n.attrs["heads"] == cfg.n_head                               # heads are NOT split
+    fwd = [n for n in att if n.op == "attention"][0]
+    assert list(fwd.outputs[0].shape) == [2, cfg.n_ctx // 2, cfg.n_embd] and list(fwd.outputs[1].shape) == [2, cfg.n_head, cfg.n_ctx // 2]
+    wpe = [n for n in out.nodes if n.name == "model/wpe"][0]
+    assert list(wpe.outputs[0].shape) == [cfg.n_ctx // 2, cfg.n_embd] and wpe.attrs["shard_dims"] == [0]
+    # candidates: ring cost = 2/3 of the qkv bytes x (n-1)/n forward, twice that backward
+    cg = to_native(g)
+    i = [k for k in range(cg.num_nodes()) if cg.node_op(k) == "attention"][0]
+    seq = [c for c in _C.enumerate_candidates(cg, i, 2, True) if c.tag == "seq"][0]
+    qkv_bytes = 2 * cfg.n_ctx * 3 * cfg.n_embd * (2 if g.nodes[i].outputs[0].dtype == "bf16" else 4)
+    assert seq.node_cost == pytest.approx(qkv_bytes * (2 / 3) * 0.5)
+    # 3 heads on 2 devices, one sequence per step: no batch, no head split.  Short sequence: gathering it and running attention
+    # replicated moves fewer bytes than the ring and repeats little work; long sequence: the repeated S^2 FLOPs (priced as the
+    # bytes the links move in that time) and the ring's per-hop launches decide -> the planner takes the ring by itself
+    for n_ctx, want in ((128, 0), (8192, 2)):
+        odd = dataclasses.replace(cfg, n_head=3, n_embd=96, n_ctx=n_ctx)
+        _, info3 = plan_spmd(build_gpt2_graph(odd, batch=1), 2, "auto")
+        assert info3["context_parallel"] == want, (n_ctx, info3["collectives"])

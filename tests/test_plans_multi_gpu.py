@@ -24,9 +24,9 @@ def _free_port():
     return p
 
 
-def _run(case, world, tmp_path):
+def _run(case, world, tmp_path, extra_env=None):
     out = str(tmp_path / f"out{world}.json")
-    env = dict(os.environ, TEPDIST_TEST_DEVICE="cuda", OMP_NUM_THREADS="2")
+    env = dict(os.environ, TEPDIST_TEST_DEVICE="cuda", OMP_NUM_THREADS="2", **(extra_env or {}))
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}", "--master-addr", "127.0.0.1",
            "--master-port", str(_free_port()), os.path.join(HERE, "dist_worker.py"), case, out]
     if world == 1:
@@ -60,3 +60,16 @@ def test_pipeline_x_spmd_and_2d_mesh_on_four_gpus_match_one_gpu(tmp_path):
     assert got["gpt2:pp2m2"]["parallelism"] == "pp2xspmd2/micro2", got["gpt2:pp2m2"]
     _close(got["gpt2:pp2m2"], ref)
     _close(got["gpt2:dp2tp2"], ref)
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
+def test_context_parallel_ring_attention_on_two_gpus_matches_one_gpu(tmp_path):
+    """`cp`: the sequence (256 tokens) is cut in two blocks of 128, every token-wise op runs on its block, attention keeps its
+    queries and passes K / V (forward) and K / V + the fp32 dK / dV accumulators (backward) around the ring over NCCL; the
+    diagonal block runs the causal tcgen05 kernel, the off-diagonal one the unmasked kernel, partial outputs merge by
+    log-sum-exp (parallel/ring_attention.py)."""
+    env = {"TEPDIST_TEST_NCTX": "256"}
+    ref = _run("gpt2:auto", 1, tmp_path, env)
+    got = _run("gpt2:cp", 2, tmp_path, env)
+    assert got["parallelism"] == "cp2", got
+    _close(got, ref)

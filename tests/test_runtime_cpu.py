@@ -504,3 +504,15 @@ def test_pipeline_slot_assignment_follows_the_release_plan():
                 live[w.slot_of[m]] = m
             for dead in t.get("release", ()):
                 live.pop(w.slot_of[dead], None)
+
+
+def test_ring_attention_block_schedule_equals_full_attention():
+    """Every virtual rank's ring schedule (causal diagonal block, unmasked earlier blocks, log-sum-exp merge, backward blocks fed
+    the global log-sum-exp, fp32 dK / dV accumulation) reproduces full-sequence attention and its gradients (fp32, CPU branch of
+    the same functions the GPU test drives through the kernels)."""
+    import os
+    import sys
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    import kernel_checks as kc
+    errs = kc.check_ring_blocks("cpu")
+    assert errs and max(errs.values()) < 1e-5, errs
