@@ -101,6 +101,10 @@ class _Sig:
     tepd_moe_gather_scale = [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp]
     tepd_moe_combine_sum = [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp]
     tepd_moe_route_dots = [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp]
+    tepd_maxpool_nhwc = [_vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _i, _vp]
+    tepd_maxpool_bwd_nhwc = [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _i, _vp]
+    tepd_gap_nhwc = [_vp, _vp, _i, _i, _i, _vp]
+    tepd_gap_bwd_nhwc = [_vp, _vp, _i, _i, _i, _vp]
     tepd_attn_merge = [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp]
     tepd_attn_ring_accum = [_vp, _vp, _vp, _ll, _i, _i, _vp]
     tepd_attn_fwd = [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _f, _i, _ll, _ll, _ll, _vp]
@@ -490,6 +494,65 @@ def conv2d_wgrad(dy: torch.Tensor, x: torch.Tensor, w_shape, stride: int, pad: i
     dyn = _nhwc(dy).reshape(N * Ho * Wo, Cout)
     gw = gemm(dyn, col, a_mn=True, b_mn=True, out_dtype=torch.float32)   # [Cout, Kpad]
     return gw[:, :kh * kw * C].reshape(Cout, kh, kw, C).permute(0, 3, 1, 2)
+
+
+# --------------------------------------------------------------------------------------------- pooling (NHWC kernels, conv_sm100.cu)
+def pool_native_ok(x: torch.Tensor) -> bool:
+    return CONV_NATIVE and x.is_cuda and x.dtype == torch.bfloat16 and x.dim() == 4 and x.shape[1] % 8 == 0 and x.numel() > 0
+
+
+def _cl(x: torch.Tensor) -> torch.Tensor:
+    return x.contiguous(memory_format=torch.channels_last)
+
+
+def maxpool2d_fwd(x: torch.Tensor, k: int, stride: int, pad: int) -> torch.Tensor:
+    """[N, C, H, W] -> [N, C, Ho, Wo] (floor mode, -inf padding); own kernel on channels_last bf16, torch elsewhere."""
+    if not pool_native_ok(x):
+        return torch.nn.functional.max_pool2d(x, k, stride, pad)
+    N, C, H, W = x.shape
+    Ho, Wo = (H + 2 * pad - k) // stride + 1, (W + 2 * pad - k) // stride + 1
+    xc = _cl(x)
+    y = torch.empty((N, C, Ho, Wo), dtype=x.dtype, device=x.device, memory_format=torch.channels_last)
+    _check(lib().tepd_maxpool_nhwc(xc.data_ptr(), y.data_ptr(), N, H, W, C, Ho, Wo, k, stride, pad, _stream()), "maxpool")
+    _count()
+    return y
+
+
+def maxpool2d_bwd(dy: torch.Tensor, x: torch.Tensor, y: torch.Tensor, k: int, stride: int, pad: int) -> torch.Tensor:
+    """Gradient of max_pool2d given the forward input and output (gather form, first-maximum tie rule like torch)."""
+    if not (pool_native_ok(x) and dy.dtype == x.dtype and y.dtype == x.dtype):
+        xr = x.detach().float().requires_grad_(True)
+        with torch.enable_grad():
+            yy = torch.nn.functional.max_pool2d(xr, k, stride, pad)
+        (gx,) = torch.autograd.grad(yy, xr, dy.float())
+        return gx.to(x.dtype)
+    N, C, H, W = x.shape
+    Ho, Wo = y.shape[2], y.shape[3]
+    dx = torch.empty((N, C, H, W), dtype=x.dtype, device=x.device, memory_format=torch.channels_last)
+    _check(lib().tepd_maxpool_bwd_nhwc(_cl(dy).data_ptr(), _cl(x).data_ptr(), _cl(y).data_ptr(), dx.data_ptr(), N, H, W, C, Ho, Wo, k, stride,
+                                       pad, _stream()), "maxpool_bwd")
+    _count()
+    return dx
+
+
+def global_avgpool_fwd(x: torch.Tensor) -> torch.Tensor:
+    if not pool_native_ok(x):
+        return x.float().mean((2, 3)).to(x.dtype)
+    N, C, H, W = x.shape
+    y = torch.empty(N, C, dtype=x.dtype, device=x.device)
+    _check(lib().tepd_gap_nhwc(_cl(x).data_ptr(), y.data_ptr(), N, H * W, C, _stream()), "gap")
+    _count()
+    return y
+
+
+def global_avgpool_bwd(dy: torch.Tensor, shape) -> torch.Tensor:
+    N, C, H, W = shape
+    if not (CONV_NATIVE and dy.is_cuda and dy.dtype == torch.bfloat16 and C % 8 == 0):
+        return (dy / (H * W)).view(N, C, 1, 1).expand(N, C, H, W).contiguous()
+    dx = torch.empty((N, C, H, W), dtype=dy.dtype, device=dy.device, memory_format=torch.channels_last)
+    _check(lib().tepd_gap_bwd_nhwc(dy.contiguous().data_ptr(), dx.data_ptr(), N, H * W, C, _stream()), "gap_bwd")
+    _count()
+    return dx
 
 
 def bn_native_ok(x: torch.Tensor) -> bool:

@@ -124,6 +124,127 @@ inline int grid_for(long long work) {
   return (int)(b < 1 ? 1 : (b > cap ? cap : b));
 }
 
+// ---- pooling, NHWC bf16, C % 8 == 0, one thread per 8 channels (reference K9: XLA reduce-window / select-and-scatter on cuDNN-era
+// codegen).  Max pool backward is a GATHER (no atomics): an input pixel looks at the <= ceil(k/stride)^2 windows that cover it,
+// re-scans each window and takes dy when it is that window's FIRST maximum in row-major scan order (torch's tie rule).
+__device__ __forceinline__ void ld8(const bf16* p, float (&f)[8]) {
+  const uint4 u = __ldg(reinterpret_cast<const uint4*>(p));
+  const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) { const float2 t = __bfloat1622float2(h[i]); f[2 * i] = t.x; f[2 * i + 1] = t.y; }
+}
+__device__ __forceinline__ void st8(bf16* p, const float (&f)[8]) {
+  uint4 u;
+  __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&u);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) h[i] = __floats2bfloat162_rn(f[2 * i], f[2 * i + 1]);
+  *reinterpret_cast<uint4*>(p) = u;
+}
+__global__ void __launch_bounds__(256) maxpool_fwd_nhwc_kernel(const bf16* __restrict__ x, bf16* __restrict__ y, ConvGeom g) {
+  const int cv = g.C / 8;
+  const long long total = (long long)g.N * g.Ho * g.Wo * cv;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(i % cv) * 8;
+    long long r = i / cv;
+    const int wo = (int)(r % g.Wo); r /= g.Wo;
+    const int ho = (int)(r % g.Ho);
+    const int n = (int)(r / g.Ho);
+    float m[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) m[j] = -INFINITY;
+    for (int ky = 0; ky < g.kh; ++ky) {
+      const int ih = ho * g.stride - g.pad + ky;
+      if (ih < 0 || ih >= g.H) continue;
+      for (int kx = 0; kx < g.kw; ++kx) {
+        const int iw = wo * g.stride - g.pad + kx;
+        if (iw < 0 || iw >= g.W) continue;
+        float v[8];
+        ld8(x + (((long long)n * g.H + ih) * g.W + iw) * g.C + c, v);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) m[j] = fmaxf(m[j], v[j]);
+      }
+    }
+    st8(y + i * 8, m);
+  }
+}
+__global__ void __launch_bounds__(256) maxpool_bwd_nhwc_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ x,
+                                                               const bf16* __restrict__ y, bf16* __restrict__ dx, ConvGeom g) {
+  const int cv = g.C / 8;
+  const long long total = (long long)g.N * g.H * g.W * cv;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(i % cv) * 8;
+    long long r = i / cv;
+    const int iw = (int)(r % g.W); r /= g.W;
+    const int ih = (int)(r % g.H);
+    const int n = (int)(r / g.H);
+    float xv[8], acc[8];
+    ld8(x + i * 8, xv);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+    // output rows / columns whose window contains (ih, iw):  ho*stride - pad <= ih <= ho*stride - pad + k - 1
+    const int ho_lo = max(0, (ih + g.pad - g.kh + g.stride) / g.stride), ho_hi = min(g.Ho - 1, (ih + g.pad) / g.stride);
+    const int wo_lo = max(0, (iw + g.pad - g.kw + g.stride) / g.stride), wo_hi = min(g.Wo - 1, (iw + g.pad) / g.stride);
+    for (int ho = ho_lo; ho <= ho_hi; ++ho)
+      for (int wo = wo_lo; wo <= wo_hi; ++wo) {
+        const long long oidx = (((long long)n * g.Ho + ho) * g.Wo + wo) * g.C + c;
+        float yv[8], gv[8];
+        ld8(y + oidx, yv);
+        ld8(dy + oidx, gv);
+        unsigned cand = 0;                       // channels where this pixel holds the window maximum
+#pragma unroll
+        for (int j = 0; j < 8; ++j) cand |= (xv[j] == yv[j]) ? (1u << j) : 0u;
+        if (!cand) continue;
+        // an EARLIER pixel of the window (row-major) with the same value wins the tie
+        const int my = (ih - (ho * g.stride - g.pad)) * g.kw + (iw - (wo * g.stride - g.pad));
+        for (int t = 0; t < my && cand; ++t) {
+          const int ph = ho * g.stride - g.pad + t / g.kw, pw = wo * g.stride - g.pad + t % g.kw;
+          if (ph < 0 || ph >= g.H || pw < 0 || pw >= g.W) continue;
+          float pv[8];
+          ld8(x + (((long long)n * g.H + ph) * g.W + pw) * g.C + c, pv);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) if (pv[j] == yv[j]) cand &= ~(1u << j);
+        }
+#pragma unroll
+        for (int j = 0; j < 8; ++j) if (cand & (1u << j)) acc[j] += gv[j];
+      }
+    st8(dx + i * 8, acc);
+  }
+}
+// global average pool: y[n, c] = mean over H*W (fp32 accumulation); backward: dx[n, h, w, c] = dy[n, c] / (H*W)
+__global__ void __launch_bounds__(256) gap_fwd_nhwc_kernel(const bf16* __restrict__ x, bf16* __restrict__ y, int N, int HW, int C) {
+  const int cv = C / 8;
+  const long long total = (long long)N * cv;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(i % cv) * 8, n = (int)(i / cv);
+    float s[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) s[j] = 0.f;
+    for (int p = 0; p < HW; ++p) {
+      float v[8];
+      ld8(x + ((long long)n * HW + p) * C + c, v);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) s[j] += v[j];
+    }
+    const float inv = 1.f / (float)HW;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) s[j] *= inv;
+    st8(y + (long long)n * C + c, s);
+  }
+}
+__global__ void __launch_bounds__(256) gap_bwd_nhwc_kernel(const bf16* __restrict__ dy, bf16* __restrict__ dx, int N, int HW, int C) {
+  const int cv = C / 8;
+  const long long total = (long long)N * HW * cv;
+  const float inv = 1.f / (float)HW;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(i % cv) * 8, n = (int)(i / ((long long)cv * HW));
+    float v[8];
+    ld8(dy + (long long)n * C + c, v);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v[j] *= inv;
+    st8(dx + i * 8, v);
+  }
+}
+
 ConvGeom MakeGeom(int N, int H, int W, int C, int Ho, int Wo, int kh, int kw, int stride, int pad, int Kpad) {
   ConvGeom g;
   g.N = N; g.H = H; g.W = W; g.C = C; g.Ho = Ho; g.Wo = Wo; g.kh = kh; g.kw = kw; g.stride = stride; g.pad = pad; g.Kpad = Kpad;
@@ -157,4 +278,29 @@ extern "C" int tepd_col2im_nhwc(const void* dcol, void* dx, int N, int H, int W,
     return (int)tepd::launch(col2im_nhwc_kernel<8>, dim3(grid_for(px * (C / 8))), dim3(256), 0, CS(stream), (const bf16*)dcol,
                              (bf16*)dx, g);
   return (int)tepd::launch(col2im_nhwc_kernel<1>, dim3(grid_for(px * C)), dim3(256), 0, CS(stream), (const bf16*)dcol, (bf16*)dx, g);
+}
+
+extern "C" int tepd_maxpool_nhwc(const void* x, void* y, int N, int H, int W, int C, int Ho, int Wo, int k, int stride, int pad, void* stream) {
+  if (C % 8) return -2;
+  const ConvGeom g = MakeGeom(N, H, W, C, Ho, Wo, k, k, stride, pad, 0);
+  maxpool_fwd_nhwc_kernel<<<grid_for((long long)N * Ho * Wo * (C / 8)), 256, 0, CS(stream)>>>((const bf16*)x, (bf16*)y, g);
+  return (int)cudaGetLastError();
+}
+extern "C" int tepd_maxpool_bwd_nhwc(const void* dy, const void* x, const void* y, void* dx, int N, int H, int W, int C, int Ho, int Wo,
+                                     int k, int stride, int pad, void* stream) {
+  if (C % 8) return -2;
+  const ConvGeom g = MakeGeom(N, H, W, C, Ho, Wo, k, k, stride, pad, 0);
+  maxpool_bwd_nhwc_kernel<<<grid_for((long long)N * H * W * (C / 8)), 256, 0, CS(stream)>>>((const bf16*)dy, (const bf16*)x, (const bf16*)y,
+                                                                                          (bf16*)dx, g);
+  return (int)cudaGetLastError();
+}
+extern "C" int tepd_gap_nhwc(const void* x, void* y, int N, int HW, int C, void* stream) {
+  if (C % 8) return -2;
+  gap_fwd_nhwc_kernel<<<grid_for((long long)N * (C / 8)), 256, 0, CS(stream)>>>((const bf16*)x, (bf16*)y, N, HW, C);
+  return (int)cudaGetLastError();
+}
+extern "C" int tepd_gap_bwd_nhwc(const void* dy, void* dx, int N, int HW, int C, void* stream) {
+  if (C % 8) return -2;
+  gap_bwd_nhwc_kernel<<<grid_for((long long)N * HW * (C / 8)), 256, 0, CS(stream)>>>((const bf16*)dy, (bf16*)dx, N, HW, C);
+  return (int)cudaGetLastError();
 }

@@ -1657,18 +1657,12 @@ class Executor:
             dg = self._grad_out(n, 1, n.outputs[1].shape); dg.add_((dyf * xh).sum((0, 2, 3)))
             db = self._grad_out(n, 2, n.outputs[2].shape); db.add_(dyf.sum((0, 2, 3)))
             return [dx.to(xx.dtype), dg, db]
-        if op == "maxpool2d": return [F.max_pool2d(x, a["k"], a["stride"], a["padding"])]
-        if op == "maxpool2d_bwd":
-            dy, xx, y = ins
-            xr = xx.detach().float().requires_grad_(True)
-            with torch.enable_grad():
-                yy = F.max_pool2d(xr, a["k"], a["stride"], a["padding"])
-            (gx,) = torch.autograd.grad(yy, xr, dy.float())
-            return [gx.to(xx.dtype)]
-        if op == "global_avgpool": return [x.float().mean((2, 3)).to(x.dtype)]
-        if op == "global_avgpool_bwd":
-            N, C, H, W = n.outputs[0].shape
-            return [(x / (H * W)).view(N, C, 1, 1).expand(N, C, H, W).contiguous()]
+        # pooling: own NHWC kernels on the GPU (conv_sm100.cu; gather-form max-pool backward from the saved input / output instead of
+        # re-running the forward under autograd), torch ops on CPU
+        if op == "maxpool2d": return [ops.maxpool2d_fwd(x, a["k"], a["stride"], a["padding"])]
+        if op == "maxpool2d_bwd": return [ops.maxpool2d_bwd(ins[0], ins[1], ins[2], a["k"], a["stride"], a["padding"])]
+        if op == "global_avgpool": return [ops.global_avgpool_fwd(x)]
+        if op == "global_avgpool_bwd": return [ops.global_avgpool_bwd(x, tuple(n.outputs[0].shape))]
         if op in ("all_reduce", "all_gather", "reduce_scatter", "all_to_all", "dynamic_slice", "send", "recv"):
             assert self.collective is not None, f"collective op {op} without a communicator"
             # (a bound gradient is ADDED into the flat buffer by the caller: with micro-batching the collective runs once

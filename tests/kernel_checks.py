@@ -730,7 +730,39 @@ def check_ring_blocks(device="cuda"):
     return out
 
 
+def check_pool():
+    """Own NHWC pooling kernels vs torch (fp32 math on the same bf16 values, so ties -- plentiful after a ReLU -- must resolve to the
+    same element: first maximum in row-major window order)."""
+    import torch.nn.functional as F
+    from tepdist_b200 import ops
+    out = {}
+    torch.manual_seed(9)
+    for (N, C, H, W, k, s_, p_) in [(4, 64, 56, 56, 3, 2, 1), (2, 32, 15, 17, 2, 2, 0), (2, 16, 9, 9, 3, 1, 1)]:
+        x = torch.randn(N, C, H, W, device="cuda").relu().to(torch.bfloat16).contiguous(memory_format=torch.channels_last)
+        n0 = ops.launch_count()
+        y = ops.maxpool2d_fwd(x, k, s_, p_)
+        xr = x.float().requires_grad_(True)
+        yr = F.max_pool2d(xr, k, s_, p_)
+        assert torch.equal(y.float(), yr.detach()), "maxpool fwd"
+        dy = torch.randn_like(yr).to(torch.bfloat16)
+        dx = ops.maxpool2d_bwd(dy, x, y, k, s_, p_)
+        (gr,) = torch.autograd.grad(yr, xr, dy.float())
+        assert ops.launch_count() - n0 == 2
+        out[f"maxpool_bwd_{H}x{W}k{k}s{s_}"] = _rel_err(dx, gr)
+        assert out[f"maxpool_bwd_{H}x{W}k{k}s{s_}"] < 1e-2, out
+        assert int(((dx.float() != 0) != (gr != 0)).sum()) == 0, "gradient routed to a different element of a tie"
+    x = torch.randn(8, 256, 7, 7, device="cuda").to(torch.bfloat16).contiguous(memory_format=torch.channels_last)
+    g = ops.global_avgpool_fwd(x)
+    out["gap"] = _rel_err(g, x.float().mean((2, 3)))
+    dyg = torch.randn(8, 256, device="cuda").to(torch.bfloat16)
+    dxg = ops.global_avgpool_bwd(dyg, (8, 256, 7, 7))
+    out["gap_bwd"] = _rel_err(dxg, (dyg.float() / 49).view(8, 256, 1, 1).expand(8, 256, 7, 7))
+    assert out["gap"] < 1e-2 and out["gap_bwd"] < 1e-2, out
+    return out
+
+
 CHECKS = {
+    "pool": check_pool,
     "ring_blocks": check_ring_blocks,
     "gemm_layouts": check_gemm_layouts,
     "gemm_epilogues": check_gemm_epilogues,

@@ -8,7 +8,7 @@ pytestmark = pytest.mark.gpu
 
 
 @pytest.mark.parametrize("name", ["gemm_layouts", "gemm_epilogues", "layernorm", "gelu_colsum_embed", "xent_adam",
-                                  "attn_fwd", "attn_bwd", "gemm2", "conv", "einsum", "moe_routes", "ew", "ring_blocks"])
+                                  "attn_fwd", "attn_bwd", "gemm2", "conv", "einsum", "moe_routes", "ew", "ring_blocks", "pool"])
 def test_kernel(name):
     assert torch.cuda.is_available()
     from tepdist_b200 import ops
