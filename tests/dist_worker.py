@@ -298,9 +298,58 @@ def case_moe(strategy):
     return {"losses": losses, "parallelism": tr.plan_info.get("parallelism"), "collectives": tr.plan_info.get("collectives")}
 
 
+def case_collectives(strategy):
+    """Collective lowering on its own (reference xla/tests/dapple_all_gather_test.cc Dim0 / Dim1 / Dim1_2x3, dapple_all_to_all_test.cc,
+    dapple_all_reduce tests): every collective op of the IR on every dim of a rank-3 tensor, on each level of the mesh named by
+    `strategy` ("1d": one level over the world; "2d": 2 x (world/2)), against the result computed locally from the known contents of
+    every rank's shard.  Returns the number of checks and the list of failures."""
+    from types import SimpleNamespace
+    from tepdist_b200.parallel.collectives import CollectiveRunner
+    from tepdist_b200.parallel.mesh import DeviceMesh
+    from tepdist_b200.api import init_distributed
+    dev = _dev()
+    init_distributed("nccl" if dev.type == "cuda" else "gloo")
+    world, rank = dist.get_world_size(), dist.get_rank()
+    nums = [world] if strategy in ("auto", "1d") else [2, world // 2]
+    mesh = DeviceMesh(nums, [False] * len(nums), rank=rank, world=world)
+    mesh.build_process_groups()
+    run = CollectiveRunner(mesh)
+    shape = (8, 8, 16)      # every dim divisible by 2, 4 and 8
+
+    def content(r, sh=shape):        # what global rank r holds
+        g = torch.Generator().manual_seed(100 + r)
+        return torch.randint(-8, 9, sh, generator=g).float()       # small integers: every reduction is exact in fp32 (and bf16 sums)
+    fails, checks = [], 0
+    for lvl, num in enumerate(nums):
+        ranks = mesh.group_ranks(lvl)
+        me = mesh.index_in_group(lvl)
+        mine = content(rank).to(dev)
+        node = lambda op, **a: SimpleNamespace(op=op, attrs=dict(a, level=lvl, num=num))
+
+        def check(tag, got, want):
+            nonlocal checks
+            checks += 1
+            if tuple(got.shape) != tuple(want.shape) or not torch.equal(got.cpu(), want):
+                fails.append(f"level{lvl} {tag}")
+        total = sum(content(r) for r in ranks)
+        check("all_reduce", run.run(node("all_reduce", reduce=0), [mine])[0], total)
+        for d in range(3):
+            check(f"all_gather dim{d}", run.run(node("all_gather", dim=d), [mine])[0], torch.cat([content(r) for r in ranks], d))
+            sz = shape[d] // num
+            check(f"reduce_scatter dim{d}", run.run(node("reduce_scatter", dim=d, reduce=0), [mine])[0], total.narrow(d, me * sz, sz))
+            check(f"dynamic_slice dim{d}", run.run(node("dynamic_slice", dim=d), [mine])[0], content(rank).narrow(d, me * sz, sz))
+            for cd in range(3):
+                if cd == d:
+                    continue
+                # split `d` -> split `cd` reshard: piece `me` (along d) of every peer, concatenated along cd in group order
+                want = torch.cat([content(r).narrow(d, me * sz, sz) for r in ranks], cd)
+                check(f"all_to_all split{d} concat{cd}", run.run(node("all_to_all", split_dim=d, concat_dim=cd), [mine])[0], want)
+    return {"losses": [], "parallelism": strategy, "collectives": None, "checks": checks, "fails": fails}
+
+
 if __name__ == "__main__":
     case, out = sys.argv[1], sys.argv[2]
-    CASES_ = {"gpt2": case_gpt2, "gpt2s": lambda st: case_gpt2(st, True), "gpt2b1": lambda st: case_gpt2(st, False, 1), "mlp": case_mlp, "moe": case_moe, "ckpt": case_ckpt, "state": case_state, "tpfused": case_tpfused, "manualdp": case_manualdp, "opts": case_opts, "optsgpt": case_optsgpt, "conv": case_conv, "resume": case_resume, "fullstate": case_fullstate, "clip": case_clip, "sched": case_sched}
+    CASES_ = {"gpt2": case_gpt2, "gpt2s": lambda st: case_gpt2(st, True), "gpt2b1": lambda st: case_gpt2(st, False, 1), "mlp": case_mlp, "moe": case_moe, "ckpt": case_ckpt, "state": case_state, "tpfused": case_tpfused, "manualdp": case_manualdp, "opts": case_opts, "optsgpt": case_optsgpt, "conv": case_conv, "resume": case_resume, "fullstate": case_fullstate, "clip": case_clip, "sched": case_sched, "collectives": case_collectives}
 
     def run_case(c):
         name, _, strat = c.partition(":")

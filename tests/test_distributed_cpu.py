@@ -87,6 +87,16 @@ def test_spmd_world2_matches_single_process(case, tmp_path):
         assert got["parallelism"].startswith("dp"), got
 
 
+@pytest.mark.parametrize("case,world", [("collectives:1d", 2), ("collectives:2d", 4)])
+def test_collective_lowering_every_op_every_dim_every_mesh_level(tmp_path, case, world):
+    """The reference tests its collective thunks directly (xla/tests/dapple_all_gather_test.cc Dim0 / Dim1 / Dim1_2x3,
+    dapple_all_to_all_test.cc 2-shard reshape, all-reduce tests): here every collective op of the IR (all_reduce, all_gather,
+    reduce_scatter, dynamic_slice, all_to_all for every split / concat dim pair) runs on every dim of a rank-3 tensor and on each
+    level of a 1-D and a 2 x 2 mesh, bit-exact against the result assembled locally from the known shard contents."""
+    got = _run(case, world, tmp_path)
+    assert got["checks"] == (16 if world == 2 else 32) and not got["fails"], got
+
+
 def test_context_parallel_on_a_2d_mesh_matches_single_process(tmp_path):
     """dp2cp2 on 4 ranks: the batch is split over one mesh level, the sequence over the other; each pair of ranks that shares a
     batch shard forms its own K / V ring (the ring's process group is the cp level's group, not the world)."""

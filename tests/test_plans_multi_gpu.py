@@ -73,3 +73,15 @@ def test_context_parallel_ring_attention_on_two_gpus_matches_one_gpu(tmp_path):
     got = _run("gpt2:cp", 2, tmp_path, env)
     assert got["parallelism"] == "cp2", got
     _close(got, ref)
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
+def test_collective_lowering_on_gpus_over_nccl(tmp_path):
+    """Every collective op of the IR on every dim of a rank-3 tensor over NCCL (the reference's dapple_*_test.cc run on real
+    devices): 1-D mesh over all visible GPUs, and a 2 x (n/2) mesh when there are at least 4."""
+    n = 8 if torch.cuda.device_count() >= 8 else (4 if torch.cuda.device_count() >= 4 else 2)
+    got = _run("collectives:1d", n, tmp_path)
+    assert got["checks"] == 16 and not got["fails"], got
+    if n >= 4:
+        got = _run("collectives:2d", n, tmp_path)
+        assert got["checks"] == 32 and not got["fails"], got
