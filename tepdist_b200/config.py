@@ -62,6 +62,7 @@ def spmd_overrides() -> Dict[str, Any]:
     _take(o, "aux_affinity", "AUX_AFFINITY", "bool")
     _take(o, "forward_sub_graph_num", "FORWARD_SUB_GRAPH_NUM", "int")
     _take(o, "ilp_time_limit_s", "ILP_TIME_LIMIT", "float", 60.0)
+    _take(o, "num_threads", "ILP_NUM_THREADS", "int")      # sub-graph problems solved concurrently
     import os
     if os.environ.get("TEPDIST_COLL_LATENCY_BYTES") is not None:   # per-collective latency term of the SPMD cost (bytes of wire
         o["collective_latency_bytes"] = float(os.environ["TEPDIST_COLL_LATENCY_BYTES"])   # time; 0 = byte counts only)
@@ -112,12 +113,11 @@ def check_num_gradients(n_apply: int) -> None:
 
 
 # Accepted for compatibility with the reference's config files but without effect here (and why):
-#   ILP_NUM_THREADS       the built-in simplex / branch-and-bound is single threaded
 #   ASYNC_SEND            pipeline sends are always isend: a blocking send can deadlock two stages that send to each other at the
 #                         same point of the 1F1B steady state (their receives are posted later in their own task lists)
 #   DISABLE_BUFFER_ALIAS  variables are always updated in place in the flat store
 #   CLUSTER_SPEC, FRONTEND informational (set by the launcher)
-INERT_KEYS = ("ILP_NUM_THREADS", "ASYNC_SEND", "DISABLE_BUFFER_ALIAS", "CLUSTER_SPEC", "FRONTEND")
+INERT_KEYS = ("ASYNC_SEND", "DISABLE_BUFFER_ALIAS", "CLUSTER_SPEC", "FRONTEND")
 
 
 def resolve_strategy(strategy: str) -> str:

@@ -185,6 +185,7 @@ PYBIND11_MODULE(_C, m) {
       .def_readwrite("var_mem_limit", &SpmdOptions::var_mem_limit)
       .def_readwrite("mem_split_min_rank", &SpmdOptions::mem_split_min_rank)
       .def_readwrite("context_parallel", &SpmdOptions::context_parallel)
+      .def_readwrite("num_threads", &SpmdOptions::num_threads)
       .def_readwrite("collective_latency_bytes", &SpmdOptions::collective_latency_bytes)
       .def_readwrite("min_segment_flops_frac", &SpmdOptions::min_segment_flops_frac)
       .def_readwrite("cost_factor", &SpmdOptions::cost_factor)
@@ -206,6 +207,7 @@ PYBIND11_MODULE(_C, m) {
       .def_readonly("var_bytes_per_device", &SpmdStats::var_bytes_per_device)
       .def_readonly("forced_weight_splits", &SpmdStats::forced_weight_splits)
       .def_readonly("infeasible_subgraphs", &SpmdStats::infeasible_subgraphs)
+      .def_readonly("threads_used", &SpmdStats::threads_used)
       .def_readonly("ignored_annotations", &SpmdStats::ignored_annotations)
       .def_readonly("collectives", &SpmdStats::collectives);
   py::class_<SpmdPlan>(m, "SpmdPlan")

@@ -1,5 +1,8 @@
 #include "spmd_planner.h"
 
+#include <atomic>
+#include <thread>
+
 #include <algorithm>
 #include <chrono>
 #include <functional>
@@ -499,6 +502,39 @@ SpmdPlan PlanSpmdLevel(Graph* gp, const SpmdOptions& opt) {
   struct Cell { double cost = kInfCost; int prev = -1; SubSolution sol; };
   std::vector<std::vector<Cell>> dp(S);
   std::set<std::string> distinct;
+  // ILP_NUM_THREADS > 1: the sub-problems (one per distinct sub-graph signature x head layout x tail layout) are independent --
+  // solve them on a pool first, the DP below then only looks them up (reference: ILP_NUM_THREADS feeds its MIP solver's threads)
+  if (opt.num_threads > 1) {
+    struct Job { std::string key; int k; const DimStrategy* sh; const DimStrategy* st; SubSolution sol; };
+    std::vector<Job> jobs;
+    std::set<std::string> queued;
+    for (int k = 0; k < S; ++k) {
+      const int nh = k > 0 ? (int)sopt[k - 1].size() : 1;
+      const int nt = k < S - 1 ? (int)sopt[k].size() : 1;
+      const std::string sig = SegmentSignature(p, members[k], k > 0 ? seps[k - 1] : -1, k < S - 1 ? seps[k] : -1);
+      for (int it = 0; it < nt; ++it)
+        for (int ih = 0; ih < nh; ++ih) {
+          const DimStrategy* sh = k > 0 ? &sopt[k - 1][ih] : nullptr;
+          const DimStrategy* st = k < S - 1 ? &sopt[k][it] : nullptr;
+          std::string key = sig + "|" + (sh ? sh->str() : "-") + "|" + (st ? st->str() : "-");
+          if (queued.insert(key).second) jobs.push_back({std::move(key), k, sh, st, SubSolution()});
+        }
+    }
+    std::atomic<size_t> next{0};
+    auto worker = [&]() {
+      for (size_t i = next++; i < jobs.size(); i = next++) {
+        Job& j = jobs[i];
+        j.sol = SolveSub(p, members[j.k], pin_map(j.k, j.sh, j.st), foreign_map(j.k, j.sh, j.st));
+      }
+    };
+    const int nthr = (int)std::min<size_t>((size_t)opt.num_threads, std::max<size_t>(1, jobs.size()));
+    std::vector<std::thread> pool;
+    for (int t = 1; t < nthr; ++t) pool.emplace_back(worker);
+    worker();
+    for (auto& t : pool) t.join();
+    for (auto& j : jobs) memo.emplace(j.key, std::move(j.sol));
+    plan.stats.threads_used = nthr;
+  }
   for (int k = 0; k < S; ++k) {
     const int nh = k > 0 ? (int)sopt[k - 1].size() : 1;
     const int nt = k < S - 1 ? (int)sopt[k].size() : 1;

@@ -22,6 +22,7 @@ namespace tepdist {
 struct SpmdOptions {
   int num = 2;                       // devices at this mesh level
   double var_mem_limit = 150e9;      // VAR_MEM_LIMIT (bytes per device for variables + slots + grads)
+  int num_threads = 1;               // ILP_NUM_THREADS: sub-graph problems solved concurrently (same plan, less wall time)
   bool context_parallel = false;     // attention never reshards to heads: the sequence split stays, K / V ride a ring ("cp" strategy)
   int mem_split_min_rank = 1;        // memory plan: only variables of at least this rank may be FORCED to be stored sharded
                                      // (2 = matrices only: Megatron-style tensor parallelism keeps biases / LayerNorm vectors whole)
@@ -52,6 +53,7 @@ struct SpmdStats {
   double var_bytes_per_device = 0;
   int forced_weight_splits = 0;
   int ignored_annotations = 0;   // user split / replicate annotations no candidate of the node can honour
+  int threads_used = 1;          // worker threads that solved the sub-graph problems (SpmdOptions::num_threads)
   int infeasible_subgraphs = 0;  // sub-graphs without a consistent assignment (their nodes keep candidate 0): a planner defect if > 0
   std::map<std::string, int> collectives;  // kind -> count implied by the chosen plan
 };

@@ -800,3 +800,27 @@ def test_context_parallel_plan_keeps_the_sequence_split_through_attention():
         odd = dataclasses.replace(cfg, n_head=3, n_embd=96, n_ctx=n_ctx)
         _, info3 = plan_spmd(build_gpt2_graph(odd, batch=1), 2, "auto")
         assert info3["context_parallel"] == want, (n_ctx, info3["collectives"])
+
+
+def test_ilp_num_threads_solves_sub_graphs_concurrently_with_the_same_plan(monkeypatch):
+    """ILP_NUM_THREADS (reference: threads of its MIP solver): the per-sub-graph problems are independent, a pool solves them
+    before the DP over separators looks them up -- the plan must not depend on the thread count."""
+    from tepdist_b200 import config
+    g = build_gpt2_graph(CONFIGS["tiny"], batch=4)
+    got = {}
+    for thr in (1, 3):
+        cg = to_native(g)
+        o = _C.SpmdOptions()
+        o.num, o.num_threads = 2, thr
+        o.var_mem_limit, o.mem_split_min_rank = 1.0, 2            # the tensor-parallel plan: most sub-problems
+        plan = _C.plan_spmd_level(cg, o)
+        assert plan.stats.threads_used == thr
+        got[thr] = ([c.tag for c in plan.choice], plan.stats.comm_bytes, plan.stats.infeasible_subgraphs)
+    assert got[1] == got[3]
+    monkeypatch.setenv("ILP_NUM_THREADS", "3")
+    config.env(reload=True)
+    try:
+        assert config.spmd_overrides()["num_threads"] == 3 and "ILP_NUM_THREADS" not in config.INERT_KEYS
+    finally:
+        monkeypatch.undo()
+        config.env(reload=True)
