@@ -12,7 +12,7 @@ Launch with torchrun (one process per GPU); single-process works for 1 GPU / CPU
 from __future__ import annotations
 
 import os
-from typing import Any, Dict, List, Optional
+from typing import Any, Dict, Optional
 
 import torch
 import torch.distributed as dist

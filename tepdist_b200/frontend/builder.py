@@ -8,7 +8,6 @@ them shard-wise (F5 `init_from_remote`).
 """
 from __future__ import annotations
 
-import math
 from typing import Any, Dict, List, Optional, Sequence, Tuple
 
 from ..ir import Graph, Node, TensorType, Value, numel

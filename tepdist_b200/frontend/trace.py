@@ -10,7 +10,7 @@ from __future__ import annotations
 
 import math
 import operator
-from typing import Any, Callable, Dict, Optional, Sequence, Tuple
+from typing import Any, Dict, Optional
 
 import torch
 import torch.fx as fx

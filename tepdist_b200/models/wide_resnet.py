@@ -4,7 +4,6 @@ kConvolution custom-calls do; the planner sees batch / in-channel / 
 from __future__ import annotations
 
 from dataclasses import dataclass
-from typing import List
 
 from ..frontend.builder import GraphBuilder, build_training_step
 from ..ir import Graph, Value

@@ -10,10 +10,9 @@ ExecuteRemotePlan gRPCs) rides on the torch.distributed control plane of the ser
 from __future__ import annotations
 
 import io
-import json
 import threading
 from concurrent import futures
-from typing import Any, Callable, Dict, List, Optional
+from typing import Any, Dict, List, Optional
 
 import grpc
 import torch

@@ -14,14 +14,13 @@ the flat buffers directly.
 """
 from __future__ import annotations
 
-import math
 import os
-from typing import Any, Callable, Dict, List, Optional, Sequence, Tuple
+from typing import Any, Callable, Dict, List, Optional, Tuple
 
 import torch
 
 from .. import ops
-from ..ir import COLLECTIVE_OPS, SOURCE_OPS, Graph, Node, TensorType, Value
+from ..ir import COLLECTIVE_OPS, SOURCE_OPS, Graph, Node, Value
 from ..utils.init import init_tensor
 
 # tensor-parallel plans: run `linear -> all_reduce [-> + bias] [-> + residual]` as GEMM -> all-reduce over peer memory

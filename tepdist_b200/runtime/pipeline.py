@@ -12,7 +12,6 @@ from typing import Any, Dict, List, Optional, Tuple
 import torch
 import torch.distributed as dist
 
-from .. import ops
 from ..ir import Graph, Node, Value
 from .executor import Executor, shard_of
 

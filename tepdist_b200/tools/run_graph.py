@@ -19,7 +19,7 @@ from typing import Dict
 
 import torch
 
-from ..frontend.builder import GraphBuilder, build_training_step
+from ..frontend.builder import GraphBuilder
 from ..ir import Graph
 from ..runtime.executor import Executor
 

@@ -102,7 +102,6 @@ def case_state(strategy):
 def case_clip(strategy):
     """GPT-2 tiny with global-norm and per-tensor gradient clipping at a threshold that bites on every step."""
     from tepdist_b200.api import Trainer
-    from tepdist_b200.frontend import builder
     from tepdist_b200.models.gpt2 import CONFIGS, build_gpt2_graph
     cfg = CONFIGS["tiny"]
     if strategy.startswith(("pp", "dp2")) and int(os.environ.get("WORLD_SIZE", "1")) == 1:

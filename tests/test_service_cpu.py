@@ -1,7 +1,6 @@
 """CPU tests: client -> gRPC -> service -> planner -> runtime round trip, checkpoint save / rotate / lazy / restore."""
 import json
 import os
-import threading
 
 import pytest
 
