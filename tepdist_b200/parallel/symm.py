@@ -220,6 +220,33 @@ class SymmetricBuffer:
         if self.world > 1:
             dist.barrier(self.group)
 
+    def close(self) -> None:
+        """Collective release (every rank of the group calls it, after the last kernel that touches the buffer has finished):
+        unmap the multicast mapping and every peer mapping, drop the allocation handles.  Buffers normally live as long as the
+        process; this exists for long-running services that rebuild plans (rpc/service.py plan cache eviction)."""
+        if getattr(self, "_closed", False):
+            return
+        torch.cuda.synchronize()
+        if self.world > 1:
+            dist.barrier(self.group)          # nobody unmaps pages a peer kernel may still be reading
+        lib = self.lib
+        if self.backend == "vmm":
+            if self.mc_ptr is not None:
+                lib.tepd_vmm_unmap(self.mc_ptr, self.nbytes)
+                lib.tepd_vmm_release(self._mc_handle)
+                self.mc_ptr = None
+            for q, h in zip(self.ptrs, self._handles):
+                lib.tepd_vmm_unmap(q, self.nbytes)
+                lib.tepd_vmm_release(h)
+        else:
+            for r, q in enumerate(self.ptrs):
+                if r != self.rank:
+                    lib.tepd_ipc_close(q)
+            if self.world > 1:
+                dist.barrier(self.group)      # peers have closed their mappings before the owner frees
+            lib.tepd_symm_free(self.local_ptr)
+        self.ptrs, self._closed = [], True
+
     def tensor(self, dtype: torch.dtype, numel: Optional[int] = None, offset_bytes: int = 0) -> torch.Tensor:
         """Zero-copy torch view of the LOCAL buffer."""
         t = torch.as_tensor(_CudaArray(self.local_ptr + offset_bytes, self.nbytes - offset_bytes), device="cuda")
