@@ -346,9 +346,38 @@ def case_collectives(strategy):
     return {"losses": [], "parallelism": strategy, "collectives": None, "checks": checks, "fails": fails}
 
 
+def case_ring(strategy):
+    """parallel/ring_attention.py on its own: contiguous and zig-zag K / V rings (forward + backward) against full-sequence
+    attention, every rank checking its own block; reports the largest error and each layout's per-rank work (block products)."""
+    from tepdist_b200.api import init_distributed
+    from tepdist_b200.ops.attention import attention_bwd, attention_fwd
+    from tepdist_b200.parallel.ring_attention import RingAttention
+    init_distributed("gloo")
+    r, n = dist.get_rank(), dist.get_world_size()
+    torch.manual_seed(0)
+    B, S, H, D = 2, 16 * n, 2, 16
+    qkv, do = torch.randn(B, S, H, 3, D), torch.randn(B, S, H, D)
+    q, k, v = qkv[:, :, :, 0], qkv[:, :, :, 1], qkv[:, :, :, 2]
+    res = {"losses": [], "parallelism": None, "collectives": None}
+    L = S // n
+    sl = slice(r * L, (r + 1) * L)
+    for causal in (True, False):
+        o, lse = attention_fwd(q, k, v, causal=causal)
+        grads = attention_bwd(do, q, k, v, o, lse, causal=causal)
+        for zz in (False, True):
+            ring = RingAttention(dist.group.WORLD, list(range(n)), r, zigzag=zz)
+            o2, lse2 = ring.forward(q[:, sl], k[:, sl], v[:, sl], causal=causal)
+            g2 = ring.backward(do[:, sl], q[:, sl], k[:, sl], v[:, sl], o2, lse2, causal=causal)
+            err = max([(o2 - o[:, sl]).abs().max().item()] + [(a - b[:, sl]).abs().max().item() for a, b in zip(g2, grads)])
+            stats = [None] * n
+            dist.all_gather_object(stats, (err, ring.block_products))
+            res[f"{'causal' if causal else 'full'}_{'zigzag' if zz else 'contiguous'}"] = {"err": max(e for e, _ in stats), "work": [w for _, w in stats]}
+    return res
+
+
 if __name__ == "__main__":
     case, out = sys.argv[1], sys.argv[2]
-    CASES_ = {"gpt2": case_gpt2, "gpt2s": lambda st: case_gpt2(st, True), "gpt2b1": lambda st: case_gpt2(st, False, 1), "mlp": case_mlp, "moe": case_moe, "ckpt": case_ckpt, "state": case_state, "tpfused": case_tpfused, "manualdp": case_manualdp, "opts": case_opts, "optsgpt": case_optsgpt, "conv": case_conv, "resume": case_resume, "fullstate": case_fullstate, "clip": case_clip, "sched": case_sched, "collectives": case_collectives}
+    CASES_ = {"gpt2": case_gpt2, "gpt2s": lambda st: case_gpt2(st, True), "gpt2b1": lambda st: case_gpt2(st, False, 1), "mlp": case_mlp, "moe": case_moe, "ckpt": case_ckpt, "state": case_state, "tpfused": case_tpfused, "manualdp": case_manualdp, "opts": case_opts, "optsgpt": case_optsgpt, "conv": case_conv, "resume": case_resume, "fullstate": case_fullstate, "clip": case_clip, "sched": case_sched, "collectives": case_collectives, "ring": case_ring}
 
     def run_case(c):
         name, _, strat = c.partition(":")

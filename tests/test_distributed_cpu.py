@@ -97,6 +97,26 @@ def test_collective_lowering_every_op_every_dim_every_mesh_level(tmp_path, case,
     assert got["checks"] == (16 if world == 2 else 32) and not got["fails"], got
 
 
+def test_ring_attention_contiguous_and_zigzag_equal_full_attention_and_zigzag_balances_causal_work(tmp_path):
+    """3 ranks (odd: two zig-zag chunks travel between one pair of ranks): both ring layouts reproduce full attention and its
+    gradients; with a causal mask the contiguous ring's work grows with the rank (0.5 / 1.5 / 2.5 block products forward),
+    the zig-zag layout gives every rank n / 2."""
+    got = _run("ring:auto", 3, tmp_path)
+    for key in ("causal_contiguous", "causal_zigzag", "full_contiguous", "full_zigzag"):
+        assert got[key]["err"] < 5e-6, (key, got[key])
+    assert got["causal_contiguous"]["work"] == [1.0, 3.0, 5.0]            # forward + backward
+    assert got["causal_zigzag"]["work"] == [3.0, 3.0, 3.0]
+    assert got["full_zigzag"]["work"] == got["full_contiguous"]["work"] == [6.0, 6.0, 6.0]    # (no mask: zig-zag is not used)
+
+
+def test_context_parallel_zigzag_trains_like_a_single_process(tmp_path):
+    ref = _single("gpt2:auto")
+    got = _run("gpt2:cp", 2, tmp_path, extra_env={"TEPDIST_CP_ZIGZAG": "1"})
+    assert got["parallelism"] == "cp2", got
+    for a, b in zip(got["losses"], ref["losses"]):
+        assert abs(a - b) <= 2e-4 * max(1.0, abs(b)), (got, ref)
+
+
 def test_context_parallel_on_a_2d_mesh_matches_single_process(tmp_path):
     """dp2cp2 on 4 ranks: the batch is split over one mesh level, the sequence over the other; each pair of ranks that shares a
     batch shard forms its own K / V ring (the ring's process group is the cp level's group, not the world)."""

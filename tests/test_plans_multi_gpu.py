@@ -76,6 +76,17 @@ def test_context_parallel_ring_attention_on_two_gpus_matches_one_gpu(tmp_path):
 
 
 @pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
+def test_context_parallel_zigzag_on_two_gpus_matches_one_gpu(tmp_path):
+    """Load-balanced (zig-zag) ring: 512 tokens = 4 chunks of 128; rank 0 computes for chunks (0, 3), rank 1 for (1, 2); the
+    half-block products run the same tcgen05 block kernels as the contiguous ring."""
+    env = {"TEPDIST_TEST_NCTX": "512", "TEPDIST_CP_ZIGZAG": "1"}
+    ref = _run("gpt2:auto", 1, tmp_path, env)
+    got = _run("gpt2:cp", 2, tmp_path, env)
+    assert got["parallelism"] == "cp2", got
+    _close(got, ref)
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
 def test_collective_lowering_on_gpus_over_nccl(tmp_path):
     """Every collective op of the IR on every dim of a rank-3 tensor over NCCL (the reference's dapple_*_test.cc run on real
     devices): 1-D mesh over all visible GPUs, and a 2 x (n/2) mesh when there are at least 4."""
