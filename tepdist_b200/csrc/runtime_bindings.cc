@@ -2,6 +2,7 @@
 #include <pybind11/pybind11.h>
 #include <pybind11/stl.h>
 
+#include "runtime/data_loader.h"
 #include "runtime/dev_mesh.h"
 #include "runtime/slice_philox.h"
 #include "runtime/task_graph.h"
@@ -11,6 +12,43 @@ namespace py = pybind11;
 using namespace tepdist;
 
 void BindRuntime(py::module_& m) {
+  // ---- native input pipeline (runtime/data_loader.h)
+  py::class_<TokenSource, std::shared_ptr<TokenSource>>(m, "TokenSource")
+      .def(py::init<>())
+      .def("add_dataset", &TokenSource::AddDataset, py::arg("files"), py::arg("weight") = 1.0, py::arg("bytes_per_token") = 2)
+      .def("set_synthetic", &TokenSource::SetSynthetic, py::arg("vocab"))
+      .def("total_tokens", &TokenSource::total_tokens)
+      .def("num_datasets", &TokenSource::num_datasets)
+      .def("sample", [](const TokenSource& s, uint64_t seed, uint64_t sample_id, int n) {
+        std::vector<int32_t> v((size_t)n);
+        s.Sample(seed, sample_id, n, v.data());
+        return v;
+      })
+      .def("locate", [](const TokenSource& s, uint64_t seed, uint64_t sample_id, int n) {
+        int d, f;
+        uint64_t off;
+        s.Locate(seed, sample_id, n, &d, &f, &off);
+        return py::make_tuple(d, f, off);
+      });
+  py::class_<BatchLoader>(m, "BatchLoader")
+      .def(py::init<std::shared_ptr<TokenSource>, int, int, int, int, uint64_t, int>(), py::arg("source"), py::arg("batch"), py::arg("n_ctx"),
+           py::arg("rank") = 0, py::arg("world") = 1, py::arg("seed") = 0, py::arg("threads") = 2)
+      .def("set_buffers", &BatchLoader::SetBuffers)
+      .def("start", &BatchLoader::Start, py::arg("first_step") = 0)
+      .def("acquire", [](BatchLoader& l) {
+        uint64_t step = 0;
+        int slot;
+        {
+          py::gil_scoped_release nogil;      // blocks until a worker thread has finished the batch
+          slot = l.Acquire(&step);
+        }
+        return py::make_tuple(slot, step);
+      })
+      .def("release", &BatchLoader::Release)
+      .def("stop", &BatchLoader::Stop, py::call_guard<py::gil_scoped_release>())
+      .def("num_slots", &BatchLoader::num_slots)
+      .def("batches_filled", &BatchLoader::batches_filled);
+
   // ---- device mesh
   py::class_<DevGroup>(m, "DevGroup").def_readonly("ordinal", &DevGroup::ordinal).def_readonly("devices", &DevGroup::devices);
   py::class_<CommDevManager>(m, "CommDevManager")
