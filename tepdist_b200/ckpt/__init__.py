@@ -16,6 +16,8 @@ import torch
 
 
 class CheckpointManager:
+    COMMIT = "COMMITTED"     # written into step_<n>/ after all ranks' shards of that step are on disk
+
     def __init__(self, root: str, rank: int, world: int, max_to_keep: int = 5):
         self.dir = os.path.join(root, f"ckpt_{rank}_of_{world}")
         self.rank, self.world, self.max_to_keep = rank, world, max_to_keep
@@ -74,7 +76,13 @@ class CheckpointManager:
         json.dump(manifest, open(os.path.join(tmp, "manifest.json"), "w"))
         if os.path.exists(prefix):
             shutil.rmtree(prefix)
-        os.replace(tmp, prefix)     # atomic publish
+        os.replace(tmp, prefix)     # atomic publish of THIS rank's shards
+        # commit: the step counts only once EVERY rank has published its shards -- a rank that died mid-save must not leave a
+        # checkpoint that looks complete from the others' point of view (restore / latest() skip steps without the marker)
+        import torch.distributed as dist
+        if self.world > 1 and dist.is_available() and dist.is_initialized() and dist.get_world_size() == self.world:
+            dist.barrier()
+        open(os.path.join(prefix, self.COMMIT), "w").write(str(global_step))
         if global_step in self.queue:          # re-saving a step (lazy save then explicit save, resume then save) must not
             self.queue.remove(global_step)     # make rotation delete the directory that was just written
         self.queue.append(global_step)
@@ -92,8 +100,15 @@ class CheckpointManager:
         return None
 
     # ------------------------------------------------------------------ restore
+    def committed(self, step: int, rank_dir: Optional[str] = None) -> bool:
+        return os.path.exists(os.path.join(rank_dir or self.dir, f"step_{step}", self.COMMIT))
+
     def latest(self) -> Optional[int]:
-        return self.queue[-1] if self.queue else None
+        """Newest step of this rank's queue whose save completed on every rank."""
+        for step in reversed(self.queue):
+            if self.committed(step):
+                return step
+        return None
 
     def restore(self, executor, global_step: Optional[int] = None) -> int:
         step = self.latest() if global_step is None else global_step
@@ -103,6 +118,8 @@ class CheckpointManager:
             raise FileNotFoundError("no checkpoint to restore")
         prefix = os.path.join(self.dir, f"step_{step}")
         st = executor.store
+        if os.path.isdir(prefix) and not self.committed(step):
+            raise FileNotFoundError(f"checkpoint step {step} was never committed (a rank failed while saving it)")
         same_layout = os.path.exists(os.path.join(prefix, "manifest.json"))
         if same_layout:
             manifest = json.load(open(os.path.join(prefix, "manifest.json")))
@@ -135,7 +152,7 @@ class CheckpointManager:
         for d in self._all_rank_dirs():
             qf = os.path.join(d, "checkpoint_queue.json")
             if os.path.exists(qf):
-                q = json.load(open(qf))
+                q = [s_ for s_ in json.load(open(qf)) if self.committed(s_, d)]
                 if q:
                     best = q[-1] if best is None else max(best, q[-1])
         return best

@@ -155,6 +155,24 @@ def test_resaving_a_step_keeps_its_directory(tmp_path):
     assert cm.restore(ex) == 5
 
 
+def test_a_step_counts_only_once_its_save_was_committed(tmp_path):
+    """Every rank publishes its shards, then (after a barrier over the job) writes a COMMITTED marker into its step directory.
+    A step whose marker is missing -- a rank died between the two -- is skipped by latest() and refused by restore()."""
+    from tepdist_b200.ckpt import CheckpointManager
+    from tepdist_b200.runtime.executor import Executor
+    ex = Executor(build_gpt2_graph(CONFIGS["tiny"]), torch.device("cpu"), use_cuda_graph=False)
+    cm = CheckpointManager(str(tmp_path), 0, 1, max_to_keep=3)
+    cm.save(ex, 1)
+    cm.save(ex, 2)
+    assert cm.latest() == 2 and cm.committed(2)
+    os.remove(os.path.join(cm.dir, "step_2", CheckpointManager.COMMIT))       # "the job died while saving step 2"
+    fresh = CheckpointManager(str(tmp_path), 0, 1, max_to_keep=3)             # a restarted job
+    assert fresh.latest() == 1 and fresh.restore(ex) == 1
+    with pytest.raises(FileNotFoundError, match="never committed"):
+        fresh.restore(ex, 2)
+    assert fresh._latest_any_layout() == 1                                    # (the cross-plan restore path picks the same step)
+
+
 def test_launcher_cluster_spec(tmp_path):
     from tepdist_b200.launch import entry_for
     spec = {"master": {"ip": "10.0.0.1", "port": 2222, "gpu_ids": [0, 1]}, "workers": [{"ip": "10.0.0.2", "port": 2223, "gpu_ids": [2, 3]}]}
