@@ -22,6 +22,7 @@ def main():
                     help='reference: "optimizer" in examples/gpt_moe/pretrain_moe.json')
     ap.add_argument("--clip-norm", default=None, choices=["global", "local"], help='gradient clipping (reference gpt_moe config: "clip_norm")')
     ap.add_argument("--clip-norm-value", type=float, default=1.0)
+    ap.add_argument("--data", default=None, help="comma-separated token files (tepdist_b200.data.write_token_file) or 'synthetic'; default: one fixed random batch")
     ap.add_argument("--no-graph", action="store_true", help="run the step eagerly (default: whole step replayed from a CUDA graph)")
     a = ap.parse_args()
     clip = {"clip_norm": a.clip_norm, "clip_norm_value": a.clip_norm_value} if a.clip_norm else {}
@@ -29,9 +30,15 @@ def main():
     if a.tiny:
         cfg = MoEConfig(n_layer=2, hidden=128, ffn=256, n_head=2, experts=4, capacity=64, groups=4, seq=128, batch=a.batch, vocab=1000)
     tr = Trainer(build_gpt_moe_graph(cfg, optimizer=a.optimizer, **clip), strategy=a.strategy, use_cuda_graph=not a.no_graph)
-    gen = torch.Generator().manual_seed(0)
-    tok = torch.randint(0, cfg.vocab, (cfg.batch, cfg.seq), generator=gen, dtype=torch.int32)
-    feeds = {"tokens": tok, "labels": torch.roll(tok, -1, 1)}
+    if a.data:      # native prefetching loader: every rank draws the same global batch, the trainer takes what its plan assigns to it
+        from tepdist_b200.data import TokenLoader
+        src = {"synthetic_vocab": cfg.vocab} if a.data == "synthetic" else {"files": a.data.split(",")}
+        batches = iter(TokenLoader(batch=cfg.batch, n_ctx=cfg.seq, **src))
+    else:
+        gen = torch.Generator().manual_seed(0)
+        tok = torch.randint(0, cfg.vocab, (cfg.batch, cfg.seq), generator=gen, dtype=torch.int32)
+        fixed = {"tokens": tok, "labels": torch.roll(tok, -1, 1)}
+        batches = iter(lambda: fixed, None)
     t0 = time.time()
     t_steady = None
     for i in range(a.steps):
@@ -39,7 +46,7 @@ def main():
             if torch.cuda.is_available():
                 torch.cuda.synchronize()
             t_steady = time.time()
-        loss = tr.step(feeds)
+        loss = tr.step(next(batches))
         if tr.rank == 0:
             print(f"step {i} loss {loss:.4f}")
     if torch.cuda.is_available():
