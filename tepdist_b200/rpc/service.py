@@ -164,19 +164,26 @@ class ServiceImpl:
         m = unpack(req)     # {"name", "tensor" | ("shape","dtype"), "variable": bool}
         if m.get("variable"):
             return pack({"ok": True, "note": "variables are initialised on the servers from their init specs"})
-        self.host_inputs[m["name"]] = m["tensor"]
+        with self.exec_lock:                  # (ExecutePlan snapshots the registered inputs under the same lock)
+            self.host_inputs[m["name"]] = m["tensor"]
         return pack({"ok": True})
 
     def ExecutePlan(self, req: bytes, ctx) -> bytes:
         import time
         m = unpack(req)
-        feeds = m.get("feeds") or {k: self.host_inputs[k] for k in m.get("input_names", self.host_inputs)}
         seq = m.get("seq")
         with self.seq_cv:                     # == exec_lock; every broadcast + command pair runs under it
             if seq is not None:               # pipelined clients (NUM_PARALLEL_RPC_STEPS): steps run in the order they were issued
                 ok = self.seq_cv.wait_for(lambda: seq <= self.next_seq, timeout=600)
-                if not ok or seq < self.next_seq:
-                    raise RuntimeError(f"ExecutePlan seq {seq}: expected {self.next_seq}")
+                if seq < self.next_seq:
+                    raise RuntimeError(f"ExecutePlan seq {seq} arrived after step {self.next_seq - 1} had run (duplicate or reordered request)")
+                if not ok:
+                    # the predecessor never arrived (lost request): give up on it so that the steps queued behind this one do not
+                    # each sit out their own timeout
+                    self.next_seq = seq + 1
+                    self.seq_cv.notify_all()
+                    raise RuntimeError(f"ExecutePlan seq {seq}: step {seq - 1} never arrived within 600 s")
+            feeds = m.get("feeds") or {k: self.host_inputs[k] for k in m.get("input_names", self.host_inputs)}
             try:
                 t0 = time.time()
                 msg = {"cmd": "execute", "handle": m["handle"], "feeds": feeds}
