@@ -23,6 +23,7 @@ struct Candidate {
 struct RuleOptions {
   bool allow_glue_compute_intensive = false;  // dots/convs never run replicated (reference: no Glue candidate)
   bool save_variable_mem = false;             // suppress batch-split proposals (reference: split_for_mem_save_)
+  bool sequence_parallel = false;             // row-parallel linears may reduce-scatter over a token dim inside the node ("contract_rs<d>")
   bool context_parallel = false;              // attention keeps a sequence split (ring over K / V) instead of resharding to heads
 };
 

@@ -82,6 +82,7 @@ void BuildProblem(Problem& p, SpmdStats* stats) {
     RuleOptions ro;
     ro.save_variable_mem = IsComputeIntensive(n.op) && mem_save_groups.count(n.group) > 0;
     ro.context_parallel = opt.context_parallel;
+    ro.sequence_parallel = opt.sequence_parallel;
     if (ro.save_variable_mem) p.forced.insert(n.id);   // (candidates restricted to the ones that keep the weight split)
     auto c = EnumerateCandidates(g, n, opt.num, ro);
     // user annotations (xla_sharding.split / replicate equivalents)
@@ -109,6 +110,8 @@ void BuildProblem(Problem& p, SpmdStats* stats) {
     nc.resize(c.size());
     for (size_t i = 0; i < c.size(); ++i) {
       double cost = c[i].node_cost;
+      if (n.op == "linear" && c[i].tag.rfind("contract_rs", 0) == 0)   // the reduce-scatter inside the node is a launch like any other
+        cost += opt.collective_latency_bytes >= 0 ? opt.collective_latency_bytes : opt.hw.coll_latency * opt.hw.link_bw;
       if (c[i].tag == "seq" && (n.op == "attention" || n.op == "attention_bwd")) {
         // the ring posts one exchange per hop (forward: K / V; backward: K / V and the dK / dV accumulator): same per-launch
         // price as every other collective, or the ring would look free next to the gathers it competes with

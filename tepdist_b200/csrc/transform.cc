@@ -158,7 +158,9 @@ struct Rewriter {
       std::map<std::string, Attr> a = n.attrs;
       FixAttrs(n, c, a, outs);
 
-      const bool unfuse = n.op == "linear" && c.outs[0].partial && (n.attr_b("bias") || n.attr_b("residual"));
+      // "contract_rs<d>": row-parallel linear whose reduction is a reduce-scatter over dim d inside the node (rules.cc LinearRule)
+      const bool rs_inside = n.op == "linear" && c.tag.rfind("contract_rs", 0) == 0;
+      const bool unfuse = rs_inside || (n.op == "linear" && c.outs[0].partial && (n.attr_b("bias") || n.attr_b("residual")));
       if (!unfuse) {
         int id = out.AddNode(n.op, ins, outs, a, n.name, n.group, n.backward);
         out.nodes[id].stage = n.stage;
@@ -175,20 +177,27 @@ struct Rewriter {
       std::map<std::string, Attr> la = a;
       la["bias"] = false;
       la["residual"] = false;
-      int lid = out.AddNode("linear", {ins[0], ins[1]}, outs, la, n.name, n.group, n.backward);
+      const DimStrategy partial = DimStrategy::Partial(num, 0);
+      std::vector<TensorType> louts = outs;
+      if (rs_inside) louts[0] = Sharded(n.outputs[0], partial);     // the GEMM itself produces the full-shape partial sum
+      int lid = out.AddNode("linear", {ins[0], ins[1]}, louts, la, n.name, n.group, n.backward);
       out.nodes[lid].stage = n.stage;
       ValueRef self{n.id, 0};
       DimStrategy want = DimStrategy::Glue();
-      bool first = true, same = true;
-      for (auto& u : g.users(self)) {
-        const DimStrategy& need = plan.choice[u.node].ins[u.operand];
-        if (need.partial) { same = false; break; }
-        if (first) { want = need; first = false; }
-        else if (need != want) same = false;
+      if (rs_inside) {
+        want = c.outs[0];
+      } else {
+        bool first = true, same = true;
+        for (auto& u : g.users(self)) {
+          const DimStrategy& need = plan.choice[u.node].ins[u.operand];
+          if (need.partial) { same = false; break; }
+          if (first) { want = need; first = false; }
+          else if (need != want) same = false;
+        }
+        if (!same || first) want = DimStrategy::Glue();
       }
-      if (!same || first) want = DimStrategy::Glue();
       vmap[self] = ValueRef{lid, 0};
-      produced[self] = c.outs[0];
+      produced[self] = rs_inside ? partial : c.outs[0];
       ValueRef red = DoReshard(self, want, n);
       for (auto it = reshard_cache.begin(); it != reshard_cache.end();)  // cached entries refer to the pre-epilogue value
         it = (it->first.first == self) ? reshard_cache.erase(it) : std::next(it);

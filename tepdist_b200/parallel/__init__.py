@@ -17,6 +17,9 @@ def plan_spmd(graph: Graph, num: int, strategy: str = "auto", options: Optional[
     from ..planner import from_native, merge_client_attrs, to_native
     options = dict(options or {})
     g = graph
+    sp = strategy == "tpsp"      # tensor parallel in the sequence-parallel form: reduce-scatter / all-gather around the token-wise ops
+    if sp:
+        strategy = "tp"
     if strategy in ("dp", "tp", "cp"):
         g = Graph.from_dict(graph.to_dict())
         for n in g.nodes:
@@ -31,6 +34,8 @@ def plan_spmd(graph: Graph, num: int, strategy: str = "auto", options: Optional[
         o.ignore_annotation = False
     if strategy == "cp":
         o.context_parallel = True
+    if sp:
+        o.sequence_parallel = True
     if strategy == "tp":
         o.var_mem_limit = 1.0  # force every weight MATRIX to be stored sharded -> tensor parallel (vectors stay whole)
         o.mem_split_min_rank = 2

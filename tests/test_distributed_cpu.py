@@ -71,7 +71,7 @@ def _single(case):
             "gpt2b1": lambda st: dist_worker.case_gpt2(st, False, 1), "moe": dist_worker.case_moe}[name]("auto")
 
 
-_WORLD2_CASES = ["mlp:auto", "mlp:dp", "gpt2:auto", "gpt2s:auto", "gpt2:explore", "gpt2:tp", "gpt2:pp2m2", "moe:ep", "gpt2:cp"]
+_WORLD2_CASES = ["mlp:auto", "mlp:dp", "gpt2:auto", "gpt2s:auto", "gpt2:explore", "gpt2:tp", "gpt2:pp2m2", "moe:ep", "gpt2:cp", "gpt2:tpsp"]
 
 
 @pytest.mark.parametrize("case", _WORLD2_CASES)
@@ -87,6 +87,8 @@ def test_spmd_world2_matches_single_process(case, tmp_path):
         assert got["parallelism"].startswith("pp2"), got
     if case == "gpt2:tp":
         assert got["parallelism"].startswith("tp"), got
+    if case == "gpt2:tpsp":   # tensor parallel, sequence-parallel form: the row-parallel linears reduce-scatter inside the node
+        assert got["parallelism"].startswith("tp") and got["collectives"].get("reduce_scatter", 0) >= 2 * 2, got
     if case == "gpt2:cp":     # context parallel: sequence split through attention, K / V ring (parallel/ring_attention.py)
         assert got["parallelism"] == "cp2", got
     if case in ("mlp:dp", "gpt2:auto", "gpt2:explore"):  # (mlp:auto legitimately prefers a 128-byte activation all-reduce over gradient sync)

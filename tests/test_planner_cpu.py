@@ -824,3 +824,28 @@ def test_ilp_num_threads_solves_sub_graphs_concurrently_with_the_same_plan(monke
     finally:
         monkeypatch.undo()
         config.env(reload=True)
+
+
+def test_sequence_parallel_form_of_tensor_parallelism_is_opt_in():
+    """`tp`: row-parallel linears produce partial sums that are all-reduced (the form the fused NVLS chains execute and the
+    measured tensor-parallel numbers belong to).  `tpsp` adds the "contract_rs<d>" candidates: the reduction becomes a
+    reduce-scatter over a token dim inside the node, bias and the SPLIT residual are added after it, the token-wise backward
+    (LayerNorm, residual adds) runs on 1/n of the tokens and the next column-parallel linear all-gathers its input -- the
+    Megatron sequence-parallel form, which the planner prices at roughly half the bytes of the all-reduce form."""
+    from tepdist_b200.parallel import plan_spmd
+    cfg = CONFIGS["tiny"]
+    g = build_gpt2_graph(cfg, batch=4)
+    out_tp, info_tp = plan_spmd(g, 2, "tp")
+    out_sp, info_sp = plan_spmd(g, 2, "tpsp")
+    assert "contract_rs" not in info_tp["strategies_txt"]
+    assert info_sp["strategies_txt"].count("[contract_rs") == 2 * cfg.n_layer          # attention and MLP output projections
+    assert info_sp["collectives"].get("reduce_scatter", 0) >= 2 * cfg.n_layer
+    assert info_sp["comm_bytes"] < info_tp["comm_bytes"]
+    # the rewritten graph: GEMM (full-shape partial output) -> reduce_scatter -> + bias -> + residual shard
+    names = {n.name: n for n in out_sp.nodes}
+    lin = names["model/h0/attn/c_proj"]
+    assert lin.op == "linear" and not lin.attrs.get("bias") and not lin.attrs.get("residual")
+    assert list(lin.outputs[0].shape) == [4, cfg.n_ctx, cfg.n_embd]
+    users = [n for n in out_sp.nodes if any(v.node == lin.id for v in n.inputs)]
+    assert [u.op for u in users] == ["reduce_scatter"] and list(users[0].outputs[0].shape) == [2, cfg.n_ctx, cfg.n_embd]
+    assert names["model/h0/attn/c_proj/bias"].op == "add" and names["model/h0/attn/c_proj/res"].op == "add"

@@ -96,3 +96,13 @@ def test_collective_lowering_on_gpus_over_nccl(tmp_path):
     if n >= 4:
         got = _run("collectives:2d", n, tmp_path)
         assert got["checks"] == 32 and not got["fails"], got
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
+def test_sequence_parallel_tensor_parallelism_on_two_gpus_matches_one_gpu(tmp_path):
+    """`tpsp`: row-parallel GEMM -> NCCL reduce-scatter over tokens -> bias + residual shard; all-gather before the next
+    column-parallel GEMM."""
+    ref = _run("gpt2:auto", 1, tmp_path)
+    got = _run("gpt2:tpsp", 2, tmp_path)
+    assert got["parallelism"].startswith("tp") and got["collectives"].get("reduce_scatter", 0) >= 4, got
+    _close(got, ref)
