@@ -2,6 +2,7 @@
 
 #include <atomic>
 #include <thread>
+#include <tuple>
 
 #include <algorithm>
 #include <chrono>
@@ -591,12 +592,24 @@ SpmdPlan PlanSpmdLevel(Graph* gp, const SpmdOptions& opt) {
     plan.choice[n.id] = p.cands[n.id][chosen[n.id]];
     for (int o = 0; o < (int)n.outputs.size(); ++o) n.dist[o].levels.push_back(plan.choice[n.id].outs[o]);
   }
+  for (auto& n : g.nodes) {      // communication INSIDE nodes (K / V ring of context-parallel attention, reduce-scatter of "contract_rs")
+    const Candidate& c = plan.choice[n.id];
+    const bool ring = c.tag == "seq" && (n.op == "attention" || n.op == "attention_bwd");
+    const bool rs = n.op == "linear" && c.tag.rfind("contract_rs", 0) == 0;
+    if (ring || rs) plan.stats.comm_bytes += c.node_cost;
+    if (rs) plan.stats.collectives["reduce_scatter"]++;
+  }
+  std::set<std::tuple<int, int, std::string>> counted;
   for (auto& e : p.edges) {
     if (e.operand == -2) continue;
     const DimStrategy& from = plan.choice[e.prod].outs[e.out_idx];
     const DimStrategy& to = e.operand >= 0 ? plan.choice[e.cons].ins[e.operand] : plan.choice[e.cons].outs[0];
     Reshard r = ClassifyReshard(from, to);
     if (r == Reshard::kNone) continue;
+    // the rewrite re-lays a value out once per TARGET layout, however many consumers want it (transform.cc reshard cache): count
+    // it once here too.  (The PBQP objective itself is pairwise -- it charges every consumer edge -- so the solver is biased
+    // against re-laying out values with several consumers; the statistics are exact.)
+    if (!counted.insert({e.prod, e.out_idx, to.str()}).second) continue;
     plan.stats.collectives[ReshardName(r)]++;
     if (r != Reshard::kInvalid && r != Reshard::kDynamicSlice)
       plan.stats.comm_bytes += ReshardBytes(r, e.bytes, opt.num, opt.cost_factor);

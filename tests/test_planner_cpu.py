@@ -831,7 +831,8 @@ def test_sequence_parallel_form_of_tensor_parallelism_is_opt_in():
     measured tensor-parallel numbers belong to).  `tpsp` adds the "contract_rs<d>" candidates: the reduction becomes a
     reduce-scatter over a token dim inside the node, bias and the SPLIT residual are added after it, the token-wise backward
     (LayerNorm, residual adds) runs on 1/n of the tokens and the next column-parallel linear all-gathers its input -- the
-    Megatron sequence-parallel form, which the planner prices at roughly half the bytes of the all-reduce form."""
+    Megatron sequence-parallel form: the same bytes on the wire as the all-reduce form (reduce-scatter + all-gather = all-reduce),
+    less replicated token-wise work."""
     from tepdist_b200.parallel import plan_spmd
     cfg = CONFIGS["tiny"]
     g = build_gpt2_graph(cfg, batch=4)
@@ -840,7 +841,7 @@ def test_sequence_parallel_form_of_tensor_parallelism_is_opt_in():
     assert "contract_rs" not in info_tp["strategies_txt"]
     assert info_sp["strategies_txt"].count("[contract_rs") == 2 * cfg.n_layer          # attention and MLP output projections
     assert info_sp["collectives"].get("reduce_scatter", 0) >= 2 * cfg.n_layer
-    assert info_sp["comm_bytes"] < info_tp["comm_bytes"]
+    assert abs(info_sp["comm_bytes"] - info_tp["comm_bytes"]) < 0.1 * info_tp["comm_bytes"]     # RS + AG = AR
     # the rewritten graph: GEMM (full-shape partial output) -> reduce_scatter -> + bias -> + residual shard
     names = {n.name: n for n in out_sp.nodes}
     lin = names["model/h0/attn/c_proj"]
