@@ -39,6 +39,12 @@ def _run(case, world, tmp_path, extra_env=None):
         # one retry on a fresh port: a job that dies in the rendezvous (port grabbed between _free_port() and the bind, a
         # gloo connect reset on a loaded box) says nothing about the code under test; a real failure fails twice
         print(f"[dist test] {case} x{world} attempt {attempt} failed (rc {pr.returncode}):\n{pr.stderr[-1500:]}")
+        try:      # keep the evidence of an intermittent failure where a later session can find it
+            os.makedirs("/tmp/tepdist_test_failures", exist_ok=True)
+            with open(f"/tmp/tepdist_test_failures/{case.replace(':', '_').replace('+', '_')[:80]}_x{world}_attempt{attempt}.log", "w") as f:
+                f.write(pr.stdout[-20000:] + "\n==== stderr ====\n" + pr.stderr[-20000:])
+        except OSError:
+            pass
     assert pr.returncode == 0, pr.stderr[-3000:]
     return json.load(open(out))
 
