@@ -108,9 +108,10 @@ def plan_spmd_mesh(graph: Graph, nums, kinds):
         for k, v in config.spmd_overrides().items():
             if hasattr(o, k):
                 setattr(o, k, v)
-        if kind == "tp":
+        if kind in ("tp", "tpsp"):
             o.var_mem_limit = 1.0
             o.mem_split_min_rank = 2
+            o.sequence_parallel = kind == "tpsp"
         if kind == "cp":    # sequence split seeded on the sample inputs of THIS level, attention keeps it (K / V ring)
             o.context_parallel = True
             o.ignore_annotation = False
@@ -141,12 +142,12 @@ def plan_spmd_mesh(graph: Graph, nums, kinds):
 def _parse_mesh_strategy(strategy: str):
     """"dp4tp2" / "tp2dp4" / "dp2tp2dp2" -> ([4, 2], ["dp", "tp"]) ; None when `strategy` is not a mesh spec."""
     import re
-    parts = re.findall(r"(dp|tp|cp|auto)(\d+)", strategy)
+    parts = re.findall(r"(dp|tpsp|tp|cp|auto)(\d+)", strategy)
     if len(parts) < 2 or "".join(k + n for k, n in parts) != strategy:
         return None
     # tensor-parallel levels are planned first: the data-parallel level (with its ZeRO-style optimizer sharding) then acts
     # on the already tensor-sharded variables, which is the nesting the executor's in-place sharded update understands
-    parts.sort(key=lambda kn: 0 if kn[0] == "tp" else 1)
+    parts.sort(key=lambda kn: 0 if kn[0] in ("tp", "tpsp") else 1)
     return [int(n) for _, n in parts], [k for k, _ in parts]
 
 

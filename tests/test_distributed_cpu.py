@@ -62,7 +62,7 @@ def _batch(cases, world, tmp_path):
 
 # cases of the feature tests below that share one job per world size
 _SHARED = {2: ["fullstate:auto", "fullstate:pp2m2", "conv:dp", "opts:auto", "sched:auto", "sched:pp2m2"],
-           4: ["fullstate:dp2tp2", "clip:dp2tp2", "clip:pp2m2", "conv:dp2tp2", "optsgpt:dp2tp2", "gpt2:dp2cp2"]}
+           4: ["fullstate:dp2tp2", "clip:dp2tp2", "clip:pp2m2", "conv:dp2tp2", "optsgpt:dp2tp2", "gpt2:dp2cp2", "gpt2:dp2tpsp2"]}
 
 
 def _get(case, world, tmp_path):
@@ -137,6 +137,16 @@ def test_context_parallel_on_a_2d_mesh_matches_single_process(tmp_path):
     ref = _single("gpt2:auto")
     got = _get("gpt2:dp2cp2", 4, tmp_path)
     assert got["parallelism"] == "dp2xcp2", got
+    for a, b in zip(got["losses"], ref["losses"]):
+        assert abs(a - b) <= 2e-4 * max(1.0, abs(b)), (got, ref)
+
+
+def test_sequence_parallel_tensor_parallelism_inside_a_data_parallel_mesh(tmp_path):
+    """dp2tpsp2 on 4 ranks: the tensor-parallel level uses the reduce-scatter / all-gather form, the data-parallel level shards the
+    batch (and the optimizer) on top of it."""
+    ref = _single("gpt2:auto")
+    got = _get("gpt2:dp2tpsp2", 4, tmp_path)
+    assert got["parallelism"] == "tpsp2xdp2" and got["collectives"].get("reduce_scatter", 0) >= 4, got
     for a, b in zip(got["losses"], ref["losses"]):
         assert abs(a - b) <= 2e-4 * max(1.0, abs(b)), (got, ref)
 
