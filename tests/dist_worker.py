@@ -361,6 +361,9 @@ def case_ring(strategy):
     res = {"losses": [], "parallelism": None, "collectives": None}
     L = S // n
     sl = slice(r * L, (r + 1) * L)
+    sums = [None] * n      # every rank must have drawn the same tensors (the reference and the ring are compared rank by rank)
+    dist.all_gather_object(sums, (float(qkv.double().sum()), float(qkv.double().abs().sum()), float(do.double().sum())))
+    res["inputs_identical"] = all(s_ == sums[0] for s_ in sums)
     for causal in (True, False):
         o, lse = attention_fwd(q, k, v, causal=causal)
         grads = attention_bwd(do, q, k, v, o, lse, causal=causal)
@@ -368,10 +371,14 @@ def case_ring(strategy):
             ring = RingAttention(dist.group.WORLD, list(range(n)), r, zigzag=zz)
             o2, lse2 = ring.forward(q[:, sl], k[:, sl], v[:, sl], causal=causal)
             g2 = ring.backward(do[:, sl], q[:, sl], k[:, sl], v[:, sl], o2, lse2, causal=causal)
-            err = max([(o2 - o[:, sl]).abs().max().item()] + [(a - b[:, sl]).abs().max().item() for a, b in zip(g2, grads)])
+            work = ring.block_products
+            o3, _ = ring.forward(q[:, sl], k[:, sl], v[:, sl], causal=causal)      # (diagnostic: is a deviation reproducible in-process?)
+            again = (o3 - o2).abs().max().item()
+            errs = [(o2 - o[:, sl]).abs().max().item()] + [(a - b[:, sl]).abs().max().item() for a, b in zip(g2, grads)] + [again]
             stats = [None] * n
-            dist.all_gather_object(stats, (err, ring.block_products))
-            res[f"{'causal' if causal else 'full'}_{'zigzag' if zz else 'contiguous'}"] = {"err": max(e for e, _ in stats), "work": [w for _, w in stats]}
+            dist.all_gather_object(stats, (errs, work))
+            res[f"{'causal' if causal else 'full'}_{'zigzag' if zz else 'contiguous'}"] = {
+                "err": max(max(e) for e, _ in stats), "work": [w for _, w in stats], "per_rank_o_dq_dk_dv_again": [e for e, _ in stats]}
     return res
 
 
