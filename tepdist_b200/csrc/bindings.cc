@@ -186,6 +186,7 @@ PYBIND11_MODULE(_C, m) {
       .def_readwrite("mem_split_min_rank", &SpmdOptions::mem_split_min_rank)
       .def_readwrite("context_parallel", &SpmdOptions::context_parallel)
       .def_readwrite("sequence_parallel", &SpmdOptions::sequence_parallel)
+      .def_readwrite("share_relayout_cost", &SpmdOptions::share_relayout_cost)
       .def_readwrite("num_threads", &SpmdOptions::num_threads)
       .def_readwrite("collective_latency_bytes", &SpmdOptions::collective_latency_bytes)
       .def_readwrite("min_segment_flops_frac", &SpmdOptions::min_segment_flops_frac)

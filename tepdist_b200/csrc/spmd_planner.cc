@@ -19,6 +19,7 @@ namespace {
 struct Edge {
   int prod, out_idx, cons, operand;  // operand = -1: "update" edge (value -> variable storage)
   double bytes;
+  int fanout = 1;                    // consumer edges of the same produced value
 };
 
 bool IsFwdCompute(const Node& n) {
@@ -152,6 +153,13 @@ void BuildProblem(Problem& p, SpmdStats* stats) {
     for (auto& n : g.nodes)  // Var/Aux affinity: slots follow their variable (zero-byte edge with infinite mismatch)
       if (n.op == "state" && n.has("slot_of") && n.outputs[0].dims == g.nodes[(int)n.attr_i("slot_of")].outputs[0].dims)
         p.edges.push_back({(int)n.attr_i("slot_of"), 0, n.id, -2, 0.0});   // (reduced-shape slots: see rules.cc AdafactorRule)
+  {
+    std::map<std::pair<int, int>, int> fan;     // produced value -> number of operand edges reading it
+    for (auto& e : p.edges)
+      if (e.operand >= 0) ++fan[{e.prod, e.out_idx}];
+    for (auto& e : p.edges)
+      if (e.operand >= 0) e.fanout = fan[{e.prod, e.out_idx}];
+  }
   for (int e = 0; e < (int)p.edges.size(); ++e) {
     p.edges_of[p.edges[e].prod].push_back(e);
     p.edges_of[p.edges[e].cons].push_back(e);
@@ -169,6 +177,12 @@ double EdgeCost(const Problem& p, const Edge& e, const Candidate& cp, const Cand
       p.g.nodes[e.cons].op.rfind("apply_", 0) == 0)
     return kInfCost;
   double cost = ReshardCost(from, to, e.bytes, p.opt.num, p.opt.cost_factor);
+  // Experimental (SpmdOptions::share_relayout_cost): the rewrite re-lays a value out once per target layout however many
+  // consumers want it, the pairwise objective charges every consumer edge.  Splitting the price over the value's consumers is
+  // exact when they all ask for the same layout (the common case: an all-reduced activation read by a LayerNorm and a residual
+  // add) and an under-estimate when they ask for different ones.
+  const double share = (p.opt.share_relayout_cost && e.operand >= 0 && e.fanout > 1) ? 1.0 / e.fanout : 1.0;
+  if (cost > 0 && cost < kInfCost) cost *= share;
   if (cost > 0 && cost < kInfCost) {
     // a collective is not free below its byte count: launch + cross-GPU synchronisation (~8 us on NVSwitch = ~6 MB of wire
     // time).  Without this term dozens of tiny LayerNorm-statistics / loss all-reduces look free next to one large one.
@@ -180,7 +194,7 @@ double EdgeCost(const Problem& p, const Edge& e, const Candidate& cp, const Cand
     const bool bucketed = po == "parameter" || po == "state" || po.rfind("apply_", 0) == 0 || co.rfind("apply_", 0) == 0;
     if (launches && !bucketed) {
       const double lat = p.opt.collective_latency_bytes >= 0 ? p.opt.collective_latency_bytes : p.opt.hw.coll_latency * p.opt.hw.link_bw;
-      cost += lat;
+      cost += lat * share;
     }
   }
   return cost;

@@ -850,3 +850,19 @@ def test_sequence_parallel_form_of_tensor_parallelism_is_opt_in():
     users = [n for n in out_sp.nodes if any(v.node == lin.id for v in n.inputs)]
     assert [u.op for u in users] == ["reduce_scatter"] and list(users[0].outputs[0].shape) == [2, cfg.n_ctx, cfg.n_embd]
     assert names["model/h0/attn/c_proj/bias"].op == "add" and names["model/h0/attn/c_proj/res"].op == "add"
+
+
+def test_shared_relayout_pricing_is_an_experiment_that_leaves_the_default_plans_alone():
+    """The PBQP objective is pairwise: a re-layout read by k consumers is charged k times although the rewrite performs it once
+    (the reported statistics count it once).  `share_relayout_cost` splits the price over the consumers; it must not be on by
+    default (the measured plans were found without it) and, when on, must yield a consistent plan that does not move more bytes."""
+    from tepdist_b200.parallel import plan_spmd
+    g = build_gpt2_graph(CONFIGS["tiny"], batch=4)
+    for strategy in ("auto", "tp"):
+        _, base = plan_spmd(g, 2, strategy)
+        _, off = plan_spmd(g, 2, strategy, {"share_relayout_cost": False})
+        _, on = plan_spmd(g, 2, strategy, {"share_relayout_cost": True})
+        assert base["collectives"] == off["collectives"] and base["comm_bytes"] == off["comm_bytes"]
+        assert on["infeasible_subgraphs"] == 0
+        assert on["comm_bytes"] <= 1.05 * base["comm_bytes"], (strategy, on["comm_bytes"], base["comm_bytes"])
+    assert _C.SpmdOptions().share_relayout_cost is False
